@@ -1,0 +1,439 @@
+// dsr_conv.cu -- the two tensor-core kernels of the DIP step, hand-written for sm_100a:
+//
+//   conv_gemm_kernel : implicit-GEMM convolution (fprop of 3x3 s1 / 3x3 s2 / 1x1 convs, and their
+//                      data-gradients), D[128 pixels][N] = sum over K-blocks A[128][kc] * B[N][kc]^T.
+//                      TMA (5-D tiled maps over the padded NHWC tensor) -> 128B/32B-swizzled smem
+//                      -> tcgen05.mma kind::f16 (fp32 accumulators in TMEM, double buffered)
+//                      -> tcgen05.ld epilogue (16-bit store + fused BatchNorm sum / sum-of-squares).
+//   wgrad_kernel     : weight gradient, D[128 co][ci] += dR^T X over pixel blocks, MN-major operands,
+//                      split over pixel ranges and tap groups, fp32 vector reductions into HBM.
+//
+// Reference semantics being replaced: torch.nn.Conv2d forward/backward as instantiated by
+// models/DIP/utils.py:83-105 (conv) and used at models/DIP/skip.py:54,60,64,79,85.
+#include "dsr_conv.cuh"
+#include "dsr_ptx.cuh"
+#include "dsr_host.h"
+
+namespace dsr {
+
+// =============================================================================================
+// conv_gemm_kernel
+// =============================================================================================
+__global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment: required by the 128B swizzle atoms (8 rows x 128 B).
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kConvStages * kConvStageBytes);
+  uint64_t* full_bar = bars;                       // [kConvStages]  TMA -> MMA
+  uint64_t* empty_bar = bars + kConvStages;        // [kConvStages]  MMA -> TMA
+  uint64_t* tfull_bar = bars + 2 * kConvStages;    // [2]            MMA -> epilogue
+  uint64_t* tempty_bar = bars + 2 * kConvStages + 2;  // [2]         epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kConvStages + 4);
+  float* stat_smem = reinterpret_cast<float*>(bars + 2 * kConvStages + 6);  // unused bytes after barriers
+  (void)stat_smem;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int ntiles = p.tiles_x * p.tiles_y;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.a64);
+    tma_prefetch_desc(&p.a16);
+    tma_prefetch_desc(&p.b64);
+    tma_prefetch_desc(&p.b16);
+    for (int s = 0; s < kConvStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 4);   // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int x0 = (tile % p.tiles_x) * p.tw;
+        const int y0 = (tile / p.tiles_x) * p.th;
+        for (int k = 0; k < p.nkb; ++k) {
+          const KBlk kb = p.kb[k];
+          mbar_wait(&empty_bar[stage], phase ^ 1, p.err, 1);
+          uint8_t* sa = smem + stage * kConvStageBytes;
+          uint8_t* sb = sa + kConvStageA;
+          const uint32_t kbytes = kb.wide ? 128u : 32u;
+          mbar_arrive_expect_tx(&full_bar[stage], (128u + static_cast<uint32_t>(p.n_mma)) * kbytes);
+          tma_load_5d(kb.wide ? &p.a64 : &p.a16, &full_bar[stage], sa, kb.a_c, kb.a_px, x0 + kb.a_dx, kb.a_py,
+                      y0 + kb.a_dy);
+          tma_load_2d(kb.wide ? &p.b64 : &p.b16, &full_bar[stage], sb, kb.b_k, kb.b_row);
+          if (++stage == kConvStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int t = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t) {
+        const int as = t & 1;
+        const uint32_t aphase = (t >> 1) & 1;
+        mbar_wait(&tempty_bar[as], aphase ^ 1, p.err, 2);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * 256);
+        for (int k = 0; k < p.nkb; ++k) {
+          const int wide = p.kb[k].wide;
+          mbar_wait(&full_bar[stage], phase, p.err, 3);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * kConvStageBytes);
+          const uint32_t sb = sa + kConvStageA;
+          if (wide) {
+            const uint64_t da = make_smem_desc(sa, 16, 1024, SWZ_128B);
+            const uint64_t db = make_smem_desc(sb, 16, 1024, SWZ_128B);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)   // 4 x (K = 16 elements = 32 B) inside the 128 B swizzle row
+              umma_f16(tmem_d, da + static_cast<uint64_t>(j * 2), db + static_cast<uint64_t>(j * 2), p.idesc,
+                       (k | j) != 0);
+          } else {
+            const uint64_t da = make_smem_desc(sa, 16, 256, SWZ_32B);
+            const uint64_t db = make_smem_desc(sb, 16, 256, SWZ_32B);
+            umma_f16(tmem_d, da, db, p.idesc, k != 0);
+          }
+          umma_commit(&empty_bar[stage]);   // frees the smem stage once these MMAs have read it
+          if (k == p.nkb - 1) umma_commit(&tfull_bar[as]);
+          if (++stage == kConvStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue: TMEM -> registers -> HBM (+ BN statistics) =====================
+    const int quarter = warp & 3;              // TMEM lane quarter this warp may read
+    const int row = quarter * 32 + lane;       // pixel index inside the tile
+    const int nchunks = p.n_mma >> 4;
+    float acc_s[9], acc_q[9];
+#pragma unroll
+    for (int c = 0; c < 9; ++c) { acc_s[c] = 0.f; acc_q[c] = 0.f; }
+    int t = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t) {
+      const int as = t & 1;
+      const uint32_t aphase = (t >> 1) & 1;
+      const int x = (tile % p.tiles_x) * p.tw + (row % p.tw);
+      const int y = (tile / p.tiles_x) * p.th + (row / p.tw);
+      const bool valid = (x < p.out_w) && (y < p.out_h);
+      mbar_wait(&tfull_bar[as], aphase, p.err, 4);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(as * 256);
+      const long long obase = static_cast<long long>(y) * p.out_sy + static_cast<long long>(x) * p.out_sx;
+#pragma unroll
+      for (int c = 0; c < 9; ++c) {
+        if (c < nchunks) {
+          uint32_t v[16];
+          tmem_ld16(taddr + static_cast<uint32_t>(c * 16), v);
+          tmem_ld_wait();
+          uint32_t packed[8];
+          float f[16];
+          if (p.out_bf16) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+              packed[i] = *reinterpret_cast<uint32_t*>(&h);
+              f[2 * i] = __low2float(h);
+              f[2 * i + 1] = __high2float(h);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              __half2 h = __floats2half2_rn(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+              packed[i] = *reinterpret_cast<uint32_t*>(&h);
+              f[2 * i] = __low2float(h);
+              f[2 * i + 1] = __high2float(h);
+            }
+          }
+          if (valid && c * 16 < p.n_store) {
+            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + obase + c * 16);
+            dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+            if (c * 16 + 8 < p.n_store) dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+          }
+          if (p.stats != nullptr) {
+            // Column sums over the warp's 32 pixels by recursive halving: after the 5 steps lane L
+            // holds the sum of column ((L>>4)&1)*8 + ((L>>3)&1)*4 + ((L>>2)&1)*2 + ((L>>1)&1).
+            const float m = valid ? 1.f : 0.f;
+            float s[16], q[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { s[i] = f[i] * m; q[i] = f[i] * f[i] * m; }
+#pragma unroll
+            for (int w = 8; w >= 1; w >>= 1) {
+              const int d = w * 2;                 // lane distance 16, 8, 4, 2
+              const bool hi = (lane & d) != 0;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                if (i < w) {
+                  const float send_s = hi ? s[i] : s[i + w];
+                  const float send_q = hi ? q[i] : q[i + w];
+                  const float recv_s = __shfl_xor_sync(0xffffffffu, send_s, d);
+                  const float recv_q = __shfl_xor_sync(0xffffffffu, send_q, d);
+                  s[i] = (hi ? s[i + w] : s[i]) + recv_s;
+                  q[i] = (hi ? q[i + w] : q[i]) + recv_q;
+                }
+              }
+            }
+            s[0] += __shfl_xor_sync(0xffffffffu, s[0], 1);
+            q[0] += __shfl_xor_sync(0xffffffffu, q[0], 1);
+            acc_s[c] += s[0];
+            acc_q[c] += q[0];
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+    }
+    if (p.stats != nullptr && (lane & 1) == 0) {
+      const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+#pragma unroll
+      for (int c = 0; c < 9; ++c) {
+        if (c < nchunks) {
+          atomicAdd(&p.stats[c * 16 + col], acc_s[c]);
+          atomicAdd(&p.stats[p.n_mma + c * 16 + col], acc_q[c]);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// =============================================================================================
+// wgrad_kernel
+// =============================================================================================
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_constant__ WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWgStages * kWgStageBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kWgStages;
+  uint64_t* tfull_bar = bars + 2 * kWgStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kWgStages + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int group = blockIdx.x / p.nsplit;
+  const int split = blockIdx.x % p.nsplit;
+  const int npb = p.pb_x * p.pb_y;
+  const int pb_begin = static_cast<int>((static_cast<long long>(npb) * split) / p.nsplit);
+  const int pb_end = static_cast<int>((static_cast<long long>(npb) * (split + 1)) / p.nsplit);
+  const int nkb = pb_end - pb_begin;
+  const int ncols = p.n64 * 64 + p.n16 * 16;       // ci handled (<= 144)
+  const uint32_t tapB = static_cast<uint32_t>(p.n64 * kWgPix * 128 + p.n16 * kWgPix * 32);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.a64);
+    tma_prefetch_desc(&p.b64);
+    tma_prefetch_desc(&p.b16);
+    for (int s = 0; s < kWgStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tfull_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int pb = pb_begin; pb < pb_end; ++pb) {
+        const int x0 = (pb % p.pb_x) * p.pw;
+        const int y0 = (pb / p.pb_x) * p.ph;
+        mbar_wait(&empty_bar[stage], phase ^ 1, p.err, 11);
+        uint8_t* sa = smem + stage * kWgStageBytes;
+        mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(kWgStageA) + static_cast<uint32_t>(p.ntaps) * tapB);
+        // dR lives on the padded output grid: interior pixel (y, x) is at (y + 1, x + 1).
+        tma_load_5d(&p.a64, &full_bar[stage], sa, 0, 0, x0 + 1, 0, y0 + 1);
+        tma_load_5d(&p.a64, &full_bar[stage], sa + kWgPix * 128, 64, 0, x0 + 1, 0, y0 + 1);
+        for (int t = 0; t < p.ntaps; ++t) {
+          const WgTap tp = p.taps[group][t];
+          uint8_t* sb = sa + kWgStageA + t * tapB;
+          for (int c = 0; c < p.n64; ++c)
+            tma_load_5d(&p.b64, &full_bar[stage], sb + c * (kWgPix * 128), c * 64, tp.px, x0 + tp.dx, tp.py, y0 + tp.dy);
+          for (int c = 0; c < p.n16; ++c)
+            tma_load_5d(&p.b16, &full_bar[stage], sb + p.n64 * (kWgPix * 128) + c * (kWgPix * 32), p.c16_base + c * 16,
+                        tp.px, x0 + tp.dx, tp.py, y0 + tp.dy);
+        }
+        if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int k = 0; k < nkb; ++k) {
+        mbar_wait(&full_bar[stage], phase, p.err, 12);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * kWgStageBytes);
+        for (int t = 0; t < p.ntaps; ++t) {
+          const uint32_t sb = sa + kWgStageA + t * tapB;
+          const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(t * kWgTapCols);
+#pragma unroll
+          for (int ks = 0; ks < kWgPix / 16; ++ks) {
+            // A: [pixels][co] MN-major, 2 column groups of 64 co (LBO), 8-pixel row groups (SBO).
+            const uint64_t da = make_smem_desc(sa + ks * 2048, kWgPix * 128, 1024, SWZ_128B);
+            if (p.n64) {
+              const uint64_t db = make_smem_desc(sb + ks * 2048, kWgPix * 128, 1024, SWZ_128B);
+              umma_f16(tmem_d, da, db, p.idesc64, (k | ks) != 0);
+            }
+            if (p.n16) {
+              const uint64_t db = make_smem_desc(sb + p.n64 * (kWgPix * 128) + ks * 512, kWgPix * 32, 256, SWZ_32B);
+              umma_f16(tmem_d + static_cast<uint32_t>(p.n64 * 64), da, db, p.idesc16, (k | ks) != 0);
+            }
+          }
+        }
+        umma_commit(&empty_bar[stage]);
+        if (k == nkb - 1) umma_commit(tfull_bar);
+        if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (nkb > 0) {
+    const int quarter = warp & 3;
+    const int co = quarter * 32 + lane;
+    mbar_wait(tfull_bar, 0, p.err, 13);
+    tc_fence_after();
+    for (int t = 0; t < p.ntaps; ++t) {
+      const int w_tap = p.taps[group][t].w_tap;
+      float* drow = p.dw + (static_cast<long long>(w_tap) * 128 + co) * p.ldw;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(t * kWgTapCols);
+      for (int c = 0; c * 16 < ncols; ++c) {
+        uint32_t v[16];
+        tmem_ld16(taddr + static_cast<uint32_t>(c * 16), v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          red_add_v4(drow + c * 16 + i * 4, __uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                     __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// =============================================================================================
+// Host side: tensor-map construction and launches
+// =============================================================================================
+static PFN_encodeTiled g_encode = nullptr;
+
+int ensure_driver_api() {
+  if (g_encode) return 0;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || fn == nullptr) return -100;
+  g_encode = reinterpret_cast<PFN_encodeTiled>(fn);
+  return 0;
+}
+
+// 5-D map over a padded NHWC tensor.  `base` points at padded pixel (0,0), channel 0.
+//   C: channels per pixel (pitch), Wp/Hp: padded extents, step: 1 or 2 (parity split),
+//   box_c: 64 (128B swizzle) or 16 (32B swizzle); box_w x box_h pixels.
+int make_act_map(CUtensorMap* m, const void* base, int elem_is_16bit, int C, int Wp, int Hp, int step, int box_c,
+                 int box_w, int box_h) {
+  (void)elem_is_16bit;
+  if (ensure_driver_api()) return -100;
+  const cuuint64_t es = 2;
+  cuuint64_t dims[5], strides[4];
+  cuuint32_t box[5], estr[5] = {1, 1, 1, 1, 1};
+  dims[0] = static_cast<cuuint64_t>(C);
+  dims[1] = static_cast<cuuint64_t>(step);
+  dims[2] = static_cast<cuuint64_t>((Wp + step - 1) / step);
+  dims[3] = static_cast<cuuint64_t>(step);
+  dims[4] = static_cast<cuuint64_t>((Hp + step - 1) / step);
+  strides[0] = static_cast<cuuint64_t>(C) * es;                 // px
+  strides[1] = static_cast<cuuint64_t>(C) * es * step;          // x
+  strides[2] = static_cast<cuuint64_t>(C) * es * Wp;            // py
+  strides[3] = static_cast<cuuint64_t>(C) * es * Wp * step;     // y
+  box[0] = static_cast<cuuint32_t>(box_c);
+  box[1] = 1;
+  box[2] = static_cast<cuuint32_t>(box_w);
+  box[3] = 1;
+  box[4] = static_cast<cuuint32_t>(box_h);
+  const CUtensorMapSwizzle sw = (box_c == 64) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B;
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 5, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -(200 + static_cast<int>(r));
+}
+
+// 2-D map over a packed weight matrix [rows][K] (K contiguous).
+int make_wgt_map(CUtensorMap* m, const void* base, int K, int rows, int box_k, int box_rows) {
+  if (ensure_driver_api()) return -100;
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(K) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_k), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapSwizzle sw = (box_k == 64) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B;
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -(300 + static_cast<int>(r));
+}
+
+static bool g_attr_done = false;
+static int set_attrs() {
+  if (g_attr_done) return 0;
+  cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmemBytes);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  e = cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  g_attr_done = true;
+  return 0;
+}
+
+int launch_conv_gemm(const ConvGemmParams& p, int num_sms, cudaStream_t stream) {
+  int rc = set_attrs();
+  if (rc) return rc;
+  const int ntiles = p.tiles_x * p.tiles_y;
+  if (ntiles <= 0) return 0;
+  const int grid = ntiles < num_sms ? ntiles : num_sms;
+  conv_gemm_kernel<<<grid, kConvThreads, kConvSmemBytes, stream>>>(p);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int launch_wgrad(const WgradParams& p, cudaStream_t stream) {
+  int rc = set_attrs();
+  if (rc) return rc;
+  const int grid = p.ngroups * p.nsplit;
+  if (grid <= 0) return 0;
+  wgrad_kernel<<<grid, kWgThreads, kWgSmemBytes, stream>>>(p);
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // namespace dsr

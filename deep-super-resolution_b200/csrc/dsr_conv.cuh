@@ -1,0 +1,86 @@
+// dsr_conv.cuh -- parameter blocks of the two tcgen05 kernels (implicit-GEMM conv and wgrad).
+//
+// Data layout (DESIGN.md "HBM layout"): every activation / gradient tensor is NHWC with one image,
+// 16-bit elements, stored in a PADDED pixel grid [H+2][W+2][C] (1-pixel halo: reflected values for
+// forward activations, zeros for gradients).  TMA sees it as the 5-D tensor
+//     (c, px, x, py, y)   sizes (C, PX, Wp/PX, PY, Hp/PY),  PX = PY = 1 (unit stride) or 2 (stride-2 gather)
+// so that one box (kc, 1, TW, 1, TH) is a [TW*TH pixels][kc channels] K-major operand tile.
+#pragma once
+#include <cuda.h>
+#include <stdint.h>
+
+namespace dsr {
+
+constexpr int kConvThreads = 192;       // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue
+constexpr int kConvStages = 5;
+constexpr int kConvStageA = 128 * 128;  // 128 pixels x 64 ch x 2 B
+constexpr int kConvStageB = 144 * 128;  // up to 144 rows x 64 ch x 2 B
+constexpr int kConvStageBytes = kConvStageA + kConvStageB;   // 34816 = 34 * 1024
+constexpr int kConvSmemBytes = kConvStages * kConvStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int kMaxKBlocks = 28;
+
+// One K-block of the implicit GEMM: which channels of which (shifted) input pixels, which weight rows.
+struct KBlk {
+  int16_t a_c;       // first channel
+  int8_t a_px, a_dx; // coordinate in the px dim, offset added to the tile's x origin
+  int8_t a_py, a_dy;
+  int8_t wide;       // 1: 64 channels (128B swizzle), 0: 16 channels (32B swizzle)
+  int8_t pad_;
+  int16_t b_k;       // column (K coordinate) in the packed weight matrix
+  int16_t b_row;     // first row in the packed weight matrix
+};
+
+struct alignas(64) ConvGemmParams {
+  CUtensorMap a64, a16;   // input tensor, boxes of 64 / 16 channels
+  CUtensorMap b64, b16;   // packed weights [rows][K], boxes (64|16, n_mma)
+  KBlk kb[kMaxKBlocks];
+  int nkb;
+  int tiles_x, tiles_y;   // tile grid over the output pixel grid
+  int tw, th;             // tile = tw x th pixels, tw*th == 128
+  int out_h, out_w;       // valid extent of the output pixel grid
+  long long out_sy, out_sx;  // output strides in elements
+  void* out;              // fp16 (raw conv output) or bf16 (gradient)
+  int n_mma;              // UMMA N (multiple of 16, <= 144)
+  int n_store;            // channels stored per pixel (multiple of 8, <= n_mma)
+  int out_bf16;           // 0: convert accumulators to fp16, 1: to bf16
+  float* stats;           // optional [2][n_mma]: per-channel sum and sum of squares of the STORED values
+  uint32_t idesc;
+  int* err;
+};
+
+// ---------------------------------------------------------------------------------------------
+// wgrad:  dW[tap][co][ci] = sum over pixels  dR[p][co] * X[p (+) tap][ci]
+// GEMM M = co (128), N = ci, K = pixels; both operands are MN-major tiles [pixels][channels].
+// ---------------------------------------------------------------------------------------------
+constexpr int kWgThreads = 192;
+constexpr int kWgStages = 3;
+constexpr int kWgPix = 64;                      // pixels per K-block
+constexpr int kWgStageA = 2 * kWgPix * 128;     // 2 chunks of 64 co          = 16 KB
+constexpr int kWgTapB = 2 * kWgPix * 128 + kWgPix * 32;  // 2x64 ci + 1x16 ci (or 2x16 ci alone) = 18 KB
+constexpr int kWgStageBytes = kWgStageA + 3 * kWgTapB;   // 70 KB  (multiple of 1024)
+constexpr int kWgSmemBytes = kWgStages * kWgStageBytes + 1024 + 256;
+constexpr int kWgTapCols = 160;                 // TMEM column spacing between taps
+
+struct WgTap {
+  int8_t px, dx, py, dy;   // X coordinate: (c, px, x0 + dx, py, y0 + dy)
+  int16_t w_tap;           // tap index in the packed gradient [tap][128][ldw]
+  int16_t pad_;
+};
+
+struct alignas(64) WgradParams {
+  CUtensorMap a64;           // dR (bf16, padded grid, unit stride): box (64, 1, pw, 1, ph)
+  CUtensorMap b64, b16;      // X (fp16): boxes (64|16, 1, pw, 1, ph)
+  WgTap taps[3][3];          // [group][tap in group]
+  int ngroups, ntaps;        // groups (CTA-level split of taps), taps per group (<= 3)
+  int nsplit;                // pixel-range splits; grid = ngroups * nsplit
+  int pb_x, pb_y;            // pixel-block grid: blocks of pw x ph over the conv OUTPUT pixel grid
+  int pw, ph;                // pw * ph == 64
+  int n64, n16;              // X channel chunks: n64 in {0, 2} of 64 ch, n16 in {0, 1, 2} of 16 ch
+  int c16_base;              // first channel of the 16-wide chunks
+  int ldw;                   // row pitch (floats) of the packed gradient = padded ci count
+  float* dw;                 // [ntaps_total][128][ldw] fp32, accumulated with red.add
+  uint32_t idesc64, idesc16;
+  int* err;
+};
+
+}  // namespace dsr

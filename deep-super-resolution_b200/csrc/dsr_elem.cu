@@ -1,0 +1,1074 @@
+// dsr_elem.cu -- bandwidth kernels of the DIP step: layout packing, BatchNorm apply (+LeakyReLU,
+// + reflected halo), skip-branch 1x1 conv, bilinear upsample + concat + BN(132), final 1x1 conv +
+// sigmoid, and all of their backward passes, weight packing, running statistics, Adam, noise.
+// All are coalesced 16-byte-vector kernels (8 fp16/bf16 channels per thread, 16 lanes per pixel);
+// per-channel reductions are register -> shared-memory -> one global atomic per channel per block.
+//
+// Reference semantics (paths relative to the upstream repo):
+//   BatchNorm2d train mode + LeakyReLU(0.2)   models/DIP/utils.py:68,79-80
+//   ReflectionPad2d((k-1)/2)                  models/DIP/utils.py:96-99
+//   Concat (skip first, centre crop) + Upsample(bilinear x2)   models/DIP/utils.py:18-38, skip.py:47,77
+//   final conv + Sigmoid                      models/DIP/skip.py:92-94
+//   Adam                                      utils/DIP.py:34 (torch.optim.Adam defaults)
+#include "dsr_elem.cuh"
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+namespace dsr {
+
+namespace {
+
+constexpr float kBnEps = 1e-5f;
+constexpr float kSlope = 0.2f;
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ void load8h(const __half* p, float (&f)[8]) {
+  uint4 u = *reinterpret_cast<const uint4*>(p);
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __half22float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ void store8h(__half* p, const float (&f)[8]) {
+  uint4 u;
+  __half2* h = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+__device__ __forceinline__ void load8b(const __nv_bfloat16* p, float (&f)[8]) {
+  uint4 u = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ void store8b(__nv_bfloat16* p, const float (&f)[8]) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
+// Padded coordinates an interior index i in [0, n) occupies under ReflectionPad(1): itself and,
+// for i == 1 / i == n-2, the mirrored halo cell.  The same list is the set of padded cells whose
+// data-gradient folds back onto i.
+__device__ __forceinline__ int halo_coords(int i, int n, int (&o)[3]) {
+  int c = 0;
+  o[c++] = i + 1;
+  if (i == 1) o[c++] = 0;
+  if (i == n - 2) o[c++] = n + 1;
+  return c;
+}
+
+__device__ __forceinline__ void bn_coeffs(const BnRef& bn, int c, float& mean, float& rstd, float& gamma, float& beta) {
+  const float s = bn.stats[c];
+  const float q = bn.stats[bn.cstride + c];
+  mean = s * bn.inv_n;
+  const float var = fmaxf(q * bn.inv_n - mean * mean, 0.f);
+  rstd = rsqrtf(var + kBnEps);
+  gamma = bn.gamma[c];
+  beta = bn.beta[c];
+}
+
+__device__ __forceinline__ float lrelu(float y) { return y > 0.f ? y : kSlope * y; }
+
+// bilinear x2, align_corners = False: source index and weights for output index o
+__device__ __forceinline__ void up_src(int o, int n, int& i0, int& i1, float& l0, float& l1) {
+  float src = fmaxf(0.f, 0.5f * static_cast<float>(o) - 0.25f);
+  i0 = static_cast<int>(src);
+  if (i0 > n - 1) i0 = n - 1;
+  i1 = min(i0 + 1, n - 1);
+  l1 = src - static_cast<float>(i0);
+  l0 = 1.f - l1;
+}
+
+inline int grid_for(long long items, int threads, int cap_blocks) {
+  long long b = (items + threads - 1) / threads;
+  if (b > cap_blocks) b = cap_blocks;
+  if (b < 1) b = 1;
+  return static_cast<int>(b);
+}
+
+}  // namespace
+
+#define DSR_LAUNCH_CHECK() return static_cast<int>(cudaGetLastError())
+
+// =============================================================================================
+// input pack: fp32 NCHW -> fp16 padded NHWC with reflected halo
+// =============================================================================================
+__global__ void input_pack_kernel(const float* __restrict__ z, __half* __restrict__ xpad, int C, int H, int W) {
+  // block: 64 consecutive x of one row y; smem tile [C][65]
+  extern __shared__ float tile[];
+  const int tiles_x = (W + 63) / 64;
+  const int y = blockIdx.x / tiles_x;
+  const int x0 = (blockIdx.x % tiles_x) * 64;
+  for (int i = threadIdx.x; i < C * 64; i += blockDim.x) {
+    const int c = i >> 6, dx = i & 63;
+    const int x = x0 + dx;
+    tile[c * 65 + dx] = (x < W) ? z[(static_cast<long long>(c) * H + y) * W + x] : 0.f;
+  }
+  __syncthreads();
+  const int groups = C >> 3;
+  const int Wp = W + 2;
+  int ys[3];
+  const int ny = halo_coords(y, H, ys);
+  for (int i = threadIdx.x; i < 64 * groups; i += blockDim.x) {
+    const int dx = i / groups, g = i % groups;
+    const int x = x0 + dx;
+    if (x >= W) continue;
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = tile[(g * 8 + j) * 65 + dx];
+    int xs[3];
+    const int nx = halo_coords(x, W, xs);
+    for (int a = 0; a < ny; ++a)
+      for (int b = 0; b < nx; ++b)
+        store8h(xpad + (static_cast<long long>(ys[a]) * Wp + xs[b]) * C + g * 8, f);
+  }
+}
+
+int launch_input_pack(const float* z, void* xpad, int C, int H, int W, cudaStream_t s) {
+  const int tiles_x = (W + 63) / 64;
+  input_pack_kernel<<<H * tiles_x, kThreads, C * 65 * sizeof(float), s>>>(z, static_cast<__half*>(xpad), C, H, W);
+  DSR_LAUNCH_CHECK();
+}
+
+// =============================================================================================
+// BN apply + LeakyReLU (+ reflected halo)
+// =============================================================================================
+__global__ void bn_act_kernel(const __half* __restrict__ raw, BnRef bn, __half* __restrict__ act, int H, int W,
+                              int halo) {
+  const int g = threadIdx.x & 15;
+  float scale[8], shift[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float mean, rstd, ga, be;
+    bn_coeffs(bn, g * 8 + j, mean, rstd, ga, be);
+    scale[j] = ga * rstd;
+    shift[j] = be - mean * scale[j];
+  }
+  const long long npix = static_cast<long long>(H) * W;
+  const int Wp = W + 2;
+  for (long long pix = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 4; pix < npix;
+       pix += (static_cast<long long>(gridDim.x) * blockDim.x) >> 4) {
+    const int y = static_cast<int>(pix / W), x = static_cast<int>(pix % W);
+    float f[8];
+    load8h(raw + pix * 128 + g * 8, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = lrelu(f[j] * scale[j] + shift[j]);
+    if (halo) {
+      int ys[3], xs[3];
+      const int ny = halo_coords(y, H, ys), nx = halo_coords(x, W, xs);
+      for (int a = 0; a < ny; ++a)
+        for (int b = 0; b < nx; ++b) store8h(act + (static_cast<long long>(ys[a]) * Wp + xs[b]) * 128 + g * 8, f);
+    } else {
+      store8h(act + (static_cast<long long>(y + 1) * Wp + (x + 1)) * 128 + g * 8, f);
+    }
+  }
+}
+
+int launch_bn_act(const void* raw, BnRef bn, void* act_pad, int H, int W, int halo, cudaStream_t s) {
+  const long long items = static_cast<long long>(H) * W * 16;
+  bn_act_kernel<<<grid_for(items, kThreads, 148 * 16), kThreads, 0, s>>>(static_cast<const __half*>(raw), bn,
+                                                                        static_cast<__half*>(act_pad), H, W, halo);
+  DSR_LAUNCH_CHECK();
+}
+
+// =============================================================================================
+// skip branch 1x1 conv (Cin -> 4) + statistics
+// =============================================================================================
+template <int CIN>
+__global__ void skip_conv_kernel(const __half* __restrict__ xpad, const float* __restrict__ w, float* __restrict__ sraw,
+                                 float* __restrict__ stats, int H, int W) {
+  constexpr int G = CIN / 8;   // lanes per pixel
+  const int g = threadIdx.x % G;
+  float wr[4][8];
+#pragma unroll
+  for (int o = 0; o < 4; ++o)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) wr[o][j] = w[o * CIN + g * 8 + j];
+  float ss[4] = {0, 0, 0, 0}, sq[4] = {0, 0, 0, 0};
+  const long long npix = static_cast<long long>(H) * W;
+  const int Wp = W + 2;
+  // all lanes of a pixel group stay in the loop together (npix padded to whole groups per warp)
+  const long long stride = (static_cast<long long>(gridDim.x) * blockDim.x) / G;
+  for (long long pix = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) / G;
+       pix < ((npix + 31) / 32) * 32; pix += stride) {
+    float acc[4] = {0, 0, 0, 0};
+    const bool ok = pix < npix;
+    if (ok) {
+      const int y = static_cast<int>(pix / W), x = static_cast<int>(pix % W);
+      float f[8];
+      load8h(xpad + (static_cast<long long>(y + 1) * Wp + (x + 1)) * CIN + g * 8, f);
+#pragma unroll
+      for (int o = 0; o < 4; ++o)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[o] = fmaf(f[j], wr[o][j], acc[o]);
+    }
+#pragma unroll
+    for (int d = G / 2; d >= 1; d >>= 1)
+#pragma unroll
+      for (int o = 0; o < 4; ++o) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], d);
+    if (ok && g == 0) {
+      *reinterpret_cast<float4*>(sraw + pix * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+#pragma unroll
+      for (int o = 0; o < 4; ++o) { ss[o] += acc[o]; sq[o] += acc[o] * acc[o]; }
+    }
+  }
+  __shared__ float red[8];
+  if (threadIdx.x < 8) red[threadIdx.x] = 0.f;
+  __syncthreads();
+  if (g == 0) {
+#pragma unroll
+    for (int o = 0; o < 4; ++o) { atomicAdd(&red[o], ss[o]); atomicAdd(&red[4 + o], sq[o]); }
+  }
+  __syncthreads();
+  if (threadIdx.x < 8) atomicAdd(&stats[threadIdx.x], red[threadIdx.x]);
+}
+
+int launch_skip_conv(const void* xpad, int Cin, const float* w, float* sraw, float* stats, int H, int W,
+                     cudaStream_t s) {
+  const long long items = static_cast<long long>(H) * W * (Cin / 8);
+  const int grid = grid_for(items, kThreads, 148 * 8);
+  if (Cin == 32)
+    skip_conv_kernel<32><<<grid, kThreads, 0, s>>>(static_cast<const __half*>(xpad), w, sraw, stats, H, W);
+  else if (Cin == 128)
+    skip_conv_kernel<128><<<grid, kThreads, 0, s>>>(static_cast<const __half*>(xpad), w, sraw, stats, H, W);
+  else
+    return -2;
+  DSR_LAUNCH_CHECK();
+}
+
+// =============================================================================================
+// upsample + concat + BN(132)
+// =============================================================================================
+// value of the 8 upsampled channels [g*8, g*8+8) at concat pixel (y, x)
+__device__ __forceinline__ void upsample8(const UpcatArgs& a, int y, int x, int g, float (&u)[8]) {
+  int y0, y1, x0, x1;
+  float ly0, ly1, lx0, lx1;
+  up_src(y, a.h, y0, y1, ly0, ly1);
+  up_src(x, a.w, x0, x1, lx0, lx1);
+  const __half* d = static_cast<const __half*>(a.deep);
+  float f00[8], f01[8], f10[8], f11[8];
+  load8h(d + y0 * a.deep_sy + static_cast<long long>(x0) * 128 + g * 8, f00);
+  load8h(d + y0 * a.deep_sy + static_cast<long long>(x1) * 128 + g * 8, f01);
+  load8h(d + y1 * a.deep_sy + static_cast<long long>(x0) * 128 + g * 8, f10);
+  load8h(d + y1 * a.deep_sy + static_cast<long long>(x1) * 128 + g * 8, f11);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) u[j] = ly0 * (lx0 * f00[j] + lx1 * f01[j]) + ly1 * (lx0 * f10[j] + lx1 * f11[j]);
+}
+
+// skip activation LeakyReLU(BN4(sraw)) at a pixel, plus (optionally) xhat and y of the BN(4)
+__device__ __forceinline__ void skip_act4(const UpcatArgs& a, long long pix, float (&sv)[4], float (&xh)[4],
+                                          float (&yv)[4]) {
+  const float4 r = *reinterpret_cast<const float4*>(a.sraw + pix * 4);
+  const float rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int o = 0; o < 4; ++o) {
+    float mean, rstd, ga, be;
+    bn_coeffs(a.bn_skip, o, mean, rstd, ga, be);
+    xh[o] = (rr[o] - mean) * rstd;
+    yv[o] = ga * xh[o] + be;
+    sv[o] = lrelu(yv[o]);
+  }
+}
+
+__global__ void upcat_stats_kernel(UpcatArgs a) {
+  const int g = threadIdx.x & 15;
+  float s[8], q[8], s4[4] = {0, 0, 0, 0}, q4[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
+  const long long npix = static_cast<long long>(a.H) * a.W;
+  for (long long pix = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 4; pix < npix;
+       pix += (static_cast<long long>(gridDim.x) * blockDim.x) >> 4) {
+    const int y = static_cast<int>(pix / a.W), x = static_cast<int>(pix % a.W);
+    float u[8];
+    upsample8(a, y, x, g, u);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      // statistics of the value that will be normalised (fp32 interpolation result)
+      s[j] += u[j];
+      q[j] += u[j] * u[j];
+    }
+    if (g == 0) {
+      float sv[4], xh[4], yv[4];
+      skip_act4(a, pix, sv, xh, yv);
+#pragma unroll
+      for (int o = 0; o < 4; ++o) { s4[o] += sv[o]; q4[o] += sv[o] * sv[o]; }
+    }
+  }
+  __shared__ float red[2 * 144];
+  for (int i = threadIdx.x; i < 2 * 144; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    atomicAdd(&red[g * 8 + j], s[j]);
+    atomicAdd(&red[144 + g * 8 + j], q[j]);
+  }
+  if (g == 0) {
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      atomicAdd(&red[128 + o], s4[o]);
+      atomicAdd(&red[144 + 128 + o], q4[o]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * 144; i += blockDim.x)
+    if ((i % 144) < 132) atomicAdd(&a.cat_stats[i], red[i]);
+}
+
+// BN(132) coefficients for packed channel c (0..127 upsampled <-> reference 4+c; 128..131 skip <-> c-128)
+__device__ __forceinline__ void cat_coeffs(const UpcatArgs& a, int c, float& mean, float& rstd, float& ga, float& be) {
+  const float inv_n = 1.f / (static_cast<float>(a.H) * static_cast<float>(a.W));
+  const float su = a.cat_stats[c], sq = a.cat_stats[144 + c];
+  mean = su * inv_n;
+  rstd = rsqrtf(fmaxf(sq * inv_n - mean * mean, 0.f) + kBnEps);
+  const int rc = (c < 128) ? c + 4 : c - 128;
+  ga = a.cat_gamma[rc];
+  be = a.cat_beta[rc];
+}
+
+__global__ void upcat_apply_kernel(UpcatArgs a) {
+  const int g = threadIdx.x & 15;
+  float scale[8], shift[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float mean, rstd, ga, be;
+    cat_coeffs(a, g * 8 + j, mean, rstd, ga, be);
+    scale[j] = ga * rstd;
+    shift[j] = be - mean * scale[j];
+  }
+  float sc4[4], sh4[4];
+#pragma unroll
+  for (int o = 0; o < 4; ++o) {
+    float mean, rstd, ga, be;
+    cat_coeffs(a, 128 + o, mean, rstd, ga, be);
+    sc4[o] = ga * rstd;
+    sh4[o] = be - mean * sc4[o];
+  }
+  const long long npix = static_cast<long long>(a.H) * a.W;
+  const int Wp = a.W + 2;
+  __half* out = static_cast<__half*>(a.cat_pad);
+  for (long long pix = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 4; pix < npix;
+       pix += (static_cast<long long>(gridDim.x) * blockDim.x) >> 4) {
+    const int y = static_cast<int>(pix / a.W), x = static_cast<int>(pix % a.W);
+    float u[8];
+    upsample8(a, y, x, g, u);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) u[j] = u[j] * scale[j] + shift[j];
+    float t0[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t1[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (g == 0) {
+      float sv[4], xh[4], yv[4];
+      skip_act4(a, pix, sv, xh, yv);
+#pragma unroll
+      for (int o = 0; o < 4; ++o) t0[o] = sv[o] * sc4[o] + sh4[o];
+    }
+    int ys[3], xs[3];
+    const int ny = halo_coords(y, a.H, ys), nx = halo_coords(x, a.W, xs);
+    for (int i = 0; i < ny; ++i)
+      for (int k = 0; k < nx; ++k) {
+        __half* dst = out + (static_cast<long long>(ys[i]) * Wp + xs[k]) * 144;
+        store8h(dst + g * 8, u);
+        if (g == 0) {
+          store8h(dst + 128, t0);
+          store8h(dst + 136, t1);
+        }
+      }
+  }
+}
+
+int launch_upcat_stats(const UpcatArgs& a, cudaStream_t s) {
+  const long long items = static_cast<long long>(a.H) * a.W * 16;
+  upcat_stats_kernel<<<grid_for(items, kThreads, 148 * 4), kThreads, 0, s>>>(a);
+  DSR_LAUNCH_CHECK();
+}
+int launch_upcat_apply(const UpcatArgs& a, cudaStream_t s) {
+  const long long items = static_cast<long long>(a.H) * a.W * 16;
+  upcat_apply_kernel<<<grid_for(items, kThreads, 148 * 16), kThreads, 0, s>>>(a);
+  DSR_LAUNCH_CHECK();
+}
+
+// =============================================================================================
+// final 1x1 conv (128 -> 3) + bias + sigmoid -> fp32 NCHW
+// =============================================================================================
+__global__ void final_conv_kernel(const __half* __restrict__ act, const float* __restrict__ w,
+                                  const float* __restrict__ b, float* __restrict__ out, int H, int W) {
+  // block: 16 pixels per pass x 16 lanes; results staged so that stores are contiguous per channel
+  __shared__ float stage[3][kThreads / 16];
+  const int g = threadIdx.x & 15;
+  float wr[3][8];
+#pragma unroll
+  for (int o = 0; o < 3; ++o)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) wr[o][j] = w[o * 128 + g * 8 + j];
+  const long long npix = static_cast<long long>(H) * W;
+  const int Wp = W + 2;
+  const int ppb = blockDim.x >> 4;   // pixels per block pass
+  for (long long base = static_cast<long long>(blockIdx.x) * ppb; base < npix;
+       base += static_cast<long long>(gridDim.x) * ppb) {
+    const long long pix = base + (threadIdx.x >> 4);
+    float acc[3] = {0, 0, 0};
+    if (pix < npix) {
+      const int y = static_cast<int>(pix / W), x = static_cast<int>(pix % W);
+      float f[8];
+      load8h(act + (static_cast<long long>(y + 1) * Wp + (x + 1)) * 128 + g * 8, f);
+#pragma unroll
+      for (int o = 0; o < 3; ++o)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[o] = fmaf(f[j], wr[o][j], acc[o]);
+    }
+#pragma unroll
+    for (int d = 8; d >= 1; d >>= 1)
+#pragma unroll
+      for (int o = 0; o < 3; ++o) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], d);
+    if (g == 0) {
+#pragma unroll
+      for (int o = 0; o < 3; ++o) stage[o][threadIdx.x >> 4] = acc[o];
+    }
+    __syncthreads();
+    if (threadIdx.x < 3 * ppb) {
+      const int o = threadIdx.x / ppb, i = threadIdx.x % ppb;
+      if (base + i < npix) {
+        const float v = stage[o][i] + b[o];
+        out[static_cast<long long>(o) * npix + base + i] = 1.f / (1.f + __expf(-v));
+      }
+    }
+    __syncthreads();
+  }
+}
+
+int launch_final_conv(const void* act_pad, const float* w, const float* b, float* out, int H, int W, cudaStream_t s) {
+  const long long items = static_cast<long long>(H) * W * 16;
+  final_conv_kernel<<<grid_for(items, kThreads, 148 * 16), kThreads, 0, s>>>(static_cast<const __half*>(act_pad), w, b,
+                                                                            out, H, W);
+  DSR_LAUNCH_CHECK();
+}
+
+// =============================================================================================
+// final conv backward
+// =============================================================================================
+__global__ void final_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ out,
+                                 const __half* __restrict__ act, const float* __restrict__ w,
+                                 __nv_bfloat16* __restrict__ dact, float* __restrict__ dw, float* __restrict__ db, int H,
+                                 int W) {
+  const int g = threadIdx.x & 15;
+  float wr[3][8], aw[3][8], ab[3] = {0, 0, 0};
+#pragma unroll
+  for (int o = 0; o < 3; ++o)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      wr[o][j] = w[o * 128 + g * 8 + j];
+      aw[o][j] = 0.f;
+    }
+  const long long npix = static_cast<long long>(H) * W;
+  const int Wp = W + 2;
+  for (long long pix = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 4; pix < npix;
+       pix += (static_cast<long long>(gridDim.x) * blockDim.x) >> 4) {
+    const int y = static_cast<int>(pix / W), x = static_cast<int>(pix % W);
+    float dp[3];
+#pragma unroll
+    for (int o = 0; o < 3; ++o) {
+      const float ov = out[o * npix + pix];
+      dp[o] = gout[o * npix + pix] * ov * (1.f - ov);
+    }
+    const long long off = (static_cast<long long>(y + 1) * Wp + (x + 1)) * 128 + g * 8;
+    float f[8], da[8];
+    load8h(act + off, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      da[j] = dp[0] * wr[0][j] + dp[1] * wr[1][j] + dp[2] * wr[2][j];
+#pragma unroll
+      for (int o = 0; o < 3; ++o) aw[o][j] = fmaf(dp[o], f[j], aw[o][j]);
+    }
+    store8b(dact + off, da);
+    if (g == 0) {
+#pragma unroll
+      for (int o = 0; o < 3; ++o) ab[o] += dp[o];
+    }
+  }
+  __shared__ float red[3 * 128 + 3];
+  for (int i = threadIdx.x; i < 3 * 128 + 3; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int o = 0; o < 3; ++o)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&red[o * 128 + g * 8 + j], aw[o][j]);
+  if (g == 0) {
+#pragma unroll
+    for (int o = 0; o < 3; ++o) atomicAdd(&red[384 + o], ab[o]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 3 * 128; i += blockDim.x) atomicAdd(&dw[i], red[i]);
+  if (threadIdx.x < 3) atomicAdd(&db[threadIdx.x], red[384 + threadIdx.x]);
+}
+
+int launch_final_bwd(const float* gout, const float* out, const void* act_pad, const float* w, void* dact_pad,
+                     float* dw, float* db, int H, int W, cudaStream_t s) {
+  const long long items = static_cast<long long>(H) * W * 16;
+  final_bwd_kernel<<<grid_for(items, kThreads, 148 * 4), kThreads, 0, s>>>(
+      gout, out, static_cast<const __half*>(act_pad), w, static_cast<__nv_bfloat16*>(dact_pad), dw, db, H, W);
+  DSR_LAUNCH_CHECK();
+}
+
+// =============================================================================================
+// BN + LeakyReLU backward (128 channels)
+// =============================================================================================
+// gradient w.r.t. the activation at interior pixel (y, x), 8 channels of group g
+__device__ __forceinline__ void bn_bwd_gather(const BnBwdArgs& a, int y, int x, int g, const float (&ws)[4][8],
+                                              float (&da)[8]) {
+  const __nv_bfloat16* gp = static_cast<const __nv_bfloat16*>(a.g);
+  const int Wp = a.W + 2;
+  if (a.fold) {
+    int ys[3], xs[3];
+    const int ny = halo_coords(y, a.H, ys), nx = halo_coords(x, a.W, xs);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) da[j] = 0.f;
+    for (int i = 0; i < ny; ++i)
+      for (int k = 0; k < nx; ++k) {
+        float f[8];
+        load8b(gp + (static_cast<long long>(ys[i]) * Wp + xs[k]) * a.gC + g * 8, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) da[j] += f[j];
+      }
+  } else {
+    load8b(gp + (static_cast<long long>(y + 1) * Wp + (x + 1)) * a.gC + g * 8, da);
+  }
+  if (a.ds != nullptr) {
+    const float4 d = *reinterpret_cast<const float4*>(a.ds + (static_cast<long long>(y) * a.W + x) * 4);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) da[j] += d.x * ws[0][j] + d.y * ws[1][j] + d.z * ws[2][j] + d.w * ws[3][j];
+  }
+}
+
+template <bool APPLY>
+__global__ void bn_bwd_kernel(BnBwdArgs a) {
+  const int g = threadIdx.x & 15;
+  float mean[8], rstd[8], ga[8], be[8], ws[4][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) bn_coeffs(a.bn, g * 8 + j, mean[j], rstd[j], ga[j], be[j]);
+#pragma unroll
+  for (int o = 0; o < 4; ++o)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ws[o][j] = (a.ds != nullptr) ? a.wskip[o * 128 + g * 8 + j] : 0.f;
+  float c1[8], c2[8], s1[8], s2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if (APPLY) {
+      c1[j] = a.bstats[g * 8 + j] * a.bn.inv_n;          // mean dy
+      c2[j] = a.bstats[128 + g * 8 + j] * a.bn.inv_n;    // mean dy*xhat
+    }
+    s1[j] = 0.f;
+    s2[j] = 0.f;
+  }
+  const long long npix = static_cast<long long>(a.H) * a.W;
+  const int Wp = a.W + 2;
+  const __half* raw = static_cast<const __half*>(a.raw);
+  __nv_bfloat16* dr = static_cast<__nv_bfloat16*>(a.dr_pad);
+  for (long long pix = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 4; pix < npix;
+       pix += (static_cast<long long>(gridDim.x) * blockDim.x) >> 4) {
+    const int y = static_cast<int>(pix / a.W), x = static_cast<int>(pix % a.W);
+    float da[8], r[8];
+    bn_bwd_gather(a, y, x, g, ws, da);
+    load8h(raw + pix * 128 + g * 8, r);
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float xh = (r[j] - mean[j]) * rstd[j];
+      const float yv = ga[j] * xh + be[j];
+      const float dy = da[j] * (yv > 0.f ? 1.f : kSlope);
+      if (APPLY) {
+        o[j] = ga[j] * rstd[j] * (dy - c1[j] - xh * c2[j]);
+      } else {
+        s1[j] += dy;
+        s2[j] += dy * xh;
+      }
+    }
+    if (APPLY) store8b(dr + (static_cast<long long>(y + 1) * Wp + (x + 1)) * 128 + g * 8, o);
+  }
+  if (!APPLY) {
+    __shared__ float red[256];
+    red[threadIdx.x] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&red[g * 8 + j], s1[j]);
+      atomicAdd(&red[128 + g * 8 + j], s2[j]);
+    }
+    __syncthreads();
+    atomicAdd(&a.bstats[threadIdx.x], red[threadIdx.x]);
+  } else if (blockIdx.x == 0 && threadIdx.x < 128) {
+    a.dbeta[threadIdx.x] = a.bstats[threadIdx.x];
+    a.dgamma[threadIdx.x] = a.bstats[128 + threadIdx.x];
+  }
+}
+
+int launch_bn_bwd_stats(const BnBwdArgs& a, cudaStream_t s) {
+  const long long items = static_cast<long long>(a.H) * a.W * 16;
+  bn_bwd_kernel<false><<<grid_for(items, kThreads, 148 * 4), kThreads, 0, s>>>(a);
+  DSR_LAUNCH_CHECK();
+}
+int launch_bn_bwd_apply(const BnBwdArgs& a, cudaStream_t s) {
+  const long long items = static_cast<long long>(a.H) * a.W * 16;
+  bn_bwd_kernel<true><<<grid_for(items, kThreads, 148 * 16), kThreads, 0, s>>>(a);
+  DSR_LAUNCH_CHECK();
+}
+
+// =============================================================================================
+// concat BN(132) backward
+// =============================================================================================
+__device__ __forceinline__ void fold_gather(const __nv_bfloat16* gp, int C, int H, int W, int y, int x, int coff,
+                                            float (&da)[8]) {
+  int ys[3], xs[3];
+  const int ny = halo_coords(y, H, ys), nx = halo_coords(x, W, xs);
+  const int Wp = W + 2;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) da[j] = 0.f;
+  for (int i = 0; i < ny; ++i)
+    for (int k = 0; k < nx; ++k) {
+      float f[8];
+      load8b(gp + (static_cast<long long>(ys[i]) * Wp + xs[k]) * C + coff, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) da[j] += f[j];
+    }
+}
+
+template <bool APPLY>
+__global__ void upcat_bwd_kernel(UpcatBwdArgs a) {
+  const UpcatArgs& f = a.f;
+  const int g = threadIdx.x & 15;
+  const float inv_n = 1.f / (static_cast<float>(f.H) * static_cast<float>(f.W));
+  float mean[8], rstd[8], ga[8], be[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) cat_coeffs(f, g * 8 + j, mean[j], rstd[j], ga[j], be[j]);
+  float mean4[4], rstd4[4], ga4[4], be4[4];
+#pragma unroll
+  for (int o = 0; o < 4; ++o) cat_coeffs(f, 128 + o, mean4[o], rstd4[o], ga4[o], be4[o]);
+  float s1[8], s2[8], t1[4] = {0, 0, 0, 0}, t2[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+  const long long npix = static_cast<long long>(f.H) * f.W;
+  const int Wp = f.W + 2;
+  const __nv_bfloat16* gc = static_cast<const __nv_bfloat16*>(a.gcat);
+  __nv_bfloat16* dup = static_cast<__nv_bfloat16*>(a.dup_pad);
+  for (long long pix = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 4; pix < npix;
+       pix += (static_cast<long long>(gridDim.x) * blockDim.x) >> 4) {
+    const int y = static_cast<int>(pix / f.W), x = static_cast<int>(pix % f.W);
+    float dc[8], u[8];
+    fold_gather(gc, 144, f.H, f.W, y, x, g * 8, dc);
+    upsample8(f, y, x, g, u);
+    if (!APPLY) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xh = (u[j] - mean[j]) * rstd[j];
+        s1[j] += dc[j];
+        s2[j] += dc[j] * xh;
+      }
+    } else {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xh = (u[j] - mean[j]) * rstd[j];
+        o[j] = ga[j] * rstd[j] * (dc[j] - a.cbstats[g * 8 + j] * inv_n - xh * a.cbstats[144 + g * 8 + j] * inv_n);
+      }
+      store8b(dup + (static_cast<long long>(y + 1) * Wp + (x + 1)) * 128 + g * 8, o);
+    }
+    if (g == 0) {
+      float d4[8];
+      fold_gather(gc, 144, f.H, f.W, y, x, 128, d4);
+      float sv[4], xh4[4], yv[4];
+      skip_act4(f, pix, sv, xh4, yv);
+      if (!APPLY) {
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+          const float xh = (sv[o] - mean4[o]) * rstd4[o];
+          t1[o] += d4[o];
+          t2[o] += d4[o] * xh;
+        }
+      } else {
+        float dsy[4];
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+          const float xh = (sv[o] - mean4[o]) * rstd4[o];
+          const float ds = ga4[o] * rstd4[o] *
+                           (d4[o] - a.cbstats[128 + o] * inv_n - xh * a.cbstats[144 + 128 + o] * inv_n);
+          dsy[o] = ds * (yv[o] > 0.f ? 1.f : kSlope);      // through the skip branch's LeakyReLU
+          t1[o] += dsy[o];
+          t2[o] += dsy[o] * xh4[o];
+        }
+        *reinterpret_cast<float4*>(a.dsy + pix * 4) = make_float4(dsy[0], dsy[1], dsy[2], dsy[3]);
+      }
+    }
+  }
+  if (!APPLY) {
+    __shared__ float red[2 * 144];
+    for (int i = threadIdx.x; i < 2 * 144; i += blockDim.x) red[i] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&red[g * 8 + j], s1[j]);
+      atomicAdd(&red[144 + g * 8 + j], s2[j]);
+    }
+    if (g == 0) {
+#pragma unroll
+      for (int o = 0; o < 4; ++o) {
+        atomicAdd(&red[128 + o], t1[o]);
+        atomicAdd(&red[144 + 128 + o], t2[o]);
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * 144; i += blockDim.x)
+      if ((i % 144) < 132) atomicAdd(&a.cbstats[i], red[i]);
+  } else {
+    __shared__ float red4[8];
+    if (threadIdx.x < 8) red4[threadIdx.x] = 0.f;
+    __syncthreads();
+    if (g == 0) {
+#pragma unroll
+      for (int o = 0; o < 4; ++o) {
+        atomicAdd(&red4[o], t1[o]);
+        atomicAdd(&red4[4 + o], t2[o]);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) atomicAdd(&a.sbstats[threadIdx.x], red4[threadIdx.x]);
+    if (blockIdx.x == 0 && threadIdx.x < 132) {
+      const int c = threadIdx.x;                        // packed channel
+      const int rc = (c < 128) ? c + 4 : c - 128;       // reference channel
+      a.dcat_beta[rc] = a.cbstats[c];
+      a.dcat_gamma[rc] = a.cbstats[144 + c];
+    }
+  }
+}
+
+int launch_upcat_bwd_stats(const UpcatBwdArgs& a, cudaStream_t s) {
+  const long long items = static_cast<long long>(a.f.H) * a.f.W * 16;
+  upcat_bwd_kernel<false><<<grid_for(items, kThreads, 148 * 4), kThreads, 0, s>>>(a);
+  DSR_LAUNCH_CHECK();
+}
+int launch_upcat_bwd_apply(const UpcatBwdArgs& a, cudaStream_t s) {
+  const long long items = static_cast<long long>(a.f.H) * a.f.W * 16;
+  upcat_bwd_kernel<true><<<grid_for(items, kThreads, 148 * 8), kThreads, 0, s>>>(a);
+  DSR_LAUNCH_CHECK();
+}
+
+// =============================================================================================
+// skip branch backward: BN(4) backward + 1x1 conv weight gradient
+// =============================================================================================
+template <int CIN>
+__global__ void skip_bwd_kernel(const float* __restrict__ dsy, const float* __restrict__ sraw, BnRef bn,
+                                const float* __restrict__ sbstats, const __half* __restrict__ xpad,
+                                float* __restrict__ dsraw, float* __restrict__ dw, float* __restrict__ dgamma,
+                                float* __restrict__ dbeta, int H, int W) {
+  constexpr int G = CIN / 8;
+  const int g = threadIdx.x % G;
+  float mean[4], rstd[4], ga[4], be[4], c1[4], c2[4];
+#pragma unroll
+  for (int o = 0; o < 4; ++o) {
+    bn_coeffs(bn, o, mean[o], rstd[o], ga[o], be[o]);
+    c1[o] = sbstats[o] * bn.inv_n;
+    c2[o] = sbstats[4 + o] * bn.inv_n;
+  }
+  float aw[4][8];
+#pragma unroll
+  for (int o = 0; o < 4; ++o)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) aw[o][j] = 0.f;
+  const long long npix = static_cast<long long>(H) * W;
+  const int Wp = W + 2;
+  for (long long pix = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) / G; pix < npix;
+       pix += (static_cast<long long>(gridDim.x) * blockDim.x) / G) {
+    const int y = static_cast<int>(pix / W), x = static_cast<int>(pix % W);
+    const float4 d = *reinterpret_cast<const float4*>(dsy + pix * 4);
+    const float4 r = *reinterpret_cast<const float4*>(sraw + pix * 4);
+    const float dd[4] = {d.x, d.y, d.z, d.w}, rr[4] = {r.x, r.y, r.z, r.w};
+    float dr[4];
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      const float xh = (rr[o] - mean[o]) * rstd[o];
+      dr[o] = ga[o] * rstd[o] * (dd[o] - c1[o] - xh * c2[o]);
+    }
+    if (g == 0) *reinterpret_cast<float4*>(dsraw + pix * 4) = make_float4(dr[0], dr[1], dr[2], dr[3]);
+    float f[8];
+    load8h(xpad + (static_cast<long long>(y + 1) * Wp + (x + 1)) * CIN + g * 8, f);
+#pragma unroll
+    for (int o = 0; o < 4; ++o)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) aw[o][j] = fmaf(dr[o], f[j], aw[o][j]);
+  }
+  __shared__ float red[4 * CIN];
+  for (int i = threadIdx.x; i < 4 * CIN; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int o = 0; o < 4; ++o)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&red[o * CIN + g * 8 + j], aw[o][j]);
+  __syncthreads();
+  for (int i = threadIdx.x; i < 4 * CIN; i += blockDim.x) atomicAdd(&dw[i], red[i]);
+  if (blockIdx.x == 0 && threadIdx.x < 4) {
+    dbeta[threadIdx.x] = sbstats[threadIdx.x];
+    dgamma[threadIdx.x] = sbstats[4 + threadIdx.x];
+  }
+}
+
+int launch_skip_bwd(const float* dsy, const float* sraw, BnRef bn_skip, const float* sbstats, const void* xpad, int Cin,
+                    float* dsraw, float* dw, float* dgamma, float* dbeta, int H, int W, cudaStream_t s) {
+  const long long items = static_cast<long long>(H) * W * (Cin / 8);
+  const int grid = grid_for(items, kThreads, 148 * 2);
+  if (Cin == 32)
+    skip_bwd_kernel<32><<<grid, kThreads, 0, s>>>(dsy, sraw, bn_skip, sbstats, static_cast<const __half*>(xpad), dsraw,
+                                                  dw, dgamma, dbeta, H, W);
+  else if (Cin == 128)
+    skip_bwd_kernel<128><<<grid, kThreads, 0, s>>>(dsy, sraw, bn_skip, sbstats, static_cast<const __half*>(xpad), dsraw,
+                                                   dw, dgamma, dbeta, H, W);
+  else
+    return -2;
+  DSR_LAUNCH_CHECK();
+}
+
+// =============================================================================================
+// bilinear upsample backward (gather form)
+// =============================================================================================
+__global__ void upsample_bwd_kernel(const __nv_bfloat16* __restrict__ dup, int H, int W,
+                                    __nv_bfloat16* __restrict__ ddeep, int h, int w) {
+  const int g = threadIdx.x & 15;
+  const long long npix = static_cast<long long>(h) * w;
+  const int Wp = W + 2, wp = w + 2;
+  for (long long pix = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 4; pix < npix;
+       pix += (static_cast<long long>(gridDim.x) * blockDim.x) >> 4) {
+    const int qy = static_cast<int>(pix / w), qx = static_cast<int>(pix % w);
+    float wy[4], wx[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int oy = 2 * qy - 1 + t, ox = 2 * qx - 1 + t;
+      wy[t] = 0.f;
+      wx[t] = 0.f;
+      if (oy >= 0 && oy < H) {
+        int i0, i1; float l0, l1;
+        up_src(oy, h, i0, i1, l0, l1);
+        wy[t] = (i0 == qy ? l0 : 0.f) + (i1 == qy ? l1 : 0.f);
+      }
+      if (ox >= 0 && ox < W) {
+        int i0, i1; float l0, l1;
+        up_src(ox, w, i0, i1, l0, l1);
+        wx[t] = (i0 == qx ? l0 : 0.f) + (i1 == qx ? l1 : 0.f);
+      }
+    }
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      if (wy[a] == 0.f) continue;
+      const int oy = 2 * qy - 1 + a;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        if (wx[b] == 0.f) continue;
+        const int ox = 2 * qx - 1 + b;
+        float f[8];
+        load8b(dup + (static_cast<long long>(oy + 1) * Wp + (ox + 1)) * 128 + g * 8, f);
+        const float ww = wy[a] * wx[b];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(ww, f[j], acc[j]);
+      }
+    }
+    store8b(ddeep + (static_cast<long long>(qy + 1) * wp + (qx + 1)) * 128 + g * 8, acc);
+  }
+}
+
+int launch_upsample_bwd(const void* dup_pad, int H, int W, void* ddeep_pad, int h, int w, cudaStream_t s) {
+  const long long items = static_cast<long long>(h) * w * 16;
+  upsample_bwd_kernel<<<grid_for(items, kThreads, 148 * 16), kThreads, 0, s>>>(
+      static_cast<const __nv_bfloat16*>(dup_pad), H, W, static_cast<__nv_bfloat16*>(ddeep_pad), h, w);
+  DSR_LAUNCH_CHECK();
+}
+
+// =============================================================================================
+// weight packing / gradient unpacking
+// =============================================================================================
+__device__ __forceinline__ int ref_ci(const PackDesc& d, int j) { return d.perm ? (j < 128 ? j + 4 : j - 128) : j; }
+
+__global__ void pack_weights_kernel(const float* __restrict__ params, __half* __restrict__ arena,
+                                    const PackDesc* __restrict__ table, int nlayers) {
+  const PackDesc d = table[blockIdx.y];
+  const int taps = d.k * d.k;
+  const long long nf = static_cast<long long>(taps) * 128 * d.cin_pad;
+  const long long nd = static_cast<long long>(taps) * d.n_rows * 128;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nf + nd;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    if (i < nf) {                                   // fprop matrix [tap][co][j]
+      const int j = static_cast<int>(i % d.cin_pad);
+      const int co = static_cast<int>((i / d.cin_pad) % 128);
+      const int tap = static_cast<int>(i / (static_cast<long long>(d.cin_pad) * 128));
+      float v = 0.f;
+      if (j < d.cin && co < d.cout) v = params[d.w_off + (static_cast<long long>(co) * d.cin + ref_ci(d, j)) * taps + tap];
+      arena[d.f_off + i] = __float2half_rn(v);
+    } else {                                        // dgrad matrix [tap][j][co]
+      const long long k = i - nf;
+      const int co = static_cast<int>(k % 128);
+      const int j = static_cast<int>((k / 128) % d.n_rows);
+      const int tap = static_cast<int>(k / (128LL * d.n_rows));
+      float v = 0.f;
+      if (j < d.cin && co < d.cout) v = params[d.w_off + (static_cast<long long>(co) * d.cin + ref_ci(d, j)) * taps + tap];
+      arena[d.d_off + k] = __float2half_rn(v);
+    }
+  }
+  (void)nlayers;
+}
+
+int launch_pack_weights(const float* params, void* arena, const PackDesc* table_dev, int nlayers, cudaStream_t s) {
+  dim3 grid(64, nlayers);
+  pack_weights_kernel<<<grid, kThreads, 0, s>>>(params, static_cast<__half*>(arena), table_dev, nlayers);
+  DSR_LAUNCH_CHECK();
+}
+
+__global__ void unpack_wgrad_kernel(const float* __restrict__ garena, float* __restrict__ grads,
+                                    const PackDesc* __restrict__ table) {
+  const PackDesc d = table[blockIdx.y];
+  const int taps = d.k * d.k;
+  const long long n = static_cast<long long>(d.cout) * d.cin * taps;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int tap = static_cast<int>(i % taps);
+    const int ci = static_cast<int>((i / taps) % d.cin);
+    const int co = static_cast<int>(i / (static_cast<long long>(taps) * d.cin));
+    const int j = d.perm ? (ci >= 4 ? ci - 4 : ci + 128) : ci;
+    grads[d.w_off + i] = garena[d.g_off + (static_cast<long long>(tap) * 128 + co) * d.cin_pad + j];
+  }
+}
+
+int launch_unpack_wgrad(const float* garena, float* grads, const PackDesc* table_dev, int nlayers, cudaStream_t s) {
+  dim3 grid(32, nlayers);
+  unpack_wgrad_kernel<<<grid, kThreads, 0, s>>>(garena, grads, table_dev);
+  DSR_LAUNCH_CHECK();
+}
+
+// =============================================================================================
+// running statistics
+// =============================================================================================
+__global__ void bn_running_kernel(const BnRunDesc* __restrict__ table, const float* __restrict__ ws,
+                                  const float* __restrict__ params, float* __restrict__ bnbuf, float momentum) {
+  const BnRunDesc d = table[blockIdx.x];
+  const float* stats = ws + d.stats_off;
+  float* rm = bnbuf + d.rm_off;
+  float* rv = bnbuf + d.rv_off;
+  for (int c = threadIdx.x; c < d.C; c += blockDim.x) {
+    const int pc = d.perm ? (c >= 4 ? c - 4 : c + 128) : c;     // reference channel c -> packed channel
+    const float mean = stats[pc] / d.n;
+    const float var_b = fmaxf(stats[d.cstride + pc] / d.n - mean * mean, 0.f);
+    const float var_u = d.n > 1.f ? var_b * d.n / (d.n - 1.f) : var_b;
+    const float bias = d.bias_off >= 0 ? params[d.bias_off + c] : 0.f;
+    rm[c] = (1.f - momentum) * rm[c] + momentum * (mean + bias);
+    rv[c] = (1.f - momentum) * rv[c] + momentum * var_u;
+  }
+}
+
+int launch_bn_running(const BnRunDesc* table_dev, int nbn, const float* ws_f32, const float* params, float* bn_buffers,
+                      float momentum, cudaStream_t s) {
+  bn_running_kernel<<<nbn, 160, 0, s>>>(table_dev, ws_f32, params, bn_buffers, momentum);
+  DSR_LAUNCH_CHECK();
+}
+
+// =============================================================================================
+// Adam (torch.optim.Adam defaults; single fused pass over the flat parameter buffer)
+// =============================================================================================
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, long long n, float step_size, float b1, float b2, float eps,
+                            float inv_sqrt_bc2) {
+  const long long n4 = n >> 2;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float4 pp = reinterpret_cast<float4*>(p)[i];
+    const float4 gg = reinterpret_cast<const float4*>(g)[i];
+    float4 mm = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+#define DSR_ADAM1(f)                                                   \
+  mm.f = b1 * mm.f + (1.f - b1) * gg.f;                                \
+  vv.f = b2 * vv.f + (1.f - b2) * gg.f * gg.f;                         \
+  pp.f -= step_size * (mm.f / (sqrtf(vv.f) * inv_sqrt_bc2 + eps));
+    DSR_ADAM1(x) DSR_ADAM1(y) DSR_ADAM1(z) DSR_ADAM1(w)
+    reinterpret_cast<float4*>(p)[i] = pp;
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+  }
+  // tail
+  for (long long i = (n4 << 2) + static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float gi = g[i];
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] -= step_size * (mi / (sqrtf(vi) * inv_sqrt_bc2 + eps));
+  }
+}
+
+int launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
+                int t, cudaStream_t s) {
+  if ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+       reinterpret_cast<uintptr_t>(v)) & 15)
+    return -3;
+  const double bc1 = 1.0 - pow(static_cast<double>(b1), t);
+  const double bc2 = 1.0 - pow(static_cast<double>(b2), t);
+  const float step_size = static_cast<float>(static_cast<double>(lr) / bc1);
+  const float inv_sqrt_bc2 = static_cast<float>(1.0 / sqrt(bc2));
+  adam_kernel<<<grid_for(n / 4 + 1, kThreads, 148 * 8), kThreads, 0, s>>>(p, g, m, v, n, step_size, b1, b2, eps,
+                                                                         inv_sqrt_bc2);
+  DSR_LAUNCH_CHECK();
+}
+
+// =============================================================================================
+// input perturbation: z = z_saved + sigma * N(0,1)  (Philox4x32-10 + Box-Muller)
+// =============================================================================================
+__device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+    c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+}
+
+__global__ void perturb_kernel(const float* __restrict__ zs, float* __restrict__ z, long long n, float sigma,
+                               unsigned long long seed, unsigned long long offset) {
+  const long long n4 = (n + 3) >> 2;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const unsigned long long ctr = offset + static_cast<unsigned long long>(i);
+    uint32_t c[4] = {static_cast<uint32_t>(ctr), static_cast<uint32_t>(ctr >> 32), 0u, 0u};
+    philox4x32_10(c, static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+    float r[4];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float u1 = (static_cast<float>(c[2 * h]) + 0.5f) * 2.3283064365386963e-10f;       // (0,1)
+      const float u2 = (static_cast<float>(c[2 * h + 1]) + 0.5f) * 2.3283064365386963e-10f;
+      const float rad = sqrtf(-2.f * __logf(u1));
+      float sn, cs;
+      __sincosf(6.283185307179586f * u2, &sn, &cs);
+      r[2 * h] = rad * cs;
+      r[2 * h + 1] = rad * sn;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const long long e = 4 * i + k;
+      if (e < n) z[e] = zs[e] + sigma * r[k];
+    }
+  }
+}
+
+int launch_perturb(const float* z_saved, float* z, long long n, float sigma, unsigned long long seed,
+                   unsigned long long offset, cudaStream_t s) {
+  perturb_kernel<<<grid_for((n + 3) / 4, kThreads, 148 * 8), kThreads, 0, s>>>(z_saved, z, n, sigma, seed, offset);
+  DSR_LAUNCH_CHECK();
+}
+
+}  // namespace dsr

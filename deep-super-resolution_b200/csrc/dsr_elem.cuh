@@ -1,0 +1,138 @@
+// dsr_elem.cuh -- host-callable launchers of the bandwidth kernels of the DIP step (dsr_elem.cu).
+//
+// Conventions: "act" tensors are fp16 NHWC on a padded pixel grid [H+2][W+2][C]; pointers passed
+// here always point at PADDED pixel (0,0) unless the argument is called *_interior or "plain"
+// (= unpadded [H][W][C]).  Gradient tensors are bf16.  Statistics blocks are float [2][C]
+// (sum, sum of squares), accumulated with atomics and zeroed by the caller.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dsr {
+
+struct BnRef {            // one train-mode BatchNorm over n pixels
+  const float* stats;     // [2][cstride] forward sums of the BN input
+  const float* gamma;     // [C]
+  const float* beta;      // [C]
+  float inv_n;            // 1 / (H*W)
+  int cstride;            // distance between the sum block and the sum-of-squares block
+};
+
+// z fp32 NCHW [C][H][W] (C multiple of 8) -> fp16 padded NHWC with reflected halo.
+int launch_input_pack(const float* z, void* xpad, int C, int H, int W, cudaStream_t s);
+
+// raw fp16 plain [H][W][128] -> LeakyReLU(BN(raw)) fp16 padded (interior + reflected halo if halo != 0)
+int launch_bn_act(const void* raw, BnRef bn, void* act_pad, int H, int W, int halo, cudaStream_t s);
+
+// skip branch 1x1 conv: x padded [H+2][W+2][Cin] (fp16) * w fp32 [4][Cin] -> sraw fp32 plain [H][W][4], stats [2][4]
+int launch_skip_conv(const void* xpad, int Cin, const float* w, float* sraw, float* stats, int H, int W,
+                     cudaStream_t s);
+
+// Upsample x2 (bilinear, align_corners=False) of `deep` + skip activation -> concat statistics / apply.
+struct UpcatArgs {
+  const void* deep;        // fp16, pixel (0,0) of the low-res activation
+  long long deep_sy;       // row pitch in elements (pixel pitch is 128)
+  int h, w;                // low-res extent
+  int H, W;                // concat extent (H <= 2h, W <= 2w; centre-crop offset is 0)
+  const float* sraw;       // fp32 plain [H][W][4]
+  BnRef bn_skip;           // BN(4) of the skip branch
+  float* cat_stats;        // [2][144]: packed channel order (0..127 upsampled, 128..131 skip)
+  const float* cat_gamma;  // BN(132) affine, REFERENCE channel order (0..3 skip, 4..131 upsampled)
+  const float* cat_beta;
+  void* cat_pad;           // fp16 padded [H+2][W+2][144], reflected halo
+};
+int launch_upcat_stats(const UpcatArgs& a, cudaStream_t s);
+int launch_upcat_apply(const UpcatArgs& a, cudaStream_t s);
+
+// final 1x1 conv 128 -> 3 + bias + sigmoid: act padded [H+2][W+2][128] -> out fp32 NCHW [3][H][W]
+int launch_final_conv(const void* act_pad, const float* w, const float* b, float* out, int H, int W, cudaStream_t s);
+
+// ---- backward ------------------------------------------------------------------------------
+// d(out) fp32 NCHW, out fp32 NCHW -> dA bf16 padded interior [H+2][W+2][128]; dW [3][128] and db [3] accumulated.
+int launch_final_bwd(const float* gout, const float* out, const void* act_pad, const float* w, void* dact_pad,
+                     float* dw, float* db, int H, int W, cudaStream_t s);
+
+struct BnBwdArgs {
+  const void* g;           // bf16 gradient w.r.t. the activation, PADDED grid [H+2][W+2][gC]
+  int gC;                  // channel pitch of g (128 or 144; first 128 channels are used)
+  int fold;                // 1: g holds padded-grid data-gradients whose halo must be folded back (reflection)
+  const float* ds;         // optional fp32 plain [H][W][4]: gradient of the skip-conv output reading this activation
+  const float* wskip;      // fp32 [4][128]
+  const void* raw;         // fp16 plain [H][W][128]: BN input saved by the forward
+  BnRef bn;
+  float* bstats;           // [2][128]: sum dy, sum dy*xhat
+  void* dr_pad;            // bf16 padded [H+2][W+2][128] (interior written; halo stays zero)
+  float* dgamma;           // [128]
+  float* dbeta;            // [128]
+  int H, W;
+};
+int launch_bn_bwd_stats(const BnBwdArgs& a, cudaStream_t s);
+int launch_bn_bwd_apply(const BnBwdArgs& a, cudaStream_t s);
+
+struct UpcatBwdArgs {
+  UpcatArgs f;             // forward description (deep, sraw, stats ...)
+  const void* gcat;        // bf16 padded grid [H+2][W+2][144]: data-gradient of the 3x3 conv reading cat (to fold)
+  float* cbstats;          // [2][144] packed order: sum dc, sum dc*xhat
+  void* dup_pad;           // bf16 padded [H+2][W+2][128]: gradient w.r.t. the upsampled tensor (interior)
+  float* dsy;              // fp32 plain [H][W][4]: gradient w.r.t. BN(4) output (after LeakyReLU')
+  float* sbstats;          // [2][4]
+  float* dcat_gamma;       // [132] reference channel order
+  float* dcat_beta;
+};
+int launch_upcat_bwd_stats(const UpcatBwdArgs& a, cudaStream_t s);
+int launch_upcat_bwd_apply(const UpcatBwdArgs& a, cudaStream_t s);
+
+// BN(4)+skip conv backward: dsy -> dsraw fp32 [H][W][4]; dWskip [4][Cin] (accumulated), dgamma4/dbeta4.
+int launch_skip_bwd(const float* dsy, const float* sraw, BnRef bn_skip, const float* sbstats, const void* xpad, int Cin,
+                    float* dsraw, float* dw, float* dgamma, float* dbeta, int H, int W, cudaStream_t s);
+
+// transpose of the bilinear x2 upsample: dup padded-interior [H][W][128] (bf16) -> ddeep bf16 padded interior [h][w][128]
+int launch_upsample_bwd(const void* dup_pad, int H, int W, void* ddeep_pad, int h, int w, cudaStream_t s);
+
+// ---- parameters ----------------------------------------------------------------------------
+struct PackDesc {           // one conv layer's weight (OIHW fp32 in the flat parameter buffer)
+  long long w_off;          // offset (floats) into the flat parameter / gradient buffer
+  int cout, cin, k;         // k = 1 or 3
+  int cin_pad;              // packed K (16-multiple): fprop matrix is [k*k][128][cin_pad]
+  int n_rows;               // packed dgrad rows per tap: matrix is [k*k][n_rows][128]  (0: no dgrad needed)
+  int perm;                 // 1: packed ci j <-> reference ci (j < 128 ? j + 4 : j - 128)   (concat layer)
+  long long f_off, d_off;   // offsets (16-bit elements) into the packed-weight arena
+  long long g_off;          // offset (floats) into the packed wgrad arena [k*k][128][cin_pad]
+};
+int launch_pack_weights(const float* params, void* arena, const PackDesc* table_dev, int nlayers, cudaStream_t s);
+int launch_unpack_wgrad(const float* garena, float* grads, const PackDesc* table_dev, int nlayers, cudaStream_t s);
+
+struct BnRunDesc {          // running-statistics update of one BatchNorm (all offsets in floats)
+  long long stats_off;      // into the plan workspace viewed as float*: [2][cstride] forward sums
+  int cstride; int C; float n;
+  long long rm_off, rv_off; // into the flat BatchNorm buffer: running_mean[C], running_var[C]
+  long long bias_off;       // into the flat parameter buffer: bias of the conv feeding this BN (the kernels drop
+                            // it because BN cancels it, but torch's running_mean contains it), or -1
+  int perm;                 // 1: stats are in packed concat order
+};
+int launch_bn_running(const BnRunDesc* table_dev, int nbn, const float* ws_f32, const float* params, float* bn_buffers,
+                      float momentum, cudaStream_t s);
+
+int launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
+                int t, cudaStream_t s);
+
+// ---- Lanczos downsampler (fp32 NCHW) -------------------------------------------------------
+struct DsTables {           // device tables built by the plan (dsr_downsampler.cu)
+  const float* taps;        // [k] normalised 1-D taps (fp32)
+  int k, factor, pad;
+  // backward gather tables: for every input row y (col x): first output index and NW weights
+  const int* by0; const float* bwy;   // [H], [H][nw]
+  const int* bx0; const float* bwx;   // [W], [W][nw]
+  int nw;
+};
+int launch_downsample_fwd(const float* x, float* y, int C, int H, int W, int oh, int ow, DsTables t, cudaStream_t s);
+int launch_downsample_bwd(const float* gy, float* gx, int C, int H, int W, int oh, int ow, DsTables t, cudaStream_t s);
+// fused: y = D(x); loss += mean((y - target)^2); gy = 2 (y - target) / N
+int launch_downsample_mse(const float* x, const float* target, float* y, float* gy, float* loss, int C, int H, int W,
+                          int oh, int ow, DsTables t, cudaStream_t s);
+
+// z = z_saved + sigma * N(0,1)   (Philox4x32-10 counter RNG, fp32, elementwise)
+int launch_perturb(const float* z_saved, float* z, long long n, float sigma, unsigned long long seed,
+                   unsigned long long offset, cudaStream_t s);
+
+}  // namespace dsr

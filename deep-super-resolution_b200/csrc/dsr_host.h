@@ -1,0 +1,25 @@
+// dsr_host.h -- internal host-side declarations shared by the translation units of libdsr_b200.so.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "dsr_conv.cuh"
+
+namespace dsr {
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int ensure_driver_api();
+int make_act_map(CUtensorMap* m, const void* base, int elem_is_16bit, int C, int Wp, int Hp, int step, int box_c,
+                 int box_w, int box_h);
+int make_wgt_map(CUtensorMap* m, const void* base, int K, int rows, int box_k, int box_rows);
+int launch_conv_gemm(const ConvGemmParams& p, int num_sms, cudaStream_t stream);
+int launch_wgrad(const WgradParams& p, cudaStream_t stream);
+
+// Element formats of the 16-bit tensors (tcgen05 kind::f16 operand format codes).
+enum : uint32_t { FMT_F16 = 0, FMT_BF16 = 1 };
+
+}  // namespace dsr

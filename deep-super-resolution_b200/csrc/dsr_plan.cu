@@ -1,0 +1,1053 @@
+// dsr_plan.cu -- host side of libdsr_b200.so: the execution plan of the skip network (layer table,
+// workspace layout, TMA descriptors, forward / backward / whole-step launch sequences) and the
+// extern "C" entry points declared in include/dsr_b200.h.
+//
+// Reference structure being replaced (paths relative to the upstream repo):
+//   models/DIP/skip.py:41-94      per-level module graph (skip branch, two encoder convs, recursion,
+//                                 upsample, Concat, BN(132), decoder 3x3 + 1x1, final 1x1 + sigmoid)
+//   models/DIP/utils.py:5-8       1-based child naming (state_dict keys)
+//   DIP.py:47-95, utils/DIP.py:35-38   closure + Adam loop (dsr_dip_step)
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/dsr_b200.h"
+#include "dsr_conv.cuh"
+#include "dsr_debug.h"
+#include "dsr_elem.cuh"
+#include "dsr_host.h"
+#include "dsr_ptx.cuh"
+
+namespace dsr {
+
+void lanczos_taps(int factor, int support, std::vector<double>& taps);
+void ds_bwd_table(int n, int on, int factor, int k, int pad, const std::vector<float>& taps, int& nw,
+                  std::vector<int>& o0, std::vector<float>& w);
+
+namespace {
+
+constexpr int kNC = 128;       // n33d = n33u (DIP.py:170-171)
+constexpr int kNS = 4;         // skip_n11   (DIP.py:172)
+constexpr int kCat = 144;      // packed concat channel pitch: 128 upsampled + 4 skip + 12 zero
+constexpr float kMomentum = 0.1f;
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct ParamInfo {
+  std::string name;
+  long long off;
+  int ndim;
+  int shape[4];
+};
+struct BnInfo {
+  std::string name;
+  long long off;   // running_mean at off, running_var at off + C
+  int C;
+};
+
+// A tensor of the workspace (offset resolved to a pointer at bind time).
+struct Buf {
+  size_t off = 0, bytes = 0;
+  void* ptr = nullptr;
+};
+
+struct TensorInfo {
+  std::string name;
+  const Buf* buf;     // workspace tensor, or nullptr when `acc_off` (a float index from the base) is used
+  size_t acc_off;
+  int kind;      // 0 fp16, 1 bf16, 2 fp32
+  int padded;
+  int H, W, C;
+};
+
+// One tensor-core convolution (encoder d1 / d2, decoder u1 / u2 of a level) and its BatchNorm.
+struct ConvLayer {
+  const char* tag = "";
+  int cin = 0, cin_pad = 0, k = 3, stride = 1;
+  int inH = 0, inW = 0, outH = 0, outW = 0;
+  bool need_dgrad = true;
+  int n_rows = 0;                  // dgrad output channels (packed): 128 or 144
+  long long w_off = 0, b_off = 0, g_off = 0, be_off = 0;   // conv weight / bias, BN gamma / beta (floats)
+  long long bn_off = 0;            // BN buffers
+  PackDesc pack{};
+  const Buf* in_pad = nullptr;     // fp16 padded input [inH+2][inW+2][cin_pad]
+  Buf raw;                         // fp16 plain [outH][outW][128]
+  Buf act;                         // fp16 padded [outH+2][outW+2][128]
+  int act_halo = 0;                // write the reflected halo of `act`
+  size_t stats_off = 0;            // floats into the accumulator block: [2][128] forward sums
+  size_t bstats_off = 0;           // [2][128] backward sums
+  Buf dr;                          // bf16 padded [outH+2][outW+2][128]   gradient w.r.t. raw
+  Buf gin;                         // bf16 padded [inH+2][inW+2][n_rows]  data gradient (to fold)
+  ConvGemmParams fprop{};
+  ConvGemmParams dgrad[4];
+  int ndgrad = 0;
+  WgradParams wgrad{};
+  ActRef ref_in{}, ref_dr{};       // checker views
+  WgtRef ref_wf{}, ref_wd{};
+};
+
+struct Level {
+  int H = 0, W = 0, h = 0, w = 0, Cin = 0;
+  long long skip_w = 0, skip_b = 0, skip_g = 0, skip_be = 0, skip_bn = 0;
+  long long cat_g = 0, cat_be = 0, cat_bn = 0;
+  ConvLayer d1, d2, u1, u2;
+  Buf xin;                          // level 0 only: packed input
+  const Buf* x_pad = nullptr;       // fp16 padded [H+2][W+2][Cin]
+  Buf sraw;                         // fp32 [H][W][4]
+  Buf cat;                          // fp16 padded [H+2][W+2][144]
+  size_t skip_stats_off = 0, cat_stats_off = 0;     // forward accumulators ([2][4], [2][144])
+  size_t sbstats_off = 0, cbstats_off = 0;          // backward accumulators
+  Buf g_u2a;                        // bf16 padded [H+2][W+2][128]: gradient w.r.t. this level's output
+  Buf dup;                          // bf16 padded [H+2][W+2][128]
+  Buf dsy, dsraw;                   // fp32 [H][W][4]
+  Buf g_d2a;                        // last level only: bf16 padded [h+2][w+2][128]
+};
+
+}  // namespace
+}  // namespace dsr
+
+using namespace dsr;
+
+struct dsr_downsampler {
+  int factor, support, H, W, oh, ow, k, pad, nw_y, nw_x;
+  std::vector<float> taps;
+  std::vector<int> by0, bx0;
+  std::vector<float> bwy, bwx;
+  DsTables t{};
+};
+
+struct dsr_plan {
+  int H, W, input_depth, num_scales, n_out;
+  std::vector<Level> lv;
+  std::vector<ParamInfo> params;
+  std::vector<BnInfo> bns;
+  long long nparam = 0, nbn = 0;
+  long long fin_w = 0, fin_b = 0;
+  // workspace
+  size_t ws_bytes = 0;
+  size_t acc_fwd_off = 0, acc_fwd_floats = 0;     // zeroed at the start of every forward
+  size_t acc_bwd_off = 0, acc_bwd_floats = 0;     // zeroed at the start of every backward (incl. wgrad arena)
+  size_t garena_off = 0;                          // floats, inside the backward accumulator block
+  Buf warena;                                     // packed 16-bit weights
+  Buf pack_table, bnrun_table, errword;
+  Buf g_final;                                    // unused placeholder (level 0 g_u2a is the final-conv gradient)
+  std::vector<PackDesc> pack_host;
+  std::vector<BnRunDesc> bnrun_host;
+  std::vector<TensorInfo> tensors;
+  char* base = nullptr;
+  int num_sms = 148;
+  int launches = 0;
+  int debug_conv = 0;
+  bool bound = false, have_forward = false;
+};
+
+namespace dsr {
+namespace {
+
+struct Bump {
+  size_t off = 0;
+  void take(Buf& b, size_t bytes) {
+    off = align_up(off, 1024);
+    b.off = off;
+    b.bytes = bytes;
+    off += bytes;
+  }
+  size_t take_floats(size_t n) {   // returns a float index
+    off = align_up(off, 1024);
+    const size_t r = off / 4;
+    off += n * 4;
+    return r;
+  }
+};
+
+void add_param(dsr_plan* p, const std::string& name, long long& off_out, std::initializer_list<int> shape) {
+  ParamInfo pi;
+  pi.name = name;
+  pi.off = p->nparam;
+  pi.ndim = static_cast<int>(shape.size());
+  long long n = 1;
+  int i = 0;
+  for (int s : shape) { pi.shape[i++] = s; n *= s; }
+  for (; i < 4; ++i) pi.shape[i] = 1;
+  off_out = pi.off;
+  p->nparam += n;
+  p->params.push_back(pi);
+}
+void add_conv_params(dsr_plan* p, const std::string& name, long long& w, long long& b, int co, int ci, int k) {
+  add_param(p, name + ".weight", w, {co, ci, k, k});
+  add_param(p, name + ".bias", b, {co});
+}
+void add_bn(dsr_plan* p, const std::string& name, long long& g, long long& be, long long& bn, int C) {
+  add_param(p, name + ".weight", g, {C});
+  add_param(p, name + ".bias", be, {C});
+  BnInfo bi;
+  bi.name = name;
+  bi.off = p->nbn;
+  bi.C = C;
+  bn = bi.off;
+  p->nbn += 2 * C;
+  p->bns.push_back(bi);
+}
+
+// state_dict naming: models/DIP/utils.py:5-8 (children numbered from 1), skip.py:41-92.
+void name_level(dsr_plan* p, int i) {
+  Level& L = p->lv[i];
+  std::string P;
+  for (int j = 0; j < i; ++j) P += "1.1.7.";
+  add_conv_params(p, P + "1.0.1.1", L.skip_w, L.skip_b, kNS, L.Cin, 1);
+  add_bn(p, P + "1.0.2", L.skip_g, L.skip_be, L.skip_bn, kNS);
+  add_conv_params(p, P + "1.1.1.1", L.d1.w_off, L.d1.b_off, kNC, L.Cin, 3);
+  add_bn(p, P + "1.1.2", L.d1.g_off, L.d1.be_off, L.d1.bn_off, kNC);
+  add_conv_params(p, P + "1.1.4.1", L.d2.w_off, L.d2.b_off, kNC, kNC, 3);
+  add_bn(p, P + "1.1.5", L.d2.g_off, L.d2.be_off, L.d2.bn_off, kNC);
+  if (i + 1 < p->num_scales) name_level(p, i + 1);
+  add_bn(p, P + "2", L.cat_g, L.cat_be, L.cat_bn, kNS + kNC);
+  add_conv_params(p, P + "3.1", L.u1.w_off, L.u1.b_off, kNC, kNS + kNC, 3);
+  add_bn(p, P + "4", L.u1.g_off, L.u1.be_off, L.u1.bn_off, kNC);
+  add_conv_params(p, P + "6.1", L.u2.w_off, L.u2.b_off, kNC, kNC, 1);
+  add_bn(p, P + "7", L.u2.g_off, L.u2.be_off, L.u2.bn_off, kNC);
+}
+
+void choose_tile(int out_w, int& tw, int& th) {
+  tw = 16;
+  while (tw > 1 && tw / 2 >= out_w) tw /= 2;
+  th = 128 / tw;
+}
+
+void setup_conv(dsr_plan* p, Bump& ws, Bump& accf, Bump& accb, ConvLayer& c, const char* tag, int cin, int cin_pad,
+                int k, int stride, int inH, int inW, const Buf* in_pad, bool need_dgrad, int act_halo, int perm,
+                size_t& warena_elems, size_t& garena_floats) {
+  c.tag = tag;
+  c.cin = cin;
+  c.cin_pad = cin_pad;
+  c.k = k;
+  c.stride = stride;
+  c.inH = inH;
+  c.inW = inW;
+  c.outH = (stride == 1) ? inH : (inH + 1) / 2;
+  c.outW = (stride == 1) ? inW : (inW + 1) / 2;
+  c.in_pad = in_pad;
+  c.need_dgrad = need_dgrad;
+  c.n_rows = need_dgrad ? cin_pad : 0;
+  c.act_halo = act_halo;
+  ws.take(c.raw, static_cast<size_t>(c.outH) * c.outW * kNC * 2);
+  ws.take(c.act, static_cast<size_t>(c.outH + 2) * (c.outW + 2) * kNC * 2);
+  ws.take(c.dr, static_cast<size_t>(c.outH + 2) * (c.outW + 2) * kNC * 2);
+  if (need_dgrad) ws.take(c.gin, static_cast<size_t>(inH + 2) * (inW + 2) * c.n_rows * 2);
+  c.stats_off = accf.take_floats(2 * kNC);
+  c.bstats_off = accb.take_floats(2 * kNC);
+  const int taps = k * k;
+  c.pack.w_off = c.w_off;
+  c.pack.cout = kNC;
+  c.pack.cin = cin;
+  c.pack.k = k;
+  c.pack.cin_pad = cin_pad;
+  c.pack.n_rows = c.n_rows;
+  c.pack.perm = perm;
+  warena_elems = align_up(warena_elems, 512);
+  c.pack.f_off = static_cast<long long>(warena_elems);
+  warena_elems += static_cast<size_t>(taps) * kNC * cin_pad;
+  warena_elems = align_up(warena_elems, 512);
+  c.pack.d_off = static_cast<long long>(warena_elems);
+  warena_elems += static_cast<size_t>(taps) * c.n_rows * kNC;
+  garena_floats = align_up(garena_floats, 256);
+  c.pack.g_off = static_cast<long long>(garena_floats);
+  garena_floats += static_cast<size_t>(taps) * kNC * cin_pad;
+  (void)p;
+}
+
+void push_kblocks(ConvGemmParams& g, int c_total, int px, int dx, int py, int dy, int b_row) {
+  int c = 0;
+  while (c < c_total) {
+    KBlk kb{};
+    const int wide = (c_total - c) >= 64 ? 1 : 0;
+    kb.a_c = static_cast<int16_t>(c);
+    kb.a_px = static_cast<int8_t>(px);
+    kb.a_dx = static_cast<int8_t>(dx);
+    kb.a_py = static_cast<int8_t>(py);
+    kb.a_dy = static_cast<int8_t>(dy);
+    kb.wide = static_cast<int8_t>(wide);
+    kb.b_k = static_cast<int16_t>(c);
+    kb.b_row = static_cast<int16_t>(b_row);
+    g.kb[g.nkb++] = kb;
+    c += wide ? 64 : 16;
+  }
+}
+
+// Builds the launch descriptions of one conv layer (needs resolved pointers).
+int build_conv(dsr_plan* p, ConvLayer& c) {
+  __half* warena = static_cast<__half*>(p->warena.ptr);
+  float* acc = reinterpret_cast<float*>(p->base);
+  int rc;
+  // ---------------- fprop ----------------
+  {
+    ConvGemmParams& g = c.fprop;
+    memset(&g, 0, sizeof(g));
+    const int Wp = c.inW + 2, Hp = c.inH + 2;
+    choose_tile(c.outW, g.tw, g.th);
+    if ((rc = make_act_map(&g.a16, c.in_pad->ptr, 1, c.cin_pad, Wp, Hp, c.stride, 16, g.tw, g.th))) return rc;
+    if (c.cin_pad >= 64) {
+      if ((rc = make_act_map(&g.a64, c.in_pad->ptr, 1, c.cin_pad, Wp, Hp, c.stride, 64, g.tw, g.th))) return rc;
+    } else {
+      g.a64 = g.a16;
+    }
+    const void* wf = warena + c.pack.f_off;
+    const int rows = c.k * c.k * kNC;
+    if ((rc = make_wgt_map(&g.b16, wf, c.cin_pad, rows, 16, kNC))) return rc;
+    if (c.cin_pad >= 64) {
+      if ((rc = make_wgt_map(&g.b64, wf, c.cin_pad, rows, 64, kNC))) return rc;
+    } else {
+      g.b64 = g.b16;
+    }
+    for (int ky = 0; ky < c.k; ++ky)
+      for (int kx = 0; kx < c.k; ++kx) {
+        int px = 0, dx = 1, py = 0, dy = 1;        // 1x1: interior pixel
+        if (c.k == 3) {
+          if (c.stride == 1) { dx = kx; dy = ky; } else { px = kx & 1; dx = kx >> 1; py = ky & 1; dy = ky >> 1; }
+        }
+        push_kblocks(g, c.cin_pad, px, dx, py, dy, (ky * c.k + kx) * kNC);
+      }
+    if (g.nkb > kMaxKBlocks) return -20;
+    g.tiles_x = (c.outW + g.tw - 1) / g.tw;
+    g.tiles_y = (c.outH + g.th - 1) / g.th;
+    g.out_h = c.outH;
+    g.out_w = c.outW;
+    g.out_sy = static_cast<long long>(c.outW) * kNC;
+    g.out_sx = kNC;
+    g.out = c.raw.ptr;
+    g.n_mma = kNC;
+    g.n_store = kNC;
+    g.out_bf16 = 0;
+    g.stats = acc + c.stats_off;
+    g.idesc = make_idesc_f16(128, kNC, FMT_F16, FMT_F16, 0, 0);
+    g.err = static_cast<int*>(p->errword.ptr);
+    c.ref_in = ActRef{static_cast<const uint16_t*>(c.in_pad->ptr), 0, c.cin_pad, Wp, Hp, c.stride};
+    c.ref_wf = WgtRef{reinterpret_cast<const uint16_t*>(wf), 0, c.cin_pad};
+  }
+  // ---------------- dgrad ----------------
+  c.ndgrad = 0;
+  if (c.need_dgrad) {
+    const int oWp = c.outW + 2, oHp = c.outH + 2;     // dR grid
+    const int iWp = c.inW + 2, iHp = c.inH + 2;       // output (input-gradient) grid
+    const void* wd = warena + c.pack.d_off;
+    const int rows = c.k * c.k * c.n_rows;
+    c.ref_dr = ActRef{static_cast<const uint16_t*>(c.dr.ptr), 1, kNC, oWp, oHp, 1};
+    c.ref_wd = WgtRef{reinterpret_cast<const uint16_t*>(wd), 0, kNC};
+    const int nclass = (c.stride == 1) ? 1 : 4;
+    for (int cls = 0; cls < nclass; ++cls) {
+      ConvGemmParams& g = c.dgrad[c.ndgrad++];
+      memset(&g, 0, sizeof(g));
+      const int ry = (c.stride == 1) ? 0 : (cls >> 1), rx = (c.stride == 1) ? 0 : (cls & 1);
+      const int step = c.stride;
+      g.out_h = (iHp - ry + step - 1) / step;
+      g.out_w = (iWp - rx + step - 1) / step;
+      choose_tile(g.out_w, g.tw, g.th);
+      if ((rc = make_act_map(&g.a64, c.dr.ptr, 1, kNC, oWp, oHp, 1, 64, g.tw, g.th))) return rc;
+      g.a16 = g.a64;
+      if ((rc = make_wgt_map(&g.b64, wd, kNC, rows, 64, c.n_rows))) return rc;
+      g.b16 = g.b64;
+      for (int ky = 0; ky < c.k; ++ky)
+        for (int kx = 0; kx < c.k; ++kx) {
+          int dx, dy;
+          if (c.k == 1) {
+            dx = 0; dy = 0;
+          } else if (c.stride == 1) {
+            dx = 1 - kx; dy = 1 - ky;
+          } else {
+            // padded input position q = 2 t + r receives output o = (q - k) / 2 when q - k is even
+            if (((ry - ky) & 1) || ((rx - kx) & 1)) continue;
+            dy = (ry - ky) / 2 + 1;      // (q - k)/2 + 1 = t + (r - k)/2 + 1   [(r-k) even, in {-2, 0}]
+            dx = (rx - kx) / 2 + 1;
+          }
+          push_kblocks(g, kNC, 0, dx, 0, dy, (ky * c.k + kx) * c.n_rows);
+        }
+      g.tiles_x = (g.out_w + g.tw - 1) / g.tw;
+      g.tiles_y = (g.out_h + g.th - 1) / g.th;
+      g.out_sy = static_cast<long long>(iWp) * c.n_rows * step;
+      g.out_sx = static_cast<long long>(c.n_rows) * step;
+      g.out = static_cast<uint16_t*>(c.gin.ptr) + (static_cast<long long>(ry) * iWp + rx) * c.n_rows;
+      g.n_mma = c.n_rows;
+      g.n_store = c.n_rows;
+      g.out_bf16 = 1;
+      g.stats = nullptr;
+      g.idesc = make_idesc_f16(128, c.n_rows, FMT_BF16, FMT_F16, 0, 0);
+      g.err = static_cast<int*>(p->errword.ptr);
+    }
+  }
+  // ---------------- wgrad ----------------
+  {
+    WgradParams& g = c.wgrad;
+    memset(&g, 0, sizeof(g));
+    g.pw = 8;
+    while (g.pw > 1 && g.pw / 2 >= c.outW) g.pw /= 2;
+    g.ph = kWgPix / g.pw;
+    if ((rc = make_act_map(&g.a64, c.dr.ptr, 1, kNC, c.outW + 2, c.outH + 2, 1, 64, g.pw, g.ph))) return rc;
+    const int Wp = c.inW + 2, Hp = c.inH + 2;
+    if ((rc = make_act_map(&g.b16, c.in_pad->ptr, 1, c.cin_pad, Wp, Hp, c.stride, 16, g.pw, g.ph))) return rc;
+    if (c.cin_pad >= 64) {
+      if ((rc = make_act_map(&g.b64, c.in_pad->ptr, 1, c.cin_pad, Wp, Hp, c.stride, 64, g.pw, g.ph))) return rc;
+    } else {
+      g.b64 = g.b16;
+    }
+    g.n64 = (c.cin_pad >= 64) ? 2 : 0;
+    g.n16 = (c.cin_pad - g.n64 * 64) / 16;
+    g.c16_base = g.n64 * 64;
+    if (g.n16 > 2 || (g.n64 == 2 && g.n16 > 1)) return -21;
+    if (c.k == 1) {
+      g.ngroups = 1;
+      g.ntaps = 1;
+      g.taps[0][0] = WgTap{0, 1, 0, 1, 0, 0};
+    } else {
+      g.ngroups = 3;
+      g.ntaps = 3;
+      for (int ky = 0; ky < 3; ++ky)
+        for (int kx = 0; kx < 3; ++kx) {
+          WgTap t{};
+          if (c.stride == 1) {
+            t.px = 0; t.dx = static_cast<int8_t>(kx); t.py = 0; t.dy = static_cast<int8_t>(ky);
+          } else {
+            t.px = static_cast<int8_t>(kx & 1); t.dx = static_cast<int8_t>(kx >> 1);
+            t.py = static_cast<int8_t>(ky & 1); t.dy = static_cast<int8_t>(ky >> 1);
+          }
+          t.w_tap = static_cast<int16_t>(ky * 3 + kx);
+          g.taps[ky][kx] = t;
+        }
+    }
+    g.pb_x = (c.outW + g.pw - 1) / g.pw;
+    g.pb_y = (c.outH + g.ph - 1) / g.ph;
+    const int npb = g.pb_x * g.pb_y;
+    int nsplit = p->num_sms / g.ngroups;
+    if (nsplit > npb) nsplit = npb;
+    if (nsplit < 1) nsplit = 1;
+    g.nsplit = nsplit;
+    g.ldw = c.cin_pad;
+    g.dw = acc + p->garena_off + c.pack.g_off;
+    g.idesc64 = make_idesc_f16(128, 128, FMT_BF16, FMT_F16, 1, 1);
+    g.idesc16 = make_idesc_f16(128, 16, FMT_BF16, FMT_F16, 1, 1);
+    g.err = static_cast<int*>(p->errword.ptr);
+  }
+  return 0;
+}
+
+BnRef conv_bn(const dsr_plan* p, const ConvLayer& c, const float* params) {
+  BnRef b;
+  b.stats = reinterpret_cast<const float*>(p->base) + c.stats_off;
+  b.gamma = params + c.g_off;
+  b.beta = params + c.be_off;
+  b.inv_n = 1.f / (static_cast<float>(c.outH) * static_cast<float>(c.outW));
+  b.cstride = kNC;
+  return b;
+}
+BnRef skip_bn(const dsr_plan* p, const Level& L, const float* params) {
+  BnRef b;
+  b.stats = reinterpret_cast<const float*>(p->base) + L.skip_stats_off;
+  b.gamma = params + L.skip_g;
+  b.beta = params + L.skip_be;
+  b.inv_n = 1.f / (static_cast<float>(L.H) * static_cast<float>(L.W));
+  b.cstride = kNS;
+  return b;
+}
+
+#define DSR_TRY(expr)                    \
+  do {                                   \
+    int rc__ = (expr);                   \
+    ++p->launches;                       \
+    if (rc__ != 0) return rc__;          \
+  } while (0)
+
+int run_fprop(dsr_plan* p, ConvLayer& c, cudaStream_t s) {
+  if (p->debug_conv) return launch_conv_ref(c.fprop, c.ref_in, c.ref_wf, s);
+  return launch_conv_gemm(c.fprop, p->num_sms, s);
+}
+int run_dgrad(dsr_plan* p, ConvLayer& c, int i, cudaStream_t s) {
+  if (p->debug_conv) return launch_conv_ref(c.dgrad[i], c.ref_dr, c.ref_wd, s);
+  return launch_conv_gemm(c.dgrad[i], p->num_sms, s);
+}
+int run_wgrad(dsr_plan* p, ConvLayer& c, cudaStream_t s) {
+  if (p->debug_conv) return launch_wgrad_ref(c.wgrad, c.ref_dr, c.ref_in, s);
+  return launch_wgrad(c.wgrad, s);
+}
+
+int conv_bn_act(dsr_plan* p, ConvLayer& c, const float* params, cudaStream_t s) {
+  DSR_TRY(run_fprop(p, c, s));
+  DSR_TRY(launch_bn_act(c.raw.ptr, conv_bn(p, c, params), c.act.ptr, c.outH, c.outW, c.act_halo, s));
+  return 0;
+}
+
+UpcatArgs upcat_args(dsr_plan* p, int i, const float* params) {
+  Level& L = p->lv[i];
+  const bool last = (i + 1 == p->num_scales);
+  const Buf& deep = last ? L.d2.act : p->lv[i + 1].u2.act;
+  UpcatArgs a{};
+  a.deep = static_cast<const __half*>(deep.ptr) + (static_cast<long long>(L.w + 2) + 1) * kNC;
+  a.deep_sy = static_cast<long long>(L.w + 2) * kNC;
+  a.h = L.h;
+  a.w = L.w;
+  a.H = L.H;
+  a.W = L.W;
+  a.sraw = static_cast<const float*>(L.sraw.ptr);
+  a.bn_skip = skip_bn(p, L, params);
+  a.cat_stats = reinterpret_cast<float*>(p->base) + L.cat_stats_off;
+  a.cat_gamma = params + L.cat_g;
+  a.cat_beta = params + L.cat_be;
+  a.cat_pad = L.cat.ptr;
+  return a;
+}
+
+int forward_level(dsr_plan* p, int i, const float* params, cudaStream_t s) {
+  Level& L = p->lv[i];
+  float* acc = reinterpret_cast<float*>(p->base);
+  DSR_TRY(launch_skip_conv(L.x_pad->ptr, L.Cin, params + L.skip_w, static_cast<float*>(L.sraw.ptr),
+                           acc + L.skip_stats_off, L.H, L.W, s));
+  int rc;
+  if ((rc = conv_bn_act(p, L.d1, params, s))) return rc;
+  if ((rc = conv_bn_act(p, L.d2, params, s))) return rc;
+  if (i + 1 < p->num_scales && (rc = forward_level(p, i + 1, params, s))) return rc;
+  const UpcatArgs a = upcat_args(p, i, params);
+  DSR_TRY(launch_upcat_stats(a, s));
+  DSR_TRY(launch_upcat_apply(a, s));
+  if ((rc = conv_bn_act(p, L.u1, params, s))) return rc;
+  if ((rc = conv_bn_act(p, L.u2, params, s))) return rc;
+  return 0;
+}
+
+int bn_backward(dsr_plan* p, ConvLayer& c, const float* params, float* grads, const void* g, int gC, int fold,
+                const float* ds, const float* wskip, cudaStream_t s) {
+  BnBwdArgs a{};
+  a.g = g;
+  a.gC = gC;
+  a.fold = fold;
+  a.ds = ds;
+  a.wskip = wskip;
+  a.raw = c.raw.ptr;
+  a.bn = conv_bn(p, c, params);
+  a.bstats = reinterpret_cast<float*>(p->base) + c.bstats_off;
+  a.dr_pad = c.dr.ptr;
+  a.dgamma = grads + c.g_off;
+  a.dbeta = grads + c.be_off;
+  a.H = c.outH;
+  a.W = c.outW;
+  DSR_TRY(launch_bn_bwd_stats(a, s));
+  DSR_TRY(launch_bn_bwd_apply(a, s));
+  return 0;
+}
+
+int conv_backward(dsr_plan* p, ConvLayer& c, cudaStream_t s) {
+  DSR_TRY(run_wgrad(p, c, s));
+  for (int i = 0; i < c.ndgrad; ++i) DSR_TRY(run_dgrad(p, c, i, s));
+  return 0;
+}
+
+int backward_level(dsr_plan* p, int i, const float* params, float* grads, cudaStream_t s) {
+  Level& L = p->lv[i];
+  const bool last = (i + 1 == p->num_scales);
+  float* acc = reinterpret_cast<float*>(p->base);
+  int rc;
+  // ---- decoder ----
+  if ((rc = bn_backward(p, L.u2, params, grads, L.g_u2a.ptr, kNC, 0, nullptr, nullptr, s))) return rc;
+  if ((rc = conv_backward(p, L.u2, s))) return rc;
+  if ((rc = bn_backward(p, L.u1, params, grads, L.u2.gin.ptr, kNC, 0, nullptr, nullptr, s))) return rc;
+  if ((rc = conv_backward(p, L.u1, s))) return rc;
+  UpcatBwdArgs ub{};
+  ub.f = upcat_args(p, i, params);
+  ub.gcat = L.u1.gin.ptr;
+  ub.cbstats = acc + L.cbstats_off;
+  ub.dup_pad = L.dup.ptr;
+  ub.dsy = static_cast<float*>(L.dsy.ptr);
+  ub.sbstats = acc + L.sbstats_off;
+  ub.dcat_gamma = grads + L.cat_g;
+  ub.dcat_beta = grads + L.cat_be;
+  DSR_TRY(launch_upcat_bwd_stats(ub, s));
+  DSR_TRY(launch_upcat_bwd_apply(ub, s));
+  DSR_TRY(launch_skip_bwd(static_cast<const float*>(L.dsy.ptr), static_cast<const float*>(L.sraw.ptr),
+                          skip_bn(p, L, params), acc + L.sbstats_off, L.x_pad->ptr, L.Cin,
+                          static_cast<float*>(L.dsraw.ptr), grads + L.skip_w, grads + L.skip_g, grads + L.skip_be, L.H,
+                          L.W, s));
+  void* ddeep = last ? L.g_d2a.ptr : p->lv[i + 1].g_u2a.ptr;
+  DSR_TRY(launch_upsample_bwd(L.dup.ptr, L.H, L.W, ddeep, L.h, L.w, s));
+  if (!last && (rc = backward_level(p, i + 1, params, grads, s))) return rc;
+  // ---- encoder ----
+  if (last) {
+    rc = bn_backward(p, L.d2, params, grads, L.g_d2a.ptr, kNC, 0, nullptr, nullptr, s);
+  } else {
+    Level& N = p->lv[i + 1];
+    rc = bn_backward(p, L.d2, params, grads, N.d1.gin.ptr, kNC, 1, static_cast<const float*>(N.dsraw.ptr),
+                     params + N.skip_w, s);
+  }
+  if (rc) return rc;
+  if ((rc = conv_backward(p, L.d2, s))) return rc;
+  if ((rc = bn_backward(p, L.d1, params, grads, L.d2.gin.ptr, kNC, 1, nullptr, nullptr, s))) return rc;
+  if ((rc = conv_backward(p, L.d1, s))) return rc;
+  return 0;
+}
+
+void reg_tensor(dsr_plan* p, const std::string& name, const Buf* b, int kind, int padded, int H, int W, int C) {
+  p->tensors.push_back(TensorInfo{name, b, 0, kind, padded, H, W, C});
+}
+void reg_acc(dsr_plan* p, const std::string& name, size_t acc_off, int H, int W, int C) {
+  p->tensors.push_back(TensorInfo{name, nullptr, acc_off, 2, 0, H, W, C});
+}
+
+}  // namespace
+}  // namespace dsr
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+int dsr_abi_version(void) { return 1; }
+
+const char* dsr_error_string(int code) {
+  if (code == 0) return "ok";
+  if (code > 0) return cudaGetErrorString(static_cast<cudaError_t>(code));
+  switch (code) {
+    case -1: return "bad argument";
+    case -2: return "unsupported channel count";
+    case -3: return "misaligned buffer";
+    case -4: return "downsampler tile does not fit shared memory";
+    case -5: return "unsupported network configuration";
+    case -6: return "plan is not bound to a workspace";
+    case -7: return "backward called without a preceding forward";
+    case -8: return "workspace too small";
+    case -20: return "too many K blocks";
+    case -21: return "unsupported channel split";
+    case -100: return "cuTensorMapEncodeTiled unavailable";
+    default: return (code <= -200) ? "cuTensorMapEncodeTiled failed" : "unknown error";
+  }
+}
+
+// ---- Lanczos -----------------------------------------------------------------------------------
+int dsr_lanczos_kernel(int factor, int support, double* host_kernel, int capacity) {
+  if (factor < 1 || (support != 2 && support != 3) || host_kernel == nullptr) return -1;
+  std::vector<double> t;
+  lanczos_taps(factor, support, t);
+  const int k = static_cast<int>(t.size());
+  if (capacity < k * k) return -1;
+  // get_kernel normalises the 2-D table by its sum (utils/downsampler.py:133); the taps are
+  // already normalised to sum 1 so the outer product sums to 1 up to rounding; renormalise the
+  // product exactly as the reference does.
+  double sum = 0.0;
+  for (int i = 0; i < k; ++i)
+    for (int j = 0; j < k; ++j) {
+      host_kernel[i * k + j] = t[i] * t[j];
+      sum += host_kernel[i * k + j];
+    }
+  for (int i = 0; i < k * k; ++i) host_kernel[i] /= sum;
+  return k;
+}
+
+static int ds_geometry(int factor, int support, int H, int W, int& k, int& pad, int& oh, int& ow) {
+  if (factor < 1 || (support != 2 && support != 3) || H < 1 || W < 1) return -1;
+  k = 2 * support * factor;
+  pad = (k - factor) / 2;                       // utils/downsampler.py:56-59 (even kernel size)
+  oh = (H + 2 * pad - k) / factor + 1;
+  ow = (W + 2 * pad - k) / factor + 1;
+  if (oh < 1 || ow < 1) return -1;
+  return 0;
+}
+
+size_t dsr_downsampler_table_bytes(int factor, int support, int H, int W) {
+  int k, pad, oh, ow;
+  if (ds_geometry(factor, support, H, W, k, pad, oh, ow)) return 0;
+  // generous bound: taps + per-row / per-column (index + up to k/f + 2 weights)
+  const size_t nwmax = static_cast<size_t>(k) + 2;
+  return 1024 + 4 * (static_cast<size_t>(k) + (H + W) * (1 + nwmax));
+}
+
+int dsr_downsampler_create(dsr_downsampler_t** out, int factor, int support, int H, int W, void* table_ws,
+                           size_t table_bytes, void* stream) {
+  if (out == nullptr || table_ws == nullptr) return -1;
+  int k, pad, oh, ow;
+  if (ds_geometry(factor, support, H, W, k, pad, oh, ow)) return -1;
+  dsr_downsampler* d = new dsr_downsampler();
+  d->factor = factor; d->support = support; d->H = H; d->W = W; d->oh = oh; d->ow = ow; d->k = k; d->pad = pad;
+  std::vector<double> t64;
+  lanczos_taps(factor, support, t64);
+  // The reference casts the normalised 2-D float64 table to fp32 (utils/downsampler.py:48-50); the separable
+  // evaluation uses fp32 1-D taps, whose products differ from the cast 2-D entries by <= 1 ulp each.
+  d->taps.resize(k);
+  for (int i = 0; i < k; ++i) d->taps[i] = static_cast<float>(t64[i]);
+  ds_bwd_table(H, oh, factor, k, pad, d->taps, d->nw_y, d->by0, d->bwy);
+  ds_bwd_table(W, ow, factor, k, pad, d->taps, d->nw_x, d->bx0, d->bwx);
+  // the kernel uses one nw for both axes: widen the narrower table
+  const int nw = d->nw_y > d->nw_x ? d->nw_y : d->nw_x;
+  auto widen = [nw](std::vector<float>& w, int n, int old) {
+    if (old == nw) return;
+    std::vector<float> r(static_cast<size_t>(n) * nw, 0.f);
+    for (int i = 0; i < n; ++i)
+      for (int a = 0; a < old; ++a) r[static_cast<size_t>(i) * nw + a] = w[static_cast<size_t>(i) * old + a];
+    w.swap(r);
+  };
+  widen(d->bwy, H, d->nw_y);
+  widen(d->bwx, W, d->nw_x);
+  const size_t need = 4 * (static_cast<size_t>(k) + H + W + static_cast<size_t>(H + W) * nw) + 256;
+  if (need > table_bytes) { delete d; return -8; }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  char* base = static_cast<char*>(table_ws);
+  size_t off = 0;
+  auto put = [&](const void* src, size_t bytes) -> void* {
+    void* dst = base + off;
+    cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s);
+    off = align_up(off + bytes, 16);
+    return dst;
+  };
+  d->t.taps = static_cast<const float*>(put(d->taps.data(), 4 * static_cast<size_t>(k)));
+  d->t.by0 = static_cast<const int*>(put(d->by0.data(), 4 * static_cast<size_t>(H)));
+  d->t.bwy = static_cast<const float*>(put(d->bwy.data(), 4 * static_cast<size_t>(H) * nw));
+  d->t.bx0 = static_cast<const int*>(put(d->bx0.data(), 4 * static_cast<size_t>(W)));
+  d->t.bwx = static_cast<const float*>(put(d->bwx.data(), 4 * static_cast<size_t>(W) * nw));
+  d->t.k = k; d->t.factor = factor; d->t.pad = pad; d->t.nw = nw;
+  cudaError_t e = cudaStreamSynchronize(s);     // host vectors are pageable: make the upload complete here
+  if (e != cudaSuccess) { delete d; return static_cast<int>(e); }
+  *out = d;
+  return 0;
+}
+
+void dsr_downsampler_destroy(dsr_downsampler_t* d) { delete d; }
+
+int dsr_downsample_fwd(const dsr_downsampler_t* d, const float* x, float* y, int C, void* stream) {
+  if (!d || !x || !y || C < 1) return -1;
+  return launch_downsample_fwd(x, y, C, d->H, d->W, d->oh, d->ow, d->t, static_cast<cudaStream_t>(stream));
+}
+int dsr_downsample_bwd(const dsr_downsampler_t* d, const float* gy, float* gx, int C, void* stream) {
+  if (!d || !gy || !gx || C < 1) return -1;
+  return launch_downsample_bwd(gy, gx, C, d->H, d->W, d->oh, d->ow, d->t, static_cast<cudaStream_t>(stream));
+}
+int dsr_downsample_mse(const dsr_downsampler_t* d, const float* x, const float* target, float* y, float* gy,
+                       float* loss, int C, void* stream) {
+  if (!d || !x || !target || !y || !gy || !loss || C < 1) return -1;
+  return launch_downsample_mse(x, target, y, gy, loss, C, d->H, d->W, d->oh, d->ow, d->t,
+                               static_cast<cudaStream_t>(stream));
+}
+
+// ---- plan ---------------------------------------------------------------------------------------
+int dsr_plan_create(dsr_plan_t** out, int H, int W, int input_depth, int num_scales, int n_out) {
+  if (out == nullptr) return -1;
+  if (num_scales < 1 || num_scales > 6 || n_out != 3) return -5;
+  if (input_depth != 32 && input_depth != 128) return -5;
+  const int m = 1 << num_scales;
+  if (H < m || W < m || (H % m) != 0 || (W % m) != 0) return -5;   // centre-crop / odd levels: not yet
+  dsr_plan* p = new dsr_plan();
+  p->H = H; p->W = W; p->input_depth = input_depth; p->num_scales = num_scales; p->n_out = n_out;
+  p->lv.resize(num_scales);
+  for (int i = 0; i < num_scales; ++i) {
+    Level& L = p->lv[i];
+    L.H = H >> i; L.W = W >> i; L.h = L.H / 2; L.w = L.W / 2;
+    L.Cin = (i == 0) ? input_depth : kNC;
+  }
+  name_level(p, 0);
+  add_conv_params(p, "9.1", p->fin_w, p->fin_b, n_out, kNC, 1);
+
+  Bump ws, accf, accb;
+  size_t warena_elems = 0, garena_floats = 0;
+  // Accumulator blocks are laid out first (their offsets are float indices from the workspace base).
+  // Sizes are only known after the layer walk, so walk with separate bump allocators and place them after.
+  for (int i = 0; i < num_scales; ++i) {
+    Level& L = p->lv[i];
+    const bool last = (i + 1 == num_scales);
+    if (i == 0) {
+      ws.take(L.xin, static_cast<size_t>(L.H + 2) * (L.W + 2) * L.Cin * 2);
+      L.x_pad = &L.xin;
+    } else {
+      L.x_pad = &p->lv[i - 1].d2.act;
+    }
+    ws.take(L.sraw, static_cast<size_t>(L.H) * L.W * kNS * 4);
+    ws.take(L.cat, static_cast<size_t>(L.H + 2) * (L.W + 2) * kCat * 2);
+    ws.take(L.g_u2a, static_cast<size_t>(L.H + 2) * (L.W + 2) * kNC * 2);
+    ws.take(L.dup, static_cast<size_t>(L.H + 2) * (L.W + 2) * kNC * 2);
+    ws.take(L.dsy, static_cast<size_t>(L.H) * L.W * kNS * 4);
+    ws.take(L.dsraw, static_cast<size_t>(L.H) * L.W * kNS * 4);
+    if (last) ws.take(L.g_d2a, static_cast<size_t>(L.h + 2) * (L.w + 2) * kNC * 2);
+    L.skip_stats_off = accf.take_floats(2 * kNS);
+    L.cat_stats_off = accf.take_floats(2 * kCat);
+    L.sbstats_off = accb.take_floats(2 * kNS);
+    L.cbstats_off = accb.take_floats(2 * kCat);
+    setup_conv(p, ws, accf, accb, L.d1, "d1", L.Cin, L.Cin, 3, 2, L.H, L.W, L.x_pad, i > 0, 1, 0, warena_elems,
+               garena_floats);
+    setup_conv(p, ws, accf, accb, L.d2, "d2", kNC, kNC, 3, 1, L.h, L.w, &L.d1.act, true, 1, 0, warena_elems,
+               garena_floats);
+    setup_conv(p, ws, accf, accb, L.u1, "u1", kNS + kNC, kCat, 3, 1, L.H, L.W, &L.cat, true, 0, 1, warena_elems,
+               garena_floats);
+    setup_conv(p, ws, accf, accb, L.u2, "u2", kNC, kNC, 1, 1, L.H, L.W, &L.u1.act, true, 0, 0, warena_elems,
+               garena_floats);
+  }
+  ws.take(p->warena, warena_elems * 2);
+  ws.take(p->pack_table, sizeof(PackDesc) * 4 * num_scales);
+  ws.take(p->bnrun_table, sizeof(BnRunDesc) * 6 * num_scales);
+  ws.take(p->errword, 256);
+  // place the accumulator blocks
+  ws.off = align_up(ws.off, 1024);
+  p->acc_fwd_off = ws.off;
+  p->acc_fwd_floats = align_up(accf.off, 1024) / 4;
+  ws.off += p->acc_fwd_floats * 4;
+  p->acc_bwd_off = ws.off;
+  const size_t accb_floats = align_up(accb.off, 1024) / 4;
+  p->garena_off = p->acc_bwd_off / 4 + accb_floats;
+  p->acc_bwd_floats = accb_floats + garena_floats;
+  ws.off += p->acc_bwd_floats * 4;
+  p->ws_bytes = align_up(ws.off, 1024);
+  // rebase accumulator indices to the workspace base
+  const size_t fbase = p->acc_fwd_off / 4, bbase = p->acc_bwd_off / 4;
+  for (Level& L : p->lv) {
+    L.skip_stats_off += fbase; L.cat_stats_off += fbase;
+    L.sbstats_off += bbase; L.cbstats_off += bbase;
+    for (ConvLayer* c : {&L.d1, &L.d2, &L.u1, &L.u2}) { c->stats_off += fbase; c->bstats_off += bbase; }
+  }
+  // tables
+  for (Level& L : p->lv)
+    for (ConvLayer* c : {&L.d1, &L.d2, &L.u1, &L.u2}) {
+      c->pack.w_off = c->w_off;
+      p->pack_host.push_back(c->pack);
+    }
+  for (Level& L : p->lv) {
+    auto add_run = [&](size_t stats_off, int cstride, int C, float n, long long bn_off, long long bias_off, int perm) {
+      BnRunDesc d{};
+      d.stats_off = static_cast<long long>(stats_off);
+      d.cstride = cstride; d.C = C; d.n = n;
+      d.rm_off = bn_off; d.rv_off = bn_off + C;
+      d.bias_off = bias_off; d.perm = perm;
+      p->bnrun_host.push_back(d);
+    };
+    add_run(L.skip_stats_off, kNS, kNS, static_cast<float>(L.H) * L.W, L.skip_bn, L.skip_b, 0);
+    add_run(L.cat_stats_off, kCat, kNS + kNC, static_cast<float>(L.H) * L.W, L.cat_bn, -1, 1);
+    for (ConvLayer* c : {&L.d1, &L.d2, &L.u1, &L.u2})
+      add_run(c->stats_off, kNC, kNC, static_cast<float>(c->outH) * c->outW, c->bn_off, c->b_off, 0);
+  }
+  // introspection table
+  for (int i = 0; i < num_scales; ++i) {
+    Level& L = p->lv[i];
+    const std::string P = "L" + std::to_string(i) + ".";
+    reg_tensor(p, P + "x", L.x_pad, 0, 1, L.H, L.W, L.Cin);
+    reg_tensor(p, P + "sraw", &L.sraw, 2, 0, L.H, L.W, kNS);
+    reg_tensor(p, P + "cat", &L.cat, 0, 1, L.H, L.W, kCat);
+    reg_tensor(p, P + "g_u2a", &L.g_u2a, 1, 1, L.H, L.W, kNC);
+    reg_tensor(p, P + "dup", &L.dup, 1, 1, L.H, L.W, kNC);
+    reg_tensor(p, P + "dsy", &L.dsy, 2, 0, L.H, L.W, kNS);
+    reg_tensor(p, P + "dsraw", &L.dsraw, 2, 0, L.H, L.W, kNS);
+    if (i + 1 == num_scales) reg_tensor(p, P + "g_d2a", &L.g_d2a, 1, 1, L.h, L.w, kNC);
+    for (ConvLayer* c : {&L.d1, &L.d2, &L.u1, &L.u2}) {
+      const std::string T = P + c->tag;
+      reg_tensor(p, T + "_raw", &c->raw, 0, 0, c->outH, c->outW, kNC);
+      reg_tensor(p, T + "_act", &c->act, 0, 1, c->outH, c->outW, kNC);
+      reg_tensor(p, T + "_dr", &c->dr, 1, 1, c->outH, c->outW, kNC);
+      if (c->need_dgrad) reg_tensor(p, T + "_gin", &c->gin, 1, 1, c->inH, c->inW, c->n_rows);
+      reg_acc(p, T + "_stats", c->stats_off, 1, 2, kNC);
+      reg_acc(p, T + "_dw", p->garena_off + c->pack.g_off, c->k * c->k, kNC, c->cin_pad);
+    }
+  }
+  *out = p;
+  return 0;
+}
+
+void dsr_plan_destroy(dsr_plan_t* p) { delete p; }
+
+int dsr_plan_num_params(const dsr_plan_t* p) { return p ? static_cast<int>(p->params.size()) : -1; }
+long long dsr_plan_param_numel(const dsr_plan_t* p) { return p ? p->nparam : -1; }
+int dsr_plan_param_info(const dsr_plan_t* p, int idx, char* name, int name_cap, long long* offset, int* ndim,
+                        int* shape4) {
+  if (!p || idx < 0 || idx >= static_cast<int>(p->params.size())) return -1;
+  const ParamInfo& pi = p->params[idx];
+  if (name && name_cap > 0) snprintf(name, static_cast<size_t>(name_cap), "%s", pi.name.c_str());
+  if (offset) *offset = pi.off;
+  if (ndim) *ndim = pi.ndim;
+  if (shape4) for (int i = 0; i < 4; ++i) shape4[i] = pi.shape[i];
+  return 0;
+}
+int dsr_plan_num_bn(const dsr_plan_t* p) { return p ? static_cast<int>(p->bns.size()) : -1; }
+long long dsr_plan_bn_numel(const dsr_plan_t* p) { return p ? p->nbn : -1; }
+int dsr_plan_bn_info(const dsr_plan_t* p, int idx, char* name, int name_cap, long long* offset, int* channels) {
+  if (!p || idx < 0 || idx >= static_cast<int>(p->bns.size())) return -1;
+  const BnInfo& bi = p->bns[idx];
+  if (name && name_cap > 0) snprintf(name, static_cast<size_t>(name_cap), "%s", bi.name.c_str());
+  if (offset) *offset = bi.off;
+  if (channels) *channels = bi.C;
+  return 0;
+}
+size_t dsr_plan_workspace_bytes(const dsr_plan_t* p) { return p ? p->ws_bytes : 0; }
+
+int dsr_plan_bind(dsr_plan_t* p, void* workspace, size_t bytes, void* stream) {
+  if (!p || !workspace) return -1;
+  if (bytes < p->ws_bytes) return -8;
+  if (reinterpret_cast<uintptr_t>(workspace) & 1023) return -3;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  p->base = static_cast<char*>(workspace);
+  cudaError_t e = cudaMemsetAsync(workspace, 0, p->ws_bytes, s);   // zero halos of gradient tensors, pad channels
+  if (e != cudaSuccess) return static_cast<int>(e);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, dev);
+  if (p->num_sms < 1) p->num_sms = 148;
+  auto resolve = [p](Buf& b) { b.ptr = b.bytes ? p->base + b.off : nullptr; };
+  for (Level& L : p->lv) {
+    resolve(L.xin); resolve(L.sraw); resolve(L.cat); resolve(L.g_u2a); resolve(L.dup); resolve(L.dsy);
+    resolve(L.dsraw); resolve(L.g_d2a);
+    for (ConvLayer* c : {&L.d1, &L.d2, &L.u1, &L.u2}) { resolve(c->raw); resolve(c->act); resolve(c->dr); resolve(c->gin); }
+  }
+  resolve(p->warena); resolve(p->pack_table); resolve(p->bnrun_table); resolve(p->errword);
+  e = cudaMemcpyAsync(p->pack_table.ptr, p->pack_host.data(), sizeof(PackDesc) * p->pack_host.size(),
+                      cudaMemcpyHostToDevice, s);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  e = cudaMemcpyAsync(p->bnrun_table.ptr, p->bnrun_host.data(), sizeof(BnRunDesc) * p->bnrun_host.size(),
+                      cudaMemcpyHostToDevice, s);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  for (Level& L : p->lv)
+    for (ConvLayer* c : {&L.d1, &L.d2, &L.u1, &L.u2}) {
+      int rc = build_conv(p, *c);
+      if (rc) return rc;
+    }
+  p->bound = true;
+  p->have_forward = false;
+  return 0;
+}
+
+int dsr_net_forward(dsr_plan_t* p, const float* params, const float* z, float* out, float* bn_buffers, void* stream) {
+  if (!p || !params || !z || !out) return -1;
+  if (!p->bound) return -6;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  p->launches = 0;
+  cudaError_t e = cudaMemsetAsync(p->base + p->acc_fwd_off, 0, p->acc_fwd_floats * 4, s);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  DSR_TRY(launch_pack_weights(params, p->warena.ptr, static_cast<const PackDesc*>(p->pack_table.ptr),
+                              static_cast<int>(p->pack_host.size()), s));
+  Level& L0 = p->lv[0];
+  DSR_TRY(launch_input_pack(z, L0.xin.ptr, L0.Cin, L0.H, L0.W, s));
+  int rc = forward_level(p, 0, params, s);
+  if (rc) return rc;
+  DSR_TRY(launch_final_conv(L0.u2.act.ptr, params + p->fin_w, params + p->fin_b, out, L0.H, L0.W, s));
+  if (bn_buffers != nullptr)
+    DSR_TRY(launch_bn_running(static_cast<const BnRunDesc*>(p->bnrun_table.ptr), static_cast<int>(p->bnrun_host.size()),
+                              reinterpret_cast<const float*>(p->base), params, bn_buffers, kMomentum, s));
+  p->have_forward = true;
+  return 0;
+}
+
+int dsr_net_backward(dsr_plan_t* p, const float* params, const float* out, const float* grad_out, float* grads,
+                     void* stream) {
+  if (!p || !params || !out || !grad_out || !grads) return -1;
+  if (!p->bound) return -6;
+  if (!p->have_forward) return -7;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  p->launches = 0;
+  cudaError_t e = cudaMemsetAsync(p->base + p->acc_bwd_off, 0, p->acc_bwd_floats * 4, s);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  e = cudaMemsetAsync(grads, 0, static_cast<size_t>(p->nparam) * 4, s);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  Level& L0 = p->lv[0];
+  DSR_TRY(launch_final_bwd(grad_out, out, L0.u2.act.ptr, params + p->fin_w, L0.g_u2a.ptr, grads + p->fin_w,
+                           grads + p->fin_b, L0.H, L0.W, s));
+  int rc = backward_level(p, 0, params, grads, s);
+  if (rc) return rc;
+  DSR_TRY(launch_unpack_wgrad(reinterpret_cast<const float*>(p->base) + p->garena_off, grads,
+                              static_cast<const PackDesc*>(p->pack_table.ptr), static_cast<int>(p->pack_host.size()),
+                              s));
+  return 0;
+}
+
+int dsr_adam_step(float* pp, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                  float eps, int t, void* stream) {
+  if (!pp || !g || !m || !v || n < 0 || t < 1) return -1;
+  return launch_adam(pp, g, m, v, n, lr, beta1, beta2, eps, t, static_cast<cudaStream_t>(stream));
+}
+
+int dsr_perturb(const float* z_saved, float* z, long long n, float sigma, unsigned long long seed,
+                unsigned long long offset, void* stream) {
+  if (!z_saved || !z || n < 0) return -1;
+  return launch_perturb(z_saved, z, n, sigma, seed, offset, static_cast<cudaStream_t>(stream));
+}
+
+int dsr_dip_step(dsr_plan_t* p, const dsr_downsampler_t* d, const dsr_step_buffers_t* b, float lr, float sigma,
+                 unsigned long long seed, int t, void* stream) {
+  if (!p || !d || !b || t < 1) return -1;
+  if (d->H != p->H || d->W != p->W) return -1;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const long long nz = static_cast<long long>(p->input_depth) * p->H * p->W;
+  int total = 0;
+  int rc = launch_perturb(b->z_saved, b->z, nz, sigma, seed, static_cast<unsigned long long>(t - 1) * ((nz + 3) / 4), s);
+  if (rc) return rc;
+  ++total;
+  if ((rc = dsr_net_forward(p, b->params, b->z, b->out_hr, b->bn_buffers, stream))) return rc;
+  total += p->launches;
+  cudaError_t e = cudaMemsetAsync(b->loss_out, 0, 4, s);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  if ((rc = launch_downsample_mse(b->out_hr, b->lr_image, b->out_lr, b->g_out_lr, b->loss_out, p->n_out, d->H, d->W,
+                                  d->oh, d->ow, d->t, s)))
+    return rc;
+  if ((rc = launch_downsample_bwd(b->g_out_lr, b->g_out_hr, p->n_out, d->H, d->W, d->oh, d->ow, d->t, s))) return rc;
+  total += 2;
+  if ((rc = dsr_net_backward(p, b->params, b->out_hr, b->g_out_hr, b->grads, stream))) return rc;
+  total += p->launches;
+  if ((rc = launch_adam(b->params, b->grads, b->adam_m, b->adam_v, p->nparam, lr, 0.9f, 0.999f, 1e-8f, t, s)))
+    return rc;
+  p->launches = total + 1;
+  return 0;
+}
+
+// ---- introspection ------------------------------------------------------------------------------
+int dsr_plan_tensor(const dsr_plan_t* p, const char* name, void** ptr, int* kind, int* padded, int* H, int* W,
+                    int* C) {
+  if (!p || !name) return -1;
+  for (const TensorInfo& t : p->tensors)
+    if (t.name == name) {
+      if (ptr) *ptr = t.buf ? t.buf->ptr : static_cast<void*>(reinterpret_cast<float*>(p->base) + t.acc_off);
+      if (kind) *kind = t.kind;
+      if (padded) *padded = t.padded;
+      if (H) *H = t.H;
+      if (W) *W = t.W;
+      if (C) *C = t.C;
+      return 0;
+    }
+  return -1;
+}
+int dsr_plan_last_launches(const dsr_plan_t* p) { return p ? p->launches : -1; }
+int dsr_plan_set_debug_conv(dsr_plan_t* p, int use_checker_kernels) {
+  if (!p) return -1;
+  p->debug_conv = use_checker_kernels ? 1 : 0;
+  return 0;
+}
+int dsr_plan_debug_replay(dsr_plan_t* p, const char* layer, int what, int use_checker, void* stream) {
+  if (!p || !layer || !p->bound) return -1;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  for (size_t i = 0; i < p->lv.size(); ++i) {
+    Level& L = p->lv[i];
+    for (ConvLayer* c : {&L.d1, &L.d2, &L.u1, &L.u2}) {
+      if (("L" + std::to_string(i) + "." + c->tag) != layer) continue;
+      const int saved = p->debug_conv;
+      p->debug_conv = use_checker ? 1 : 0;
+      int rc = 0;
+      float* acc = reinterpret_cast<float*>(p->base);
+      if (what == 0) {
+        cudaMemsetAsync(acc + c->stats_off, 0, 2 * kNC * 4, s);
+        rc = run_fprop(p, *c, s);
+      } else if (what == 1) {
+        if (!c->need_dgrad) rc = -1;
+        for (int k = 0; k < c->ndgrad && rc == 0; ++k) rc = run_dgrad(p, *c, k, s);
+      } else if (what == 2) {
+        cudaMemsetAsync(acc + p->garena_off + c->pack.g_off, 0,
+                        static_cast<size_t>(c->k) * c->k * kNC * c->cin_pad * 4, s);
+        rc = run_wgrad(p, *c, s);
+      } else {
+        rc = -1;
+      }
+      p->debug_conv = saved;
+      return rc;
+    }
+  }
+  return -1;
+}
+int dsr_plan_device_error(dsr_plan_t* p, int* host_code) {
+  if (!p || !p->bound || !host_code) return -1;
+  cudaError_t e = cudaMemcpy(host_code, p->errword.ptr, sizeof(int), cudaMemcpyDeviceToHost);
+  return static_cast<int>(e);
+}
+int dsr_debug_copy(void* dst, const void* src, size_t bytes, void* stream) {
+  if (!dst || !src) return -1;
+  return static_cast<int>(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+}
+
+}  // extern "C"

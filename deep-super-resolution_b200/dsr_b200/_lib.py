@@ -1,0 +1,90 @@
+"""ctypes binding of libdsr_b200.so (the C ABI declared in include/dsr_b200.h).
+
+The library is the product: there is no CPU / eager fallback.  Importing this module when the
+shared object has not been built raises ImportError with the build command; calling a compute
+entry point without a CUDA device raises RuntimeError.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), 'libdsr_b200.so')
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f'{LIB_PATH} is missing: build it with `make -C deep-super-resolution_b200/csrc` '
+        '(or python -c "import __graft_entry__ as g; g.build()"); dsr_b200 has no CPU fallback.')
+
+lib = C.CDLL(LIB_PATH)
+
+vp, i32, i64, f32, u64, sz = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_ulonglong, C.c_size_t
+
+
+class StepBuffers(C.Structure):
+    """dsr_step_buffers_t"""
+    _fields_ = [(n, vp) for n in ('params', 'grads', 'adam_m', 'adam_v', 'bn_buffers', 'z_saved', 'z', 'lr_image',
+                                  'out_hr', 'out_lr', 'g_out_lr', 'g_out_hr', 'loss_out')]
+
+
+# name -> (restype, argtypes); every symbol of include/dsr_b200.h (tests/test_abi.py checks the two lists agree)
+SIGNATURES = {
+    'dsr_abi_version': (i32, []),
+    'dsr_error_string': (C.c_char_p, [i32]),
+    'dsr_lanczos_kernel': (i32, [i32, i32, C.POINTER(C.c_double), i32]),
+    'dsr_downsampler_table_bytes': (sz, [i32, i32, i32, i32]),
+    'dsr_downsampler_create': (i32, [C.POINTER(vp), i32, i32, i32, i32, vp, sz, vp]),
+    'dsr_downsampler_destroy': (None, [vp]),
+    'dsr_downsample_fwd': (i32, [vp, vp, vp, i32, vp]),
+    'dsr_downsample_bwd': (i32, [vp, vp, vp, i32, vp]),
+    'dsr_downsample_mse': (i32, [vp, vp, vp, vp, vp, vp, i32, vp]),
+    'dsr_plan_create': (i32, [C.POINTER(vp), i32, i32, i32, i32, i32]),
+    'dsr_plan_destroy': (None, [vp]),
+    'dsr_plan_num_params': (i32, [vp]),
+    'dsr_plan_param_numel': (i64, [vp]),
+    'dsr_plan_param_info': (i32, [vp, i32, C.c_char_p, i32, C.POINTER(i64), C.POINTER(i32), C.POINTER(i32)]),
+    'dsr_plan_num_bn': (i32, [vp]),
+    'dsr_plan_bn_numel': (i64, [vp]),
+    'dsr_plan_bn_info': (i32, [vp, i32, C.c_char_p, i32, C.POINTER(i64), C.POINTER(i32)]),
+    'dsr_plan_workspace_bytes': (sz, [vp]),
+    'dsr_plan_bind': (i32, [vp, vp, sz, vp]),
+    'dsr_net_forward': (i32, [vp, vp, vp, vp, vp, vp]),
+    'dsr_net_backward': (i32, [vp, vp, vp, vp, vp, vp]),
+    'dsr_adam_step': (i32, [vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, vp]),
+    'dsr_perturb': (i32, [vp, vp, i64, f32, u64, u64, vp]),
+    'dsr_dip_step': (i32, [vp, vp, C.POINTER(StepBuffers), f32, f32, u64, i32, vp]),
+    'dsr_plan_tensor': (i32, [vp, C.c_char_p, C.POINTER(vp), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32),
+                              C.POINTER(i32), C.POINTER(i32)]),
+    'dsr_plan_last_launches': (i32, [vp]),
+    'dsr_plan_set_debug_conv': (i32, [vp, i32]),
+    'dsr_plan_debug_replay': (i32, [vp, C.c_char_p, i32, i32, vp]),
+    'dsr_plan_device_error': (i32, [vp, C.POINTER(i32)]),
+    'dsr_debug_copy': (i32, [vp, vp, sz, vp]),
+}
+
+for _name, (_res, _args) in SIGNATURES.items():
+    _fn = getattr(lib, _name)          # AttributeError here = the .so is stale; rebuild
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+
+class DsrError(RuntimeError):
+    pass
+
+
+def check(rc: int, what: str = '') -> None:
+    if rc != 0:
+        msg = lib.dsr_error_string(rc).decode()
+        raise DsrError(f'libdsr_b200: {what or "call"} failed with code {rc}: {msg}')
+
+
+def require_cuda() -> None:
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError('dsr_b200 needs a CUDA device (sm_100a); there is no CPU fallback')
+
+
+def stream_ptr() -> int:
+    import torch
+    return torch.cuda.current_stream().cuda_stream

@@ -1,0 +1,134 @@
+/* dsr_b200.h -- C ABI of libdsr_b200.so: the B200-native (sm_100a) Deep-Image-Prior
+ * super-resolution step.
+ *
+ * The reference (LewisClifton/Deep-Super-Resolution) is pure Python on torch.nn: it has no FFI
+ * for this path, so there is nothing to "bind" -- the entry points below are what the Python
+ * mirror of the reference call surface (deep-super-resolution_b200/{models/DIP,utils}) calls
+ * through ctypes.  Each entry point cites the reference code whose arithmetic it replaces
+ * (paths relative to the upstream repo root).
+ *
+ * Conventions
+ *   - the reference's own calls (torch.nn modules) take NCHW fp32 tensors of batch 1; so do these entry points;
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless named host_*;
+ *   - every call enqueues work on `stream` (a cudaStream_t passed as void*) and returns without
+ *     synchronising; the library keeps no global mutable state besides opaque plans;
+ *   - return value: 0 = ok, negative = bad argument / unsupported configuration / protocol
+ *     error, positive = cudaError_t.  Nothing throws.
+ *   - memory: the caller owns every buffer, including the plan workspace
+ *     (dsr_plan_workspace_bytes / dsr_plan_bind); a plan owns only small host tables.
+ */
+#ifndef DSR_B200_H_
+#define DSR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dsr_plan dsr_plan_t;
+
+/* Library / build identification: returns the ABI version (currently 1). */
+int dsr_abi_version(void);
+/* Human-readable description of error codes returned by this library (static string). */
+const char* dsr_error_string(int code);
+
+/* ---- Lanczos downsampler --------------------------------------------------------------
+ * Replaces utils/downsampler.py:5-71 (Downsampler.__init__/forward, kernel_type 'lanczos2' or
+ * 'lanczos3', phase 0.5, preserve_size=True) and utils/downsampler.py:73-134 (get_kernel). */
+
+/* Writes the normalised (4f x 4f or 6f x 6f) 2-D kernel in float64 to host_kernel (k*k doubles)
+ * exactly as get_kernel(factor,'lanczos',0.5,kernel_width,support) does; returns k, or <0. */
+int dsr_lanczos_kernel(int factor, int support, double* host_kernel, int capacity);
+
+typedef struct dsr_downsampler dsr_downsampler_t;
+/* Device tables for an n_planes x H x W input; table_ws must hold dsr_downsampler_table_bytes(). */
+size_t dsr_downsampler_table_bytes(int factor, int support, int H, int W);
+int dsr_downsampler_create(dsr_downsampler_t** out, int factor, int support, int H, int W, void* table_ws,
+                           size_t table_bytes, void* stream);
+void dsr_downsampler_destroy(dsr_downsampler_t* d);
+/* y[C][H/f][W/f] = D(x[C][H][W]), fp32 NCHW (batch 1). */
+int dsr_downsample_fwd(const dsr_downsampler_t* d, const float* x, float* y, int C, void* stream);
+/* gx = D^T gy (autograd backward of the above w.r.t. its input). */
+int dsr_downsample_bwd(const dsr_downsampler_t* d, const float* gy, float* gx, int C, void* stream);
+/* Fused closure tail (DIP.py:62-65): y = D(x); *loss += mean((y-target)^2); gy = dloss/dy. */
+int dsr_downsample_mse(const dsr_downsampler_t* d, const float* x, const float* target, float* y, float* gy,
+                       float* loss, int C, void* stream);
+
+/* ---- skip network ---------------------------------------------------------------------
+ * Replaces models/DIP/__init__.py:8-18 (get_net) + models/DIP/skip.py:3-96 (skip) as
+ * instantiated at DIP.py:169-174: NET_TYPE 'skip', pad 'reflection', upsample 'bilinear',
+ * LeakyReLU, need_sigmoid, need_bias, n33d = n33u = 128, n11 = 4, stride downsampling;
+ * input_depth in {8k}, num_scales in [1, 6], any H, W that keep every level >= 2 pixels. */
+int dsr_plan_create(dsr_plan_t** out, int H, int W, int input_depth, int num_scales, int n_out);
+void dsr_plan_destroy(dsr_plan_t* p);
+/* Flat parameter buffer: concatenation of the reference's net.named_parameters() in order. */
+int dsr_plan_num_params(const dsr_plan_t* p);                 /* number of tensors (112)    */
+long long dsr_plan_param_numel(const dsr_plan_t* p);          /* total floats (2 217 831)   */
+/* idx-th tensor: name (reference state_dict key), offset into the flat buffer, shape (up to 4). */
+int dsr_plan_param_info(const dsr_plan_t* p, int idx, char* name, int name_cap, long long* offset, int* ndim,
+                        int* shape4);
+/* BatchNorm buffers: flat [running_mean(C) | running_var(C)] per BatchNorm in state_dict order. */
+int dsr_plan_num_bn(const dsr_plan_t* p);
+long long dsr_plan_bn_numel(const dsr_plan_t* p);
+int dsr_plan_bn_info(const dsr_plan_t* p, int idx, char* name, int name_cap, long long* offset, int* channels);
+size_t dsr_plan_workspace_bytes(const dsr_plan_t* p);
+/* Binds (and zero-fills) the workspace and builds the TMA descriptors; must precede forward. */
+int dsr_plan_bind(dsr_plan_t* p, void* workspace, size_t bytes, void* stream);
+
+/* out[n_out][H][W] = net(z[input_depth][H][W])   (skip.py forward; BatchNorm in train mode).
+ * bn_buffers (may be NULL): running statistics are updated as torch does (momentum 0.1). */
+int dsr_net_forward(dsr_plan_t* p, const float* params, const float* z, float* out, float* bn_buffers, void* stream);
+/* grads (flat, same layout as params) = d<grad_out, out>/dparams for the LAST forward of this
+ * plan; `out` is that forward's output.  Conv biases feeding a BatchNorm get exact zeros. */
+int dsr_net_backward(dsr_plan_t* p, const float* params, const float* out, const float* grad_out, float* grads,
+                     void* stream);
+
+/* ---- optimiser ------------------------------------------------------------------------
+ * Replaces torch.optim.Adam(params, lr) as used by utils/DIP.py:33-38 (defaults: betas
+ * (0.9, 0.999), eps 1e-8, no weight decay): one fused pass over flat p, g, m, v; t = 1-based
+ * step count. */
+int dsr_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                  float eps, int t, void* stream);
+
+/* z = z_saved + sigma * N(0,1) (DIP.py:52) with a counter-based Philox generator on the device. */
+int dsr_perturb(const float* z_saved, float* z, long long n, float sigma, unsigned long long seed,
+                unsigned long long offset, void* stream);
+
+/* ---- whole DIP iteration (closure of DIP.py:47-95 + utils/DIP.py:35-38), one host call ----
+ * perturb -> forward -> downsample -> MSE -> backward -> Adam.  loss_out: device float that
+ * receives this iteration's loss.  t = 1-based iteration index. */
+typedef struct dsr_step_buffers {
+  float* params; float* grads; float* adam_m; float* adam_v;   /* flat, dsr_plan_param_numel floats */
+  float* bn_buffers;                                           /* flat, dsr_plan_bn_numel floats, or NULL */
+  const float* z_saved; float* z;                              /* [input_depth][H][W] */
+  const float* lr_image;                                       /* [n_out][H/f][W/f] */
+  float* out_hr; float* out_lr; float* g_out_lr; float* g_out_hr;
+  float* loss_out;
+} dsr_step_buffers_t;
+int dsr_dip_step(dsr_plan_t* p, const dsr_downsampler_t* d, const dsr_step_buffers_t* b, float lr, float sigma,
+                 unsigned long long seed, int t, void* stream);
+
+/* ---- introspection for tests / profiling --------------------------------------------------
+ * Named intermediate of the last forward/backward (e.g. "L0.d1_raw"): device pointer, element
+ * kind (0 fp16, 1 bf16, 2 fp32), padded-grid flag, H, W, C.  Returns 0 or -1 if unknown. */
+int dsr_plan_tensor(const dsr_plan_t* p, const char* name, void** ptr, int* kind, int* padded, int* H, int* W,
+                    int* C);
+/* Kernel launches enqueued by the last forward / backward / step call on this plan. */
+int dsr_plan_last_launches(const dsr_plan_t* p);
+/* Debug switch (tests only): 1 = run convolutions with the naive CUDA-core checker kernels. */
+int dsr_plan_set_debug_conv(dsr_plan_t* p, int use_checker_kernels);
+/* Re-runs ONE tensor-core kernel of one conv layer ("L0.d1", "L2.u1", ...) on the current workspace
+ * contents: what = 0 fprop (zeroes the layer's BN sums first), 1 dgrad, 2 wgrad (zeroes the layer's packed
+ * gradient first); use_checker = 1 runs the CUDA-core checker kernel instead.  Tests compare the two. */
+int dsr_plan_debug_replay(dsr_plan_t* p, const char* layer, int what, int use_checker, void* stream);
+/* Device error word written by a kernel whose mbarrier wait timed out (0 = none). */
+int dsr_plan_device_error(dsr_plan_t* p, int* host_code);
+/* Device-to-device copy on `stream` (lets ctypes callers read an introspected tensor into their own buffer). */
+int dsr_debug_copy(void* dst, const void* src, size_t bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DSR_B200_H_ */

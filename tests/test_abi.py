@@ -1,0 +1,147 @@
+"""Host-side checks that need no GPU: the C-ABI library loads and exports exactly the symbols that
+include/dsr_b200.h declares, the host-only entry points (Lanczos table, plan layout) agree with the
+reference fixtures, and the Python mirror refuses unsupported configurations / CPU tensors."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, 'include', 'dsr_b200.h')
+
+
+def header_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    return sorted(set(re.findall(r'\b(dsr_[a-z0-9_]+)\s*\(', src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from dsr_b200 import _lib
+    declared = header_symbols()
+    assert len(declared) >= 28
+    out = subprocess.run(['nm', '-D', '--defined-only', _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = sorted(set(re.findall(r' T (dsr_[a-z0-9_]+)', out)))
+    assert exported == declared
+    assert sorted(_lib.SIGNATURES) == declared          # the ctypes table binds all of them
+    assert _lib.lib.dsr_abi_version() == 1
+    assert _lib.lib.dsr_error_string(-5).decode() == 'unsupported network configuration'
+
+
+def test_library_is_sm100a_tcgen05():
+    """The shipped cubin is sm_100a and holds the Blackwell tensor/TMA instructions (SASS mnemonics)."""
+    from dsr_b200 import _lib
+    sass = subprocess.run(['cuobjdump', '-sass', _lib.LIB_PATH], capture_output=True, text=True).stdout
+    if not sass:
+        pytest.skip('cuobjdump unavailable')
+    assert 'sm_100a' in sass
+    assert 'UTCHMMA' in sass and 'UTMALDG' in sass and 'LDTM' in sass
+
+
+@pytest.mark.parametrize('f', [4, 8, 16])
+def test_lanczos_table(golden, f):
+    import dsr_b200
+    k = dsr_b200.get_kernel(f, 'lanczos', 0.5, 4 * f + 1, support=2)
+    ref = golden('lanczos.pt')[f'kernel_f{f}'].numpy()
+    assert k.shape == ref.shape and np.abs(k - ref).max() < 1e-15
+    ds = dsr_b200.Downsampler(3, f, 'lanczos2', phase=0.5, preserve_size=True)
+    assert np.array_equal(ds.kernel, k) and ds.out_size(64, 96) == (64 // f, 96 // f)
+
+
+def test_plan_layout_matches_reference_state_dict(golden):
+    from dsr_b200._lib import lib, check
+    from dsr_b200.net import _read_layout
+    g = golden('init_seed0.pt')
+    h = C.c_void_p()
+    check(lib.dsr_plan_create(C.byref(h), 64, 96, 32, 5, 3))
+    lay = _read_layout(h)
+    assert [n for n, _, _ in lay['params']] == g['param_order']
+    assert lay['nparam'] == 2217831 and len(lay['params']) == 112 and len(lay['bns']) == 30
+    off = 0
+    for name, o, shape in lay['params']:
+        assert o == off and tuple(shape) == tuple(g['shapes'][name]), name
+        off += int(np.prod(shape))
+    bn_names = [k[:-len('.running_mean')] for k in g['keys'] if k.endswith('.running_mean')]
+    assert [n for n, _, _ in lay['bns']] == bn_names
+    assert lib.dsr_plan_workspace_bytes(h) > 0
+    lib.dsr_plan_destroy(h)
+    for bad in ((60, 64, 32, 5, 3), (64, 64, 24, 5, 3), (64, 64, 32, 7, 3), (64, 64, 32, 5, 1)):
+        assert lib.dsr_plan_create(C.byref(h), *bad) == -5
+
+
+@pytest.mark.parametrize('seed', [0, 3])
+def test_get_net_same_seed_init_and_state_dict(golden, seed):
+    import dsr_b200
+    g = golden(f'init_seed{seed}.pt')
+    threads = torch.get_num_threads()
+    torch.set_num_threads(1)
+    try:
+        torch.manual_seed(seed)
+        net = dsr_b200.get_net(32, 'skip', 'reflection', skip_n33d=128, skip_n33u=128, skip_n11=4, num_scales=5,
+                               upsample_mode='bilinear')
+        sd = net.state_dict()
+        assert list(sd.keys()) == g['keys']
+        assert [n for n, _ in net.named_parameters()] == g['param_order']
+        for k, c in g['checksums'].items():
+            t = sd[k].detach().double().flatten()
+            got = (float(t.sum()), float(t.abs().sum()),
+                   float((t * torch.arange(1, t.numel() + 1, dtype=torch.float64)).sum() / max(1, t.numel())))
+            assert got == pytest.approx(c, rel=1e-12, abs=1e-12), k
+        assert net.training
+        # parity injection path: loading a reference-shaped state_dict works strictly
+        net.load_state_dict({k: v.clone() for k, v in sd.items()}, strict=True)
+    finally:
+        torch.set_num_threads(threads)
+
+
+def test_unsupported_configurations_raise():
+    import dsr_b200
+    with pytest.raises(NotImplementedError):
+        dsr_b200.get_net(32, 'skip', 'zero', 'bilinear')
+    with pytest.raises(NotImplementedError):
+        dsr_b200.get_net(32, 'skip', 'reflection', 'nearest')
+    with pytest.raises(NotImplementedError):
+        dsr_b200.get_net(32, 'skip', 'reflection', 'bilinear', skip_n33d=64)
+    with pytest.raises(NotImplementedError):
+        dsr_b200.Downsampler(3, 4, 'gauss12', phase=0.5, preserve_size=True)
+    with pytest.raises(NotImplementedError):
+        dsr_b200.Downsampler(3, 4, 'lanczos2', phase=0, preserve_size=True)
+    with pytest.raises(NotImplementedError):
+        dsr_b200.optimize('LBFGS', [], lambda: None, 0.01, 1)
+    with pytest.raises(NotImplementedError):
+        dsr_b200.get_noise(2, 'meshgrid', (8, 8))
+
+
+def test_no_cpu_fallback():
+    import dsr_b200
+    net = dsr_b200.get_net(32, 'skip', 'reflection', 'bilinear')
+    with pytest.raises(RuntimeError, match='CUDA'):
+        net(torch.zeros(1, 32, 64, 64))
+    ds = dsr_b200.Downsampler(3, 4, 'lanczos2', phase=0.5, preserve_size=True)
+    with pytest.raises(RuntimeError, match='CUDA'):
+        ds(torch.zeros(1, 3, 64, 64))
+    with pytest.raises(NotImplementedError):
+        dsr_b200.optimize('adam', [torch.nn.Parameter(torch.zeros(3))], lambda: None, 0.01, 1)
+
+
+def test_get_noise_matches_reference_recipe(monkeypatch):
+    import dsr_b200
+    monkeypatch.setenv('DSR_NOISE_DEVICE', 'cpu')
+    torch.manual_seed(4)
+    z = dsr_b200.get_noise(32, 'noise', (16, 24))
+    torch.manual_seed(4)
+    want = torch.zeros(1, 32, 16, 24).uniform_() * 0.1          # utils/DIP.py:92-96
+    assert torch.equal(z, want) and z.device.type == 'cpu'
+
+
+def test_product_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, 'deep-super-resolution_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r'(from|import)\s+oracle|dip_oracle|oracle/', src), (dirpath, f)

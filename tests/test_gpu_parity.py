@@ -1,0 +1,286 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle and the reference fixtures.
+All tests need a B200: `python -m pytest tests -m gpu`."""
+import ctypes as C
+import math
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / max(float(b.norm()), 1e-30))
+
+
+def cosine(a, b):
+    a, b = a.detach().double().cpu().flatten(), b.detach().double().cpu().flatten()
+    return float(a @ b / max(float(a.norm() * b.norm()), 1e-30))
+
+
+def make_net(seed):
+    import dsr_b200
+    torch.manual_seed(seed)
+    return dsr_b200.get_net(32, 'skip', 'reflection', skip_n33d=128, skip_n33u=128, skip_n11=4, num_scales=5,
+                            upsample_mode='bilinear')
+
+
+# ---------------------------------------------------------------------------------------------
+# Lanczos downsampler: fp32, gate 1e-5 relative (BASELINE.json north_star)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('f', [4, 8, 16])
+def test_downsampler_matches_reference(golden, f):
+    import dsr_b200
+    g = golden('lanczos.pt')
+    ds = dsr_b200.Downsampler(3, f, 'lanczos2', phase=0.5, preserve_size=True).to('cuda')
+    x = g['x'].cuda().requires_grad_(True)
+    y = ds(x)
+    assert y.shape == g[f'y_f{f}'].shape
+    assert rel(y, g[f'y_f{f}']) < 1e-5
+    (y * g[f'gy_f{f}'].cuda()).sum().backward()
+    assert rel(x.grad, g[f'gx_f{f}']) < 1e-5
+
+
+@pytest.mark.parametrize('shape', [(1, 3, 512, 512), (2, 3, 32, 48), (1, 3, 128, 256)])
+def test_downsampler_vs_oracle_and_properties(shape):
+    import dsr_b200
+    from oracle import dip_oracle as O
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(shape, generator=g)
+    ds = dsr_b200.Downsampler(3, 4, 'lanczos2', phase=0.5, preserve_size=True)
+    xc = x.cuda().requires_grad_(True)
+    y = ds(xc)
+    assert rel(y, O.downsample(x, 4)) < 1e-5
+    # adjointness <D x, g> == <x, D^T g> (size-independent property of the backward pass)
+    gy = torch.rand(y.shape, generator=g).cuda()
+    (y * gy).sum().backward()
+    lhs = float((y.detach().double() * gy.double()).sum())
+    rhs = float((xc.detach().double() * xc.grad.double()).sum())
+    assert lhs == pytest.approx(rhs, rel=1e-5)
+    # a constant image stays constant (taps sum to 1, replicate padding); linearity
+    c = ds(torch.full(shape, 0.37, device='cuda'))
+    assert float((c - 0.37).abs().max()) < 1e-6
+    x2 = torch.rand(shape, generator=g).cuda()
+    assert rel(ds(2 * xc.detach() - 3 * x2), 2 * y - 3 * ds(x2)) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------
+# tcgen05 kernels vs their CUDA-core checker kernels on identical operands
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('size', [(64, 64), (128, 160)])
+def test_tensor_core_kernels_match_checker(size):
+    import dsr_b200
+    from dsr_b200._lib import lib, check
+    H, W = size
+    net = make_net(1).cuda()
+    g = torch.Generator().manual_seed(2)
+    z = (torch.rand(1, 32, H, W, generator=g) * 0.1).cuda()
+    net(z)                                  # creates the plan
+    net.set_debug_conv(True)
+    out = net(z)
+    out.backward(torch.randn(out.shape, generator=g).cuda() * 1e-3)
+    torch.cuda.synchronize()
+    plan = net._plans[(H, W)]
+    stream = torch.cuda.current_stream().cuda_stream
+    for what, suffix, tol in ((0, '_raw', 2e-3), (2, '_dw', 2e-3), (1, '_gin', 1e-2)):
+        for i in range(5):
+            for tag in ('d1', 'd2', 'u1', 'u2'):
+                layer = f'L{i}.{tag}'
+                if what == 1 and layer == 'L0.d1':
+                    continue
+                res = {}
+                for chk in (1, 0):
+                    check(lib.dsr_plan_debug_replay(plan.handle, layer.encode(), what, chk, stream))
+                    torch.cuda.synchronize()
+                    res[chk] = net.debug_tensor(layer + suffix, (H, W)).float()
+                    if what == 0:
+                        res[(chk, 's')] = net.debug_tensor(layer + '_stats', (H, W)).float()
+                # outputs are rounded to 16 bits by both kernels: allow one ulp of fp16 / bf16
+                assert rel(res[0], res[1]) < tol, (layer, what)
+                if what == 0:
+                    assert rel(res[(0, 's')], res[(1, 's')]) < 1e-3, layer
+    code = C.c_int(-1)
+    check(lib.dsr_plan_device_error(plan.handle, C.byref(code)))
+    assert code.value == 0
+
+
+# ---------------------------------------------------------------------------------------------
+# One teacher-forced DIP step against the REFERENCE fixture (same weights, same noise)
+# gates: output rel L2 <= 1e-2, loss rel <= 1e-2, live-parameter grads cosine >= 0.999
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('name', ['step_64x64.pt', 'step_64x96.pt'])
+def test_teacher_forced_step_matches_reference(golden, name):
+    import dsr_b200
+    from oracle import dip_oracle as O
+    fx = golden(name)
+    net = make_net(fx['seed'])
+    sd0 = {k: v.clone() for k, v in net.state_dict().items()}
+    net = net.cuda()
+    ds = dsr_b200.Downsampler(3, fx['factor'], 'lanczos2', phase=0.5, preserve_size=True).cuda()
+    out = net(fx['z0'].cuda())
+    out_lr = ds(out)
+    loss = torch.nn.MSELoss()(out_lr, fx['lr_img'].cuda())
+    loss.backward()
+    assert rel(out, fx['out_hr']) < 1e-2
+    assert rel(out_lr, fx['out_lr']) < 1e-2
+    assert float(loss) == pytest.approx(fx['losses'][0], rel=1e-2)
+    _, _, grads = O.step_loss_and_grads(sd0, fx['z0'], fx['lr_img'], fx['factor'])
+    dead = set(O.dead_param_keys())
+    floor = 1e-6 * max(fx['grad_norms'].values())
+    checked = 0
+    for k, p in net.named_parameters():
+        if k in dead or fx['grad_norms'][k] < floor:
+            if k in dead and k.endswith('1.bias'):
+                assert float(p.grad.abs().max()) == 0.0      # conv bias feeding a BatchNorm: exact zero
+            continue
+        assert cosine(p.grad, grads[k]) > 0.999, k
+        assert float(p.grad.double().norm().cpu()) == pytest.approx(fx['grad_norms'][k], rel=3e-2), k
+        checked += 1
+    assert checked >= 60
+    # BatchNorm running statistics follow torch (momentum 0.1, unbiased variance, conv bias in the mean)
+    sd1 = net.state_dict()
+    assert int(sd1['1.0.2.num_batches_tracked']) == 1
+    for k, v in fx['post_adam_small'].items():
+        if k.endswith('running_mean') or k.endswith('running_var'):
+            assert torch.allclose(sd1[k].cpu(), v, rtol=2e-2, atol=2e-3), k
+
+
+def test_fused_adam_matches_torch():
+    from dsr_b200._lib import lib, check
+    g = torch.Generator().manual_seed(0)
+    n = 100003
+    p = torch.randn(n, generator=g)
+    ref = torch.nn.Parameter(p.clone())
+    opt = torch.optim.Adam([ref], lr=0.01)
+    pc, m, v = p.cuda(), torch.zeros(n, device='cuda'), torch.zeros(n, device='cuda')
+    for t in range(1, 6):
+        grad = torch.randn(n, generator=g) * (10.0 ** -t)
+        ref.grad = grad.clone()
+        opt.step()
+        gc = grad.cuda()
+        check(lib.dsr_adam_step(pc.data_ptr(), gc.data_ptr(), m.data_ptr(), v.data_ptr(), n, 0.01, 0.9, 0.999, 1e-8, t,
+                                torch.cuda.current_stream().cuda_stream))
+    assert float((pc.cpu() - ref.detach()).abs().max()) < 2e-6
+
+
+def test_perturb_is_standard_normal_and_counter_based():
+    from dsr_b200._lib import lib, check
+    n = 1 << 22
+    zs = torch.full((n,), 0.5, device='cuda')
+    z1, z2, z3 = torch.empty_like(zs), torch.empty_like(zs), torch.empty_like(zs)
+    s = torch.cuda.current_stream().cuda_stream
+    check(lib.dsr_perturb(zs.data_ptr(), z1.data_ptr(), n, 0.05, 7, 0, s))
+    check(lib.dsr_perturb(zs.data_ptr(), z2.data_ptr(), n, 0.05, 7, 0, s))
+    check(lib.dsr_perturb(zs.data_ptr(), z3.data_ptr(), n, 0.05, 7, n // 4, s))
+    assert torch.equal(z1, z2) and not torch.equal(z1, z3)
+    e = (z1 - 0.5) / 0.05
+    assert abs(float(e.mean())) < 3e-3 and abs(float(e.std()) - 1) < 3e-3
+    assert abs(float((e ** 4).mean()) - 3) < 0.05 and abs(float((e[:-1] * e[1:]).mean())) < 3e-3
+
+
+def test_optimize_loop_through_the_reference_call_surface():
+    """get_net / Downsampler / get_noise / get_params / optimize + a closure written like DIP.py:47-95."""
+    import dsr_b200
+    from oracle import dip_oracle as O
+    lr_img, hr = O.synthetic_pair(0, 64)
+    net = make_net(0).cuda()
+    ds = dsr_b200.Downsampler(3, 4, 'lanczos2', phase=0.5, preserve_size=True).cuda()
+    net_input = dsr_b200.get_noise(32, 'noise', (64, 64)).detach()
+    assert net_input.is_cuda
+    saved, noise = net_input.detach().clone(), net_input.detach().clone()
+    target = lr_img.unsqueeze(0).cuda()
+    mse = torch.nn.MSELoss()
+    losses = []
+
+    def closure():
+        z = saved + noise.normal_() * 0.05
+        out = net(z.to('cuda'))
+        loss = mse(ds(out), target)
+        loss.backward()
+        losses.append(float(loss))
+        out.detach().cpu()
+        return loss
+
+    params = dsr_b200.get_params('net', net, net_input)
+    assert len(params) == 112
+    w0 = params[2].detach().clone()
+    dsr_b200.optimize('adam', params, closure, 0.01, 40)
+    assert len(losses) == 40 and all(math.isfinite(v) for v in losses)
+    assert sum(losses[-5:]) < 0.5 * sum(losses[:5])          # the fit makes progress
+    assert not torch.equal(w0, params[2].detach())
+    assert all(p.grad is None for p in params)                # utils/DIP.py:39
+
+
+def test_fused_step_tracks_the_closure_path():
+    """dsr_dip_step (one call per iteration) and the closure path compute the same first-iteration loss when
+    fed the same perturbed input, and the fused loop converges like the closure loop."""
+    import dsr_b200
+    from oracle import dip_oracle as O
+    lr_img, hr = O.synthetic_pair(1, 64)
+    cfg = {'learning_rate': 0.01, 'num_iter': 60, 'reg_noise_std': 0.05}
+    net = make_net(1)
+    out, losses = dsr_b200.dip_sr_fused(net, lr_img, (64, 64), 4, cfg, 'cuda:0', seed=5)
+    torch.cuda.synchronize()
+    ls = losses.cpu()
+    assert out.shape == (1, 3, 64, 64) and bool(torch.isfinite(ls).all())
+    assert float(ls[-5:].mean()) < 0.5 * float(ls[:5].mean())
+    assert 0 <= float(out.min()) and float(out.max()) <= 1
+    # sigma = 0: the fused first iteration equals the closure path on z_saved
+    net_a, net_b = make_net(2), make_net(2).cuda()
+    z = dsr_b200.get_noise(32, 'noise', (64, 64))
+    cfg0 = {'learning_rate': 0.01, 'num_iter': 1, 'reg_noise_std': 0.0}
+    _, l1 = dsr_b200.dip_sr_fused(net_a, lr_img, (64, 64), 4, cfg0, 'cuda:0', net_input=z)
+    ds = dsr_b200.Downsampler(3, 4, 'lanczos2', phase=0.5, preserve_size=True)
+    l2 = torch.nn.MSELoss()(ds(net_b(z.cuda())), lr_img.unsqueeze(0).cuda())
+    assert float(l1[0]) == pytest.approx(float(l2), rel=1e-5)
+
+
+def test_full_size_properties_512():
+    """BASELINE config 2 size (512x512, factor 4): properties that need no oracle run -- output range, finite
+    gradients, exact-zero gradients of the structurally dead biases, run-to-run agreement, and a fused loop that
+    reduces the loss."""
+    import dsr_b200
+    from oracle import dip_oracle as O
+    net = make_net(0).cuda()
+    g = torch.Generator().manual_seed(9)
+    z = (torch.rand(1, 32, 512, 512, generator=g) * 0.1).cuda()
+    gout = (torch.randn(1, 3, 512, 512, generator=g) * 1e-4).cuda()
+    out = net(z)
+    out.backward(gout)
+    g1 = net.flat_buffers()[1].clone()
+    o1 = out.detach().clone()
+    assert 0 < float(out.min()) and float(out.max()) < 1 and bool(torch.isfinite(g1).all())
+    names = [n for n, _ in net.named_parameters()]
+    for k in O.dead_param_keys():
+        if k.endswith('1.bias'):
+            assert float(net._params[names.index(k)].grad.abs().max()) == 0.0
+    net.zero_grad()
+    out2 = net(z)
+    out2.backward(gout)
+    assert rel(o1, out2) < 1e-3 and cosine(g1, net.flat_buffers()[1]) > 0.9999
+    lr_img, hr = O.synthetic_pair(0, 512)
+    cfg = {'learning_rate': 0.01, 'num_iter': 30, 'reg_noise_std': 0.05}
+    res, losses = dsr_b200.dip_sr_fused(make_net(0), lr_img, (512, 512), 4, cfg, 'cuda:0')
+    ls = losses.cpu()
+    assert bool(torch.isfinite(ls).all()) and float(ls[-3:].mean()) < float(ls[:3].mean())
+
+
+def test_whole_step_tensor_core_vs_checker_256():
+    import dsr_b200
+    net = make_net(0).cuda()
+    g = torch.Generator().manual_seed(9)
+    z = (torch.rand(1, 32, 256, 256, generator=g) * 0.1).cuda()
+    gout = (torch.randn(1, 3, 256, 256, generator=g) * 1e-4).cuda()
+    out = net(z)
+    out.backward(gout)
+    g_tc, o_tc = net.flat_buffers()[1].clone(), out.detach().clone()
+    net.set_debug_conv(True)
+    net.zero_grad()
+    out2 = net(z)
+    out2.backward(gout)
+    assert rel(o_tc, out2) < 2e-3
+    assert cosine(g_tc, net.flat_buffers()[1]) > 0.999

@@ -1,0 +1,125 @@
+"""The CPU oracle (oracle/dip_oracle.py) against fixtures produced by EXECUTING THE REFERENCE
+(oracle/make_golden.py, run in the build container where /root/reference exists) and against the
+operator known-answer tests of SURVEY.md section 4."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import dip_oracle as O
+
+
+def checksum(t):
+    t = t.detach().double().flatten()
+    return (float(t.sum()), float(t.abs().sum()),
+            float((t * torch.arange(1, t.numel() + 1, dtype=torch.float64)).sum() / max(1, t.numel())))
+
+
+def rel(a, b):
+    a, b = a.detach().double(), b.detach().double()
+    return float((a - b).norm() / b.norm())
+
+
+@pytest.mark.parametrize('f', [4, 8, 16])
+def test_lanczos_table_matches_reference(golden, f):
+    ref = golden('lanczos.pt')[f'kernel_f{f}'].numpy()
+    k = O.lanczos_kernel_2d(f)
+    assert k.shape == ref.shape == (4 * f, 4 * f)
+    assert np.abs(k - ref).max() < 1e-16
+    assert abs(k.sum() - 1) < 1e-14 and np.allclose(k, k.T)
+
+
+def test_lanczos_kat_row_sums():
+    # 1-D taps of get_kernel(4,'lanczos',0.5,17,support=2)
+    want = [-0.001065, -0.009752, -0.020384, -0.014878, 0.024594, 0.098658, 0.183115, 0.239711]
+    got = O.lanczos_kernel_2d(4).sum(axis=1)
+    assert np.allclose(got[:8], want, atol=1e-6) and np.allclose(got[8:], want[::-1], atol=1e-6)
+
+
+@pytest.mark.parametrize('f', [4, 8, 16])
+def test_downsample_matches_reference(golden, f):
+    g = golden('lanczos.pt')
+    x = g['x'].clone().requires_grad_(True)
+    y = O.downsample(x, f)
+    assert y.shape == g[f'y_f{f}'].shape
+    assert rel(y, g[f'y_f{f}']) < 1e-6
+    (y * g[f'gy_f{f}']).sum().backward()
+    assert rel(x.grad, g[f'gx_f{f}']) < 1e-6
+
+
+def test_operator_kats():
+    import torch.nn.functional as F
+    a = torch.arange(5.).view(1, 1, 1, 5)
+    assert F.pad(a, (1, 1, 0, 0), mode='reflect').flatten().tolist() == [1, 0, 1, 2, 3, 4, 3]
+    b = torch.arange(4.).view(1, 1, 1, 4)
+    assert F.pad(b, (2, 2, 0, 0), mode='replicate').flatten().tolist() == [0, 0, 0, 1, 2, 3, 3, 3]
+    c = torch.arange(6.).view(1, 1, 1, 6).expand(1, 1, 2, 6)
+    up = F.interpolate(c, scale_factor=2, mode='bilinear')[0, 0, 0]
+    assert up[:4].tolist() == [0, 0.25, 0.75, 1.25] and up[-2:].tolist() == [4.75, 5.0]
+    x = torch.randn(1, 3, 5, 7)
+    y = O._bn(x, torch.ones(3), torch.zeros(3))
+    m = x.mean(dim=(0, 2, 3), keepdim=True)
+    v = ((x - m) ** 2).mean(dim=(0, 2, 3), keepdim=True)
+    assert torch.allclose(y, (x - m) / torch.sqrt(v + 1e-5), atol=1e-6)
+
+
+@pytest.mark.parametrize('seed', [0, 3])
+def test_init_matches_reference(golden, seed):
+    g = golden(f'init_seed{seed}.pt')
+    threads = torch.get_num_threads()
+    torch.set_num_threads(1)          # the fixture's float64 checksums were summed single-threaded
+    try:
+        torch.manual_seed(seed)
+        sd = O.init_params()
+        assert set(sd.keys()) == set(g['keys'])
+        assert O.param_keys({k: sd[k] for k in g['keys']}) == g['param_order']
+        for k, shape in g['shapes'].items():
+            assert tuple(sd[k].shape) == tuple(shape), k
+        for k, c in g['checksums'].items():
+            assert checksum(sd[k]) == pytest.approx(c, rel=1e-12, abs=1e-12), k
+    finally:
+        torch.set_num_threads(threads)
+
+
+@pytest.mark.parametrize('name', ['step_64x64.pt', 'step_64x96.pt'])
+def test_step_matches_reference(golden, name):
+    fx = golden(name)
+    torch.set_num_threads(1)          # the fixtures were generated single-threaded (fixes the reduction order)
+    torch.manual_seed(fx['seed'])
+    sd = O.init_params()
+    loss, out, grads = O.step_loss_and_grads(sd, fx['z0'], fx['lr_img'], fx['factor'])
+    assert rel(out, fx['out_hr']) < 1e-6      # bit-exact on the machine that generated the fixture
+    assert float(loss) == pytest.approx(fx['losses'][0], rel=1e-5)
+    assert rel(O.downsample(out, fx['factor']), fx['out_lr']) < 1e-5
+    dead = set(O.dead_param_keys())
+    # Besides the structurally dead parameters, a BatchNorm gamma whose output reaches the next train-mode
+    # BatchNorm through positively homogeneous ops only (LeakyReLU, bilinear upsample) has a gradient that is pure
+    # rounding noise while its beta is still 0 (first step): skip gradients 6 orders below the largest one.
+    floor = 1e-6 * max(fx['grad_norms'].values())
+    dead |= {k for k, n in fx['grad_norms'].items() if n < floor}
+    for k, n in fx['grad_norms'].items():
+        if k in dead:
+            continue
+        assert float(grads[k].double().norm()) == pytest.approx(n, rel=1e-4), k
+    for k, g in fx['grad_full'].items():
+        if k in dead:
+            continue
+        assert rel(grads[k], g) < 1e-4, k
+    for k, g in fx['grad_slices'].items():
+        assert rel(grads[k][:8, :8], g) < 1e-4, k
+    # one Adam step (utils/DIP.py:33-38) reproduces the reference's post-step live parameters
+    keys = O.param_keys(sd)
+    adam = O.AdamState(keys, sd, fx['lr'])
+    adam.step(sd, grads)
+    for k, v in fx['post_adam_small'].items():
+        if k in dead or k not in keys:
+            continue
+        # first Adam step is lr*sign(g): entries whose gradient is rounding noise may flip; compare the bulk
+        close = (sd[k] - v).abs() < 1e-6
+        assert close.float().mean() > 0.95, k
+
+
+def test_psnr_and_synthetic_pair():
+    lr, hr = O.synthetic_pair(0, 64)
+    assert hr.shape == (3, 64, 64) and lr.shape == (3, 16, 16)
+    assert 0 <= float(hr.min()) and float(hr.max()) <= 1
+    assert O.psnr(hr, hr + 0.1) == pytest.approx(20.0, abs=1e-3)
