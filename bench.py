@@ -1,0 +1,388 @@
+#!/usr/bin/env python
+"""bench.py -- DIP iterations/s of the B200-native step (BASELINE.json metric), one JSON line on rank 0.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--size 512] [--impl ours|reference]
+
+A "step" is ONE Deep-Image-Prior iteration at 512x512, factor 4 (BASELINE.json configs[1]): input perturbation,
+skip-net forward, Lanczos downsample, MSE, full backward, Adam -- the closure of DIP.py:47-95 plus
+utils/DIP.py:35-38.
+
+* value      device-resident: every iteration is one dsr_dip_step() call (dsr_b200.dip_sr_fused machinery), noise
+             drawn on the device, nothing crosses PCIe.  K steps timed with CUDA events between
+             barrier + synchronize, max over ranks; N ranks each optimise their own image (weak scaling, no
+             collective) and value = N*K / time.
+* e2e        the same iteration through the reference-facing Python call surface (get_net, Downsampler,
+             get_params, optimize and a closure written like DIP.py:47-95) with HOST buffers: the step's perturbed
+             input z comes from pinned host memory (H2D inside the timed region, as DIP.py:57 does) and out_HR /
+             out_LR / loss are read back every step (DIP.py:90-91).
+* roofline   the implicit-GEMM tcgen05 conv kernel (fprop + dgrad launches): algorithmic FLOPs / CUDA-event time
+             per launch, summed over a profiled pass, against MEASURED_PEAKS.json bf16 (sustained) peak.
+* cpu_baseline / --impl reference   the CPU restatement of the reference path (oracle/dip_oracle.py: the same
+             torch CPU primitives the reference's nn.Modules call), all host threads, same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (os.path.join(ROOT, 'deep-super-resolution_b200'), ROOT):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+FLOPS_PER_ITER = {512: 460.07e9, 256: 115.02e9}      # convs, fwd + dgrad + wgrad, true K
+FACTOR = 4
+LR_RATE, SIGMA = 0.01, 0.05                          # DIP.py:318,323
+
+
+def peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return dict(tflops=d.get('bf16_tflops_sustained', d.get('bf16_tflops')), tflops_burst=d.get('bf16_tflops'),
+                    hbm=d.get('hbm_gbs'), src='measured (MEASURED_PEAKS.json, sustained bf16)')
+    return dict(tflops=1590.0, tflops_burst=1590.0, hbm=6650.0, src='fallback (B200_PROFILING.md)')
+
+
+def synthetic_pair(index, size):
+    """HR / LR of image `index` (SURVEY.md 8d recipe).  The LR image is produced with the CUDA Lanczos downsampler
+    so that bench.py does not depend on the oracle for its own arm."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(1000 + index)
+    low = torch.rand(1, 3, size // 8, size // 8, generator=g)
+    field = F.interpolate(low, size=(size, size), mode='bicubic', align_corners=False)[0]
+    yy, xx = torch.meshgrid(torch.arange(size), torch.arange(size), indexing='ij')
+    checker = (((yy // 16) + (xx // 16)) % 2).float() - 0.5
+    return (field * 0.7 + 0.15 + 0.3 * checker).clamp(0, 1)
+
+
+class ClockSampler:
+    QUERY = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+             'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
+        try:
+            self.p = subprocess.Popen(['nvidia-smi', '-i', str(gpu_index), f'--query-gpu={self.QUERY}',
+                                       '--format=csv,noheader,nounits', '-lms', '100'], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(',') for r in open(self.f.name).read().strip().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        sm, reasons, mx = [], set(), None
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for n, v in zip(names, r[3:7]):
+                    if v.strip().lower().startswith('active'):
+                        reasons.add(n)
+            except Exception:
+                continue
+        if sm:
+            sm.sort()
+            out = dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# -------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference path
+# -------------------------------------------------------------------------------------------------
+def cpu_steps(size, warmup, steps, budget_s):
+    """Times DIP iterations of the CPU restatement (fp32, all host threads).  Returns (it/s, steps timed, cores)."""
+    from oracle import dip_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    sd = O.init_params()
+    lr_img, hr = O.synthetic_pair(0, size)
+    z_saved = torch.zeros(1, 32, size, size).uniform_() * 0.1
+    noise = z_saved.clone()
+    keys = O.param_keys(sd)
+    adam = O.AdamState(keys, sd, LR_RATE)
+    times = []
+    t_begin = time.time()
+    for i in range(warmup + steps):
+        t0 = time.time()
+        z = z_saved + noise.normal_() * SIGMA                                  # DIP.py:52 (host RNG, as the reference)
+        loss, out, grads = O.step_loss_and_grads(sd, z, lr_img.unsqueeze(0), FACTOR)
+        adam.step(sd, grads)
+        dt = time.time() - t0
+        if i >= warmup:
+            times.append(dt)
+        if time.time() - t_begin > budget_s and len(times) >= 2:
+            break
+    times.sort()
+    med = times[len(times) // 2]
+    return 1.0 / med, len(times), cores
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    its, n, cores = cpu_steps(args.size, min(args.warmup, 2), args.steps, budget_s=150.0)
+    line = {
+        'impl': 'reference', 'metric': 'DIP iters/s (512^2 4x SR)', 'value': its, 'unit': 'it/s', 'n_gpus': args.gpus,
+        'steps': n, 'warmup': min(args.warmup, 2), 'ms_per_step': 1000.0 / its, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': f'DIP 4x SR of one synthetic {args.size}x{args.size} image, skip net fwd+bwd+Adam',
+                   'size': args.size, 'factor': FACTOR},
+        'cpu_baseline': {'value': its, 'unit': 'it/s', 'cores': cores, 'kind': 'port',
+                         'sample': f'{n} full iterations at {args.size}^2 (median), oracle/dip_oracle.py on torch CPU'},
+        'e2e': {'value': its, 'unit': 'it/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# -------------------------------------------------------------------------------------------------
+# our arm
+# -------------------------------------------------------------------------------------------------
+def run_ours(args, rank, local_rank, world):
+    import ctypes as C
+    import torch.distributed as dist
+    import dsr_b200
+    from dsr_b200._lib import lib, check, StepBuffers
+    from dsr_b200 import _lib
+
+    dev = torch.device('cuda', local_rank)
+    torch.cuda.set_device(dev)
+    size = args.size
+    H = W = size
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- workload: image `rank`, fresh same-seed network (DIP.py:169) ----
+    hr = synthetic_pair(rank, size)
+    ds = dsr_b200.Downsampler(3, FACTOR, 'lanczos2', phase=0.5, preserve_size=True)
+    lr_img = ds(hr.unsqueeze(0).to(dev))[0].contiguous()
+    torch.manual_seed(rank)
+    net = dsr_b200.get_net(32, 'skip', 'reflection', skip_n33d=128, skip_n33u=128, skip_n11=4, num_scales=5,
+                           upsample_mode='bilinear').to(dev)
+    z_saved = dsr_b200.get_noise(32, 'noise', (H, W)).to(dev).contiguous()
+    z = z_saved.clone()
+    net(z)                                   # flattens parameters, builds the plan + workspace
+    net.zero_grad()
+    plan = net._plans[(H, W)]
+    tables = ds._tables_for(H, W, dev)
+    oh, ow = ds.out_size(H, W)
+    flat, gflat = net.flat_buffers()
+    m, v = torch.zeros_like(flat), torch.zeros_like(flat)
+    f32 = dict(dtype=torch.float32, device=dev)
+    out_hr = torch.empty((1, 3, H, W), **f32)
+    out_lr, g_lr, g_hr = torch.empty((3, oh, ow), **f32), torch.empty((3, oh, ow), **f32), torch.empty((1, 3, H, W), **f32)
+    total = args.warmup + args.steps + 64
+    losses = torch.zeros(total, **f32)
+    b = StepBuffers(flat.data_ptr(), gflat.data_ptr(), m.data_ptr(), v.data_ptr(), net._bnflat.data_ptr(),
+                    z_saved.data_ptr(), z.data_ptr(), lr_img.data_ptr(), out_hr.data_ptr(), out_lr.data_ptr(),
+                    g_lr.data_ptr(), g_hr.data_ptr(), losses.data_ptr())
+    stream = _lib.stream_ptr()
+    t_iter = [0]
+
+    def step():
+        t_iter[0] += 1
+        b.loss_out = losses.data_ptr() + 4 * (t_iter[0] - 1)
+        check(lib.dsr_dip_step(plan.handle, tables.handle, C.byref(b), LR_RATE, SIGMA, 1234 + rank, t_iter[0], stream),
+              'dsr_dip_step')
+
+    # ---- device-resident throughput ----
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if sampler else None
+    launches_per_step = lib.dsr_plan_last_launches(plan.handle)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    loss_first, loss_last = float(losses[args.warmup]), float(losses[args.warmup + args.steps - 1])
+
+    # ---- roofline of the conv kernel: profiled pass (CUDA events around every launch) ----
+    roof = None
+    if rank == 0:
+        check(lib.dsr_plan_set_profile(plan.handle, 1))
+        nprof = 3
+        for _ in range(nprof):
+            step()
+        torch.cuda.synchronize()
+        pk = peaks()
+        res = {}
+        for cls, name in ((0, 'conv_gemm_kernel'), (1, 'wgrad_kernel')):
+            msx, fl, n = C.c_double(), C.c_double(), C.c_int()
+            check(lib.dsr_plan_profile_read(plan.handle, cls, C.byref(msx), C.byref(fl), C.byref(n)))
+            res[name] = dict(ms_per_step=msx.value / nprof, tflops=(fl.value / (msx.value * 1e-3) / 1e12) if msx.value else 0.0,
+                             launches_per_step=n.value // nprof, gflop_per_step=fl.value / nprof / 1e9)
+        check(lib.dsr_plan_set_profile(plan.handle, 0))
+        a = res['conv_gemm_kernel']
+        roof = {'bound': 'tensor', 'kernel': 'conv_gemm_kernel (implicit-GEMM fprop + dgrad, tcgen05 kind::f16)',
+                'achieved': a['tflops'], 'peak': pk['tflops'], 'unit': 'TFLOP/s',
+                'frac': a['tflops'] / pk['tflops'] if pk['tflops'] else None, 'traffic': None, 'peak_source': pk['src'],
+                'kernel_ms_per_step': a['ms_per_step'], 'launches_per_step': a['launches_per_step'],
+                'wgrad_kernel': res['wgrad_kernel'],
+                'step_tflops_all_convs': FLOPS_PER_ITER.get(size, 0) / (ms / args.steps * 1e-3) / 1e12}
+
+    # ---- end to end through the public call surface with host buffers ----
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, rank, world, dev, net, ds, lr_img, z_saved, barrier)
+
+    if rank != 0:
+        return
+    its = world * args.steps / (ms * 1e-3)
+    line = {
+        'metric': 'DIP iters/s (512^2 4x SR)', 'value': its, 'unit': 'it/s', 'n_gpus': world, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f16 operands / f32 accumulate (tcgen05 kind::f16), f32 master weights + Adam',
+        'data': 'synthetic',
+        'config': {'workload': f'DIP 4x SR of one synthetic {size}x{size} image per GPU, skip net fwd+bwd+Adam '
+                               f'(BASELINE configs[1]); {world} independent image(s), no collective',
+                   'size': size, 'factor': FACTOR, 'noise': 'device Philox (value) / pinned host buffer (e2e)',
+                   'l2': 'working set per iteration ~1 GB >> 126 MB L2: no flush needed'},
+        'roofline': roof, 'e2e': e2e, 'gpu_launches': launches_per_step * args.steps, 'clocks': clocks,
+        'loss_first_last': [loss_first, loss_last],
+        'conv_tflops_per_gpu': FLOPS_PER_ITER.get(size, 0) * (args.steps / (ms * 1e-3)) / 1e12,
+    }
+    if world == 1 and not args.no_cpu:
+        its_cpu, n, cores = cpu_steps(size, 1, 3, budget_s=40.0)
+        line['cpu_baseline'] = {'value': its_cpu, 'unit': 'it/s', 'cores': cores, 'kind': 'port',
+                                'sample': f'{n} full iterations at {size}^2 after 1 warm-up (median), '
+                                          'oracle/dip_oracle.py on torch CPU'}
+    print(json.dumps(line), flush=True)
+
+
+def run_e2e(args, rank, world, dev, net, ds, lr_img, z_saved, barrier):
+    """Closure path of DIP.py:47-95 through get_params / optimize with HOST buffers for the step's input and
+    results.  A ring of pre-drawn perturbed inputs lives in pinned host memory (drawing 8M normals per step on
+    the CPU is the reference's 71 ms host cost and is not part of this metric); the copy of step t+1's input is
+    enqueued on a side stream while step t computes."""
+    import dsr_b200
+    H, W = z_saved.shape[2], z_saved.shape[3]
+    ring_n = 4
+    zs = z_saved.cpu()
+    ring = [(zs + torch.randn(zs.shape) * SIGMA).pin_memory() for _ in range(ring_n)]
+    dev_z = [torch.empty_like(z_saved) for _ in range(2)]
+    host_hr = torch.empty((1, 3, H, W), dtype=torch.float32).pin_memory()
+    host_lr = torch.empty((1, 3, H // FACTOR, W // FACTOR), dtype=torch.float32).pin_memory()
+    host_loss = torch.empty((), dtype=torch.float32).pin_memory()
+    copy_stream = torch.cuda.Stream(device=dev)
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+    target = lr_img.unsqueeze(0)
+    mse = torch.nn.MSELoss()
+    state = {'i': 0}
+
+    def prefetch(i):
+        slot = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[slot])
+            dev_z[slot].copy_(ring[i % ring_n], non_blocking=True)
+            ready[slot].record(copy_stream)
+
+    def closure():
+        i = state['i']
+        slot = i % 2
+        torch.cuda.current_stream().wait_event(ready[slot])
+        out_hr = net(dev_z[slot])
+        consumed[slot].record()
+        prefetch(i + 2)
+        out_lr = ds(out_hr)
+        loss = mse(out_lr, target)
+        loss.backward()
+        host_hr.copy_(out_hr.detach(), non_blocking=True)                  # DIP.py:90-91 reads
+        host_lr.copy_(out_lr.detach(), non_blocking=True)
+        host_loss.copy_(loss.detach(), non_blocking=True)
+        torch.cuda.current_stream().synchronize()                          # the reference's .cpu() blocks here
+        state['i'] += 1
+        return loss
+
+    for s in range(2):
+        consumed[s].record()
+    prefetch(0)
+    prefetch(1)
+    params = dsr_b200.get_params('net', net, z_saved)
+    dsr_b200.optimize('adam', params, closure, LR_RATE, max(args.warmup, 3))
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    e0.record()
+    dsr_b200.optimize('adam', params, closure, LR_RATE, args.steps)
+    e1.record()
+    barrier()
+    wall = time.time() - t0
+    ms = max(e0.elapsed_time(e1), wall * 1e3)
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    h2d = z_saved.numel() * 4
+    d2h = host_hr.numel() * 4 + host_lr.numel() * 4 + 4
+    return {'value': world * args.steps / (ms * 1e-3), 'unit': 'it/s', 'h2d_bytes_per_step': h2d,
+            'd2h_bytes_per_step': d2h, 'ms_per_step': ms / args.steps,
+            'path': 'get_net/Downsampler/get_params/optimize + DIP.py-style closure; z from pinned host memory, '
+                    'out_HR/out_LR/loss read back each step'}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=30)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--size', type=int, default=512)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-cpu', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device (the product path has no CPU fallback; use --impl reference for the CPU arm)')
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    try:
+        run_ours(args, rank, local_rank, world)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -1,7 +1,7 @@
 // dsr_elem.cu -- bandwidth kernels of the DIP step: layout packing, BatchNorm apply (+LeakyReLU,
 // + reflected halo), skip-branch 1x1 conv, bilinear upsample + concat + BN(132), final 1x1 conv +
 // sigmoid, and all of their backward passes, weight packing, running statistics, Adam, noise.
-// All are coalesced 16-byte-vector kernels (8 fp16/bf16 channels per thread, 16 lanes per pixel);
+// All are coalesced 16-byte-vector kernels (8 fp16 channels per thread, 16 lanes per pixel);
 // per-channel reductions are register -> shared-memory -> one global atomic per channel per block.
 //
 // Reference semantics (paths relative to the upstream repo):
@@ -12,7 +12,6 @@
 //   Adam                                      utils/DIP.py:34 (torch.optim.Adam defaults)
 #include "dsr_elem.cuh"
 
-#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
 namespace dsr {
@@ -40,24 +39,6 @@ __device__ __forceinline__ void store8h(__half* p, const float (&f)[8]) {
   for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
   *reinterpret_cast<uint4*>(p) = u;
 }
-__device__ __forceinline__ void load8b(const __nv_bfloat16* p, float (&f)[8]) {
-  uint4 u = *reinterpret_cast<const uint4*>(p);
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    float2 t = __bfloat1622float2(h[i]);
-    f[2 * i] = t.x;
-    f[2 * i + 1] = t.y;
-  }
-}
-__device__ __forceinline__ void store8b(__nv_bfloat16* p, const float (&f)[8]) {
-  uint4 u;
-  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-  *reinterpret_cast<uint4*>(p) = u;
-}
-
 // Padded coordinates an interior index i in [0, n) occupies under ReflectionPad(1): itself and,
 // for i == 1 / i == n-2, the mirrored halo cell.  The same list is the set of padded cells whose
 // data-gradient folds back onto i.
@@ -89,6 +70,26 @@ __device__ __forceinline__ void up_src(int o, int n, int& i0, int& i1, float& l0
   i1 = min(i0 + 1, n - 1);
   l1 = src - static_cast<float>(i0);
   l0 = 1.f - l1;
+}
+
+// Gradient scaling (fp16 gradients): gs[0] = S, gs[1] = 1/S, gs[2] = bit pattern of max |S * dR| seen in this
+// backward pass, gs[3] = non-finite flag.  Every activation-gradient tensor holds S * gradient.
+__device__ __forceinline__ void track_amax(float* gs, float local_max, bool bad) {
+  __shared__ float s_max[8];
+  __shared__ int s_bad;
+  if (threadIdx.x == 0) s_bad = 0;
+  __syncthreads();
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) local_max = fmaxf(local_max, __shfl_xor_sync(0xffffffffu, local_max, d));
+  if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = local_max;
+  if (bad) s_bad = 1;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float m = 0.f;
+    for (int i = 0; i < static_cast<int>(blockDim.x >> 5); ++i) m = fmaxf(m, s_max[i]);
+    atomicMax(reinterpret_cast<unsigned int*>(gs + 2), __float_as_uint(m));
+    if (s_bad) gs[3] = 1.f;
+  }
 }
 
 inline int grid_for(long long items, int threads, int cap_blocks) {
@@ -458,9 +459,10 @@ int launch_final_conv(const void* act_pad, const float* w, const float* b, float
 // =============================================================================================
 __global__ void final_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ out,
                                  const __half* __restrict__ act, const float* __restrict__ w,
-                                 __nv_bfloat16* __restrict__ dact, float* __restrict__ dw, float* __restrict__ db, int H,
-                                 int W) {
+                                 __half* __restrict__ dact, float* __restrict__ dw, float* __restrict__ db,
+                                 const float* __restrict__ gs, int H, int W) {
   const int g = threadIdx.x & 15;
+  const float S = gs[0], invS = gs[1];
   float wr[3][8], aw[3][8], ab[3] = {0, 0, 0};
 #pragma unroll
   for (int o = 0; o < 3; ++o)
@@ -478,7 +480,7 @@ __global__ void final_bwd_kernel(const float* __restrict__ gout, const float* __
 #pragma unroll
     for (int o = 0; o < 3; ++o) {
       const float ov = out[o * npix + pix];
-      dp[o] = gout[o * npix + pix] * ov * (1.f - ov);
+      dp[o] = S * gout[o * npix + pix] * ov * (1.f - ov);
     }
     const long long off = (static_cast<long long>(y + 1) * Wp + (x + 1)) * 128 + g * 8;
     float f[8], da[8];
@@ -489,7 +491,7 @@ __global__ void final_bwd_kernel(const float* __restrict__ gout, const float* __
 #pragma unroll
       for (int o = 0; o < 3; ++o) aw[o][j] = fmaf(dp[o], f[j], aw[o][j]);
     }
-    store8b(dact + off, da);
+    store8h(dact + off, da);
     if (g == 0) {
 #pragma unroll
       for (int o = 0; o < 3; ++o) ab[o] += dp[o];
@@ -507,15 +509,15 @@ __global__ void final_bwd_kernel(const float* __restrict__ gout, const float* __
     for (int o = 0; o < 3; ++o) atomicAdd(&red[384 + o], ab[o]);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 3 * 128; i += blockDim.x) atomicAdd(&dw[i], red[i]);
-  if (threadIdx.x < 3) atomicAdd(&db[threadIdx.x], red[384 + threadIdx.x]);
+  for (int i = threadIdx.x; i < 3 * 128; i += blockDim.x) atomicAdd(&dw[i], red[i] * invS);
+  if (threadIdx.x < 3) atomicAdd(&db[threadIdx.x], red[384 + threadIdx.x] * invS);
 }
 
 int launch_final_bwd(const float* gout, const float* out, const void* act_pad, const float* w, void* dact_pad,
-                     float* dw, float* db, int H, int W, cudaStream_t s) {
+                     float* dw, float* db, const float* gs, int H, int W, cudaStream_t s) {
   const long long items = static_cast<long long>(H) * W * 16;
   final_bwd_kernel<<<grid_for(items, kThreads, 148 * 4), kThreads, 0, s>>>(
-      gout, out, static_cast<const __half*>(act_pad), w, static_cast<__nv_bfloat16*>(dact_pad), dw, db, H, W);
+      gout, out, static_cast<const __half*>(act_pad), w, static_cast<__half*>(dact_pad), dw, db, gs, H, W);
   DSR_LAUNCH_CHECK();
 }
 
@@ -525,7 +527,7 @@ int launch_final_bwd(const float* gout, const float* out, const void* act_pad, c
 // gradient w.r.t. the activation at interior pixel (y, x), 8 channels of group g
 __device__ __forceinline__ void bn_bwd_gather(const BnBwdArgs& a, int y, int x, int g, const float (&ws)[4][8],
                                               float (&da)[8]) {
-  const __nv_bfloat16* gp = static_cast<const __nv_bfloat16*>(a.g);
+  const __half* gp = static_cast<const __half*>(a.g);
   const int Wp = a.W + 2;
   if (a.fold) {
     int ys[3], xs[3];
@@ -535,12 +537,12 @@ __device__ __forceinline__ void bn_bwd_gather(const BnBwdArgs& a, int y, int x, 
     for (int i = 0; i < ny; ++i)
       for (int k = 0; k < nx; ++k) {
         float f[8];
-        load8b(gp + (static_cast<long long>(ys[i]) * Wp + xs[k]) * a.gC + g * 8, f);
+        load8h(gp + (static_cast<long long>(ys[i]) * Wp + xs[k]) * a.gC + g * 8, f);
 #pragma unroll
         for (int j = 0; j < 8; ++j) da[j] += f[j];
       }
   } else {
-    load8b(gp + (static_cast<long long>(y + 1) * Wp + (x + 1)) * a.gC + g * 8, da);
+    load8h(gp + (static_cast<long long>(y + 1) * Wp + (x + 1)) * a.gC + g * 8, da);
   }
   if (a.ds != nullptr) {
     const float4 d = *reinterpret_cast<const float4*>(a.ds + (static_cast<long long>(y) * a.W + x) * 4);
@@ -572,7 +574,9 @@ __global__ void bn_bwd_kernel(BnBwdArgs a) {
   const long long npix = static_cast<long long>(a.H) * a.W;
   const int Wp = a.W + 2;
   const __half* raw = static_cast<const __half*>(a.raw);
-  __nv_bfloat16* dr = static_cast<__nv_bfloat16*>(a.dr_pad);
+  __half* dr = static_cast<__half*>(a.dr_pad);
+  float amax = 0.f;
+  bool bad = false;
   for (long long pix = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 4; pix < npix;
        pix += (static_cast<long long>(gridDim.x) * blockDim.x) >> 4) {
     const int y = static_cast<int>(pix / a.W), x = static_cast<int>(pix % a.W);
@@ -587,12 +591,14 @@ __global__ void bn_bwd_kernel(BnBwdArgs a) {
       const float dy = da[j] * (yv > 0.f ? 1.f : kSlope);
       if (APPLY) {
         o[j] = ga[j] * rstd[j] * (dy - c1[j] - xh * c2[j]);
+        amax = fmaxf(amax, fabsf(o[j]));
+        bad = bad || !isfinite(o[j]);
       } else {
         s1[j] += dy;
         s2[j] += dy * xh;
       }
     }
-    if (APPLY) store8b(dr + (static_cast<long long>(y + 1) * Wp + (x + 1)) * 128 + g * 8, o);
+    if (APPLY) store8h(dr + (static_cast<long long>(y + 1) * Wp + (x + 1)) * 128 + g * 8, o);
   }
   if (!APPLY) {
     __shared__ float red[256];
@@ -605,9 +611,12 @@ __global__ void bn_bwd_kernel(BnBwdArgs a) {
     }
     __syncthreads();
     atomicAdd(&a.bstats[threadIdx.x], red[threadIdx.x]);
-  } else if (blockIdx.x == 0 && threadIdx.x < 128) {
-    a.dbeta[threadIdx.x] = a.bstats[threadIdx.x];
-    a.dgamma[threadIdx.x] = a.bstats[128 + threadIdx.x];
+  } else {
+    track_amax(a.gs, amax, bad);
+    if (blockIdx.x == 0 && threadIdx.x < 128) {
+      a.dbeta[threadIdx.x] = a.bstats[threadIdx.x] * a.gs[1];
+      a.dgamma[threadIdx.x] = a.bstats[128 + threadIdx.x] * a.gs[1];
+    }
   }
 }
 
@@ -625,7 +634,7 @@ int launch_bn_bwd_apply(const BnBwdArgs& a, cudaStream_t s) {
 // =============================================================================================
 // concat BN(132) backward
 // =============================================================================================
-__device__ __forceinline__ void fold_gather(const __nv_bfloat16* gp, int C, int H, int W, int y, int x, int coff,
+__device__ __forceinline__ void fold_gather(const __half* gp, int C, int H, int W, int y, int x, int coff,
                                             float (&da)[8]) {
   int ys[3], xs[3];
   const int ny = halo_coords(y, H, ys), nx = halo_coords(x, W, xs);
@@ -635,7 +644,7 @@ __device__ __forceinline__ void fold_gather(const __nv_bfloat16* gp, int C, int 
   for (int i = 0; i < ny; ++i)
     for (int k = 0; k < nx; ++k) {
       float f[8];
-      load8b(gp + (static_cast<long long>(ys[i]) * Wp + xs[k]) * C + coff, f);
+      load8h(gp + (static_cast<long long>(ys[i]) * Wp + xs[k]) * C + coff, f);
 #pragma unroll
       for (int j = 0; j < 8; ++j) da[j] += f[j];
     }
@@ -657,8 +666,8 @@ __global__ void upcat_bwd_kernel(UpcatBwdArgs a) {
   for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
   const long long npix = static_cast<long long>(f.H) * f.W;
   const int Wp = f.W + 2;
-  const __nv_bfloat16* gc = static_cast<const __nv_bfloat16*>(a.gcat);
-  __nv_bfloat16* dup = static_cast<__nv_bfloat16*>(a.dup_pad);
+  const __half* gc = static_cast<const __half*>(a.gcat);
+  __half* dup = static_cast<__half*>(a.dup_pad);
   for (long long pix = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 4; pix < npix;
        pix += (static_cast<long long>(gridDim.x) * blockDim.x) >> 4) {
     const int y = static_cast<int>(pix / f.W), x = static_cast<int>(pix % f.W);
@@ -679,7 +688,7 @@ __global__ void upcat_bwd_kernel(UpcatBwdArgs a) {
         const float xh = (u[j] - mean[j]) * rstd[j];
         o[j] = ga[j] * rstd[j] * (dc[j] - a.cbstats[g * 8 + j] * inv_n - xh * a.cbstats[144 + g * 8 + j] * inv_n);
       }
-      store8b(dup + (static_cast<long long>(y + 1) * Wp + (x + 1)) * 128 + g * 8, o);
+      store8h(dup + (static_cast<long long>(y + 1) * Wp + (x + 1)) * 128 + g * 8, o);
     }
     if (g == 0) {
       float d4[8];
@@ -743,8 +752,8 @@ __global__ void upcat_bwd_kernel(UpcatBwdArgs a) {
     if (blockIdx.x == 0 && threadIdx.x < 132) {
       const int c = threadIdx.x;                        // packed channel
       const int rc = (c < 128) ? c + 4 : c - 128;       // reference channel
-      a.dcat_beta[rc] = a.cbstats[c];
-      a.dcat_gamma[rc] = a.cbstats[144 + c];
+      a.dcat_beta[rc] = a.cbstats[c] * a.gs[1];
+      a.dcat_gamma[rc] = a.cbstats[144 + c] * a.gs[1];
     }
   }
 }
@@ -767,8 +776,9 @@ template <int CIN>
 __global__ void skip_bwd_kernel(const float* __restrict__ dsy, const float* __restrict__ sraw, BnRef bn,
                                 const float* __restrict__ sbstats, const __half* __restrict__ xpad,
                                 float* __restrict__ dsraw, float* __restrict__ dw, float* __restrict__ dgamma,
-                                float* __restrict__ dbeta, int H, int W) {
+                                float* __restrict__ dbeta, const float* __restrict__ gs, int H, int W) {
   constexpr int G = CIN / 8;
+  const float invS = gs[1];
   const int g = threadIdx.x % G;
   float mean[4], rstd[4], ga[4], be[4], c1[4], c2[4];
 #pragma unroll
@@ -812,23 +822,24 @@ __global__ void skip_bwd_kernel(const float* __restrict__ dsy, const float* __re
 #pragma unroll
     for (int j = 0; j < 8; ++j) atomicAdd(&red[o * CIN + g * 8 + j], aw[o][j]);
   __syncthreads();
-  for (int i = threadIdx.x; i < 4 * CIN; i += blockDim.x) atomicAdd(&dw[i], red[i]);
+  for (int i = threadIdx.x; i < 4 * CIN; i += blockDim.x) atomicAdd(&dw[i], red[i] * invS);
   if (blockIdx.x == 0 && threadIdx.x < 4) {
-    dbeta[threadIdx.x] = sbstats[threadIdx.x];
-    dgamma[threadIdx.x] = sbstats[4 + threadIdx.x];
+    dbeta[threadIdx.x] = sbstats[threadIdx.x] * invS;
+    dgamma[threadIdx.x] = sbstats[4 + threadIdx.x] * invS;
   }
 }
 
 int launch_skip_bwd(const float* dsy, const float* sraw, BnRef bn_skip, const float* sbstats, const void* xpad, int Cin,
-                    float* dsraw, float* dw, float* dgamma, float* dbeta, int H, int W, cudaStream_t s) {
+                    float* dsraw, float* dw, float* dgamma, float* dbeta, const float* gs, int H, int W,
+                    cudaStream_t s) {
   const long long items = static_cast<long long>(H) * W * (Cin / 8);
   const int grid = grid_for(items, kThreads, 148 * 2);
   if (Cin == 32)
     skip_bwd_kernel<32><<<grid, kThreads, 0, s>>>(dsy, sraw, bn_skip, sbstats, static_cast<const __half*>(xpad), dsraw,
-                                                  dw, dgamma, dbeta, H, W);
+                                                  dw, dgamma, dbeta, gs, H, W);
   else if (Cin == 128)
     skip_bwd_kernel<128><<<grid, kThreads, 0, s>>>(dsy, sraw, bn_skip, sbstats, static_cast<const __half*>(xpad), dsraw,
-                                                   dw, dgamma, dbeta, H, W);
+                                                   dw, dgamma, dbeta, gs, H, W);
   else
     return -2;
   DSR_LAUNCH_CHECK();
@@ -837,8 +848,8 @@ int launch_skip_bwd(const float* dsy, const float* sraw, BnRef bn_skip, const fl
 // =============================================================================================
 // bilinear upsample backward (gather form)
 // =============================================================================================
-__global__ void upsample_bwd_kernel(const __nv_bfloat16* __restrict__ dup, int H, int W,
-                                    __nv_bfloat16* __restrict__ ddeep, int h, int w) {
+__global__ void upsample_bwd_kernel(const __half* __restrict__ dup, int H, int W,
+                                    __half* __restrict__ ddeep, int h, int w) {
   const int g = threadIdx.x & 15;
   const long long npix = static_cast<long long>(h) * w;
   const int Wp = W + 2, wp = w + 2;
@@ -872,20 +883,20 @@ __global__ void upsample_bwd_kernel(const __nv_bfloat16* __restrict__ dup, int H
         if (wx[b] == 0.f) continue;
         const int ox = 2 * qx - 1 + b;
         float f[8];
-        load8b(dup + (static_cast<long long>(oy + 1) * Wp + (ox + 1)) * 128 + g * 8, f);
+        load8h(dup + (static_cast<long long>(oy + 1) * Wp + (ox + 1)) * 128 + g * 8, f);
         const float ww = wy[a] * wx[b];
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] = fmaf(ww, f[j], acc[j]);
       }
     }
-    store8b(ddeep + (static_cast<long long>(qy + 1) * wp + (qx + 1)) * 128 + g * 8, acc);
+    store8h(ddeep + (static_cast<long long>(qy + 1) * wp + (qx + 1)) * 128 + g * 8, acc);
   }
 }
 
 int launch_upsample_bwd(const void* dup_pad, int H, int W, void* ddeep_pad, int h, int w, cudaStream_t s) {
   const long long items = static_cast<long long>(h) * w * 16;
   upsample_bwd_kernel<<<grid_for(items, kThreads, 148 * 16), kThreads, 0, s>>>(
-      static_cast<const __nv_bfloat16*>(dup_pad), H, W, static_cast<__nv_bfloat16*>(ddeep_pad), h, w);
+      static_cast<const __half*>(dup_pad), H, W, static_cast<__half*>(ddeep_pad), h, w);
   DSR_LAUNCH_CHECK();
 }
 
@@ -929,8 +940,9 @@ int launch_pack_weights(const float* params, void* arena, const PackDesc* table_
 }
 
 __global__ void unpack_wgrad_kernel(const float* __restrict__ garena, float* __restrict__ grads,
-                                    const PackDesc* __restrict__ table) {
+                                    const PackDesc* __restrict__ table, const float* __restrict__ gs) {
   const PackDesc d = table[blockIdx.y];
+  const float invS = gs[1];
   const int taps = d.k * d.k;
   const long long n = static_cast<long long>(d.cout) * d.cin * taps;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
@@ -939,13 +951,46 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ garena, float* __r
     const int ci = static_cast<int>((i / taps) % d.cin);
     const int co = static_cast<int>(i / (static_cast<long long>(taps) * d.cin));
     const int j = d.perm ? (ci >= 4 ? ci - 4 : ci + 128) : ci;
-    grads[d.w_off + i] = garena[d.g_off + (static_cast<long long>(tap) * 128 + co) * d.cin_pad + j];
+    grads[d.w_off + i] = invS * garena[d.g_off + (static_cast<long long>(tap) * 128 + co) * d.cin_pad + j];
   }
 }
 
-int launch_unpack_wgrad(const float* garena, float* grads, const PackDesc* table_dev, int nlayers, cudaStream_t s) {
+int launch_unpack_wgrad(const float* garena, float* grads, const PackDesc* table_dev, int nlayers, const float* gs,
+                        cudaStream_t s) {
   dim3 grid(32, nlayers);
-  unpack_wgrad_kernel<<<grid, kThreads, 0, s>>>(garena, grads, table_dev);
+  unpack_wgrad_kernel<<<grid, kThreads, 0, s>>>(garena, grads, table_dev, gs);
+  DSR_LAUNCH_CHECK();
+}
+
+// =============================================================================================
+// gradient-scale maintenance: zero the gradients of a pass that produced non-finite values, then
+// adapt S for the next pass (max |S dR| kept within [2^9, 2^14], fp16 max is 65504)
+// =============================================================================================
+__global__ void grad_sanitize_kernel(float* __restrict__ grads, long long n, const float* __restrict__ gs) {
+  if (gs[3] == 0.f) return;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    grads[i] = 0.f;
+}
+__global__ void grad_scale_update_kernel(float* __restrict__ gs) {
+  float S = gs[0];
+  gs[6] = S;                   // scale used by the pass that just finished
+  const float amax = __uint_as_float(reinterpret_cast<unsigned int*>(gs)[2]);
+  const bool bad = gs[3] != 0.f || !isfinite(amax);
+  if (bad) S *= (1.f / 256.f);
+  else if (amax > 16384.f) S *= (1.f / 16.f);
+  else if (amax < 512.f) S *= 8.f;
+  S = fminf(fmaxf(S, 1.f), 1073741824.f);
+  gs[0] = S;
+  gs[1] = 1.f / S;
+  gs[2] = 0.f;
+  gs[3] = 0.f;
+  gs[4] = amax;                // last pass, for inspection
+  gs[5] = bad ? gs[5] + 1.f : gs[5];
+}
+int launch_grad_scale_finish(float* grads, long long n, float* gs, cudaStream_t s) {
+  grad_sanitize_kernel<<<148 * 4, kThreads, 0, s>>>(grads, n, gs);
+  grad_scale_update_kernel<<<1, 1, 0, s>>>(gs);
   DSR_LAUNCH_CHECK();
 }
 

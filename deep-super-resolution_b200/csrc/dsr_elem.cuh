@@ -2,7 +2,7 @@
 //
 // Conventions: "act" tensors are fp16 NHWC on a padded pixel grid [H+2][W+2][C]; pointers passed
 // here always point at PADDED pixel (0,0) unless the argument is called *_interior or "plain"
-// (= unpadded [H][W][C]).  Gradient tensors are bf16.  Statistics blocks are float [2][C]
+// (= unpadded [H][W][C]).  Gradient tensors are fp16 and hold S * gradient (S = gs[0], see launch_grad_scale_finish).  Statistics blocks are float [2][C]
 // (sum, sum of squares), accumulated with atomics and zeroed by the caller.
 #pragma once
 #include <cuda_runtime.h>
@@ -48,12 +48,12 @@ int launch_upcat_apply(const UpcatArgs& a, cudaStream_t s);
 int launch_final_conv(const void* act_pad, const float* w, const float* b, float* out, int H, int W, cudaStream_t s);
 
 // ---- backward ------------------------------------------------------------------------------
-// d(out) fp32 NCHW, out fp32 NCHW -> dA bf16 padded interior [H+2][W+2][128]; dW [3][128] and db [3] accumulated.
+// d(out) fp32 NCHW, out fp32 NCHW -> dA fp16 padded interior [H+2][W+2][128]; dW [3][128] and db [3] accumulated.
 int launch_final_bwd(const float* gout, const float* out, const void* act_pad, const float* w, void* dact_pad,
-                     float* dw, float* db, int H, int W, cudaStream_t s);
+                     float* dw, float* db, const float* gs, int H, int W, cudaStream_t s);
 
 struct BnBwdArgs {
-  const void* g;           // bf16 gradient w.r.t. the activation, PADDED grid [H+2][W+2][gC]
+  const void* g;           // fp16 gradient w.r.t. the activation, PADDED grid [H+2][W+2][gC]
   int gC;                  // channel pitch of g (128 or 144; first 128 channels are used)
   int fold;                // 1: g holds padded-grid data-gradients whose halo must be folded back (reflection)
   const float* ds;         // optional fp32 plain [H][W][4]: gradient of the skip-conv output reading this activation
@@ -61,9 +61,10 @@ struct BnBwdArgs {
   const void* raw;         // fp16 plain [H][W][128]: BN input saved by the forward
   BnRef bn;
   float* bstats;           // [2][128]: sum dy, sum dy*xhat
-  void* dr_pad;            // bf16 padded [H+2][W+2][128] (interior written; halo stays zero)
+  void* dr_pad;            // fp16 padded [H+2][W+2][128] (interior written; halo stays zero)
   float* dgamma;           // [128]
   float* dbeta;            // [128]
+  float* gs;               // gradient-scale block {S, 1/S, amax bits, non-finite flag, ...}
   int H, W;
 };
 int launch_bn_bwd_stats(const BnBwdArgs& a, cudaStream_t s);
@@ -71,22 +72,24 @@ int launch_bn_bwd_apply(const BnBwdArgs& a, cudaStream_t s);
 
 struct UpcatBwdArgs {
   UpcatArgs f;             // forward description (deep, sraw, stats ...)
-  const void* gcat;        // bf16 padded grid [H+2][W+2][144]: data-gradient of the 3x3 conv reading cat (to fold)
+  const void* gcat;        // fp16 padded grid [H+2][W+2][144]: data-gradient of the 3x3 conv reading cat (to fold)
   float* cbstats;          // [2][144] packed order: sum dc, sum dc*xhat
-  void* dup_pad;           // bf16 padded [H+2][W+2][128]: gradient w.r.t. the upsampled tensor (interior)
+  void* dup_pad;           // fp16 padded [H+2][W+2][128]: gradient w.r.t. the upsampled tensor (interior)
   float* dsy;              // fp32 plain [H][W][4]: gradient w.r.t. BN(4) output (after LeakyReLU')
   float* sbstats;          // [2][4]
   float* dcat_gamma;       // [132] reference channel order
   float* dcat_beta;
+  const float* gs;
 };
 int launch_upcat_bwd_stats(const UpcatBwdArgs& a, cudaStream_t s);
 int launch_upcat_bwd_apply(const UpcatBwdArgs& a, cudaStream_t s);
 
 // BN(4)+skip conv backward: dsy -> dsraw fp32 [H][W][4]; dWskip [4][Cin] (accumulated), dgamma4/dbeta4.
 int launch_skip_bwd(const float* dsy, const float* sraw, BnRef bn_skip, const float* sbstats, const void* xpad, int Cin,
-                    float* dsraw, float* dw, float* dgamma, float* dbeta, int H, int W, cudaStream_t s);
+                    float* dsraw, float* dw, float* dgamma, float* dbeta, const float* gs, int H, int W,
+                    cudaStream_t s);
 
-// transpose of the bilinear x2 upsample: dup padded-interior [H][W][128] (bf16) -> ddeep bf16 padded interior [h][w][128]
+// transpose of the bilinear x2 upsample: dup padded-interior [H][W][128] (fp16) -> ddeep fp16 padded interior [h][w][128]
 int launch_upsample_bwd(const void* dup_pad, int H, int W, void* ddeep_pad, int h, int w, cudaStream_t s);
 
 // ---- parameters ----------------------------------------------------------------------------
@@ -100,7 +103,10 @@ struct PackDesc {           // one conv layer's weight (OIHW fp32 in the flat pa
   long long g_off;          // offset (floats) into the packed wgrad arena [k*k][128][cin_pad]
 };
 int launch_pack_weights(const float* params, void* arena, const PackDesc* table_dev, int nlayers, cudaStream_t s);
-int launch_unpack_wgrad(const float* garena, float* grads, const PackDesc* table_dev, int nlayers, cudaStream_t s);
+int launch_unpack_wgrad(const float* garena, float* grads, const PackDesc* table_dev, int nlayers, const float* gs,
+                        cudaStream_t s);
+// zero `grads` if the pass saw a non-finite gradient, then adapt the scale for the next pass
+int launch_grad_scale_finish(float* grads, long long n, float* gs, cudaStream_t s);
 
 struct BnRunDesc {          // running-statistics update of one BatchNorm (all offsets in floats)
   long long stats_off;      // into the plan workspace viewed as float*: [2][cstride] forward sums

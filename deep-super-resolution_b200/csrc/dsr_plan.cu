@@ -79,8 +79,8 @@ struct ConvLayer {
   int act_halo = 0;                // write the reflected halo of `act`
   size_t stats_off = 0;            // floats into the accumulator block: [2][128] forward sums
   size_t bstats_off = 0;           // [2][128] backward sums
-  Buf dr;                          // bf16 padded [outH+2][outW+2][128]   gradient w.r.t. raw
-  Buf gin;                         // bf16 padded [inH+2][inW+2][n_rows]  data gradient (to fold)
+  Buf dr;                          // fp16 padded [outH+2][outW+2][128]   gradient w.r.t. raw
+  Buf gin;                         // fp16 padded [inH+2][inW+2][n_rows]  data gradient (to fold)
   ConvGemmParams fprop{};
   ConvGemmParams dgrad[4];
   int ndgrad = 0;
@@ -100,8 +100,8 @@ struct Level {
   Buf cat;                          // fp16 padded [H+2][W+2][144]
   size_t skip_stats_off = 0, cat_stats_off = 0;     // forward accumulators ([2][4], [2][144])
   size_t sbstats_off = 0, cbstats_off = 0;          // backward accumulators
-  Buf g_u2a;                        // bf16 padded [H+2][W+2][128]: gradient w.r.t. this level's output
-  Buf dup;                          // bf16 padded [H+2][W+2][128]
+  Buf g_u2a;                        // fp16 padded [H+2][W+2][128]: gradient w.r.t. this level's output
+  Buf dup;                          // fp16 padded [H+2][W+2][128]
   Buf dsy, dsraw;                   // fp32 [H][W][4]
   Buf g_d2a;                        // last level only: bf16 padded [h+2][w+2][128]
 };
@@ -132,7 +132,7 @@ struct dsr_plan {
   size_t acc_bwd_off = 0, acc_bwd_floats = 0;     // zeroed at the start of every backward (incl. wgrad arena)
   size_t garena_off = 0;                          // floats, inside the backward accumulator block
   Buf warena;                                     // packed 16-bit weights
-  Buf pack_table, bnrun_table, errword;
+  Buf pack_table, bnrun_table, errword, gscale;
   Buf g_final;                                    // unused placeholder (level 0 g_u2a is the final-conv gradient)
   std::vector<PackDesc> pack_host;
   std::vector<BnRunDesc> bnrun_host;
@@ -142,6 +142,10 @@ struct dsr_plan {
   int launches = 0;
   int debug_conv = 0;
   bool bound = false, have_forward = false;
+  // optional per-launch timing of the tensor-core kernels (bench.py roofline): class 0 = conv_gemm, 1 = wgrad
+  struct ProfRec { int cls; cudaEvent_t a, b; double flops; };
+  std::vector<ProfRec> prof;
+  int profile = 0;
 };
 
 namespace dsr {
@@ -329,12 +333,12 @@ int build_conv(dsr_plan* p, ConvLayer& c) {
   }
   // ---------------- dgrad ----------------
   c.ndgrad = 0;
+  c.ref_dr = ActRef{static_cast<const uint16_t*>(c.dr.ptr), 0, kNC, c.outW + 2, c.outH + 2, 1};
   if (c.need_dgrad) {
     const int oWp = c.outW + 2, oHp = c.outH + 2;     // dR grid
     const int iWp = c.inW + 2, iHp = c.inH + 2;       // output (input-gradient) grid
     const void* wd = warena + c.pack.d_off;
     const int rows = c.k * c.k * c.n_rows;
-    c.ref_dr = ActRef{static_cast<const uint16_t*>(c.dr.ptr), 1, kNC, oWp, oHp, 1};
     c.ref_wd = WgtRef{reinterpret_cast<const uint16_t*>(wd), 0, kNC};
     const int nclass = (c.stride == 1) ? 1 : 4;
     for (int cls = 0; cls < nclass; ++cls) {
@@ -371,9 +375,9 @@ int build_conv(dsr_plan* p, ConvLayer& c) {
       g.out = static_cast<uint16_t*>(c.gin.ptr) + (static_cast<long long>(ry) * iWp + rx) * c.n_rows;
       g.n_mma = c.n_rows;
       g.n_store = c.n_rows;
-      g.out_bf16 = 1;
+      g.out_bf16 = 0;
       g.stats = nullptr;
-      g.idesc = make_idesc_f16(128, c.n_rows, FMT_BF16, FMT_F16, 0, 0);
+      g.idesc = make_idesc_f16(128, c.n_rows, FMT_F16, FMT_F16, 0, 0);
       g.err = static_cast<int*>(p->errword.ptr);
     }
   }
@@ -425,8 +429,8 @@ int build_conv(dsr_plan* p, ConvLayer& c) {
     g.nsplit = nsplit;
     g.ldw = c.cin_pad;
     g.dw = acc + p->garena_off + c.pack.g_off;
-    g.idesc64 = make_idesc_f16(128, 128, FMT_BF16, FMT_F16, 1, 1);
-    g.idesc16 = make_idesc_f16(128, 16, FMT_BF16, FMT_F16, 1, 1);
+    g.idesc64 = make_idesc_f16(128, 128, FMT_F16, FMT_F16, 1, 1);
+    g.idesc16 = make_idesc_f16(128, 16 * (g.n16 > 0 ? g.n16 : 1), FMT_F16, FMT_F16, 1, 1);   // n16 chunks, LBO apart
     g.err = static_cast<int*>(p->errword.ptr);
   }
   return 0;
@@ -458,16 +462,41 @@ BnRef skip_bn(const dsr_plan* p, const Level& L, const float* params) {
     if (rc__ != 0) return rc__;          \
   } while (0)
 
+// Algorithmic FLOPs of one conv pass (fprop, dgrad or wgrad): 2 * M * N * K with the true channel count.
+double conv_flops(const ConvLayer& c) {
+  return 2.0 * c.outH * c.outW * kNC * static_cast<double>(c.cin) * c.k * c.k;
+}
+struct ProfScope {
+  dsr_plan* p;
+  cudaStream_t s;
+  dsr_plan::ProfRec r;
+  ProfScope(dsr_plan* p_, int cls, double flops, cudaStream_t s_) : p(p_), s(s_) {
+    if (!p->profile) return;
+    r.cls = cls;
+    r.flops = flops;
+    cudaEventCreate(&r.a);
+    cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, s);
+  }
+  ~ProfScope() {
+    if (!p->profile) return;
+    cudaEventRecord(r.b, s);
+    p->prof.push_back(r);
+  }
+};
 int run_fprop(dsr_plan* p, ConvLayer& c, cudaStream_t s) {
   if (p->debug_conv) return launch_conv_ref(c.fprop, c.ref_in, c.ref_wf, s);
+  ProfScope ps(p, 0, conv_flops(c), s);
   return launch_conv_gemm(c.fprop, p->num_sms, s);
 }
 int run_dgrad(dsr_plan* p, ConvLayer& c, int i, cudaStream_t s) {
   if (p->debug_conv) return launch_conv_ref(c.dgrad[i], c.ref_dr, c.ref_wd, s);
+  ProfScope ps(p, 0, conv_flops(c) / c.ndgrad, s);
   return launch_conv_gemm(c.dgrad[i], p->num_sms, s);
 }
 int run_wgrad(dsr_plan* p, ConvLayer& c, cudaStream_t s) {
   if (p->debug_conv) return launch_wgrad_ref(c.wgrad, c.ref_dr, c.ref_in, s);
+  ProfScope ps(p, 1, conv_flops(c), s);
   return launch_wgrad(c.wgrad, s);
 }
 
@@ -528,6 +557,7 @@ int bn_backward(dsr_plan* p, ConvLayer& c, const float* params, float* grads, co
   a.dr_pad = c.dr.ptr;
   a.dgamma = grads + c.g_off;
   a.dbeta = grads + c.be_off;
+  a.gs = static_cast<float*>(p->gscale.ptr);
   a.H = c.outH;
   a.W = c.outW;
   DSR_TRY(launch_bn_bwd_stats(a, s));
@@ -560,12 +590,13 @@ int backward_level(dsr_plan* p, int i, const float* params, float* grads, cudaSt
   ub.sbstats = acc + L.sbstats_off;
   ub.dcat_gamma = grads + L.cat_g;
   ub.dcat_beta = grads + L.cat_be;
+  ub.gs = static_cast<const float*>(p->gscale.ptr);
   DSR_TRY(launch_upcat_bwd_stats(ub, s));
   DSR_TRY(launch_upcat_bwd_apply(ub, s));
   DSR_TRY(launch_skip_bwd(static_cast<const float*>(L.dsy.ptr), static_cast<const float*>(L.sraw.ptr),
                           skip_bn(p, L, params), acc + L.sbstats_off, L.x_pad->ptr, L.Cin,
-                          static_cast<float*>(L.dsraw.ptr), grads + L.skip_w, grads + L.skip_g, grads + L.skip_be, L.H,
-                          L.W, s));
+                          static_cast<float*>(L.dsraw.ptr), grads + L.skip_w, grads + L.skip_g, grads + L.skip_be,
+                          static_cast<const float*>(p->gscale.ptr), L.H, L.W, s));
   void* ddeep = last ? L.g_d2a.ptr : p->lv[i + 1].g_u2a.ptr;
   DSR_TRY(launch_upsample_bwd(L.dup.ptr, L.H, L.W, ddeep, L.h, L.w, s));
   if (!last && (rc = backward_level(p, i + 1, params, grads, s))) return rc;
@@ -779,6 +810,7 @@ int dsr_plan_create(dsr_plan_t** out, int H, int W, int input_depth, int num_sca
   ws.take(p->pack_table, sizeof(PackDesc) * 4 * num_scales);
   ws.take(p->bnrun_table, sizeof(BnRunDesc) * 6 * num_scales);
   ws.take(p->errword, 256);
+  ws.take(p->gscale, 256);
   // place the accumulator blocks
   ws.off = align_up(ws.off, 1024);
   p->acc_fwd_off = ws.off;
@@ -821,20 +853,21 @@ int dsr_plan_create(dsr_plan_t** out, int H, int W, int input_depth, int num_sca
   for (int i = 0; i < num_scales; ++i) {
     Level& L = p->lv[i];
     const std::string P = "L" + std::to_string(i) + ".";
+    if (i == 0) reg_acc(p, "gscale", p->gscale.off / 4, 1, 1, 8);
     reg_tensor(p, P + "x", L.x_pad, 0, 1, L.H, L.W, L.Cin);
     reg_tensor(p, P + "sraw", &L.sraw, 2, 0, L.H, L.W, kNS);
     reg_tensor(p, P + "cat", &L.cat, 0, 1, L.H, L.W, kCat);
-    reg_tensor(p, P + "g_u2a", &L.g_u2a, 1, 1, L.H, L.W, kNC);
-    reg_tensor(p, P + "dup", &L.dup, 1, 1, L.H, L.W, kNC);
+    reg_tensor(p, P + "g_u2a", &L.g_u2a, 0, 1, L.H, L.W, kNC);
+    reg_tensor(p, P + "dup", &L.dup, 0, 1, L.H, L.W, kNC);
     reg_tensor(p, P + "dsy", &L.dsy, 2, 0, L.H, L.W, kNS);
     reg_tensor(p, P + "dsraw", &L.dsraw, 2, 0, L.H, L.W, kNS);
-    if (i + 1 == num_scales) reg_tensor(p, P + "g_d2a", &L.g_d2a, 1, 1, L.h, L.w, kNC);
+    if (i + 1 == num_scales) reg_tensor(p, P + "g_d2a", &L.g_d2a, 0, 1, L.h, L.w, kNC);
     for (ConvLayer* c : {&L.d1, &L.d2, &L.u1, &L.u2}) {
       const std::string T = P + c->tag;
       reg_tensor(p, T + "_raw", &c->raw, 0, 0, c->outH, c->outW, kNC);
       reg_tensor(p, T + "_act", &c->act, 0, 1, c->outH, c->outW, kNC);
-      reg_tensor(p, T + "_dr", &c->dr, 1, 1, c->outH, c->outW, kNC);
-      if (c->need_dgrad) reg_tensor(p, T + "_gin", &c->gin, 1, 1, c->inH, c->inW, c->n_rows);
+      reg_tensor(p, T + "_dr", &c->dr, 0, 1, c->outH, c->outW, kNC);
+      if (c->need_dgrad) reg_tensor(p, T + "_gin", &c->gin, 0, 1, c->inH, c->inW, c->n_rows);
       reg_acc(p, T + "_stats", c->stats_off, 1, 2, kNC);
       reg_acc(p, T + "_dw", p->garena_off + c->pack.g_off, c->k * c->k, kNC, c->cin_pad);
     }
@@ -843,7 +876,10 @@ int dsr_plan_create(dsr_plan_t** out, int H, int W, int input_depth, int num_sca
   return 0;
 }
 
-void dsr_plan_destroy(dsr_plan_t* p) { delete p; }
+void dsr_plan_destroy(dsr_plan_t* p) {
+  if (p) dsr_plan_set_profile(p, 0);
+  delete p;
+}
 
 int dsr_plan_num_params(const dsr_plan_t* p) { return p ? static_cast<int>(p->params.size()) : -1; }
 long long dsr_plan_param_numel(const dsr_plan_t* p) { return p ? p->nparam : -1; }
@@ -887,12 +923,15 @@ int dsr_plan_bind(dsr_plan_t* p, void* workspace, size_t bytes, void* stream) {
     resolve(L.dsraw); resolve(L.g_d2a);
     for (ConvLayer* c : {&L.d1, &L.d2, &L.u1, &L.u2}) { resolve(c->raw); resolve(c->act); resolve(c->dr); resolve(c->gin); }
   }
-  resolve(p->warena); resolve(p->pack_table); resolve(p->bnrun_table); resolve(p->errword);
+  resolve(p->warena); resolve(p->pack_table); resolve(p->bnrun_table); resolve(p->errword); resolve(p->gscale);
   e = cudaMemcpyAsync(p->pack_table.ptr, p->pack_host.data(), sizeof(PackDesc) * p->pack_host.size(),
                       cudaMemcpyHostToDevice, s);
   if (e != cudaSuccess) return static_cast<int>(e);
   e = cudaMemcpyAsync(p->bnrun_table.ptr, p->bnrun_host.data(), sizeof(BnRunDesc) * p->bnrun_host.size(),
                       cudaMemcpyHostToDevice, s);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  const float gs0[8] = {65536.f, 1.f / 65536.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // initial gradient scale 2^16
+  e = cudaMemcpyAsync(p->gscale.ptr, gs0, sizeof(gs0), cudaMemcpyHostToDevice, s);
   if (e != cudaSuccess) return static_cast<int>(e);
   e = cudaStreamSynchronize(s);
   if (e != cudaSuccess) return static_cast<int>(e);
@@ -940,12 +979,14 @@ int dsr_net_backward(dsr_plan_t* p, const float* params, const float* out, const
   if (e != cudaSuccess) return static_cast<int>(e);
   Level& L0 = p->lv[0];
   DSR_TRY(launch_final_bwd(grad_out, out, L0.u2.act.ptr, params + p->fin_w, L0.g_u2a.ptr, grads + p->fin_w,
-                           grads + p->fin_b, L0.H, L0.W, s));
+                           grads + p->fin_b, static_cast<const float*>(p->gscale.ptr), L0.H, L0.W, s));
   int rc = backward_level(p, 0, params, grads, s);
   if (rc) return rc;
   DSR_TRY(launch_unpack_wgrad(reinterpret_cast<const float*>(p->base) + p->garena_off, grads,
                               static_cast<const PackDesc*>(p->pack_table.ptr), static_cast<int>(p->pack_host.size()),
-                              s));
+                              static_cast<const float*>(p->gscale.ptr), s));
+  DSR_TRY(launch_grad_scale_finish(grads, p->nparam, static_cast<float*>(p->gscale.ptr), s));
+  ++p->launches;
   return 0;
 }
 
@@ -1039,6 +1080,33 @@ int dsr_plan_debug_replay(dsr_plan_t* p, const char* layer, int what, int use_ch
     }
   }
   return -1;
+}
+int dsr_plan_set_profile(dsr_plan_t* p, int on) {
+  if (!p) return -1;
+  for (auto& r : p->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  p->prof.clear();
+  p->profile = on ? 1 : 0;
+  return 0;
+}
+int dsr_plan_profile_read(dsr_plan_t* p, int cls, double* ms_total, double* flops_total, int* launches) {
+  if (!p) return -1;
+  double ms = 0.0, fl = 0.0;
+  int n = 0;
+  for (auto& r : p->prof) {
+    if (r.cls != cls) continue;
+    cudaError_t e = cudaEventSynchronize(r.b);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    float t = 0.f;
+    e = cudaEventElapsedTime(&t, r.a, r.b);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    ms += t;
+    fl += r.flops;
+    ++n;
+  }
+  if (ms_total) *ms_total = ms;
+  if (flops_total) *flops_total = fl;
+  if (launches) *launches = n;
+  return 0;
 }
 int dsr_plan_device_error(dsr_plan_t* p, int* host_code) {
   if (!p || !p->bound || !host_code) return -1;

@@ -58,18 +58,22 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity
   return ok;
 }
 
-// Bounded wait: a protocol bug must not hang the GPU box (a hang is a strike).  On timeout the
-// kernel records a code in *err (global) and traps; the host sees a launch failure, not a hang.
+// Bounded wait: a protocol bug must not hang the GPU box (a hang is a strike) and must not poison the
+// context either.  On timeout the kernel records a code in *err (global) and every later wait of
+// the grid returns immediately, so the launch drains with garbage results; the host reads the
+// error word (dsr_plan_device_error) and reports it.
 #ifndef DSR_MBAR_SPIN_LIMIT
-#define DSR_MBAR_SPIN_LIMIT (1u << 24)
+#define DSR_MBAR_SPIN_LIMIT (1u << 22)
 #endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err, int code) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > DSR_MBAR_SPIN_LIMIT) {
-      if (err) atomicExch(err, code);
-      __threadfence_system();
-      __trap();
+    ++spins;
+    if ((spins & 255u) == 0 && err != nullptr && *reinterpret_cast<volatile int*>(err) != 0) return;
+    if (spins > DSR_MBAR_SPIN_LIMIT) {
+      if (err) atomicCAS(err, 0, code);
+      __threadfence();
+      return;
     }
   }
 }

@@ -123,6 +123,12 @@ int dsr_plan_set_debug_conv(dsr_plan_t* p, int use_checker_kernels);
  * contents: what = 0 fprop (zeroes the layer's BN sums first), 1 dgrad, 2 wgrad (zeroes the layer's packed
  * gradient first); use_checker = 1 runs the CUDA-core checker kernel instead.  Tests compare the two. */
 int dsr_plan_debug_replay(dsr_plan_t* p, const char* layer, int what, int use_checker, void* stream);
+/* Per-launch CUDA-event timing of the tensor-core kernels (used by bench.py for the roofline figure; off by
+ * default).  set_profile(on) clears earlier records.  profile_read sums, for kernel class `cls` (0 = implicit-GEMM
+ * conv kernel: fprop + dgrad launches, 1 = wgrad kernel), the event-measured milliseconds, the algorithmic FLOPs
+ * (2*M*N*K per pass, true channel counts) and the number of launches recorded since; it synchronises on them. */
+int dsr_plan_set_profile(dsr_plan_t* p, int on);
+int dsr_plan_profile_read(dsr_plan_t* p, int cls, double* ms_total, double* flops_total, int* launches);
 /* Device error word written by a kernel whose mbarrier wait timed out (0 = none). */
 int dsr_plan_device_error(dsr_plan_t* p, int* host_code);
 /* Device-to-device copy on `stream` (lets ctypes callers read an introspected tensor into their own buffer). */

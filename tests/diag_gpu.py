@@ -41,6 +41,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--mode', default='checker', choices=['checker', 'replay', 'tc'])
     ap.add_argument('--fixture', default='step_64x64.pt')
+    ap.add_argument('--only', default='', help='replay mode: what:layer, e.g. 2:L0.u2')
     ap.add_argument('--size', type=int, default=0, help='use a random problem of this size instead of the fixture')
     args = ap.parse_args()
     dev = torch.device('cuda:0')
@@ -111,14 +112,17 @@ def main():
             ]
             print(P, '  '.join(f'{k} {rel(a, b.detach()):.2e}' for k, a, b in rows))
         print(f'==== {tag}: backward intermediates ====')
+        gsc = net.debug_tensor('gscale', hw).flatten().cpu()
+        S = float(gsc[6])
+        print(f'gradient scale used {S}, amax {float(gsc[4]):.3e}, non-finite passes {float(gsc[5])}')
         for i in range(5):
             P = f'L{i}.'
             rows = []
             for ours, theirs in (('u2_dr', 'u2_raw'), ('u1_dr', 'u1_raw'), ('d2_dr', 'd2_raw'), ('d1_dr', 'd1_raw')):
                 g = taps[P + theirs].grad
-                rows.append((ours, nchw(net.debug_tensor(P + ours, hw), 1), g))
+                rows.append((ours, nchw(net.debug_tensor(P + ours, hw), 1) / S, g))
             gc = taps[P + 'cat'].grad
-            rows.append(('dsraw', nchw(net.debug_tensor(P + 'dsraw', hw), 0), taps[P + 'skip_raw'].grad))
+            rows.append(('dsraw', nchw(net.debug_tensor(P + 'dsraw', hw), 0) / S, taps[P + 'skip_raw'].grad))
             print(P, '  '.join(f'{k} {rel(a, b):.2e}' for k, a, b in rows), f'|gcat| {float(gc.norm()):.2e}')
 
     def report_grads(tag):
@@ -158,10 +162,18 @@ def main():
                     layer = f'L{i}.{tag}'
                     if what == 1 and layer == 'L0.d1':
                         continue
+                    if args.only and args.only != f'{what}:{layer}':
+                        continue
                     res = {}
                     for chk in (1, 0):
                         check(lib.dsr_plan_debug_replay(plan.handle, layer.encode(), what, chk, stream), 'replay')
                         torch.cuda.synchronize()
+                        if chk == 0:
+                            import ctypes
+                            code = ctypes.c_int()
+                            check(lib.dsr_plan_device_error(plan.handle, ctypes.byref(code)))
+                            if code.value:
+                                print(f'!! device error word {code.value} after {wname} {layer}', flush=True)
                         res[chk] = net.debug_tensor(layer + suffix, hw).float().cpu()
                         if what == 0:
                             res[(chk, 's')] = net.debug_tensor(layer + '_stats', hw).float().cpu()
