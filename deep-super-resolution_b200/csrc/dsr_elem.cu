@@ -39,6 +39,22 @@ __device__ __forceinline__ void store8h(__half* p, const float (&f)[8]) {
   for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
   *reinterpret_cast<uint4*>(p) = u;
 }
+__device__ __forceinline__ void cvt4h(uint2 u, float (&f)[4]) {
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+  const float2 a = __half22float2(h[0]), b = __half22float2(h[1]);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
+}
+__device__ __forceinline__ uint2 pack4h(const float (&f)[4]) {
+  uint2 u;
+  __half2* h = reinterpret_cast<__half2*>(&u);
+  h[0] = __floats2half2_rn(f[0], f[1]);
+  h[1] = __floats2half2_rn(f[2], f[3]);
+  return u;
+}
+// streaming 8-byte accesses (each activation byte is touched once per pass)
+__device__ __forceinline__ uint2 ldg8(const __half* p) { return __ldg(reinterpret_cast<const uint2*>(p)); }
+__device__ __forceinline__ void stg8(__half* p, uint2 v) { *reinterpret_cast<uint2*>(p) = v; }
+
 // Padded coordinates an interior index i in [0, n) occupies under ReflectionPad(1): itself and,
 // for i == 1 / i == n-2, the mirrored halo cell.  The same list is the set of padded cells whose
 // data-gradient folds back onto i.
@@ -146,41 +162,73 @@ int launch_input_pack(const float* z, void* xpad, int C, int H, int W, cudaStrea
 // =============================================================================================
 // BN apply + LeakyReLU (+ reflected halo)
 // =============================================================================================
-__global__ void bn_act_kernel(const __half* __restrict__ raw, BnRef bn, __half* __restrict__ act, int H, int W,
-                              int halo) {
-  const int g = threadIdx.x & 15;
-  float scale[8], shift[8];
+// Thread mapping of the 128-channel bandwidth kernels: one warp per pixel per access (lane = 4 channels = 8 bytes,
+// a warp access is one 256-byte pixel row), kPixUnroll pixels in flight per warp so that every thread keeps
+// several independent loads outstanding; ~50 registers -> 4+ resident blocks per SM.
+constexpr int kPixUnroll = 4;
+
+// (y, x) of pixel base + u given (y0, x0) of pixel `base`: one integer division per kPixUnroll pixels
+__device__ __forceinline__ void pix_advance(int y0, int x0, int u, int W, int& y, int& x) {
+  y = y0;
+  x = x0 + u;
+  while (x >= W) { x -= W; ++y; }
+}
+
+__global__ void __launch_bounds__(kThreads) bn_act_kernel(const __half* __restrict__ raw, BnRef bn,
+                                                          __half* __restrict__ act, int H, int W, int halo) {
+  const int lane = threadIdx.x & 31;
+  float scale[4], shift[4];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
+  for (int j = 0; j < 4; ++j) {
     float mean, rstd, ga, be;
-    bn_coeffs(bn, g * 8 + j, mean, rstd, ga, be);
+    bn_coeffs(bn, lane * 4 + j, mean, rstd, ga, be);
     scale[j] = ga * rstd;
     shift[j] = be - mean * scale[j];
   }
-  const long long npix = static_cast<long long>(H) * W;
+  const int npix = H * W;
   const int Wp = W + 2;
-  for (long long pix = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 4; pix < npix;
-       pix += (static_cast<long long>(gridDim.x) * blockDim.x) >> 4) {
-    const int y = static_cast<int>(pix / W), x = static_cast<int>(pix % W);
-    float f[8];
-    load8h(raw + pix * 128 + g * 8, f);
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int base = (((blockIdx.x * blockDim.x) + threadIdx.x) >> 5) * kPixUnroll; base < npix;
+       base += warps * kPixUnroll) {
+    uint2 v[kPixUnroll];
+    const int y0 = base / W, x0 = base - y0 * W;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) f[j] = lrelu(f[j] * scale[j] + shift[j]);
-    if (halo) {
-      int ys[3], xs[3];
-      const int ny = halo_coords(y, H, ys), nx = halo_coords(x, W, xs);
-      for (int a = 0; a < ny; ++a)
-        for (int b = 0; b < nx; ++b) store8h(act + (static_cast<long long>(ys[a]) * Wp + xs[b]) * 128 + g * 8, f);
-    } else {
-      store8h(act + (static_cast<long long>(y + 1) * Wp + (x + 1)) * 128 + g * 8, f);
+    for (int u = 0; u < kPixUnroll; ++u)
+      if (base + u < npix) v[u] = ldg8(raw + static_cast<long long>(base + u) * 128 + lane * 4);
+#pragma unroll
+    for (int u = 0; u < kPixUnroll; ++u) {
+      const int pix = base + u;
+      if (pix >= npix) break;
+      float f[4];
+      cvt4h(v[u], f);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) f[j] = lrelu(fmaf(f[j], scale[j], shift[j]));
+      const uint2 o = pack4h(f);
+      int y, x;
+      pix_advance(y0, x0, u, W, y, x);
+      stg8(act + (static_cast<long long>(y + 1) * Wp + (x + 1)) * 128 + lane * 4, o);
+      if (halo && (x == 1 || x == W - 2 || y == 1 || y == H - 2)) {       // warp-uniform: reflected copies
+        int ys[3], xs[3];
+        const int ny = halo_coords(y, H, ys), nx = halo_coords(x, W, xs);
+        for (int a = 0; a < ny; ++a)
+          for (int b = 0; b < nx; ++b)
+            if (a | b) stg8(act + (static_cast<long long>(ys[a]) * Wp + xs[b]) * 128 + lane * 4, o);
+      }
     }
   }
 }
 
+inline int warp_grid(int H, int W, int cap_blocks) {      // one warp per kPixUnroll pixels per iteration
+  const long long npix = static_cast<long long>(H) * W;
+  long long b = (npix + (kThreads / 32) * kPixUnroll - 1) / ((kThreads / 32) * kPixUnroll);
+  if (b > cap_blocks) b = cap_blocks;
+  if (b < 1) b = 1;
+  return static_cast<int>(b);
+}
+
 int launch_bn_act(const void* raw, BnRef bn, void* act_pad, int H, int W, int halo, cudaStream_t s) {
-  const long long items = static_cast<long long>(H) * W * 16;
-  bn_act_kernel<<<grid_for(items, kThreads, 148 * 16), kThreads, 0, s>>>(static_cast<const __half*>(raw), bn,
-                                                                        static_cast<__half*>(act_pad), H, W, halo);
+  bn_act_kernel<<<warp_grid(H, W, 148 * 8), kThreads, 0, s>>>(
+      static_cast<const __half*>(raw), bn, static_cast<__half*>(act_pad), H, W, halo);
   DSR_LAUNCH_CHECK();
 }
 
@@ -252,26 +300,53 @@ int launch_skip_conv(const void* xpad, int Cin, const float* w, float* sraw, flo
 // =============================================================================================
 // upsample + concat + BN(132)
 // =============================================================================================
-// value of the 8 upsampled channels [g*8, g*8+8) at concat pixel (y, x)
-__device__ __forceinline__ void upsample8(const UpcatArgs& a, int y, int x, int g, float (&u)[8]) {
-  int y0, y1, x0, x1;
-  float ly0, ly1, lx0, lx1;
-  up_src(y, a.h, y0, y1, ly0, ly1);
-  up_src(x, a.w, x0, x1, lx0, lx1);
-  const __half* d = static_cast<const __half*>(a.deep);
-  float f00[8], f01[8], f10[8], f11[8];
-  load8h(d + y0 * a.deep_sy + static_cast<long long>(x0) * 128 + g * 8, f00);
-  load8h(d + y0 * a.deep_sy + static_cast<long long>(x1) * 128 + g * 8, f01);
-  load8h(d + y1 * a.deep_sy + static_cast<long long>(x0) * 128 + g * 8, f10);
-  load8h(d + y1 * a.deep_sy + static_cast<long long>(x1) * 128 + g * 8, f11);
+// Bilinear x2 (align_corners = False) evaluated per 2x2 OUTPUT block: outputs (2by+1+r, 2bx+1+c), r,c in {0,1},
+// read exactly the sources (by..by+1) x (bx..bx+1) (clamped) with the constant weights {3/4, 1/4}; block indices
+// run over [-1, h-1] x [-1, w-1] so that the clamped first / last output rows and columns are covered.  One warp
+// per block (lane = 4 channels): 4 source loads serve 4 output pixels, no per-pixel coordinate arithmetic.
+struct UpBlock {
+  int oy0, ox0;              // output coordinates of (r, c) = (0, 0); may be -1 (invalid) at the top / left edge
+  const __half* p00; const __half* p01; const __half* p10; const __half* p11;
+};
+__device__ __forceinline__ UpBlock up_block(const UpcatArgs& a, int blk, int lane) {
+  const int bw = a.w + 1;
+  const int by = blk / bw - 1, bx = blk - (blk / bw) * bw - 1;
+  const int sy0 = max(by, 0), sy1 = min(by + 1, a.h - 1), sx0 = max(bx, 0), sx1 = min(bx + 1, a.w - 1);
+  const __half* d = static_cast<const __half*>(a.deep) + lane * 4;
+  UpBlock b;
+  b.oy0 = 2 * by + 1;
+  b.ox0 = 2 * bx + 1;
+  b.p00 = d + sy0 * a.deep_sy + static_cast<long long>(sx0) * 128;
+  b.p01 = d + sy0 * a.deep_sy + static_cast<long long>(sx1) * 128;
+  b.p10 = d + sy1 * a.deep_sy + static_cast<long long>(sx0) * 128;
+  b.p11 = d + sy1 * a.deep_sy + static_cast<long long>(sx1) * 128;
+  return b;
+}
+struct UpRaw { uint2 v00, v01, v10, v11; };
+__device__ __forceinline__ UpRaw up_load(const UpBlock& t) {
+  UpRaw r;
+  r.v00 = ldg8(t.p00); r.v01 = ldg8(t.p01); r.v10 = ldg8(t.p10); r.v11 = ldg8(t.p11);
+  return r;
+}
+// u[r][c][j]: the four output pixels of the block, 4 channels each
+__device__ __forceinline__ void up_eval(const UpRaw& r, float (&u)[2][2][4]) {
+  float f00[4], f01[4], f10[4], f11[4];
+  cvt4h(r.v00, f00); cvt4h(r.v01, f01); cvt4h(r.v10, f10); cvt4h(r.v11, f11);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) u[j] = ly0 * (lx0 * f00[j] + lx1 * f01[j]) + ly1 * (lx0 * f10[j] + lx1 * f11[j]);
+  for (int j = 0; j < 4; ++j) {
+    const float t0 = 0.75f * f00[j] + 0.25f * f01[j], t1 = 0.25f * f00[j] + 0.75f * f01[j];   // source row 0, c = 0, 1
+    const float b0 = 0.75f * f10[j] + 0.25f * f11[j], b1 = 0.25f * f10[j] + 0.75f * f11[j];   // source row 1
+    u[0][0][j] = 0.75f * t0 + 0.25f * b0;
+    u[0][1][j] = 0.75f * t1 + 0.25f * b1;
+    u[1][0][j] = 0.25f * t0 + 0.75f * b0;
+    u[1][1][j] = 0.25f * t1 + 0.75f * b1;
+  }
 }
 
-// skip activation LeakyReLU(BN4(sraw)) at a pixel, plus (optionally) xhat and y of the BN(4)
+// skip activation LeakyReLU(BN4(sraw)) at a pixel, plus xhat and y of the BN(4)
 __device__ __forceinline__ void skip_act4(const UpcatArgs& a, long long pix, float (&sv)[4], float (&xh)[4],
                                           float (&yv)[4]) {
-  const float4 r = *reinterpret_cast<const float4*>(a.sraw + pix * 4);
+  const float4 r = __ldg(reinterpret_cast<const float4*>(a.sraw + pix * 4));
   const float rr[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
   for (int o = 0; o < 4; ++o) {
@@ -283,39 +358,56 @@ __device__ __forceinline__ void skip_act4(const UpcatArgs& a, long long pix, flo
   }
 }
 
-__global__ void upcat_stats_kernel(UpcatArgs a) {
-  const int g = threadIdx.x & 15;
-  float s[8], q[8], s4[4] = {0, 0, 0, 0}, q4[4] = {0, 0, 0, 0};
+constexpr int kUpUnroll = 2;     // 2x2 blocks in flight per warp
+
+__global__ void __launch_bounds__(kThreads, 3) upcat_stats_kernel(UpcatArgs a) {
+  const int lane = threadIdx.x & 31;
+  float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0}, s4[4] = {0, 0, 0, 0}, q4[4] = {0, 0, 0, 0};
+  const int nblk = (a.h + 1) * (a.w + 1);
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int base = (((blockIdx.x * blockDim.x) + threadIdx.x) >> 5) * kUpUnroll; base < nblk;
+       base += warps * kUpUnroll) {
+    UpBlock t[kUpUnroll];
+    UpRaw r[kUpUnroll];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
-  const long long npix = static_cast<long long>(a.H) * a.W;
-  for (long long pix = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 4; pix < npix;
-       pix += (static_cast<long long>(gridDim.x) * blockDim.x) >> 4) {
-    const int y = static_cast<int>(pix / a.W), x = static_cast<int>(pix % a.W);
-    float u[8];
-    upsample8(a, y, x, g, u);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      // statistics of the value that will be normalised (fp32 interpolation result)
-      s[j] += u[j];
-      q[j] += u[j] * u[j];
+    for (int u = 0; u < kUpUnroll; ++u) {
+      t[u] = up_block(a, min(base + u, nblk - 1), lane);
+      r[u] = up_load(t[u]);
     }
-    if (g == 0) {
-      float sv[4], xh[4], yv[4];
-      skip_act4(a, pix, sv, xh, yv);
 #pragma unroll
-      for (int o = 0; o < 4; ++o) { s4[o] += sv[o]; q4[o] += sv[o] * sv[o]; }
+    for (int u = 0; u < kUpUnroll; ++u) {
+      if (base + u >= nblk) break;
+      float v[2][2][4];
+      up_eval(r[u], v);
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          const int oy = t[u].oy0 + rr, ox = t[u].ox0 + cc;
+          if (oy < 0 || ox < 0 || oy >= a.H || ox >= a.W) continue;       // warp-uniform
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { s[j] += v[rr][cc][j]; q[j] = fmaf(v[rr][cc][j], v[rr][cc][j], q[j]); }
+        }
+      if (lane < 4) {                       // lane l: skip channels of output pixel (l >> 1, l & 1)
+        const int oy = t[u].oy0 + (lane >> 1), ox = t[u].ox0 + (lane & 1);
+        if (oy >= 0 && ox >= 0 && oy < a.H && ox < a.W) {
+          float sv[4], xh[4], yv[4];
+          skip_act4(a, static_cast<long long>(oy) * a.W + ox, sv, xh, yv);
+#pragma unroll
+          for (int o = 0; o < 4; ++o) { s4[o] += sv[o]; q4[o] = fmaf(sv[o], sv[o], q4[o]); }
+        }
+      }
     }
   }
   __shared__ float red[2 * 144];
   for (int i = threadIdx.x; i < 2 * 144; i += blockDim.x) red[i] = 0.f;
   __syncthreads();
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    atomicAdd(&red[g * 8 + j], s[j]);
-    atomicAdd(&red[144 + g * 8 + j], q[j]);
+  for (int j = 0; j < 4; ++j) {
+    atomicAdd(&red[lane * 4 + j], s[j]);
+    atomicAdd(&red[144 + lane * 4 + j], q[j]);
   }
-  if (g == 0) {
+  if (lane < 4) {
 #pragma unroll
     for (int o = 0; o < 4; ++o) {
       atomicAdd(&red[128 + o], s4[o]);
@@ -338,63 +430,94 @@ __device__ __forceinline__ void cat_coeffs(const UpcatArgs& a, int c, float& mea
   be = a.cat_beta[rc];
 }
 
-__global__ void upcat_apply_kernel(UpcatArgs a) {
-  const int g = threadIdx.x & 15;
-  float scale[8], shift[8];
+__global__ void __launch_bounds__(kThreads, 3) upcat_apply_kernel(UpcatArgs a) {
+  const int lane = threadIdx.x & 31;
+  float scale[4], shift[4], sc4[4], sh4[4];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
+  for (int j = 0; j < 4; ++j) {
     float mean, rstd, ga, be;
-    cat_coeffs(a, g * 8 + j, mean, rstd, ga, be);
+    cat_coeffs(a, lane * 4 + j, mean, rstd, ga, be);
     scale[j] = ga * rstd;
     shift[j] = be - mean * scale[j];
+    cat_coeffs(a, 128 + j, mean, rstd, ga, be);
+    sc4[j] = ga * rstd;
+    sh4[j] = be - mean * sc4[j];
   }
-  float sc4[4], sh4[4];
-#pragma unroll
-  for (int o = 0; o < 4; ++o) {
-    float mean, rstd, ga, be;
-    cat_coeffs(a, 128 + o, mean, rstd, ga, be);
-    sc4[o] = ga * rstd;
-    sh4[o] = be - mean * sc4[o];
-  }
-  const long long npix = static_cast<long long>(a.H) * a.W;
+  const int nblk = (a.h + 1) * (a.w + 1);
   const int Wp = a.W + 2;
   __half* out = static_cast<__half*>(a.cat_pad);
-  for (long long pix = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 4; pix < npix;
-       pix += (static_cast<long long>(gridDim.x) * blockDim.x) >> 4) {
-    const int y = static_cast<int>(pix / a.W), x = static_cast<int>(pix % a.W);
-    float u[8];
-    upsample8(a, y, x, g, u);
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int base = (((blockIdx.x * blockDim.x) + threadIdx.x) >> 5) * kUpUnroll; base < nblk;
+       base += warps * kUpUnroll) {
+    UpBlock t[kUpUnroll];
+    UpRaw r[kUpUnroll];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) u[j] = u[j] * scale[j] + shift[j];
-    float t0[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t1[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (g == 0) {
-      float sv[4], xh[4], yv[4];
-      skip_act4(a, pix, sv, xh, yv);
-#pragma unroll
-      for (int o = 0; o < 4; ++o) t0[o] = sv[o] * sc4[o] + sh4[o];
+    for (int u = 0; u < kUpUnroll; ++u) {
+      t[u] = up_block(a, min(base + u, nblk - 1), lane);
+      r[u] = up_load(t[u]);
     }
-    int ys[3], xs[3];
-    const int ny = halo_coords(y, a.H, ys), nx = halo_coords(x, a.W, xs);
-    for (int i = 0; i < ny; ++i)
-      for (int k = 0; k < nx; ++k) {
-        __half* dst = out + (static_cast<long long>(ys[i]) * Wp + xs[k]) * 144;
-        store8h(dst + g * 8, u);
-        if (g == 0) {
-          store8h(dst + 128, t0);
-          store8h(dst + 136, t1);
+#pragma unroll
+    for (int u = 0; u < kUpUnroll; ++u) {
+      if (base + u >= nblk) break;
+      float v[2][2][4];
+      up_eval(r[u], v);
+      // the 16 tail channels [128, 144) of the block's four pixels: lane l < 4 evaluates the skip channels of pixel l
+      uint2 mytail = make_uint2(0u, 0u);
+      if (lane < 4) {
+        const int oy = t[u].oy0 + (lane >> 1), ox = t[u].ox0 + (lane & 1);
+        if (oy >= 0 && ox >= 0 && oy < a.H && ox < a.W) {
+          float sv[4], xh[4], yv[4], t0[4];
+          skip_act4(a, static_cast<long long>(oy) * a.W + ox, sv, xh, yv);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) t0[k] = fmaf(sv[k], sc4[k], sh4[k]);
+          mytail = pack4h(t0);
         }
       }
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          const int y = t[u].oy0 + rr, x = t[u].ox0 + cc;
+          uint2 tail;                         // skip channels of pixel (rr, cc) live in lane rr*2+cc
+          tail.x = __shfl_sync(0xffffffffu, mytail.x, rr * 2 + cc);
+          tail.y = __shfl_sync(0xffffffffu, mytail.y, rr * 2 + cc);
+          if (y < 0 || x < 0 || y >= a.H || x >= a.W) continue;             // warp-uniform
+          float o4[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) o4[j] = fmaf(v[rr][cc][j], scale[j], shift[j]);
+          const uint2 o = pack4h(o4);
+          if (lane != 0) tail = make_uint2(0u, 0u);                         // lanes 1..3 write the 12 zero channels
+          int ys[3], xs[3];
+          int ny = 1, nx = 1;
+          ys[0] = y + 1;
+          xs[0] = x + 1;
+          if (x == 1 || x == a.W - 2 || y == 1 || y == a.H - 2) {           // warp-uniform: reflected halo copies
+            ny = halo_coords(y, a.H, ys);
+            nx = halo_coords(x, a.W, xs);
+          }
+          for (int i = 0; i < ny; ++i)
+            for (int k = 0; k < nx; ++k) {
+              __half* dst = out + (static_cast<long long>(ys[i]) * Wp + xs[k]) * 144;
+              stg8(dst + lane * 4, o);
+              if (lane < 4) stg8(dst + 128 + lane * 4, tail);
+            }
+        }
+    }
   }
 }
 
+static int up_grid(const UpcatArgs& a, int cap) {
+  const long long nblk = static_cast<long long>(a.h + 1) * (a.w + 1);
+  long long blocks = (nblk + 8 * kUpUnroll - 1) / (8 * kUpUnroll);
+  if (blocks > cap) blocks = cap;
+  return static_cast<int>(blocks < 1 ? 1 : blocks);
+}
 int launch_upcat_stats(const UpcatArgs& a, cudaStream_t s) {
-  const long long items = static_cast<long long>(a.H) * a.W * 16;
-  upcat_stats_kernel<<<grid_for(items, kThreads, 148 * 4), kThreads, 0, s>>>(a);
+  upcat_stats_kernel<<<up_grid(a, 148 * 6), kThreads, 0, s>>>(a);
   DSR_LAUNCH_CHECK();
 }
 int launch_upcat_apply(const UpcatArgs& a, cudaStream_t s) {
-  const long long items = static_cast<long long>(a.H) * a.W * 16;
-  upcat_apply_kernel<<<grid_for(items, kThreads, 148 * 16), kThreads, 0, s>>>(a);
+  upcat_apply_kernel<<<up_grid(a, 148 * 12), kThreads, 0, s>>>(a);
   DSR_LAUNCH_CHECK();
 }
 
@@ -457,56 +580,77 @@ int launch_final_conv(const void* act_pad, const float* w, const float* b, float
 // =============================================================================================
 // final conv backward
 // =============================================================================================
-__global__ void final_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ out,
-                                 const __half* __restrict__ act, const float* __restrict__ w,
-                                 __half* __restrict__ dact, float* __restrict__ dw, float* __restrict__ db,
-                                 const float* __restrict__ gs, int H, int W) {
-  const int g = threadIdx.x & 15;
+// One warp per 32 consecutive pixels: lane l first forms dp[o] = S * gout * out * (1 - out) of pixel base + l
+// (coalesced fp32 plane reads), then the warp walks the 32 pixels (lane = 4 channels), 4 pixels in flight.
+__global__ void __launch_bounds__(kThreads, 3) final_bwd_kernel(const float* __restrict__ gout,
+                                                                const float* __restrict__ out,
+                                                                const __half* __restrict__ act,
+                                                                const float* __restrict__ w, __half* __restrict__ dact,
+                                                                float* __restrict__ dw, float* __restrict__ db,
+                                                                const float* __restrict__ gs, int H, int W) {
+  const int lane = threadIdx.x & 31;
+  const int c0 = lane * 4;
   const float S = gs[0], invS = gs[1];
-  float wr[3][8], aw[3][8], ab[3] = {0, 0, 0};
+  float wr[3][4], aw[3][4], ab[3] = {0, 0, 0};
 #pragma unroll
   for (int o = 0; o < 3; ++o)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      wr[o][j] = w[o * 128 + g * 8 + j];
+    for (int j = 0; j < 4; ++j) {
+      wr[o][j] = w[o * 128 + c0 + j];
       aw[o][j] = 0.f;
     }
-  const long long npix = static_cast<long long>(H) * W;
+  const int npix = H * W;
   const int Wp = W + 2;
-  for (long long pix = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 4; pix < npix;
-       pix += (static_cast<long long>(gridDim.x) * blockDim.x) >> 4) {
-    const int y = static_cast<int>(pix / W), x = static_cast<int>(pix % W);
-    float dp[3];
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int base = (((blockIdx.x * blockDim.x) + threadIdx.x) >> 5) * 32; base < npix; base += warps * 32) {
+    float dp[3] = {0, 0, 0};
+    if (base + lane < npix) {
 #pragma unroll
-    for (int o = 0; o < 3; ++o) {
-      const float ov = out[o * npix + pix];
-      dp[o] = S * gout[o * npix + pix] * ov * (1.f - ov);
+      for (int o = 0; o < 3; ++o) {
+        const float ov = __ldg(out + static_cast<long long>(o) * npix + base + lane);
+        dp[o] = S * __ldg(gout + static_cast<long long>(o) * npix + base + lane) * ov * (1.f - ov);
+        ab[o] += dp[o];
+      }
     }
-    const long long off = (static_cast<long long>(y + 1) * Wp + (x + 1)) * 128 + g * 8;
-    float f[8], da[8];
-    load8h(act + off, f);
+    const int cnt = min(32, npix - base);
+    for (int j0 = 0; j0 < cnt; j0 += 4) {
+      uint2 v[4];
+      long long off[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      da[j] = dp[0] * wr[0][j] + dp[1] * wr[1][j] + dp[2] * wr[2][j];
+      for (int u = 0; u < 4; ++u) {
+        const int pix = min(base + j0 + u, npix - 1);
+        const int y = pix / W, x = pix - y * W;
+        off[u] = (static_cast<long long>(y + 1) * Wp + (x + 1)) * 128 + c0;
+        v[u] = ldg8(act + off[u]);
+      }
 #pragma unroll
-      for (int o = 0; o < 3; ++o) aw[o][j] = fmaf(dp[o], f[j], aw[o][j]);
-    }
-    store8h(dact + off, da);
-    if (g == 0) {
+      for (int u = 0; u < 4; ++u) {
+        const float d0 = __shfl_sync(0xffffffffu, dp[0], j0 + u);
+        const float d1 = __shfl_sync(0xffffffffu, dp[1], j0 + u);
+        const float d2 = __shfl_sync(0xffffffffu, dp[2], j0 + u);
+        if (j0 + u < cnt) {
+          float f[4], da[4];
+          cvt4h(v[u], f);
 #pragma unroll
-      for (int o = 0; o < 3; ++o) ab[o] += dp[o];
+          for (int j = 0; j < 4; ++j) {
+            da[j] = d0 * wr[0][j] + d1 * wr[1][j] + d2 * wr[2][j];
+            aw[0][j] = fmaf(d0, f[j], aw[0][j]);
+            aw[1][j] = fmaf(d1, f[j], aw[1][j]);
+            aw[2][j] = fmaf(d2, f[j], aw[2][j]);
+          }
+          stg8(dact + off[u], pack4h(da));
+        }
+      }
     }
   }
   __shared__ float red[3 * 128 + 3];
   for (int i = threadIdx.x; i < 3 * 128 + 3; i += blockDim.x) red[i] = 0.f;
   __syncthreads();
 #pragma unroll
-  for (int o = 0; o < 3; ++o)
+  for (int o = 0; o < 3; ++o) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(&red[o * 128 + g * 8 + j], aw[o][j]);
-  if (g == 0) {
-#pragma unroll
-    for (int o = 0; o < 3; ++o) atomicAdd(&red[384 + o], ab[o]);
+    for (int j = 0; j < 4; ++j) atomicAdd(&red[o * 128 + c0 + j], aw[o][j]);
+    atomicAdd(&red[384 + o], ab[o]);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 3 * 128; i += blockDim.x) atomicAdd(&dw[i], red[i] * invS);
@@ -515,8 +659,10 @@ __global__ void final_bwd_kernel(const float* __restrict__ gout, const float* __
 
 int launch_final_bwd(const float* gout, const float* out, const void* act_pad, const float* w, void* dact_pad,
                      float* dw, float* db, const float* gs, int H, int W, cudaStream_t s) {
-  const long long items = static_cast<long long>(H) * W * 16;
-  final_bwd_kernel<<<grid_for(items, kThreads, 148 * 4), kThreads, 0, s>>>(
+  const long long npix = static_cast<long long>(H) * W;
+  long long blocks = (npix + 255) / 256;
+  if (blocks > 148 * 6) blocks = 148 * 6;
+  final_bwd_kernel<<<static_cast<int>(blocks), kThreads, 0, s>>>(
       gout, out, static_cast<const __half*>(act_pad), w, static_cast<__half*>(dact_pad), dw, db, gs, H, W);
   DSR_LAUNCH_CHECK();
 }
@@ -524,95 +670,122 @@ int launch_final_bwd(const float* gout, const float* out, const void* act_pad, c
 // =============================================================================================
 // BN + LeakyReLU backward (128 channels)
 // =============================================================================================
-// gradient w.r.t. the activation at interior pixel (y, x), 8 channels of group g
-__device__ __forceinline__ void bn_bwd_gather(const BnBwdArgs& a, int y, int x, int g, const float (&ws)[4][8],
-                                              float (&da)[8]) {
-  const __half* gp = static_cast<const __half*>(a.g);
-  const int Wp = a.W + 2;
-  if (a.fold) {
-    int ys[3], xs[3];
-    const int ny = halo_coords(y, a.H, ys), nx = halo_coords(x, a.W, xs);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) da[j] = 0.f;
-    for (int i = 0; i < ny; ++i)
-      for (int k = 0; k < nx; ++k) {
-        float f[8];
-        load8h(gp + (static_cast<long long>(ys[i]) * Wp + xs[k]) * a.gC + g * 8, f);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) da[j] += f[j];
-      }
-  } else {
-    load8h(gp + (static_cast<long long>(y + 1) * Wp + (x + 1)) * a.gC + g * 8, da);
-  }
-  if (a.ds != nullptr) {
-    const float4 d = *reinterpret_cast<const float4*>(a.ds + (static_cast<long long>(y) * a.W + x) * 4);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) da[j] += d.x * ws[0][j] + d.y * ws[1][j] + d.z * ws[2][j] + d.w * ws[3][j];
-  }
-}
-
-template <bool APPLY>
-__global__ void bn_bwd_kernel(BnBwdArgs a) {
-  const int g = threadIdx.x & 15;
-  float mean[8], rstd[8], ga[8], be[8], ws[4][8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) bn_coeffs(a.bn, g * 8 + j, mean[j], rstd[j], ga[j], be[j]);
-#pragma unroll
-  for (int o = 0; o < 4; ++o)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) ws[o][j] = (a.ds != nullptr) ? a.wskip[o * 128 + g * 8 + j] : 0.f;
-  float c1[8], c2[8], s1[8], s2[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    if (APPLY) {
-      c1[j] = a.bstats[g * 8 + j] * a.bn.inv_n;          // mean dy
-      c2[j] = a.bstats[128 + g * 8 + j] * a.bn.inv_n;    // mean dy*xhat
+template <bool APPLY, bool HAS_DS>
+__global__ void __launch_bounds__(kThreads, HAS_DS ? 2 : 3) bn_bwd_kernel(BnBwdArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int c0 = lane * 4;
+  // xhat = r * xa + xb;  y = ga * xhat + be;  APPLY: dr = k1 * (dy - c1 - xhat * c2)
+  float xa[4], xb[4], ga[4], be[4], c1[4], c2[4], k1[4], s1[4], s2[4];
+  __shared__ float4 sws[4][32];      // skip-conv weights [o][lane] (only with HAS_DS), kept out of the registers
+  if (HAS_DS) {
+    if (threadIdx.x < 128) {
+      const int o = threadIdx.x >> 5, l = threadIdx.x & 31;
+      sws[o][l] = *reinterpret_cast<const float4*>(a.wskip + o * 128 + l * 4);
     }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float mean, rstd;
+    bn_coeffs(a.bn, c0 + j, mean, rstd, ga[j], be[j]);
+    xa[j] = rstd;
+    xb[j] = -mean * rstd;
+    k1[j] = ga[j] * rstd;
+    c1[j] = APPLY ? a.bstats[c0 + j] * a.bn.inv_n : 0.f;
+    c2[j] = APPLY ? a.bstats[128 + c0 + j] * a.bn.inv_n : 0.f;
     s1[j] = 0.f;
     s2[j] = 0.f;
   }
-  const long long npix = static_cast<long long>(a.H) * a.W;
-  const int Wp = a.W + 2;
-  const __half* raw = static_cast<const __half*>(a.raw);
-  __half* dr = static_cast<__half*>(a.dr_pad);
-  float amax = 0.f;
-  bool bad = false;
-  for (long long pix = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 4; pix < npix;
-       pix += (static_cast<long long>(gridDim.x) * blockDim.x) >> 4) {
-    const int y = static_cast<int>(pix / a.W), x = static_cast<int>(pix % a.W);
-    float da[8], r[8];
-    bn_bwd_gather(a, y, x, g, ws, da);
-    load8h(raw + pix * 128 + g * 8, r);
-    float o[8];
+  const int H = a.H, W = a.W, Wp = W + 2;
+  const __half* __restrict__ gp = static_cast<const __half*>(a.g);
+  const __half* __restrict__ raw = static_cast<const __half*>(a.raw);
+  __half* __restrict__ dr = static_cast<__half*>(a.dr_pad);
+  __half2 amax2 = __float2half2_rn(0.f);
+  const int npix = H * W;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int base = (((blockIdx.x * blockDim.x) + threadIdx.x) >> 5) * kPixUnroll; base < npix;
+       base += warps * kPixUnroll) {
+    uint2 vg[kPixUnroll], vr[kPixUnroll];
+    float4 vd[kPixUnroll];
+    const int y0 = base / W, x0 = base - y0 * W;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float xh = (r[j] - mean[j]) * rstd[j];
-      const float yv = ga[j] * xh + be[j];
-      const float dy = da[j] * (yv > 0.f ? 1.f : kSlope);
-      if (APPLY) {
-        o[j] = ga[j] * rstd[j] * (dy - c1[j] - xh * c2[j]);
-        amax = fmaxf(amax, fabsf(o[j]));
-        bad = bad || !isfinite(o[j]);
-      } else {
-        s1[j] += dy;
-        s2[j] += dy * xh;
+    for (int u = 0; u < kPixUnroll; ++u) {
+      const int pix = base + u;
+      if (pix < npix) {
+        int y, x;
+        pix_advance(y0, x0, u, W, y, x);
+        vg[u] = ldg8(gp + (static_cast<long long>(y + 1) * Wp + (x + 1)) * a.gC + c0);
+        vr[u] = ldg8(raw + static_cast<long long>(pix) * 128 + c0);
+        if (HAS_DS) vd[u] = __ldg(reinterpret_cast<const float4*>(a.ds + static_cast<long long>(pix) * 4));
       }
     }
-    if (APPLY) store8h(dr + (static_cast<long long>(y + 1) * Wp + (x + 1)) * 128 + g * 8, o);
+#pragma unroll
+    for (int u = 0; u < kPixUnroll; ++u) {
+      const int pix = base + u;
+      if (pix >= npix) break;
+      int y, x;
+      pix_advance(y0, x0, u, W, y, x);
+      float da[4], r[4];
+      cvt4h(vg[u], da);
+      cvt4h(vr[u], r);
+      if (a.fold && (x == 1 || x == W - 2 || y == 1 || y == H - 2)) {      // warp-uniform: fold the halo copies back
+        int ys[3], xs[3];
+        const int ny = halo_coords(y, H, ys), nx = halo_coords(x, W, xs);
+        for (int ii = 0; ii < ny; ++ii)
+          for (int k = 0; k < nx; ++k)
+            if (ii | k) {
+              float f[4];
+              cvt4h(ldg8(gp + (static_cast<long long>(ys[ii]) * Wp + xs[k]) * a.gC + c0), f);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) da[j] += f[j];
+            }
+      }
+      if (HAS_DS) {
+        const float dd[4] = {vd[u].x, vd[u].y, vd[u].z, vd[u].w};
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+          const float4 w4 = sws[o][lane];
+          da[0] = fmaf(dd[o], w4.x, da[0]);
+          da[1] = fmaf(dd[o], w4.y, da[1]);
+          da[2] = fmaf(dd[o], w4.z, da[2]);
+          da[3] = fmaf(dd[o], w4.w, da[3]);
+        }
+      }
+      float o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float xh = fmaf(r[j], xa[j], xb[j]);
+        const float yv = fmaf(ga[j], xh, be[j]);
+        const float dy = yv > 0.f ? da[j] : kSlope * da[j];
+        if (APPLY) {
+          o[j] = k1[j] * (dy - c1[j] - xh * c2[j]);
+        } else {
+          s1[j] += dy;
+          s2[j] = fmaf(dy, xh, s2[j]);
+        }
+      }
+      if (APPLY) {
+        const uint2 pk = pack4h(o);
+        const __half2* h2 = reinterpret_cast<const __half2*>(&pk);
+        amax2 = __hmax2_nan(amax2, __hmax2_nan(__habs2(h2[0]), __habs2(h2[1])));   // inf / NaN propagate
+        stg8(dr + (static_cast<long long>(y + 1) * Wp + (x + 1)) * 128 + c0, pk);
+      }
+    }
   }
   if (!APPLY) {
     __shared__ float red[256];
     red[threadIdx.x] = 0.f;
     __syncthreads();
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      atomicAdd(&red[g * 8 + j], s1[j]);
-      atomicAdd(&red[128 + g * 8 + j], s2[j]);
+    for (int j = 0; j < 4; ++j) {
+      atomicAdd(&red[c0 + j], s1[j]);
+      atomicAdd(&red[128 + c0 + j], s2[j]);
     }
     __syncthreads();
     atomicAdd(&a.bstats[threadIdx.x], red[threadIdx.x]);
   } else {
-    track_amax(a.gs, amax, bad);
+    const float amax = fmaxf(__low2float(amax2), __high2float(amax2));
+    track_amax(a.gs, isfinite(amax) ? amax : 0.f, !isfinite(amax));
     if (blockIdx.x == 0 && threadIdx.x < 128) {
       a.dbeta[threadIdx.x] = a.bstats[threadIdx.x] * a.gs[1];
       a.dgamma[threadIdx.x] = a.bstats[128 + threadIdx.x] * a.gs[1];
@@ -621,99 +794,130 @@ __global__ void bn_bwd_kernel(BnBwdArgs a) {
 }
 
 int launch_bn_bwd_stats(const BnBwdArgs& a, cudaStream_t s) {
-  const long long items = static_cast<long long>(a.H) * a.W * 16;
-  bn_bwd_kernel<false><<<grid_for(items, kThreads, 148 * 4), kThreads, 0, s>>>(a);
+  const int grid = warp_grid(a.H, a.W, 148 * 4);
+  if (a.ds != nullptr) bn_bwd_kernel<false, true><<<grid, kThreads, 0, s>>>(a);
+  else bn_bwd_kernel<false, false><<<grid, kThreads, 0, s>>>(a);
   DSR_LAUNCH_CHECK();
 }
 int launch_bn_bwd_apply(const BnBwdArgs& a, cudaStream_t s) {
-  const long long items = static_cast<long long>(a.H) * a.W * 16;
-  bn_bwd_kernel<true><<<grid_for(items, kThreads, 148 * 16), kThreads, 0, s>>>(a);
+  const int grid = warp_grid(a.H, a.W, 148 * 8);
+  if (a.ds != nullptr) bn_bwd_kernel<true, true><<<grid, kThreads, 0, s>>>(a);
+  else bn_bwd_kernel<true, false><<<grid, kThreads, 0, s>>>(a);
   DSR_LAUNCH_CHECK();
 }
 
 // =============================================================================================
 // concat BN(132) backward
 // =============================================================================================
-__device__ __forceinline__ void fold_gather(const __half* gp, int C, int H, int W, int y, int x, int coff,
-                                            float (&da)[8]) {
-  int ys[3], xs[3];
-  const int ny = halo_coords(y, H, ys), nx = halo_coords(x, W, xs);
-  const int Wp = W + 2;
+// folded data-gradient of 4 channels at interior pixel (y, x) of a padded-grid tensor with channel pitch C
+__device__ __forceinline__ void fold_gather4(const __half* gp, int C, int H, int W, int y, int x, int coff, uint2 main,
+                                             float (&da)[4]) {
+  cvt4h(main, da);
+  if (x == 1 || x == W - 2 || y == 1 || y == H - 2) {
+    int ys[3], xs[3];
+    const int ny = halo_coords(y, H, ys), nx = halo_coords(x, W, xs);
+    const int Wp = W + 2;
+    for (int i = 0; i < ny; ++i)
+      for (int k = 0; k < nx; ++k)
+        if (i | k) {
+          float f[4];
+          cvt4h(ldg8(gp + (static_cast<long long>(ys[i]) * Wp + xs[k]) * C + coff), f);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) da[j] = 0.f;
-  for (int i = 0; i < ny; ++i)
-    for (int k = 0; k < nx; ++k) {
-      float f[8];
-      load8h(gp + (static_cast<long long>(ys[i]) * Wp + xs[k]) * C + coff, f);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) da[j] += f[j];
-    }
+          for (int j = 0; j < 4; ++j) da[j] += f[j];
+        }
+  }
 }
 
 template <bool APPLY>
-__global__ void upcat_bwd_kernel(UpcatBwdArgs a) {
+__global__ void __launch_bounds__(kThreads, 2) upcat_bwd_kernel(UpcatBwdArgs a) {
   const UpcatArgs& f = a.f;
-  const int g = threadIdx.x & 15;
+  const int lane = threadIdx.x & 31;
+  const int c0 = lane * 4;
   const float inv_n = 1.f / (static_cast<float>(f.H) * static_cast<float>(f.W));
-  float mean[8], rstd[8], ga[8], be[8];
+  // xhat = u * xa + xb;  APPLY: dup = k1 * (dc - c1 - xhat * c2)
+  float xa[4], xb[4], k1[4], c1[4], c2[4], s1[4], s2[4];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) cat_coeffs(f, g * 8 + j, mean[j], rstd[j], ga[j], be[j]);
-  float mean4[4], rstd4[4], ga4[4], be4[4];
-#pragma unroll
-  for (int o = 0; o < 4; ++o) cat_coeffs(f, 128 + o, mean4[o], rstd4[o], ga4[o], be4[o]);
-  float s1[8], s2[8], t1[4] = {0, 0, 0, 0}, t2[4] = {0, 0, 0, 0};
-#pragma unroll
-  for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
-  const long long npix = static_cast<long long>(f.H) * f.W;
+  for (int j = 0; j < 4; ++j) {
+    float mean, rstd, ga, be;
+    cat_coeffs(f, c0 + j, mean, rstd, ga, be);
+    xa[j] = rstd;
+    xb[j] = -mean * rstd;
+    k1[j] = ga * rstd;
+    c1[j] = APPLY ? a.cbstats[c0 + j] * inv_n : 0.f;
+    c2[j] = APPLY ? a.cbstats[144 + c0 + j] * inv_n : 0.f;
+    s1[j] = 0.f;
+    s2[j] = 0.f;
+  }
+  float t1[4] = {0, 0, 0, 0}, t2[4] = {0, 0, 0, 0};
+  const int nblk = (f.h + 1) * (f.w + 1);
   const int Wp = f.W + 2;
-  const __half* gc = static_cast<const __half*>(a.gcat);
-  __half* dup = static_cast<__half*>(a.dup_pad);
-  for (long long pix = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 4; pix < npix;
-       pix += (static_cast<long long>(gridDim.x) * blockDim.x) >> 4) {
-    const int y = static_cast<int>(pix / f.W), x = static_cast<int>(pix % f.W);
-    float dc[8], u[8];
-    fold_gather(gc, 144, f.H, f.W, y, x, g * 8, dc);
-    upsample8(f, y, x, g, u);
-    if (!APPLY) {
+  const __half* __restrict__ gc = static_cast<const __half*>(a.gcat);
+  __half* __restrict__ dup = static_cast<__half*>(a.dup_pad);
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int blk = ((blockIdx.x * blockDim.x) + threadIdx.x) >> 5; blk < nblk; blk += warps) {
+    const UpBlock t = up_block(f, blk, lane);
+    const UpRaw r = up_load(t);
+    uint2 vg[2][2];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float xh = (u[j] - mean[j]) * rstd[j];
-        s1[j] += dc[j];
-        s2[j] += dc[j] * xh;
+    for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const int y = min(max(t.oy0 + rr, 0), f.H - 1), x = min(max(t.ox0 + cc, 0), f.W - 1);
+        vg[rr][cc] = ldg8(gc + (static_cast<long long>(y + 1) * Wp + (x + 1)) * 144 + c0);
       }
-    } else {
-      float o[8];
+    float v[2][2][4];
+    up_eval(r, v);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float xh = (u[j] - mean[j]) * rstd[j];
-        o[j] = ga[j] * rstd[j] * (dc[j] - a.cbstats[g * 8 + j] * inv_n - xh * a.cbstats[144 + g * 8 + j] * inv_n);
-      }
-      store8h(dup + (static_cast<long long>(y + 1) * Wp + (x + 1)) * 128 + g * 8, o);
-    }
-    if (g == 0) {
-      float d4[8];
-      fold_gather(gc, 144, f.H, f.W, y, x, 128, d4);
-      float sv[4], xh4[4], yv[4];
-      skip_act4(f, pix, sv, xh4, yv);
-      if (!APPLY) {
+    for (int rr = 0; rr < 2; ++rr)
 #pragma unroll
-        for (int o = 0; o < 4; ++o) {
-          const float xh = (sv[o] - mean4[o]) * rstd4[o];
-          t1[o] += d4[o];
-          t2[o] += d4[o] * xh;
+      for (int cc = 0; cc < 2; ++cc) {
+        const int y = t.oy0 + rr, x = t.ox0 + cc;
+        if (y < 0 || x < 0 || y >= f.H || x >= f.W) continue;               // warp-uniform
+        float dc[4];
+        fold_gather4(gc, 144, f.H, f.W, y, x, c0, vg[rr][cc], dc);
+        if (!APPLY) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float xh = fmaf(v[rr][cc][j], xa[j], xb[j]);
+            s1[j] += dc[j];
+            s2[j] = fmaf(dc[j], xh, s2[j]);
+          }
+        } else {
+          float o[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float xh = fmaf(v[rr][cc][j], xa[j], xb[j]);
+            o[j] = k1[j] * (dc[j] - c1[j] - xh * c2[j]);
+          }
+          stg8(dup + (static_cast<long long>(y + 1) * Wp + (x + 1)) * 128 + c0, pack4h(o));
         }
-      } else {
+      }
+    if (lane < 4) {                 // lane l: the 4 skip channels of output pixel (l >> 1, l & 1)
+      const int y = t.oy0 + (lane >> 1), x = t.ox0 + (lane & 1);
+      if (y >= 0 && x >= 0 && y < f.H && x < f.W) {
+        const long long pix = static_cast<long long>(y) * f.W + x;
+        float d4[4];
+        fold_gather4(gc, 144, f.H, f.W, y, x, 128,
+                     ldg8(gc + (static_cast<long long>(y + 1) * Wp + (x + 1)) * 144 + 128), d4);
+        float sv[4], xh4[4], yv[4];
+        skip_act4(f, pix, sv, xh4, yv);
         float dsy[4];
 #pragma unroll
         for (int o = 0; o < 4; ++o) {
-          const float xh = (sv[o] - mean4[o]) * rstd4[o];
-          const float ds = ga4[o] * rstd4[o] *
-                           (d4[o] - a.cbstats[128 + o] * inv_n - xh * a.cbstats[144 + 128 + o] * inv_n);
-          dsy[o] = ds * (yv[o] > 0.f ? 1.f : kSlope);      // through the skip branch's LeakyReLU
-          t1[o] += dsy[o];
-          t2[o] += dsy[o] * xh4[o];
+          float mean4, rstd4, ga4, be4;
+          cat_coeffs(f, 128 + o, mean4, rstd4, ga4, be4);
+          const float xh = (sv[o] - mean4) * rstd4;
+          if (!APPLY) {
+            t1[o] += d4[o];
+            t2[o] = fmaf(d4[o], xh, t2[o]);
+          } else {
+            const float ds = ga4 * rstd4 * (d4[o] - a.cbstats[128 + o] * inv_n - xh * a.cbstats[144 + 128 + o] * inv_n);
+            dsy[o] = ds * (yv[o] > 0.f ? 1.f : kSlope);      // through the skip branch's LeakyReLU
+            t1[o] += dsy[o];
+            t2[o] = fmaf(dsy[o], xh4[o], t2[o]);
+          }
         }
-        *reinterpret_cast<float4*>(a.dsy + pix * 4) = make_float4(dsy[0], dsy[1], dsy[2], dsy[3]);
+        if (APPLY) *reinterpret_cast<float4*>(a.dsy + pix * 4) = make_float4(dsy[0], dsy[1], dsy[2], dsy[3]);
       }
     }
   }
@@ -722,11 +926,11 @@ __global__ void upcat_bwd_kernel(UpcatBwdArgs a) {
     for (int i = threadIdx.x; i < 2 * 144; i += blockDim.x) red[i] = 0.f;
     __syncthreads();
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      atomicAdd(&red[g * 8 + j], s1[j]);
-      atomicAdd(&red[144 + g * 8 + j], s2[j]);
+    for (int j = 0; j < 4; ++j) {
+      atomicAdd(&red[c0 + j], s1[j]);
+      atomicAdd(&red[144 + c0 + j], s2[j]);
     }
-    if (g == 0) {
+    if (lane < 4) {
 #pragma unroll
       for (int o = 0; o < 4; ++o) {
         atomicAdd(&red[128 + o], t1[o]);
@@ -740,7 +944,7 @@ __global__ void upcat_bwd_kernel(UpcatBwdArgs a) {
     __shared__ float red4[8];
     if (threadIdx.x < 8) red4[threadIdx.x] = 0.f;
     __syncthreads();
-    if (g == 0) {
+    if (lane < 4) {
 #pragma unroll
       for (int o = 0; o < 4; ++o) {
         atomicAdd(&red4[o], t1[o]);
@@ -758,14 +962,18 @@ __global__ void upcat_bwd_kernel(UpcatBwdArgs a) {
   }
 }
 
+static int upb_grid(const UpcatArgs& f, int cap) {
+  const long long nblk = static_cast<long long>(f.h + 1) * (f.w + 1);
+  long long blocks = (nblk + 7) / 8;
+  if (blocks > cap) blocks = cap;
+  return static_cast<int>(blocks < 1 ? 1 : blocks);
+}
 int launch_upcat_bwd_stats(const UpcatBwdArgs& a, cudaStream_t s) {
-  const long long items = static_cast<long long>(a.f.H) * a.f.W * 16;
-  upcat_bwd_kernel<false><<<grid_for(items, kThreads, 148 * 4), kThreads, 0, s>>>(a);
+  upcat_bwd_kernel<false><<<upb_grid(a.f, 148 * 6), kThreads, 0, s>>>(a);
   DSR_LAUNCH_CHECK();
 }
 int launch_upcat_bwd_apply(const UpcatBwdArgs& a, cudaStream_t s) {
-  const long long items = static_cast<long long>(a.f.H) * a.f.W * 16;
-  upcat_bwd_kernel<true><<<grid_for(items, kThreads, 148 * 8), kThreads, 0, s>>>(a);
+  upcat_bwd_kernel<true><<<upb_grid(a.f, 148 * 12), kThreads, 0, s>>>(a);
   DSR_LAUNCH_CHECK();
 }
 
