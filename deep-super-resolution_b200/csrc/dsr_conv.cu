@@ -83,11 +83,14 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
+    // ===================== MMA issuer =====================
+    // warp-uniform loop (descriptors stay in uniform registers); one elected lane issues the tcgen05 instructions
+    {
       int stage = 0;
       uint32_t phase = 0;
       int t = 0;
+      const uint64_t hi_w = make_smem_desc(0, 16, 1024, SWZ_128B);
+      const uint64_t hi_n = make_smem_desc(0, 16, 256, SWZ_32B);
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t) {
         const int as = t & 1;
         const uint32_t aphase = (t >> 1) & 1;
@@ -100,20 +103,21 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * kConvStageBytes);
           const uint32_t sb = sa + kConvStageA;
-          if (wide) {
-            const uint64_t da = make_smem_desc(sa, 16, 1024, SWZ_128B);
-            const uint64_t db = make_smem_desc(sb, 16, 1024, SWZ_128B);
+          const uint64_t da = (wide ? hi_w : hi_n) | static_cast<uint64_t>((sa & 0x3FFFF) >> 4);
+          const uint64_t db = (wide ? hi_w : hi_n) | static_cast<uint64_t>((sb & 0x3FFFF) >> 4);
+          if (elect_one()) {
+            if (wide) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j)   // 4 x (K = 16 elements = 32 B) inside the 128 B swizzle row
-              umma_f16(tmem_d, da + static_cast<uint64_t>(j * 2), db + static_cast<uint64_t>(j * 2), p.idesc,
-                       (k | j) != 0);
-          } else {
-            const uint64_t da = make_smem_desc(sa, 16, 256, SWZ_32B);
-            const uint64_t db = make_smem_desc(sb, 16, 256, SWZ_32B);
-            umma_f16(tmem_d, da, db, p.idesc, k != 0);
+              for (int j = 0; j < 4; ++j)   // 4 x (K = 16 elements = 32 B) inside the 128 B swizzle row
+                umma_f16(tmem_d, da + static_cast<uint64_t>(j * 2), db + static_cast<uint64_t>(j * 2), p.idesc,
+                         (k | j) != 0);
+            } else {
+              umma_f16(tmem_d, da, db, p.idesc, k != 0);
+            }
+            umma_commit(&empty_bar[stage]);   // frees the smem stage once these MMAs have read it
+            if (k == p.nkb - 1) umma_commit(&tfull_bar[as]);
           }
-          umma_commit(&empty_bar[stage]);   // frees the smem stage once these MMAs have read it
-          if (k == p.nkb - 1) umma_commit(&tfull_bar[as]);
+          __syncwarp();
           if (++stage == kConvStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -219,6 +223,455 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
 }
 
 // =============================================================================================
+// conv_halo_kernel  (see dsr_conv.cuh)
+// =============================================================================================
+__device__ __forceinline__ void halo_epilogue_chunk(const HaloParams& p, uint32_t taddr, int c, int col0, bool valid,
+                                                    long long obase, int lane, float& acc_s, float& acc_q) {
+  uint32_t v[16];
+  tmem_ld16(taddr + static_cast<uint32_t>(c * 16), v);
+  tmem_ld_wait();
+  uint32_t packed[8];
+  float f[16];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    __half2 h = __floats2half2_rn(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+    packed[i] = *reinterpret_cast<uint32_t*>(&h);
+    f[2 * i] = __low2float(h);
+    f[2 * i + 1] = __high2float(h);
+  }
+  const int ch = col0 + c * 16;
+  if (valid && ch < p.n_store) {
+    uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + obase + ch);
+    dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+    if (ch + 8 < p.n_store) dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+  }
+  if (p.stats != nullptr) {
+    // column sums over the warp's 32 pixels by recursive halving (see conv_gemm_kernel)
+    const float m = valid ? 1.f : 0.f;
+    float s[16], q[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { s[i] = f[i] * m; q[i] = f[i] * f[i] * m; }
+#pragma unroll
+    for (int w = 8; w >= 1; w >>= 1) {
+      const int d = w * 2;
+      const bool hi = (lane & d) != 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (i < w) {
+          const float send_s = hi ? s[i] : s[i + w];
+          const float send_q = hi ? q[i] : q[i + w];
+          const float recv_s = __shfl_xor_sync(0xffffffffu, send_s, d);
+          const float recv_q = __shfl_xor_sync(0xffffffffu, send_q, d);
+          s[i] = (hi ? s[i + w] : s[i]) + recv_s;
+          q[i] = (hi ? q[i + w] : q[i]) + recv_q;
+        }
+      }
+    }
+    s[0] += __shfl_xor_sync(0xffffffffu, s[0], 1);
+    q[0] += __shfl_xor_sync(0xffffffffu, q[0], 1);
+    acc_s += s[0];
+    acc_q += q[0];
+  }
+}
+
+__global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid_constant__ HaloParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int wb = p.n_part * 128, nb = p.n_part * 32;                    // bytes of one resident weight block
+  uint8_t* bres_w = smem;                                               // [9][n_wide] wide blocks
+  uint8_t* bres_n = bres_w + 9 * p.n_wide * wb;                         // [9] narrow blocks
+  uint8_t* a_wide = bres_n + ((9 * p.n_narrow * nb + 1023) & ~1023);    // ring of wide_slots x kHaloWideSlot
+  uint8_t* a_narrow = a_wide + p.wide_slots * kHaloWideSlot;            // ring of 2 x kHaloNarrowSlot (if any)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(a_narrow + (p.n_narrow ? 2 * kHaloNarrowSlot : 0));
+  uint64_t* wfull = bars;                 // [3]
+  uint64_t* wempty = bars + 3;            // [3]
+  uint64_t* nfull = bars + 6;             // [2]
+  uint64_t* nempty = bars + 8;            // [2]
+  uint64_t* tfull = bars + 10;            // [kHaloAccStages]
+  uint64_t* tempty = bars + 14;           // [kHaloAccStages]
+  uint64_t* bres_bar = bars + 18;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int part = blockIdx.x % p.parts;
+  const int seq0 = blockIdx.x / p.parts, seq_stride = gridDim.x / p.parts;
+  const int ntiles = p.tiles_x * p.tiles_y;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.a64);
+    tma_prefetch_desc(&p.b64);
+    if (p.n_narrow) { tma_prefetch_desc(&p.a16); tma_prefetch_desc(&p.b16); }
+    for (int i = 0; i < 3; ++i) { mbar_init(&wfull[i], 1); mbar_init(&wempty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&nfull[i], 1); mbar_init(&nempty[i], 1); }
+    for (int i = 0; i < kHaloAccStages; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    mbar_init(bres_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, kHaloAccStages * 64);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bres_bar, static_cast<uint32_t>(9 * (p.n_wide * wb + p.n_narrow * nb)));
+      for (int t = 0; t < 9; ++t) {
+        const int row = p.taps[t].b_row + part * p.n_part;
+        for (int c = 0; c < p.n_wide; ++c)
+          tma_load_2d(&p.b64, bres_bar, bres_w + (t * p.n_wide + c) * wb, c * 64, row);
+        if (p.n_narrow) tma_load_2d(&p.b16, bres_bar, bres_n + t * nb, p.n_wide * 64, row);
+      }
+      int ws = 0, ns = 0;
+      uint32_t wph = 0, nph = 0;
+      for (int tile = seq0; tile < ntiles; tile += seq_stride) {
+        const int x0 = (tile % p.tiles_x) * kHaloTW + p.org_x;
+        const int y0 = (tile / p.tiles_x) * kHaloTH + p.org_y;
+        for (int c = 0; c < p.n_wide; ++c) {
+          mbar_wait(&wempty[ws], wph ^ 1, p.err, 21);
+          if (p.dbg & 1) {
+            mbar_arrive(&wfull[ws]);
+          } else {
+            mbar_arrive_expect_tx(&wfull[ws], kHaloRows * 128);
+            tma_load_5d(&p.a64, &wfull[ws], a_wide + ws * kHaloWideSlot, c * 64, 0, x0, 0, y0);
+          }
+          if (++ws == p.wide_slots) { ws = 0; wph ^= 1; }
+        }
+        if (p.n_narrow) {
+          mbar_wait(&nempty[ns], nph ^ 1, p.err, 22);
+          if (p.dbg & 1) {
+            mbar_arrive(&nfull[ns]);
+          } else {
+            mbar_arrive_expect_tx(&nfull[ns], kHaloRows * 32);
+            tma_load_5d(&p.a16, &nfull[ns], a_narrow + ns * kHaloNarrowSlot, p.n_wide * 64, 0, x0, 0, y0);
+          }
+          if (++ns == 2) { ns = 0; nph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    // The whole warp walks the loop with warp-uniform values (so that ptxas keeps descriptors in uniform
+    // registers); only the tcgen05 instructions themselves are issued by one elected lane.
+    {
+      mbar_wait(bres_bar, 0, p.err, 23);
+      int ws = 0, ns = 0, it = 0;
+      uint32_t wph = 0, nph = 0;
+      const uint32_t bw_addr = smem_u32(bres_w), bn_addr = smem_u32(bres_n);
+      // descriptor = {hi word (constant), lo word = flags | (address >> 4)}; all per-tap / per-K-step changes are
+      // plain adds on the lo word (addresses are < 256 KB, so they never carry into the LBO field)
+      const uint64_t dw = make_smem_desc(0, 16, (kHaloTW + 2) * 128, SWZ_128B);   // A, wide
+      const uint64_t db_ = make_smem_desc(0, 16, 1024, SWZ_128B);                 // B, wide
+      const uint64_t dan = make_smem_desc(0, 16, (kHaloTW + 2) * 32, SWZ_32B);    // A, narrow
+      const uint64_t dbn = make_smem_desc(0, 16, 256, SWZ_32B);                   // B, narrow
+      const uint32_t aw_hi = static_cast<uint32_t>(dw >> 32), aw_lo0 = static_cast<uint32_t>(dw);
+      const uint32_t bw_hi = static_cast<uint32_t>(db_ >> 32), bw_lo0 = static_cast<uint32_t>(db_);
+      const uint32_t an_hi = static_cast<uint32_t>(dan >> 32), an_lo0 = static_cast<uint32_t>(dan);
+      const uint32_t bn_hi = static_cast<uint32_t>(dbn >> 32), bn_lo0 = static_cast<uint32_t>(dbn);
+      uint32_t tap_row[9];                                  // (oy * 10 + ox): halo row of the tap's view origin
+#pragma unroll
+      for (int t = 0; t < 9; ++t) tap_row[t] = static_cast<uint32_t>(p.taps[t].oy * (kHaloTW + 2) + p.taps[t].ox);
+      const uint32_t b_tap_step = static_cast<uint32_t>(p.n_wide * wb) >> 4, bn_tap_step = static_cast<uint32_t>(nb) >> 4;
+      const uint32_t idw = p.idesc_wide, idn = p.idesc_narrow;
+      for (int tile = seq0; tile < ntiles; tile += seq_stride, ++it) {
+        const int as = it % kHaloAccStages;
+        const uint32_t aph = (it / kHaloAccStages) & 1;
+        mbar_wait(&tempty[as], aph ^ 1, p.err, 24);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * 64);
+        uint32_t accum = 0;
+        for (int c = 0; c < p.n_wide; ++c) {
+          mbar_wait(&wfull[ws], wph, p.err, 25);
+          tc_fence_after();
+          const uint32_t a_lo = aw_lo0 | ((smem_u32(a_wide + ws * kHaloWideSlot) & 0x3FFFF) >> 4);
+          const uint32_t b_lo = bw_lo0 | (((bw_addr + static_cast<uint32_t>(c * wb)) & 0x3FFFF) >> 4);
+          if (elect_one()) {          // one elected region per chunk: 36 MMAs + the commit, descriptors by adds
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+              const uint32_t da_lo = a_lo + tap_row[t] * 8u;          // 128 B per halo row = 8 x 16 B
+              const uint32_t db_lo = b_lo + static_cast<uint32_t>(t) * b_tap_step;
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                umma_f16(tmem_d, (static_cast<uint64_t>(aw_hi) << 32) | (da_lo + 2u * j),
+                         (static_cast<uint64_t>(bw_hi) << 32) | (db_lo + 2u * j), idw, (t | j) ? 1u : accum);
+            }
+            umma_commit(&wempty[ws]);
+          }
+          __syncwarp();
+          accum = 1;
+          if (++ws == p.wide_slots) { ws = 0; wph ^= 1; }
+        }
+        if (p.n_narrow) {
+          mbar_wait(&nfull[ns], nph, p.err, 26);
+          tc_fence_after();
+          const uint32_t a_lo = an_lo0 | ((smem_u32(a_narrow + ns * kHaloNarrowSlot) & 0x3FFFF) >> 4);
+          const uint32_t b_lo = bn_lo0 | ((bn_addr & 0x3FFFF) >> 4);
+          if (elect_one()) {
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+              const uint32_t da_lo = a_lo + tap_row[t] * 2u;          // 32 B per halo row
+              const uint32_t db_lo = b_lo + static_cast<uint32_t>(t) * bn_tap_step;
+              umma_f16(tmem_d, (static_cast<uint64_t>(an_hi) << 32) | da_lo, (static_cast<uint64_t>(bn_hi) << 32) | db_lo,
+                       idn, 1u);
+            }
+            umma_commit(&nempty[ns]);
+          }
+          __syncwarp();
+          if (++ns == 2) { ns = 0; nph ^= 1; }
+        }
+        if (elect_one()) umma_commit(&tfull[as]);
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const int nchunks = p.n_part >> 4;
+    const int col0 = part * p.n_part;
+    float acc_s[4] = {0.f, 0.f, 0.f, 0.f}, acc_q[4] = {0.f, 0.f, 0.f, 0.f};
+    int it = 0;
+    for (int tile = seq0; tile < ntiles; tile += seq_stride, ++it) {
+      const int as = it % kHaloAccStages;
+      const uint32_t aph = (it / kHaloAccStages) & 1;
+      const int x = (tile % p.tiles_x) * kHaloTW + (row & (kHaloTW - 1));
+      const int y = (tile / p.tiles_x) * kHaloTH + (row / kHaloTW);
+      const bool valid = (x < p.out_w) && (y < p.out_h);
+      mbar_wait(&tfull[as], aph, p.err, 27);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(as * 64);
+      const long long obase = static_cast<long long>(y) * p.out_sy + static_cast<long long>(x) * p.out_sx;
+      if (!(p.dbg & 2)) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (c < nchunks) halo_epilogue_chunk(p, taddr, c, col0, valid, obase, lane, acc_s[c], acc_q[c]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[as]);
+    }
+    if (p.stats != nullptr && (lane & 1) == 0) {
+      const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (c < nchunks) {
+          atomicAdd(&p.stats[col0 + c * 16 + col], acc_s[c]);
+          atomicAdd(&p.stats[p.stats_stride + col0 + c * 16 + col], acc_q[c]);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, kHaloAccStages * 64);
+}
+
+// =============================================================================================
+// conv_halo2_kernel: the halo-tile kernel on CTA PAIRS (tcgen05 cta_group::2).  Each CTA of a pair owns one
+// 8 x 16 pixel tile (its own halo ring) and keeps HALF of the weight rows resident; CTA 0 issues M = 256
+// (both tiles) x N = all output channels MMAs, so every shared-memory operand byte feeds twice the math of the
+// single-CTA kernel (SS-mode MMAs are operand-fetch bound: measured 76 clk per 128x64x16 MMA vs the 32 clk pipe
+// floor).  Both CTAs stream A with pair-TMA loads accounted on CTA 0's barriers; MMA completion is multicast to
+// both CTAs' barriers; both CTAs' epilogue warps release the accumulator stage on CTA 0's barrier.
+// =============================================================================================
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHaloThreads, 1)
+    conv_halo2_kernel(const __grid_constant__ HaloParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int wb = p.n_part * 128, nb = p.n_part * 32;                    // bytes of one resident weight block
+  uint8_t* bres_w = smem;
+  uint8_t* bres_n = bres_w + 9 * p.n_wide * wb;
+  uint8_t* a_wide = bres_n + ((9 * p.n_narrow * nb + 1023) & ~1023);
+  uint8_t* a_narrow = a_wide + p.wide_slots * kHaloWideSlot;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(a_narrow + (p.n_narrow ? 2 * kHaloNarrowSlot : 0));
+  uint64_t* wfull = bars;                 // [3]  (CTA 0's copy is the live one)
+  uint64_t* wempty = bars + 3;            // [3]  (each CTA waits on its own copy; multicast commit)
+  uint64_t* nfull = bars + 6;             // [2]
+  uint64_t* nempty = bars + 8;            // [2]
+  uint64_t* tfull = bars + 10;            // [2]  (multicast commit)
+  uint64_t* tempty = bars + 14;           // [2]  (CTA 0's copy: 8 arrivals = 4 epilogue warps x 2 CTAs)
+  uint64_t* bres_bar = bars + 18;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair0 = blockIdx.x >> 1, pair_stride = gridDim.x >> 1;
+  const int ntiles = p.tiles_x * p.tiles_y;
+  const int npairs = (ntiles + 1) >> 1;
+  constexpr int kAcc = 2;                 // accumulator stages, 256 TMEM columns apart
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.a64);
+    tma_prefetch_desc(&p.b64);
+    if (p.n_narrow) { tma_prefetch_desc(&p.a16); tma_prefetch_desc(&p.b16); }
+    for (int i = 0; i < 3; ++i) { mbar_init(&wfull[i], 1); mbar_init(&wempty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&nfull[i], 1); mbar_init(&nempty[i], 1); }
+    for (int i = 0; i < kAcc; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
+    mbar_init(bres_bar, 1);
+    fence_barrier_init();
+  }
+  cluster_sync_all();                     // barriers of both CTAs exist before anyone signals across the pair
+  if (warp == 1) {
+    tmem_alloc_pair(tmem_slot, 512);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      const uint32_t bbytes = static_cast<uint32_t>(9 * (p.n_wide * wb + p.n_narrow * nb));
+      if (rank == 0) mbar_arrive_expect_tx(bres_bar, 2 * bbytes);
+      for (int t = 0; t < 9; ++t) {
+        const int row = p.taps[t].b_row + static_cast<int>(rank) * p.n_part;
+        for (int c = 0; c < p.n_wide; ++c)
+          tma_load_2d_pair(&p.b64, bres_bar, bres_w + (t * p.n_wide + c) * wb, c * 64, row);
+        if (p.n_narrow) tma_load_2d_pair(&p.b16, bres_bar, bres_n + t * nb, p.n_wide * 64, row);
+      }
+      int ws = 0, ns = 0;
+      uint32_t wph = 0, nph = 0;
+      for (int pair = pair0; pair < npairs; pair += pair_stride) {
+        const int tile = 2 * pair + static_cast<int>(rank);      // may be == ntiles (odd count): coordinates still valid to fetch
+        const int x0 = (tile % p.tiles_x) * kHaloTW + p.org_x;
+        const int y0 = (tile / p.tiles_x) * kHaloTH + p.org_y;
+        for (int c = 0; c < p.n_wide; ++c) {
+          mbar_wait(&wempty[ws], wph ^ 1, p.err, 31);
+          if (rank == 0) mbar_arrive_expect_tx(&wfull[ws], 2 * kHaloRows * 128);
+          tma_load_5d_pair(&p.a64, &wfull[ws], a_wide + ws * kHaloWideSlot, c * 64, 0, x0, 0, y0);
+          if (++ws == p.wide_slots) { ws = 0; wph ^= 1; }
+        }
+        if (p.n_narrow) {
+          mbar_wait(&nempty[ns], nph ^ 1, p.err, 32);
+          if (rank == 0) mbar_arrive_expect_tx(&nfull[ns], 2 * kHaloRows * 32);
+          tma_load_5d_pair(&p.a16, &nfull[ns], a_narrow + ns * kHaloNarrowSlot, p.n_wide * 64, 0, x0, 0, y0);
+          if (++ns == 2) { ns = 0; nph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (CTA 0 only; warp-uniform loop, one elected lane issues) =====================
+    if (rank == 0) {
+      mbar_wait(bres_bar, 0, p.err, 33);
+      int ws = 0, ns = 0, it = 0;
+      uint32_t wph = 0, nph = 0;
+      const uint32_t bw_addr = smem_u32(bres_w), bn_addr = smem_u32(bres_n);
+      const uint64_t dw = make_smem_desc(0, 16, (kHaloTW + 2) * 128, SWZ_128B);
+      const uint64_t db_ = make_smem_desc(0, 16, 1024, SWZ_128B);
+      const uint64_t dan = make_smem_desc(0, 16, (kHaloTW + 2) * 32, SWZ_32B);
+      const uint64_t dbn = make_smem_desc(0, 16, 256, SWZ_32B);
+      const uint32_t aw_hi = static_cast<uint32_t>(dw >> 32), aw_lo0 = static_cast<uint32_t>(dw);
+      const uint32_t bw_hi = static_cast<uint32_t>(db_ >> 32), bw_lo0 = static_cast<uint32_t>(db_);
+      const uint32_t an_hi = static_cast<uint32_t>(dan >> 32), an_lo0 = static_cast<uint32_t>(dan);
+      const uint32_t bn_hi = static_cast<uint32_t>(dbn >> 32), bn_lo0 = static_cast<uint32_t>(dbn);
+      uint32_t tap_row[9];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) tap_row[t] = static_cast<uint32_t>(p.taps[t].oy * (kHaloTW + 2) + p.taps[t].ox);
+      const uint32_t b_tap_step = static_cast<uint32_t>(p.n_wide * wb) >> 4, bn_tap_step = static_cast<uint32_t>(nb) >> 4;
+      const uint32_t idw = p.idesc_wide, idn = p.idesc_narrow;
+      for (int pair = pair0; pair < npairs; pair += pair_stride, ++it) {
+        const int as = it % kAcc;
+        const uint32_t aph = (it / kAcc) & 1;
+        mbar_wait(&tempty[as], aph ^ 1, p.err, 34);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * 256);
+        uint32_t accum = 0;
+        for (int c = 0; c < p.n_wide; ++c) {
+          mbar_wait(&wfull[ws], wph, p.err, 35);
+          tc_fence_after();
+          const uint32_t a_lo = aw_lo0 | ((smem_u32(a_wide + ws * kHaloWideSlot) & 0x3FFFF) >> 4);
+          const uint32_t b_lo = bw_lo0 | (((bw_addr + static_cast<uint32_t>(c * wb)) & 0x3FFFF) >> 4);
+          if (elect_one()) {
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+              const uint32_t da_lo = a_lo + tap_row[t] * 8u;
+              const uint32_t db_lo = b_lo + static_cast<uint32_t>(t) * b_tap_step;
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                umma_f16_pair(tmem_d, (static_cast<uint64_t>(aw_hi) << 32) | (da_lo + 2u * j),
+                              (static_cast<uint64_t>(bw_hi) << 32) | (db_lo + 2u * j), idw, (t | j) ? 1u : accum);
+            }
+            umma_commit_pair(&wempty[ws]);
+          }
+          __syncwarp();
+          accum = 1;
+          if (++ws == p.wide_slots) { ws = 0; wph ^= 1; }
+        }
+        if (p.n_narrow) {
+          mbar_wait(&nfull[ns], nph, p.err, 36);
+          tc_fence_after();
+          const uint32_t a_lo = an_lo0 | ((smem_u32(a_narrow + ns * kHaloNarrowSlot) & 0x3FFFF) >> 4);
+          const uint32_t b_lo = bn_lo0 | ((bn_addr & 0x3FFFF) >> 4);
+          if (elect_one()) {
+#pragma unroll
+            for (int t = 0; t < 9; ++t)
+              umma_f16_pair(tmem_d, (static_cast<uint64_t>(an_hi) << 32) | (a_lo + tap_row[t] * 2u),
+                            (static_cast<uint64_t>(bn_hi) << 32) | (b_lo + static_cast<uint32_t>(t) * bn_tap_step), idn,
+                            1u);
+            umma_commit_pair(&nempty[ns]);
+          }
+          __syncwarp();
+          if (++ns == 2) { ns = 0; nph ^= 1; }
+        }
+        if (elect_one()) umma_commit_pair(&tfull[as]);
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===================== epilogue (both CTAs: own tile, all output channels) =====================
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const int nchunks = (2 * p.n_part) >> 4;              // 8 (N = 128) or 9 (N = 144)
+    float acc_s[9], acc_q[9];
+#pragma unroll
+    for (int c = 0; c < 9; ++c) { acc_s[c] = 0.f; acc_q[c] = 0.f; }
+    int it = 0;
+    for (int pair = pair0; pair < npairs; pair += pair_stride, ++it) {
+      const int as = it % kAcc;
+      const uint32_t aph = (it / kAcc) & 1;
+      const int tile = 2 * pair + static_cast<int>(rank);
+      const int x = (tile % p.tiles_x) * kHaloTW + (row & (kHaloTW - 1));
+      const int y = (tile / p.tiles_x) * kHaloTH + (row / kHaloTW);
+      const bool valid = (tile < ntiles) && (x < p.out_w) && (y < p.out_h);
+      mbar_wait(&tfull[as], aph, p.err, 37);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(as * 256);
+      const long long obase = static_cast<long long>(y) * p.out_sy + static_cast<long long>(x) * p.out_sx;
+#pragma unroll
+      for (int c = 0; c < 9; ++c)
+        if (c < nchunks) halo_epilogue_chunk(p, taddr, c, 0, valid, obase, lane, acc_s[c], acc_q[c]);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(&tempty[as], 0);
+    }
+    if (p.stats != nullptr && (lane & 1) == 0) {
+      const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+#pragma unroll
+      for (int c = 0; c < 9; ++c) {
+        if (c < nchunks) {
+          atomicAdd(&p.stats[c * 16 + col], acc_s[c]);
+          atomicAdd(&p.stats[p.stats_stride + c * 16 + col], acc_q[c]);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                     // the peer may still be reading our shared memory / signalling our barriers
+  if (warp == 1) tmem_dealloc_pair(tmem_base, 512);
+}
+
+// =============================================================================================
 // wgrad_kernel
 // =============================================================================================
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
@@ -291,9 +744,12 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // warp-uniform loop; one elected lane issues the tcgen05 instructions
+    {
       int stage = 0;
       uint32_t phase = 0;
+      const uint64_t hi_a = make_smem_desc(0, kWgPix * 128, 1024, SWZ_128B);
+      const uint64_t hi_b16 = make_smem_desc(0, kWgPix * 32, 256, SWZ_32B);
       for (int k = 0; k < nkb; ++k) {
         mbar_wait(&full_bar[stage], phase, p.err, 12);
         tc_fence_after();
@@ -301,22 +757,29 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
         for (int t = 0; t < p.ntaps; ++t) {
           const uint32_t sb = sa + kWgStageA + t * tapB;
           const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(t * kWgTapCols);
+          const uint32_t sb16 = sb + p.n64 * (kWgPix * 128);
+          if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < kWgPix / 16; ++ks) {
-            // A: [pixels][co] MN-major, 2 column groups of 64 co (LBO), 8-pixel row groups (SBO).
-            const uint64_t da = make_smem_desc(sa + ks * 2048, kWgPix * 128, 1024, SWZ_128B);
-            if (p.n64) {
-              const uint64_t db = make_smem_desc(sb + ks * 2048, kWgPix * 128, 1024, SWZ_128B);
-              umma_f16(tmem_d, da, db, p.idesc64, (k | ks) != 0);
-            }
-            if (p.n16) {
-              const uint64_t db = make_smem_desc(sb + p.n64 * (kWgPix * 128) + ks * 512, kWgPix * 32, 256, SWZ_32B);
-              umma_f16(tmem_d + static_cast<uint32_t>(p.n64 * 64), da, db, p.idesc16, (k | ks) != 0);
+            for (int ks = 0; ks < kWgPix / 16; ++ks) {
+              // A: [pixels][co] MN-major, 2 column groups of 64 co (LBO), 8-pixel row groups (SBO).
+              const uint64_t da = hi_a | static_cast<uint64_t>(((sa + ks * 2048) & 0x3FFFF) >> 4);
+              if (p.n64) {
+                const uint64_t db = hi_a | static_cast<uint64_t>(((sb + ks * 2048) & 0x3FFFF) >> 4);
+                umma_f16(tmem_d, da, db, p.idesc64, (k | ks) != 0);
+              }
+              if (p.n16) {
+                const uint64_t db = hi_b16 | static_cast<uint64_t>(((sb16 + ks * 512) & 0x3FFFF) >> 4);
+                umma_f16(tmem_d + static_cast<uint32_t>(p.n64 * 64), da, db, p.idesc16, (k | ks) != 0);
+              }
             }
           }
+          __syncwarp();
         }
-        umma_commit(&empty_bar[stage]);
-        if (k == nkb - 1) umma_commit(tfull_bar);
+        if (elect_one()) {
+          umma_commit(&empty_bar[stage]);
+          if (k == nkb - 1) umma_commit(tfull_bar);
+        }
+        __syncwarp();
         if (++stage == kWgStages) { stage = 0; phase ^= 1; }
       }
     }
@@ -424,6 +887,35 @@ int launch_conv_gemm(const ConvGemmParams& p, int num_sms, cudaStream_t stream) 
   if (ntiles <= 0) return 0;
   const int grid = ntiles < num_sms ? ntiles : num_sms;
   conv_gemm_kernel<<<grid, kConvThreads, kConvSmemBytes, stream>>>(p);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int halo_smem_bytes(int n_part, int n_wide, int n_narrow, int wide_slots) {
+  const int bres = 9 * n_wide * n_part * 128 + ((9 * n_narrow * n_part * 32 + 1023) & ~1023);
+  return bres + wide_slots * kHaloWideSlot + (n_narrow ? 2 * kHaloNarrowSlot : 0) + 256 + 1024;
+}
+
+int launch_conv_halo(const HaloParams& p, int num_sms, cudaStream_t stream) {
+  static int configured = 0;
+  if (p.smem_bytes > configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem_bytes);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    e = cudaFuncSetAttribute(conv_halo2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem_bytes);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    configured = p.smem_bytes;
+  }
+  const int ntiles = p.tiles_x * p.tiles_y;
+  if (ntiles <= 0) return 0;
+  if (p.pair) {                          // CTA pairs: one pair per two tiles, every CTA keeps half of the weights
+    const int npairs = (ntiles + 1) / 2;
+    int clusters = num_sms / 2;
+    if (clusters > npairs) clusters = npairs;
+    conv_halo2_kernel<<<2 * clusters, kHaloThreads, p.smem_bytes, stream>>>(p);
+    return static_cast<int>(cudaGetLastError());
+  }
+  int grid = (num_sms / p.parts) * p.parts;
+  if (grid > ntiles * p.parts) grid = ntiles * p.parts;
+  conv_halo_kernel<<<grid, kHaloThreads, p.smem_bytes, stream>>>(p);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -49,6 +49,47 @@ struct alignas(64) ConvGemmParams {
 };
 
 // ---------------------------------------------------------------------------------------------
+// conv_halo_kernel: stride-1 3x3 convolution (fprop and dgrad) with WEIGHT-STATIONARY CTAs and HALO-TILE reuse.
+//   * a CTA owns one slice of N_part output channels for the whole launch and keeps the 9 x N_part x K weight
+//     slice resident in shared memory (loaded once by TMA);
+//   * per 8 x 16 pixel tile it streams the (8+2) x (16+2) input halo ONCE per 64-channel chunk (one 5-D TMA box,
+//     128B-swizzled) and issues the 9 taps as 9 shifted descriptor views of that single tile (start address
+//     + (oy*10 + ox) rows, stride between 8-row groups = 10 rows; the swizzle is a function of the absolute
+//     shared-memory address, verified on B200 with tools/umma_probe.cu);
+//   => shared-memory fill traffic drops from 864 KB to ~50 KB per tile, so the kernel is MMA-bound, not L2-bound.
+// ---------------------------------------------------------------------------------------------
+constexpr int kHaloThreads = 192;        // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+constexpr int kHaloTW = 8, kHaloTH = 16; // output tile (pixels); halo = 10 x 18
+constexpr int kHaloRows = (kHaloTW + 2) * (kHaloTH + 2);          // 180
+constexpr int kHaloWideSlot = 23552;     // 180 rows x 128 B = 23040, rounded up to 1024
+constexpr int kHaloNarrowSlot = 6144;    // 180 rows x 32 B = 5760, rounded up to 1024
+constexpr int kHaloAccStages = 4;        // TMEM accumulator ring (4 x 64 columns)
+
+struct HaloTap { int8_t oy, ox; int16_t b_row; };   // halo-relative view offset, first row of the weight block
+
+struct alignas(64) HaloParams {
+  CUtensorMap a64, a16;      // input (padded grid): boxes (64 | 16, 1, 10, 1, 18)
+  CUtensorMap b64, b16;      // packed weights [rows][K]: boxes (64 | 16, n_part)
+  HaloTap taps[9];
+  int n_wide, n_narrow;      // 64-channel chunks (2) and 16-channel chunks (0 or 1) of K
+  int n_part, parts;         // output channels per CTA slice (64 or 48), number of slices (2 or 3)
+  int org_x, org_y;          // halo origin relative to the tile origin in input coordinates (0 fprop, -1 dgrad)
+  int tiles_x, tiles_y;
+  int out_h, out_w;
+  long long out_sy, out_sx;  // output strides (elements)
+  void* out;                 // fp16
+  int n_store;               // channels actually stored per pixel (<= n_part * parts)
+  float* stats;              // optional [2][stats_stride]
+  int stats_stride;
+  int wide_slots;            // A ring depth for 64-channel chunks (2 or 3)
+  uint32_t idesc_wide, idesc_narrow;
+  int smem_bytes;
+  int pair;                  // 1: CTA-pair kernel (cta_group::2; parts must be 2, n_part = N / 2)
+  int dbg;                   // experiments only (DSR_HALO_DBG): bit 0 skip the A loads, bit 1 skip the epilogue work
+  int* err;
+};
+
+// ---------------------------------------------------------------------------------------------
 // wgrad:  dW[tap][co][ci] = sum over pixels  dR[p][co] * X[p (+) tap][ci]
 // GEMM M = co (128), N = ci, K = pixels; both operands are MN-major tiles [pixels][channels].
 // ---------------------------------------------------------------------------------------------

@@ -9,6 +9,7 @@
 //   DIP.py:47-95, utils/DIP.py:35-38   closure + Adam loop (dsr_dip_step)
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -84,6 +85,8 @@ struct ConvLayer {
   ConvGemmParams fprop{};
   ConvGemmParams dgrad[4];
   int ndgrad = 0;
+  HaloParams hfprop{}, hdgrad{};   // weight-stationary halo-tile variants (3x3 stride 1 only)
+  bool has_halo = false;
   WgradParams wgrad{};
   ActRef ref_in{}, ref_dr{};       // checker views
   WgtRef ref_wf{}, ref_wd{};
@@ -141,6 +144,7 @@ struct dsr_plan {
   int num_sms = 148;
   int launches = 0;
   int debug_conv = 0;
+  int use_halo = 1;              // 3x3 stride-1 layers: halo-tile weight-stationary kernel (0: generic kernel)
   bool bound = false, have_forward = false;
   // optional per-launch timing of the tensor-core kernels (bench.py roofline): class 0 = conv_gemm, 1 = wgrad
   struct ProfRec { int cls; cudaEvent_t a, b; double flops; };
@@ -433,6 +437,90 @@ int build_conv(dsr_plan* p, ConvLayer& c) {
     g.idesc16 = make_idesc_f16(128, 16 * (g.n16 > 0 ? g.n16 : 1), FMT_F16, FMT_F16, 1, 1);   // n16 chunks, LBO apart
     g.err = static_cast<int*>(p->errword.ptr);
   }
+  // ---------------- halo-tile variants ----------------
+  c.has_halo = (c.k == 3 && c.stride == 1 && c.cin_pad >= 128);
+  if (c.has_halo) {
+    {
+      HaloParams& h = c.hfprop;
+      memset(&h, 0, sizeof(h));
+      const int Wp = c.inW + 2, Hp = c.inH + 2;
+      h.n_wide = 2;
+      h.n_narrow = (c.cin_pad - 128) / 16;
+      h.n_part = 64;
+      h.parts = 2;
+      h.wide_slots = h.n_narrow ? 2 : 3;
+      if ((rc = make_act_map(&h.a64, c.in_pad->ptr, 1, c.cin_pad, Wp, Hp, 1, 64, kHaloTW + 2, kHaloTH + 2))) return rc;
+      h.a16 = h.a64;
+      if (h.n_narrow &&
+          (rc = make_act_map(&h.a16, c.in_pad->ptr, 1, c.cin_pad, Wp, Hp, 1, 16, kHaloTW + 2, kHaloTH + 2)))
+        return rc;
+      const void* wf = warena + c.pack.f_off;
+      if ((rc = make_wgt_map(&h.b64, wf, c.cin_pad, 9 * kNC, 64, h.n_part))) return rc;
+      h.b16 = h.b64;
+      if (h.n_narrow && (rc = make_wgt_map(&h.b16, wf, c.cin_pad, 9 * kNC, 16, h.n_part))) return rc;
+      for (int ky = 0; ky < 3; ++ky)
+        for (int kx = 0; kx < 3; ++kx)
+          h.taps[ky * 3 + kx] = HaloTap{static_cast<int8_t>(ky), static_cast<int8_t>(kx),
+                                        static_cast<int16_t>((ky * 3 + kx) * kNC)};
+      h.org_x = 0;
+      h.org_y = 0;
+      h.tiles_x = (c.outW + kHaloTW - 1) / kHaloTW;
+      h.tiles_y = (c.outH + kHaloTH - 1) / kHaloTH;
+      h.out_h = c.outH;
+      h.out_w = c.outW;
+      h.out_sy = static_cast<long long>(c.outW) * kNC;
+      h.out_sx = kNC;
+      h.out = c.raw.ptr;
+      h.n_store = kNC;
+      h.stats = acc + c.stats_off;
+      h.stats_stride = kNC;
+      h.idesc_wide = make_idesc_f16(128, h.n_part, FMT_F16, FMT_F16, 0, 0);
+      h.idesc_narrow = h.idesc_wide;
+      h.smem_bytes = halo_smem_bytes(h.n_part, h.n_wide, h.n_narrow, h.wide_slots);
+      h.dbg = getenv("DSR_HALO_DBG") ? atoi(getenv("DSR_HALO_DBG")) : 0;
+      h.pair = getenv("DSR_HALO_1CTA") ? 0 : 1;
+      if (h.pair) h.idesc_wide = h.idesc_narrow = make_idesc_f16(256, 2 * h.n_part, FMT_F16, FMT_F16, 0, 0);
+      h.err = static_cast<int*>(p->errword.ptr);
+    }
+    if (c.need_dgrad) {
+      HaloParams& h = c.hdgrad;
+      memset(&h, 0, sizeof(h));
+      const int oWp = c.outW + 2, oHp = c.outH + 2;     // dR grid
+      const int iWp = c.inW + 2, iHp = c.inH + 2;       // output (input-gradient) grid
+      h.n_wide = 2;
+      h.n_narrow = 0;
+      h.pair = getenv("DSR_HALO_1CTA") ? 0 : 1;
+      h.parts = (h.pair || c.n_rows == 128) ? 2 : 3;
+      h.n_part = c.n_rows / h.parts;                    // 64 / 72 (pairs) or 64 / 48
+      h.wide_slots = (h.n_part > 64) ? 2 : 3;           // 72-row weight slices leave room for two halo slots only
+      if ((rc = make_act_map(&h.a64, c.dr.ptr, 1, kNC, oWp, oHp, 1, 64, kHaloTW + 2, kHaloTH + 2))) return rc;
+      h.a16 = h.a64;
+      const void* wd = warena + c.pack.d_off;
+      if ((rc = make_wgt_map(&h.b64, wd, kNC, 9 * c.n_rows, 64, h.n_part))) return rc;
+      h.b16 = h.b64;
+      for (int ky = 0; ky < 3; ++ky)
+        for (int kx = 0; kx < 3; ++kx)
+          h.taps[ky * 3 + kx] = HaloTap{static_cast<int8_t>(2 - ky), static_cast<int8_t>(2 - kx),
+                                        static_cast<int16_t>((ky * 3 + kx) * c.n_rows)};
+      h.org_x = -1;                                     // padded position q reads dR (padded) at q - k + 1
+      h.org_y = -1;
+      h.tiles_x = (iWp + kHaloTW - 1) / kHaloTW;
+      h.tiles_y = (iHp + kHaloTH - 1) / kHaloTH;
+      h.out_h = iHp;
+      h.out_w = iWp;
+      h.out_sy = static_cast<long long>(iWp) * c.n_rows;
+      h.out_sx = c.n_rows;
+      h.out = c.gin.ptr;
+      h.n_store = c.n_rows;
+      h.stats = nullptr;
+      h.stats_stride = 0;
+      h.idesc_wide = h.pair ? make_idesc_f16(256, 2 * h.n_part, FMT_F16, FMT_F16, 0, 0)
+                            : make_idesc_f16(128, h.n_part, FMT_F16, FMT_F16, 0, 0);
+      h.idesc_narrow = h.idesc_wide;
+      h.smem_bytes = halo_smem_bytes(h.n_part, h.n_wide, h.n_narrow, h.wide_slots);
+      h.err = static_cast<int*>(p->errword.ptr);
+    }
+  }
   return 0;
 }
 
@@ -487,11 +575,13 @@ struct ProfScope {
 int run_fprop(dsr_plan* p, ConvLayer& c, cudaStream_t s) {
   if (p->debug_conv) return launch_conv_ref(c.fprop, c.ref_in, c.ref_wf, s);
   ProfScope ps(p, 0, conv_flops(c), s);
+  if (c.has_halo && p->use_halo) return launch_conv_halo(c.hfprop, p->num_sms, s);
   return launch_conv_gemm(c.fprop, p->num_sms, s);
 }
 int run_dgrad(dsr_plan* p, ConvLayer& c, int i, cudaStream_t s) {
   if (p->debug_conv) return launch_conv_ref(c.dgrad[i], c.ref_dr, c.ref_wd, s);
   ProfScope ps(p, 0, conv_flops(c) / c.ndgrad, s);
+  if (c.has_halo && p->use_halo) return launch_conv_halo(c.hdgrad, p->num_sms, s);
   return launch_conv_gemm(c.dgrad[i], p->num_sms, s);
 }
 int run_wgrad(dsr_plan* p, ConvLayer& c, cudaStream_t s) {
@@ -1048,7 +1138,10 @@ int dsr_plan_tensor(const dsr_plan_t* p, const char* name, void** ptr, int* kind
 int dsr_plan_last_launches(const dsr_plan_t* p) { return p ? p->launches : -1; }
 int dsr_plan_set_debug_conv(dsr_plan_t* p, int use_checker_kernels) {
   if (!p) return -1;
-  p->debug_conv = use_checker_kernels ? 1 : 0;
+  // 0: product kernels; 1: CUDA-core checker kernels; 2: product path but with the generic implicit-GEMM kernel
+  // instead of the halo-tile kernel on the 3x3 stride-1 layers (A/B comparison)
+  p->debug_conv = (use_checker_kernels == 1) ? 1 : 0;
+  p->use_halo = (use_checker_kernels == 2) ? 0 : 1;
   return 0;
 }
 int dsr_plan_debug_replay(dsr_plan_t* p, const char* layer, int what, int use_checker, void* stream) {

@@ -270,7 +270,7 @@ class SkipNet(nn.Module):
 
     def set_debug_conv(self, on: bool) -> None:
         for plan in self._plans.values():
-            check(lib.dsr_plan_set_debug_conv(plan.handle, 1 if on else 0))
+            check(lib.dsr_plan_set_debug_conv(plan.handle, int(on)))
 
     def last_launches(self, hw: Tuple[int, int]) -> int:
         return lib.dsr_plan_last_launches(self._plans[hw].handle)

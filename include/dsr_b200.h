@@ -117,7 +117,8 @@ int dsr_plan_tensor(const dsr_plan_t* p, const char* name, void** ptr, int* kind
                     int* C);
 /* Kernel launches enqueued by the last forward / backward / step call on this plan. */
 int dsr_plan_last_launches(const dsr_plan_t* p);
-/* Debug switch (tests only): 1 = run convolutions with the naive CUDA-core checker kernels. */
+/* Debug switch (tests only): 1 = run convolutions with the naive CUDA-core checker kernels; 2 = product kernels
+ * but the generic implicit-GEMM kernel instead of the halo-tile kernel on 3x3 stride-1 layers; 0 = product. */
 int dsr_plan_set_debug_conv(dsr_plan_t* p, int use_checker_kernels);
 /* Re-runs ONE tensor-core kernel of one conv layer ("L0.d1", "L2.u1", ...) on the current workspace
  * contents: what = 0 fprop (zeroes the layer's BN sums first), 1 dgrad, 2 wgrad (zeroes the layer's packed
