@@ -225,11 +225,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
 // =============================================================================================
 // conv_halo_kernel  (see dsr_conv.cuh)
 // =============================================================================================
-__device__ __forceinline__ void halo_epilogue_chunk(const HaloParams& p, uint32_t taddr, int c, int col0, bool valid,
-                                                    long long obase, int lane, float& acc_s, float& acc_q) {
-  uint32_t v[16];
-  tmem_ld16(taddr + static_cast<uint32_t>(c * 16), v);
-  tmem_ld_wait();
+__device__ __forceinline__ void halo_epilogue_process(const HaloParams& p, const uint32_t (&v)[16], int c, int col0,
+                                                      bool valid, long long obase, int lane, float& acc_s,
+                                                      float& acc_q) {
   uint32_t packed[8];
   float f[16];
 #pragma unroll
@@ -241,11 +239,17 @@ __device__ __forceinline__ void halo_epilogue_chunk(const HaloParams& p, uint32_
   }
   const int ch = col0 + c * 16;
   if (valid && ch < p.n_store) {
-    uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + obase + ch);
-    dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-    if (ch + 8 < p.n_store) dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+    uint16_t* dst = reinterpret_cast<uint16_t*>(p.out) + obase + ch;
+    if (ch + 16 <= p.n_store) {          // one 32-byte store per lane (sm_100 256-bit vector store): one sector each
+      asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(packed[0]),
+                   "r"(packed[1]), "r"(packed[2]), "r"(packed[3]), "r"(packed[4]), "r"(packed[5]), "r"(packed[6]),
+                   "r"(packed[7])
+                   : "memory");
+    } else {
+      *reinterpret_cast<uint4*>(dst) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+    }
   }
-  if (p.stats != nullptr) {
+  if (p.stats != nullptr && !(p.dbg & 4)) {
     // column sums over the warp's 32 pixels by recursive halving (see conv_gemm_kernel)
     const float m = valid ? 1.f : 0.f;
     float s[16], q[16];
@@ -274,13 +278,21 @@ __device__ __forceinline__ void halo_epilogue_chunk(const HaloParams& p, uint32_
   }
 }
 
+__device__ __forceinline__ void halo_epilogue_chunk(const HaloParams& p, uint32_t taddr, int c, int col0, bool valid,
+                                                    long long obase, int lane, float& acc_s, float& acc_q) {
+  uint32_t v[16];
+  tmem_ld16(taddr + static_cast<uint32_t>(c * 16), v);
+  tmem_ld_wait();
+  halo_epilogue_process(p, v, c, col0, valid, obase, lane, acc_s, acc_q);
+}
+
 __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid_constant__ HaloParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int wb = p.n_part * 128, nb = p.n_part * 32;                    // bytes of one resident weight block
   uint8_t* bres_w = smem;                                               // [9][n_wide] wide blocks
-  uint8_t* bres_n = bres_w + 9 * p.n_wide * wb;                         // [9] narrow blocks
-  uint8_t* a_wide = bres_n + ((9 * p.n_narrow * nb + 1023) & ~1023);    // ring of wide_slots x kHaloWideSlot
+  uint8_t* bres_n = bres_w + p.ntaps * p.n_wide * wb;                   // [ntaps] narrow blocks
+  uint8_t* a_wide = bres_n + ((p.ntaps * p.n_narrow * nb + 1023) & ~1023);   // ring of wide_slots x kHaloWideSlot
   uint8_t* a_narrow = a_wide + p.wide_slots * kHaloWideSlot;            // ring of 2 x kHaloNarrowSlot (if any)
   uint64_t* bars = reinterpret_cast<uint64_t*>(a_narrow + (p.n_narrow ? 2 * kHaloNarrowSlot : 0));
   uint64_t* wfull = bars;                 // [3]
@@ -320,8 +332,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      mbar_arrive_expect_tx(bres_bar, static_cast<uint32_t>(9 * (p.n_wide * wb + p.n_narrow * nb)));
-      for (int t = 0; t < 9; ++t) {
+      mbar_arrive_expect_tx(bres_bar, static_cast<uint32_t>(p.ntaps * (p.n_wide * wb + p.n_narrow * nb)));
+      for (int t = 0; t < p.ntaps; ++t) {
         const int row = p.taps[t].b_row + part * p.n_part;
         for (int c = 0; c < p.n_wide; ++c)
           tma_load_2d(&p.b64, bres_bar, bres_w + (t * p.n_wide + c) * wb, c * 64, row);
@@ -337,7 +349,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
           if (p.dbg & 1) {
             mbar_arrive(&wfull[ws]);
           } else {
-            mbar_arrive_expect_tx(&wfull[ws], kHaloRows * 128);
+            mbar_arrive_expect_tx(&wfull[ws], p.halo_w * p.halo_h * 128);
             tma_load_5d(&p.a64, &wfull[ws], a_wide + ws * kHaloWideSlot, c * 64, 0, x0, 0, y0);
           }
           if (++ws == p.wide_slots) { ws = 0; wph ^= 1; }
@@ -347,7 +359,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
           if (p.dbg & 1) {
             mbar_arrive(&nfull[ns]);
           } else {
-            mbar_arrive_expect_tx(&nfull[ns], kHaloRows * 32);
+            mbar_arrive_expect_tx(&nfull[ns], p.halo_w * p.halo_h * 32);
             tma_load_5d(&p.a16, &nfull[ns], a_narrow + ns * kHaloNarrowSlot, p.n_wide * 64, 0, x0, 0, y0);
           }
           if (++ns == 2) { ns = 0; nph ^= 1; }
@@ -365,9 +377,9 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
       const uint32_t bw_addr = smem_u32(bres_w), bn_addr = smem_u32(bres_n);
       // descriptor = {hi word (constant), lo word = flags | (address >> 4)}; all per-tap / per-K-step changes are
       // plain adds on the lo word (addresses are < 256 KB, so they never carry into the LBO field)
-      const uint64_t dw = make_smem_desc(0, 16, (kHaloTW + 2) * 128, SWZ_128B);   // A, wide
+      const uint64_t dw = make_smem_desc(0, 16, p.halo_w * 128, SWZ_128B);   // A, wide
       const uint64_t db_ = make_smem_desc(0, 16, 1024, SWZ_128B);                 // B, wide
-      const uint64_t dan = make_smem_desc(0, 16, (kHaloTW + 2) * 32, SWZ_32B);    // A, narrow
+      const uint64_t dan = make_smem_desc(0, 16, p.halo_w * 32, SWZ_32B);    // A, narrow
       const uint64_t dbn = make_smem_desc(0, 16, 256, SWZ_32B);                   // B, narrow
       const uint32_t aw_hi = static_cast<uint32_t>(dw >> 32), aw_lo0 = static_cast<uint32_t>(dw);
       const uint32_t bw_hi = static_cast<uint32_t>(db_ >> 32), bw_lo0 = static_cast<uint32_t>(db_);
@@ -375,7 +387,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
       const uint32_t bn_hi = static_cast<uint32_t>(dbn >> 32), bn_lo0 = static_cast<uint32_t>(dbn);
       uint32_t tap_row[9];                                  // (oy * 10 + ox): halo row of the tap's view origin
 #pragma unroll
-      for (int t = 0; t < 9; ++t) tap_row[t] = static_cast<uint32_t>(p.taps[t].oy * (kHaloTW + 2) + p.taps[t].ox);
+      for (int t = 0; t < 9; ++t) tap_row[t] = static_cast<uint32_t>(p.taps[t].oy * p.halo_w + p.taps[t].ox);
       const uint32_t b_tap_step = static_cast<uint32_t>(p.n_wide * wb) >> 4, bn_tap_step = static_cast<uint32_t>(nb) >> 4;
       const uint32_t idw = p.idesc_wide, idn = p.idesc_narrow;
       for (int tile = seq0; tile < ntiles; tile += seq_stride, ++it) {
@@ -393,6 +405,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
           if (elect_one()) {          // one elected region per chunk: 36 MMAs + the commit, descriptors by adds
 #pragma unroll
             for (int t = 0; t < 9; ++t) {
+              if (t >= p.ntaps) break;
               const uint32_t da_lo = a_lo + tap_row[t] * 8u;          // 128 B per halo row = 8 x 16 B
               const uint32_t db_lo = b_lo + static_cast<uint32_t>(t) * b_tap_step;
 #pragma unroll
@@ -414,6 +427,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
           if (elect_one()) {
 #pragma unroll
             for (int t = 0; t < 9; ++t) {
+              if (t >= p.ntaps) break;
               const uint32_t da_lo = a_lo + tap_row[t] * 2u;          // 32 B per halo row
               const uint32_t db_lo = b_lo + static_cast<uint32_t>(t) * bn_tap_step;
               umma_f16(tmem_d, (static_cast<uint64_t>(an_hi) << 32) | da_lo, (static_cast<uint64_t>(bn_hi) << 32) | db_lo,
@@ -480,14 +494,14 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
 // floor).  Both CTAs stream A with pair-TMA loads accounted on CTA 0's barriers; MMA completion is multicast to
 // both CTAs' barriers; both CTAs' epilogue warps release the accumulator stage on CTA 0's barrier.
 // =============================================================================================
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHaloThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHalo2Threads, 1)
     conv_halo2_kernel(const __grid_constant__ HaloParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int wb = p.n_part * 128, nb = p.n_part * 32;                    // bytes of one resident weight block
   uint8_t* bres_w = smem;
-  uint8_t* bres_n = bres_w + 9 * p.n_wide * wb;
-  uint8_t* a_wide = bres_n + ((9 * p.n_narrow * nb + 1023) & ~1023);
+  uint8_t* bres_n = bres_w + p.ntaps * p.n_wide * wb;
+  uint8_t* a_wide = bres_n + ((p.ntaps * p.n_narrow * nb + 1023) & ~1023);
   uint8_t* a_narrow = a_wide + p.wide_slots * kHaloWideSlot;
   uint64_t* bars = reinterpret_cast<uint64_t*>(a_narrow + (p.n_narrow ? 2 * kHaloNarrowSlot : 0));
   uint64_t* wfull = bars;                 // [3]  (CTA 0's copy is the live one)
@@ -513,7 +527,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHaloThreads, 1)
     if (p.n_narrow) { tma_prefetch_desc(&p.a16); tma_prefetch_desc(&p.b16); }
     for (int i = 0; i < 3; ++i) { mbar_init(&wfull[i], 1); mbar_init(&wempty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&nfull[i], 1); mbar_init(&nempty[i], 1); }
-    for (int i = 0; i < kAcc; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
+    for (int i = 0; i < kAcc; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 16); }   // 8 epilogue warps x 2 CTAs
     mbar_init(bres_bar, 1);
     fence_barrier_init();
   }
@@ -530,9 +544,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHaloThreads, 1)
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
     if (lane == 0) {
-      const uint32_t bbytes = static_cast<uint32_t>(9 * (p.n_wide * wb + p.n_narrow * nb));
+      const uint32_t bbytes = static_cast<uint32_t>(p.ntaps * (p.n_wide * wb + p.n_narrow * nb));
       if (rank == 0) mbar_arrive_expect_tx(bres_bar, 2 * bbytes);
-      for (int t = 0; t < 9; ++t) {
+      for (int t = 0; t < p.ntaps; ++t) {
         const int row = p.taps[t].b_row + static_cast<int>(rank) * p.n_part;
         for (int c = 0; c < p.n_wide; ++c)
           tma_load_2d_pair(&p.b64, bres_bar, bres_w + (t * p.n_wide + c) * wb, c * 64, row);
@@ -546,13 +560,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHaloThreads, 1)
         const int y0 = (tile / p.tiles_x) * kHaloTH + p.org_y;
         for (int c = 0; c < p.n_wide; ++c) {
           mbar_wait(&wempty[ws], wph ^ 1, p.err, 31);
-          if (rank == 0) mbar_arrive_expect_tx(&wfull[ws], 2 * kHaloRows * 128);
+          if (rank == 0) mbar_arrive_expect_tx(&wfull[ws], 2 * p.halo_w * p.halo_h * 128);
           tma_load_5d_pair(&p.a64, &wfull[ws], a_wide + ws * kHaloWideSlot, c * 64, 0, x0, 0, y0);
           if (++ws == p.wide_slots) { ws = 0; wph ^= 1; }
         }
         if (p.n_narrow) {
           mbar_wait(&nempty[ns], nph ^ 1, p.err, 32);
-          if (rank == 0) mbar_arrive_expect_tx(&nfull[ns], 2 * kHaloRows * 32);
+          if (rank == 0) mbar_arrive_expect_tx(&nfull[ns], 2 * p.halo_w * p.halo_h * 32);
           tma_load_5d_pair(&p.a16, &nfull[ns], a_narrow + ns * kHaloNarrowSlot, p.n_wide * 64, 0, x0, 0, y0);
           if (++ns == 2) { ns = 0; nph ^= 1; }
         }
@@ -565,9 +579,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHaloThreads, 1)
       int ws = 0, ns = 0, it = 0;
       uint32_t wph = 0, nph = 0;
       const uint32_t bw_addr = smem_u32(bres_w), bn_addr = smem_u32(bres_n);
-      const uint64_t dw = make_smem_desc(0, 16, (kHaloTW + 2) * 128, SWZ_128B);
+      const uint64_t dw = make_smem_desc(0, 16, p.halo_w * 128, SWZ_128B);
       const uint64_t db_ = make_smem_desc(0, 16, 1024, SWZ_128B);
-      const uint64_t dan = make_smem_desc(0, 16, (kHaloTW + 2) * 32, SWZ_32B);
+      const uint64_t dan = make_smem_desc(0, 16, p.halo_w * 32, SWZ_32B);
       const uint64_t dbn = make_smem_desc(0, 16, 256, SWZ_32B);
       const uint32_t aw_hi = static_cast<uint32_t>(dw >> 32), aw_lo0 = static_cast<uint32_t>(dw);
       const uint32_t bw_hi = static_cast<uint32_t>(db_ >> 32), bw_lo0 = static_cast<uint32_t>(db_);
@@ -575,7 +589,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHaloThreads, 1)
       const uint32_t bn_hi = static_cast<uint32_t>(dbn >> 32), bn_lo0 = static_cast<uint32_t>(dbn);
       uint32_t tap_row[9];
 #pragma unroll
-      for (int t = 0; t < 9; ++t) tap_row[t] = static_cast<uint32_t>(p.taps[t].oy * (kHaloTW + 2) + p.taps[t].ox);
+      for (int t = 0; t < 9; ++t) tap_row[t] = static_cast<uint32_t>(p.taps[t].oy * p.halo_w + p.taps[t].ox);
       const uint32_t b_tap_step = static_cast<uint32_t>(p.n_wide * wb) >> 4, bn_tap_step = static_cast<uint32_t>(nb) >> 4;
       const uint32_t idw = p.idesc_wide, idn = p.idesc_narrow;
       for (int pair = pair0; pair < npairs; pair += pair_stride, ++it) {
@@ -593,6 +607,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHaloThreads, 1)
           if (elect_one()) {
 #pragma unroll
             for (int t = 0; t < 9; ++t) {
+              if (t >= p.ntaps) break;
               const uint32_t da_lo = a_lo + tap_row[t] * 8u;
               const uint32_t db_lo = b_lo + static_cast<uint32_t>(t) * b_tap_step;
 #pragma unroll
@@ -614,6 +629,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHaloThreads, 1)
           if (elect_one()) {
 #pragma unroll
             for (int t = 0; t < 9; ++t)
+              if (t < p.ntaps)
               umma_f16_pair(tmem_d, (static_cast<uint64_t>(an_hi) << 32) | (a_lo + tap_row[t] * 2u),
                             (static_cast<uint64_t>(bn_hi) << 32) | (b_lo + static_cast<uint32_t>(t) * bn_tap_step), idn,
                             1u);
@@ -628,12 +644,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHaloThreads, 1)
     }
   } else {
     // ===================== epilogue (both CTAs: own tile, all output channels) =====================
+    // 8 warps: warp w reads TMEM lanes 32 (w & 3) .. +31 (the quarter its id allows) and one half of the columns,
+    // so two warps per scheduler hide each other's TMEM-load / shuffle latencies; the next chunk's tcgen05.ld is
+    // in flight while the current one is converted, stored and reduced.
     const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row = quarter * 32 + lane;
     const int nchunks = (2 * p.n_part) >> 4;              // 8 (N = 128) or 9 (N = 144)
-    float acc_s[9], acc_q[9];
+    const int c_begin = half ? (nchunks + 1) / 2 : 0, c_end = half ? nchunks : (nchunks + 1) / 2;
+    float acc_s[5], acc_q[5];
 #pragma unroll
-    for (int c = 0; c < 9; ++c) { acc_s[c] = 0.f; acc_q[c] = 0.f; }
+    for (int c = 0; c < 5; ++c) { acc_s[c] = 0.f; acc_q[c] = 0.f; }
     int it = 0;
     for (int pair = pair0; pair < npairs; pair += pair_stride, ++it) {
       const int as = it % kAcc;
@@ -646,9 +667,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHaloThreads, 1)
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(as * 256);
       const long long obase = static_cast<long long>(y) * p.out_sy + static_cast<long long>(x) * p.out_sx;
+      if (!(p.dbg & 2)) {
+        uint32_t v[2][16];
+        tmem_ld16(taddr + static_cast<uint32_t>(c_begin * 16), v[0]);
 #pragma unroll
-      for (int c = 0; c < 9; ++c)
-        if (c < nchunks) halo_epilogue_chunk(p, taddr, c, 0, valid, obase, lane, acc_s[c], acc_q[c]);
+        for (int i = 0; i < 5; ++i) {
+          const int c = c_begin + i;
+          if (c < c_end) {
+            tmem_ld_wait();
+            if (c + 1 < c_end) tmem_ld16(taddr + static_cast<uint32_t>((c + 1) * 16), v[(i + 1) & 1]);
+            halo_epilogue_process(p, v[i & 1], c, 0, valid, obase, lane, acc_s[i], acc_q[i]);
+          }
+        }
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(&tempty[as], 0);
@@ -656,10 +687,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHaloThreads, 1)
     if (p.stats != nullptr && (lane & 1) == 0) {
       const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
 #pragma unroll
-      for (int c = 0; c < 9; ++c) {
-        if (c < nchunks) {
-          atomicAdd(&p.stats[c * 16 + col], acc_s[c]);
-          atomicAdd(&p.stats[p.stats_stride + c * 16 + col], acc_q[c]);
+      for (int i = 0; i < 5; ++i) {
+        const int c = c_begin + i;
+        if (c < c_end) {
+          atomicAdd(&p.stats[c * 16 + col], acc_s[i]);
+          atomicAdd(&p.stats[p.stats_stride + c * 16 + col], acc_q[i]);
         }
       }
     }
@@ -890,8 +922,8 @@ int launch_conv_gemm(const ConvGemmParams& p, int num_sms, cudaStream_t stream) 
   return static_cast<int>(cudaGetLastError());
 }
 
-int halo_smem_bytes(int n_part, int n_wide, int n_narrow, int wide_slots) {
-  const int bres = 9 * n_wide * n_part * 128 + ((9 * n_narrow * n_part * 32 + 1023) & ~1023);
+int halo_smem_bytes(int n_part, int n_wide, int n_narrow, int wide_slots, int ntaps) {
+  const int bres = ntaps * n_wide * n_part * 128 + ((ntaps * n_narrow * n_part * 32 + 1023) & ~1023);
   return bres + wide_slots * kHaloWideSlot + (n_narrow ? 2 * kHaloNarrowSlot : 0) + 256 + 1024;
 }
 
@@ -910,7 +942,7 @@ int launch_conv_halo(const HaloParams& p, int num_sms, cudaStream_t stream) {
     const int npairs = (ntiles + 1) / 2;
     int clusters = num_sms / 2;
     if (clusters > npairs) clusters = npairs;
-    conv_halo2_kernel<<<2 * clusters, kHaloThreads, p.smem_bytes, stream>>>(p);
+    conv_halo2_kernel<<<2 * clusters, kHalo2Threads, p.smem_bytes, stream>>>(p);
     return static_cast<int>(cudaGetLastError());
   }
   int grid = (num_sms / p.parts) * p.parts;

@@ -59,6 +59,7 @@ struct alignas(64) ConvGemmParams {
 //   => shared-memory fill traffic drops from 864 KB to ~50 KB per tile, so the kernel is MMA-bound, not L2-bound.
 // ---------------------------------------------------------------------------------------------
 constexpr int kHaloThreads = 192;        // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+constexpr int kHalo2Threads = 320;       // pair kernel: warps 2-9 epilogue (two per TMEM lane quarter)
 constexpr int kHaloTW = 8, kHaloTH = 16; // output tile (pixels); halo = 10 x 18
 constexpr int kHaloRows = (kHaloTW + 2) * (kHaloTH + 2);          // 180
 constexpr int kHaloWideSlot = 23552;     // 180 rows x 128 B = 23040, rounded up to 1024
@@ -71,6 +72,8 @@ struct alignas(64) HaloParams {
   CUtensorMap a64, a16;      // input (padded grid): boxes (64 | 16, 1, 10, 1, 18)
   CUtensorMap b64, b16;      // packed weights [rows][K]: boxes (64 | 16, n_part)
   HaloTap taps[9];
+  int ntaps;                 // 9 (3x3) or 1 (1x1)
+  int halo_w, halo_h;        // TMA box extent in pixels: (8+2) x (16+2) for 3x3, 8 x 16 for 1x1
   int n_wide, n_narrow;      // 64-channel chunks (2) and 16-channel chunks (0 or 1) of K
   int n_part, parts;         // output channels per CTA slice (64 or 48), number of slices (2 or 3)
   int org_x, org_y;          // halo origin relative to the tile origin in input coordinates (0 fprop, -1 dgrad)

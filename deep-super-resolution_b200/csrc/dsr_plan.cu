@@ -438,7 +438,7 @@ int build_conv(dsr_plan* p, ConvLayer& c) {
     g.err = static_cast<int*>(p->errword.ptr);
   }
   // ---------------- halo-tile variants ----------------
-  c.has_halo = (c.k == 3 && c.stride == 1 && c.cin_pad >= 128);
+  c.has_halo = (c.stride == 1 && c.cin_pad >= 128);     // 3x3 and 1x1 stride-1 layers
   if (c.has_halo) {
     {
       HaloParams& h = c.hfprop;
@@ -449,21 +449,27 @@ int build_conv(dsr_plan* p, ConvLayer& c) {
       h.n_part = 64;
       h.parts = 2;
       h.wide_slots = h.n_narrow ? 2 : 3;
-      if ((rc = make_act_map(&h.a64, c.in_pad->ptr, 1, c.cin_pad, Wp, Hp, 1, 64, kHaloTW + 2, kHaloTH + 2))) return rc;
+      h.ntaps = c.k * c.k;
+      h.halo_w = kHaloTW + (c.k - 1);
+      h.halo_h = kHaloTH + (c.k - 1);
+      if ((rc = make_act_map(&h.a64, c.in_pad->ptr, 1, c.cin_pad, Wp, Hp, 1, 64, h.halo_w, h.halo_h))) return rc;
       h.a16 = h.a64;
-      if (h.n_narrow &&
-          (rc = make_act_map(&h.a16, c.in_pad->ptr, 1, c.cin_pad, Wp, Hp, 1, 16, kHaloTW + 2, kHaloTH + 2)))
+      if (h.n_narrow && (rc = make_act_map(&h.a16, c.in_pad->ptr, 1, c.cin_pad, Wp, Hp, 1, 16, h.halo_w, h.halo_h)))
         return rc;
       const void* wf = warena + c.pack.f_off;
-      if ((rc = make_wgt_map(&h.b64, wf, c.cin_pad, 9 * kNC, 64, h.n_part))) return rc;
+      if ((rc = make_wgt_map(&h.b64, wf, c.cin_pad, h.ntaps * kNC, 64, h.n_part))) return rc;
       h.b16 = h.b64;
-      if (h.n_narrow && (rc = make_wgt_map(&h.b16, wf, c.cin_pad, 9 * kNC, 16, h.n_part))) return rc;
-      for (int ky = 0; ky < 3; ++ky)
-        for (int kx = 0; kx < 3; ++kx)
-          h.taps[ky * 3 + kx] = HaloTap{static_cast<int8_t>(ky), static_cast<int8_t>(kx),
-                                        static_cast<int16_t>((ky * 3 + kx) * kNC)};
-      h.org_x = 0;
-      h.org_y = 0;
+      if (h.n_narrow && (rc = make_wgt_map(&h.b16, wf, c.cin_pad, h.ntaps * kNC, 16, h.n_part))) return rc;
+      if (c.k == 3) {
+        for (int ky = 0; ky < 3; ++ky)
+          for (int kx = 0; kx < 3; ++kx)
+            h.taps[ky * 3 + kx] = HaloTap{static_cast<int8_t>(ky), static_cast<int8_t>(kx),
+                                          static_cast<int16_t>((ky * 3 + kx) * kNC)};
+      } else {
+        h.taps[0] = HaloTap{0, 0, 0};     // 1x1: the box starts at the interior pixel itself (origin +1 below)
+      }
+      h.org_x = (c.k == 3) ? 0 : 1;
+      h.org_y = (c.k == 3) ? 0 : 1;
       h.tiles_x = (c.outW + kHaloTW - 1) / kHaloTW;
       h.tiles_y = (c.outH + kHaloTH - 1) / kHaloTH;
       h.out_h = c.outH;
@@ -476,7 +482,7 @@ int build_conv(dsr_plan* p, ConvLayer& c) {
       h.stats_stride = kNC;
       h.idesc_wide = make_idesc_f16(128, h.n_part, FMT_F16, FMT_F16, 0, 0);
       h.idesc_narrow = h.idesc_wide;
-      h.smem_bytes = halo_smem_bytes(h.n_part, h.n_wide, h.n_narrow, h.wide_slots);
+      h.smem_bytes = halo_smem_bytes(h.n_part, h.n_wide, h.n_narrow, h.wide_slots, h.ntaps);
       h.dbg = getenv("DSR_HALO_DBG") ? atoi(getenv("DSR_HALO_DBG")) : 0;
       h.pair = getenv("DSR_HALO_1CTA") ? 0 : 1;
       if (h.pair) h.idesc_wide = h.idesc_narrow = make_idesc_f16(256, 2 * h.n_part, FMT_F16, FMT_F16, 0, 0);
@@ -493,17 +499,24 @@ int build_conv(dsr_plan* p, ConvLayer& c) {
       h.parts = (h.pair || c.n_rows == 128) ? 2 : 3;
       h.n_part = c.n_rows / h.parts;                    // 64 / 72 (pairs) or 64 / 48
       h.wide_slots = (h.n_part > 64) ? 2 : 3;           // 72-row weight slices leave room for two halo slots only
-      if ((rc = make_act_map(&h.a64, c.dr.ptr, 1, kNC, oWp, oHp, 1, 64, kHaloTW + 2, kHaloTH + 2))) return rc;
+      h.ntaps = c.k * c.k;
+      h.halo_w = kHaloTW + (c.k - 1);
+      h.halo_h = kHaloTH + (c.k - 1);
+      if ((rc = make_act_map(&h.a64, c.dr.ptr, 1, kNC, oWp, oHp, 1, 64, h.halo_w, h.halo_h))) return rc;
       h.a16 = h.a64;
       const void* wd = warena + c.pack.d_off;
-      if ((rc = make_wgt_map(&h.b64, wd, kNC, 9 * c.n_rows, 64, h.n_part))) return rc;
+      if ((rc = make_wgt_map(&h.b64, wd, kNC, h.ntaps * c.n_rows, 64, h.n_part))) return rc;
       h.b16 = h.b64;
-      for (int ky = 0; ky < 3; ++ky)
-        for (int kx = 0; kx < 3; ++kx)
-          h.taps[ky * 3 + kx] = HaloTap{static_cast<int8_t>(2 - ky), static_cast<int8_t>(2 - kx),
-                                        static_cast<int16_t>((ky * 3 + kx) * c.n_rows)};
-      h.org_x = -1;                                     // padded position q reads dR (padded) at q - k + 1
-      h.org_y = -1;
+      if (c.k == 3) {
+        for (int ky = 0; ky < 3; ++ky)
+          for (int kx = 0; kx < 3; ++kx)
+            h.taps[ky * 3 + kx] = HaloTap{static_cast<int8_t>(2 - ky), static_cast<int8_t>(2 - kx),
+                                          static_cast<int16_t>((ky * 3 + kx) * c.n_rows)};
+      } else {
+        h.taps[0] = HaloTap{0, 0, 0};
+      }
+      h.org_x = (c.k == 3) ? -1 : 0;                    // 3x3: padded position q reads dR (padded) at q - k + 1
+      h.org_y = (c.k == 3) ? -1 : 0;
       h.tiles_x = (iWp + kHaloTW - 1) / kHaloTW;
       h.tiles_y = (iHp + kHaloTH - 1) / kHaloTH;
       h.out_h = iHp;
@@ -517,7 +530,7 @@ int build_conv(dsr_plan* p, ConvLayer& c) {
       h.idesc_wide = h.pair ? make_idesc_f16(256, 2 * h.n_part, FMT_F16, FMT_F16, 0, 0)
                             : make_idesc_f16(128, h.n_part, FMT_F16, FMT_F16, 0, 0);
       h.idesc_narrow = h.idesc_wide;
-      h.smem_bytes = halo_smem_bytes(h.n_part, h.n_wide, h.n_narrow, h.wide_slots);
+      h.smem_bytes = halo_smem_bytes(h.n_part, h.n_wide, h.n_narrow, h.wide_slots, h.ntaps);
       h.err = static_cast<int*>(p->errword.ptr);
     }
   }
