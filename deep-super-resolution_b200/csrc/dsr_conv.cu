@@ -842,6 +842,146 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
 }
 
 // =============================================================================================
+// wgrad_halo_kernel  (see dsr_conv.cuh)
+// =============================================================================================
+__global__ void __launch_bounds__(kWgThreads, 1) wgrad_halo_kernel(const __grid_constant__ WgHaloParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWgHStages * kWgHStageBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kWgHStages;
+  uint64_t* tfull_bar = bars + 2 * kWgHStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kWgHStages + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int group = blockIdx.x / p.nsplit;
+  const int split = blockIdx.x % p.nsplit;
+  const int npb = p.pb_x * p.pb_y;
+  const int pb_begin = static_cast<int>((static_cast<long long>(npb) * split) / p.nsplit);
+  const int pb_end = static_cast<int>((static_cast<long long>(npb) * (split + 1)) / p.nsplit);
+  const int nkb = pb_end - pb_begin;
+  const int ncols = p.n64 * 64 + p.n16 * 16;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.a64);
+    tma_prefetch_desc(&p.b64[0]);
+    for (int s = 0; s < kWgHStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tfull_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t stage_bytes = kWgHStageA;
+      for (int b = 0; b < p.nbox; ++b)
+        stage_bytes += static_cast<uint32_t>(p.box[group][b].width * 8 * (p.n64 * 128 + p.n16 * 32));
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int pb = pb_begin; pb < pb_end; ++pb) {
+        const int x0 = (pb % p.pb_x) * 8;
+        const int y0 = (pb / p.pb_x) * 8;
+        mbar_wait(&empty_bar[stage], phase ^ 1, p.err, 41);
+        uint8_t* sa = smem + stage * kWgHStageBytes;
+        mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
+        tma_load_5d(&p.a64, &full_bar[stage], sa, 0, 0, x0 + 1, 0, y0 + 1);
+        tma_load_5d(&p.a64, &full_bar[stage], sa + 64 * 128, 64, 0, x0 + 1, 0, y0 + 1);
+        for (int b = 0; b < p.nbox; ++b) {
+          const WgBox bx = p.box[group][b];
+          uint8_t* sb = sa + kWgHStageA + bx.off16 * 16;
+          const int rows = bx.width * 8;
+          for (int c = 0; c < p.n64; ++c)
+            tma_load_5d(&p.b64[b], &full_bar[stage], sb + c * rows * 128, c * 64, bx.px, x0 + bx.dx, bx.py, y0 + bx.dy);
+          for (int c = 0; c < p.n16; ++c)
+            tma_load_5d(&p.b16[b], &full_bar[stage], sb + p.n64 * rows * 128 + c * rows * 32, p.c16_base + c * 16, bx.px,
+                        x0 + bx.dx, bx.py, y0 + bx.dy);
+        }
+        if (++stage == kWgHStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // warp-uniform loop; one elected lane issues the tcgen05 instructions
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint64_t hi_a = make_smem_desc(0, 64 * 128, 1024, SWZ_128B);     // dR: chunk stride 8 KB, 8-pixel groups 1 KB
+    for (int k = 0; k < nkb; ++k) {
+      mbar_wait(&full_bar[stage], phase, p.err, 42);
+      tc_fence_after();
+      const uint32_t sa = smem_u32(smem + stage * kWgHStageBytes);
+      for (int r = 0; r < p.nruns; ++r) {
+        const WgRun rn = p.runs[group][r];
+        const WgBox bx = p.box[group][rn.box];
+        const uint32_t rows = static_cast<uint32_t>(bx.width * 8);
+        const uint32_t sb = sa + kWgHStageA + static_cast<uint32_t>(bx.off16 * 16);
+        const uint32_t sb16 = sb + static_cast<uint32_t>(p.n64) * rows * 128;
+        // wide: N-chunks = taps (LBO = 1 pixel row); 8-pixel groups one box row apart
+        const uint64_t hi_b = make_smem_desc(0, 128, static_cast<uint32_t>(bx.width) * 128, SWZ_128B);
+        const uint64_t hi_b16 = p.merge_narrow ? make_smem_desc(0, 32, static_cast<uint32_t>(bx.width) * 32, SWZ_32B)
+                                               : make_smem_desc(0, rows * 32, static_cast<uint32_t>(bx.width) * 32, SWZ_32B);
+        const uint32_t b0 = sb + static_cast<uint32_t>(rn.shift0) * 128, b16 = sb16 + static_cast<uint32_t>(rn.shift0) * 32;
+        const uint32_t kstep = 2u * static_cast<uint32_t>(bx.width);       // K = 16 pixels = 2 rows of the box
+        const uint32_t id_w = p.idesc_base | ((static_cast<uint32_t>(rn.r) * 64u >> 3) << 17);
+        const uint32_t id_n = p.idesc_base | ((static_cast<uint32_t>(p.merge_narrow ? rn.r : p.n16) * 16u >> 3) << 17);
+        const uint32_t cw = tmem_base + static_cast<uint32_t>(rn.col_wide), cn = tmem_base + static_cast<uint32_t>(rn.col_narrow);
+        if (elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t da = hi_a | static_cast<uint64_t>(((sa + ks * 2048) & 0x3FFFF) >> 4);
+            for (int c = 0; c < p.n64; ++c) {
+              const uint64_t db = hi_b | static_cast<uint64_t>(((b0 + c * rows * 128 + ks * kstep * 128) & 0x3FFFF) >> 4);
+              umma_f16(cw + static_cast<uint32_t>(c * rn.r * 64), da, db, id_w, (k | ks) != 0);
+            }
+            if (p.n16) {
+              const uint64_t db = hi_b16 | static_cast<uint64_t>(((b16 + ks * kstep * 32) & 0x3FFFF) >> 4);
+              umma_f16(cn, da, db, id_n, (k | ks) != 0);
+            }
+          }
+        }
+        __syncwarp();
+      }
+      if (elect_one()) {
+        umma_commit(&empty_bar[stage]);
+        if (k == nkb - 1) umma_commit(tfull_bar);
+      }
+      __syncwarp();
+      if (++stage == kWgHStages) { stage = 0; phase ^= 1; }
+    }
+  } else if (nkb > 0) {
+    const int quarter = warp & 3;
+    const int co = quarter * 32 + lane;
+    mbar_wait(tfull_bar, 0, p.err, 43);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    for (int j = 0; j < p.ncolchunks; ++j) {
+      const WgCol cc = p.cols[group][j];
+      float* drow = p.dw + (static_cast<long long>(cc.w_tap) * 128 + co) * p.ldw + cc.ci0;
+      uint32_t v[16];
+      tmem_ld16(taddr + static_cast<uint32_t>(j * 16), v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        red_add_v4(drow + i * 4, __uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
+                   __uint_as_float(v[4 * i + 3]));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// =============================================================================================
 // Host side: tensor-map construction and launches
 // =============================================================================================
 static PFN_encodeTiled g_encode = nullptr;
@@ -948,6 +1088,19 @@ int launch_conv_halo(const HaloParams& p, int num_sms, cudaStream_t stream) {
   int grid = (num_sms / p.parts) * p.parts;
   if (grid > ntiles * p.parts) grid = ntiles * p.parts;
   conv_halo_kernel<<<grid, kHaloThreads, p.smem_bytes, stream>>>(p);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int launch_wgrad_halo(const WgHaloParams& p, cudaStream_t stream) {
+  static bool done = false;
+  if (!done) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgHSmemBytes);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    done = true;
+  }
+  const int grid = p.ngroups * p.nsplit;
+  if (grid <= 0) return 0;
+  wgrad_halo_kernel<<<grid, kWgThreads, kWgHSmemBytes, stream>>>(p);
   return static_cast<int>(cudaGetLastError());
 }
 

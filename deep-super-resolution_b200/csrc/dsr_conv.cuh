@@ -127,4 +127,40 @@ struct alignas(64) WgradParams {
   int* err;
 };
 
+// ---------------------------------------------------------------------------------------------
+// wgrad_halo_kernel: weight gradient with HALO-ROW reuse.  A CTA owns one tap row (ky) and a range of 8 x 8 pixel
+// blocks; per block it loads the dR tile once and, instead of one X tile per tap, ONE X box per parity plane that
+// is (8 + shift) pixels wide -- the taps of the row are column-shifted descriptor views of that box (MN-major
+// operands: a shift is a whole number of 128-byte pixel rows, the swizzle follows the absolute address).
+// Shared-memory fill per 64 pixels drops from 70 KB to 39 KB (stride 1, 144 channels).  Layers narrower than 8
+// pixels keep the per-tap kernel above.
+// ---------------------------------------------------------------------------------------------
+constexpr int kWgHStages = 4;
+constexpr int kWgHStageA = 64 * 128 * 2;          // dR: 2 chunks of [64 px][64 co]            = 16 KB
+constexpr int kWgHStageBox = 36 * 1024;           // X boxes of one stage (max: stride 2, 128 ch = 34 KB)
+constexpr int kWgHStageBytes = kWgHStageA + kWgHStageBox;
+constexpr int kWgHSmemBytes = kWgHStages * kWgHStageBytes + 1024 + 256;
+
+struct WgBox { int8_t px, py, dx, dy; int16_t width; int16_t off16; };   // off16: offset in the box area / 16
+// A RUN = taps of one tap row that are consecutive 1-pixel shifts of the same box.  One MMA per 64-channel chunk
+// covers the whole run: N = r x 64 with LBO = one pixel row (128 B), i.e. the N-chunks of the B operand ARE the
+// taps, so the dR operand is fetched once per run instead of once per tap (wgrad is operand-fetch bound).
+struct WgRun { int8_t box, shift0, r, pad_; int16_t col_wide, col_narrow; };   // first TMEM column of wide / narrow part
+struct WgCol { int16_t w_tap, ci0; };              // destination of one 16-column TMEM chunk
+
+struct alignas(64) WgHaloParams {
+  CUtensorMap a64;             // dR (padded grid): box (64, 1, 8, 1, 8)
+  CUtensorMap b64[2], b16[2];  // X source boxes: (64 | 16, 1, width, 1, 8)
+  WgBox box[3][2];             // [group][box]
+  WgRun runs[3][3];            // [group][run]
+  WgCol cols[3][28];           // [group][TMEM 16-column chunk]
+  int nbox, nruns, ncolchunks, ngroups;
+  int merge_narrow;            // 1: narrow part of a run is one MMA (N = r x 16, LBO = 32 B); 0: n16 chunks, LBO = chunk
+  int nsplit, pb_x, pb_y;
+  int n64, n16, c16_base, ldw;
+  float* dw;
+  uint32_t idesc_base;         // kind::f16, both operands MN-major, M = 128, N field left 0
+  int* err;
+};
+
 }  // namespace dsr

@@ -85,8 +85,10 @@ struct ConvLayer {
   ConvGemmParams fprop{};
   ConvGemmParams dgrad[4];
   int ndgrad = 0;
-  HaloParams hfprop{}, hdgrad{};   // weight-stationary halo-tile variants (3x3 stride 1 only)
+  HaloParams hfprop{}, hdgrad{};   // weight-stationary halo-tile variants (stride-1 layers)
   bool has_halo = false;
+  WgHaloParams hwgrad{};           // halo-row wgrad (layers at least 8 pixels wide)
+  bool has_hwgrad = false;
   WgradParams wgrad{};
   ActRef ref_in{}, ref_dr{};       // checker views
   WgtRef ref_wf{}, ref_wd{};
@@ -145,6 +147,11 @@ struct dsr_plan {
   int launches = 0;
   int debug_conv = 0;
   int use_halo = 1;              // 3x3 stride-1 layers: halo-tile weight-stationary kernel (0: generic kernel)
+  // weight-gradient kernels run on a second stream (they only feed the final unpack): fork after the layer's
+  // dR is written, join before unpack_wgrad.  Fills the SMs that the latency-bound low-resolution levels leave idle.
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  int use_side = 1;
   bool bound = false, have_forward = false;
   // optional per-launch timing of the tensor-core kernels (bench.py roofline): class 0 = conv_gemm, 1 = wgrad
   struct ProfRec { int cls; cudaEvent_t a, b; double flops; };
@@ -437,6 +444,106 @@ int build_conv(dsr_plan* p, ConvLayer& c) {
     g.idesc16 = make_idesc_f16(128, 16 * (g.n16 > 0 ? g.n16 : 1), FMT_F16, FMT_F16, 1, 1);   // n16 chunks, LBO apart
     g.err = static_cast<int*>(p->errword.ptr);
   }
+  // ---------------- halo-row wgrad ----------------
+  c.has_hwgrad = (c.outW >= 8 && c.outH >= 8 && !getenv("DSR_WGRAD_OLD"));
+  if (c.has_hwgrad) {
+    WgHaloParams& g = c.hwgrad;
+    memset(&g, 0, sizeof(g));
+    const WgradParams& o = c.wgrad;
+    if ((rc = make_act_map(&g.a64, c.dr.ptr, 1, kNC, c.outW + 2, c.outH + 2, 1, 64, 8, 8))) return rc;
+    const int Wp = c.inW + 2, Hp = c.inH + 2;
+    g.n64 = o.n64; g.n16 = o.n16; g.c16_base = o.c16_base; g.ldw = o.ldw; g.dw = o.dw;
+    g.idesc_base = make_idesc_f16(128, 0, FMT_F16, FMT_F16, 1, 1);
+    g.err = o.err;
+    g.pb_x = (c.outW + 7) / 8;
+    g.pb_y = (c.outH + 7) / 8;
+    g.merge_narrow = (g.n16 <= 1) ? 1 : 0;
+    int widths[2] = {8, 8};
+    // taps of one tap row, as runs of consecutive shifts: {box, shift0, r, kx of the run's taps...}
+    struct RunDef { int box, shift0, r, kx[3]; };
+    RunDef defs[3];
+    int ndefs = 0;
+    if (c.k == 1) {
+      g.ngroups = 1; g.nbox = 1;
+      g.box[0][0] = WgBox{0, 0, 1, 1, 8, 0};
+      defs[ndefs++] = RunDef{0, 0, 1, {0, 0, 0}};
+    } else if (c.stride == 1) {
+      g.ngroups = 3; g.nbox = 1;
+      widths[0] = 10;
+      for (int ky = 0; ky < 3; ++ky) g.box[ky][0] = WgBox{0, 0, 0, static_cast<int8_t>(ky), 10, 0};
+      if (g.merge_narrow) {
+        defs[ndefs++] = RunDef{0, 0, 3, {0, 1, 2}};
+      } else {
+        for (int kx = 0; kx < 3; ++kx) defs[ndefs++] = RunDef{0, kx, 1, {kx, 0, 0}};
+      }
+    } else {   // stride 2: parity-0 columns serve kx = 0 (shift 0) and kx = 2 (shift 1); parity-1 columns serve kx = 1
+      g.ngroups = 3; g.nbox = 2;
+      widths[0] = 9;
+      widths[1] = 8;
+      const int rows0 = 9 * 8;
+      const int off1 = rows0 * (g.n64 * 128 + g.n16 * 32);
+      for (int ky = 0; ky < 3; ++ky) {
+        g.box[ky][0] = WgBox{0, static_cast<int8_t>(ky & 1), 0, static_cast<int8_t>(ky >> 1), 9, 0};
+        g.box[ky][1] = WgBox{1, static_cast<int8_t>(ky & 1), 0, static_cast<int8_t>(ky >> 1), 8,
+                             static_cast<int16_t>(((off1 + 1023) & ~1023) / 16)};
+      }
+      if (g.merge_narrow) {
+        defs[ndefs++] = RunDef{0, 0, 2, {0, 2, 0}};
+        defs[ndefs++] = RunDef{1, 0, 1, {1, 0, 0}};
+      } else {
+        defs[ndefs++] = RunDef{0, 0, 1, {0, 0, 0}};
+        defs[ndefs++] = RunDef{1, 0, 1, {1, 0, 0}};
+        defs[ndefs++] = RunDef{0, 1, 1, {2, 0, 0}};
+      }
+    }
+    g.nruns = ndefs;
+    // TMEM column layout: per run, per 64-channel chunk: r x 64 columns (tap-major); then the narrow parts
+    for (int grp = 0; grp < g.ngroups; ++grp) {
+      int col = 0;
+      for (int r = 0; r < ndefs; ++r) {
+        g.runs[grp][r] = WgRun{static_cast<int8_t>(defs[r].box), static_cast<int8_t>(defs[r].shift0),
+                               static_cast<int8_t>(defs[r].r), 0, static_cast<int16_t>(col), 0};
+        for (int ch = 0; ch < g.n64; ++ch)
+          for (int t = 0; t < defs[r].r; ++t)
+            for (int q = 0; q < 4; ++q) {
+              g.cols[grp][col / 16] = WgCol{static_cast<int16_t>(c.k == 1 ? 0 : grp * 3 + defs[r].kx[t]),
+                                            static_cast<int16_t>(ch * 64 + q * 16)};
+              col += 16;
+            }
+      }
+      for (int r = 0; r < ndefs; ++r) {
+        g.runs[grp][r].col_narrow = static_cast<int16_t>(col);
+        if (g.merge_narrow) {
+          for (int t = 0; t < defs[r].r && g.n16; ++t) {
+            g.cols[grp][col / 16] = WgCol{static_cast<int16_t>(c.k == 1 ? 0 : grp * 3 + defs[r].kx[t]),
+                                          static_cast<int16_t>(g.c16_base)};
+            col += 16;
+          }
+        } else {
+          for (int q = 0; q < g.n16; ++q) {
+            g.cols[grp][col / 16] = WgCol{static_cast<int16_t>(c.k == 1 ? 0 : grp * 3 + defs[r].kx[0]),
+                                          static_cast<int16_t>(g.c16_base + q * 16)};
+            col += 16;
+          }
+        }
+      }
+      g.ncolchunks = col / 16;
+      if (col > 512) return -22;
+    }
+    for (int b = 0; b < g.nbox; ++b) {
+      if ((rc = make_act_map(&g.b16[b], c.in_pad->ptr, 1, c.cin_pad, Wp, Hp, c.stride, 16, widths[b], 8))) return rc;
+      g.b64[b] = g.b16[b];
+      if (c.cin_pad >= 64 &&
+          (rc = make_act_map(&g.b64[b], c.in_pad->ptr, 1, c.cin_pad, Wp, Hp, c.stride, 64, widths[b], 8)))
+        return rc;
+    }
+    if (g.nbox == 1) { g.b64[1] = g.b64[0]; g.b16[1] = g.b16[0]; }
+    const int npb = g.pb_x * g.pb_y;
+    int nsplit = p->num_sms / g.ngroups;
+    if (nsplit > npb) nsplit = npb;
+    if (nsplit < 1) nsplit = 1;
+    g.nsplit = nsplit;
+  }
   // ---------------- halo-tile variants ----------------
   c.has_halo = (c.stride == 1 && c.cin_pad >= 128);     // 3x3 and 1x1 stride-1 layers
   if (c.has_halo) {
@@ -600,6 +707,7 @@ int run_dgrad(dsr_plan* p, ConvLayer& c, int i, cudaStream_t s) {
 int run_wgrad(dsr_plan* p, ConvLayer& c, cudaStream_t s) {
   if (p->debug_conv) return launch_wgrad_ref(c.wgrad, c.ref_dr, c.ref_in, s);
   ProfScope ps(p, 1, conv_flops(c), s);
+  if (c.has_hwgrad) return launch_wgrad_halo(c.hwgrad, s);
   return launch_wgrad(c.wgrad, s);
 }
 
@@ -669,7 +777,15 @@ int bn_backward(dsr_plan* p, ConvLayer& c, const float* params, float* grads, co
 }
 
 int conv_backward(dsr_plan* p, ConvLayer& c, cudaStream_t s) {
-  DSR_TRY(run_wgrad(p, c, s));
+  if (p->side != nullptr && p->use_side) {
+    cudaError_t e = cudaEventRecord(p->ev_fork, s);              // dR of this layer is complete on the main stream
+    if (e != cudaSuccess) return static_cast<int>(e);
+    e = cudaStreamWaitEvent(p->side, p->ev_fork, 0);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    DSR_TRY(run_wgrad(p, c, p->side));
+  } else {
+    DSR_TRY(run_wgrad(p, c, s));
+  }
   for (int i = 0; i < c.ndgrad; ++i) DSR_TRY(run_dgrad(p, c, i, s));
   return 0;
 }
@@ -981,6 +1097,12 @@ int dsr_plan_create(dsr_plan_t** out, int H, int W, int input_depth, int num_sca
 
 void dsr_plan_destroy(dsr_plan_t* p) {
   if (p) dsr_plan_set_profile(p, 0);
+  if (p && p->side) {
+    cudaStreamSynchronize(p->side);
+    cudaEventDestroy(p->ev_fork);
+    cudaEventDestroy(p->ev_join);
+    cudaStreamDestroy(p->side);
+  }
   delete p;
 }
 
@@ -1043,6 +1165,14 @@ int dsr_plan_bind(dsr_plan_t* p, void* workspace, size_t bytes, void* stream) {
       int rc = build_conv(p, *c);
       if (rc) return rc;
     }
+  if (p->side == nullptr) {
+    if (cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking) != cudaSuccess) p->side = nullptr;
+    if (p->side != nullptr) {
+      cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming);
+      cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming);
+    }
+  }
+  p->use_side = getenv("DSR_NO_SIDE_STREAM") ? 0 : 1;
   p->bound = true;
   p->have_forward = false;
   return 0;
@@ -1083,8 +1213,20 @@ int dsr_net_backward(dsr_plan_t* p, const float* params, const float* out, const
   Level& L0 = p->lv[0];
   DSR_TRY(launch_final_bwd(grad_out, out, L0.u2.act.ptr, params + p->fin_w, L0.g_u2a.ptr, grads + p->fin_w,
                            grads + p->fin_b, static_cast<const float*>(p->gscale.ptr), L0.H, L0.W, s));
+  if (p->side != nullptr && p->use_side) {     // the side stream must see the zeroed accumulators
+    e = cudaEventRecord(p->ev_fork, s);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    e = cudaStreamWaitEvent(p->side, p->ev_fork, 0);
+    if (e != cudaSuccess) return static_cast<int>(e);
+  }
   int rc = backward_level(p, 0, params, grads, s);
   if (rc) return rc;
+  if (p->side != nullptr && p->use_side) {
+    e = cudaEventRecord(p->ev_join, p->side);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    e = cudaStreamWaitEvent(s, p->ev_join, 0);
+    if (e != cudaSuccess) return static_cast<int>(e);
+  }
   DSR_TRY(launch_unpack_wgrad(reinterpret_cast<const float*>(p->base) + p->garena_off, grads,
                               static_cast<const PackDesc*>(p->pack_table.ptr), static_cast<int>(p->pack_host.size()),
                               static_cast<const float*>(p->gscale.ptr), s));
