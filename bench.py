@@ -166,6 +166,8 @@ def run_ours(args, rank, local_rank, world):
 
     dev = torch.device('cuda', local_rank)
     torch.cuda.set_device(dev)
+    # everything runs on one non-default stream (the legacy default stream cannot be captured into a CUDA graph)
+    torch.cuda.set_stream(torch.cuda.Stream(device=dev))
     size = args.size
     H = W = size
 
@@ -201,21 +203,19 @@ def run_ours(args, rank, local_rank, world):
     stream = _lib.stream_ptr()
     t_iter = [0]
 
-    def step():
-        t_iter[0] += 1
-        b.loss_out = losses.data_ptr() + 4 * (t_iter[0] - 1)
-        check(lib.dsr_dip_step(plan.handle, tables.handle, C.byref(b), LR_RATE, SIGMA, 1234 + rank, t_iter[0], stream),
-              'dsr_dip_step')
+    def step(n=1):
+        """n iterations through dsr_dip_run (one CUDA-graph launch per iteration after the first call)"""
+        check(lib.dsr_dip_run(plan.handle, tables.handle, C.byref(b), LR_RATE, SIGMA, 1234 + rank, t_iter[0] + 1, n,
+                              stream), 'dsr_dip_run')
+        t_iter[0] += n
 
     # ---- device-resident throughput ----
-    for _ in range(args.warmup):
-        step()
+    step(args.warmup)
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
-        step()
+    step(args.steps)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -232,8 +232,7 @@ def run_ours(args, rank, local_rank, world):
     if rank == 0:
         check(lib.dsr_plan_set_profile(plan.handle, 1))
         nprof = 3
-        for _ in range(nprof):
-            step()
+        step(nprof)
         torch.cuda.synchronize()
         pk = peaks()
         res = {}

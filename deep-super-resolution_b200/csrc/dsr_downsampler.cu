@@ -24,8 +24,10 @@ inline void ds_tile(int factor, int& tox, int& toy) {
 // dynamic smem: patch [py][px] then rows-filtered [py][kTileOx]
 __global__ void downsample_fwd_kernel(const float* __restrict__ x, const float* __restrict__ target,
                                       float* __restrict__ y, float* __restrict__ gy, float* __restrict__ loss, int C,
-                                      int H, int W, int oh, int ow, DsTables t, int kTileOx, int kTileOy) {
+                                      int H, int W, int oh, int ow, DsTables t, int kTileOx, int kTileOy,
+                                      const float* __restrict__ state) {
   extern __shared__ float sm[];
+  if (state != nullptr && loss != nullptr) loss += __float_as_int(state[0]) - 1;
   const int f = t.factor, k = t.k, pad = t.pad;
   const int pw = (kTileOx - 1) * f + k;          // patch width (input pixels)
   const int ph = (kTileOy - 1) * f + k;
@@ -116,7 +118,7 @@ static size_t ds_smem(const DsTables& t) {
 }
 
 static int ds_launch(const float* x, const float* target, float* y, float* gy, float* loss, int C, int H, int W,
-                     int oh, int ow, DsTables t, cudaStream_t s) {
+                     int oh, int ow, DsTables t, cudaStream_t s, const float* state = nullptr) {
   const size_t smem = ds_smem(t);
   if (smem > 200 * 1024) return -4;
   static size_t configured = 0;
@@ -129,7 +131,7 @@ static int ds_launch(const float* x, const float* target, float* y, float* gy, f
   int kTileOx, kTileOy;
   ds_tile(t.factor, kTileOx, kTileOy);
   dim3 grid((ow + kTileOx - 1) / kTileOx, (oh + kTileOy - 1) / kTileOy, C);
-  downsample_fwd_kernel<<<grid, 256, smem, s>>>(x, target, y, gy, loss, C, H, W, oh, ow, t, kTileOx, kTileOy);
+  downsample_fwd_kernel<<<grid, 256, smem, s>>>(x, target, y, gy, loss, C, H, W, oh, ow, t, kTileOx, kTileOy, state);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -137,8 +139,8 @@ int launch_downsample_fwd(const float* x, float* y, int C, int H, int W, int oh,
   return ds_launch(x, nullptr, y, nullptr, nullptr, C, H, W, oh, ow, t, s);
 }
 int launch_downsample_mse(const float* x, const float* target, float* y, float* gy, float* loss, int C, int H, int W,
-                          int oh, int ow, DsTables t, cudaStream_t s) {
-  return ds_launch(x, target, y, gy, loss, C, H, W, oh, ow, t, s);
+                          int oh, int ow, DsTables t, cudaStream_t s, const float* state) {
+  return ds_launch(x, target, y, gy, loss, C, H, W, oh, ow, t, s, state);
 }
 int launch_downsample_bwd(const float* gy, float* gx, int C, int H, int W, int oh, int ow, DsTables t, cudaStream_t s) {
   const long long n = static_cast<long long>(C) * H * W;

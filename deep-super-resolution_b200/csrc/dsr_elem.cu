@@ -1203,6 +1203,23 @@ int launch_grad_scale_finish(float* grads, long long n, float* gs, cudaStream_t 
 }
 
 // =============================================================================================
+// iteration state kept on the device so that every launch of a step has iteration-independent arguments (CUDA
+// graph replay): state[0] = t (int bits), state[1] = lr / (1 - b1^t), state[2] = 1 / sqrt(1 - b2^t)
+// =============================================================================================
+__global__ void step_begin_kernel(float* __restrict__ state, float* __restrict__ loss_base, int t_set, float lr,
+                                  float b1, float b2) {
+  const int t = (t_set > 0) ? t_set : __float_as_int(state[0]) + 1;
+  state[0] = __int_as_float(t);
+  state[1] = static_cast<float>(static_cast<double>(lr) / (1.0 - pow(static_cast<double>(b1), static_cast<double>(t))));
+  state[2] = static_cast<float>(1.0 / sqrt(1.0 - pow(static_cast<double>(b2), static_cast<double>(t))));
+  if (loss_base != nullptr) loss_base[t - 1] = 0.f;
+}
+int launch_step_begin(float* state, float* loss_base, int t_set, float lr, float b1, float b2, cudaStream_t s) {
+  step_begin_kernel<<<1, 1, 0, s>>>(state, loss_base, t_set, lr, b1, b2);
+  DSR_LAUNCH_CHECK();
+}
+
+// =============================================================================================
 // running statistics
 // =============================================================================================
 __global__ void bn_running_kernel(const BnRunDesc* __restrict__ table, const float* __restrict__ ws,
@@ -1233,7 +1250,11 @@ int launch_bn_running(const BnRunDesc* table_dev, int nbn, const float* ws_f32, 
 // =============================================================================================
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, long long n, float step_size, float b1, float b2, float eps,
-                            float inv_sqrt_bc2) {
+                            float inv_sqrt_bc2, const float* __restrict__ state) {
+  if (state != nullptr) {            // bias corrections of the device-tracked iteration (step_begin_kernel)
+    step_size = state[1];
+    inv_sqrt_bc2 = state[2];
+  }
   const long long n4 = n >> 2;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -1263,16 +1284,17 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 }
 
 int launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
-                int t, cudaStream_t s) {
+                int t, cudaStream_t s, const float* state) {
   if ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
        reinterpret_cast<uintptr_t>(v)) & 15)
     return -3;
+  if (t < 1) t = 1;                  // unused when `state` is given
   const double bc1 = 1.0 - pow(static_cast<double>(b1), t);
   const double bc2 = 1.0 - pow(static_cast<double>(b2), t);
   const float step_size = static_cast<float>(static_cast<double>(lr) / bc1);
   const float inv_sqrt_bc2 = static_cast<float>(1.0 / sqrt(bc2));
   adam_kernel<<<grid_for(n / 4 + 1, kThreads, 148 * 8), kThreads, 0, s>>>(p, g, m, v, n, step_size, b1, b2, eps,
-                                                                         inv_sqrt_bc2);
+                                                                         inv_sqrt_bc2, state);
   DSR_LAUNCH_CHECK();
 }
 
@@ -1292,8 +1314,10 @@ __device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uin
 }
 
 __global__ void perturb_kernel(const float* __restrict__ zs, float* __restrict__ z, long long n, float sigma,
-                               unsigned long long seed, unsigned long long offset) {
+                               unsigned long long seed, unsigned long long offset, const float* __restrict__ state) {
   const long long n4 = (n + 3) >> 2;
+  if (state != nullptr)              // counter block of the device-tracked iteration t: (t - 1) * n4
+    offset = static_cast<unsigned long long>(__float_as_int(state[0]) - 1) * static_cast<unsigned long long>(n4);
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const unsigned long long ctr = offset + static_cast<unsigned long long>(i);
@@ -1319,8 +1343,9 @@ __global__ void perturb_kernel(const float* __restrict__ zs, float* __restrict__
 }
 
 int launch_perturb(const float* z_saved, float* z, long long n, float sigma, unsigned long long seed,
-                   unsigned long long offset, cudaStream_t s) {
-  perturb_kernel<<<grid_for((n + 3) / 4, kThreads, 148 * 8), kThreads, 0, s>>>(z_saved, z, n, sigma, seed, offset);
+                   unsigned long long offset, cudaStream_t s, const float* state) {
+  perturb_kernel<<<grid_for((n + 3) / 4, kThreads, 148 * 8), kThreads, 0, s>>>(z_saved, z, n, sigma, seed, offset,
+                                                                              state);
   DSR_LAUNCH_CHECK();
 }
 

@@ -120,7 +120,9 @@ int launch_bn_running(const BnRunDesc* table_dev, int nbn, const float* ws_f32, 
                       float momentum, cudaStream_t s);
 
 int launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
-                int t, cudaStream_t s);
+                int t, cudaStream_t s, const float* state = nullptr);
+// t_set > 0: state.t = t_set; t_set == 0: state.t += 1.  Also zeroes loss_base[t - 1] (if given).
+int launch_step_begin(float* state, float* loss_base, int t_set, float lr, float b1, float b2, cudaStream_t s);
 
 // ---- Lanczos downsampler (fp32 NCHW) -------------------------------------------------------
 struct DsTables {           // device tables built by the plan (dsr_downsampler.cu)
@@ -134,11 +136,12 @@ struct DsTables {           // device tables built by the plan (dsr_downsampler.
 int launch_downsample_fwd(const float* x, float* y, int C, int H, int W, int oh, int ow, DsTables t, cudaStream_t s);
 int launch_downsample_bwd(const float* gy, float* gx, int C, int H, int W, int oh, int ow, DsTables t, cudaStream_t s);
 // fused: y = D(x); loss += mean((y - target)^2); gy = 2 (y - target) / N
+// loss accumulates into loss[0], or into loss[t - 1] when `state` (device iteration state) is given
 int launch_downsample_mse(const float* x, const float* target, float* y, float* gy, float* loss, int C, int H, int W,
-                          int oh, int ow, DsTables t, cudaStream_t s);
+                          int oh, int ow, DsTables t, cudaStream_t s, const float* state = nullptr);
 
 // z = z_saved + sigma * N(0,1)   (Philox4x32-10 counter RNG, fp32, elementwise)
 int launch_perturb(const float* z_saved, float* z, long long n, float sigma, unsigned long long seed,
-                   unsigned long long offset, cudaStream_t s);
+                   unsigned long long offset, cudaStream_t s, const float* state = nullptr);
 
 }  // namespace dsr

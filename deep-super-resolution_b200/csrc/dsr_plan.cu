@@ -137,7 +137,7 @@ struct dsr_plan {
   size_t acc_bwd_off = 0, acc_bwd_floats = 0;     // zeroed at the start of every backward (incl. wgrad arena)
   size_t garena_off = 0;                          // floats, inside the backward accumulator block
   Buf warena;                                     // packed 16-bit weights
-  Buf pack_table, bnrun_table, errword, gscale;
+  Buf pack_table, bnrun_table, errword, gscale, stepstate;
   Buf g_final;                                    // unused placeholder (level 0 g_u2a is the final-conv gradient)
   std::vector<PackDesc> pack_host;
   std::vector<BnRunDesc> bnrun_host;
@@ -152,6 +152,14 @@ struct dsr_plan {
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int use_side = 1;
+  // CUDA graph of one whole DIP iteration (dsr_dip_run): every launch argument is iteration-independent, the
+  // iteration counter lives on the device (stepstate)
+  cudaGraphExec_t graph_exec = nullptr;
+  dsr_step_buffers_t graph_bufs{};
+  const dsr_downsampler* graph_ds = nullptr;
+  float graph_lr = 0.f, graph_sigma = 0.f;
+  unsigned long long graph_seed = 0;
+  int use_graph = 1;
   bool bound = false, have_forward = false;
   // optional per-launch timing of the tensor-core kernels (bench.py roofline): class 0 = conv_gemm, 1 = wgrad
   struct ProfRec { int cls; cudaEvent_t a, b; double flops; };
@@ -1030,6 +1038,7 @@ int dsr_plan_create(dsr_plan_t** out, int H, int W, int input_depth, int num_sca
   ws.take(p->bnrun_table, sizeof(BnRunDesc) * 6 * num_scales);
   ws.take(p->errword, 256);
   ws.take(p->gscale, 256);
+  ws.take(p->stepstate, 256);
   // place the accumulator blocks
   ws.off = align_up(ws.off, 1024);
   p->acc_fwd_off = ws.off;
@@ -1097,6 +1106,7 @@ int dsr_plan_create(dsr_plan_t** out, int H, int W, int input_depth, int num_sca
 
 void dsr_plan_destroy(dsr_plan_t* p) {
   if (p) dsr_plan_set_profile(p, 0);
+  if (p && p->graph_exec) cudaGraphExecDestroy(p->graph_exec);
   if (p && p->side) {
     cudaStreamSynchronize(p->side);
     cudaEventDestroy(p->ev_fork);
@@ -1148,7 +1158,7 @@ int dsr_plan_bind(dsr_plan_t* p, void* workspace, size_t bytes, void* stream) {
     resolve(L.dsraw); resolve(L.g_d2a);
     for (ConvLayer* c : {&L.d1, &L.d2, &L.u1, &L.u2}) { resolve(c->raw); resolve(c->act); resolve(c->dr); resolve(c->gin); }
   }
-  resolve(p->warena); resolve(p->pack_table); resolve(p->bnrun_table); resolve(p->errword); resolve(p->gscale);
+  resolve(p->warena); resolve(p->pack_table); resolve(p->bnrun_table); resolve(p->errword); resolve(p->gscale); resolve(p->stepstate);
   e = cudaMemcpyAsync(p->pack_table.ptr, p->pack_host.data(), sizeof(PackDesc) * p->pack_host.size(),
                       cudaMemcpyHostToDevice, s);
   if (e != cudaSuccess) return static_cast<int>(e);
@@ -1173,6 +1183,7 @@ int dsr_plan_bind(dsr_plan_t* p, void* workspace, size_t bytes, void* stream) {
     }
   }
   p->use_side = getenv("DSR_NO_SIDE_STREAM") ? 0 : 1;
+  p->use_graph = getenv("DSR_NO_GRAPH") ? 0 : 1;
   p->bound = true;
   p->have_forward = false;
   return 0;
@@ -1247,30 +1258,98 @@ int dsr_perturb(const float* z_saved, float* z, long long n, float sigma, unsign
   return launch_perturb(z_saved, z, n, sigma, seed, offset, static_cast<cudaStream_t>(stream));
 }
 
-int dsr_dip_step(dsr_plan_t* p, const dsr_downsampler_t* d, const dsr_step_buffers_t* b, float lr, float sigma,
-                 unsigned long long seed, int t, void* stream) {
-  if (!p || !d || !b || t < 1) return -1;
-  if (d->H != p->H || d->W != p->W) return -1;
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
+// Enqueues one iteration.  t_set > 0: explicit iteration index; t_set == 0: the device counter is incremented
+// (graph replay).  `losses` is the base of the loss array: this iteration's loss lands in losses[t - 1].
+static int enqueue_step(dsr_plan_t* p, const dsr_downsampler_t* d, const dsr_step_buffers_t* b, float* losses, float lr,
+                        float sigma, unsigned long long seed, int t_set, cudaStream_t s) {
+  void* stream = static_cast<void*>(s);
+  float* st = static_cast<float*>(p->stepstate.ptr);
   const long long nz = static_cast<long long>(p->input_depth) * p->H * p->W;
   int total = 0;
-  int rc = launch_perturb(b->z_saved, b->z, nz, sigma, seed, static_cast<unsigned long long>(t - 1) * ((nz + 3) / 4), s);
+  int rc = launch_step_begin(st, losses, t_set, lr, 0.9f, 0.999f, s);
   if (rc) return rc;
-  ++total;
+  if ((rc = launch_perturb(b->z_saved, b->z, nz, sigma, seed, 0, s, st))) return rc;
+  total += 2;
   if ((rc = dsr_net_forward(p, b->params, b->z, b->out_hr, b->bn_buffers, stream))) return rc;
   total += p->launches;
-  cudaError_t e = cudaMemsetAsync(b->loss_out, 0, 4, s);
-  if (e != cudaSuccess) return static_cast<int>(e);
-  if ((rc = launch_downsample_mse(b->out_hr, b->lr_image, b->out_lr, b->g_out_lr, b->loss_out, p->n_out, d->H, d->W,
-                                  d->oh, d->ow, d->t, s)))
+  if ((rc = launch_downsample_mse(b->out_hr, b->lr_image, b->out_lr, b->g_out_lr, losses, p->n_out, d->H, d->W, d->oh,
+                                  d->ow, d->t, s, st)))
     return rc;
   if ((rc = launch_downsample_bwd(b->g_out_lr, b->g_out_hr, p->n_out, d->H, d->W, d->oh, d->ow, d->t, s))) return rc;
   total += 2;
   if ((rc = dsr_net_backward(p, b->params, b->out_hr, b->g_out_hr, b->grads, stream))) return rc;
   total += p->launches;
-  if ((rc = launch_adam(b->params, b->grads, b->adam_m, b->adam_v, p->nparam, lr, 0.9f, 0.999f, 1e-8f, t, s)))
+  if ((rc = launch_adam(b->params, b->grads, b->adam_m, b->adam_v, p->nparam, lr, 0.9f, 0.999f, 1e-8f, 1, s, st)))
     return rc;
   p->launches = total + 1;
+  return 0;
+}
+
+int dsr_dip_step(dsr_plan_t* p, const dsr_downsampler_t* d, const dsr_step_buffers_t* b, float lr, float sigma,
+                 unsigned long long seed, int t, void* stream) {
+  if (!p || !d || !b || t < 1) return -1;
+  if (!p->bound) return -6;
+  if (d->H != p->H || d->W != p->W) return -1;
+  // loss_out receives this iteration's loss: losses[t - 1] == *loss_out
+  return enqueue_step(p, d, b, b->loss_out - (t - 1), lr, sigma, seed, t, static_cast<cudaStream_t>(stream));
+}
+
+int dsr_dip_run(dsr_plan_t* p, const dsr_downsampler_t* d, const dsr_step_buffers_t* b, float lr, float sigma,
+                unsigned long long seed, int t_first, int n_iters, void* stream) {
+  if (!p || !d || !b || t_first < 1 || n_iters < 0) return -1;
+  if (!p->bound) return -6;
+  if (d->H != p->H || d->W != p->W) return -1;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  float* losses = b->loss_out;           // base of the loss array: iteration t writes losses[t - 1]
+  int done = 0;
+  const bool same = p->graph_exec != nullptr && memcmp(&p->graph_bufs, b, sizeof(*b)) == 0 && p->graph_ds == d &&
+                    p->graph_lr == lr && p->graph_sigma == sigma && p->graph_seed == seed;
+  // the legacy default stream cannot be captured: callers that want graph replay pass a non-default stream
+  const bool capturable = (s != nullptr && s != cudaStreamLegacy && s != cudaStreamPerThread);
+  if (!p->use_graph || p->profile || p->debug_conv || !capturable) {
+    for (; done < n_iters; ++done) {
+      int rc = enqueue_step(p, d, b, losses, lr, sigma, seed, t_first + done, s);
+      if (rc) return rc;
+    }
+    return 0;
+  }
+  if (!same) {
+    if (p->graph_exec) { cudaGraphExecDestroy(p->graph_exec); p->graph_exec = nullptr; }
+    if (n_iters == 0) return 0;
+    // first iteration eagerly (sets function attributes, warms the module), then capture one iteration
+    int rc = enqueue_step(p, d, b, losses, lr, sigma, seed, t_first, s);
+    if (rc) return rc;
+    done = 1;
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    rc = enqueue_step(p, d, b, losses, lr, sigma, seed, 0, s);
+    e = cudaStreamEndCapture(s, &graph);
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (e != cudaSuccess) return static_cast<int>(e);
+    e = cudaGraphInstantiate(&p->graph_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) { p->graph_exec = nullptr; return static_cast<int>(e); }
+    p->graph_bufs = *b;
+    p->graph_ds = d;
+    p->graph_lr = lr;
+    p->graph_sigma = sigma;
+    p->graph_seed = seed;
+  } else if (n_iters > 0) {
+    // position the device counter: the next replay must run iteration t_first
+    int rc = launch_step_begin(static_cast<float*>(p->stepstate.ptr), nullptr, t_first - 1 > 0 ? t_first - 1 : 0, lr, 0.9f,
+                               0.999f, s);
+    if (rc) return rc;
+    if (t_first == 1) {      // t_set == 0 means "increment": write t = 0 explicitly
+      const float zero = 0.f;
+      cudaError_t e = cudaMemcpyAsync(p->stepstate.ptr, &zero, 4, cudaMemcpyHostToDevice, s);
+      if (e != cudaSuccess) return static_cast<int>(e);
+    }
+  }
+  for (; done < n_iters; ++done) {
+    cudaError_t e = cudaGraphLaunch(p->graph_exec, s);
+    if (e != cudaSuccess) return static_cast<int>(e);
+  }
   return 0;
 }
 

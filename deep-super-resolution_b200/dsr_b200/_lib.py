@@ -54,6 +54,7 @@ SIGNATURES = {
     'dsr_adam_step': (i32, [vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, vp]),
     'dsr_perturb': (i32, [vp, vp, i64, f32, u64, u64, vp]),
     'dsr_dip_step': (i32, [vp, vp, C.POINTER(StepBuffers), f32, f32, u64, i32, vp]),
+    'dsr_dip_run': (i32, [vp, vp, C.POINTER(StepBuffers), f32, f32, u64, i32, i32, vp]),
     'dsr_plan_tensor': (i32, [vp, C.c_char_p, C.POINTER(vp), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32),
                               C.POINTER(i32), C.POINTER(i32)]),
     'dsr_plan_last_launches': (i32, [vp]),

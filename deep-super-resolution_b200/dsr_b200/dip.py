@@ -6,7 +6,8 @@ forward, downsample, MSE, backward and the two blocking device-to-host reads of 
 
 `dip_sr_fused` is the same optimisation with every iteration enqueued by ONE library call
 (dsr_dip_step: device Philox perturbation -> forward -> Lanczos downsample + MSE -> backward ->
-Adam) and no host synchronisation inside the loop; the per-iteration losses stay on the device.
+Adam), replayed as a CUDA graph (dsr_dip_run), with no host synchronisation inside the loop; the per-iteration
+losses stay on the device.
 """
 from __future__ import annotations
 
@@ -83,7 +84,10 @@ def dip_sr_fused(net: SkipNet, LR_image: torch.Tensor, hr_size: Tuple[int, int],
     device = torch.device(device if not isinstance(device, int) else f'cuda:{device}')
     H, W = int(hr_size[0]), int(hr_size[1])
     num_iter = int(training_config['num_iter'])
-    with torch.cuda.device(device):
+    # a non-default stream: the legacy default stream cannot be captured into a CUDA graph
+    run_stream = torch.cuda.Stream(device=device)
+    run_stream.wait_stream(torch.cuda.current_stream(device))
+    with torch.cuda.device(device), torch.cuda.stream(run_stream):
         net.to(device)
         z_saved = (net_input if net_input is not None else get_noise(net.input_depth, 'noise', (H, W))).detach()
         z_saved = z_saved.to(device).contiguous()
@@ -109,10 +113,9 @@ def dip_sr_fused(net: SkipNet, LR_image: torch.Tensor, hr_size: Tuple[int, int],
                         g_lr.data_ptr(), g_hr.data_ptr(), losses.data_ptr())
         stream = _lib.stream_ptr()
         lr_rate, sigma = float(training_config['learning_rate']), float(training_config['reg_noise_std'])
-        for t in range(1, num_iter + 1):
-            b.loss_out = losses.data_ptr() + 4 * (t - 1)
-            check(lib.dsr_dip_step(plan.handle, tables.handle, C.byref(b), lr_rate, sigma, seed, t, stream),
-                  'dsr_dip_step')
+        # the whole loop in one call: iteration 1 runs eagerly, the rest replay one captured CUDA graph
+        check(lib.dsr_dip_run(plan.handle, tables.handle, C.byref(b), lr_rate, sigma, seed, 1, num_iter, stream),
+              'dsr_dip_run')
         net._nbt += num_iter
         # final resolved image: net(last perturbed input), BatchNorm still in train mode (DIP.py:102)
         check(lib.dsr_net_forward(plan.handle, flat.data_ptr(), z.data_ptr(), out_hr.data_ptr(),
@@ -120,4 +123,5 @@ def dip_sr_fused(net: SkipNet, LR_image: torch.Tensor, hr_size: Tuple[int, int],
         net._nbt += 1
         plan.forward_id += 1
         net._fused_keepalive = (m, v, z, z_saved, lr, out_lr, g_lr, g_hr, tables, ds)
+    torch.cuda.current_stream(device).wait_stream(run_stream)
     return (out_hr if keep_on_device else out_hr.cpu()), losses

@@ -109,6 +109,12 @@ typedef struct dsr_step_buffers {
 } dsr_step_buffers_t;
 int dsr_dip_step(dsr_plan_t* p, const dsr_downsampler_t* d, const dsr_step_buffers_t* b, float lr, float sigma,
                  unsigned long long seed, int t, void* stream);
+/* n_iters consecutive iterations t_first .. t_first + n_iters - 1 (the loop of utils/DIP.py:35-38).  Here
+ * b->loss_out is the BASE of a loss array: iteration t writes loss_out[t - 1].  The iteration counter and Adam's
+ * bias corrections live on the device, so one iteration is captured once as a CUDA graph (per set of buffers /
+ * hyper-parameters) and replayed: ~180 kernel launches per iteration become one cudaGraphLaunch. */
+int dsr_dip_run(dsr_plan_t* p, const dsr_downsampler_t* d, const dsr_step_buffers_t* b, float lr, float sigma,
+                unsigned long long seed, int t_first, int n_iters, void* stream);
 
 /* ---- introspection for tests / profiling --------------------------------------------------
  * Named intermediate of the last forward/backward (e.g. "L0.d1_raw"): device pointer, element
