@@ -7,7 +7,7 @@ A "step" is ONE Deep-Image-Prior iteration at 512x512, factor 4 (BASELINE.json c
 skip-net forward, Lanczos downsample, MSE, full backward, Adam -- the closure of DIP.py:47-95 plus
 utils/DIP.py:35-38.
 
-* value      device-resident: every iteration is one dsr_dip_step() call (dsr_b200.dip_sr_fused machinery), noise
+* value      device-resident: the K iterations are one dsr_dip_run() call = one CUDA-graph launch per iteration, noise
              drawn on the device, nothing crosses PCIe.  K steps timed with CUDA events between
              barrier + synchronize, max over ranks; N ranks each optimise their own image (weak scaling, no
              collective) and value = N*K / time.
@@ -15,8 +15,9 @@ utils/DIP.py:35-38.
              get_params, optimize and a closure written like DIP.py:47-95) with HOST buffers: the step's perturbed
              input z comes from pinned host memory (H2D inside the timed region, as DIP.py:57 does) and out_HR /
              out_LR / loss are read back every step (DIP.py:90-91).
-* roofline   the implicit-GEMM tcgen05 conv kernel (fprop + dgrad launches): algorithmic FLOPs / CUDA-event time
-             per launch, summed over a profiled pass, against MEASURED_PEAKS.json bf16 (sustained) peak.
+* roofline   the dominant kernel, conv_halo2_kernel (stride-1 3x3 / 1x1 fprop + dgrad = 60 % of the iteration's
+             FLOPs): algorithmic FLOPs / CUDA-event time per launch, summed over a profiled pass (all 5 levels, the
+             latency-bound 16x16..64x64 launches included), against MEASURED_PEAKS.json bf16 (sustained) peak.
 * cpu_baseline / --impl reference   the CPU restatement of the reference path (oracle/dip_oracle.py: the same
              torch CPU primitives the reference's nn.Modules call), all host threads, same workload.
 """
@@ -236,18 +237,21 @@ def run_ours(args, rank, local_rank, world):
         torch.cuda.synchronize()
         pk = peaks()
         res = {}
-        for cls, name in ((0, 'conv_gemm_kernel'), (1, 'wgrad_kernel')):
+        for cls, name in ((0, 'conv_halo2_kernel'), (1, 'wgrad_halo_kernel'), (2, 'conv_gemm_kernel')):
             msx, fl, n = C.c_double(), C.c_double(), C.c_int()
             check(lib.dsr_plan_profile_read(plan.handle, cls, C.byref(msx), C.byref(fl), C.byref(n)))
             res[name] = dict(ms_per_step=msx.value / nprof, tflops=(fl.value / (msx.value * 1e-3) / 1e12) if msx.value else 0.0,
                              launches_per_step=n.value // nprof, gflop_per_step=fl.value / nprof / 1e9)
         check(lib.dsr_plan_set_profile(plan.handle, 0))
-        a = res['conv_gemm_kernel']
-        roof = {'bound': 'tensor', 'kernel': 'conv_gemm_kernel (implicit-GEMM fprop + dgrad, tcgen05 kind::f16)',
+        a = res['conv_halo2_kernel']
+        roof = {'bound': 'tensor',
+                'kernel': 'conv_halo2_kernel (halo-tile implicit-GEMM, stride-1 3x3 / 1x1 fprop + dgrad, tcgen05 '
+                          'cta_group::2 kind::f16)',
                 'achieved': a['tflops'], 'peak': pk['tflops'], 'unit': 'TFLOP/s',
                 'frac': a['tflops'] / pk['tflops'] if pk['tflops'] else None, 'traffic': None, 'peak_source': pk['src'],
                 'kernel_ms_per_step': a['ms_per_step'], 'launches_per_step': a['launches_per_step'],
-                'wgrad_kernel': res['wgrad_kernel'],
+                'gflop_per_step': a['gflop_per_step'], 'wgrad_halo_kernel': res['wgrad_halo_kernel'],
+                'conv_gemm_kernel': res['conv_gemm_kernel'],
                 'step_tflops_all_convs': FLOPS_PER_ITER.get(size, 0) / (ms / args.steps * 1e-3) / 1e12}
 
     # ---- end to end through the public call surface with host buffers ----

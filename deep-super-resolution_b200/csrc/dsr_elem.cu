@@ -668,6 +668,208 @@ int launch_final_bwd(const float* gout, const float* out, const void* act_pad, c
 }
 
 // =============================================================================================
+// Top of the network (level 0 only), fused: BatchNorm + LeakyReLU of the last decoder conv + final 1x1 conv +
+// sigmoid in ONE pass over the raw conv output (the activation tensor is never materialised), and in the backward
+// pass sigmoid' + final-conv dgrad / wgrad + LeakyReLU' + BatchNorm statistics (pass 1) / apply (pass 2), again
+// straight from the raw tensor.  Saves ~470 MB of HBM traffic per 512x512 iteration.
+// The activation is rounded to fp16 exactly as the unfused path stored it, so both paths agree.
+// =============================================================================================
+__global__ void __launch_bounds__(kThreads, 3) bn_act_final_kernel(const __half* __restrict__ raw, BnRef bn,
+                                                                   const float* __restrict__ w,
+                                                                   const float* __restrict__ b,
+                                                                   float* __restrict__ out, int npix) {
+  const int lane = threadIdx.x & 31;
+  const int c0 = lane * 4;
+  float scale[4], shift[4], wr[3][4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float mean, rstd, ga, be;
+    bn_coeffs(bn, c0 + j, mean, rstd, ga, be);
+    scale[j] = ga * rstd;
+    shift[j] = be - mean * scale[j];
+#pragma unroll
+    for (int o = 0; o < 3; ++o) wr[o][j] = w[o * 128 + c0 + j];
+  }
+  const float b0 = b[0], b1 = b[1], b2 = b[2];
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int base = (((blockIdx.x * blockDim.x) + threadIdx.x) >> 5) * kPixUnroll; base < npix;
+       base += warps * kPixUnroll) {
+    uint2 v[kPixUnroll];
+#pragma unroll
+    for (int u = 0; u < kPixUnroll; ++u)
+      if (base + u < npix) v[u] = ldg8(raw + static_cast<long long>(base + u) * 128 + c0);
+    float acc[kPixUnroll][3];
+#pragma unroll
+    for (int u = 0; u < kPixUnroll; ++u) {
+      float f[4];
+      cvt4h(v[u], f);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) f[j] = lrelu(fmaf(f[j], scale[j], shift[j]));
+      float a[4];
+      cvt4h(pack4h(f), a);                 // the fp16-rounded activation
+#pragma unroll
+      for (int o = 0; o < 3; ++o) acc[u][o] = a[0] * wr[o][0] + a[1] * wr[o][1] + a[2] * wr[o][2] + a[3] * wr[o][3];
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1)
+#pragma unroll
+      for (int u = 0; u < kPixUnroll; ++u)
+#pragma unroll
+        for (int o = 0; o < 3; ++o) acc[u][o] += __shfl_xor_sync(0xffffffffu, acc[u][o], d);
+    if (lane < kPixUnroll * 3) {            // lane = u * 3 + o writes one output value
+      const int u = lane / 3, o = lane - u * 3;
+      if (base + u < npix) {
+        float val = 0.f;
+#pragma unroll
+        for (int uu = 0; uu < kPixUnroll; ++uu)
+#pragma unroll
+          for (int oo = 0; oo < 3; ++oo)
+            if (uu == u && oo == o) val = acc[uu][oo];
+        val += (o == 0) ? b0 : (o == 1) ? b1 : b2;
+        out[static_cast<long long>(o) * npix + base + u] = 1.f / (1.f + __expf(-val));
+      }
+    }
+  }
+}
+
+int launch_bn_act_final(const void* raw, BnRef bn, const float* w, const float* b, float* out, int H, int W,
+                        cudaStream_t s) {
+  bn_act_final_kernel<<<warp_grid(H, W, 148 * 8), kThreads, 0, s>>>(static_cast<const __half*>(raw), bn, w, b, out,
+                                                                   H * W);
+  DSR_LAUNCH_CHECK();
+}
+
+template <bool APPLY>
+__global__ void __launch_bounds__(kThreads, 2) bn_bwd_top_kernel(TopBwdArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int c0 = lane * 4;
+  const float S = a.gs[0], invS = a.gs[1];
+  float xa[4], xb[4], ga[4], be[4], c1[4], c2[4], k1[4], s1[4], s2[4], wr[3][4], aw[3][4], ab[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float mean, rstd;
+    bn_coeffs(a.bn, c0 + j, mean, rstd, ga[j], be[j]);
+    xa[j] = rstd;
+    xb[j] = -mean * rstd;
+    k1[j] = ga[j] * rstd;
+    c1[j] = APPLY ? a.bstats[c0 + j] * a.bn.inv_n : 0.f;
+    c2[j] = APPLY ? a.bstats[128 + c0 + j] * a.bn.inv_n : 0.f;
+    s1[j] = 0.f;
+    s2[j] = 0.f;
+#pragma unroll
+    for (int o = 0; o < 3; ++o) {
+      wr[o][j] = a.w[o * 128 + c0 + j];
+      aw[o][j] = 0.f;
+    }
+  }
+  const int W = a.W, npix = a.H * a.W, Wp = W + 2;
+  const __half* __restrict__ raw = static_cast<const __half*>(a.raw);
+  __half* __restrict__ dr = static_cast<__half*>(a.dr_pad);
+  __half2 amax2 = __float2half2_rn(0.f);
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int base = (((blockIdx.x * blockDim.x) + threadIdx.x) >> 5) * 32; base < npix; base += warps * 32) {
+    float dp[3] = {0.f, 0.f, 0.f};
+    if (base + lane < npix) {
+#pragma unroll
+      for (int o = 0; o < 3; ++o) {
+        const float ov = __ldg(a.out + static_cast<long long>(o) * npix + base + lane);
+        dp[o] = S * __ldg(a.gout + static_cast<long long>(o) * npix + base + lane) * ov * (1.f - ov);
+        if (!APPLY) ab[o] += dp[o];
+      }
+    }
+    const int cnt = min(32, npix - base);
+    const int y0 = base / W, x0 = base - y0 * W;
+    for (int j0 = 0; j0 < cnt; j0 += 4) {
+      uint2 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = ldg8(raw + static_cast<long long>(min(base + j0 + u, npix - 1)) * 128 + c0);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float d0 = __shfl_sync(0xffffffffu, dp[0], j0 + u);
+        const float d1 = __shfl_sync(0xffffffffu, dp[1], j0 + u);
+        const float d2 = __shfl_sync(0xffffffffu, dp[2], j0 + u);
+        if (j0 + u < cnt) {
+          float r[4], o4[4];
+          cvt4h(v[u], r);
+          float actf[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float xh = fmaf(r[j], xa[j], xb[j]);
+            const float yv = fmaf(ga[j], xh, be[j]);
+            const float da = d0 * wr[0][j] + d1 * wr[1][j] + d2 * wr[2][j];
+            const float dy = yv > 0.f ? da : kSlope * da;
+            actf[j] = lrelu(yv);
+            if (APPLY) {
+              o4[j] = k1[j] * (dy - c1[j] - xh * c2[j]);
+            } else {
+              s1[j] += dy;
+              s2[j] = fmaf(dy, xh, s2[j]);
+            }
+          }
+          if (APPLY) {
+            int y, x;
+            pix_advance(y0, x0, j0 + u, W, y, x);
+            const uint2 pk = pack4h(o4);
+            const __half2* h2 = reinterpret_cast<const __half2*>(&pk);
+            amax2 = __hmax2_nan(amax2, __hmax2_nan(__habs2(h2[0]), __habs2(h2[1])));
+            stg8(dr + (static_cast<long long>(y + 1) * Wp + (x + 1)) * 128 + c0, pk);
+          } else {
+            float ah[4];
+            cvt4h(pack4h(actf), ah);         // the fp16-rounded activation the forward pass used
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              aw[0][j] = fmaf(d0, ah[j], aw[0][j]);
+              aw[1][j] = fmaf(d1, ah[j], aw[1][j]);
+              aw[2][j] = fmaf(d2, ah[j], aw[2][j]);
+            }
+          }
+        }
+      }
+    }
+  }
+  if (!APPLY) {
+    __shared__ float red[256 + 3 * 128 + 3];
+    for (int i = threadIdx.x; i < 256 + 3 * 128 + 3; i += blockDim.x) red[i] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      atomicAdd(&red[c0 + j], s1[j]);
+      atomicAdd(&red[128 + c0 + j], s2[j]);
+#pragma unroll
+      for (int o = 0; o < 3; ++o) atomicAdd(&red[256 + o * 128 + c0 + j], aw[o][j]);
+    }
+#pragma unroll
+    for (int o = 0; o < 3; ++o) atomicAdd(&red[256 + 384 + o], ab[o]);
+    __syncthreads();
+    atomicAdd(&a.bstats[threadIdx.x], red[threadIdx.x]);
+    for (int i = threadIdx.x; i < 3 * 128; i += blockDim.x) atomicAdd(&a.dw[i], red[256 + i] * invS);
+    if (threadIdx.x < 3) atomicAdd(&a.db[threadIdx.x], red[256 + 384 + threadIdx.x] * invS);
+  } else {
+    const float amax = fmaxf(__low2float(amax2), __high2float(amax2));
+    track_amax(a.gs, isfinite(amax) ? amax : 0.f, !isfinite(amax));
+    if (blockIdx.x == 0 && threadIdx.x < 128) {
+      a.dbeta[threadIdx.x] = a.bstats[threadIdx.x] * invS;
+      a.dgamma[threadIdx.x] = a.bstats[128 + threadIdx.x] * invS;
+    }
+  }
+}
+
+int launch_bn_bwd_top_stats(const TopBwdArgs& a, cudaStream_t s) {
+  const long long npix = static_cast<long long>(a.H) * a.W;
+  long long blocks = (npix + 255) / 256;
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  bn_bwd_top_kernel<false><<<static_cast<int>(blocks), kThreads, 0, s>>>(a);
+  DSR_LAUNCH_CHECK();
+}
+int launch_bn_bwd_top_apply(const TopBwdArgs& a, cudaStream_t s) {
+  const long long npix = static_cast<long long>(a.H) * a.W;
+  long long blocks = (npix + 255) / 256;
+  if (blocks > 148 * 6) blocks = 148 * 6;
+  bn_bwd_top_kernel<true><<<static_cast<int>(blocks), kThreads, 0, s>>>(a);
+  DSR_LAUNCH_CHECK();
+}
+
+// =============================================================================================
 // BN + LeakyReLU backward (128 channels)
 // =============================================================================================
 template <bool APPLY, bool HAS_DS>

@@ -52,6 +52,25 @@ int launch_final_conv(const void* act_pad, const float* w, const float* b, float
 int launch_final_bwd(const float* gout, const float* out, const void* act_pad, const float* w, void* dact_pad,
                      float* dw, float* db, const float* gs, int H, int W, cudaStream_t s);
 
+// fused top of the network (level 0): see dsr_elem.cu
+int launch_bn_act_final(const void* raw, BnRef bn, const float* w, const float* b, float* out, int H, int W,
+                        cudaStream_t s);
+struct TopBwdArgs {
+  const float* gout;       // fp32 NCHW [3][H][W]: dL/d(out)
+  const float* out;        // fp32 NCHW: sigmoid output of the forward pass
+  const void* raw;         // fp16 plain [H][W][128]: BN input of the last decoder conv
+  BnRef bn;
+  const float* w;          // final conv weight [3][128]
+  float* bstats;           // [2][128]
+  void* dr_pad;            // fp16 padded [H+2][W+2][128]
+  float* dgamma; float* dbeta;       // BN parameter gradients
+  float* dw; float* db;              // final conv weight / bias gradients (accumulated)
+  float* gs;
+  int H, W;
+};
+int launch_bn_bwd_top_stats(const TopBwdArgs& a, cudaStream_t s);
+int launch_bn_bwd_top_apply(const TopBwdArgs& a, cudaStream_t s);
+
 struct BnBwdArgs {
   const void* g;           // fp16 gradient w.r.t. the activation, PADDED grid [H+2][W+2][gC]
   int gC;                  // channel pitch of g (128 or 144; first 128 channels are used)

@@ -160,8 +160,10 @@ struct dsr_plan {
   float graph_lr = 0.f, graph_sigma = 0.f;
   unsigned long long graph_seed = 0;
   int use_graph = 1;
+  int fuse_top = 1;              // level 0: BN/LeakyReLU of the last decoder conv fused with the final conv (fwd + bwd)
   bool bound = false, have_forward = false;
-  // optional per-launch timing of the tensor-core kernels (bench.py roofline): class 0 = conv_gemm, 1 = wgrad
+  // optional per-launch timing of the tensor-core kernels (bench.py roofline): class 0 = halo-tile conv (stride-1
+  // fprop + dgrad), 1 = wgrad, 2 = generic implicit-GEMM conv (stride-2 layers, 32-channel input)
   struct ProfRec { int cls; cudaEvent_t a, b; double flops; };
   std::vector<ProfRec> prof;
   int profile = 0;
@@ -702,13 +704,13 @@ struct ProfScope {
 };
 int run_fprop(dsr_plan* p, ConvLayer& c, cudaStream_t s) {
   if (p->debug_conv) return launch_conv_ref(c.fprop, c.ref_in, c.ref_wf, s);
-  ProfScope ps(p, 0, conv_flops(c), s);
+  ProfScope ps(p, (c.has_halo && p->use_halo) ? 0 : 2, conv_flops(c), s);
   if (c.has_halo && p->use_halo) return launch_conv_halo(c.hfprop, p->num_sms, s);
   return launch_conv_gemm(c.fprop, p->num_sms, s);
 }
 int run_dgrad(dsr_plan* p, ConvLayer& c, int i, cudaStream_t s) {
   if (p->debug_conv) return launch_conv_ref(c.dgrad[i], c.ref_dr, c.ref_wd, s);
-  ProfScope ps(p, 0, conv_flops(c) / c.ndgrad, s);
+  ProfScope ps(p, (c.has_halo && p->use_halo) ? 0 : 2, conv_flops(c) / c.ndgrad, s);
   if (c.has_halo && p->use_halo) return launch_conv_halo(c.hdgrad, p->num_sms, s);
   return launch_conv_gemm(c.dgrad[i], p->num_sms, s);
 }
@@ -758,6 +760,10 @@ int forward_level(dsr_plan* p, int i, const float* params, cudaStream_t s) {
   DSR_TRY(launch_upcat_stats(a, s));
   DSR_TRY(launch_upcat_apply(a, s));
   if ((rc = conv_bn_act(p, L.u1, params, s))) return rc;
+  if (i == 0 && p->fuse_top) {           // BN + LeakyReLU of u2 is fused with the final conv (dsr_net_forward)
+    DSR_TRY(run_fprop(p, L.u2, s));
+    return 0;
+  }
   if ((rc = conv_bn_act(p, L.u2, params, s))) return rc;
   return 0;
 }
@@ -804,7 +810,9 @@ int backward_level(dsr_plan* p, int i, const float* params, float* grads, cudaSt
   float* acc = reinterpret_cast<float*>(p->base);
   int rc;
   // ---- decoder ----
-  if ((rc = bn_backward(p, L.u2, params, grads, L.g_u2a.ptr, kNC, 0, nullptr, nullptr, s))) return rc;
+  if (!(i == 0 && p->fuse_top) &&        // level 0: done by the fused top kernels (dsr_net_backward)
+      (rc = bn_backward(p, L.u2, params, grads, L.g_u2a.ptr, kNC, 0, nullptr, nullptr, s)))
+    return rc;
   if ((rc = conv_backward(p, L.u2, s))) return rc;
   if ((rc = bn_backward(p, L.u1, params, grads, L.u2.gin.ptr, kNC, 0, nullptr, nullptr, s))) return rc;
   if ((rc = conv_backward(p, L.u1, s))) return rc;
@@ -1184,6 +1192,7 @@ int dsr_plan_bind(dsr_plan_t* p, void* workspace, size_t bytes, void* stream) {
   }
   p->use_side = getenv("DSR_NO_SIDE_STREAM") ? 0 : 1;
   p->use_graph = getenv("DSR_NO_GRAPH") ? 0 : 1;
+  p->fuse_top = getenv("DSR_NO_FUSE_TOP") ? 0 : 1;
   p->bound = true;
   p->have_forward = false;
   return 0;
@@ -1202,7 +1211,11 @@ int dsr_net_forward(dsr_plan_t* p, const float* params, const float* z, float* o
   DSR_TRY(launch_input_pack(z, L0.xin.ptr, L0.Cin, L0.H, L0.W, s));
   int rc = forward_level(p, 0, params, s);
   if (rc) return rc;
-  DSR_TRY(launch_final_conv(L0.u2.act.ptr, params + p->fin_w, params + p->fin_b, out, L0.H, L0.W, s));
+  if (p->fuse_top)
+    DSR_TRY(launch_bn_act_final(L0.u2.raw.ptr, conv_bn(p, L0.u2, params), params + p->fin_w, params + p->fin_b, out, L0.H,
+                                L0.W, s));
+  else
+    DSR_TRY(launch_final_conv(L0.u2.act.ptr, params + p->fin_w, params + p->fin_b, out, L0.H, L0.W, s));
   if (bn_buffers != nullptr)
     DSR_TRY(launch_bn_running(static_cast<const BnRunDesc*>(p->bnrun_table.ptr), static_cast<int>(p->bnrun_host.size()),
                               reinterpret_cast<const float*>(p->base), params, bn_buffers, kMomentum, s));
@@ -1222,8 +1235,28 @@ int dsr_net_backward(dsr_plan_t* p, const float* params, const float* out, const
   e = cudaMemsetAsync(grads, 0, static_cast<size_t>(p->nparam) * 4, s);
   if (e != cudaSuccess) return static_cast<int>(e);
   Level& L0 = p->lv[0];
-  DSR_TRY(launch_final_bwd(grad_out, out, L0.u2.act.ptr, params + p->fin_w, L0.g_u2a.ptr, grads + p->fin_w,
-                           grads + p->fin_b, static_cast<const float*>(p->gscale.ptr), L0.H, L0.W, s));
+  if (p->fuse_top) {
+    TopBwdArgs ta{};
+    ta.gout = grad_out;
+    ta.out = out;
+    ta.raw = L0.u2.raw.ptr;
+    ta.bn = conv_bn(p, L0.u2, params);
+    ta.w = params + p->fin_w;
+    ta.bstats = reinterpret_cast<float*>(p->base) + L0.u2.bstats_off;
+    ta.dr_pad = L0.u2.dr.ptr;
+    ta.dgamma = grads + L0.u2.g_off;
+    ta.dbeta = grads + L0.u2.be_off;
+    ta.dw = grads + p->fin_w;
+    ta.db = grads + p->fin_b;
+    ta.gs = static_cast<float*>(p->gscale.ptr);
+    ta.H = L0.H;
+    ta.W = L0.W;
+    DSR_TRY(launch_bn_bwd_top_stats(ta, s));
+    DSR_TRY(launch_bn_bwd_top_apply(ta, s));
+  } else {
+    DSR_TRY(launch_final_bwd(grad_out, out, L0.u2.act.ptr, params + p->fin_w, L0.g_u2a.ptr, grads + p->fin_w,
+                             grads + p->fin_b, static_cast<const float*>(p->gscale.ptr), L0.H, L0.W, s));
+  }
   if (p->side != nullptr && p->use_side) {     // the side stream must see the zeroed accumulators
     e = cudaEventRecord(p->ev_fork, s);
     if (e != cudaSuccess) return static_cast<int>(e);
