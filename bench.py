@@ -50,6 +50,24 @@ def peaks():
     return dict(tflops=1590.0, tflops_burst=1590.0, hbm=6650.0, src='fallback (B200_PROFILING.md)')
 
 
+def ncu_traffic():
+    """DRAM bytes (read + write) of the dominant kernel's largest launch (L0 decoder 3x3 fprop) from the committed
+    `ncu --set full` capture, profiles/r01_halo2_full_raw.csv; None if the file is missing."""
+    import csv
+    path = os.path.join(ROOT, 'profiles', 'r01_halo2_full_raw.csv')
+    try:
+        rows = list(csv.reader(open(path)))
+        hdr, units, row = rows[0], rows[1], rows[2]
+        tot = 0.0
+        for name in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
+            i = hdr.index(name)
+            scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}[units[i]]
+            tot += float(row[i]) * scale
+        return tot
+    except Exception:
+        return None
+
+
 def synthetic_pair(index, size):
     """HR / LR of image `index` (SURVEY.md 8d recipe).  The LR image is produced with the CUDA Lanczos downsampler
     so that bench.py does not depend on the oracle for its own arm."""
@@ -71,7 +89,7 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
         try:
             self.p = subprocess.Popen(['nvidia-smi', '-i', str(gpu_index), f'--query-gpu={self.QUERY}',
-                                       '--format=csv,noheader,nounits', '-lms', '100'], stdout=self.f,
+                                       '--format=csv,noheader,nounits', '-lms', '50'], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -248,7 +266,10 @@ def run_ours(args, rank, local_rank, world):
                 'kernel': 'conv_halo2_kernel (halo-tile implicit-GEMM, stride-1 3x3 / 1x1 fprop + dgrad, tcgen05 '
                           'cta_group::2 kind::f16)',
                 'achieved': a['tflops'], 'peak': pk['tflops'], 'unit': 'TFLOP/s',
-                'frac': a['tflops'] / pk['tflops'] if pk['tflops'] else None, 'traffic': None, 'peak_source': pk['src'],
+                'frac': a['tflops'] / pk['tflops'] if pk['tflops'] else None, 'traffic': ncu_traffic(),
+                'traffic_note': 'DRAM read+write bytes of the largest launch (L0 decoder 3x3 fprop, 79.7 GFLOP, '
+                                'algorithmic 76.1 MB in + 67.1 MB out) from profiles/r01_halo2_full_raw.csv',
+                'peak_source': pk['src'],
                 'kernel_ms_per_step': a['ms_per_step'], 'launches_per_step': a['launches_per_step'],
                 'gflop_per_step': a['gflop_per_step'], 'wgrad_halo_kernel': res['wgrad_halo_kernel'],
                 'conv_gemm_kernel': res['conv_gemm_kernel'],
@@ -359,7 +380,7 @@ def run_e2e(args, rank, world, dev, net, ds, lr_img, z_saved, barrier):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=30)
+    ap.add_argument('--steps', type=int, default=200)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--size', type=int, default=512)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])

@@ -343,17 +343,41 @@ __device__ __forceinline__ void up_eval(const UpRaw& r, float (&u)[2][2][4]) {
   }
 }
 
+// Per-launch constants of the 4 skip channels, computed once per block into shared memory (the per-pixel path of
+// lanes 0..3 then needs no global loads of statistics / rsqrt): BN(4) of the skip branch and BN(132)'s skip slots.
+struct SkipConst {
+  float xa[4], xb[4], ga[4], be[4];      // skip BN(4): xhat = r * xa + xb, y = ga * xhat + be
+  float cxa[4], cxb[4], ck1[4], cc1[4], cc2[4], csh[4];   // BN(132) skip channels: xhat = s * cxa + cxb; k1 = gamma * rstd;
+                                                          // c1, c2 = backward means; csh = beta - mean * k1
+};
+__device__ __forceinline__ void skip_const_init(SkipConst* sc, const UpcatArgs& a, const float* cbstats, bool have_cat) {
+  if (threadIdx.x < 4) {
+    const int o = threadIdx.x;
+    float mean, rstd, ga, be;
+    bn_coeffs(a.bn_skip, o, mean, rstd, ga, be);
+    sc->xa[o] = rstd; sc->xb[o] = -mean * rstd; sc->ga[o] = ga; sc->be[o] = be;
+    if (have_cat) {
+      const float inv_n = 1.f / (static_cast<float>(a.H) * static_cast<float>(a.W));
+      const float su = a.cat_stats[128 + o], sq = a.cat_stats[144 + 128 + o];
+      const float m4 = su * inv_n;
+      const float r4 = rsqrtf(fmaxf(sq * inv_n - m4 * m4, 0.f) + kBnEps);
+      const float g4 = a.cat_gamma[o], b4 = a.cat_beta[o];      // reference channels 0..3 are the skip channels
+      sc->cxa[o] = r4; sc->cxb[o] = -m4 * r4; sc->ck1[o] = g4 * r4; sc->csh[o] = b4 - m4 * g4 * r4;
+      sc->cc1[o] = cbstats ? cbstats[128 + o] * inv_n : 0.f;
+      sc->cc2[o] = cbstats ? cbstats[144 + 128 + o] * inv_n : 0.f;
+    }
+  }
+  __syncthreads();
+}
 // skip activation LeakyReLU(BN4(sraw)) at a pixel, plus xhat and y of the BN(4)
-__device__ __forceinline__ void skip_act4(const UpcatArgs& a, long long pix, float (&sv)[4], float (&xh)[4],
-                                          float (&yv)[4]) {
-  const float4 r = __ldg(reinterpret_cast<const float4*>(a.sraw + pix * 4));
+__device__ __forceinline__ void skip_act4(const SkipConst& sc, const float* __restrict__ sraw, long long pix,
+                                          float (&sv)[4], float (&xh)[4], float (&yv)[4]) {
+  const float4 r = __ldg(reinterpret_cast<const float4*>(sraw + pix * 4));
   const float rr[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
   for (int o = 0; o < 4; ++o) {
-    float mean, rstd, ga, be;
-    bn_coeffs(a.bn_skip, o, mean, rstd, ga, be);
-    xh[o] = (rr[o] - mean) * rstd;
-    yv[o] = ga * xh[o] + be;
+    xh[o] = fmaf(rr[o], sc.xa[o], sc.xb[o]);
+    yv[o] = fmaf(sc.ga[o], xh[o], sc.be[o]);
     sv[o] = lrelu(yv[o]);
   }
 }
@@ -361,6 +385,8 @@ __device__ __forceinline__ void skip_act4(const UpcatArgs& a, long long pix, flo
 constexpr int kUpUnroll = 2;     // 2x2 blocks in flight per warp
 
 __global__ void __launch_bounds__(kThreads, 3) upcat_stats_kernel(UpcatArgs a) {
+  __shared__ SkipConst sc;
+  skip_const_init(&sc, a, nullptr, false);
   const int lane = threadIdx.x & 31;
   float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0}, s4[4] = {0, 0, 0, 0}, q4[4] = {0, 0, 0, 0};
   const int nblk = (a.h + 1) * (a.w + 1);
@@ -392,7 +418,7 @@ __global__ void __launch_bounds__(kThreads, 3) upcat_stats_kernel(UpcatArgs a) {
         const int oy = t[u].oy0 + (lane >> 1), ox = t[u].ox0 + (lane & 1);
         if (oy >= 0 && ox >= 0 && oy < a.H && ox < a.W) {
           float sv[4], xh[4], yv[4];
-          skip_act4(a, static_cast<long long>(oy) * a.W + ox, sv, xh, yv);
+          skip_act4(sc, a.sraw, static_cast<long long>(oy) * a.W + ox, sv, xh, yv);
 #pragma unroll
           for (int o = 0; o < 4; ++o) { s4[o] += sv[o]; q4[o] = fmaf(sv[o], sv[o], q4[o]); }
         }
@@ -431,17 +457,16 @@ __device__ __forceinline__ void cat_coeffs(const UpcatArgs& a, int c, float& mea
 }
 
 __global__ void __launch_bounds__(kThreads, 3) upcat_apply_kernel(UpcatArgs a) {
+  __shared__ SkipConst sc;
+  skip_const_init(&sc, a, nullptr, true);
   const int lane = threadIdx.x & 31;
-  float scale[4], shift[4], sc4[4], sh4[4];
+  float scale[4], shift[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     float mean, rstd, ga, be;
     cat_coeffs(a, lane * 4 + j, mean, rstd, ga, be);
     scale[j] = ga * rstd;
     shift[j] = be - mean * scale[j];
-    cat_coeffs(a, 128 + j, mean, rstd, ga, be);
-    sc4[j] = ga * rstd;
-    sh4[j] = be - mean * sc4[j];
   }
   const int nblk = (a.h + 1) * (a.w + 1);
   const int Wp = a.W + 2;
@@ -467,9 +492,9 @@ __global__ void __launch_bounds__(kThreads, 3) upcat_apply_kernel(UpcatArgs a) {
         const int oy = t[u].oy0 + (lane >> 1), ox = t[u].ox0 + (lane & 1);
         if (oy >= 0 && ox >= 0 && oy < a.H && ox < a.W) {
           float sv[4], xh[4], yv[4], t0[4];
-          skip_act4(a, static_cast<long long>(oy) * a.W + ox, sv, xh, yv);
+          skip_act4(sc, a.sraw, static_cast<long long>(oy) * a.W + ox, sv, xh, yv);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) t0[k] = fmaf(sv[k], sc4[k], sh4[k]);
+          for (int k = 0; k < 4; ++k) t0[k] = fmaf(sv[k], sc.ck1[k], sc.csh[k]);
           mytail = pack4h(t0);
         }
       }
@@ -1033,6 +1058,8 @@ __device__ __forceinline__ void fold_gather4(const __half* gp, int C, int H, int
 template <bool APPLY>
 __global__ void __launch_bounds__(kThreads, 2) upcat_bwd_kernel(UpcatBwdArgs a) {
   const UpcatArgs& f = a.f;
+  __shared__ SkipConst sc;
+  skip_const_init(&sc, f, APPLY ? a.cbstats : nullptr, true);
   const int lane = threadIdx.x & 31;
   const int c0 = lane * 4;
   const float inv_n = 1.f / (static_cast<float>(f.H) * static_cast<float>(f.W));
@@ -1102,18 +1129,16 @@ __global__ void __launch_bounds__(kThreads, 2) upcat_bwd_kernel(UpcatBwdArgs a) 
         fold_gather4(gc, 144, f.H, f.W, y, x, 128,
                      ldg8(gc + (static_cast<long long>(y + 1) * Wp + (x + 1)) * 144 + 128), d4);
         float sv[4], xh4[4], yv[4];
-        skip_act4(f, pix, sv, xh4, yv);
+        skip_act4(sc, f.sraw, pix, sv, xh4, yv);
         float dsy[4];
 #pragma unroll
         for (int o = 0; o < 4; ++o) {
-          float mean4, rstd4, ga4, be4;
-          cat_coeffs(f, 128 + o, mean4, rstd4, ga4, be4);
-          const float xh = (sv[o] - mean4) * rstd4;
+          const float xh = fmaf(sv[o], sc.cxa[o], sc.cxb[o]);
           if (!APPLY) {
             t1[o] += d4[o];
             t2[o] = fmaf(d4[o], xh, t2[o]);
           } else {
-            const float ds = ga4 * rstd4 * (d4[o] - a.cbstats[128 + o] * inv_n - xh * a.cbstats[144 + 128 + o] * inv_n);
+            const float ds = sc.ck1[o] * (d4[o] - sc.cc1[o] - xh * sc.cc2[o]);
             dsy[o] = ds * (yv[o] > 0.f ? 1.f : kSlope);      // through the skip branch's LeakyReLU
             t1[o] += dsy[o];
             t2[o] = fmaf(dsy[o], xh4[o], t2[o]);

@@ -77,9 +77,11 @@ def DIP_ISR(net, LR_image, HR_image, scale_factor, training_config, train_log_fr
 
 def dip_sr_fused(net: SkipNet, LR_image: torch.Tensor, hr_size: Tuple[int, int], scale_factor: int,
                  training_config: Dict, device, seed: int = 0, net_input: Optional[torch.Tensor] = None,
-                 keep_on_device: bool = True):
+                 keep_on_device: bool = True, callback=None, callback_from: int = 1):
     """One image, `num_iter` fused iterations.  Returns (resolved image [1,3,H,W], losses [num_iter]
-    device tensor).  `training_config`: 'learning_rate', 'num_iter', 'reg_noise_std' as in DIP.py:316-324."""
+    device tensor).  `training_config`: 'learning_rate', 'num_iter', 'reg_noise_std' as in DIP.py:316-324.
+    `callback(t, out_hr)` (optional) is called after iterations t >= callback_from with the network output of that
+    iteration (the tensor is overwritten by the next iteration), e.g. to log PSNR as DIP.py:71-87 does."""
     _lib.require_cuda()
     device = torch.device(device if not isinstance(device, int) else f'cuda:{device}')
     H, W = int(hr_size[0]), int(hr_size[1])
@@ -114,8 +116,13 @@ def dip_sr_fused(net: SkipNet, LR_image: torch.Tensor, hr_size: Tuple[int, int],
         stream = _lib.stream_ptr()
         lr_rate, sigma = float(training_config['learning_rate']), float(training_config['reg_noise_std'])
         # the whole loop in one call: iteration 1 runs eagerly, the rest replay one captured CUDA graph
-        check(lib.dsr_dip_run(plan.handle, tables.handle, C.byref(b), lr_rate, sigma, seed, 1, num_iter, stream),
+        n_bulk = num_iter if callback is None else max(0, min(num_iter, int(callback_from) - 1))
+        check(lib.dsr_dip_run(plan.handle, tables.handle, C.byref(b), lr_rate, sigma, seed, 1, n_bulk, stream),
               'dsr_dip_run')
+        for t in range(n_bulk + 1, num_iter + 1):
+            check(lib.dsr_dip_run(plan.handle, tables.handle, C.byref(b), lr_rate, sigma, seed, t, 1, stream),
+                  'dsr_dip_run')
+            callback(t, out_hr)
         net._nbt += num_iter
         # final resolved image: net(last perturbed input), BatchNorm still in train mode (DIP.py:102)
         check(lib.dsr_net_forward(plan.handle, flat.data_ptr(), z.data_ptr(), out_hr.data_ptr(),

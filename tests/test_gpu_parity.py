@@ -297,3 +297,40 @@ def test_whole_step_tensor_core_vs_checker_256():
     out2.backward(gout)
     assert rel(o_tc, out2) < 5e-3
     assert cosine(g_tc, net.flat_buffers()[1]) > 0.98       # same run-to-run bound as above
+
+
+def test_long_run_psnr_matches_reference(golden):
+    """North-star gate: mean final PSNR within 0.1 dB of the reference -- evaluated, as SURVEY.md 7.2.2 prescribes,
+    on the MEAN over a batch of images (a single DIP run moves by ~0.1 dB under a 1e-7 weight perturbation).
+    Reference curves: oracle/make_golden_psnr.py (the unmodified reference on CPU, 8 images, 128x128, 400 iterations).
+    Ours: dsr_b200.dip_sr_fused (device noise stream, fp16 operands).  The tolerance is 0.1 dB plus the standard error
+    implied by the reference's own seed-to-seed spread on one image."""
+    import dsr_b200
+    from oracle import dip_oracle as O
+    g = golden('psnr_128.pt')
+    size, iters = g['size'], g['iters']
+    cfg = {'learning_rate': g['lr'], 'num_iter': iters, 'reg_noise_std': g['reg_noise_std']}
+    runs = [r for r in g['runs'] if r['image'] == r['seed']]
+    ours = []
+    for r in runs:
+        lr_img, hr = O.synthetic_pair(r['image'], size)
+        hr_c = hr.unsqueeze(0).cuda()
+        torch.manual_seed(r['seed'])
+        net = dsr_b200.get_net(32, 'skip', 'reflection', skip_n33d=128, skip_n33u=128, skip_n11=4, num_scales=5,
+                               upsample_mode='bilinear')
+        acc = []
+
+        def cb(t, out_hr):
+            acc.append(10.0 * torch.log10(1.0 / ((out_hr - hr_c) ** 2).mean()))
+
+        dsr_b200.dip_sr_fused(net, lr_img, (size, size), g['factor'], cfg, 'cuda:0', seed=100 + r['image'],
+                              callback=cb, callback_from=iters - 49)
+        ours.append(float(torch.stack(acc).mean()))
+    mean_ours = sum(ours) / len(ours)
+    mean_ref = sum(r['psnr_last50'] for r in runs) / len(runs)
+    spread = g['seed_spread_image0']
+    tol = 0.1 + 2.0 * spread / math.sqrt(len(runs))
+    print(f'PSNR mean ours {mean_ours:.3f} dB, reference {mean_ref:.3f} dB, reference seed spread {spread:.3f} dB, '
+          f'tolerance {tol:.3f} dB; per image ours {[round(v, 2) for v in ours]} '
+          f'ref {[round(r["psnr_last50"], 2) for r in runs]}')
+    assert abs(mean_ours - mean_ref) < tol
