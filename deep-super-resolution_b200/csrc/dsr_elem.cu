@@ -1020,14 +1020,137 @@ __global__ void __launch_bounds__(kThreads, HAS_DS ? 2 : 3) bn_bwd_kernel(BnBwdA
   }
 }
 
+// Lean variant for the common case (no skip-branch term, W a multiple of 4): a warp walks groups of 4 consecutive
+// pixels of one row (one integer division per group, pointer offsets inside it) and the per-channel arithmetic is
+// folded to the minimum:
+//     y  = k1 r + sh                 (sign only: LeakyReLU mask)          k1 = gamma rstd, sh = beta - mean k1
+//     dy = y > 0 ? g : 0.2 g
+//     stats: S1 += dy, S2r += dy r   (sum dy xhat = rstd (S2r - mean S1), applied when the block sums are flushed)
+//     apply: dr = k1 dy + (A + B r)  with B = -k1 c2 rstd, A = -k1 (c1 - c2 mean rstd)
+// Groups that touch the folded border (3x3 dgrad inputs) take the per-pixel path with halo gathering.
+template <bool APPLY>
+__global__ void __launch_bounds__(kThreads, 3) bn_bwd_fast_kernel(BnBwdArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int c0 = lane * 4;
+  float k1[4], sh[4], A[4], B[4], s1[4], s2[4], mean_[4], rstd_[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float mean, rstd, ga, be;
+    bn_coeffs(a.bn, c0 + j, mean, rstd, ga, be);
+    k1[j] = ga * rstd;
+    sh[j] = be - mean * k1[j];
+    mean_[j] = mean;
+    rstd_[j] = rstd;
+    if (APPLY) {
+      const float c1 = a.bstats[c0 + j] * a.bn.inv_n, c2 = a.bstats[128 + c0 + j] * a.bn.inv_n;
+      B[j] = -k1[j] * c2 * rstd;
+      A[j] = -k1[j] * (c1 - c2 * mean * rstd);
+    }
+    s1[j] = 0.f;
+    s2[j] = 0.f;
+  }
+  const int H = a.H, W = a.W, Wp = W + 2, gpr = W >> 2, ngroups = H * gpr;
+  const int gC = a.gC;
+  const __half* __restrict__ gp = static_cast<const __half*>(a.g);
+  const __half* __restrict__ raw = static_cast<const __half*>(a.raw);
+  __half* __restrict__ dr = static_cast<__half*>(a.dr_pad);
+  __half2 amax2 = __float2half2_rn(0.f);
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int grp = ((blockIdx.x * blockDim.x) + threadIdx.x) >> 5; grp < ngroups; grp += warps) {
+    const int y = grp / gpr, x = (grp - y * gpr) << 2;
+    const __half* gsrc = gp + (static_cast<long long>(y + 1) * Wp + (x + 1)) * gC + c0;
+    const __half* rsrc = raw + (static_cast<long long>(y) * W + x) * 128 + c0;
+    uint2 vg[4], vr[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      vg[u] = ldg8(gsrc + u * gC);
+      vr[u] = ldg8(rsrc + u * 128);
+    }
+    const bool border = a.fold && (y == 1 || y == H - 2 || x == 0 || x + 4 == W);
+    __half* dst = dr + (static_cast<long long>(y + 1) * Wp + (x + 1)) * 128 + c0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float da[4], r[4];
+      cvt4h(vg[u], da);
+      cvt4h(vr[u], r);
+      if (border) {                                        // warp-uniform: fold the halo copies back
+        const int xx = x + u;
+        if (xx == 1 || xx == W - 2 || y == 1 || y == H - 2) {
+          int ys[3], xs[3];
+          const int ny = halo_coords(y, H, ys), nx = halo_coords(xx, W, xs);
+          for (int ii = 0; ii < ny; ++ii)
+            for (int k = 0; k < nx; ++k)
+              if (ii | k) {
+                float f[4];
+                cvt4h(ldg8(gp + (static_cast<long long>(ys[ii]) * Wp + xs[k]) * gC + c0), f);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) da[j] += f[j];
+              }
+        }
+      }
+      float o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float yv = fmaf(k1[j], r[j], sh[j]);
+        const float dy = yv > 0.f ? da[j] : kSlope * da[j];
+        if (APPLY) {
+          o[j] = fmaf(k1[j], dy, fmaf(B[j], r[j], A[j]));
+        } else {
+          s1[j] += dy;
+          s2[j] = fmaf(dy, r[j], s2[j]);
+        }
+      }
+      if (APPLY) {
+        const uint2 pk = pack4h(o);
+        const __half2* h2 = reinterpret_cast<const __half2*>(&pk);
+        amax2 = __hmax2_nan(amax2, __hmax2_nan(__habs2(h2[0]), __habs2(h2[1])));
+        stg8(dst + u * 128, pk);
+      }
+    }
+  }
+  if (!APPLY) {
+    __shared__ float red[256];
+    red[threadIdx.x] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      atomicAdd(&red[c0 + j], s1[j]);
+      atomicAdd(&red[128 + c0 + j], rstd_[j] * (s2[j] - mean_[j] * s1[j]));     // sum dy * xhat
+    }
+    __syncthreads();
+    atomicAdd(&a.bstats[threadIdx.x], red[threadIdx.x]);
+  } else {
+    const float amax = fmaxf(__low2float(amax2), __high2float(amax2));
+    track_amax(a.gs, isfinite(amax) ? amax : 0.f, !isfinite(amax));
+    if (blockIdx.x == 0 && threadIdx.x < 128) {
+      a.dbeta[threadIdx.x] = a.bstats[threadIdx.x] * a.gs[1];
+      a.dgamma[threadIdx.x] = a.bstats[128 + threadIdx.x] * a.gs[1];
+    }
+  }
+}
+
+static int fast_grid(int H, int W, int cap) {
+  long long b = (static_cast<long long>(H) * (W >> 2) + 7) / 8;
+  if (b > cap) b = cap;
+  return static_cast<int>(b < 1 ? 1 : b);
+}
+
 int launch_bn_bwd_stats(const BnBwdArgs& a, cudaStream_t s) {
   const int grid = warp_grid(a.H, a.W, 148 * 4);
+  if (a.ds == nullptr && (a.W & 3) == 0 && a.W >= 4) {
+    bn_bwd_fast_kernel<false><<<fast_grid(a.H, a.W, 148 * 8), kThreads, 0, s>>>(a);
+    DSR_LAUNCH_CHECK();
+  }
   if (a.ds != nullptr) bn_bwd_kernel<false, true><<<grid, kThreads, 0, s>>>(a);
   else bn_bwd_kernel<false, false><<<grid, kThreads, 0, s>>>(a);
   DSR_LAUNCH_CHECK();
 }
 int launch_bn_bwd_apply(const BnBwdArgs& a, cudaStream_t s) {
   const int grid = warp_grid(a.H, a.W, 148 * 8);
+  if (a.ds == nullptr && (a.W & 3) == 0 && a.W >= 4) {
+    bn_bwd_fast_kernel<true><<<fast_grid(a.H, a.W, 148 * 16), kThreads, 0, s>>>(a);
+    DSR_LAUNCH_CHECK();
+  }
   if (a.ds != nullptr) bn_bwd_kernel<true, true><<<grid, kThreads, 0, s>>>(a);
   else bn_bwd_kernel<true, false><<<grid, kThreads, 0, s>>>(a);
   DSR_LAUNCH_CHECK();

@@ -160,12 +160,19 @@ struct dsr_plan {
   float graph_lr = 0.f, graph_sigma = 0.f;
   unsigned long long graph_seed = 0;
   int use_graph = 1;
+  // small cache of captured forward / backward passes for the separate-call path (closure protocol): key = the
+  // pointer arguments; an entry is captured on its SECOND use (the first run is eager and sets function attributes)
+  struct PassGraph { int kind; const void* a0; const void* a1; const void* a2; const void* a3; int uses; cudaGraphExec_t exec; };
+  std::vector<PassGraph> pass_graphs;
+  int in_step = 0;               // inside enqueue_step (whole-iteration graph): no nested pass graphs
   int fuse_top = 1;              // level 0: BN/LeakyReLU of the last decoder conv fused with the final conv (fwd + bwd)
   bool bound = false, have_forward = false;
   // optional per-launch timing of the tensor-core kernels (bench.py roofline): class 0 = halo-tile conv (stride-1
   // fprop + dgrad), 1 = wgrad, 2 = generic implicit-GEMM conv (stride-2 layers, 32-channel input)
   struct ProfRec { int cls; cudaEvent_t a, b; double flops; };
   std::vector<ProfRec> prof;
+  struct AllRec { const char* what; cudaEvent_t a, b; };
+  std::vector<AllRec> allprof;
   int profile = 0;
 };
 
@@ -673,11 +680,23 @@ BnRef skip_bn(const dsr_plan* p, const Level& L, const float* params) {
   return b;
 }
 
-#define DSR_TRY(expr)                    \
-  do {                                   \
-    int rc__ = (expr);                   \
-    ++p->launches;                       \
-    if (rc__ != 0) return rc__;          \
+// With profile == 2 every launch is bracketed by CUDA events on the main stream and accumulated per call-site
+// name (tools/step_table.py): warm, in-order timings of ALL kernels, unlike ncu's cold serialised replays.
+#define DSR_TRY(expr)                                                          \
+  do {                                                                         \
+    cudaEvent_t ea__ = nullptr, eb__ = nullptr;                                \
+    if (p->profile == 2) {                                                     \
+      cudaEventCreate(&ea__);                                                  \
+      cudaEventCreate(&eb__);                                                  \
+      cudaEventRecord(ea__, s);                                                \
+    }                                                                          \
+    int rc__ = (expr);                                                         \
+    ++p->launches;                                                             \
+    if (p->profile == 2) {                                                     \
+      cudaEventRecord(eb__, s);                                                \
+      p->allprof.push_back(dsr_plan::AllRec{#expr, ea__, eb__});               \
+    }                                                                          \
+    if (rc__ != 0) return rc__;                                                \
   } while (0)
 
 // Algorithmic FLOPs of one conv pass (fprop, dgrad or wgrad): 2 * M * N * K with the true channel count.
@@ -791,7 +810,7 @@ int bn_backward(dsr_plan* p, ConvLayer& c, const float* params, float* grads, co
 }
 
 int conv_backward(dsr_plan* p, ConvLayer& c, cudaStream_t s) {
-  if (p->side != nullptr && p->use_side) {
+  if (p->side != nullptr && p->use_side && p->profile != 2) {
     cudaError_t e = cudaEventRecord(p->ev_fork, s);              // dR of this layer is complete on the main stream
     if (e != cudaSuccess) return static_cast<int>(e);
     e = cudaStreamWaitEvent(p->side, p->ev_fork, 0);
@@ -1115,6 +1134,7 @@ int dsr_plan_create(dsr_plan_t** out, int H, int W, int input_depth, int num_sca
 void dsr_plan_destroy(dsr_plan_t* p) {
   if (p) dsr_plan_set_profile(p, 0);
   if (p && p->graph_exec) cudaGraphExecDestroy(p->graph_exec);
+  if (p) for (auto& g : p->pass_graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
   if (p && p->side) {
     cudaStreamSynchronize(p->side);
     cudaEventDestroy(p->ev_fork);
@@ -1198,9 +1218,8 @@ int dsr_plan_bind(dsr_plan_t* p, void* workspace, size_t bytes, void* stream) {
   return 0;
 }
 
-int dsr_net_forward(dsr_plan_t* p, const float* params, const float* z, float* out, float* bn_buffers, void* stream) {
-  if (!p || !params || !z || !out) return -1;
-  if (!p->bound) return -6;
+static int net_forward_impl(dsr_plan_t* p, const float* params, const float* z, float* out, float* bn_buffers,
+                            void* stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   p->launches = 0;
   cudaError_t e = cudaMemsetAsync(p->base + p->acc_fwd_off, 0, p->acc_fwd_floats * 4, s);
@@ -1223,11 +1242,8 @@ int dsr_net_forward(dsr_plan_t* p, const float* params, const float* z, float* o
   return 0;
 }
 
-int dsr_net_backward(dsr_plan_t* p, const float* params, const float* out, const float* grad_out, float* grads,
-                     void* stream) {
-  if (!p || !params || !out || !grad_out || !grads) return -1;
-  if (!p->bound) return -6;
-  if (!p->have_forward) return -7;
+static int net_backward_impl(dsr_plan_t* p, const float* params, const float* out, const float* grad_out, float* grads,
+                             void* stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   p->launches = 0;
   cudaError_t e = cudaMemsetAsync(p->base + p->acc_bwd_off, 0, p->acc_bwd_floats * 4, s);
@@ -1257,7 +1273,7 @@ int dsr_net_backward(dsr_plan_t* p, const float* params, const float* out, const
     DSR_TRY(launch_final_bwd(grad_out, out, L0.u2.act.ptr, params + p->fin_w, L0.g_u2a.ptr, grads + p->fin_w,
                              grads + p->fin_b, static_cast<const float*>(p->gscale.ptr), L0.H, L0.W, s));
   }
-  if (p->side != nullptr && p->use_side) {     // the side stream must see the zeroed accumulators
+  if (p->side != nullptr && p->use_side && p->profile != 2) {     // the side stream must see the zeroed accumulators
     e = cudaEventRecord(p->ev_fork, s);
     if (e != cudaSuccess) return static_cast<int>(e);
     e = cudaStreamWaitEvent(p->side, p->ev_fork, 0);
@@ -1265,7 +1281,7 @@ int dsr_net_backward(dsr_plan_t* p, const float* params, const float* out, const
   }
   int rc = backward_level(p, 0, params, grads, s);
   if (rc) return rc;
-  if (p->side != nullptr && p->use_side) {
+  if (p->side != nullptr && p->use_side && p->profile != 2) {
     e = cudaEventRecord(p->ev_join, p->side);
     if (e != cudaSuccess) return static_cast<int>(e);
     e = cudaStreamWaitEvent(s, p->ev_join, 0);
@@ -1277,6 +1293,62 @@ int dsr_net_backward(dsr_plan_t* p, const float* params, const float* out, const
   DSR_TRY(launch_grad_scale_finish(grads, p->nparam, static_cast<float*>(p->gscale.ptr), s));
   ++p->launches;
   return 0;
+}
+
+// Runs `fn` eagerly, or -- on a capturable stream, from the second call with the same pointer arguments on --
+// replays a CUDA graph of it.
+extern "C++" {
+template <class Fn>
+static int run_pass_cached(dsr_plan_t* p, int kind, const void* a0, const void* a1, const void* a2, const void* a3,
+                           cudaStream_t s, Fn fn) {
+  const bool capturable = (s != nullptr && s != cudaStreamLegacy && s != cudaStreamPerThread);
+  if (!p->use_graph || p->profile || p->debug_conv || !capturable) return fn();
+  dsr_plan::PassGraph* hit = nullptr;
+  for (auto& g : p->pass_graphs)
+    if (g.kind == kind && g.a0 == a0 && g.a1 == a1 && g.a2 == a2 && g.a3 == a3) { hit = &g; break; }
+  if (hit == nullptr) {
+    if (p->pass_graphs.size() >= 8) {                    // bounded: drop the oldest entry
+      if (p->pass_graphs.front().exec) cudaGraphExecDestroy(p->pass_graphs.front().exec);
+      p->pass_graphs.erase(p->pass_graphs.begin());
+    }
+    p->pass_graphs.push_back(dsr_plan::PassGraph{kind, a0, a1, a2, a3, 1, nullptr});
+    return fn();
+  }
+  if (hit->exec == nullptr) {
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    const int rc = fn();
+    e = cudaStreamEndCapture(s, &graph);
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (e != cudaSuccess) return static_cast<int>(e);
+    e = cudaGraphInstantiate(&hit->exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) { hit->exec = nullptr; return static_cast<int>(e); }
+  }
+  ++hit->uses;
+  return static_cast<int>(cudaGraphLaunch(hit->exec, s));
+}
+}  // extern "C++"
+
+int dsr_net_forward(dsr_plan_t* p, const float* params, const float* z, float* out, float* bn_buffers, void* stream) {
+  if (!p || !params || !z || !out) return -1;
+  if (!p->bound) return -6;
+  if (p->in_step) return net_forward_impl(p, params, z, out, bn_buffers, stream);
+  const int rc = run_pass_cached(p, 0, params, z, out, bn_buffers, static_cast<cudaStream_t>(stream),
+                                 [&]() { return net_forward_impl(p, params, z, out, bn_buffers, stream); });
+  if (rc == 0) p->have_forward = true;
+  return rc;
+}
+
+int dsr_net_backward(dsr_plan_t* p, const float* params, const float* out, const float* grad_out, float* grads,
+                     void* stream) {
+  if (!p || !params || !out || !grad_out || !grads) return -1;
+  if (!p->bound) return -6;
+  if (!p->have_forward) return -7;
+  if (p->in_step) return net_backward_impl(p, params, out, grad_out, grads, stream);
+  return run_pass_cached(p, 1, params, out, grad_out, grads, static_cast<cudaStream_t>(stream),
+                         [&]() { return net_backward_impl(p, params, out, grad_out, grads, stream); });
 }
 
 int dsr_adam_step(float* pp, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
@@ -1303,14 +1375,21 @@ static int enqueue_step(dsr_plan_t* p, const dsr_downsampler_t* d, const dsr_ste
   if (rc) return rc;
   if ((rc = launch_perturb(b->z_saved, b->z, nz, sigma, seed, 0, s, st))) return rc;
   total += 2;
-  if ((rc = dsr_net_forward(p, b->params, b->z, b->out_hr, b->bn_buffers, stream))) return rc;
+  p->in_step = 1;
+  rc = dsr_net_forward(p, b->params, b->z, b->out_hr, b->bn_buffers, stream);
+  p->in_step = 0;
+  if (rc) return rc;
+  p->have_forward = true;
   total += p->launches;
   if ((rc = launch_downsample_mse(b->out_hr, b->lr_image, b->out_lr, b->g_out_lr, losses, p->n_out, d->H, d->W, d->oh,
                                   d->ow, d->t, s, st)))
     return rc;
   if ((rc = launch_downsample_bwd(b->g_out_lr, b->g_out_hr, p->n_out, d->H, d->W, d->oh, d->ow, d->t, s))) return rc;
   total += 2;
-  if ((rc = dsr_net_backward(p, b->params, b->out_hr, b->g_out_hr, b->grads, stream))) return rc;
+  p->in_step = 1;
+  rc = dsr_net_backward(p, b->params, b->out_hr, b->g_out_hr, b->grads, stream);
+  p->in_step = 0;
+  if (rc) return rc;
   total += p->launches;
   if ((rc = launch_adam(b->params, b->grads, b->adam_m, b->adam_v, p->nparam, lr, 0.9f, 0.999f, 1e-8f, 1, s, st)))
     return rc;
@@ -1445,8 +1524,29 @@ int dsr_plan_set_profile(dsr_plan_t* p, int on) {
   if (!p) return -1;
   for (auto& r : p->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   p->prof.clear();
-  p->profile = on ? 1 : 0;
+  for (auto& r : p->allprof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  p->allprof.clear();
+  p->profile = (on == 2) ? 2 : (on ? 1 : 0);
   return 0;
+}
+// profile mode 2: writes "<microseconds>\t<call site>" lines for every launch recorded since set_profile(2)
+int dsr_plan_profile_dump(dsr_plan_t* p, char* buf, size_t cap) {
+  if (!p || !buf || cap == 0) return -1;
+  size_t off = 0;
+  buf[0] = 0;
+  for (auto& r : p->allprof) {
+    if (cudaEventSynchronize(r.b) != cudaSuccess) return -1;
+    float t = 0.f;
+    cudaEventElapsedTime(&t, r.a, r.b);
+    char name[48];
+    size_t n = 0;
+    for (const char* c = r.what; *c && *c != '(' && n < sizeof(name) - 1; ++c) name[n++] = *c;
+    name[n] = 0;
+    const int w = snprintf(buf + off, cap - off, "%.2f\t%s\n", t * 1e3f, name);
+    if (w < 0 || static_cast<size_t>(w) >= cap - off) break;
+    off += static_cast<size_t>(w);
+  }
+  return static_cast<int>(off);
 }
 int dsr_plan_profile_read(dsr_plan_t* p, int cls, double* ms_total, double* flops_total, int* launches) {
   if (!p) return -1;

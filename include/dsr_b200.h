@@ -136,6 +136,9 @@ int dsr_plan_debug_replay(dsr_plan_t* p, const char* layer, int what, int use_ch
  * (2*M*N*K per pass, true channel counts) and the number of launches recorded since; it synchronises on them. */
 int dsr_plan_set_profile(dsr_plan_t* p, int on);
 int dsr_plan_profile_read(dsr_plan_t* p, int cls, double* ms_total, double* flops_total, int* launches);
+/* set_profile(p, 2): every launch of forward / backward is bracketed by events on the main stream (side stream and
+ * graph replay off); profile_dump writes one "<microseconds>\t<call site>" line per launch into buf, returns bytes. */
+int dsr_plan_profile_dump(dsr_plan_t* p, char* buf, size_t cap);
 /* Device error word written by a kernel whose mbarrier wait timed out (0 = none). */
 int dsr_plan_device_error(dsr_plan_t* p, int* host_code);
 /* Device-to-device copy on `stream` (lets ctypes callers read an introspected tensor into their own buffer). */
