@@ -1538,7 +1538,7 @@ __global__ void grad_scale_update_kernel(float* __restrict__ gs) {
   if (bad) S *= (1.f / 256.f);
   else if (amax > 16384.f) S *= (1.f / 16.f);
   else if (amax < 512.f) S *= 8.f;
-  S = fminf(fmaxf(S, 1.f), 1073741824.f);
+  S = fminf(fmaxf(S, 1.f), 1.1529215e18f);      // [1, 2^60]
   gs[0] = S;
   gs[1] = 1.f / S;
   gs[2] = 0.f;
