@@ -260,6 +260,11 @@ def run_ours(args, rank, local_rank, world):
             check(lib.dsr_plan_profile_read(plan.handle, cls, C.byref(msx), C.byref(fl), C.byref(n)))
             res[name] = dict(ms_per_step=msx.value / nprof, tflops=(fl.value / (msx.value * 1e-3) / 1e12) if msx.value else 0.0,
                              launches_per_step=n.value // nprof, gflop_per_step=fl.value / nprof / 1e9)
+        tms, tfl = C.c_double(), C.c_double()
+        check(lib.dsr_plan_profile_top(plan.handle, 0, C.byref(tms), C.byref(tfl)))
+        top = {'gflop': tfl.value / 1e9, 'us': tms.value * 1e3,
+               'tflops': (tfl.value / (tms.value * 1e-3) / 1e12) if tms.value else 0.0}
+        top['frac'] = top['tflops'] / pk['tflops'] if pk['tflops'] else None
         check(lib.dsr_plan_set_profile(plan.handle, 0))
         a = res['conv_halo2_kernel']
         roof = {'bound': 'tensor',
@@ -271,9 +276,15 @@ def run_ours(args, rank, local_rank, world):
                                 'algorithmic 76.1 MB in + 67.1 MB out) from profiles/r01_halo2_full_raw.csv',
                 'peak_source': pk['src'],
                 'kernel_ms_per_step': a['ms_per_step'], 'launches_per_step': a['launches_per_step'],
-                'gflop_per_step': a['gflop_per_step'], 'wgrad_halo_kernel': res['wgrad_halo_kernel'],
+                'gflop_per_step': a['gflop_per_step'], 'largest_launch': top, 'wgrad_halo_kernel': res['wgrad_halo_kernel'],
                 'conv_gemm_kernel': res['conv_gemm_kernel'],
                 'step_tflops_all_convs': FLOPS_PER_ITER.get(size, 0) / (ms / args.steps * 1e-3) / 1e12}
+
+    # ---- configs[2] flavour: two independent images in flight on this GPU (separate nets / plans / streams):
+    #      the latency-bound low-resolution levels of one image overlap the tensor-bound levels of the other ----
+    conc = None
+    if args.concurrent > 1 and rank == 0:
+        conc = run_concurrent(args, dev, args.concurrent)
 
     # ---- end to end through the public call surface with host buffers ----
     e2e = None
@@ -293,7 +304,7 @@ def run_ours(args, rank, local_rank, world):
                    'size': size, 'factor': FACTOR, 'noise': 'device Philox (value) / pinned host buffer (e2e)',
                    'l2': 'working set per iteration ~1 GB >> 126 MB L2: no flush needed'},
         'roofline': roof, 'e2e': e2e, 'gpu_launches': launches_per_step * args.steps, 'clocks': clocks,
-        'loss_first_last': [loss_first, loss_last],
+        'loss_first_last': [loss_first, loss_last], 'concurrent_images': conc,
         'conv_tflops_per_gpu': FLOPS_PER_ITER.get(size, 0) * (args.steps / (ms * 1e-3)) / 1e12,
     }
     if world == 1 and not args.no_cpu:
@@ -302,6 +313,58 @@ def run_ours(args, rank, local_rank, world):
                                 'sample': f'{n} full iterations at {size}^2 after 1 warm-up (median), '
                                           'oracle/dip_oracle.py on torch CPU'}
     print(json.dumps(line), flush=True)
+
+
+def run_concurrent(args, dev, n_img):
+    """n_img independent images optimised concurrently on one GPU (each with its own net, plan and stream), as the
+    64-image configuration (BASELINE configs[2]) would be scheduled.  Returns aggregate iterations / s."""
+    import ctypes as C
+    import dsr_b200
+    from dsr_b200._lib import lib, check, StepBuffers
+    size = args.size
+    jobs = []
+    for i in range(n_img):
+        st = torch.cuda.Stream(device=dev)
+        with torch.cuda.stream(st):
+            hr = synthetic_pair(100 + i, size)
+            ds = dsr_b200.Downsampler(3, FACTOR, 'lanczos2', phase=0.5, preserve_size=True)
+            lr_img = ds(hr.unsqueeze(0).to(dev))[0].contiguous()
+            torch.manual_seed(100 + i)
+            net = dsr_b200.get_net(32, 'skip', 'reflection', skip_n33d=128, skip_n33u=128, skip_n11=4, num_scales=5,
+                                   upsample_mode='bilinear').to(dev)
+            z_saved = dsr_b200.get_noise(32, 'noise', (size, size)).to(dev).contiguous()
+            z = z_saved.clone()
+            net(z)
+            net.zero_grad()
+            plan = net._plans[(size, size)]
+            tables = ds._tables_for(size, size, dev)
+            oh, ow = ds.out_size(size, size)
+            flat, gflat = net.flat_buffers()
+            f32 = dict(dtype=torch.float32, device=dev)
+            bufs = dict(m=torch.zeros_like(flat), v=torch.zeros_like(flat), out_hr=torch.empty((1, 3, size, size), **f32),
+                        out_lr=torch.empty((3, oh, ow), **f32), g_lr=torch.empty((3, oh, ow), **f32),
+                        g_hr=torch.empty((1, 3, size, size), **f32),
+                        losses=torch.zeros(args.warmup + args.steps + 8, **f32))
+            b = StepBuffers(flat.data_ptr(), gflat.data_ptr(), bufs['m'].data_ptr(), bufs['v'].data_ptr(),
+                            net._bnflat.data_ptr(), z_saved.data_ptr(), z.data_ptr(), lr_img.data_ptr(),
+                            bufs['out_hr'].data_ptr(), bufs['out_lr'].data_ptr(), bufs['g_lr'].data_ptr(),
+                            bufs['g_hr'].data_ptr(), bufs['losses'].data_ptr())
+        jobs.append(dict(st=st, net=net, ds=ds, plan=plan, tables=tables, b=b, keep=(bufs, z, z_saved, lr_img), t=0))
+
+    def run(n):
+        for j in jobs:
+            check(lib.dsr_dip_run(j['plan'].handle, j['tables'].handle, C.byref(j['b']), LR_RATE, SIGMA, 77, j['t'] + 1, n,
+                                  j['st'].cuda_stream), 'dsr_dip_run')
+            j['t'] += n
+
+    run(args.warmup)
+    torch.cuda.synchronize()
+    t0 = time.time()
+    run(args.steps)
+    torch.cuda.synchronize()
+    dt = time.time() - t0
+    return {'images': n_img, 'value': n_img * args.steps / dt, 'unit': 'it/s (aggregate over the concurrent images)',
+            'ms_per_round': dt / args.steps * 1e3}
 
 
 def run_e2e(args, rank, world, dev, net, ds, lr_img, z_saved, barrier):
@@ -384,6 +447,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--size', type=int, default=512)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--concurrent', type=int, default=2, help='also time this many images in flight on the GPU')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
     args = ap.parse_args()

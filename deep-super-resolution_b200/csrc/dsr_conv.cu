@@ -19,6 +19,26 @@ namespace dsr {
 // =============================================================================================
 // conv_gemm_kernel
 // =============================================================================================
+struct ConvItem { int tile, kb0, nkb, out_h, out_w; long long out_off; };
+__device__ __forceinline__ ConvItem conv_item(const ConvGemmParams& p, int item) {
+  ConvItem it;
+  if (p.ncls == 0) {
+    it.tile = item; it.kb0 = 0; it.nkb = p.nkb; it.out_h = p.out_h; it.out_w = p.out_w; it.out_off = 0;
+    return it;
+  }
+  int c = 0;
+#pragma unroll
+  for (int k = 1; k < 4; ++k)
+    if (k < p.ncls && item >= p.cls_tile0[k]) c = k;
+  it.tile = item - p.cls_tile0[c];
+  it.kb0 = p.cls_kb0[c];
+  it.nkb = p.cls_nkb[c];
+  it.out_h = p.cls_out_h[c];
+  it.out_w = p.cls_out_w[c];
+  it.out_off = p.cls_out_off[c];
+  return it;
+}
+
 __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment: required by the 128B swizzle atoms (8 rows x 128 B).
@@ -34,7 +54,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int ntiles = p.tiles_x * p.tiles_y;
+  const int ntiles = p.ncls ? p.cls_tile0[p.ncls] : p.tiles_x * p.tiles_y;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.a64);
@@ -65,11 +85,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int x0 = (tile % p.tiles_x) * p.tw;
-        const int y0 = (tile / p.tiles_x) * p.th;
-        for (int k = 0; k < p.nkb; ++k) {
-          const KBlk kb = p.kb[k];
+      for (int item = blockIdx.x; item < ntiles; item += gridDim.x) {
+        const ConvItem ci = conv_item(p, item);
+        const int x0 = (ci.tile % p.tiles_x) * p.tw;
+        const int y0 = (ci.tile / p.tiles_x) * p.th;
+        for (int k = 0; k < ci.nkb; ++k) {
+          const KBlk kb = p.kb[ci.kb0 + k];
           mbar_wait(&empty_bar[stage], phase ^ 1, p.err, 1);
           uint8_t* sa = smem + stage * kConvStageBytes;
           uint8_t* sb = sa + kConvStageA;
@@ -91,14 +112,15 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       int t = 0;
       const uint64_t hi_w = make_smem_desc(0, 16, 1024, SWZ_128B);
       const uint64_t hi_n = make_smem_desc(0, 16, 256, SWZ_32B);
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t) {
+      for (int item = blockIdx.x; item < ntiles; item += gridDim.x, ++t) {
+        const ConvItem ci = conv_item(p, item);
         const int as = t & 1;
         const uint32_t aphase = (t >> 1) & 1;
         mbar_wait(&tempty_bar[as], aphase ^ 1, p.err, 2);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * 256);
-        for (int k = 0; k < p.nkb; ++k) {
-          const int wide = p.kb[k].wide;
+        for (int k = 0; k < ci.nkb; ++k) {
+          const int wide = p.kb[ci.kb0 + k].wide;
           mbar_wait(&full_bar[stage], phase, p.err, 3);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * kConvStageBytes);
@@ -115,7 +137,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
               umma_f16(tmem_d, da, db, p.idesc, k != 0);
             }
             umma_commit(&empty_bar[stage]);   // frees the smem stage once these MMAs have read it
-            if (k == p.nkb - 1) umma_commit(&tfull_bar[as]);
+            if (k == ci.nkb - 1) umma_commit(&tfull_bar[as]);
           }
           __syncwarp();
           if (++stage == kConvStages) { stage = 0; phase ^= 1; }
@@ -131,16 +153,17 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
 #pragma unroll
     for (int c = 0; c < 9; ++c) { acc_s[c] = 0.f; acc_q[c] = 0.f; }
     int t = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t) {
+    for (int item = blockIdx.x; item < ntiles; item += gridDim.x, ++t) {
+      const ConvItem ci = conv_item(p, item);
       const int as = t & 1;
       const uint32_t aphase = (t >> 1) & 1;
-      const int x = (tile % p.tiles_x) * p.tw + (row % p.tw);
-      const int y = (tile / p.tiles_x) * p.th + (row / p.tw);
-      const bool valid = (x < p.out_w) && (y < p.out_h);
+      const int x = (ci.tile % p.tiles_x) * p.tw + (row % p.tw);
+      const int y = (ci.tile / p.tiles_x) * p.th + (row / p.tw);
+      const bool valid = (x < ci.out_w) && (y < ci.out_h);
       mbar_wait(&tfull_bar[as], aphase, p.err, 4);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(as * 256);
-      const long long obase = static_cast<long long>(y) * p.out_sy + static_cast<long long>(x) * p.out_sx;
+      const long long obase = ci.out_off + static_cast<long long>(y) * p.out_sy + static_cast<long long>(x) * p.out_sx;
 #pragma unroll
       for (int c = 0; c < 9; ++c) {
         if (c < nchunks) {
@@ -1055,7 +1078,7 @@ static int set_attrs() {
 int launch_conv_gemm(const ConvGemmParams& p, int num_sms, cudaStream_t stream) {
   int rc = set_attrs();
   if (rc) return rc;
-  const int ntiles = p.tiles_x * p.tiles_y;
+  const int ntiles = p.ncls ? p.cls_tile0[p.ncls] : p.tiles_x * p.tiles_y;
   if (ntiles <= 0) return 0;
   const int grid = ntiles < num_sms ? ntiles : num_sms;
   conv_gemm_kernel<<<grid, kConvThreads, kConvSmemBytes, stream>>>(p);

@@ -35,6 +35,12 @@ struct alignas(64) ConvGemmParams {
   CUtensorMap b64, b16;   // packed weights [rows][K], boxes (64|16, n_mma)
   KBlk kb[kMaxKBlocks];
   int nkb;
+  // Up to 4 CLASSES share one launch (the 4 output-parity classes of a stride-2 dgrad): class c uses K-blocks
+  // [cls_kb0[c], cls_kb0[c] + cls_nkb[c]), writes at out + cls_out_off[c] and owns tiles [cls_tile0[c], cls_tile0[c+1]).
+  // ncls == 0 means a single class described by the plain fields below.
+  int ncls;
+  int cls_kb0[4], cls_nkb[4], cls_tile0[5], cls_out_h[4], cls_out_w[4];
+  long long cls_out_off[4];
   int tiles_x, tiles_y;   // tile grid over the output pixel grid
   int tw, th;             // tile = tw x th pixels, tw*th == 128
   int out_h, out_w;       // valid extent of the output pixel grid

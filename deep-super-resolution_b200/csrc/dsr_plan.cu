@@ -85,6 +85,8 @@ struct ConvLayer {
   ConvGemmParams fprop{};
   ConvGemmParams dgrad[4];
   int ndgrad = 0;
+  ConvGemmParams dgrad_merged{};   // stride 2: the 4 parity classes as ONE launch (product path)
+  bool has_merged = false;
   HaloParams hfprop{}, hdgrad{};   // weight-stationary halo-tile variants (stride-1 layers)
   bool has_halo = false;
   WgHaloParams hwgrad{};           // halo-row wgrad (layers at least 8 pixels wide)
@@ -409,6 +411,44 @@ int build_conv(dsr_plan* p, ConvLayer& c) {
       g.err = static_cast<int*>(p->errword.ptr);
     }
   }
+  // stride-2 dgrad: merge the parity classes into one launch when they share the tile shape
+  c.has_merged = false;
+  if (c.ndgrad == 4) {
+    bool same = true;
+    int nkb = 0;
+    for (int i = 0; i < 4; ++i) {
+      same = same && c.dgrad[i].tw == c.dgrad[0].tw && c.dgrad[i].th == c.dgrad[0].th;
+      nkb += c.dgrad[i].nkb;
+    }
+    if (same && nkb <= kMaxKBlocks) {
+      ConvGemmParams& m = c.dgrad_merged;
+      m = c.dgrad[0];
+      m.ncls = 4;
+      m.nkb = 0;
+      m.tiles_x = 0;
+      m.tiles_y = 0;
+      int tile0 = 0;
+      for (int i = 0; i < 4; ++i) {
+        const ConvGemmParams& g = c.dgrad[i];
+        if (g.tiles_x > m.tiles_x) m.tiles_x = g.tiles_x;
+        if (g.tiles_y > m.tiles_y) m.tiles_y = g.tiles_y;
+      }
+      for (int i = 0; i < 4; ++i) {
+        const ConvGemmParams& g = c.dgrad[i];
+        m.cls_kb0[i] = m.nkb;
+        m.cls_nkb[i] = g.nkb;
+        for (int k = 0; k < g.nkb; ++k) m.kb[m.nkb++] = g.kb[k];
+        m.cls_tile0[i] = tile0;
+        tile0 += m.tiles_x * m.tiles_y;          // every class enumerates the common (max) tile grid; extras are masked
+        m.cls_out_h[i] = g.out_h;
+        m.cls_out_w[i] = g.out_w;
+        m.cls_out_off[i] = static_cast<long long>(static_cast<const uint16_t*>(g.out) - static_cast<const uint16_t*>(c.gin.ptr));
+      }
+      m.cls_tile0[4] = tile0;
+      m.out = c.gin.ptr;
+      c.has_merged = true;
+    }
+  }
   // ---------------- wgrad ----------------
   {
     WgradParams& g = c.wgrad;
@@ -729,6 +769,11 @@ int run_fprop(dsr_plan* p, ConvLayer& c, cudaStream_t s) {
 }
 int run_dgrad(dsr_plan* p, ConvLayer& c, int i, cudaStream_t s) {
   if (p->debug_conv) return launch_conv_ref(c.dgrad[i], c.ref_dr, c.ref_wd, s);
+  if (c.has_merged && !getenv("DSR_NO_MERGE")) {        // one launch covers all parity classes
+    if (i > 0) return 0;
+    ProfScope ps(p, 2, conv_flops(c), s);
+    return launch_conv_gemm(c.dgrad_merged, p->num_sms, s);
+  }
   ProfScope ps(p, (c.has_halo && p->use_halo) ? 0 : 2, conv_flops(c) / c.ndgrad, s);
   if (c.has_halo && p->use_halo) return launch_conv_halo(c.hdgrad, p->num_sms, s);
   return launch_conv_gemm(c.dgrad[i], p->num_sms, s);
@@ -819,7 +864,10 @@ int conv_backward(dsr_plan* p, ConvLayer& c, cudaStream_t s) {
   } else {
     DSR_TRY(run_wgrad(p, c, s));
   }
-  for (int i = 0; i < c.ndgrad; ++i) DSR_TRY(run_dgrad(p, c, i, s));
+  for (int i = 0; i < c.ndgrad; ++i) {
+    if (i > 0 && c.has_merged && !getenv("DSR_NO_MERGE")) break;      // one launch covered all parity classes
+    DSR_TRY(run_dgrad(p, c, i, s));
+  }
   return 0;
 }
 
@@ -1566,6 +1614,26 @@ int dsr_plan_profile_read(dsr_plan_t* p, int cls, double* ms_total, double* flop
   if (ms_total) *ms_total = ms;
   if (flops_total) *flops_total = fl;
   if (launches) *launches = n;
+  return 0;
+}
+// the largest launch (by algorithmic FLOPs) of class `cls` among the recorded ones: mean milliseconds over its
+// occurrences and its FLOPs
+int dsr_plan_profile_top(dsr_plan_t* p, int cls, double* ms_mean, double* flops) {
+  if (!p) return -1;
+  double best = 0.0, ms = 0.0;
+  int n = 0;
+  for (auto& r : p->prof)
+    if (r.cls == cls && r.flops > best) best = r.flops;
+  for (auto& r : p->prof) {
+    if (r.cls != cls || r.flops != best) continue;
+    if (cudaEventSynchronize(r.b) != cudaSuccess) return -1;
+    float t = 0.f;
+    cudaEventElapsedTime(&t, r.a, r.b);
+    ms += t;
+    ++n;
+  }
+  if (ms_mean) *ms_mean = n ? ms / n : 0.0;
+  if (flops) *flops = best;
   return 0;
 }
 int dsr_plan_device_error(dsr_plan_t* p, int* host_code) {

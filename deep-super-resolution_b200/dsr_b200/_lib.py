@@ -62,6 +62,7 @@ SIGNATURES = {
     'dsr_plan_debug_replay': (i32, [vp, C.c_char_p, i32, i32, vp]),
     'dsr_plan_set_profile': (i32, [vp, i32]),
     'dsr_plan_profile_read': (i32, [vp, i32, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i32)]),
+    'dsr_plan_profile_top': (i32, [vp, i32, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     'dsr_plan_profile_dump': (i32, [vp, C.c_char_p, sz]),
     'dsr_plan_device_error': (i32, [vp, C.POINTER(i32)]),
     'dsr_debug_copy': (i32, [vp, vp, sz, vp]),

@@ -139,6 +139,8 @@ int dsr_plan_profile_read(dsr_plan_t* p, int cls, double* ms_total, double* flop
 /* set_profile(p, 2): every launch of forward / backward is bracketed by events on the main stream (side stream and
  * graph replay off); profile_dump writes one "<microseconds>\t<call site>" line per launch into buf, returns bytes. */
 int dsr_plan_profile_dump(dsr_plan_t* p, char* buf, size_t cap);
+/* The largest recorded launch (by algorithmic FLOPs) of class cls: mean milliseconds over its occurrences, its FLOPs. */
+int dsr_plan_profile_top(dsr_plan_t* p, int cls, double* ms_mean, double* flops);
 /* Device error word written by a kernel whose mbarrier wait timed out (0 = none). */
 int dsr_plan_device_error(dsr_plan_t* p, int* host_code);
 /* Device-to-device copy on `stream` (lets ctypes callers read an introspected tensor into their own buffer). */
