@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
             const float m = valid ? 1.f : 0.f;
             float s[16], q[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) { s[i] = f[i] * m; q[i] = f[i] * f[i] * m; }
+            for (int i = 0; i < 16; ++i) { s[i] = (m != 0.f) ? f[i] : 0.f; q[i] = (m != 0.f) ? f[i] * f[i] : 0.f; }
 #pragma unroll
             for (int w = 8; w >= 1; w >>= 1) {
               const int d = w * 2;                 // lane distance 16, 8, 4, 2
@@ -277,7 +277,7 @@ __device__ __forceinline__ void halo_epilogue_process(const HaloParams& p, const
     const float m = valid ? 1.f : 0.f;
     float s[16], q[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) { s[i] = f[i] * m; q[i] = f[i] * f[i] * m; }
+    for (int i = 0; i < 16; ++i) { s[i] = (m != 0.f) ? f[i] : 0.f; q[i] = (m != 0.f) ? f[i] * f[i] : 0.f; }
 #pragma unroll
     for (int w = 8; w >= 1; w >>= 1) {
       const int d = w * 2;

@@ -268,7 +268,8 @@ void setup_conv(dsr_plan* p, Bump& ws, Bump& accf, Bump& accb, ConvLayer& c, con
   c.n_rows = need_dgrad ? cin_pad : 0;
   c.act_halo = act_halo;
   ws.take(c.raw, static_cast<size_t>(c.outH) * c.outW * kNC * 2);
-  ws.take(c.act, static_cast<size_t>(c.outH + 2) * (c.outW + 2) * kNC * 2);
+  // + one padded row and one pixel of zeros: the parity-split (stride-2) TMA view of an odd-sized grid addresses them
+  ws.take(c.act, (static_cast<size_t>(c.outH + 3) * (c.outW + 2) + 1) * kNC * 2);
   ws.take(c.dr, static_cast<size_t>(c.outH + 2) * (c.outW + 2) * kNC * 2);
   if (need_dgrad) ws.take(c.gin, static_cast<size_t>(inH + 2) * (inW + 2) * c.n_rows * 2);
   c.stats_off = accf.take_floats(2 * kNC);
@@ -865,7 +866,7 @@ int conv_backward(dsr_plan* p, ConvLayer& c, cudaStream_t s) {
     DSR_TRY(run_wgrad(p, c, s));
   }
   for (int i = 0; i < c.ndgrad; ++i) {
-    if (i > 0 && c.has_merged && !getenv("DSR_NO_MERGE")) break;      // one launch covered all parity classes
+    if (i > 0 && c.has_merged && !p->debug_conv && !getenv("DSR_NO_MERGE")) break;   // one launch covered all classes
     DSR_TRY(run_dgrad(p, c, i, s));
   }
   return 0;
@@ -1062,15 +1063,26 @@ int dsr_plan_create(dsr_plan_t** out, int H, int W, int input_depth, int num_sca
   if (out == nullptr) return -1;
   if (num_scales < 1 || num_scales > 6 || n_out != 3) return -5;
   if (input_depth != 32 && input_depth != 128) return -5;
-  const int m = 1 << num_scales;
-  if (H < m || W < m || (H % m) != 0 || (W % m) != 0) return -5;   // centre-crop / odd levels: not yet
+  {  // any H, W whose level sizes stay >= 2 (ReflectionPad2d(1) needs two pixels): stride-2 convs give ceil(n / 2),
+     // the x2-upsampled deeper branch is centre-cropped to the skip branch (Concat, models/DIP/utils.py:26-36):
+     // the size difference is 0 or 1, so the crop offset is 0 and only the last row / column is dropped
+    int h = H, w = W;
+    for (int i = 0; i < num_scales; ++i) {
+      if (h < 2 || w < 2) return -5;
+      h = (h + 1) / 2;
+      w = (w + 1) / 2;
+    }
+    if (h < 2 || w < 2) return -5;
+  }
   dsr_plan* p = new dsr_plan();
   p->H = H; p->W = W; p->input_depth = input_depth; p->num_scales = num_scales; p->n_out = n_out;
   p->lv.resize(num_scales);
-  for (int i = 0; i < num_scales; ++i) {
+  for (int i = 0, h = H, w = W; i < num_scales; ++i) {
     Level& L = p->lv[i];
-    L.H = H >> i; L.W = W >> i; L.h = L.H / 2; L.w = L.W / 2;
+    L.H = h; L.W = w; L.h = (h + 1) / 2; L.w = (w + 1) / 2;
     L.Cin = (i == 0) ? input_depth : kNC;
+    h = L.h;
+    w = L.w;
   }
   name_level(p, 0);
   add_conv_params(p, "9.1", p->fin_w, p->fin_b, n_out, kNC, 1);
@@ -1083,7 +1095,7 @@ int dsr_plan_create(dsr_plan_t** out, int H, int W, int input_depth, int num_sca
     Level& L = p->lv[i];
     const bool last = (i + 1 == num_scales);
     if (i == 0) {
-      ws.take(L.xin, static_cast<size_t>(L.H + 2) * (L.W + 2) * L.Cin * 2);
+      ws.take(L.xin, (static_cast<size_t>(L.H + 3) * (L.W + 2) + 1) * L.Cin * 2);
       L.x_pad = &L.xin;
     } else {
       L.x_pad = &p->lv[i - 1].d2.act;

@@ -114,7 +114,7 @@ class SkipNet(nn.Module):
         super().__init__()
         self.input_depth, self.n_channels, self.num_scales = input_depth, n_channels, num_scales
         probe = C.c_void_p()
-        check(lib.dsr_plan_create(C.byref(probe), 1 << num_scales, 1 << num_scales, input_depth, num_scales,
+        check(lib.dsr_plan_create(C.byref(probe), 2 << num_scales, 2 << num_scales, input_depth, num_scales,
                                   n_channels), 'dsr_plan_create (configuration check)')
         self._layout = _read_layout(probe)
         lib.dsr_plan_destroy(probe)

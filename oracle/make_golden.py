@@ -73,7 +73,7 @@ def main():
                    os.path.join(OUT, f'init_seed{seed}.pt'))
 
     # ---- one teacher-forced step + a 3-iteration trajectory ---------------------------------
-    for (H, W, factor, seed) in ((64, 64, 4, 0), (64, 96, 4, 3)):
+    for (H, W, factor, seed) in ((64, 64, 4, 0), (64, 96, 4, 3), (72, 88, 4, 5)):   # last: odd level sizes + Concat crop
         torch.manual_seed(seed)
         net = make_net()
         net_input = get_noise(32, 'noise', (H, W)).detach()

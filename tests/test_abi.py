@@ -69,7 +69,9 @@ def test_plan_layout_matches_reference_state_dict(golden):
     assert [n for n, _, _ in lay['bns']] == bn_names
     assert lib.dsr_plan_workspace_bytes(h) > 0
     lib.dsr_plan_destroy(h)
-    for bad in ((60, 64, 32, 5, 3), (64, 64, 24, 5, 3), (64, 64, 32, 7, 3), (64, 64, 32, 5, 1)):
+    check(lib.dsr_plan_create(C.byref(h), 127, 84, 32, 5, 3))      # odd level sizes are supported (Concat crop)
+    lib.dsr_plan_destroy(h)
+    for bad in ((20, 64, 32, 5, 3), (64, 64, 24, 5, 3), (64, 64, 32, 7, 3), (64, 64, 32, 5, 1)):
         assert lib.dsr_plan_create(C.byref(h), *bad) == -5
 
 
@@ -145,3 +147,12 @@ def test_product_does_not_import_the_oracle():
             if f.endswith(('.py', '.cu', '.cuh', '.h')):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r'(from|import)\s+oracle|dip_oracle|oracle/', src), (dirpath, f)
+
+
+def test_drop_in_module_names_resolve_to_this_package():
+    import importlib
+    import dsr_b200
+    assert importlib.import_module('models.DIP').get_net is dsr_b200.get_net
+    assert importlib.import_module('utils.downsampler').Downsampler is dsr_b200.Downsampler
+    m = importlib.import_module('utils.DIP')
+    assert m.optimize is dsr_b200.optimize and m.get_noise is dsr_b200.get_noise and m.get_params is dsr_b200.get_params

@@ -80,7 +80,7 @@ def test_init_matches_reference(golden, seed):
         torch.set_num_threads(threads)
 
 
-@pytest.mark.parametrize('name', ['step_64x64.pt', 'step_64x96.pt'])
+@pytest.mark.parametrize('name', ['step_64x64.pt', 'step_64x96.pt', 'step_72x88.pt'])
 def test_step_matches_reference(golden, name):
     fx = golden(name)
     torch.set_num_threads(1)          # the fixtures were generated single-threaded (fixes the reduction order)
