@@ -1404,6 +1404,315 @@ int launch_skip_bwd(const float* dsy, const float* sraw, BnRef bn_skip, const fl
 }
 
 // =============================================================================================
+// Upsample + concat + BN(132) in the SOURCE (low-resolution) domain.
+//
+// u = Up d is linear in the low-resolution tensor d (U = Uy (x) Ux, rows sum to 1), so with w = U^T 1 and Q = U^T U
+// (a 3x3 stencil whose weights depend only on the position relative to the edges)
+//     sum_o u            = sum_i w_i d_i                      sum_o u^2        = sum_i d_i (Q d)_i
+//     sum_o dc           = sum_i t_i          (t = U^T dc)     sum_o dc u       = sum_i d_i t_i
+//     U^T [k1 (dc - c1 - c2 xhat)] = k1 ( t - c1 w - c2 rstd (Q d - mean w) )
+// Forward statistics and the whole backward pass of the 128 upsampled channels therefore need ONE high-resolution
+// read (the gather t = U^T fold(dc)); everything else runs on tensors with a quarter of the pixels, and neither the
+// upsampled tensor nor its gradient is ever materialised.  The 4 skip channels are handled by per-pixel kernels.
+// =============================================================================================
+// 1-D pieces for source index q (n_src sources, n_out outputs): cw[t] = U[2q-1+t][q] (t = 0..3), w = sum_t cw[t],
+// Q[k] = sum_t U[o_t][q] U[o_t][q-1+k] (k = 0..2)
+__device__ __forceinline__ void up_q(int q, int n_src, int n_out, float (&cw)[4], float& w, float (&Q)[3]) {
+  w = 0.f;
+  Q[0] = Q[1] = Q[2] = 0.f;
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const int o = 2 * q - 1 + t;
+    cw[t] = 0.f;
+    if (o >= 0 && o < n_out) {
+      int i0, i1;
+      float l0, l1;
+      up_src(o, n_src, i0, i1, l0, l1);
+      float c[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) c[k] = (i0 == q - 1 + k ? l0 : 0.f) + (i1 == q - 1 + k ? l1 : 0.f);
+      cw[t] = c[1];
+      w += c[1];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) Q[k] = fmaf(c[1], c[k], Q[k]);
+    }
+  }
+}
+
+// (Q d) at low-resolution pixel (qy, qx) for the lane's 4 channels; `d` points at pixel (0,0), row pitch sy
+__device__ __forceinline__ void q_stencil(const __half* d, long long sy, int h, int w, int qy, int qx, const float (&Qy)[3],
+                                          const float (&Qx)[3], int lane, float (&qd)[4], float (&center)[4]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) qd[j] = 0.f;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const int y = qy - 1 + a;
+    if (y < 0 || y >= h) continue;            // the corresponding Q weight is 0 there as well
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      const int x = qx - 1 + b;
+      if (x < 0 || x >= w) continue;
+      float f[4];
+      cvt4h(ldg8(d + y * sy + static_cast<long long>(x) * 128 + lane * 4), f);
+      const float ww = Qy[a] * Qx[b];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) qd[j] = fmaf(ww, f[j], qd[j]);
+      if (a == 1 && b == 1) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) center[j] = f[j];
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) upcat_stats_lowres_kernel(UpcatArgs a) {
+  const int lane = threadIdx.x & 31;
+  float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
+  const int npix = a.h * a.w;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const __half* d = static_cast<const __half*>(a.deep);
+  for (int pix = ((blockIdx.x * blockDim.x) + threadIdx.x) >> 5; pix < npix; pix += warps) {
+    const int qy = pix / a.w, qx = pix - qy * a.w;
+    float cwy[4], cwx[4], wy, wx, Qy[3], Qx[3];
+    up_q(qy, a.h, a.H, cwy, wy, Qy);
+    up_q(qx, a.w, a.W, cwx, wx, Qx);
+    float qd[4], c[4] = {0, 0, 0, 0};
+    q_stencil(d, a.deep_sy, a.h, a.w, qy, qx, Qy, Qx, lane, qd, c);
+    const float w2 = wy * wx;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      s[j] = fmaf(w2, c[j], s[j]);
+      q[j] = fmaf(c[j], qd[j], q[j]);
+    }
+  }
+  __shared__ float red[256];
+  red[threadIdx.x] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    atomicAdd(&red[lane * 4 + j], s[j]);
+    atomicAdd(&red[128 + lane * 4 + j], q[j]);
+  }
+  __syncthreads();
+  if (threadIdx.x < 128) atomicAdd(&a.cat_stats[threadIdx.x], red[threadIdx.x]);
+  else atomicAdd(&a.cat_stats[144 + threadIdx.x - 128], red[threadIdx.x]);
+}
+
+// forward statistics of the 4 skip channels of the concat tensor (one thread per pixel)
+__global__ void __launch_bounds__(kThreads) skipcat_stats_kernel(UpcatArgs a) {
+  __shared__ SkipConst sc;
+  skip_const_init(&sc, a, nullptr, false);
+  float s4[4] = {0, 0, 0, 0}, q4[4] = {0, 0, 0, 0};
+  const long long npix = static_cast<long long>(a.H) * a.W;
+  for (long long pix = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; pix < npix;
+       pix += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float sv[4], xh[4], yv[4];
+    skip_act4(sc, a.sraw, pix, sv, xh, yv);
+#pragma unroll
+    for (int o = 0; o < 4; ++o) { s4[o] += sv[o]; q4[o] = fmaf(sv[o], sv[o], q4[o]); }
+  }
+  __shared__ float red[8];
+  if (threadIdx.x < 8) red[threadIdx.x] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int o = 0; o < 4; ++o) {
+    float v = s4[o], u = q4[o];
+#pragma unroll
+    for (int dd = 16; dd >= 1; dd >>= 1) { v += __shfl_xor_sync(0xffffffffu, v, dd); u += __shfl_xor_sync(0xffffffffu, u, dd); }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&red[o], v); atomicAdd(&red[4 + o], u); }
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) atomicAdd(&a.cat_stats[128 + threadIdx.x], red[threadIdx.x]);
+  else if (threadIdx.x < 8) atomicAdd(&a.cat_stats[144 + 128 + threadIdx.x - 4], red[threadIdx.x]);
+}
+
+int launch_upcat_stats_lowres(const UpcatArgs& a, cudaStream_t s) {
+  long long blocks = (static_cast<long long>(a.h) * a.w + 7) / 8;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  upcat_stats_lowres_kernel<<<static_cast<int>(blocks < 1 ? 1 : blocks), kThreads, 0, s>>>(a);
+  long long b2 = (static_cast<long long>(a.H) * a.W + kThreads - 1) / kThreads;
+  if (b2 > 148 * 4) b2 = 148 * 4;
+  skipcat_stats_kernel<<<static_cast<int>(b2 < 1 ? 1 : b2), kThreads, 0, s>>>(a);
+  DSR_LAUNCH_CHECK();
+}
+
+// backward, pass A: t = U^T fold(dc) for the 128 upsampled channels (the only high-resolution read), written to
+// tbuf [h][w][128]; accumulates S1 = sum t and S2' = sum d t into cbstats[c], cbstats[144 + c]
+__global__ void __launch_bounds__(kThreads, 3) upT_gather_kernel(UpcatBwdArgs a) {
+  const UpcatArgs& f = a.f;
+  const int lane = threadIdx.x & 31;
+  const int c0 = lane * 4;
+  float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+  const int npix = f.h * f.w;
+  const int Wp = f.W + 2;
+  const __half* __restrict__ gc = static_cast<const __half*>(a.gcat);
+  const __half* __restrict__ d = static_cast<const __half*>(f.deep);
+  __half* __restrict__ tb = static_cast<__half*>(a.dup_pad);
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int pix = ((blockIdx.x * blockDim.x) + threadIdx.x) >> 5; pix < npix; pix += warps) {
+    const int qy = pix / f.w, qx = pix - qy * f.w;
+    float cwy[4], cwx[4], wy, wx, Qy[3], Qx[3];
+    up_q(qy, f.h, f.H, cwy, wy, Qy);
+    up_q(qx, f.w, f.W, cwx, wx, Qx);
+    uint2 v[4][4];
+#pragma unroll
+    for (int aa = 0; aa < 4; ++aa)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int oy = min(max(2 * qy - 1 + aa, 0), f.H - 1), ox = min(max(2 * qx - 1 + b, 0), f.W - 1);
+        v[aa][b] = ldg8(gc + (static_cast<long long>(oy + 1) * Wp + (ox + 1)) * 144 + c0);
+      }
+    const uint2 vd = ldg8(d + qy * f.deep_sy + static_cast<long long>(qx) * 128 + c0);
+    float acc[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int aa = 0; aa < 4; ++aa) {
+      if (cwy[aa] == 0.f) continue;
+      const int oy = 2 * qy - 1 + aa;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        if (cwx[b] == 0.f) continue;
+        const int ox = 2 * qx - 1 + b;
+        float dc[4];
+        fold_gather4(gc, 144, f.H, f.W, oy, ox, c0, v[aa][b], dc);
+        const float ww = cwy[aa] * cwx[b];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] = fmaf(ww, dc[j], acc[j]);
+      }
+    }
+    stg8(tb + static_cast<long long>(pix) * 128 + c0, pack4h(acc));
+    float dd[4];
+    cvt4h(vd, dd);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { s1[j] += acc[j]; s2[j] = fmaf(dd[j], acc[j], s2[j]); }
+  }
+  __shared__ float red[256];
+  red[threadIdx.x] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    atomicAdd(&red[c0 + j], s1[j]);
+    atomicAdd(&red[128 + c0 + j], s2[j]);
+  }
+  __syncthreads();
+  if (threadIdx.x < 128) atomicAdd(&a.cbstats[threadIdx.x], red[threadIdx.x]);
+  else atomicAdd(&a.cbstats[144 + threadIdx.x - 128], red[threadIdx.x]);
+}
+
+// backward, pass C (low resolution): ddeep = k1 ( t - c1 w - c2 rstd (Q d - mean w) ); BN(132) parameter gradients
+__global__ void __launch_bounds__(kThreads) upcat_bwd_lowres_kernel(UpcatBwdArgs a, __half* __restrict__ ddeep) {
+  const UpcatArgs& f = a.f;
+  const int lane = threadIdx.x & 31;
+  const int c0 = lane * 4;
+  const float inv_n = 1.f / (static_cast<float>(f.H) * static_cast<float>(f.W));
+  float mean[4], rstd[4], k1[4], c1[4], c2r[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float ga, be;
+    cat_coeffs(f, c0 + j, mean[j], rstd[j], ga, be);
+    k1[j] = ga * rstd[j];
+    const float S1 = a.cbstats[c0 + j];
+    const float S2 = rstd[j] * (a.cbstats[144 + c0 + j] - mean[j] * S1);      // sum dc * xhat
+    c1[j] = S1 * inv_n;
+    c2r[j] = S2 * inv_n * rstd[j];
+    if (blockIdx.x == 0 && threadIdx.x < 32) {
+      a.dcat_beta[c0 + j + 4] = S1 * a.gs[1];       // packed channel c <-> reference channel c + 4
+      a.dcat_gamma[c0 + j + 4] = S2 * a.gs[1];
+    }
+  }
+  const int npix = f.h * f.w;
+  const int wp = f.w + 2;
+  const __half* __restrict__ tb = static_cast<const __half*>(a.dup_pad);
+  const __half* __restrict__ d = static_cast<const __half*>(f.deep);
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int pix = ((blockIdx.x * blockDim.x) + threadIdx.x) >> 5; pix < npix; pix += warps) {
+    const int qy = pix / f.w, qx = pix - qy * f.w;
+    float cwy[4], cwx[4], wy, wx, Qy[3], Qx[3];
+    up_q(qy, f.h, f.H, cwy, wy, Qy);
+    up_q(qx, f.w, f.W, cwx, wx, Qx);
+    const uint2 vt = ldg8(tb + static_cast<long long>(pix) * 128 + c0);
+    float qd[4], c[4] = {0, 0, 0, 0}, t[4], o[4];
+    q_stencil(d, f.deep_sy, f.h, f.w, qy, qx, Qy, Qx, lane, qd, c);
+    cvt4h(vt, t);
+    const float w2 = wy * wx;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j] = k1[j] * (t[j] - c1[j] * w2 - c2r[j] * (qd[j] - mean[j] * w2));
+    stg8(ddeep + (static_cast<long long>(qy + 1) * wp + (qx + 1)) * 128 + c0, pack4h(o));
+  }
+}
+
+// backward of the 4 skip channels of the concat tensor (one thread per pixel): BN(132) + LeakyReLU' of the skip branch
+template <bool APPLY>
+__global__ void __launch_bounds__(kThreads) skipcat_bwd_kernel(UpcatBwdArgs a) {
+  const UpcatArgs& f = a.f;
+  __shared__ SkipConst sc;
+  skip_const_init(&sc, f, APPLY ? a.cbstats : nullptr, true);
+  float t1[4] = {0, 0, 0, 0}, t2[4] = {0, 0, 0, 0};
+  const long long npix = static_cast<long long>(f.H) * f.W;
+  const int Wp = f.W + 2;
+  const __half* __restrict__ gc = static_cast<const __half*>(a.gcat);
+  for (long long pix = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; pix < npix;
+       pix += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int y = static_cast<int>(pix / f.W), x = static_cast<int>(pix - static_cast<long long>(y) * f.W);
+    float d4[4];
+    fold_gather4(gc, 144, f.H, f.W, y, x, 128, ldg8(gc + (static_cast<long long>(y + 1) * Wp + (x + 1)) * 144 + 128), d4);
+    float sv[4], xh4[4], yv[4], dsy[4];
+    skip_act4(sc, f.sraw, pix, sv, xh4, yv);
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      const float xh = fmaf(sv[o], sc.cxa[o], sc.cxb[o]);
+      if (!APPLY) {
+        t1[o] += d4[o];
+        t2[o] = fmaf(d4[o], xh, t2[o]);
+      } else {
+        const float ds = sc.ck1[o] * (d4[o] - sc.cc1[o] - xh * sc.cc2[o]);
+        dsy[o] = ds * (yv[o] > 0.f ? 1.f : kSlope);
+        t1[o] += dsy[o];
+        t2[o] = fmaf(dsy[o], xh4[o], t2[o]);
+      }
+    }
+    if (APPLY) *reinterpret_cast<float4*>(a.dsy + pix * 4) = make_float4(dsy[0], dsy[1], dsy[2], dsy[3]);
+  }
+  __shared__ float red[8];
+  if (threadIdx.x < 8) red[threadIdx.x] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int o = 0; o < 4; ++o) {
+    float v = t1[o], u = t2[o];
+#pragma unroll
+    for (int dd = 16; dd >= 1; dd >>= 1) { v += __shfl_xor_sync(0xffffffffu, v, dd); u += __shfl_xor_sync(0xffffffffu, u, dd); }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&red[o], v); atomicAdd(&red[4 + o], u); }
+  }
+  __syncthreads();
+  if (!APPLY) {
+    if (threadIdx.x < 4) atomicAdd(&a.cbstats[128 + threadIdx.x], red[threadIdx.x]);
+    else if (threadIdx.x < 8) atomicAdd(&a.cbstats[144 + 128 + threadIdx.x - 4], red[threadIdx.x]);
+  } else {
+    if (threadIdx.x < 8) atomicAdd(&a.sbstats[threadIdx.x], red[threadIdx.x]);
+    if (blockIdx.x == 0 && threadIdx.x < 4) {       // skip channels are reference channels 0..3
+      a.dcat_beta[threadIdx.x] = a.cbstats[128 + threadIdx.x] * a.gs[1];
+      a.dcat_gamma[threadIdx.x] = a.cbstats[144 + 128 + threadIdx.x] * a.gs[1];
+    }
+  }
+}
+
+// whole backward of upsample + concat + BN(132): gcat -> ddeep (gradient w.r.t. the low-resolution tensor, padded
+// grid interior) and dsy (gradient w.r.t. the skip branch's BN(4) output), plus the BN(132) parameter gradients
+int launch_upcat_bwd_lowres(const UpcatBwdArgs& a, void* ddeep_pad, cudaStream_t s) {
+  const UpcatArgs& f = a.f;
+  long long lo = (static_cast<long long>(f.h) * f.w + 7) / 8;
+  if (lo > 148 * 12) lo = 148 * 12;
+  if (lo < 1) lo = 1;
+  long long hi = (static_cast<long long>(f.H) * f.W + kThreads - 1) / kThreads;
+  if (hi > 148 * 4) hi = 148 * 4;
+  if (hi < 1) hi = 1;
+  upT_gather_kernel<<<static_cast<int>(lo), kThreads, 0, s>>>(a);
+  skipcat_bwd_kernel<false><<<static_cast<int>(hi), kThreads, 0, s>>>(a);
+  upcat_bwd_lowres_kernel<<<static_cast<int>(lo), kThreads, 0, s>>>(a, static_cast<__half*>(ddeep_pad));
+  skipcat_bwd_kernel<true><<<static_cast<int>(hi), kThreads, 0, s>>>(a);
+  DSR_LAUNCH_CHECK();
+}
+
+// =============================================================================================
 // bilinear upsample backward (gather form)
 // =============================================================================================
 __global__ void upsample_bwd_kernel(const __half* __restrict__ dup, int H, int W,

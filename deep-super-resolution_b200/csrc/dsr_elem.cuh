@@ -100,6 +100,10 @@ struct UpcatBwdArgs {
   float* dcat_beta;
   const float* gs;
 };
+// source-domain formulation (see dsr_elem.cu): forward statistics of the concat tensor, and the whole backward of
+// upsample + concat + BN(132) (a.dup_pad is used as the [h][w][128] scratch tensor t = U^T dc)
+int launch_upcat_stats_lowres(const UpcatArgs& a, cudaStream_t s);
+int launch_upcat_bwd_lowres(const UpcatBwdArgs& a, void* ddeep_pad, cudaStream_t s);
 int launch_upcat_bwd_stats(const UpcatBwdArgs& a, cudaStream_t s);
 int launch_upcat_bwd_apply(const UpcatBwdArgs& a, cudaStream_t s);
 

@@ -166,6 +166,7 @@ struct dsr_plan {
   // pointer arguments; an entry is captured on its SECOND use (the first run is eager and sets function attributes)
   struct PassGraph { int kind; const void* a0; const void* a1; const void* a2; const void* a3; int uses; cudaGraphExec_t exec; };
   std::vector<PassGraph> pass_graphs;
+  int lowres_upcat = 1;          // upsample + concat + BN(132): statistics and backward in the low-resolution domain
   int in_step = 0;               // inside enqueue_step (whole-iteration graph): no nested pass graphs
   int fuse_top = 1;              // level 0: BN/LeakyReLU of the last decoder conv fused with the final conv (fwd + bwd)
   bool bound = false, have_forward = false;
@@ -822,7 +823,8 @@ int forward_level(dsr_plan* p, int i, const float* params, cudaStream_t s) {
   if ((rc = conv_bn_act(p, L.d2, params, s))) return rc;
   if (i + 1 < p->num_scales && (rc = forward_level(p, i + 1, params, s))) return rc;
   const UpcatArgs a = upcat_args(p, i, params);
-  DSR_TRY(launch_upcat_stats(a, s));
+  if (p->lowres_upcat) DSR_TRY(launch_upcat_stats_lowres(a, s));
+  else DSR_TRY(launch_upcat_stats(a, s));
   DSR_TRY(launch_upcat_apply(a, s));
   if ((rc = conv_bn_act(p, L.u1, params, s))) return rc;
   if (i == 0 && p->fuse_top) {           // BN + LeakyReLU of u2 is fused with the final conv (dsr_net_forward)
@@ -894,14 +896,18 @@ int backward_level(dsr_plan* p, int i, const float* params, float* grads, cudaSt
   ub.dcat_gamma = grads + L.cat_g;
   ub.dcat_beta = grads + L.cat_be;
   ub.gs = static_cast<const float*>(p->gscale.ptr);
-  DSR_TRY(launch_upcat_bwd_stats(ub, s));
-  DSR_TRY(launch_upcat_bwd_apply(ub, s));
+  void* ddeep = last ? L.g_d2a.ptr : p->lv[i + 1].g_u2a.ptr;
+  if (p->lowres_upcat) {
+    DSR_TRY(launch_upcat_bwd_lowres(ub, ddeep, s));
+  } else {
+    DSR_TRY(launch_upcat_bwd_stats(ub, s));
+    DSR_TRY(launch_upcat_bwd_apply(ub, s));
+  }
   DSR_TRY(launch_skip_bwd(static_cast<const float*>(L.dsy.ptr), static_cast<const float*>(L.sraw.ptr),
                           skip_bn(p, L, params), acc + L.sbstats_off, L.x_pad->ptr, L.Cin,
                           static_cast<float*>(L.dsraw.ptr), grads + L.skip_w, grads + L.skip_g, grads + L.skip_be,
                           static_cast<const float*>(p->gscale.ptr), L.H, L.W, s));
-  void* ddeep = last ? L.g_d2a.ptr : p->lv[i + 1].g_u2a.ptr;
-  DSR_TRY(launch_upsample_bwd(L.dup.ptr, L.H, L.W, ddeep, L.h, L.w, s));
+  if (!p->lowres_upcat) DSR_TRY(launch_upsample_bwd(L.dup.ptr, L.H, L.W, ddeep, L.h, L.w, s));
   if (!last && (rc = backward_level(p, i + 1, params, grads, s))) return rc;
   // ---- encoder ----
   if (last) {
@@ -1273,6 +1279,7 @@ int dsr_plan_bind(dsr_plan_t* p, void* workspace, size_t bytes, void* stream) {
   p->use_side = getenv("DSR_NO_SIDE_STREAM") ? 0 : 1;
   p->use_graph = getenv("DSR_NO_GRAPH") ? 0 : 1;
   p->fuse_top = getenv("DSR_NO_FUSE_TOP") ? 0 : 1;
+  p->lowres_upcat = getenv("DSR_NO_LOWRES_UPCAT") ? 0 : 1;
   p->bound = true;
   p->have_forward = false;
   return 0;
