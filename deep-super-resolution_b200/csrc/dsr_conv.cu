@@ -13,6 +13,7 @@
 #include "dsr_conv.cuh"
 #include "dsr_ptx.cuh"
 #include "dsr_host.h"
+#include "dsr_launch.cuh"
 
 namespace dsr {
 
@@ -79,6 +80,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -351,17 +353,20 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (warp == 0 && lane == 0) {          // resident weights: packed >= 2 launches ago, fetched before the PDL wait
+    mbar_arrive_expect_tx(bres_bar, static_cast<uint32_t>(p.ntaps * (p.n_wide * wb + p.n_narrow * nb)));
+    for (int t = 0; t < p.ntaps; ++t) {
+      const int row = p.taps[t].b_row + part * p.n_part;
+      for (int c = 0; c < p.n_wide; ++c)
+        tma_load_2d(&p.b64, bres_bar, bres_w + (t * p.n_wide + c) * wb, c * 64, row);
+      if (p.n_narrow) tma_load_2d(&p.b16, bres_bar, bres_n + t * nb, p.n_wide * 64, row);
+    }
+  }
+  pdl_sync();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      mbar_arrive_expect_tx(bres_bar, static_cast<uint32_t>(p.ntaps * (p.n_wide * wb + p.n_narrow * nb)));
-      for (int t = 0; t < p.ntaps; ++t) {
-        const int row = p.taps[t].b_row + part * p.n_part;
-        for (int c = 0; c < p.n_wide; ++c)
-          tma_load_2d(&p.b64, bres_bar, bres_w + (t * p.n_wide + c) * wb, c * 64, row);
-        if (p.n_narrow) tma_load_2d(&p.b16, bres_bar, bres_n + t * nb, p.n_wide * 64, row);
-      }
       int ws = 0, ns = 0;
       uint32_t wph = 0, nph = 0;
       for (int tile = seq0; tile < ntiles; tile += seq_stride) {
@@ -563,18 +568,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHalo2Threads, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (warp == 0 && lane == 0) {          // resident weights: packed >= 2 launches ago, fetched before the PDL wait
+    const uint32_t bbytes = static_cast<uint32_t>(p.ntaps * (p.n_wide * wb + p.n_narrow * nb));
+    if (rank == 0) mbar_arrive_expect_tx(bres_bar, 2 * bbytes);
+    for (int t = 0; t < p.ntaps; ++t) {
+      const int row = p.taps[t].b_row + static_cast<int>(rank) * p.n_part;
+      for (int c = 0; c < p.n_wide; ++c)
+        tma_load_2d_pair(&p.b64, bres_bar, bres_w + (t * p.n_wide + c) * wb, c * 64, row);
+      if (p.n_narrow) tma_load_2d_pair(&p.b16, bres_bar, bres_n + t * nb, p.n_wide * 64, row);
+    }
+  }
+  pdl_sync();
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
     if (lane == 0) {
-      const uint32_t bbytes = static_cast<uint32_t>(p.ntaps * (p.n_wide * wb + p.n_narrow * nb));
-      if (rank == 0) mbar_arrive_expect_tx(bres_bar, 2 * bbytes);
-      for (int t = 0; t < p.ntaps; ++t) {
-        const int row = p.taps[t].b_row + static_cast<int>(rank) * p.n_part;
-        for (int c = 0; c < p.n_wide; ++c)
-          tma_load_2d_pair(&p.b64, bres_bar, bres_w + (t * p.n_wide + c) * wb, c * 64, row);
-        if (p.n_narrow) tma_load_2d_pair(&p.b16, bres_bar, bres_n + t * nb, p.n_wide * 64, row);
-      }
       int ws = 0, ns = 0;
       uint32_t wph = 0, nph = 0;
       for (int pair = pair0; pair < npairs; pair += pair_stride) {
@@ -772,6 +780,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -904,6 +913,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_halo_kernel(const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -1081,7 +1091,7 @@ int launch_conv_gemm(const ConvGemmParams& p, int num_sms, cudaStream_t stream) 
   const int ntiles = p.ncls ? p.cls_tile0[p.ncls] : p.tiles_x * p.tiles_y;
   if (ntiles <= 0) return 0;
   const int grid = ntiles < num_sms ? ntiles : num_sms;
-  conv_gemm_kernel<<<grid, kConvThreads, kConvSmemBytes, stream>>>(p);
+  launch_k(conv_gemm_kernel, dim3(grid), dim3(kConvThreads), kConvSmemBytes, stream, p);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -1105,12 +1115,12 @@ int launch_conv_halo(const HaloParams& p, int num_sms, cudaStream_t stream) {
     const int npairs = (ntiles + 1) / 2;
     int clusters = num_sms / 2;
     if (clusters > npairs) clusters = npairs;
-    conv_halo2_kernel<<<2 * clusters, kHalo2Threads, p.smem_bytes, stream>>>(p);
+    launch_k(conv_halo2_kernel, dim3(2 * clusters), dim3(kHalo2Threads), p.smem_bytes, stream, p);
     return static_cast<int>(cudaGetLastError());
   }
   int grid = (num_sms / p.parts) * p.parts;
   if (grid > ntiles * p.parts) grid = ntiles * p.parts;
-  conv_halo_kernel<<<grid, kHaloThreads, p.smem_bytes, stream>>>(p);
+  launch_k(conv_halo_kernel, dim3(grid), dim3(kHaloThreads), p.smem_bytes, stream, p);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -1123,7 +1133,7 @@ int launch_wgrad_halo(const WgHaloParams& p, cudaStream_t stream) {
   }
   const int grid = p.ngroups * p.nsplit;
   if (grid <= 0) return 0;
-  wgrad_halo_kernel<<<grid, kWgThreads, kWgHSmemBytes, stream>>>(p);
+  launch_k(wgrad_halo_kernel, dim3(grid), dim3(kWgThreads), kWgHSmemBytes, stream, p);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -1132,7 +1142,7 @@ int launch_wgrad(const WgradParams& p, cudaStream_t stream) {
   if (rc) return rc;
   const int grid = p.ngroups * p.nsplit;
   if (grid <= 0) return 0;
-  wgrad_kernel<<<grid, kWgThreads, kWgSmemBytes, stream>>>(p);
+  launch_k(wgrad_kernel, dim3(grid), dim3(kWgThreads), kWgSmemBytes, stream, p);
   return static_cast<int>(cudaGetLastError());
 }
 

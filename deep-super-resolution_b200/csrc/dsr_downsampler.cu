@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "dsr_elem.cuh"
+#include "dsr_launch.cuh"
 
 namespace dsr {
 
@@ -26,6 +27,7 @@ __global__ void downsample_fwd_kernel(const float* __restrict__ x, const float* 
                                       float* __restrict__ y, float* __restrict__ gy, float* __restrict__ loss, int C,
                                       int H, int W, int oh, int ow, DsTables t, int kTileOx, int kTileOy,
                                       const float* __restrict__ state) {
+  pdl_sync();
   extern __shared__ float sm[];
   if (state != nullptr && loss != nullptr) loss += __float_as_int(state[0]) - 1;
   const int f = t.factor, k = t.k, pad = t.pad;
@@ -84,6 +86,7 @@ __global__ void downsample_fwd_kernel(const float* __restrict__ x, const float* 
 
 __global__ void downsample_bwd_kernel(const float* __restrict__ gy, float* __restrict__ gx, int C, int H, int W, int oh,
                                       int ow, DsTables t) {
+  pdl_sync();
   const long long n = static_cast<long long>(C) * H * W;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -131,7 +134,7 @@ static int ds_launch(const float* x, const float* target, float* y, float* gy, f
   int kTileOx, kTileOy;
   ds_tile(t.factor, kTileOx, kTileOy);
   dim3 grid((ow + kTileOx - 1) / kTileOx, (oh + kTileOy - 1) / kTileOy, C);
-  downsample_fwd_kernel<<<grid, 256, smem, s>>>(x, target, y, gy, loss, C, H, W, oh, ow, t, kTileOx, kTileOy, state);
+  launch_k(downsample_fwd_kernel, dim3(grid), dim3(256), smem, s, x, target, y, gy, loss, C, H, W, oh, ow, t, kTileOx, kTileOy, state);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -146,7 +149,7 @@ int launch_downsample_bwd(const float* gy, float* gx, int C, int H, int W, int o
   const long long n = static_cast<long long>(C) * H * W;
   long long blocks = (n + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  downsample_bwd_kernel<<<static_cast<int>(blocks), 256, 0, s>>>(gy, gx, C, H, W, oh, ow, t);
+  launch_k(downsample_bwd_kernel, dim3(static_cast<int>(blocks)), dim3(256), 0, s, gy, gx, C, H, W, oh, ow, t);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -11,6 +11,7 @@
 //   final conv + Sigmoid                      models/DIP/skip.py:92-94
 //   Adam                                      utils/DIP.py:34 (torch.optim.Adam defaults)
 #include "dsr_elem.cuh"
+#include "dsr_launch.cuh"
 
 #include <cuda_fp16.h>
 
@@ -123,6 +124,7 @@ inline int grid_for(long long items, int threads, int cap_blocks) {
 // input pack: fp32 NCHW -> fp16 padded NHWC with reflected halo
 // =============================================================================================
 __global__ void input_pack_kernel(const float* __restrict__ z, __half* __restrict__ xpad, int C, int H, int W) {
+  pdl_sync();
   // block: 64 consecutive x of one row y; smem tile [C][65]
   extern __shared__ float tile[];
   const int tiles_x = (W + 63) / 64;
@@ -155,7 +157,7 @@ __global__ void input_pack_kernel(const float* __restrict__ z, __half* __restric
 
 int launch_input_pack(const float* z, void* xpad, int C, int H, int W, cudaStream_t s) {
   const int tiles_x = (W + 63) / 64;
-  input_pack_kernel<<<H * tiles_x, kThreads, C * 65 * sizeof(float), s>>>(z, static_cast<__half*>(xpad), C, H, W);
+  launch_k(input_pack_kernel, dim3(H * tiles_x), dim3(kThreads), C * 65 * sizeof(float), s, z, static_cast<__half*>(xpad), C, H, W);
   DSR_LAUNCH_CHECK();
 }
 
@@ -176,6 +178,7 @@ __device__ __forceinline__ void pix_advance(int y0, int x0, int u, int W, int& y
 
 __global__ void __launch_bounds__(kThreads) bn_act_kernel(const __half* __restrict__ raw, BnRef bn,
                                                           __half* __restrict__ act, int H, int W, int halo) {
+  pdl_sync();
   const int lane = threadIdx.x & 31;
   float scale[4], shift[4];
 #pragma unroll
@@ -227,8 +230,7 @@ inline int warp_grid(int H, int W, int cap_blocks) {      // one warp per kPixUn
 }
 
 int launch_bn_act(const void* raw, BnRef bn, void* act_pad, int H, int W, int halo, cudaStream_t s) {
-  bn_act_kernel<<<warp_grid(H, W, 148 * 8), kThreads, 0, s>>>(
-      static_cast<const __half*>(raw), bn, static_cast<__half*>(act_pad), H, W, halo);
+  launch_k(bn_act_kernel, dim3(warp_grid(H, W, 148 * 8)), dim3(kThreads), 0, s, static_cast<const __half*>(raw), bn, static_cast<__half*>(act_pad), H, W, halo);
   DSR_LAUNCH_CHECK();
 }
 
@@ -238,6 +240,7 @@ int launch_bn_act(const void* raw, BnRef bn, void* act_pad, int H, int W, int ha
 template <int CIN>
 __global__ void skip_conv_kernel(const __half* __restrict__ xpad, const float* __restrict__ w, float* __restrict__ sraw,
                                  float* __restrict__ stats, int H, int W) {
+  pdl_sync();
   constexpr int G = CIN / 8;   // lanes per pixel
   const int g = threadIdx.x % G;
   float wr[4][8];
@@ -289,9 +292,9 @@ int launch_skip_conv(const void* xpad, int Cin, const float* w, float* sraw, flo
   const long long items = static_cast<long long>(H) * W * (Cin / 8);
   const int grid = grid_for(items, kThreads, 148 * 8);
   if (Cin == 32)
-    skip_conv_kernel<32><<<grid, kThreads, 0, s>>>(static_cast<const __half*>(xpad), w, sraw, stats, H, W);
+    launch_k(skip_conv_kernel<32>, dim3(grid), dim3(kThreads), 0, s, static_cast<const __half*>(xpad), w, sraw, stats, H, W);
   else if (Cin == 128)
-    skip_conv_kernel<128><<<grid, kThreads, 0, s>>>(static_cast<const __half*>(xpad), w, sraw, stats, H, W);
+    launch_k(skip_conv_kernel<128>, dim3(grid), dim3(kThreads), 0, s, static_cast<const __half*>(xpad), w, sraw, stats, H, W);
   else
     return -2;
   DSR_LAUNCH_CHECK();
@@ -385,6 +388,7 @@ __device__ __forceinline__ void skip_act4(const SkipConst& sc, const float* __re
 constexpr int kUpUnroll = 2;     // 2x2 blocks in flight per warp
 
 __global__ void __launch_bounds__(kThreads, 3) upcat_stats_kernel(UpcatArgs a) {
+  pdl_sync();
   __shared__ SkipConst sc;
   skip_const_init(&sc, a, nullptr, false);
   const int lane = threadIdx.x & 31;
@@ -457,6 +461,7 @@ __device__ __forceinline__ void cat_coeffs(const UpcatArgs& a, int c, float& mea
 }
 
 __global__ void __launch_bounds__(kThreads, 3) upcat_apply_kernel(UpcatArgs a) {
+  pdl_sync();
   __shared__ SkipConst sc;
   skip_const_init(&sc, a, nullptr, true);
   const int lane = threadIdx.x & 31;
@@ -538,11 +543,11 @@ static int up_grid(const UpcatArgs& a, int cap) {
   return static_cast<int>(blocks < 1 ? 1 : blocks);
 }
 int launch_upcat_stats(const UpcatArgs& a, cudaStream_t s) {
-  upcat_stats_kernel<<<up_grid(a, 148 * 6), kThreads, 0, s>>>(a);
+  launch_k(upcat_stats_kernel, dim3(up_grid(a, 148 * 6)), dim3(kThreads), 0, s, a);
   DSR_LAUNCH_CHECK();
 }
 int launch_upcat_apply(const UpcatArgs& a, cudaStream_t s) {
-  upcat_apply_kernel<<<up_grid(a, 148 * 12), kThreads, 0, s>>>(a);
+  launch_k(upcat_apply_kernel, dim3(up_grid(a, 148 * 12)), dim3(kThreads), 0, s, a);
   DSR_LAUNCH_CHECK();
 }
 
@@ -551,6 +556,7 @@ int launch_upcat_apply(const UpcatArgs& a, cudaStream_t s) {
 // =============================================================================================
 __global__ void final_conv_kernel(const __half* __restrict__ act, const float* __restrict__ w,
                                   const float* __restrict__ b, float* __restrict__ out, int H, int W) {
+  pdl_sync();
   // block: 16 pixels per pass x 16 lanes; results staged so that stores are contiguous per channel
   __shared__ float stage[3][kThreads / 16];
   const int g = threadIdx.x & 15;
@@ -597,8 +603,7 @@ __global__ void final_conv_kernel(const __half* __restrict__ act, const float* _
 
 int launch_final_conv(const void* act_pad, const float* w, const float* b, float* out, int H, int W, cudaStream_t s) {
   const long long items = static_cast<long long>(H) * W * 16;
-  final_conv_kernel<<<grid_for(items, kThreads, 148 * 16), kThreads, 0, s>>>(static_cast<const __half*>(act_pad), w, b,
-                                                                            out, H, W);
+  launch_k(final_conv_kernel, dim3(grid_for(items, kThreads, 148 * 16)), dim3(kThreads), 0, s, static_cast<const __half*>(act_pad), w, b, out, H, W);
   DSR_LAUNCH_CHECK();
 }
 
@@ -613,6 +618,7 @@ __global__ void __launch_bounds__(kThreads, 3) final_bwd_kernel(const float* __r
                                                                 const float* __restrict__ w, __half* __restrict__ dact,
                                                                 float* __restrict__ dw, float* __restrict__ db,
                                                                 const float* __restrict__ gs, int H, int W) {
+  pdl_sync();
   const int lane = threadIdx.x & 31;
   const int c0 = lane * 4;
   const float S = gs[0], invS = gs[1];
@@ -687,8 +693,7 @@ int launch_final_bwd(const float* gout, const float* out, const void* act_pad, c
   const long long npix = static_cast<long long>(H) * W;
   long long blocks = (npix + 255) / 256;
   if (blocks > 148 * 6) blocks = 148 * 6;
-  final_bwd_kernel<<<static_cast<int>(blocks), kThreads, 0, s>>>(
-      gout, out, static_cast<const __half*>(act_pad), w, static_cast<__half*>(dact_pad), dw, db, gs, H, W);
+  launch_k(final_bwd_kernel, dim3(static_cast<int>(blocks)), dim3(kThreads), 0, s, gout, out, static_cast<const __half*>(act_pad), w, static_cast<__half*>(dact_pad), dw, db, gs, H, W);
   DSR_LAUNCH_CHECK();
 }
 
@@ -703,6 +708,7 @@ __global__ void __launch_bounds__(kThreads, 3) bn_act_final_kernel(const __half*
                                                                    const float* __restrict__ w,
                                                                    const float* __restrict__ b,
                                                                    float* __restrict__ out, int npix) {
+  pdl_sync();
   const int lane = threadIdx.x & 31;
   const int c0 = lane * 4;
   float scale[4], shift[4], wr[3][4];
@@ -759,13 +765,13 @@ __global__ void __launch_bounds__(kThreads, 3) bn_act_final_kernel(const __half*
 
 int launch_bn_act_final(const void* raw, BnRef bn, const float* w, const float* b, float* out, int H, int W,
                         cudaStream_t s) {
-  bn_act_final_kernel<<<warp_grid(H, W, 148 * 8), kThreads, 0, s>>>(static_cast<const __half*>(raw), bn, w, b, out,
-                                                                   H * W);
+  launch_k(bn_act_final_kernel, dim3(warp_grid(H, W, 148 * 8)), dim3(kThreads), 0, s, static_cast<const __half*>(raw), bn, w, b, out, H * W);
   DSR_LAUNCH_CHECK();
 }
 
 template <bool APPLY>
 __global__ void __launch_bounds__(kThreads, 2) bn_bwd_top_kernel(TopBwdArgs a) {
+  pdl_sync();
   const int lane = threadIdx.x & 31;
   const int c0 = lane * 4;
   const float S = a.gs[0], invS = a.gs[1];
@@ -883,14 +889,14 @@ int launch_bn_bwd_top_stats(const TopBwdArgs& a, cudaStream_t s) {
   const long long npix = static_cast<long long>(a.H) * a.W;
   long long blocks = (npix + 255) / 256;
   if (blocks > 148 * 4) blocks = 148 * 4;
-  bn_bwd_top_kernel<false><<<static_cast<int>(blocks), kThreads, 0, s>>>(a);
+  launch_k(bn_bwd_top_kernel<false>, dim3(static_cast<int>(blocks)), dim3(kThreads), 0, s, a);
   DSR_LAUNCH_CHECK();
 }
 int launch_bn_bwd_top_apply(const TopBwdArgs& a, cudaStream_t s) {
   const long long npix = static_cast<long long>(a.H) * a.W;
   long long blocks = (npix + 255) / 256;
   if (blocks > 148 * 6) blocks = 148 * 6;
-  bn_bwd_top_kernel<true><<<static_cast<int>(blocks), kThreads, 0, s>>>(a);
+  launch_k(bn_bwd_top_kernel<true>, dim3(static_cast<int>(blocks)), dim3(kThreads), 0, s, a);
   DSR_LAUNCH_CHECK();
 }
 
@@ -899,6 +905,7 @@ int launch_bn_bwd_top_apply(const TopBwdArgs& a, cudaStream_t s) {
 // =============================================================================================
 template <bool APPLY, bool HAS_DS>
 __global__ void __launch_bounds__(kThreads, HAS_DS ? 2 : 3) bn_bwd_kernel(BnBwdArgs a) {
+  pdl_sync();
   const int lane = threadIdx.x & 31;
   const int c0 = lane * 4;
   // xhat = r * xa + xb;  y = ga * xhat + be;  APPLY: dr = k1 * (dy - c1 - xhat * c2)
@@ -1030,6 +1037,7 @@ __global__ void __launch_bounds__(kThreads, HAS_DS ? 2 : 3) bn_bwd_kernel(BnBwdA
 // Groups that touch the folded border (3x3 dgrad inputs) take the per-pixel path with halo gathering.
 template <bool APPLY>
 __global__ void __launch_bounds__(kThreads, 3) bn_bwd_fast_kernel(BnBwdArgs a) {
+  pdl_sync();
   const int lane = threadIdx.x & 31;
   const int c0 = lane * 4;
   float k1[4], sh[4], A[4], B[4], s1[4], s2[4], mean_[4], rstd_[4];
@@ -1138,21 +1146,21 @@ static int fast_grid(int H, int W, int cap) {
 int launch_bn_bwd_stats(const BnBwdArgs& a, cudaStream_t s) {
   const int grid = warp_grid(a.H, a.W, 148 * 4);
   if (a.ds == nullptr && (a.W & 3) == 0 && a.W >= 4) {
-    bn_bwd_fast_kernel<false><<<fast_grid(a.H, a.W, 148 * 8), kThreads, 0, s>>>(a);
+    launch_k(bn_bwd_fast_kernel<false>, dim3(fast_grid(a.H, a.W, 148 * 8)), dim3(kThreads), 0, s, a);
     DSR_LAUNCH_CHECK();
   }
-  if (a.ds != nullptr) bn_bwd_kernel<false, true><<<grid, kThreads, 0, s>>>(a);
-  else bn_bwd_kernel<false, false><<<grid, kThreads, 0, s>>>(a);
+  if (a.ds != nullptr) launch_k(bn_bwd_kernel<false, true>, dim3(grid), dim3(kThreads), 0, s, a);
+  else launch_k(bn_bwd_kernel<false, false>, dim3(grid), dim3(kThreads), 0, s, a);
   DSR_LAUNCH_CHECK();
 }
 int launch_bn_bwd_apply(const BnBwdArgs& a, cudaStream_t s) {
   const int grid = warp_grid(a.H, a.W, 148 * 8);
   if (a.ds == nullptr && (a.W & 3) == 0 && a.W >= 4) {
-    bn_bwd_fast_kernel<true><<<fast_grid(a.H, a.W, 148 * 16), kThreads, 0, s>>>(a);
+    launch_k(bn_bwd_fast_kernel<true>, dim3(fast_grid(a.H, a.W, 148 * 16)), dim3(kThreads), 0, s, a);
     DSR_LAUNCH_CHECK();
   }
-  if (a.ds != nullptr) bn_bwd_kernel<true, true><<<grid, kThreads, 0, s>>>(a);
-  else bn_bwd_kernel<true, false><<<grid, kThreads, 0, s>>>(a);
+  if (a.ds != nullptr) launch_k(bn_bwd_kernel<true, true>, dim3(grid), dim3(kThreads), 0, s, a);
+  else launch_k(bn_bwd_kernel<true, false>, dim3(grid), dim3(kThreads), 0, s, a);
   DSR_LAUNCH_CHECK();
 }
 
@@ -1180,6 +1188,7 @@ __device__ __forceinline__ void fold_gather4(const __half* gp, int C, int H, int
 
 template <bool APPLY>
 __global__ void __launch_bounds__(kThreads, 2) upcat_bwd_kernel(UpcatBwdArgs a) {
+  pdl_sync();
   const UpcatArgs& f = a.f;
   __shared__ SkipConst sc;
   skip_const_init(&sc, f, APPLY ? a.cbstats : nullptr, true);
@@ -1319,11 +1328,11 @@ static int upb_grid(const UpcatArgs& f, int cap) {
   return static_cast<int>(blocks < 1 ? 1 : blocks);
 }
 int launch_upcat_bwd_stats(const UpcatBwdArgs& a, cudaStream_t s) {
-  upcat_bwd_kernel<false><<<upb_grid(a.f, 148 * 6), kThreads, 0, s>>>(a);
+  launch_k(upcat_bwd_kernel<false>, dim3(upb_grid(a.f, 148 * 6)), dim3(kThreads), 0, s, a);
   DSR_LAUNCH_CHECK();
 }
 int launch_upcat_bwd_apply(const UpcatBwdArgs& a, cudaStream_t s) {
-  upcat_bwd_kernel<true><<<upb_grid(a.f, 148 * 12), kThreads, 0, s>>>(a);
+  launch_k(upcat_bwd_kernel<true>, dim3(upb_grid(a.f, 148 * 12)), dim3(kThreads), 0, s, a);
   DSR_LAUNCH_CHECK();
 }
 
@@ -1335,6 +1344,7 @@ __global__ void skip_bwd_kernel(const float* __restrict__ dsy, const float* __re
                                 const float* __restrict__ sbstats, const __half* __restrict__ xpad,
                                 float* __restrict__ dsraw, float* __restrict__ dw, float* __restrict__ dgamma,
                                 float* __restrict__ dbeta, const float* __restrict__ gs, int H, int W) {
+  pdl_sync();
   constexpr int G = CIN / 8;
   const float invS = gs[1];
   const int g = threadIdx.x % G;
@@ -1393,11 +1403,9 @@ int launch_skip_bwd(const float* dsy, const float* sraw, BnRef bn_skip, const fl
   const long long items = static_cast<long long>(H) * W * (Cin / 8);
   const int grid = grid_for(items, kThreads, 148 * 2);
   if (Cin == 32)
-    skip_bwd_kernel<32><<<grid, kThreads, 0, s>>>(dsy, sraw, bn_skip, sbstats, static_cast<const __half*>(xpad), dsraw,
-                                                  dw, dgamma, dbeta, gs, H, W);
+    launch_k(skip_bwd_kernel<32>, dim3(grid), dim3(kThreads), 0, s, dsy, sraw, bn_skip, sbstats, static_cast<const __half*>(xpad), dsraw, dw, dgamma, dbeta, gs, H, W);
   else if (Cin == 128)
-    skip_bwd_kernel<128><<<grid, kThreads, 0, s>>>(dsy, sraw, bn_skip, sbstats, static_cast<const __half*>(xpad), dsraw,
-                                                   dw, dgamma, dbeta, gs, H, W);
+    launch_k(skip_bwd_kernel<128>, dim3(grid), dim3(kThreads), 0, s, dsy, sraw, bn_skip, sbstats, static_cast<const __half*>(xpad), dsraw, dw, dgamma, dbeta, gs, H, W);
   else
     return -2;
   DSR_LAUNCH_CHECK();
@@ -1466,6 +1474,7 @@ __device__ __forceinline__ void q_stencil(const __half* d, long long sy, int h, 
 }
 
 __global__ void __launch_bounds__(kThreads) upcat_stats_lowres_kernel(UpcatArgs a) {
+  pdl_sync();
   const int lane = threadIdx.x & 31;
   float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
   const int npix = a.h * a.w;
@@ -1500,6 +1509,7 @@ __global__ void __launch_bounds__(kThreads) upcat_stats_lowres_kernel(UpcatArgs 
 
 // forward statistics of the 4 skip channels of the concat tensor (one thread per pixel)
 __global__ void __launch_bounds__(kThreads) skipcat_stats_kernel(UpcatArgs a) {
+  pdl_sync();
   __shared__ SkipConst sc;
   skip_const_init(&sc, a, nullptr, false);
   float s4[4] = {0, 0, 0, 0}, q4[4] = {0, 0, 0, 0};
@@ -1529,16 +1539,17 @@ __global__ void __launch_bounds__(kThreads) skipcat_stats_kernel(UpcatArgs a) {
 int launch_upcat_stats_lowres(const UpcatArgs& a, cudaStream_t s) {
   long long blocks = (static_cast<long long>(a.h) * a.w + 7) / 8;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  upcat_stats_lowres_kernel<<<static_cast<int>(blocks < 1 ? 1 : blocks), kThreads, 0, s>>>(a);
+  launch_k(upcat_stats_lowres_kernel, dim3(static_cast<int>(blocks < 1 ? 1 : blocks)), dim3(kThreads), 0, s, a);
   long long b2 = (static_cast<long long>(a.H) * a.W + kThreads - 1) / kThreads;
   if (b2 > 148 * 4) b2 = 148 * 4;
-  skipcat_stats_kernel<<<static_cast<int>(b2 < 1 ? 1 : b2), kThreads, 0, s>>>(a);
+  launch_k(skipcat_stats_kernel, dim3(static_cast<int>(b2 < 1 ? 1 : b2)), dim3(kThreads), 0, s, a);
   DSR_LAUNCH_CHECK();
 }
 
 // backward, pass A: t = U^T fold(dc) for the 128 upsampled channels (the only high-resolution read), written to
 // tbuf [h][w][128]; accumulates S1 = sum t and S2' = sum d t into cbstats[c], cbstats[144 + c]
 __global__ void __launch_bounds__(kThreads, 3) upT_gather_kernel(UpcatBwdArgs a) {
+  pdl_sync();
   const UpcatArgs& f = a.f;
   const int lane = threadIdx.x & 31;
   const int c0 = lane * 4;
@@ -1600,6 +1611,7 @@ __global__ void __launch_bounds__(kThreads, 3) upT_gather_kernel(UpcatBwdArgs a)
 
 // backward, pass C (low resolution): ddeep = k1 ( t - c1 w - c2 rstd (Q d - mean w) ); BN(132) parameter gradients
 __global__ void __launch_bounds__(kThreads) upcat_bwd_lowres_kernel(UpcatBwdArgs a, __half* __restrict__ ddeep) {
+  pdl_sync();
   const UpcatArgs& f = a.f;
   const int lane = threadIdx.x & 31;
   const int c0 = lane * 4;
@@ -1643,6 +1655,7 @@ __global__ void __launch_bounds__(kThreads) upcat_bwd_lowres_kernel(UpcatBwdArgs
 // backward of the 4 skip channels of the concat tensor (one thread per pixel): BN(132) + LeakyReLU' of the skip branch
 template <bool APPLY>
 __global__ void __launch_bounds__(kThreads) skipcat_bwd_kernel(UpcatBwdArgs a) {
+  pdl_sync();
   const UpcatArgs& f = a.f;
   __shared__ SkipConst sc;
   skip_const_init(&sc, f, APPLY ? a.cbstats : nullptr, true);
@@ -1705,10 +1718,10 @@ int launch_upcat_bwd_lowres(const UpcatBwdArgs& a, void* ddeep_pad, cudaStream_t
   long long hi = (static_cast<long long>(f.H) * f.W + kThreads - 1) / kThreads;
   if (hi > 148 * 4) hi = 148 * 4;
   if (hi < 1) hi = 1;
-  upT_gather_kernel<<<static_cast<int>(lo), kThreads, 0, s>>>(a);
-  skipcat_bwd_kernel<false><<<static_cast<int>(hi), kThreads, 0, s>>>(a);
-  upcat_bwd_lowres_kernel<<<static_cast<int>(lo), kThreads, 0, s>>>(a, static_cast<__half*>(ddeep_pad));
-  skipcat_bwd_kernel<true><<<static_cast<int>(hi), kThreads, 0, s>>>(a);
+  launch_k(upT_gather_kernel, dim3(static_cast<int>(lo)), dim3(kThreads), 0, s, a);
+  launch_k(skipcat_bwd_kernel<false>, dim3(static_cast<int>(hi)), dim3(kThreads), 0, s, a);
+  launch_k(upcat_bwd_lowres_kernel, dim3(static_cast<int>(lo)), dim3(kThreads), 0, s, a, static_cast<__half*>(ddeep_pad));
+  launch_k(skipcat_bwd_kernel<true>, dim3(static_cast<int>(hi)), dim3(kThreads), 0, s, a);
   DSR_LAUNCH_CHECK();
 }
 
@@ -1717,6 +1730,7 @@ int launch_upcat_bwd_lowres(const UpcatBwdArgs& a, void* ddeep_pad, cudaStream_t
 // =============================================================================================
 __global__ void upsample_bwd_kernel(const __half* __restrict__ dup, int H, int W,
                                     __half* __restrict__ ddeep, int h, int w) {
+  pdl_sync();
   const int g = threadIdx.x & 15;
   const long long npix = static_cast<long long>(h) * w;
   const int Wp = W + 2, wp = w + 2;
@@ -1762,8 +1776,7 @@ __global__ void upsample_bwd_kernel(const __half* __restrict__ dup, int H, int W
 
 int launch_upsample_bwd(const void* dup_pad, int H, int W, void* ddeep_pad, int h, int w, cudaStream_t s) {
   const long long items = static_cast<long long>(h) * w * 16;
-  upsample_bwd_kernel<<<grid_for(items, kThreads, 148 * 16), kThreads, 0, s>>>(
-      static_cast<const __half*>(dup_pad), H, W, static_cast<__half*>(ddeep_pad), h, w);
+  launch_k(upsample_bwd_kernel, dim3(grid_for(items, kThreads, 148 * 16)), dim3(kThreads), 0, s, static_cast<const __half*>(dup_pad), H, W, static_cast<__half*>(ddeep_pad), h, w);
   DSR_LAUNCH_CHECK();
 }
 
@@ -1774,6 +1787,7 @@ __device__ __forceinline__ int ref_ci(const PackDesc& d, int j) { return d.perm 
 
 __global__ void pack_weights_kernel(const float* __restrict__ params, __half* __restrict__ arena,
                                     const PackDesc* __restrict__ table, int nlayers) {
+  pdl_sync();
   const PackDesc d = table[blockIdx.y];
   const int taps = d.k * d.k;
   const long long nf = static_cast<long long>(taps) * 128 * d.cin_pad;
@@ -1802,12 +1816,13 @@ __global__ void pack_weights_kernel(const float* __restrict__ params, __half* __
 
 int launch_pack_weights(const float* params, void* arena, const PackDesc* table_dev, int nlayers, cudaStream_t s) {
   dim3 grid(64, nlayers);
-  pack_weights_kernel<<<grid, kThreads, 0, s>>>(params, static_cast<__half*>(arena), table_dev, nlayers);
+  launch_k(pack_weights_kernel, dim3(grid), dim3(kThreads), 0, s, params, static_cast<__half*>(arena), table_dev, nlayers);
   DSR_LAUNCH_CHECK();
 }
 
 __global__ void unpack_wgrad_kernel(const float* __restrict__ garena, float* __restrict__ grads,
                                     const PackDesc* __restrict__ table, const float* __restrict__ gs) {
+  pdl_sync();
   const PackDesc d = table[blockIdx.y];
   const float invS = gs[1];
   const int taps = d.k * d.k;
@@ -1825,7 +1840,7 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ garena, float* __r
 int launch_unpack_wgrad(const float* garena, float* grads, const PackDesc* table_dev, int nlayers, const float* gs,
                         cudaStream_t s) {
   dim3 grid(32, nlayers);
-  unpack_wgrad_kernel<<<grid, kThreads, 0, s>>>(garena, grads, table_dev, gs);
+  launch_k(unpack_wgrad_kernel, dim3(grid), dim3(kThreads), 0, s, garena, grads, table_dev, gs);
   DSR_LAUNCH_CHECK();
 }
 
@@ -1834,12 +1849,14 @@ int launch_unpack_wgrad(const float* garena, float* grads, const PackDesc* table
 // adapt S for the next pass (max |S dR| kept within [2^9, 2^14], fp16 max is 65504)
 // =============================================================================================
 __global__ void grad_sanitize_kernel(float* __restrict__ grads, long long n, const float* __restrict__ gs) {
+  pdl_sync();
   if (gs[3] == 0.f) return;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x)
     grads[i] = 0.f;
 }
 __global__ void grad_scale_update_kernel(float* __restrict__ gs) {
+  pdl_sync();
   float S = gs[0];
   gs[6] = S;                   // scale used by the pass that just finished
   const float amax = __uint_as_float(reinterpret_cast<unsigned int*>(gs)[2]);
@@ -1856,8 +1873,8 @@ __global__ void grad_scale_update_kernel(float* __restrict__ gs) {
   gs[5] = bad ? gs[5] + 1.f : gs[5];
 }
 int launch_grad_scale_finish(float* grads, long long n, float* gs, cudaStream_t s) {
-  grad_sanitize_kernel<<<148 * 4, kThreads, 0, s>>>(grads, n, gs);
-  grad_scale_update_kernel<<<1, 1, 0, s>>>(gs);
+  launch_k(grad_sanitize_kernel, dim3(148 * 4), dim3(kThreads), 0, s, grads, n, gs);
+  launch_k(grad_scale_update_kernel, dim3(1), dim3(1), 0, s, gs);
   DSR_LAUNCH_CHECK();
 }
 
@@ -1867,6 +1884,7 @@ int launch_grad_scale_finish(float* grads, long long n, float* gs, cudaStream_t 
 // =============================================================================================
 __global__ void step_begin_kernel(float* __restrict__ state, float* __restrict__ loss_base, int t_set, float lr,
                                   float b1, float b2) {
+  pdl_sync();
   const int t = (t_set > 0) ? t_set : __float_as_int(state[0]) + 1;
   state[0] = __int_as_float(t);
   state[1] = static_cast<float>(static_cast<double>(lr) / (1.0 - pow(static_cast<double>(b1), static_cast<double>(t))));
@@ -1874,7 +1892,7 @@ __global__ void step_begin_kernel(float* __restrict__ state, float* __restrict__
   if (loss_base != nullptr) loss_base[t - 1] = 0.f;
 }
 int launch_step_begin(float* state, float* loss_base, int t_set, float lr, float b1, float b2, cudaStream_t s) {
-  step_begin_kernel<<<1, 1, 0, s>>>(state, loss_base, t_set, lr, b1, b2);
+  launch_k(step_begin_kernel, dim3(1), dim3(1), 0, s, state, loss_base, t_set, lr, b1, b2);
   DSR_LAUNCH_CHECK();
 }
 
@@ -1883,6 +1901,7 @@ int launch_step_begin(float* state, float* loss_base, int t_set, float lr, float
 // =============================================================================================
 __global__ void bn_running_kernel(const BnRunDesc* __restrict__ table, const float* __restrict__ ws,
                                   const float* __restrict__ params, float* __restrict__ bnbuf, float momentum) {
+  pdl_sync();
   const BnRunDesc d = table[blockIdx.x];
   const float* stats = ws + d.stats_off;
   float* rm = bnbuf + d.rm_off;
@@ -1900,7 +1919,7 @@ __global__ void bn_running_kernel(const BnRunDesc* __restrict__ table, const flo
 
 int launch_bn_running(const BnRunDesc* table_dev, int nbn, const float* ws_f32, const float* params, float* bn_buffers,
                       float momentum, cudaStream_t s) {
-  bn_running_kernel<<<nbn, 160, 0, s>>>(table_dev, ws_f32, params, bn_buffers, momentum);
+  launch_k(bn_running_kernel, dim3(nbn), dim3(160), 0, s, table_dev, ws_f32, params, bn_buffers, momentum);
   DSR_LAUNCH_CHECK();
 }
 
@@ -1910,6 +1929,7 @@ int launch_bn_running(const BnRunDesc* table_dev, int nbn, const float* ws_f32, 
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, long long n, float step_size, float b1, float b2, float eps,
                             float inv_sqrt_bc2, const float* __restrict__ state) {
+  pdl_sync();
   if (state != nullptr) {            // bias corrections of the device-tracked iteration (step_begin_kernel)
     step_size = state[1];
     inv_sqrt_bc2 = state[2];
@@ -1952,8 +1972,7 @@ int launch_adam(float* p, const float* g, float* m, float* v, long long n, float
   const double bc2 = 1.0 - pow(static_cast<double>(b2), t);
   const float step_size = static_cast<float>(static_cast<double>(lr) / bc1);
   const float inv_sqrt_bc2 = static_cast<float>(1.0 / sqrt(bc2));
-  adam_kernel<<<grid_for(n / 4 + 1, kThreads, 148 * 8), kThreads, 0, s>>>(p, g, m, v, n, step_size, b1, b2, eps,
-                                                                         inv_sqrt_bc2, state);
+  launch_k(adam_kernel, dim3(grid_for(n / 4 + 1, kThreads, 148 * 8)), dim3(kThreads), 0, s, p, g, m, v, n, step_size, b1, b2, eps, inv_sqrt_bc2, state);
   DSR_LAUNCH_CHECK();
 }
 
@@ -1974,6 +1993,7 @@ __device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uin
 
 __global__ void perturb_kernel(const float* __restrict__ zs, float* __restrict__ z, long long n, float sigma,
                                unsigned long long seed, unsigned long long offset, const float* __restrict__ state) {
+  pdl_sync();
   const long long n4 = (n + 3) >> 2;
   if (state != nullptr)              // counter block of the device-tracked iteration t: (t - 1) * n4
     offset = static_cast<unsigned long long>(__float_as_int(state[0]) - 1) * static_cast<unsigned long long>(n4);
@@ -2003,8 +2023,7 @@ __global__ void perturb_kernel(const float* __restrict__ zs, float* __restrict__
 
 int launch_perturb(const float* z_saved, float* z, long long n, float sigma, unsigned long long seed,
                    unsigned long long offset, cudaStream_t s, const float* state) {
-  perturb_kernel<<<grid_for((n + 3) / 4, kThreads, 148 * 8), kThreads, 0, s>>>(z_saved, z, n, sigma, seed, offset,
-                                                                              state);
+  launch_k(perturb_kernel, dim3(grid_for((n + 3) / 4, kThreads, 148 * 8)), dim3(kThreads), 0, s, z_saved, z, n, sigma, seed, offset, state);
   DSR_LAUNCH_CHECK();
 }
 

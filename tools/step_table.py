@@ -30,3 +30,9 @@ T = sum(tot.values())
 print(f'{size}^2: {T:.0f} us per fwd+bwd over {len(rows) // N} launches; launches under 8 us sum to {small:.0f} us')
 for k, v in sorted(tot.items(), key=lambda kv: -kv[1]):
     print(f'{v:9.1f} us {100 * v / T:5.1f}%  n={cnt[k] // N:3d}  {k}')
+if os.environ.get('STEP_TABLE_ORDERED', '1') != '0':
+    per = len(rows) // N
+    print('--- launches in order (mean us over %d iterations) ---' % N)
+    for i in range(per):
+        t = sum(float(rows[k * per + i][0]) for k in range(N)) / N
+        print(f'{i:4d} {t:8.1f}  {rows[i][1][:110]}')
