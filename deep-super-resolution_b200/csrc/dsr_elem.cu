@@ -1426,6 +1426,12 @@ int launch_skip_bwd(const float* dsy, const float* sraw, BnRef bn_skip, const fl
 // 1-D pieces for source index q (n_src sources, n_out outputs): cw[t] = U[2q-1+t][q] (t = 0..3), w = sum_t cw[t],
 // Q[k] = sum_t U[o_t][q] U[o_t][q-1+k] (k = 0..2)
 __device__ __forceinline__ void up_q(int q, int n_src, int n_out, float (&cw)[4], float& w, float (&Q)[3]) {
+  if (q >= 1 && 2 * q + 2 < n_out && q + 1 < n_src) {      // interior: no clamped source, all 4 outputs exist
+    cw[0] = 0.25f; cw[1] = 0.75f; cw[2] = 0.75f; cw[3] = 0.25f;
+    w = 2.f;
+    Q[0] = 0.375f; Q[1] = 1.25f; Q[2] = 0.375f;
+    return;
+  }
   w = 0.f;
   Q[0] = Q[1] = Q[2] = 0.f;
 #pragma unroll
@@ -1473,20 +1479,20 @@ __device__ __forceinline__ void q_stencil(const __half* d, long long sy, int h, 
   }
 }
 
-__global__ void __launch_bounds__(kThreads) upcat_stats_lowres_kernel(UpcatArgs a) {
-  pdl_sync();
+__device__ __forceinline__ void upcat_stats_lowres_body(const UpcatArgs& a, int vblock, int vgrid) {
   const int lane = threadIdx.x & 31;
   float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
   const int npix = a.h * a.w;
-  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const int warps = (vgrid * blockDim.x) >> 5;
   const __half* d = static_cast<const __half*>(a.deep);
-  for (int pix = ((blockIdx.x * blockDim.x) + threadIdx.x) >> 5; pix < npix; pix += warps) {
+  for (int pix = ((vblock * blockDim.x) + threadIdx.x) >> 5; pix < npix; pix += warps) {
     const int qy = pix / a.w, qx = pix - qy * a.w;
     float cwy[4], cwx[4], wy, wx, Qy[3], Qx[3];
     up_q(qy, a.h, a.H, cwy, wy, Qy);
     up_q(qx, a.w, a.W, cwx, wx, Qx);
     float qd[4], c[4] = {0, 0, 0, 0};
     q_stencil(d, a.deep_sy, a.h, a.w, qy, qx, Qy, Qx, lane, qd, c);
+    stg8(static_cast<__half*>(a.qd) + static_cast<long long>(pix) * 128 + lane * 4, pack4h(qd));   // for the backward
     const float w2 = wy * wx;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -1508,14 +1514,13 @@ __global__ void __launch_bounds__(kThreads) upcat_stats_lowres_kernel(UpcatArgs 
 }
 
 // forward statistics of the 4 skip channels of the concat tensor (one thread per pixel)
-__global__ void __launch_bounds__(kThreads) skipcat_stats_kernel(UpcatArgs a) {
-  pdl_sync();
+__device__ __forceinline__ void skipcat_stats_body(const UpcatArgs& a, int vblock, int vgrid) {
   __shared__ SkipConst sc;
   skip_const_init(&sc, a, nullptr, false);
   float s4[4] = {0, 0, 0, 0}, q4[4] = {0, 0, 0, 0};
   const long long npix = static_cast<long long>(a.H) * a.W;
-  for (long long pix = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; pix < npix;
-       pix += static_cast<long long>(gridDim.x) * blockDim.x) {
+  for (long long pix = static_cast<long long>(vblock) * blockDim.x + threadIdx.x; pix < npix;
+       pix += static_cast<long long>(vgrid) * blockDim.x) {
     float sv[4], xh[4], yv[4];
     skip_act4(sc, a.sraw, pix, sv, xh, yv);
 #pragma unroll
@@ -1536,126 +1541,225 @@ __global__ void __launch_bounds__(kThreads) skipcat_stats_kernel(UpcatArgs a) {
   else if (threadIdx.x < 8) atomicAdd(&a.cat_stats[144 + 128 + threadIdx.x - 4], red[threadIdx.x]);
 }
 
+// one launch: blocks [0, nb_lo) take the 128 upsampled channels (low-resolution domain), the rest the 4 skip channels
+__global__ void __launch_bounds__(kThreads) upcat_stats_merged_kernel(UpcatArgs a, int nb_lo) {
+  pdl_sync();
+  if (static_cast<int>(blockIdx.x) < nb_lo) upcat_stats_lowres_body(a, blockIdx.x, nb_lo);
+  else skipcat_stats_body(a, blockIdx.x - nb_lo, gridDim.x - nb_lo);
+}
+
 int launch_upcat_stats_lowres(const UpcatArgs& a, cudaStream_t s) {
   long long blocks = (static_cast<long long>(a.h) * a.w + 7) / 8;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  launch_k(upcat_stats_lowres_kernel, dim3(static_cast<int>(blocks < 1 ? 1 : blocks)), dim3(kThreads), 0, s, a);
+  if (blocks < 1) blocks = 1;
   long long b2 = (static_cast<long long>(a.H) * a.W + kThreads - 1) / kThreads;
-  if (b2 > 148 * 4) b2 = 148 * 4;
-  launch_k(skipcat_stats_kernel, dim3(static_cast<int>(b2 < 1 ? 1 : b2)), dim3(kThreads), 0, s, a);
+  if (b2 > 148) b2 = 148;
+  if (b2 < 1) b2 = 1;
+  launch_k(upcat_stats_merged_kernel, dim3(static_cast<int>(blocks + b2)), dim3(kThreads), 0, s, a,
+           static_cast<int>(blocks));
   DSR_LAUNCH_CHECK();
 }
 
+// weight of high-resolution index o on low-resolution index q (forward: out[o] = l0 in[i0] + l1 in[i1])
+__device__ __forceinline__ float up_weight(int o, int q, int n_src) {
+  int i0, i1;
+  float l0, l1;
+  up_src(o, n_src, i0, i1, l0, l1);
+  return (i0 == q ? l0 : 0.f) + (i1 == q ? l1 : 0.f);
+}
+
 // backward, pass A: t = U^T fold(dc) for the 128 upsampled channels (the only high-resolution read), written to
-// tbuf [h][w][128]; accumulates S1 = sum t and S2' = sum d t into cbstats[c], cbstats[144 + c]
-__global__ void __launch_bounds__(kThreads, 3) upT_gather_kernel(UpcatBwdArgs a) {
-  pdl_sync();
+// tbuf [h][w][128]; accumulates S1 = sum t and S2' = sum d t into cbstats[c], cbstats[144 + c], and the skip-channel
+// sums (sum dc, sum dc * xhat of channels 128..131) into cbstats[128 + o], cbstats[144 + 128 + o].
+//
+// A block owns a tile of kGtW x kGtH low-resolution pixels.  Phase 1 stages the (2 kGtW + 2) x (2 kGtH + 2)
+// high-resolution gradient pixels that touch it in shared memory with 16-byte loads (one pixel = 16 lanes x 8
+// channels = 256 contiguous bytes, ~11 independent loads in flight per thread), folding the reflection-padding halo
+// cells onto their source pixel on the way; threads 0..127 also take one owned high-resolution pixel each for the
+// skip-channel sums.  Phase 2: thread = 8 channels of two low-resolution pixels, 4 x 4 transposed-bilinear taps
+// from shared memory (weights per tile row / column precomputed once per tile, so borders, odd sizes and the
+// centre crop cost nothing in the inner loop).
+constexpr int kGtW = 8;
+constexpr int kGtH = 4;
+constexpr int kGtRW = 2 * kGtW + 2;                       // staged region, pixels
+constexpr int kGtRH = 2 * kGtH + 2;
+constexpr int kGtSmem = kGtRW * kGtRH * 128 * 2;          // 46 080 bytes
+
+// folded gradient of 8 channels at interior pixel (y, x): own cell + the reflected halo cells whose source it is
+__device__ __forceinline__ uint4 fold_gather8(const __half* __restrict__ gp, int C, int H, int W, int y, int x, int coff) {
+  const int Wp = W + 2;
+  uint4 m = __ldg(reinterpret_cast<const uint4*>(gp + (static_cast<long long>(y + 1) * Wp + (x + 1)) * C + coff));
+  if (x == 1 || x == W - 2 || y == 1 || y == H - 2) {
+    float acc[8];
+    {
+      const __half2* h = reinterpret_cast<const __half2*>(&m);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { const float2 t = __half22float2(h[i]); acc[2 * i] = t.x; acc[2 * i + 1] = t.y; }
+    }
+    int ys[3], xs[3];
+    const int ny = halo_coords(y, H, ys), nx = halo_coords(x, W, xs);
+    for (int i = 0; i < ny; ++i)
+      for (int k = 0; k < nx; ++k)
+        if (i | k) {
+          float f[8];
+          load8h(gp + (static_cast<long long>(ys[i]) * Wp + xs[k]) * C + coff, f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] += f[j];
+        }
+    __half2* h = reinterpret_cast<__half2*>(&m);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(acc[2 * i], acc[2 * i + 1]);
+  }
+  return m;
+}
+
+__device__ __forceinline__ void upT_gather_tile_body(const UpcatBwdArgs& a, uint8_t* smem_raw) {
   const UpcatArgs& f = a.f;
-  const int lane = threadIdx.x & 31;
-  const int c0 = lane * 4;
-  float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
-  const int npix = f.h * f.w;
-  const int Wp = f.W + 2;
+  __shared__ SkipConst sc;
+  __shared__ float wy_s[kGtH][4], wx_s[kGtW][4];
+  __shared__ float red[264];
+  skip_const_init(&sc, f, nullptr, true);
+  for (int i = threadIdx.x; i < 264; i += blockDim.x) red[i] = 0.f;
+  __half* S = reinterpret_cast<__half*>(smem_raw);
+  const int g = threadIdx.x & 15, c0 = g * 8;
+  const int ps = threadIdx.x >> 4;                 // 0..15: low-res pixels ps and ps + 16 of the tile
   const __half* __restrict__ gc = static_cast<const __half*>(a.gcat);
   const __half* __restrict__ d = static_cast<const __half*>(f.deep);
   __half* __restrict__ tb = static_cast<__half*>(a.dup_pad);
-  const int warps = (gridDim.x * blockDim.x) >> 5;
-  for (int pix = ((blockIdx.x * blockDim.x) + threadIdx.x) >> 5; pix < npix; pix += warps) {
-    const int qy = pix / f.w, qx = pix - qy * f.w;
-    float cwy[4], cwx[4], wy, wx, Qy[3], Qx[3];
-    up_q(qy, f.h, f.H, cwy, wy, Qy);
-    up_q(qx, f.w, f.W, cwx, wx, Qx);
-    uint2 v[4][4];
+  const int tiles_x = (f.w + kGtW - 1) / kGtW, tiles_y = (f.h + kGtH - 1) / kGtH;
+  float s1[8], s2[8], t1[4] = {0, 0, 0, 0}, t2[4] = {0, 0, 0, 0};
 #pragma unroll
-    for (int aa = 0; aa < 4; ++aa)
+  for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+  for (int tile = blockIdx.x; tile < tiles_x * tiles_y; tile += gridDim.x) {
+    const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+    const int qx0 = tx * kGtW, qy0 = ty * kGtH;
+    const int ox0 = 2 * qx0 - 1, oy0 = 2 * qy0 - 1;          // interior coordinates of staged pixel (0, 0)
+    __syncthreads();                                          // previous tile's phase 2 is done with S / weights
+    // loads that do not depend on the staged region are issued first: the skip-channel cell of this thread's owned
+    // high-resolution pixel and the low-resolution activations of its two output pixels
+    const int spy = threadIdx.x / (2 * kGtW), spx = threadIdx.x - spy * (2 * kGtW);
+    const int soy = 2 * qy0 + spy, sox = 2 * qx0 + spx;
+    const bool sk_ok = threadIdx.x < 4 * kGtW * kGtH && soy < f.H && sox < f.W;
+    uint2 sk_g = make_uint2(0u, 0u);
+    float4 sk_r = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (sk_ok) {
+      sk_g = ldg8(gc + (static_cast<long long>(soy + 1) * (f.W + 2) + (sox + 1)) * 144 + 128);
+      sk_r = __ldg(reinterpret_cast<const float4*>(f.sraw + (static_cast<long long>(soy) * f.W + sox) * 4));
+    }
+    uint4 draw[2];
 #pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        const int oy = min(max(2 * qy - 1 + aa, 0), f.H - 1), ox = min(max(2 * qx - 1 + b, 0), f.W - 1);
-        v[aa][b] = ldg8(gc + (static_cast<long long>(oy + 1) * Wp + (ox + 1)) * 144 + c0);
+    for (int half = 0; half < 2; ++half) {
+      const int lp = ps + 16 * half;
+      const int qy = qy0 + lp / kGtW, qx = qx0 + lp % kGtW;
+      draw[half] = (qy < f.h && qx < f.w)
+                       ? __ldg(reinterpret_cast<const uint4*>(d + qy * f.deep_sy + static_cast<long long>(qx) * 128 + c0))
+                       : make_uint4(0u, 0u, 0u, 0u);
+    }
+    // ---- phase 1: stage the folded gradient region ----
+    constexpr int kItems = kGtRW * kGtRH * 16, kBatch = 12;    // 11.25 items per thread: one round trip
+    for (int i0 = threadIdx.x; i0 < kItems; i0 += kBatch * kThreads) {     // kBatch independent loads in flight
+      uint4 v[kBatch];
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        const int pixr = (i0 + u * kThreads) >> 4;
+        const int ry = pixr / kGtRW, rx = pixr - ry * kGtRW;
+        const int oy = oy0 + ry, ox = ox0 + rx;
+        v[u] = make_uint4(0u, 0u, 0u, 0u);
+        if (i0 + u * kThreads < kItems && oy >= 0 && oy < f.H && ox >= 0 && ox < f.W)
+          v[u] = fold_gather8(gc, 144, f.H, f.W, oy, ox, c0);
       }
-    const uint2 vd = ldg8(d + qy * f.deep_sy + static_cast<long long>(qx) * 128 + c0);
-    float acc[4] = {0, 0, 0, 0};
 #pragma unroll
-    for (int aa = 0; aa < 4; ++aa) {
-      if (cwy[aa] == 0.f) continue;
-      const int oy = 2 * qy - 1 + aa;
-#pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        if (cwx[b] == 0.f) continue;
-        const int ox = 2 * qx - 1 + b;
-        float dc[4];
-        fold_gather4(gc, 144, f.H, f.W, oy, ox, c0, v[aa][b], dc);
-        const float ww = cwy[aa] * cwx[b];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[j] = fmaf(ww, dc[j], acc[j]);
+      for (int u = 0; u < kBatch; ++u)
+        if (i0 + u * kThreads < kItems) *reinterpret_cast<uint4*>(S + ((i0 + u * kThreads) >> 4) * 128 + c0) = v[u];
+    }
+    if (threadIdx.x < kGtH * 4 + kGtW * 4) {                  // transposed-bilinear weights of this tile
+      if (threadIdx.x < kGtH * 4) {
+        const int ly = threadIdx.x >> 2, aa = threadIdx.x & 3;
+        const int oy = 2 * (qy0 + ly) - 1 + aa;
+        wy_s[ly][aa] = (oy >= 0 && oy < f.H && qy0 + ly < f.h) ? up_weight(oy, qy0 + ly, f.h) : 0.f;
+      } else {
+        const int t = threadIdx.x - kGtH * 4;
+        const int lx = t >> 2, bb = t & 3;
+        const int ox = 2 * (qx0 + lx) - 1 + bb;
+        wx_s[lx][bb] = (ox >= 0 && ox < f.W && qx0 + lx < f.w) ? up_weight(ox, qx0 + lx, f.w) : 0.f;
       }
     }
-    stg8(tb + static_cast<long long>(pix) * 128 + c0, pack4h(acc));
-    float dd[4];
-    cvt4h(vd, dd);
+    // skip channels: one owned high-resolution pixel per thread (2 kGtW x 2 kGtH = 128 of them)
+    if (sk_ok) {
+      float d4[4];
+      fold_gather4(gc, 144, f.H, f.W, soy, sox, 128, sk_g, d4);
+      const float rr[4] = {sk_r.x, sk_r.y, sk_r.z, sk_r.w};
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { s1[j] += acc[j]; s2[j] = fmaf(dd[j], acc[j], s2[j]); }
+      for (int o = 0; o < 4; ++o) {
+        const float sv = lrelu(fmaf(sc.ga[o], fmaf(rr[o], sc.xa[o], sc.xb[o]), sc.be[o]));
+        const float xh = fmaf(sv, sc.cxa[o], sc.cxb[o]);
+        t1[o] += d4[o];
+        t2[o] = fmaf(d4[o], xh, t2[o]);
+      }
+    }
+    __syncthreads();
+    // ---- phase 2: 4 x 4 taps per low-resolution pixel ----
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int lp = ps + 16 * half;
+      const int ly = lp / kGtW, lx = lp - ly * kGtW;
+      const int qy = qy0 + ly, qx = qx0 + lx;
+      if (qy >= f.h || qx >= f.w) continue;
+      float dd[8];
+      {
+        const __half2* h = reinterpret_cast<const __half2*>(&draw[half]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { const float2 t = __half22float2(h[i]); dd[2 * i] = t.x; dd[2 * i + 1] = t.y; }
+      }
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+      for (int aa = 0; aa < 4; ++aa) {
+        const float wya = wy_s[ly][aa];
+#pragma unroll
+        for (int bb = 0; bb < 4; ++bb) {
+          const float ww = wya * wx_s[lx][bb];
+          const uint4 u = *reinterpret_cast<const uint4*>(S + ((2 * ly + aa) * kGtRW + 2 * lx + bb) * 128 + c0);
+          const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 t = __half22float2(h[i]);
+            acc[2 * i] = fmaf(ww, t.x, acc[2 * i]);
+            acc[2 * i + 1] = fmaf(ww, t.y, acc[2 * i + 1]);
+          }
+        }
+      }
+      store8h(tb + (static_cast<long long>(qy) * f.w + qx) * 128 + c0, acc);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s1[j] += acc[j]; s2[j] = fmaf(dd[j], acc[j], s2[j]); }
+    }
   }
-  __shared__ float red[256];
-  red[threadIdx.x] = 0.f;
   __syncthreads();
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
+  for (int j = 0; j < 8; ++j) {
     atomicAdd(&red[c0 + j], s1[j]);
     atomicAdd(&red[128 + c0 + j], s2[j]);
   }
-  __syncthreads();
-  if (threadIdx.x < 128) atomicAdd(&a.cbstats[threadIdx.x], red[threadIdx.x]);
-  else atomicAdd(&a.cbstats[144 + threadIdx.x - 128], red[threadIdx.x]);
-}
-
-// backward, pass C (low resolution): ddeep = k1 ( t - c1 w - c2 rstd (Q d - mean w) ); BN(132) parameter gradients
-__global__ void __launch_bounds__(kThreads) upcat_bwd_lowres_kernel(UpcatBwdArgs a, __half* __restrict__ ddeep) {
-  pdl_sync();
-  const UpcatArgs& f = a.f;
-  const int lane = threadIdx.x & 31;
-  const int c0 = lane * 4;
-  const float inv_n = 1.f / (static_cast<float>(f.H) * static_cast<float>(f.W));
-  float mean[4], rstd[4], k1[4], c1[4], c2r[4];
+  if (threadIdx.x < 4 * kGtW * kGtH) {
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    float ga, be;
-    cat_coeffs(f, c0 + j, mean[j], rstd[j], ga, be);
-    k1[j] = ga * rstd[j];
-    const float S1 = a.cbstats[c0 + j];
-    const float S2 = rstd[j] * (a.cbstats[144 + c0 + j] - mean[j] * S1);      // sum dc * xhat
-    c1[j] = S1 * inv_n;
-    c2r[j] = S2 * inv_n * rstd[j];
-    if (blockIdx.x == 0 && threadIdx.x < 32) {
-      a.dcat_beta[c0 + j + 4] = S1 * a.gs[1];       // packed channel c <-> reference channel c + 4
-      a.dcat_gamma[c0 + j + 4] = S2 * a.gs[1];
+    for (int o = 0; o < 4; ++o) {
+      float v = t1[o], u = t2[o];
+#pragma unroll
+      for (int dd = 16; dd >= 1; dd >>= 1) { v += __shfl_xor_sync(0xffffffffu, v, dd); u += __shfl_xor_sync(0xffffffffu, u, dd); }
+      if ((threadIdx.x & 31) == 0) { atomicAdd(&red[256 + o], v); atomicAdd(&red[260 + o], u); }
     }
   }
-  const int npix = f.h * f.w;
-  const int wp = f.w + 2;
-  const __half* __restrict__ tb = static_cast<const __half*>(a.dup_pad);
-  const __half* __restrict__ d = static_cast<const __half*>(f.deep);
-  const int warps = (gridDim.x * blockDim.x) >> 5;
-  for (int pix = ((blockIdx.x * blockDim.x) + threadIdx.x) >> 5; pix < npix; pix += warps) {
-    const int qy = pix / f.w, qx = pix - qy * f.w;
-    float cwy[4], cwx[4], wy, wx, Qy[3], Qx[3];
-    up_q(qy, f.h, f.H, cwy, wy, Qy);
-    up_q(qx, f.w, f.W, cwx, wx, Qx);
-    const uint2 vt = ldg8(tb + static_cast<long long>(pix) * 128 + c0);
-    float qd[4], c[4] = {0, 0, 0, 0}, t[4], o[4];
-    q_stencil(d, f.deep_sy, f.h, f.w, qy, qx, Qy, Qx, lane, qd, c);
-    cvt4h(vt, t);
-    const float w2 = wy * wx;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) o[j] = k1[j] * (t[j] - c1[j] * w2 - c2r[j] * (qd[j] - mean[j] * w2));
-    stg8(ddeep + (static_cast<long long>(qy + 1) * wp + (qx + 1)) * 128 + c0, pack4h(o));
+  __syncthreads();
+  for (int i = threadIdx.x; i < 264; i += blockDim.x) {
+    const int dst = i < 128 ? i : i < 256 ? 144 + i - 128 : i < 260 ? 128 + i - 256 : 144 + 128 + i - 260;
+    atomicAdd(&a.cbstats[dst], red[i]);
   }
 }
 
 // backward of the 4 skip channels of the concat tensor (one thread per pixel): BN(132) + LeakyReLU' of the skip branch
 template <bool APPLY>
-__global__ void __launch_bounds__(kThreads) skipcat_bwd_kernel(UpcatBwdArgs a) {
-  pdl_sync();
+__device__ __forceinline__ void skipcat_bwd_body(const UpcatBwdArgs& a, int vblock, int vgrid) {
   const UpcatArgs& f = a.f;
   __shared__ SkipConst sc;
   skip_const_init(&sc, f, APPLY ? a.cbstats : nullptr, true);
@@ -1663,8 +1767,8 @@ __global__ void __launch_bounds__(kThreads) skipcat_bwd_kernel(UpcatBwdArgs a) {
   const long long npix = static_cast<long long>(f.H) * f.W;
   const int Wp = f.W + 2;
   const __half* __restrict__ gc = static_cast<const __half*>(a.gcat);
-  for (long long pix = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; pix < npix;
-       pix += static_cast<long long>(gridDim.x) * blockDim.x) {
+  for (long long pix = static_cast<long long>(vblock) * blockDim.x + threadIdx.x; pix < npix;
+       pix += static_cast<long long>(vgrid) * blockDim.x) {
     const int y = static_cast<int>(pix / f.W), x = static_cast<int>(pix - static_cast<long long>(y) * f.W);
     float d4[4];
     fold_gather4(gc, 144, f.H, f.W, y, x, 128, ldg8(gc + (static_cast<long long>(y + 1) * Wp + (x + 1)) * 144 + 128), d4);
@@ -1701,27 +1805,113 @@ __global__ void __launch_bounds__(kThreads) skipcat_bwd_kernel(UpcatBwdArgs a) {
     else if (threadIdx.x < 8) atomicAdd(&a.cbstats[144 + 128 + threadIdx.x - 4], red[threadIdx.x]);
   } else {
     if (threadIdx.x < 8) atomicAdd(&a.sbstats[threadIdx.x], red[threadIdx.x]);
-    if (blockIdx.x == 0 && threadIdx.x < 4) {       // skip channels are reference channels 0..3
+    if (vblock == 0 && threadIdx.x < 4) {       // skip channels are reference channels 0..3
       a.dcat_beta[threadIdx.x] = a.cbstats[128 + threadIdx.x] * a.gs[1];
       a.dcat_gamma[threadIdx.x] = a.cbstats[144 + 128 + threadIdx.x] * a.gs[1];
     }
   }
 }
 
+// backward, pass C, element-wise form: with Q d saved by the forward pass,
+//     ddeep = k1 t + B (Q d) + A w,   B = -k1 c2 rstd,  A = -k1 (c1 - c2 rstd mean),  w = wy(qy) wx(qx)
+// thread = 8 channels of one low-resolution pixel (16-byte accesses), two pixels in flight per thread
+__device__ __forceinline__ float up_wsum(int q, int n_src, int n_out) {
+  if (q >= 1 && 2 * q + 2 < n_out && q + 1 < n_src) return 2.f;
+  float cw[4], w, Q[3];
+  up_q(q, n_src, n_out, cw, w, Q);
+  return w;
+}
+__device__ __forceinline__ void upcat_bwd_elem_body(const UpcatBwdArgs& a, __half* __restrict__ ddeep, int vblock,
+                                                    int vgrid) {
+  const UpcatArgs& f = a.f;
+  const int g = threadIdx.x & 15;
+  const int c0 = g * 8;
+  const float inv_n = 1.f / (static_cast<float>(f.H) * static_cast<float>(f.W));
+  float k1[8], A[8], B[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float mean, rstd, ga, be;
+    cat_coeffs(f, c0 + j, mean, rstd, ga, be);
+    k1[j] = ga * rstd;
+    const float S1 = a.cbstats[c0 + j];
+    const float S2 = rstd * (a.cbstats[144 + c0 + j] - mean * S1);      // sum dc * xhat
+    const float c1 = S1 * inv_n, c2r = S2 * inv_n * rstd;
+    B[j] = -k1[j] * c2r;
+    A[j] = -k1[j] * (c1 - c2r * mean);
+    if (vblock == 0 && threadIdx.x < 16) {
+      a.dcat_beta[c0 + j + 4] = S1 * a.gs[1];       // packed channel c <-> reference channel c + 4
+      a.dcat_gamma[c0 + j + 4] = S2 * a.gs[1];
+    }
+  }
+  const int npix = f.h * f.w;
+  const int wp = f.w + 2;
+  const __half* __restrict__ tb = static_cast<const __half*>(a.dup_pad) + c0;
+  const __half* __restrict__ qb = static_cast<const __half*>(f.qd) + c0;
+  const int ppb = blockDim.x >> 4;                   // pixels per block per pass
+  for (int base = vblock * ppb * 2 + (threadIdx.x >> 4); base < npix; base += vgrid * ppb * 2) {
+    const int pix1 = base + ppb;
+    const bool ok1 = pix1 < npix;
+    float t0[8], q0[8], t1[8], q1[8];
+    load8h(tb + static_cast<long long>(base) * 128, t0);
+    load8h(qb + static_cast<long long>(base) * 128, q0);
+    if (ok1) {
+      load8h(tb + static_cast<long long>(pix1) * 128, t1);
+      load8h(qb + static_cast<long long>(pix1) * 128, q1);
+    }
+    {
+      const int qy = base / f.w, qx = base - qy * f.w;
+      const float w2 = up_wsum(qy, f.h, f.H) * up_wsum(qx, f.w, f.W);
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = fmaf(k1[j], t0[j], fmaf(B[j], q0[j], A[j] * w2));
+      store8h(ddeep + (static_cast<long long>(qy + 1) * wp + (qx + 1)) * 128 + c0, o);
+    }
+    if (ok1) {
+      const int qy = pix1 / f.w, qx = pix1 - qy * f.w;
+      const float w2 = up_wsum(qy, f.h, f.H) * up_wsum(qx, f.w, f.W);
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = fmaf(k1[j], t1[j], fmaf(B[j], q1[j], A[j] * w2));
+      store8h(ddeep + (static_cast<long long>(qy + 1) * wp + (qx + 1)) * 128 + c0, o);
+    }
+  }
+}
+
 // whole backward of upsample + concat + BN(132): gcat -> ddeep (gradient w.r.t. the low-resolution tensor, padded
 // grid interior) and dsy (gradient w.r.t. the skip branch's BN(4) output), plus the BN(132) parameter gradients
-int launch_upcat_bwd_lowres(const UpcatBwdArgs& a, void* ddeep_pad, cudaStream_t s) {
+// two launches: A = tiled gather (+ skip-channel sums), C = element-wise apply (+ skip-channel apply blocks)
+__global__ void __launch_bounds__(kThreads, 2) upcat_bwd_a_kernel(UpcatBwdArgs a) {
+  extern __shared__ __align__(16) uint8_t gt_smem[];
+  pdl_sync();
+  upT_gather_tile_body(a, gt_smem);
+}
+__global__ void __launch_bounds__(kThreads) upcat_bwd_c_kernel(UpcatBwdArgs a, __half* __restrict__ ddeep, int nb_skip) {
+  pdl_sync();
+  // the skip-channel blocks (one thread per high-resolution pixel, dependent loads) go first so that they overlap
+  // the element-wise blocks
+  if (static_cast<int>(blockIdx.x) < nb_skip) skipcat_bwd_body<true>(a, blockIdx.x, nb_skip);
+  else upcat_bwd_elem_body(a, ddeep, blockIdx.x - nb_skip, gridDim.x - nb_skip);
+}
+
+int launch_upcat_bwd_gather(const UpcatBwdArgs& a, cudaStream_t s) {
   const UpcatArgs& f = a.f;
-  long long lo = (static_cast<long long>(f.h) * f.w + 7) / 8;
-  if (lo > 148 * 12) lo = 148 * 12;
+  const long long tiles = static_cast<long long>((f.w + kGtW - 1) / kGtW) * ((f.h + kGtH - 1) / kGtH);
+  long long grid = tiles;
+  if (grid > 148 * 2) grid = 148 * 2;
+  if (grid < 1) grid = 1;
+  launch_k(upcat_bwd_a_kernel, dim3(static_cast<int>(grid)), dim3(kThreads), kGtSmem, s, a);
+  DSR_LAUNCH_CHECK();
+}
+int launch_upcat_bwd_apply_lowres(const UpcatBwdArgs& a, void* ddeep_pad, cudaStream_t s) {
+  const UpcatArgs& f = a.f;
+  long long lo = (static_cast<long long>(f.h) * f.w + 31) / 32;            // 32 low-resolution pixels per block
+  if (lo > 148 * 8) lo = 148 * 8;
   if (lo < 1) lo = 1;
   long long hi = (static_cast<long long>(f.H) * f.W + kThreads - 1) / kThreads;
   if (hi > 148 * 4) hi = 148 * 4;
   if (hi < 1) hi = 1;
-  launch_k(upT_gather_kernel, dim3(static_cast<int>(lo)), dim3(kThreads), 0, s, a);
-  launch_k(skipcat_bwd_kernel<false>, dim3(static_cast<int>(hi)), dim3(kThreads), 0, s, a);
-  launch_k(upcat_bwd_lowres_kernel, dim3(static_cast<int>(lo)), dim3(kThreads), 0, s, a, static_cast<__half*>(ddeep_pad));
-  launch_k(skipcat_bwd_kernel<true>, dim3(static_cast<int>(hi)), dim3(kThreads), 0, s, a);
+  launch_k(upcat_bwd_c_kernel, dim3(static_cast<int>(lo + hi)), dim3(kThreads), 0, s, a,
+           static_cast<__half*>(ddeep_pad), static_cast<int>(hi));
   DSR_LAUNCH_CHECK();
 }
 

@@ -40,6 +40,7 @@ struct UpcatArgs {
   const float* cat_gamma;  // BN(132) affine, REFERENCE channel order (0..3 skip, 4..131 upsampled)
   const float* cat_beta;
   void* cat_pad;           // fp16 padded [H+2][W+2][144], reflected halo
+  void* qd;                // fp16 plain [h][w][128]: (U^T U d), written by the forward statistics, read by the backward
 };
 int launch_upcat_stats(const UpcatArgs& a, cudaStream_t s);
 int launch_upcat_apply(const UpcatArgs& a, cudaStream_t s);
@@ -103,7 +104,8 @@ struct UpcatBwdArgs {
 // source-domain formulation (see dsr_elem.cu): forward statistics of the concat tensor, and the whole backward of
 // upsample + concat + BN(132) (a.dup_pad is used as the [h][w][128] scratch tensor t = U^T dc)
 int launch_upcat_stats_lowres(const UpcatArgs& a, cudaStream_t s);
-int launch_upcat_bwd_lowres(const UpcatBwdArgs& a, void* ddeep_pad, cudaStream_t s);
+int launch_upcat_bwd_gather(const UpcatBwdArgs& a, cudaStream_t s);
+int launch_upcat_bwd_apply_lowres(const UpcatBwdArgs& a, void* ddeep_pad, cudaStream_t s);
 int launch_upcat_bwd_stats(const UpcatBwdArgs& a, cudaStream_t s);
 int launch_upcat_bwd_apply(const UpcatBwdArgs& a, cudaStream_t s);
 

@@ -810,6 +810,8 @@ UpcatArgs upcat_args(dsr_plan* p, int i, const float* params) {
   a.cat_gamma = params + L.cat_g;
   a.cat_beta = params + L.cat_be;
   a.cat_pad = L.cat.ptr;
+  // second quarter of the (otherwise backward-only) scratch tensor dup: [0, h w 128) holds t = U^T dc, then Q d
+  a.qd = static_cast<__half*>(L.dup.ptr) + static_cast<size_t>(L.h) * L.w * kNC;
   return a;
 }
 
@@ -898,7 +900,8 @@ int backward_level(dsr_plan* p, int i, const float* params, float* grads, cudaSt
   ub.gs = static_cast<const float*>(p->gscale.ptr);
   void* ddeep = last ? L.g_d2a.ptr : p->lv[i + 1].g_u2a.ptr;
   if (p->lowres_upcat) {
-    DSR_TRY(launch_upcat_bwd_lowres(ub, ddeep, s));
+    DSR_TRY(launch_upcat_bwd_gather(ub, s));
+    DSR_TRY(launch_upcat_bwd_apply_lowres(ub, ddeep, s));
   } else {
     DSR_TRY(launch_upcat_bwd_stats(ub, s));
     DSR_TRY(launch_upcat_bwd_apply(ub, s));

@@ -1,26 +1,41 @@
-"""Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list: time per kernel name and share."""
+"""Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list: whole iterations are cut out of the
+captured window (pack_weights_kernel starts one), then time per kernel name, share, and the in-order list of one
+iteration (`--order`)."""
 import collections
 import csv
 import re
 import sys
 
 
-def main(path, steps):
+def main(path, order):
     lines = [l for l in open(path) if not l.startswith('==')]
-    tot, cnt = collections.OrderedDict(), collections.Counter()
+    rows = []
     for row in csv.DictReader(lines):
         v = float(row['Metric Value'].replace(',', ''))
         unit = row['Metric Unit']
         v = v / 1e3 if unit == 'ns' else v * 1e3 if unit == 'ms' else v
         name = re.sub(r'\(.*', '', row['Kernel Name'])
         name = re.sub(r'^void |dsr::|\(anonymous namespace\)::|<unnamed>::', '', name)
+        rows.append((name, v, row['Grid Size']))
+    starts = [i for i, r in enumerate(rows) if r[0].startswith('pack_weights')]
+    if len(starts) >= 2:
+        steps = len(starts) - 1
+        rows_used = rows[starts[0]:starts[-1]]
+    else:
+        steps, rows_used = 1, rows
+    tot, cnt = collections.OrderedDict(), collections.Counter()
+    for name, v, _ in rows_used:
         tot[name] = tot.get(name, 0) + v
         cnt[name] += 1
     T = sum(tot.values())
-    print(f'total {T / steps:.1f} us/step over {sum(cnt.values())} launches ({steps} steps)')
+    print(f'total {T / steps:.1f} us/step over {len(rows_used)} launches ({steps} whole iterations)')
     for k, v in sorted(tot.items(), key=lambda kv: -kv[1]):
         print(f'{v / steps:9.1f} us/step {100 * v / T:5.1f}%  n/step={cnt[k] / steps:5.1f}  {k}')
+    if order and len(starts) >= 2:
+        print('--- one iteration in launch order (us, grid) ---')
+        for i, (name, v, grid) in enumerate(rows[starts[0]:starts[1]]):
+            print(f'{i:4d} {v:8.1f}  {grid:>14s}  {name}')
 
 
 if __name__ == '__main__':
-    main(sys.argv[1], float(sys.argv[2]) if len(sys.argv) > 2 else 1.0)
+    main(sys.argv[1], '--order' in sys.argv or True)
