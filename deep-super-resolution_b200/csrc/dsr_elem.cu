@@ -109,6 +109,35 @@ __device__ __forceinline__ void track_amax(float* gs, float local_max, bool bad)
   }
 }
 
+__device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+    c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+}
+
+// 4 standard normals of counter `ctr` (Philox4x32-10 + Box-Muller); the stream of element group i of iteration t is
+// ctr = (t - 1) * ceil(n / 4) + i, whichever kernel draws it
+__device__ __forceinline__ void philox_normal4(unsigned long long ctr, unsigned long long seed, float (&r)[4]) {
+  uint32_t c[4] = {static_cast<uint32_t>(ctr), static_cast<uint32_t>(ctr >> 32), 0u, 0u};
+  philox4x32_10(c, static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const float u1 = (static_cast<float>(c[2 * h]) + 0.5f) * 2.3283064365386963e-10f;       // (0,1)
+    const float u2 = (static_cast<float>(c[2 * h + 1]) + 0.5f) * 2.3283064365386963e-10f;
+    const float rad = sqrtf(-2.f * __logf(u1));
+    float sn, cs;
+    __sincosf(6.283185307179586f * u2, &sn, &cs);
+    r[2 * h] = rad * cs;
+    r[2 * h + 1] = rad * sn;
+  }
+}
+
 inline int grid_for(long long items, int threads, int cap_blocks) {
   long long b = (items + threads - 1) / threads;
   if (b > cap_blocks) b = cap_blocks;
@@ -123,6 +152,7 @@ inline int grid_for(long long items, int threads, int cap_blocks) {
 // =============================================================================================
 // input pack: fp32 NCHW -> fp16 padded NHWC with reflected halo
 // =============================================================================================
+// Generic packer (any C multiple of 8).
 __global__ void input_pack_kernel(const float* __restrict__ z, __half* __restrict__ xpad, int C, int H, int W) {
   pdl_sync();
   // block: 64 consecutive x of one row y; smem tile [C][65]
@@ -155,11 +185,146 @@ __global__ void input_pack_kernel(const float* __restrict__ z, __half* __restric
   }
 }
 
-int launch_input_pack(const float* z, void* xpad, int C, int H, int W, cudaStream_t s) {
+// C == 32, W % 4 == 0: the product path.  One pass does up to three jobs:
+//   PERTURB  z = z_saved + sigma N(0,1) drawn here (same Philox counters as perturb_kernel: one counter per 4
+//            consecutive elements of the NCHW tensor), z written back for the caller (DIP.py:52,102 reuses it);
+//   pack     fp32 NCHW -> fp16 NHWC padded with the reflected halo (16-byte loads, 2 per thread, all in flight);
+//   SKIP     level 0's skip-branch 1x1 conv (32 -> 4) + BN(4) sums from the fp16-rounded values in registers:
+//            thread = 8 channels of a pixel, the 4 threads of a pixel are adjacent lanes (two shuffle steps).
+struct PerturbSpec {
+  const float* zs;            // z_saved (PERTURB) -- the `z` argument is then the OUTPUT buffer
+  float sigma;
+  unsigned long long seed;
+  const float* state;         // device iteration counter (state[0] = t as int bits)
+  long long n4;               // ceil(C H W / 4)
+};
+template <bool SKIP, bool PERTURB>
+__global__ void __launch_bounds__(kThreads) input_pack32_kernel(float* __restrict__ z, __half* __restrict__ xpad, int H,
+                                                                int W, const float* __restrict__ skip_w,
+                                                                float* __restrict__ sraw, float* __restrict__ skip_stats,
+                                                                PerturbSpec ps) {
+  pdl_sync();
+  constexpr int C = 32;
+  __shared__ float tile[C * 65];
   const int tiles_x = (W + 63) / 64;
-  launch_k(input_pack_kernel, dim3(H * tiles_x), dim3(kThreads), C * 65 * sizeof(float), s, z, static_cast<__half*>(xpad), C, H, W);
+  const int y = blockIdx.x / tiles_x;
+  const int x0 = (blockIdx.x % tiles_x) * 64;
+  {
+    float4 v[2];
+    long long e[2];
+    bool okv[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int i = threadIdx.x + u * kThreads;          // 512 float4 per tile
+      const int c = i >> 4, x = x0 + 4 * (i & 15);
+      okv[u] = x < W;
+      e[u] = (static_cast<long long>(c) * H + y) * W + x;
+      v[u] = okv[u] ? __ldg(reinterpret_cast<const float4*>((PERTURB ? ps.zs : z) + e[u])) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (PERTURB) {
+      const unsigned long long off =
+          static_cast<unsigned long long>(__float_as_int(ps.state[0]) - 1) * static_cast<unsigned long long>(ps.n4);
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (!okv[u]) continue;
+        float r[4];
+        philox_normal4(off + static_cast<unsigned long long>(e[u] >> 2), ps.seed, r);
+        v[u].x += ps.sigma * r[0];
+        v[u].y += ps.sigma * r[1];
+        v[u].z += ps.sigma * r[2];
+        v[u].w += ps.sigma * r[3];
+        *reinterpret_cast<float4*>(z + e[u]) = v[u];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int i = threadIdx.x + u * kThreads;
+      float* t = tile + (i >> 4) * 65 + 4 * (i & 15);
+      t[0] = v[u].x; t[1] = v[u].y; t[2] = v[u].z; t[3] = v[u].w;
+    }
+  }
+  __syncthreads();
+  const int Wp = W + 2;
+  int ys[3];
+  const int ny = halo_coords(y, H, ys);
+  const int dx = threadIdx.x >> 2, g = threadIdx.x & 3;       // 64 pixels x 4 channel groups = one pass
+  const int x = x0 + dx;
+  const bool ok = x < W;
+  float f[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) f[j] = tile[(g * 8 + j) * 65 + dx];
+  if (ok) {
+    int xs[3];
+    const int nx = halo_coords(x, W, xs);
+    for (int a = 0; a < ny; ++a)
+      for (int b = 0; b < nx; ++b)
+        store8h(xpad + (static_cast<long long>(ys[a]) * Wp + xs[b]) * C + g * 8, f);
+  }
+  if (SKIP) {
+    float acc[4];
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(skip_w + o * 32 + g * 8));
+      const float4 w1 = __ldg(reinterpret_cast<const float4*>(skip_w + o * 32 + g * 8 + 4));
+      const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+      acc[o] = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[o] = fmaf(__half2float(__float2half_rn(f[j])), wv[j], acc[o]);
+    }
+#pragma unroll
+    for (int d = 2; d >= 1; d >>= 1)
+#pragma unroll
+      for (int o = 0; o < 4; ++o) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], d);
+    float ss[4], sq[4];
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      const bool mine = ok && g == 0;
+      ss[o] = mine ? acc[o] : 0.f;
+      sq[o] = mine ? acc[o] * acc[o] : 0.f;
+    }
+    if (ok && g == 0)
+      *reinterpret_cast<float4*>(sraw + (static_cast<long long>(y) * W + x) * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    __shared__ float red[8];
+    if (threadIdx.x < 8) red[threadIdx.x] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      float v = ss[o], u = sq[o];
+#pragma unroll
+      for (int d = 16; d >= 4; d >>= 1) { v += __shfl_xor_sync(0xffffffffu, v, d); u += __shfl_xor_sync(0xffffffffu, u, d); }
+      if ((threadIdx.x & 31) == 0) { atomicAdd(&red[o], v); atomicAdd(&red[4 + o], u); }
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) atomicAdd(&skip_stats[threadIdx.x], red[threadIdx.x]);
+  }
+}
+
+// z: input (perturb_zs == nullptr) or OUTPUT of the fused perturbation z = perturb_zs + sigma N(0,1)
+int launch_input_pack(float* z, void* xpad, int C, int H, int W, cudaStream_t s, const float* skip_w, float* sraw,
+                      float* skip_stats, const float* perturb_zs, float sigma, unsigned long long seed,
+                      const float* state) {
+  const int tiles_x = (W + 63) / 64;
+  const bool fast = (C == 32) && (W % 4 == 0);
+  if (!fast) {
+    if (skip_w != nullptr || perturb_zs != nullptr) return -2;      // caller launches those separately
+    launch_k(input_pack_kernel, dim3(H * tiles_x), dim3(kThreads), C * 65 * sizeof(float), s, z,
+             static_cast<__half*>(xpad), C, H, W);
+    DSR_LAUNCH_CHECK();
+  }
+  PerturbSpec ps{perturb_zs, sigma, seed, state, (static_cast<long long>(C) * H * W + 3) / 4};
+  const dim3 grid(H * tiles_x), block(kThreads);
+  __half* xp = static_cast<__half*>(xpad);
+  if (skip_w != nullptr && perturb_zs != nullptr)
+    launch_k(input_pack32_kernel<true, true>, grid, block, 0, s, z, xp, H, W, skip_w, sraw, skip_stats, ps);
+  else if (skip_w != nullptr)
+    launch_k(input_pack32_kernel<true, false>, grid, block, 0, s, z, xp, H, W, skip_w, sraw, skip_stats, ps);
+  else if (perturb_zs != nullptr)
+    launch_k(input_pack32_kernel<false, true>, grid, block, 0, s, z, xp, H, W, skip_w, sraw, skip_stats, ps);
+  else
+    launch_k(input_pack32_kernel<false, false>, grid, block, 0, s, z, xp, H, W, skip_w, sraw, skip_stats, ps);
   DSR_LAUNCH_CHECK();
 }
+int input_pack_fast(int C, int W) { return (C == 32) && (W % 4 == 0); }
 
 // =============================================================================================
 // BN apply + LeakyReLU (+ reflected halo)
@@ -176,18 +341,34 @@ __device__ __forceinline__ void pix_advance(int y0, int x0, int u, int W, int& y
   while (x >= W) { x -= W; ++y; }
 }
 
+// SKIP: the activation written here is the input of the next level's skip branch (1x1 conv 128 -> 4): its raw output
+// sraw [H][W][4] (fp32) and BN(4) statistics are produced from the fp16-rounded activation while it is in registers
+// (4 partial dot products per lane, transposed butterfly reduction of the 4 pixels x 4 outputs of a warp pass)
+struct SkipFuse {
+  const float* w;          // [4][128] fp32
+  float* sraw;             // [H][W][4]
+  float* stats;            // [2][4]
+};
+template <bool SKIP>
 __global__ void __launch_bounds__(kThreads) bn_act_kernel(const __half* __restrict__ raw, BnRef bn,
-                                                          __half* __restrict__ act, int H, int W, int halo) {
+                                                          __half* __restrict__ act, int H, int W, int halo,
+                                                          SkipFuse sf) {
   pdl_sync();
   const int lane = threadIdx.x & 31;
   float scale[4], shift[4];
+  float wr[SKIP ? 4 : 1][4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     float mean, rstd, ga, be;
     bn_coeffs(bn, lane * 4 + j, mean, rstd, ga, be);
     scale[j] = ga * rstd;
     shift[j] = be - mean * scale[j];
+    if (SKIP) {
+#pragma unroll
+      for (int o = 0; o < 4; ++o) wr[o][j] = sf.w[o * 128 + lane * 4 + j];
+    }
   }
+  float ss = 0.f, sq = 0.f;          // SKIP: sums of output (lane >> 1) & 3 (held by the even lanes)
   const int npix = H * W;
   const int Wp = W + 2;
   const int warps = (gridDim.x * blockDim.x) >> 5;
@@ -198,15 +379,29 @@ __global__ void __launch_bounds__(kThreads) bn_act_kernel(const __half* __restri
 #pragma unroll
     for (int u = 0; u < kPixUnroll; ++u)
       if (base + u < npix) v[u] = ldg8(raw + static_cast<long long>(base + u) * 128 + lane * 4);
+    float dot[SKIP ? 4 * kPixUnroll : 1];
 #pragma unroll
     for (int u = 0; u < kPixUnroll; ++u) {
       const int pix = base + u;
-      if (pix >= npix) break;
+      if (pix >= npix) {
+        if (SKIP) {
+#pragma unroll
+          for (int o = 0; o < 4; ++o) dot[u * 4 + o] = 0.f;
+        }
+        continue;
+      }
       float f[4];
       cvt4h(v[u], f);
 #pragma unroll
       for (int j = 0; j < 4; ++j) f[j] = lrelu(fmaf(f[j], scale[j], shift[j]));
       const uint2 o = pack4h(f);
+      if (SKIP) {
+        float a[4];
+        cvt4h(o, a);                   // the fp16-rounded activation the skip conv sees
+#pragma unroll
+        for (int oo = 0; oo < 4; ++oo)
+          dot[u * 4 + oo] = a[0] * wr[oo][0] + a[1] * wr[oo][1] + a[2] * wr[oo][2] + a[3] * wr[oo][3];
+      }
       int y, x;
       pix_advance(y0, x0, u, W, y, x);
       stg8(act + (static_cast<long long>(y + 1) * Wp + (x + 1)) * 128 + lane * 4, o);
@@ -218,6 +413,42 @@ __global__ void __launch_bounds__(kThreads) bn_act_kernel(const __half* __restri
             if (a | b) stg8(act + (static_cast<long long>(ys[a]) * Wp + xs[b]) * 128 + lane * 4, o);
       }
     }
+    if (SKIP) {
+      // transposed butterfly: 16 values over 32 lanes -> lane l ends with the full sum of value (l >> 1) & 15
+      static_assert(kPixUnroll == 4, "reduction below assumes 4 pixels x 4 outputs");
+#pragma unroll
+      for (int step = 0; step < 4; ++step) {
+        const int off = 16 >> step, n = 8 >> step;         // lanes with bit `off` set keep the upper half
+        const bool up = lane & off;
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+          const float send = up ? dot[i] : dot[i + n];
+          const float keep = up ? dot[i + n] : dot[i];
+          dot[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+      }
+      dot[0] += __shfl_xor_sync(0xffffffffu, dot[0], 1);
+      // value index held by this lane: bits (16, 8, 4, 2) of the lane select halves in that order
+      const int vi = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+      const int u = vi >> 2;
+      if ((lane & 1) == 0 && base + u < npix) {
+        sf.sraw[static_cast<long long>(base + u) * 4 + (vi & 3)] = dot[0];
+        ss += dot[0];
+        sq = fmaf(dot[0], dot[0], sq);
+      }
+    }
+  }
+  if (SKIP) {
+    __shared__ float red[8];
+    if (threadIdx.x < 8) red[threadIdx.x] = 0.f;
+    __syncthreads();
+    if ((lane & 1) == 0) {
+      const int o = (((lane >> 2) & 1) * 2 + ((lane >> 1) & 1));
+      atomicAdd(&red[o], ss);
+      atomicAdd(&red[4 + o], sq);
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) atomicAdd(&sf.stats[threadIdx.x], red[threadIdx.x]);
   }
 }
 
@@ -229,8 +460,15 @@ inline int warp_grid(int H, int W, int cap_blocks) {      // one warp per kPixUn
   return static_cast<int>(b);
 }
 
-int launch_bn_act(const void* raw, BnRef bn, void* act_pad, int H, int W, int halo, cudaStream_t s) {
-  launch_k(bn_act_kernel, dim3(warp_grid(H, W, 148 * 8)), dim3(kThreads), 0, s, static_cast<const __half*>(raw), bn, static_cast<__half*>(act_pad), H, W, halo);
+int launch_bn_act(const void* raw, BnRef bn, void* act_pad, int H, int W, int halo, cudaStream_t s,
+                  const float* skip_w, float* skip_sraw, float* skip_stats) {
+  SkipFuse sf{skip_w, skip_sraw, skip_stats};
+  if (skip_w != nullptr)
+    launch_k(bn_act_kernel<true>, dim3(warp_grid(H, W, 148 * 8)), dim3(kThreads), 0, s,
+             static_cast<const __half*>(raw), bn, static_cast<__half*>(act_pad), H, W, halo, sf);
+  else
+    launch_k(bn_act_kernel<false>, dim3(warp_grid(H, W, 148 * 8)), dim3(kThreads), 0, s,
+             static_cast<const __half*>(raw), bn, static_cast<__half*>(act_pad), H, W, halo, sf);
   DSR_LAUNCH_CHECK();
 }
 
@@ -2169,18 +2407,6 @@ int launch_adam(float* p, const float* g, float* m, float* v, long long n, float
 // =============================================================================================
 // input perturbation: z = z_saved + sigma * N(0,1)  (Philox4x32-10 + Box-Muller)
 // =============================================================================================
-__device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
-    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
-    const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
-    c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
-    k0 += 0x9E3779B9u;
-    k1 += 0xBB67AE85u;
-  }
-}
-
 __global__ void perturb_kernel(const float* __restrict__ zs, float* __restrict__ z, long long n, float sigma,
                                unsigned long long seed, unsigned long long offset, const float* __restrict__ state) {
   pdl_sync();
@@ -2189,20 +2415,8 @@ __global__ void perturb_kernel(const float* __restrict__ zs, float* __restrict__
     offset = static_cast<unsigned long long>(__float_as_int(state[0]) - 1) * static_cast<unsigned long long>(n4);
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const unsigned long long ctr = offset + static_cast<unsigned long long>(i);
-    uint32_t c[4] = {static_cast<uint32_t>(ctr), static_cast<uint32_t>(ctr >> 32), 0u, 0u};
-    philox4x32_10(c, static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
     float r[4];
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const float u1 = (static_cast<float>(c[2 * h]) + 0.5f) * 2.3283064365386963e-10f;       // (0,1)
-      const float u2 = (static_cast<float>(c[2 * h + 1]) + 0.5f) * 2.3283064365386963e-10f;
-      const float rad = sqrtf(-2.f * __logf(u1));
-      float sn, cs;
-      __sincosf(6.283185307179586f * u2, &sn, &cs);
-      r[2 * h] = rad * cs;
-      r[2 * h + 1] = rad * sn;
-    }
+    philox_normal4(offset + static_cast<unsigned long long>(i), seed, r);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const long long e = 4 * i + k;

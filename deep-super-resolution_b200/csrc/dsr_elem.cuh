@@ -19,10 +19,19 @@ struct BnRef {            // one train-mode BatchNorm over n pixels
 };
 
 // z fp32 NCHW [C][H][W] (C multiple of 8) -> fp16 padded NHWC with reflected halo.
-int launch_input_pack(const float* z, void* xpad, int C, int H, int W, cudaStream_t s);
+// z fp32 NCHW -> fp16 padded NHWC with the reflected halo.  Fast path (input_pack_fast: C == 32, W % 4 == 0) can
+// fuse level 0's skip-branch 1x1 conv (skip_w -> sraw fp32 [H][W][4], skip_stats [2][4]) and the input perturbation
+// (z = perturb_zs + sigma N(0,1), Philox counters of perturb_kernel; z is then the OUTPUT); otherwise both must be null.
+int launch_input_pack(float* z, void* xpad, int C, int H, int W, cudaStream_t s, const float* skip_w = nullptr,
+                      float* sraw = nullptr, float* skip_stats = nullptr, const float* perturb_zs = nullptr,
+                      float sigma = 0.f, unsigned long long seed = 0, const float* state = nullptr);
+int input_pack_fast(int C, int W);
 
 // raw fp16 plain [H][W][128] -> LeakyReLU(BN(raw)) fp16 padded (interior + reflected halo if halo != 0)
-int launch_bn_act(const void* raw, BnRef bn, void* act_pad, int H, int W, int halo, cudaStream_t s);
+// optional fusion of the NEXT level's skip-branch 1x1 conv (128 -> 4) on the activation being written:
+// skip_w fp32 [4][128] -> skip_sraw fp32 plain [H][W][4], skip_stats [2][4] (accumulated)
+int launch_bn_act(const void* raw, BnRef bn, void* act_pad, int H, int W, int halo, cudaStream_t s,
+                  const float* skip_w = nullptr, float* skip_sraw = nullptr, float* skip_stats = nullptr);
 
 // skip branch 1x1 conv: x padded [H+2][W+2][Cin] (fp16) * w fp32 [4][Cin] -> sraw fp32 plain [H][W][4], stats [2][4]
 int launch_skip_conv(const void* xpad, int Cin, const float* w, float* sraw, float* stats, int H, int W,

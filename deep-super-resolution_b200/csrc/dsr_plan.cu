@@ -166,8 +166,13 @@ struct dsr_plan {
   // pointer arguments; an entry is captured on its SECOND use (the first run is eager and sets function attributes)
   struct PassGraph { int kind; const void* a0; const void* a1; const void* a2; const void* a3; int uses; cudaGraphExec_t exec; };
   std::vector<PassGraph> pass_graphs;
+  int fuse_skip = 1;             // skip-branch 1x1 conv of level i+1 fused into level i's last BN + LeakyReLU pass
   int lowres_upcat = 1;          // upsample + concat + BN(132): statistics and backward in the low-resolution domain
   int in_step = 0;               // inside enqueue_step (whole-iteration graph): no nested pass graphs
+  // set by enqueue_step around the forward pass: z = pz_saved + psigma N(0,1) is drawn by the input packing pass
+  const float* pz_saved = nullptr;
+  float psigma = 0.f;
+  unsigned long long pseed = 0;
   int fuse_top = 1;              // level 0: BN/LeakyReLU of the last decoder conv fused with the final conv (fwd + bwd)
   bool bound = false, have_forward = false;
   // optional per-launch timing of the tensor-core kernels (bench.py roofline): class 0 = halo-tile conv (stride-1
@@ -787,9 +792,17 @@ int run_wgrad(dsr_plan* p, ConvLayer& c, cudaStream_t s) {
   return launch_wgrad(c.wgrad, s);
 }
 
-int conv_bn_act(dsr_plan* p, ConvLayer& c, const float* params, cudaStream_t s) {
+// `next` != nullptr: c is the last encoder conv of a level whose activation feeds level `next`'s skip branch; the
+// skip 1x1 conv and its statistics are fused into the BN + LeakyReLU pass
+int conv_bn_act(dsr_plan* p, ConvLayer& c, const float* params, cudaStream_t s, Level* next = nullptr) {
   DSR_TRY(run_fprop(p, c, s));
-  DSR_TRY(launch_bn_act(c.raw.ptr, conv_bn(p, c, params), c.act.ptr, c.outH, c.outW, c.act_halo, s));
+  if (next != nullptr && p->fuse_skip) {
+    DSR_TRY(launch_bn_act(c.raw.ptr, conv_bn(p, c, params), c.act.ptr, c.outH, c.outW, c.act_halo, s,
+                          params + next->skip_w, static_cast<float*>(next->sraw.ptr),
+                          reinterpret_cast<float*>(p->base) + next->skip_stats_off));
+  } else {
+    DSR_TRY(launch_bn_act(c.raw.ptr, conv_bn(p, c, params), c.act.ptr, c.outH, c.outW, c.act_halo, s));
+  }
   return 0;
 }
 
@@ -818,11 +831,12 @@ UpcatArgs upcat_args(dsr_plan* p, int i, const float* params) {
 int forward_level(dsr_plan* p, int i, const float* params, cudaStream_t s) {
   Level& L = p->lv[i];
   float* acc = reinterpret_cast<float*>(p->base);
-  DSR_TRY(launch_skip_conv(L.x_pad->ptr, L.Cin, params + L.skip_w, static_cast<float*>(L.sraw.ptr),
-                           acc + L.skip_stats_off, L.H, L.W, s));
+  if (!p->fuse_skip || (i == 0 && !input_pack_fast(L.Cin, L.W)))   // otherwise produced by the pass that wrote this level's input
+    DSR_TRY(launch_skip_conv(L.x_pad->ptr, L.Cin, params + L.skip_w, static_cast<float*>(L.sraw.ptr),
+                             acc + L.skip_stats_off, L.H, L.W, s));
   int rc;
   if ((rc = conv_bn_act(p, L.d1, params, s))) return rc;
-  if ((rc = conv_bn_act(p, L.d2, params, s))) return rc;
+  if ((rc = conv_bn_act(p, L.d2, params, s, i + 1 < p->num_scales ? &p->lv[i + 1] : nullptr))) return rc;
   if (i + 1 < p->num_scales && (rc = forward_level(p, i + 1, params, s))) return rc;
   const UpcatArgs a = upcat_args(p, i, params);
   if (p->lowres_upcat) DSR_TRY(launch_upcat_stats_lowres(a, s));
@@ -1283,6 +1297,7 @@ int dsr_plan_bind(dsr_plan_t* p, void* workspace, size_t bytes, void* stream) {
   p->use_graph = getenv("DSR_NO_GRAPH") ? 0 : 1;
   p->fuse_top = getenv("DSR_NO_FUSE_TOP") ? 0 : 1;
   p->lowres_upcat = getenv("DSR_NO_LOWRES_UPCAT") ? 0 : 1;
+  p->fuse_skip = getenv("DSR_NO_FUSE_SKIP") ? 0 : 1;
   p->bound = true;
   p->have_forward = false;
   return 0;
@@ -1297,7 +1312,21 @@ static int net_forward_impl(dsr_plan_t* p, const float* params, const float* z, 
   DSR_TRY(launch_pack_weights(params, p->warena.ptr, static_cast<const PackDesc*>(p->pack_table.ptr),
                               static_cast<int>(p->pack_host.size()), s));
   Level& L0 = p->lv[0];
-  DSR_TRY(launch_input_pack(z, L0.xin.ptr, L0.Cin, L0.H, L0.W, s));
+  {
+    // level 0's skip conv and (whole-step path) the input perturbation ride on the packing pass when it has the
+    // fast layout; otherwise they are separate launches
+    const bool fast = input_pack_fast(L0.Cin, L0.W) != 0;
+    const bool fskip = fast && p->fuse_skip;
+    float* zw = const_cast<float*>(z);
+    const long long nz = static_cast<long long>(L0.Cin) * L0.H * L0.W;
+    if (p->pz_saved != nullptr && !fast)
+      DSR_TRY(launch_perturb(p->pz_saved, zw, nz, p->psigma, p->pseed, 0, s, static_cast<float*>(p->stepstate.ptr)));
+    DSR_TRY(launch_input_pack(zw, L0.xin.ptr, L0.Cin, L0.H, L0.W, s, fskip ? params + L0.skip_w : nullptr,
+                              fskip ? static_cast<float*>(L0.sraw.ptr) : nullptr,
+                              fskip ? reinterpret_cast<float*>(p->base) + L0.skip_stats_off : nullptr,
+                              fast ? p->pz_saved : nullptr, p->psigma, p->pseed,
+                              static_cast<const float*>(p->stepstate.ptr)));
+  }
   int rc = forward_level(p, 0, params, s);
   if (rc) return rc;
   if (p->fuse_top)
@@ -1443,10 +1472,13 @@ static int enqueue_step(dsr_plan_t* p, const dsr_downsampler_t* d, const dsr_ste
   int total = 0;
   int rc = launch_step_begin(st, losses, t_set, lr, 0.9f, 0.999f, s);
   if (rc) return rc;
-  if ((rc = launch_perturb(b->z_saved, b->z, nz, sigma, seed, 0, s, st))) return rc;
-  total += 2;
+  total += 1;
   p->in_step = 1;
+  p->pz_saved = b->z_saved;          // z = z_saved + sigma N(0,1) is drawn inside the forward pass (input packing)
+  p->psigma = sigma;
+  p->pseed = seed;
   rc = dsr_net_forward(p, b->params, b->z, b->out_hr, b->bn_buffers, stream);
+  p->pz_saved = nullptr;
   p->in_step = 0;
   if (rc) return rc;
   p->have_forward = true;

@@ -251,6 +251,28 @@ def test_fused_step_tracks_the_closure_path():
     assert float(l1[0]) == pytest.approx(float(l2), rel=2e-2)
 
 
+def test_fused_step_draws_the_counter_based_noise():
+    """The whole-step path draws z inside the input-packing pass; it must be the stream dsr_perturb defines:
+    iteration t uses counters (t - 1) * ceil(n / 4) + i."""
+    import dsr_b200
+    from dsr_b200._lib import lib, check
+    from oracle import dip_oracle as O
+    lr_img, hr = O.synthetic_pair(2, 64)
+    net = make_net(3)
+    cfg = {'learning_rate': 0.01, 'num_iter': 3, 'reg_noise_std': 0.05}
+    z0 = dsr_b200.get_noise(32, 'noise', (64, 64))
+    dsr_b200.dip_sr_fused(net, lr_img, (64, 64), 4, cfg, 'cuda:0', seed=11, net_input=z0)
+    torch.cuda.synchronize()
+    z_last = net._fused_keepalive[2]
+    n = z0.numel()
+    zs = z0.cuda().contiguous()
+    ref = torch.empty_like(zs)
+    check(lib.dsr_perturb(zs.data_ptr(), ref.data_ptr(), n, 0.05, 11, 2 * ((n + 3) // 4),
+                          torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert torch.equal(z_last.reshape(-1), ref.reshape(-1))
+
+
 def test_full_size_properties_512():
     """BASELINE config 2 size (512x512, factor 4): properties that need no oracle run -- output range, finite
     gradients, exact-zero gradients of the structurally dead biases, run-to-run agreement, and a fused loop that
