@@ -1149,10 +1149,31 @@ __global__ void __launch_bounds__(kThreads, HAS_DS ? 2 : 3) bn_bwd_kernel(BnBwdA
   // xhat = r * xa + xb;  y = ga * xhat + be;  APPLY: dr = k1 * (dy - c1 - xhat * c2)
   float xa[4], xb[4], ga[4], be[4], c1[4], c2[4], k1[4], s1[4], s2[4];
   __shared__ float4 sws[4][32];      // skip-conv weights [o][lane] (only with HAS_DS), kept out of the registers
+  __shared__ float skc[3][4];        // dsraw[o] = skc[0][o] dsy[o] + skc[1][o] sraw[o] + skc[2][o]
+  float aw[HAS_DS && !APPLY ? 4 : 1][4];
   if (HAS_DS) {
     if (threadIdx.x < 128) {
       const int o = threadIdx.x >> 5, l = threadIdx.x & 31;
       sws[o][l] = *reinterpret_cast<const float4*>(a.wskip + o * 128 + l * 4);
+    }
+    if (threadIdx.x < 4) {
+      const int o = threadIdx.x;
+      float mean, rstd, g4, b4;
+      bn_coeffs(a.bn_skip, o, mean, rstd, g4, b4);
+      const float k = g4 * rstd, c1s = a.sbstats[o] * a.bn_skip.inv_n, c2s = a.sbstats[4 + o] * a.bn_skip.inv_n;
+      skc[0][o] = k;                                   // xhat = (sraw - mean) rstd
+      skc[1][o] = -k * c2s * rstd;
+      skc[2][o] = -k * (c1s - c2s * mean * rstd);
+      if (APPLY && blockIdx.x == 0) {
+        a.dskip_beta[o] = a.sbstats[o] * a.gs[1];
+        a.dskip_gamma[o] = a.sbstats[4 + o] * a.gs[1];
+      }
+    }
+    if (!APPLY) {
+#pragma unroll
+      for (int o = 0; o < 4; ++o)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) aw[o][j] = 0.f;
     }
     __syncthreads();
   }
@@ -1178,7 +1199,7 @@ __global__ void __launch_bounds__(kThreads, HAS_DS ? 2 : 3) bn_bwd_kernel(BnBwdA
   for (int base = (((blockIdx.x * blockDim.x) + threadIdx.x) >> 5) * kPixUnroll; base < npix;
        base += warps * kPixUnroll) {
     uint2 vg[kPixUnroll], vr[kPixUnroll];
-    float4 vd[kPixUnroll];
+    float4 vd[kPixUnroll], vs[kPixUnroll];
     const int y0 = base / W, x0 = base - y0 * W;
 #pragma unroll
     for (int u = 0; u < kPixUnroll; ++u) {
@@ -1188,7 +1209,10 @@ __global__ void __launch_bounds__(kThreads, HAS_DS ? 2 : 3) bn_bwd_kernel(BnBwdA
         pix_advance(y0, x0, u, W, y, x);
         vg[u] = ldg8(gp + (static_cast<long long>(y + 1) * Wp + (x + 1)) * a.gC + c0);
         vr[u] = ldg8(raw + static_cast<long long>(pix) * 128 + c0);
-        if (HAS_DS) vd[u] = __ldg(reinterpret_cast<const float4*>(a.ds + static_cast<long long>(pix) * 4));
+        if (HAS_DS) {
+          vd[u] = __ldg(reinterpret_cast<const float4*>(a.dsy + static_cast<long long>(pix) * 4));
+          vs[u] = __ldg(reinterpret_cast<const float4*>(a.sraw + static_cast<long long>(pix) * 4));
+        }
       }
     }
 #pragma unroll
@@ -1212,8 +1236,13 @@ __global__ void __launch_bounds__(kThreads, HAS_DS ? 2 : 3) bn_bwd_kernel(BnBwdA
               for (int j = 0; j < 4; ++j) da[j] += f[j];
             }
       }
+      float dd[4];
       if (HAS_DS) {
-        const float dd[4] = {vd[u].x, vd[u].y, vd[u].z, vd[u].w};
+        const float dy4[4] = {vd[u].x, vd[u].y, vd[u].z, vd[u].w}, sr4[4] = {vs[u].x, vs[u].y, vs[u].z, vs[u].w};
+#pragma unroll
+        for (int o = 0; o < 4; ++o) dd[o] = fmaf(skc[0][o], dy4[o], fmaf(skc[1][o], sr4[o], skc[2][o]));
+        if (APPLY && lane == 0)
+          *reinterpret_cast<float4*>(a.dsraw + static_cast<long long>(pix) * 4) = make_float4(dd[0], dd[1], dd[2], dd[3]);
 #pragma unroll
         for (int o = 0; o < 4; ++o) {
           const float4 w4 = sws[o][lane];
@@ -1223,18 +1252,27 @@ __global__ void __launch_bounds__(kThreads, HAS_DS ? 2 : 3) bn_bwd_kernel(BnBwdA
           da[3] = fmaf(dd[o], w4.w, da[3]);
         }
       }
-      float o[4];
+      float o[4], actf[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float xh = fmaf(r[j], xa[j], xb[j]);
         const float yv = fmaf(ga[j], xh, be[j]);
         const float dy = yv > 0.f ? da[j] : kSlope * da[j];
+        actf[j] = lrelu(yv);
         if (APPLY) {
           o[j] = k1[j] * (dy - c1[j] - xh * c2[j]);
         } else {
           s1[j] += dy;
           s2[j] = fmaf(dy, xh, s2[j]);
         }
+      }
+      if (HAS_DS && !APPLY) {               // skip conv weight gradient: dW[o][c] += dsraw[o] * act[c] (fp16-rounded act)
+        float ah[4];
+        cvt4h(pack4h(actf), ah);
+#pragma unroll
+        for (int oo = 0; oo < 4; ++oo)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) aw[oo][j] = fmaf(dd[oo], ah[j], aw[oo][j]);
       }
       if (APPLY) {
         const uint2 pk = pack4h(o);
@@ -1245,16 +1283,24 @@ __global__ void __launch_bounds__(kThreads, HAS_DS ? 2 : 3) bn_bwd_kernel(BnBwdA
     }
   }
   if (!APPLY) {
-    __shared__ float red[256];
-    red[threadIdx.x] = 0.f;
+    __shared__ float red[HAS_DS ? 256 + 512 : 256];
+    for (int i = threadIdx.x; i < (HAS_DS ? 256 + 512 : 256); i += blockDim.x) red[i] = 0.f;
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       atomicAdd(&red[c0 + j], s1[j]);
       atomicAdd(&red[128 + c0 + j], s2[j]);
+      if (HAS_DS) {
+#pragma unroll
+        for (int oo = 0; oo < 4; ++oo) atomicAdd(&red[256 + oo * 128 + c0 + j], aw[oo][j]);
+      }
     }
     __syncthreads();
     atomicAdd(&a.bstats[threadIdx.x], red[threadIdx.x]);
+    if (HAS_DS) {
+      const float invS = a.gs[1];
+      for (int i = threadIdx.x; i < 512; i += blockDim.x) atomicAdd(&a.dwskip[i], red[256 + i] * invS);
+    }
   } else {
     const float amax = fmaxf(__low2float(amax2), __high2float(amax2));
     track_amax(a.gs, isfinite(amax) ? amax : 0.f, !isfinite(amax));
@@ -1383,21 +1429,21 @@ static int fast_grid(int H, int W, int cap) {
 
 int launch_bn_bwd_stats(const BnBwdArgs& a, cudaStream_t s) {
   const int grid = warp_grid(a.H, a.W, 148 * 4);
-  if (a.ds == nullptr && (a.W & 3) == 0 && a.W >= 4) {
+  if (a.dsy == nullptr && (a.W & 3) == 0 && a.W >= 4) {
     launch_k(bn_bwd_fast_kernel<false>, dim3(fast_grid(a.H, a.W, 148 * 8)), dim3(kThreads), 0, s, a);
     DSR_LAUNCH_CHECK();
   }
-  if (a.ds != nullptr) launch_k(bn_bwd_kernel<false, true>, dim3(grid), dim3(kThreads), 0, s, a);
+  if (a.dsy != nullptr) launch_k(bn_bwd_kernel<false, true>, dim3(grid), dim3(kThreads), 0, s, a);
   else launch_k(bn_bwd_kernel<false, false>, dim3(grid), dim3(kThreads), 0, s, a);
   DSR_LAUNCH_CHECK();
 }
 int launch_bn_bwd_apply(const BnBwdArgs& a, cudaStream_t s) {
   const int grid = warp_grid(a.H, a.W, 148 * 8);
-  if (a.ds == nullptr && (a.W & 3) == 0 && a.W >= 4) {
+  if (a.dsy == nullptr && (a.W & 3) == 0 && a.W >= 4) {
     launch_k(bn_bwd_fast_kernel<true>, dim3(fast_grid(a.H, a.W, 148 * 16)), dim3(kThreads), 0, s, a);
     DSR_LAUNCH_CHECK();
   }
-  if (a.ds != nullptr) launch_k(bn_bwd_kernel<true, true>, dim3(grid), dim3(kThreads), 0, s, a);
+  if (a.dsy != nullptr) launch_k(bn_bwd_kernel<true, true>, dim3(grid), dim3(kThreads), 0, s, a);
   else launch_k(bn_bwd_kernel<true, false>, dim3(grid), dim3(kThreads), 0, s, a);
   DSR_LAUNCH_CHECK();
 }

@@ -85,8 +85,17 @@ struct BnBwdArgs {
   const void* g;           // fp16 gradient w.r.t. the activation, PADDED grid [H+2][W+2][gC]
   int gC;                  // channel pitch of g (128 or 144; first 128 channels are used)
   int fold;                // 1: g holds padded-grid data-gradients whose halo must be folded back (reflection)
-  const float* ds;         // optional fp32 plain [H][W][4]: gradient of the skip-conv output reading this activation
+  // optional (HAS_DS): this activation also feeds the next level's skip branch (1x1 conv 128 -> 4, BN(4)); the whole
+  // backward of that branch is done here: dsraw = BN(4)' (dsy), act-gradient += W^T dsraw, dW += dsraw act^T
+  const float* dsy;        // fp32 plain [H][W][4]: gradient w.r.t. the skip BN(4) output (null: no skip branch)
+  const float* sraw;       // fp32 plain [H][W][4]: skip conv output saved by the forward
+  BnRef bn_skip;           // BN(4)
+  const float* sbstats;    // [2][4]: sum dsy, sum dsy * xhat
   const float* wskip;      // fp32 [4][128]
+  float* dwskip;           // [4][128] accumulated
+  float* dskip_gamma;      // [4]
+  float* dskip_beta;       // [4]
+  float* dsraw;            // fp32 plain [H][W][4]: written for inspection (diagnostics)
   const void* raw;         // fp16 plain [H][W][128]: BN input saved by the forward
   BnRef bn;
   float* bstats;           // [2][128]: sum dy, sum dy*xhat

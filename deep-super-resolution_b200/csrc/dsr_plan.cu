@@ -851,14 +851,24 @@ int forward_level(dsr_plan* p, int i, const float* params, cudaStream_t s) {
   return 0;
 }
 
+// `next` != nullptr: c's activation also feeds level `next`'s skip branch, whose backward is done in the same passes
 int bn_backward(dsr_plan* p, ConvLayer& c, const float* params, float* grads, const void* g, int gC, int fold,
-                const float* ds, const float* wskip, cudaStream_t s) {
+                Level* next, cudaStream_t s) {
   BnBwdArgs a{};
   a.g = g;
   a.gC = gC;
   a.fold = fold;
-  a.ds = ds;
-  a.wskip = wskip;
+  if (next != nullptr) {
+    a.dsy = static_cast<const float*>(next->dsy.ptr);
+    a.sraw = static_cast<const float*>(next->sraw.ptr);
+    a.bn_skip = skip_bn(p, *next, params);
+    a.sbstats = reinterpret_cast<float*>(p->base) + next->sbstats_off;
+    a.wskip = params + next->skip_w;
+    a.dwskip = grads + next->skip_w;
+    a.dskip_gamma = grads + next->skip_g;
+    a.dskip_beta = grads + next->skip_be;
+    a.dsraw = static_cast<float*>(next->dsraw.ptr);
+  }
   a.raw = c.raw.ptr;
   a.bn = conv_bn(p, c, params);
   a.bstats = reinterpret_cast<float*>(p->base) + c.bstats_off;
@@ -897,10 +907,10 @@ int backward_level(dsr_plan* p, int i, const float* params, float* grads, cudaSt
   int rc;
   // ---- decoder ----
   if (!(i == 0 && p->fuse_top) &&        // level 0: done by the fused top kernels (dsr_net_backward)
-      (rc = bn_backward(p, L.u2, params, grads, L.g_u2a.ptr, kNC, 0, nullptr, nullptr, s)))
+      (rc = bn_backward(p, L.u2, params, grads, L.g_u2a.ptr, kNC, 0, nullptr, s)))
     return rc;
   if ((rc = conv_backward(p, L.u2, s))) return rc;
-  if ((rc = bn_backward(p, L.u1, params, grads, L.u2.gin.ptr, kNC, 0, nullptr, nullptr, s))) return rc;
+  if ((rc = bn_backward(p, L.u1, params, grads, L.u2.gin.ptr, kNC, 0, nullptr, s))) return rc;
   if ((rc = conv_backward(p, L.u1, s))) return rc;
   UpcatBwdArgs ub{};
   ub.f = upcat_args(p, i, params);
@@ -920,6 +930,7 @@ int backward_level(dsr_plan* p, int i, const float* params, float* grads, cudaSt
     DSR_TRY(launch_upcat_bwd_stats(ub, s));
     DSR_TRY(launch_upcat_bwd_apply(ub, s));
   }
+  if (i == 0)       // levels >= 1: the skip branch's backward rides on the BN backward of the activation it reads
   DSR_TRY(launch_skip_bwd(static_cast<const float*>(L.dsy.ptr), static_cast<const float*>(L.sraw.ptr),
                           skip_bn(p, L, params), acc + L.sbstats_off, L.x_pad->ptr, L.Cin,
                           static_cast<float*>(L.dsraw.ptr), grads + L.skip_w, grads + L.skip_g, grads + L.skip_be,
@@ -928,15 +939,14 @@ int backward_level(dsr_plan* p, int i, const float* params, float* grads, cudaSt
   if (!last && (rc = backward_level(p, i + 1, params, grads, s))) return rc;
   // ---- encoder ----
   if (last) {
-    rc = bn_backward(p, L.d2, params, grads, L.g_d2a.ptr, kNC, 0, nullptr, nullptr, s);
+    rc = bn_backward(p, L.d2, params, grads, L.g_d2a.ptr, kNC, 0, nullptr, s);
   } else {
     Level& N = p->lv[i + 1];
-    rc = bn_backward(p, L.d2, params, grads, N.d1.gin.ptr, kNC, 1, static_cast<const float*>(N.dsraw.ptr),
-                     params + N.skip_w, s);
+    rc = bn_backward(p, L.d2, params, grads, N.d1.gin.ptr, kNC, 1, &N, s);
   }
   if (rc) return rc;
   if ((rc = conv_backward(p, L.d2, s))) return rc;
-  if ((rc = bn_backward(p, L.d1, params, grads, L.d2.gin.ptr, kNC, 1, nullptr, nullptr, s))) return rc;
+  if ((rc = bn_backward(p, L.d1, params, grads, L.d2.gin.ptr, kNC, 1, nullptr, s))) return rc;
   if ((rc = conv_backward(p, L.d1, s))) return rc;
   return 0;
 }
