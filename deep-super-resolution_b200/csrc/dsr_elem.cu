@@ -1644,35 +1644,65 @@ __global__ void skip_bwd_kernel(const float* __restrict__ dsy, const float* __re
   for (int o = 0; o < 4; ++o)
 #pragma unroll
     for (int j = 0; j < 8; ++j) aw[o][j] = 0.f;
-  const long long npix = static_cast<long long>(H) * W;
+  const int npix = H * W;
   const int Wp = W + 2;
-  for (long long pix = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) / G; pix < npix;
-       pix += (static_cast<long long>(gridDim.x) * blockDim.x) / G) {
-    const int y = static_cast<int>(pix / W), x = static_cast<int>(pix % W);
-    const float4 d = *reinterpret_cast<const float4*>(dsy + pix * 4);
-    const float4 r = *reinterpret_cast<const float4*>(sraw + pix * 4);
-    const float dd[4] = {d.x, d.y, d.z, d.w}, rr[4] = {r.x, r.y, r.z, r.w};
-    float dr[4];
+  const int stride = (gridDim.x * blockDim.x) / G;
+  for (int pix0 = (blockIdx.x * blockDim.x + threadIdx.x) / G; pix0 < npix; pix0 += 2 * stride) {
+    // two pixels per pass: all six loads are issued before any arithmetic
+    float4 d[2], r[2];
+    uint4 xv[2];
+    bool okp[2];
 #pragma unroll
-    for (int o = 0; o < 4; ++o) {
-      const float xh = (rr[o] - mean[o]) * rstd[o];
-      dr[o] = ga[o] * rstd[o] * (dd[o] - c1[o] - xh * c2[o]);
+    for (int u = 0; u < 2; ++u) {
+      const int pix = pix0 + u * stride;
+      okp[u] = pix < npix;
+      if (okp[u]) {
+        const int y = pix / W, x = pix - y * W;
+        d[u] = __ldg(reinterpret_cast<const float4*>(dsy + static_cast<long long>(pix) * 4));
+        r[u] = __ldg(reinterpret_cast<const float4*>(sraw + static_cast<long long>(pix) * 4));
+        xv[u] = __ldg(reinterpret_cast<const uint4*>(xpad + (static_cast<long long>(y + 1) * Wp + (x + 1)) * CIN + g * 8));
+      }
     }
-    if (g == 0) *reinterpret_cast<float4*>(dsraw + pix * 4) = make_float4(dr[0], dr[1], dr[2], dr[3]);
-    float f[8];
-    load8h(xpad + (static_cast<long long>(y + 1) * Wp + (x + 1)) * CIN + g * 8, f);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (!okp[u]) continue;
+      const int pix = pix0 + u * stride;
+      const float dd[4] = {d[u].x, d[u].y, d[u].z, d[u].w}, rr[4] = {r[u].x, r[u].y, r[u].z, r[u].w};
+      float dr[4];
+#pragma unroll
+      for (int o = 0; o < 4; ++o) {
+        const float xh = (rr[o] - mean[o]) * rstd[o];
+        dr[o] = ga[o] * rstd[o] * (dd[o] - c1[o] - xh * c2[o]);
+      }
+      if (g == 0) *reinterpret_cast<float4*>(dsraw + static_cast<long long>(pix) * 4) = make_float4(dr[0], dr[1], dr[2], dr[3]);
+      float f[8];
+      {
+        const __half2* hh = reinterpret_cast<const __half2*>(&xv[u]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { const float2 t = __half22float2(hh[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+      }
+#pragma unroll
+      for (int o = 0; o < 4; ++o)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) aw[o][j] = fmaf(dr[o], f[j], aw[o][j]);
+    }
+  }
+  // lanes with the same channel group (lane % G) hold partial sums of the same 32 weights: shuffle-reduce them first
+#pragma unroll
+  for (int sh = 16; sh >= G; sh >>= 1)
 #pragma unroll
     for (int o = 0; o < 4; ++o)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) aw[o][j] = fmaf(dr[o], f[j], aw[o][j]);
-  }
+      for (int j = 0; j < 8; ++j) aw[o][j] += __shfl_xor_sync(0xffffffffu, aw[o][j], sh);
   __shared__ float red[4 * CIN];
   for (int i = threadIdx.x; i < 4 * CIN; i += blockDim.x) red[i] = 0.f;
   __syncthreads();
+  if ((threadIdx.x & 31) < G) {
 #pragma unroll
-  for (int o = 0; o < 4; ++o)
+    for (int o = 0; o < 4; ++o)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(&red[o * CIN + g * 8 + j], aw[o][j]);
+      for (int j = 0; j < 8; ++j) atomicAdd(&red[o * CIN + g * 8 + j], aw[o][j]);
+  }
   __syncthreads();
   for (int i = threadIdx.x; i < 4 * CIN; i += blockDim.x) atomicAdd(&dw[i], red[i] * invS);
   if (blockIdx.x == 0 && threadIdx.x < 4) {
@@ -1685,7 +1715,7 @@ int launch_skip_bwd(const float* dsy, const float* sraw, BnRef bn_skip, const fl
                     float* dsraw, float* dw, float* dgamma, float* dbeta, const float* gs, int H, int W,
                     cudaStream_t s) {
   const long long items = static_cast<long long>(H) * W * (Cin / 8);
-  const int grid = grid_for(items, kThreads, 148 * 2);
+  const int grid = grid_for(items, kThreads, 148 * 4);
   if (Cin == 32)
     launch_k(skip_bwd_kernel<32>, dim3(grid), dim3(kThreads), 0, s, dsy, sraw, bn_skip, sbstats, static_cast<const __half*>(xpad), dsraw, dw, dgamma, dbeta, gs, H, W);
   else if (Cin == 128)
@@ -2257,63 +2287,97 @@ int launch_upsample_bwd(const void* dup_pad, int H, int W, void* ddeep_pad, int 
 // =============================================================================================
 // weight packing / gradient unpacking
 // =============================================================================================
-__device__ __forceinline__ int ref_ci(const PackDesc& d, int j) { return d.perm ? (j < 128 ? j + 4 : j - 128) : j; }
 
-__global__ void pack_weights_kernel(const float* __restrict__ params, __half* __restrict__ arena,
-                                    const PackDesc* __restrict__ table, int nlayers) {
+// Tiled transposes through shared memory: a block owns a 32 (co) x 32 (packed ci j) tile of one layer for all
+// taps.  The reference layout [co][ci][tap] is read / written as rows of 32 * taps contiguous floats (within a
+// 32-aligned tile the packed -> reference channel map is a constant offset), the packed GEMM layouts as
+// 64-byte (fp16) / 128-byte (fp32) row segments.  Row pitch 32 * taps + 1 keeps both access directions
+// conflict-free.
+constexpr int kPkTile = 32;
+constexpr int kPkMaxTaps = 9;
+constexpr int kPkPitch = kPkTile * kPkMaxTaps + 1;
+
+__global__ void __launch_bounds__(kThreads) pack_weights_kernel(const float* __restrict__ params, __half* __restrict__ arena,
+                                                                const PackDesc* __restrict__ table, int nlayers) {
   pdl_sync();
+  __shared__ float T[kPkTile * kPkPitch];
   const PackDesc d = table[blockIdx.y];
   const int taps = d.k * d.k;
-  const long long nf = static_cast<long long>(taps) * 128 * d.cin_pad;
-  const long long nd = static_cast<long long>(taps) * d.n_rows * 128;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nf + nd;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    if (i < nf) {                                   // fprop matrix [tap][co][j]
-      const int j = static_cast<int>(i % d.cin_pad);
-      const int co = static_cast<int>((i / d.cin_pad) % 128);
-      const int tap = static_cast<int>(i / (static_cast<long long>(d.cin_pad) * 128));
-      float v = 0.f;
-      if (j < d.cin && co < d.cout) v = params[d.w_off + (static_cast<long long>(co) * d.cin + ref_ci(d, j)) * taps + tap];
-      arena[d.f_off + i] = __float2half_rn(v);
-    } else {                                        // dgrad matrix [tap][j][co]
-      const long long k = i - nf;
-      const int co = static_cast<int>(k % 128);
-      const int j = static_cast<int>((k / 128) % d.n_rows);
-      const int tap = static_cast<int>(k / (128LL * d.n_rows));
-      float v = 0.f;
-      if (j < d.cin && co < d.cout) v = params[d.w_off + (static_cast<long long>(co) * d.cin + ref_ci(d, j)) * taps + tap];
-      arena[d.d_off + k] = __float2half_rn(v);
+  const int jmax = max(d.cin_pad, d.n_rows);
+  const int jt = (jmax + kPkTile - 1) / kPkTile;
+  if (static_cast<int>(blockIdx.x) >= 4 * jt) return;
+  const int co0 = (blockIdx.x & 3) * kPkTile, j0 = (blockIdx.x >> 2) * kPkTile;
+  const int row_len = kPkTile * taps;
+  // tile channel map: j -> reference ci = j + off (perm: j < 128 -> +4, j >= 128 -> -128; 128 is a tile boundary)
+  const int off = d.perm ? (j0 < 128 ? 4 : -128) : 0;
+#pragma unroll 6
+  for (int i = threadIdx.x; i < kPkTile * row_len; i += kThreads) {
+    const int r = i / row_len, e = i - r * row_len;          // e = jj * taps + tap
+    const int jj = e / taps;
+    const int co = co0 + r, j = j0 + jj;
+    float v = 0.f;
+    if (co < d.cout && j < d.cin) v = __ldg(params + d.w_off + (static_cast<long long>(co) * d.cin + j + off) * taps + (e - jj * taps));
+    T[r * kPkPitch + e] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < taps * kPkTile * kPkTile; i += kThreads) {
+    const int tap = i / (kPkTile * kPkTile), rem = i - tap * (kPkTile * kPkTile);
+    const int a = rem >> 5, b2 = rem & 31;
+    {                                              // fprop matrix [tap][co][j]: row co0 + a, columns j0 + b2
+      const int j = j0 + b2;
+      if (j < d.cin_pad)
+        arena[d.f_off + (static_cast<long long>(tap) * 128 + co0 + a) * d.cin_pad + j] = __float2half_rn(T[a * kPkPitch + b2 * taps + tap]);
+    }
+    {                                              // dgrad matrix [tap][j][co]: row j0 + a, columns co0 + b2
+      const int j = j0 + a;
+      if (j < d.n_rows)
+        arena[d.d_off + (static_cast<long long>(tap) * d.n_rows + j) * 128 + co0 + b2] = __float2half_rn(T[b2 * kPkPitch + a * taps + tap]);
     }
   }
   (void)nlayers;
 }
 
 int launch_pack_weights(const float* params, void* arena, const PackDesc* table_dev, int nlayers, cudaStream_t s) {
-  dim3 grid(64, nlayers);
+  dim3 grid(4 * 5, nlayers);                       // up to 5 j-tiles (144 packed channels)
   launch_k(pack_weights_kernel, dim3(grid), dim3(kThreads), 0, s, params, static_cast<__half*>(arena), table_dev, nlayers);
   DSR_LAUNCH_CHECK();
 }
 
-__global__ void unpack_wgrad_kernel(const float* __restrict__ garena, float* __restrict__ grads,
-                                    const PackDesc* __restrict__ table, const float* __restrict__ gs) {
+__global__ void __launch_bounds__(kThreads) unpack_wgrad_kernel(const float* __restrict__ garena, float* __restrict__ grads,
+                                                                const PackDesc* __restrict__ table,
+                                                                const float* __restrict__ gs) {
   pdl_sync();
+  __shared__ float T[kPkTile * kPkPitch];
   const PackDesc d = table[blockIdx.y];
   const float invS = gs[1];
   const int taps = d.k * d.k;
-  const long long n = static_cast<long long>(d.cout) * d.cin * taps;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int tap = static_cast<int>(i % taps);
-    const int ci = static_cast<int>((i / taps) % d.cin);
-    const int co = static_cast<int>(i / (static_cast<long long>(taps) * d.cin));
-    const int j = d.perm ? (ci >= 4 ? ci - 4 : ci + 128) : ci;
-    grads[d.w_off + i] = invS * garena[d.g_off + (static_cast<long long>(tap) * 128 + co) * d.cin_pad + j];
+  const int jt = (d.cin_pad + kPkTile - 1) / kPkTile;
+  if (static_cast<int>(blockIdx.x) >= 4 * jt) return;
+  const int co0 = (blockIdx.x & 3) * kPkTile, j0 = (blockIdx.x >> 2) * kPkTile;
+  const int off = d.perm ? (j0 < 128 ? 4 : -128) : 0;
+#pragma unroll 6
+  for (int i = threadIdx.x; i < taps * kPkTile * kPkTile; i += kThreads) {     // packed [tap][co][j] rows -> T[co][j][tap]
+    const int tap = i / (kPkTile * kPkTile), rem = i - tap * (kPkTile * kPkTile);
+    const int r = rem >> 5, jj = rem & 31;
+    const int j = j0 + jj;
+    float v = 0.f;
+    if (j < d.cin_pad) v = __ldg(garena + d.g_off + (static_cast<long long>(tap) * 128 + co0 + r) * d.cin_pad + j);
+    T[r * kPkPitch + jj * taps + tap] = v;
+  }
+  __syncthreads();
+  const int row_len = kPkTile * taps;
+  for (int i = threadIdx.x; i < kPkTile * row_len; i += kThreads) {
+    const int r = i / row_len, e = i - r * row_len;
+    const int jj = e / taps;
+    const int co = co0 + r, j = j0 + jj;
+    if (co < d.cout && j < d.cin)
+      grads[d.w_off + (static_cast<long long>(co) * d.cin + j + off) * taps + (e - jj * taps)] = invS * T[r * kPkPitch + e];
   }
 }
 
 int launch_unpack_wgrad(const float* garena, float* grads, const PackDesc* table_dev, int nlayers, const float* gs,
                         cudaStream_t s) {
-  dim3 grid(32, nlayers);
+  dim3 grid(4 * 5, nlayers);
   launch_k(unpack_wgrad_kernel, dim3(grid), dim3(kThreads), 0, s, garena, grads, table_dev, gs);
   DSR_LAUNCH_CHECK();
 }
