@@ -15,9 +15,10 @@ utils/DIP.py:35-38.
              get_params, optimize and a closure written like DIP.py:47-95) with HOST buffers: the step's perturbed
              input z comes from pinned host memory (H2D inside the timed region, as DIP.py:57 does) and out_HR /
              out_LR / loss are read back every step (DIP.py:90-91).
-* roofline   the dominant kernel, conv_halo2_kernel (stride-1 3x3 / 1x1 fprop + dgrad = 60 % of the iteration's
+* roofline   the dominant kernel, conv_halo2_kernel on the stride-1 3x3 layers (fprop + dgrad, 56 % of the iteration's
              FLOPs): algorithmic FLOPs / CUDA-event time per launch, summed over a profiled pass (all 5 levels, the
-             latency-bound 16x16..64x64 launches included), against MEASURED_PEAKS.json bf16 (sustained) peak.
+             latency-bound 16x16..64x64 launches included), against MEASURED_PEAKS.json bf16 (sustained) peak.  Its
+             1x1 launches (64 FLOP per byte) are listed against the HBM roof, the other tensor-core kernels beside.
 * cpu_baseline / --impl reference   the CPU restatement of the reference path (oracle/dip_oracle.py: the same
              torch CPU primitives the reference's nn.Modules call), all host threads, same workload.
 """
@@ -255,7 +256,8 @@ def run_ours(args, rank, local_rank, world):
         torch.cuda.synchronize()
         pk = peaks()
         res = {}
-        for cls, name in ((0, 'conv_halo2_kernel'), (1, 'wgrad_halo_kernel'), (2, 'conv_gemm_kernel')):
+        for cls, name in ((0, 'conv_halo2_kernel'), (1, 'wgrad_halo_kernel'), (2, 'conv_gemm_kernel'),
+                          (3, 'conv_halo2_kernel_1x1')):
             msx, fl, n = C.c_double(), C.c_double(), C.c_int()
             check(lib.dsr_plan_profile_read(plan.handle, cls, C.byref(msx), C.byref(fl), C.byref(n)))
             res[name] = dict(ms_per_step=msx.value / nprof, tflops=(fl.value / (msx.value * 1e-3) / 1e12) if msx.value else 0.0,
@@ -267,9 +269,15 @@ def run_ours(args, rank, local_rank, world):
         top['frac'] = top['tflops'] / pk['tflops'] if pk['tflops'] else None
         check(lib.dsr_plan_set_profile(plan.handle, 0))
         a = res['conv_halo2_kernel']
+        # the same kernel on the 1x1 layers moves 2 x 128 channels x 2 B per pixel for 2 x 128 x 128 FLOP: 64 FLOP/B,
+        # HBM-bound (<= ~410 TFLOP/s at the measured copy bandwidth); reported against the HBM roof
+        one = res['conv_halo2_kernel_1x1']
+        one_gbs = (one['gflop_per_step'] / 64.0) / (one['ms_per_step'] * 1e-3) if one['ms_per_step'] else 0.0
+        one.update({'bound': 'hbm', 'achieved_gbs': one_gbs, 'peak_gbs': pk['hbm'],
+                    'frac': one_gbs / pk['hbm'] if pk['hbm'] else None})
         roof = {'bound': 'tensor',
-                'kernel': 'conv_halo2_kernel (halo-tile implicit-GEMM, stride-1 3x3 / 1x1 fprop + dgrad, tcgen05 '
-                          'cta_group::2 kind::f16)',
+                'kernel': 'conv_halo2_kernel, 3x3 launches (halo-tile implicit-GEMM, stride-1 fprop + dgrad, tcgen05 '
+                          'cta_group::2 kind::f16; all 5 levels incl. the latency-bound 16^2..64^2 ones)',
                 'achieved': a['tflops'], 'peak': pk['tflops'], 'unit': 'TFLOP/s',
                 'frac': a['tflops'] / pk['tflops'] if pk['tflops'] else None, 'traffic': ncu_traffic(),
                 'traffic_note': 'DRAM read+write bytes of the largest launch (L0 decoder 3x3 fprop, 79.7 GFLOP, '
@@ -277,7 +285,7 @@ def run_ours(args, rank, local_rank, world):
                 'peak_source': pk['src'],
                 'kernel_ms_per_step': a['ms_per_step'], 'launches_per_step': a['launches_per_step'],
                 'gflop_per_step': a['gflop_per_step'], 'largest_launch': top, 'wgrad_halo_kernel': res['wgrad_halo_kernel'],
-                'conv_gemm_kernel': res['conv_gemm_kernel'],
+                'conv_gemm_kernel': res['conv_gemm_kernel'], 'conv_halo2_kernel_1x1': one,
                 'step_tflops_all_convs': FLOPS_PER_ITER.get(size, 0) / (ms / args.steps * 1e-3) / 1e12}
 
     # ---- configs[2] flavour: two independent images in flight on this GPU (separate nets / plans / streams):

@@ -942,6 +942,10 @@ int launch_final_bwd(const float* gout, const float* out, const void* act_pad, c
 // straight from the raw tensor.  Saves ~470 MB of HBM traffic per 512x512 iteration.
 // The activation is rounded to fp16 exactly as the unfused path stored it, so both paths agree.
 // =============================================================================================
+// 8 pixels per warp pass (lane = 4 channels, 8 independent 256-byte row loads in flight); the 8 x 3 partial dot
+// products are reduced with a transposed butterfly (32 values over 32 lanes, 31 shuffles): lane l ends up with the
+// full sum of value l = pixel (l >> 2), output (l & 3), applies bias + sigmoid and stores it.
+constexpr int kFinUnroll = 8;
 __global__ void __launch_bounds__(kThreads, 3) bn_act_final_kernel(const __half* __restrict__ raw, BnRef bn,
                                                                    const float* __restrict__ w,
                                                                    const float* __restrict__ b,
@@ -959,17 +963,17 @@ __global__ void __launch_bounds__(kThreads, 3) bn_act_final_kernel(const __half*
 #pragma unroll
     for (int o = 0; o < 3; ++o) wr[o][j] = w[o * 128 + c0 + j];
   }
-  const float b0 = b[0], b1 = b[1], b2 = b[2];
+  const int my_o = lane & 3;
+  const float my_b = my_o < 3 ? b[my_o] : 0.f;
   const int warps = (gridDim.x * blockDim.x) >> 5;
-  for (int base = (((blockIdx.x * blockDim.x) + threadIdx.x) >> 5) * kPixUnroll; base < npix;
-       base += warps * kPixUnroll) {
-    uint2 v[kPixUnroll];
+  for (int base = (((blockIdx.x * blockDim.x) + threadIdx.x) >> 5) * kFinUnroll; base < npix;
+       base += warps * kFinUnroll) {
+    uint2 v[kFinUnroll];
 #pragma unroll
-    for (int u = 0; u < kPixUnroll; ++u)
-      if (base + u < npix) v[u] = ldg8(raw + static_cast<long long>(base + u) * 128 + c0);
-    float acc[kPixUnroll][3];
+    for (int u = 0; u < kFinUnroll; ++u) v[u] = ldg8(raw + static_cast<long long>(min(base + u, npix - 1)) * 128 + c0);
+    float acc[kFinUnroll * 4];
 #pragma unroll
-    for (int u = 0; u < kPixUnroll; ++u) {
+    for (int u = 0; u < kFinUnroll; ++u) {
       float f[4];
       cvt4h(v[u], f);
 #pragma unroll
@@ -977,52 +981,63 @@ __global__ void __launch_bounds__(kThreads, 3) bn_act_final_kernel(const __half*
       float a[4];
       cvt4h(pack4h(f), a);                 // the fp16-rounded activation
 #pragma unroll
-      for (int o = 0; o < 3; ++o) acc[u][o] = a[0] * wr[o][0] + a[1] * wr[o][1] + a[2] * wr[o][2] + a[3] * wr[o][3];
+      for (int o = 0; o < 3; ++o) acc[u * 4 + o] = a[0] * wr[o][0] + a[1] * wr[o][1] + a[2] * wr[o][2] + a[3] * wr[o][3];
+      acc[u * 4 + 3] = 0.f;
     }
 #pragma unroll
-    for (int d = 16; d >= 1; d >>= 1)
+    for (int step = 0; step < 5; ++step) {
+      const int off = 16 >> step, n = 16 >> step;          // lanes with bit `off` set keep the upper half
+      const bool up = lane & off;
 #pragma unroll
-      for (int u = 0; u < kPixUnroll; ++u)
-#pragma unroll
-        for (int o = 0; o < 3; ++o) acc[u][o] += __shfl_xor_sync(0xffffffffu, acc[u][o], d);
-    if (lane < kPixUnroll * 3) {            // lane = u * 3 + o writes one output value
-      const int u = lane / 3, o = lane - u * 3;
-      if (base + u < npix) {
-        float val = 0.f;
-#pragma unroll
-        for (int uu = 0; uu < kPixUnroll; ++uu)
-#pragma unroll
-          for (int oo = 0; oo < 3; ++oo)
-            if (uu == u && oo == o) val = acc[uu][oo];
-        val += (o == 0) ? b0 : (o == 1) ? b1 : b2;
-        out[static_cast<long long>(o) * npix + base + u] = 1.f / (1.f + __expf(-val));
+      for (int i = 0; i < n; ++i) {
+        const float send = up ? acc[i] : acc[i + n];
+        const float keep = up ? acc[i + n] : acc[i];
+        acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
       }
     }
+    const int u = lane >> 2;
+    if (my_o < 3 && base + u < npix)
+      out[static_cast<long long>(my_o) * npix + base + u] = 1.f / (1.f + __expf(-(acc[0] + my_b)));
   }
 }
 
 int launch_bn_act_final(const void* raw, BnRef bn, const float* w, const float* b, float* out, int H, int W,
                         cudaStream_t s) {
-  launch_k(bn_act_final_kernel, dim3(warp_grid(H, W, 148 * 8)), dim3(kThreads), 0, s, static_cast<const __half*>(raw), bn, w, b, out, H * W);
+  long long blocks = (static_cast<long long>(H) * W + 8 * kFinUnroll - 1) / (8 * kFinUnroll);
+  if (blocks > 148 * 6) blocks = 148 * 6;
+  launch_k(bn_act_final_kernel, dim3(static_cast<int>(blocks < 1 ? 1 : blocks)), dim3(kThreads), 0, s,
+           static_cast<const __half*>(raw), bn, w, b, out, H * W);
   DSR_LAUNCH_CHECK();
 }
 
+// Per channel, with y = k1 r + sh (k1 = gamma rstd, sh = beta - mean k1) and the LeakyReLU slope m = (y > 0 ? 1 : 0.2):
+//   da = sum_o dp[o] w[o][c],  dy = m da,  act = m y
+//   stats:  S1 += dy,  S2r += dy r   (sum dy xhat = rstd (S2r - mean S1), applied when the block sums are flushed),
+//           dW[o][c] += dp[o] act (fp16-rounded act, as the forward used),  db[o] += dp[o]
+//   apply:  dr = k1 dy + (A + B r),  B = -k1 c2 rstd,  A = -k1 (c1 - c2 mean rstd)
+// A warp takes 32 consecutive pixels: lane l fetches dp of pixel l (3 coalesced loads), then the warp walks the 32
+// pixels 8 at a time (lane = 4 channels, 8 independent 256-byte row loads in flight), dp broadcast by shuffle.
+constexpr int kTopUnroll = 8;
 template <bool APPLY>
-__global__ void __launch_bounds__(kThreads, 2) bn_bwd_top_kernel(TopBwdArgs a) {
+__global__ void __launch_bounds__(kThreads, 3) bn_bwd_top_kernel(TopBwdArgs a) {
   pdl_sync();
   const int lane = threadIdx.x & 31;
   const int c0 = lane * 4;
   const float S = a.gs[0], invS = a.gs[1];
-  float xa[4], xb[4], ga[4], be[4], c1[4], c2[4], k1[4], s1[4], s2[4], wr[3][4], aw[3][4], ab[3] = {0.f, 0.f, 0.f};
+  float k1[4], sh[4], A[4], B[4], s1[4], s2[4], wr[3][4], aw[3][4], ab[3] = {0.f, 0.f, 0.f}, mean_[4], rstd_[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    float mean, rstd;
-    bn_coeffs(a.bn, c0 + j, mean, rstd, ga[j], be[j]);
-    xa[j] = rstd;
-    xb[j] = -mean * rstd;
-    k1[j] = ga[j] * rstd;
-    c1[j] = APPLY ? a.bstats[c0 + j] * a.bn.inv_n : 0.f;
-    c2[j] = APPLY ? a.bstats[128 + c0 + j] * a.bn.inv_n : 0.f;
+    float mean, rstd, ga, be;
+    bn_coeffs(a.bn, c0 + j, mean, rstd, ga, be);
+    k1[j] = ga * rstd;
+    sh[j] = be - mean * k1[j];
+    mean_[j] = mean;
+    rstd_[j] = rstd;
+    if (APPLY) {
+      const float c1 = a.bstats[c0 + j] * a.bn.inv_n, c2 = a.bstats[128 + c0 + j] * a.bn.inv_n;
+      B[j] = -k1[j] * c2 * rstd;
+      A[j] = -k1[j] * (c1 - c2 * mean * rstd);
+    }
     s1[j] = 0.f;
     s2[j] = 0.f;
 #pragma unroll
@@ -1032,8 +1047,8 @@ __global__ void __launch_bounds__(kThreads, 2) bn_bwd_top_kernel(TopBwdArgs a) {
     }
   }
   const int W = a.W, npix = a.H * a.W, Wp = W + 2;
-  const __half* __restrict__ raw = static_cast<const __half*>(a.raw);
-  __half* __restrict__ dr = static_cast<__half*>(a.dr_pad);
+  const __half* __restrict__ raw = static_cast<const __half*>(a.raw) + c0;
+  __half* __restrict__ dr = static_cast<__half*>(a.dr_pad) + c0;
   __half2 amax2 = __float2half2_rn(0.f);
   const int warps = (gridDim.x * blockDim.x) >> 5;
   for (int base = (((blockIdx.x * blockDim.x) + threadIdx.x) >> 5) * 32; base < npix; base += warps * 32) {
@@ -1048,31 +1063,29 @@ __global__ void __launch_bounds__(kThreads, 2) bn_bwd_top_kernel(TopBwdArgs a) {
     }
     const int cnt = min(32, npix - base);
     const int y0 = base / W, x0 = base - y0 * W;
-    for (int j0 = 0; j0 < cnt; j0 += 4) {
-      uint2 v[4];
+    for (int j0 = 0; j0 < cnt; j0 += kTopUnroll) {
+      uint2 v[kTopUnroll];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = ldg8(raw + static_cast<long long>(min(base + j0 + u, npix - 1)) * 128 + c0);
+      for (int u = 0; u < kTopUnroll; ++u) v[u] = ldg8(raw + static_cast<long long>(min(base + j0 + u, npix - 1)) * 128);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < kTopUnroll; ++u) {
         const float d0 = __shfl_sync(0xffffffffu, dp[0], j0 + u);
         const float d1 = __shfl_sync(0xffffffffu, dp[1], j0 + u);
         const float d2 = __shfl_sync(0xffffffffu, dp[2], j0 + u);
         if (j0 + u < cnt) {
-          float r[4], o4[4];
+          float r[4], o4[4], actf[4];
           cvt4h(v[u], r);
-          float actf[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const float xh = fmaf(r[j], xa[j], xb[j]);
-            const float yv = fmaf(ga[j], xh, be[j]);
-            const float da = d0 * wr[0][j] + d1 * wr[1][j] + d2 * wr[2][j];
-            const float dy = yv > 0.f ? da : kSlope * da;
-            actf[j] = lrelu(yv);
+            const float yv = fmaf(k1[j], r[j], sh[j]);
+            const float m = yv > 0.f ? 1.f : kSlope;
+            const float dy = m * fmaf(d0, wr[0][j], fmaf(d1, wr[1][j], d2 * wr[2][j]));
             if (APPLY) {
-              o4[j] = k1[j] * (dy - c1[j] - xh * c2[j]);
+              o4[j] = fmaf(k1[j], dy, fmaf(B[j], r[j], A[j]));
             } else {
+              actf[j] = m * yv;
               s1[j] += dy;
-              s2[j] = fmaf(dy, xh, s2[j]);
+              s2[j] = fmaf(dy, r[j], s2[j]);
             }
           }
           if (APPLY) {
@@ -1081,7 +1094,7 @@ __global__ void __launch_bounds__(kThreads, 2) bn_bwd_top_kernel(TopBwdArgs a) {
             const uint2 pk = pack4h(o4);
             const __half2* h2 = reinterpret_cast<const __half2*>(&pk);
             amax2 = __hmax2_nan(amax2, __hmax2_nan(__habs2(h2[0]), __habs2(h2[1])));
-            stg8(dr + (static_cast<long long>(y + 1) * Wp + (x + 1)) * 128 + c0, pk);
+            stg8(dr + (static_cast<long long>(y + 1) * Wp + (x + 1)) * 128, pk);
           } else {
             float ah[4];
             cvt4h(pack4h(actf), ah);         // the fp16-rounded activation the forward pass used
@@ -1103,7 +1116,7 @@ __global__ void __launch_bounds__(kThreads, 2) bn_bwd_top_kernel(TopBwdArgs a) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       atomicAdd(&red[c0 + j], s1[j]);
-      atomicAdd(&red[128 + c0 + j], s2[j]);
+      atomicAdd(&red[128 + c0 + j], rstd_[j] * (s2[j] - mean_[j] * s1[j]));      // sum dy * xhat
 #pragma unroll
       for (int o = 0; o < 3; ++o) atomicAdd(&red[256 + o * 128 + c0 + j], aw[o][j]);
     }
@@ -1126,7 +1139,7 @@ __global__ void __launch_bounds__(kThreads, 2) bn_bwd_top_kernel(TopBwdArgs a) {
 int launch_bn_bwd_top_stats(const TopBwdArgs& a, cudaStream_t s) {
   const long long npix = static_cast<long long>(a.H) * a.W;
   long long blocks = (npix + 255) / 256;
-  if (blocks > 148 * 4) blocks = 148 * 4;
+  if (blocks > 148 * 3) blocks = 148 * 3;
   launch_k(bn_bwd_top_kernel<false>, dim3(static_cast<int>(blocks)), dim3(kThreads), 0, s, a);
   DSR_LAUNCH_CHECK();
 }

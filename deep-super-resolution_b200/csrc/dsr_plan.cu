@@ -175,8 +175,9 @@ struct dsr_plan {
   unsigned long long pseed = 0;
   int fuse_top = 1;              // level 0: BN/LeakyReLU of the last decoder conv fused with the final conv (fwd + bwd)
   bool bound = false, have_forward = false;
-  // optional per-launch timing of the tensor-core kernels (bench.py roofline): class 0 = halo-tile conv (stride-1
-  // fprop + dgrad), 1 = wgrad, 2 = generic implicit-GEMM conv (stride-2 layers, 32-channel input)
+  // optional per-launch timing of the tensor-core kernels (bench.py roofline): class 0 = halo-tile conv (3x3
+  // stride-1 fprop + dgrad), 1 = wgrad, 2 = generic implicit-GEMM conv (stride-2 layers, 32-channel input), 3 = halo-tile
+  // conv on 1x1 layers (memory-bound)
   struct ProfRec { int cls; cudaEvent_t a, b; double flops; };
   std::vector<ProfRec> prof;
   struct AllRec { const char* what; cudaEvent_t a, b; };
@@ -770,7 +771,7 @@ struct ProfScope {
 };
 int run_fprop(dsr_plan* p, ConvLayer& c, cudaStream_t s) {
   if (p->debug_conv) return launch_conv_ref(c.fprop, c.ref_in, c.ref_wf, s);
-  ProfScope ps(p, (c.has_halo && p->use_halo) ? 0 : 2, conv_flops(c), s);
+  ProfScope ps(p, (c.has_halo && p->use_halo) ? (c.k == 1 ? 3 : 0) : 2, conv_flops(c), s);
   if (c.has_halo && p->use_halo) return launch_conv_halo(c.hfprop, p->num_sms, s);
   return launch_conv_gemm(c.fprop, p->num_sms, s);
 }
@@ -781,7 +782,7 @@ int run_dgrad(dsr_plan* p, ConvLayer& c, int i, cudaStream_t s) {
     ProfScope ps(p, 2, conv_flops(c), s);
     return launch_conv_gemm(c.dgrad_merged, p->num_sms, s);
   }
-  ProfScope ps(p, (c.has_halo && p->use_halo) ? 0 : 2, conv_flops(c) / c.ndgrad, s);
+  ProfScope ps(p, (c.has_halo && p->use_halo) ? (c.k == 1 ? 3 : 0) : 2, conv_flops(c) / c.ndgrad, s);
   if (c.has_halo && p->use_halo) return launch_conv_halo(c.hdgrad, p->num_sms, s);
   return launch_conv_gemm(c.dgrad[i], p->num_sms, s);
 }

@@ -132,7 +132,8 @@ int dsr_plan_set_debug_conv(dsr_plan_t* p, int use_checker_kernels);
 int dsr_plan_debug_replay(dsr_plan_t* p, const char* layer, int what, int use_checker, void* stream);
 /* Per-launch CUDA-event timing of the tensor-core kernels (used by bench.py for the roofline figure; off by
  * default).  set_profile(on) clears earlier records.  profile_read sums, for kernel class `cls` (0 = halo-tile
- * conv kernel: stride-1 fprop + dgrad launches, 1 = wgrad kernels, 2 = generic implicit-GEMM conv kernel: stride-2 layers), the event-measured milliseconds, the algorithmic FLOPs
+ * conv kernel, 3x3 stride-1 fprop + dgrad launches (tensor-bound), 1 = wgrad kernels, 2 = generic implicit-GEMM conv
+ * kernel: stride-2 layers, 3 = halo-tile conv kernel, 1x1 launches (64 FLOP per byte: HBM-bound)), the event-measured milliseconds, the algorithmic FLOPs
  * (2*M*N*K per pass, true channel counts) and the number of launches recorded since; it synchronises on them. */
 int dsr_plan_set_profile(dsr_plan_t* p, int on);
 int dsr_plan_profile_read(dsr_plan_t* p, int cls, double* ms_total, double* flops_total, int* launches);
