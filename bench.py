@@ -187,7 +187,7 @@ def run_ours(args, rank, local_rank, world):
     dev = torch.device('cuda', local_rank)
     torch.cuda.set_device(dev)
     # everything runs on one non-default stream (the legacy default stream cannot be captured into a CUDA graph)
-    torch.cuda.set_stream(torch.cuda.Stream(device=dev))
+    torch.cuda.set_stream(torch.cuda.Stream(device=dev, priority=int(os.environ.get('DSR_BENCH_PRIO', '0'))))
     size = args.size
     H = W = size
 

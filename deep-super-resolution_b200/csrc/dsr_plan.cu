@@ -499,7 +499,12 @@ int build_conv(dsr_plan* p, ConvLayer& c) {
     g.pb_x = (c.outW + g.pw - 1) / g.pw;
     g.pb_y = (c.outH + g.ph - 1) / g.ph;
     const int npb = g.pb_x * g.pb_y;
+    // split-K over pixel ranges: every CTA ends with a full-size fp32 atomic epilogue (128 x up to 432 values), so
+    // small layers get few CTAs (>= kWgMinBlocks pixel blocks each) -- less atomic traffic, and SMs left free for
+    // the main stream's conv kernels that run beside the weight-gradient stream
     int nsplit = p->num_sms / g.ngroups;
+    const int kWgMinBlocks = getenv("DSR_WG_MINBLK") ? atoi(getenv("DSR_WG_MINBLK")) : 16;
+    if (nsplit > npb / kWgMinBlocks) nsplit = npb / kWgMinBlocks;
     if (nsplit > npb) nsplit = npb;
     if (nsplit < 1) nsplit = 1;
     g.nsplit = nsplit;
@@ -604,7 +609,12 @@ int build_conv(dsr_plan* p, ConvLayer& c) {
     }
     if (g.nbox == 1) { g.b64[1] = g.b64[0]; g.b16[1] = g.b16[0]; }
     const int npb = g.pb_x * g.pb_y;
+    // split-K over pixel ranges: every CTA ends with a full-size fp32 atomic epilogue (128 x up to 432 values), so
+    // small layers get few CTAs (>= kWgMinBlocks pixel blocks each) -- less atomic traffic, and SMs left free for
+    // the main stream's conv kernels that run beside the weight-gradient stream
     int nsplit = p->num_sms / g.ngroups;
+    const int kWgMinBlocks = getenv("DSR_WG_MINBLK") ? atoi(getenv("DSR_WG_MINBLK")) : 16;
+    if (nsplit > npb / kWgMinBlocks) nsplit = npb / kWgMinBlocks;
     if (nsplit > npb) nsplit = npb;
     if (nsplit < 1) nsplit = 1;
     g.nsplit = nsplit;
