@@ -17,9 +17,9 @@ namespace dsr {
 
 namespace {
 
-// outputs per block: 32 x 8 (factor <= 8) or 16 x 4 (larger factors, to keep the staged patch in smem)
+// outputs per block: 16 x 8 (factor <= 8; 384 blocks at 512^2 / factor 4) or 16 x 4 (larger factors, to keep the staged patch in smem)
 inline void ds_tile(int factor, int& tox, int& toy) {
-  if (factor <= 8) { tox = 32; toy = 8; } else { tox = 16; toy = 4; }
+  if (factor <= 8) { tox = 16; toy = 8; } else { tox = 16; toy = 4; }
 }
 
 // dynamic smem: patch [py][px] then rows-filtered [py][kTileOx]
@@ -40,8 +40,9 @@ __global__ void downsample_fwd_kernel(const float* __restrict__ x, const float* 
   const int ox0 = blockIdx.x * kTileOx, oy0 = blockIdx.y * kTileOy;
   const float* xc = x + static_cast<long long>(c) * H * W;
   for (int i = threadIdx.x; i < k; i += blockDim.x) taps[i] = t.taps[i];
-  for (int i = threadIdx.x; i < ph * pw; i += blockDim.x) {
-    const int py = i / pw, px = i % pw;
+#pragma unroll 8
+  for (int i = threadIdx.x; i < ph * pw; i += blockDim.x) {      // unrolled: 8 independent clamped loads in flight
+    const int py = i / pw, px = i - py * pw;
     int sy = oy0 * f + py - pad, sx = ox0 * f + px - pad;    // replicate padding = clamp
     sy = min(max(sy, 0), H - 1);
     sx = min(max(sx, 0), W - 1);
@@ -87,12 +88,10 @@ __global__ void downsample_fwd_kernel(const float* __restrict__ x, const float* 
 __global__ void downsample_bwd_kernel(const float* __restrict__ gy, float* __restrict__ gx, int C, int H, int W, int oh,
                                       int ow, DsTables t) {
   pdl_sync();
-  const long long n = static_cast<long long>(C) * H * W;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int x = static_cast<int>(i % W);
-    const int y = static_cast<int>((i / W) % H);
-    const int c = static_cast<int>(i / (static_cast<long long>(W) * H));
+  const int n = C * H * W;                      // < 2^31 (checked by the launcher)
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int c = i / (W * H), rem = i - c * (W * H);
+    const int y = rem / W, x = rem - y * W;
     const int y0 = t.by0[y], x0 = t.bx0[x];
     const float* g = gy + static_cast<long long>(c) * oh * ow;
     float acc = 0.f;
@@ -147,6 +146,7 @@ int launch_downsample_mse(const float* x, const float* target, float* y, float* 
 }
 int launch_downsample_bwd(const float* gy, float* gx, int C, int H, int W, int oh, int ow, DsTables t, cudaStream_t s) {
   const long long n = static_cast<long long>(C) * H * W;
+  if (n >= (1LL << 31)) return -5;
   long long blocks = (n + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   launch_k(downsample_bwd_kernel, dim3(static_cast<int>(blocks)), dim3(256), 0, s, gy, gx, C, H, W, oh, ow, t);

@@ -1151,6 +1151,20 @@ int launch_bn_bwd_top_apply(const TopBwdArgs& a, cudaStream_t s) {
   DSR_LAUNCH_CHECK();
 }
 
+// second BN-backward sum of channel c: bstats[128 + c] holds sum dy*xhat, or (bstats_raw) sum dy*r to be converted
+__device__ __forceinline__ float bn_bwd_s2(const BnBwdArgs& a, int c, float mean, float rstd) {
+  const float v = a.bstats[128 + c];
+  return a.bstats_raw ? rstd * (v - mean * a.bstats[c]) : v;
+}
+__device__ __forceinline__ void bn_bwd_write_param_grads(const BnBwdArgs& a) {
+  if (blockIdx.x == 0 && threadIdx.x < 128) {
+    float mean, rstd, ga, be;
+    bn_coeffs(a.bn, threadIdx.x, mean, rstd, ga, be);
+    a.dbeta[threadIdx.x] = a.bstats[threadIdx.x] * a.gs[1];
+    a.dgamma[threadIdx.x] = bn_bwd_s2(a, threadIdx.x, mean, rstd) * a.gs[1];
+  }
+}
+
 // =============================================================================================
 // BN + LeakyReLU backward (128 channels)
 // =============================================================================================
@@ -1198,7 +1212,7 @@ __global__ void __launch_bounds__(kThreads, HAS_DS ? 2 : 3) bn_bwd_kernel(BnBwdA
     xb[j] = -mean * rstd;
     k1[j] = ga[j] * rstd;
     c1[j] = APPLY ? a.bstats[c0 + j] * a.bn.inv_n : 0.f;
-    c2[j] = APPLY ? a.bstats[128 + c0 + j] * a.bn.inv_n : 0.f;
+    c2[j] = APPLY ? bn_bwd_s2(a, c0 + j, mean, rstd) * a.bn.inv_n : 0.f;
     s1[j] = 0.f;
     s2[j] = 0.f;
   }
@@ -1317,10 +1331,7 @@ __global__ void __launch_bounds__(kThreads, HAS_DS ? 2 : 3) bn_bwd_kernel(BnBwdA
   } else {
     const float amax = fmaxf(__low2float(amax2), __high2float(amax2));
     track_amax(a.gs, isfinite(amax) ? amax : 0.f, !isfinite(amax));
-    if (blockIdx.x == 0 && threadIdx.x < 128) {
-      a.dbeta[threadIdx.x] = a.bstats[threadIdx.x] * a.gs[1];
-      a.dgamma[threadIdx.x] = a.bstats[128 + threadIdx.x] * a.gs[1];
-    }
+    bn_bwd_write_param_grads(a);
   }
 }
 
@@ -1347,7 +1358,7 @@ __global__ void __launch_bounds__(kThreads, 3) bn_bwd_fast_kernel(BnBwdArgs a) {
     mean_[j] = mean;
     rstd_[j] = rstd;
     if (APPLY) {
-      const float c1 = a.bstats[c0 + j] * a.bn.inv_n, c2 = a.bstats[128 + c0 + j] * a.bn.inv_n;
+      const float c1 = a.bstats[c0 + j] * a.bn.inv_n, c2 = bn_bwd_s2(a, c0 + j, mean, rstd) * a.bn.inv_n;
       B[j] = -k1[j] * c2 * rstd;
       A[j] = -k1[j] * (c1 - c2 * mean * rstd);
     }
@@ -1427,10 +1438,7 @@ __global__ void __launch_bounds__(kThreads, 3) bn_bwd_fast_kernel(BnBwdArgs a) {
   } else {
     const float amax = fmaxf(__low2float(amax2), __high2float(amax2));
     track_amax(a.gs, isfinite(amax) ? amax : 0.f, !isfinite(amax));
-    if (blockIdx.x == 0 && threadIdx.x < 128) {
-      a.dbeta[threadIdx.x] = a.bstats[threadIdx.x] * a.gs[1];
-      a.dgamma[threadIdx.x] = a.bstats[128 + threadIdx.x] * a.gs[1];
-    }
+    bn_bwd_write_param_grads(a);
   }
 }
 
@@ -2174,16 +2182,34 @@ __device__ __forceinline__ void upcat_bwd_elem_body(const UpcatBwdArgs& a, __hal
   const int wp = f.w + 2;
   const __half* __restrict__ tb = static_cast<const __half*>(a.dup_pad) + c0;
   const __half* __restrict__ qb = static_cast<const __half*>(f.qd) + c0;
+  const bool cons = a.cons_raw != nullptr;
+  const __half* __restrict__ rb = static_cast<const __half*>(a.cons_raw) + c0;
+  float ck1[8], csh[8], cs1[8], cs2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    cs1[j] = 0.f;
+    cs2[j] = 0.f;
+    ck1[j] = 0.f;
+    csh[j] = 0.f;
+    if (cons) {
+      float mean, rstd, ga, be;
+      bn_coeffs(a.cons_bn, c0 + j, mean, rstd, ga, be);
+      ck1[j] = ga * rstd;
+      csh[j] = be - mean * ck1[j];
+    }
+  }
   const int ppb = blockDim.x >> 4;                   // pixels per block per pass
   for (int base = vblock * ppb * 2 + (threadIdx.x >> 4); base < npix; base += vgrid * ppb * 2) {
     const int pix1 = base + ppb;
     const bool ok1 = pix1 < npix;
-    float t0[8], q0[8], t1[8], q1[8];
+    float t0[8], q0[8], t1[8], q1[8], r0[8], r1[8];
     load8h(tb + static_cast<long long>(base) * 128, t0);
     load8h(qb + static_cast<long long>(base) * 128, q0);
+    if (cons) load8h(rb + static_cast<long long>(base) * 128, r0);
     if (ok1) {
       load8h(tb + static_cast<long long>(pix1) * 128, t1);
       load8h(qb + static_cast<long long>(pix1) * 128, q1);
+      if (cons) load8h(rb + static_cast<long long>(pix1) * 128, r1);
     }
     {
       const int qy = base / f.w, qx = base - qy * f.w;
@@ -2192,6 +2218,15 @@ __device__ __forceinline__ void upcat_bwd_elem_body(const UpcatBwdArgs& a, __hal
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = fmaf(k1[j], t0[j], fmaf(B[j], q0[j], A[j] * w2));
       store8h(ddeep + (static_cast<long long>(qy + 1) * wp + (qx + 1)) * 128 + c0, o);
+      if (cons) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float g16 = __half2float(__float2half_rn(o[j]));          // what the consumer's apply pass will read
+          const float dy = fmaf(ck1[j], r0[j], csh[j]) > 0.f ? g16 : kSlope * g16;
+          cs1[j] += dy;
+          cs2[j] = fmaf(dy, r0[j], cs2[j]);
+        }
+      }
     }
     if (ok1) {
       const int qy = pix1 / f.w, qx = pix1 - qy * f.w;
@@ -2200,7 +2235,36 @@ __device__ __forceinline__ void upcat_bwd_elem_body(const UpcatBwdArgs& a, __hal
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = fmaf(k1[j], t1[j], fmaf(B[j], q1[j], A[j] * w2));
       store8h(ddeep + (static_cast<long long>(qy + 1) * wp + (qx + 1)) * 128 + c0, o);
+      if (cons) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float g16 = __half2float(__float2half_rn(o[j]));
+          const float dy = fmaf(ck1[j], r1[j], csh[j]) > 0.f ? g16 : kSlope * g16;
+          cs1[j] += dy;
+          cs2[j] = fmaf(dy, r1[j], cs2[j]);
+        }
+      }
     }
+  }
+  if (cons) {        // block-uniform
+    // the two half-warps of a warp hold the same channels: one shuffle, then shared-memory and global atomics
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      cs1[j] += __shfl_xor_sync(0xffffffffu, cs1[j], 16);
+      cs2[j] += __shfl_xor_sync(0xffffffffu, cs2[j], 16);
+    }
+    __shared__ float cred[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) cred[i] = 0.f;
+    __syncthreads();
+    if ((threadIdx.x & 31) < 16) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        atomicAdd(&cred[c0 + j], cs1[j]);
+        atomicAdd(&cred[128 + c0 + j], cs2[j]);
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) atomicAdd(&a.cons_bstats[i], cred[i]);
   }
 }
 
@@ -2212,7 +2276,7 @@ __global__ void __launch_bounds__(kThreads, 2) upcat_bwd_a_kernel(UpcatBwdArgs a
   pdl_sync();
   upT_gather_tile_body(a, gt_smem);
 }
-__global__ void __launch_bounds__(kThreads) upcat_bwd_c_kernel(UpcatBwdArgs a, __half* __restrict__ ddeep, int nb_skip) {
+__global__ void __launch_bounds__(kThreads, 2) upcat_bwd_c_kernel(UpcatBwdArgs a, __half* __restrict__ ddeep, int nb_skip) {
   pdl_sync();
   // the skip-channel blocks (one thread per high-resolution pixel, dependent loads) go first so that they overlap
   // the element-wise blocks

@@ -98,7 +98,9 @@ struct BnBwdArgs {
   float* dsraw;            // fp32 plain [H][W][4]: written for inspection (diagnostics)
   const void* raw;         // fp16 plain [H][W][128]: BN input saved by the forward
   BnRef bn;
-  float* bstats;           // [2][128]: sum dy, sum dy*xhat
+  float* bstats;           // [2][128]: sum dy, sum dy*xhat (bstats_raw: sum dy, sum dy*r -- see below)
+  int bstats_raw;          // 1: the sums were accumulated by the kernel that PRODUCED g (no separate statistics pass),
+                           //    in raw form: [1] = sum dy * r; sum dy*xhat = rstd ([1] - mean [0])
   void* dr_pad;            // fp16 padded [H+2][W+2][128] (interior written; halo stays zero)
   float* dgamma;           // [128]
   float* dbeta;            // [128]
@@ -118,6 +120,11 @@ struct UpcatBwdArgs {
   float* dcat_gamma;       // [132] reference channel order
   float* dcat_beta;
   const float* gs;
+  // optional: BatchNorm-backward sums of the layer that CONSUMES ddeep (the deeper level's last decoder conv, or the
+  // last level's second encoder conv), accumulated by pass C while ddeep is in registers: sum dy, sum dy * r
+  const void* cons_raw;    // fp16 plain [h][w][128]: that layer's BN input (null: no fusion)
+  BnRef cons_bn;
+  float* cons_bstats;      // [2][128]
 };
 // source-domain formulation (see dsr_elem.cu): forward statistics of the concat tensor, and the whole backward of
 // upsample + concat + BN(132) (a.dup_pad is used as the [h][w][128] scratch tensor t = U^T dc)

@@ -70,6 +70,7 @@ struct ConvLayer {
   int cin = 0, cin_pad = 0, k = 3, stride = 1;
   int inH = 0, inW = 0, outH = 0, outW = 0;
   bool need_dgrad = true;
+  bool bstats_ready = false;       // transient: BN-backward sums of this layer were accumulated by the kernel that produced its g
   int n_rows = 0;                  // dgrad output channels (packed): 128 or 144
   long long w_off = 0, b_off = 0, g_off = 0, be_off = 0;   // conv weight / bias, BN gamma / beta (floats)
   long long bn_off = 0;            // BN buffers
@@ -166,6 +167,7 @@ struct dsr_plan {
   // pointer arguments; an entry is captured on its SECOND use (the first run is eager and sets function attributes)
   struct PassGraph { int kind; const void* a0; const void* a1; const void* a2; const void* a3; int uses; cudaGraphExec_t exec; };
   std::vector<PassGraph> pass_graphs;
+  int fuse_ubstats = 1;          // BN-backward sums of the layer consuming ddeep accumulated by the upcat backward pass C
   int fuse_skip = 1;             // skip-branch 1x1 conv of level i+1 fused into level i's last BN + LeakyReLU pass
   int lowres_upcat = 1;          // upsample + concat + BN(132): statistics and backward in the low-resolution domain
   int in_step = 0;               // inside enqueue_step (whole-iteration graph): no nested pass graphs
@@ -869,6 +871,7 @@ int bn_backward(dsr_plan* p, ConvLayer& c, const float* params, float* grads, co
   a.g = g;
   a.gC = gC;
   a.fold = fold;
+  a.bstats_raw = c.bstats_ready ? 1 : 0;
   if (next != nullptr) {
     a.dsy = static_cast<const float*>(next->dsy.ptr);
     a.sraw = static_cast<const float*>(next->sraw.ptr);
@@ -889,7 +892,8 @@ int bn_backward(dsr_plan* p, ConvLayer& c, const float* params, float* grads, co
   a.gs = static_cast<float*>(p->gscale.ptr);
   a.H = c.outH;
   a.W = c.outW;
-  DSR_TRY(launch_bn_bwd_stats(a, s));
+  if (!c.bstats_ready) DSR_TRY(launch_bn_bwd_stats(a, s));     // else: accumulated by the kernel that produced g
+  c.bstats_ready = false;
   DSR_TRY(launch_bn_bwd_apply(a, s));
   return 0;
 }
@@ -934,6 +938,15 @@ int backward_level(dsr_plan* p, int i, const float* params, float* grads, cudaSt
   ub.dcat_beta = grads + L.cat_be;
   ub.gs = static_cast<const float*>(p->gscale.ptr);
   void* ddeep = last ? L.g_d2a.ptr : p->lv[i + 1].g_u2a.ptr;
+  // the consumer's BN-backward sums ride on pass C where the launch saved outweighs the extra register pressure of the
+  // element-wise pass (measured: a gain up to 128 x 128 low-resolution pixels, a loss at 256 x 256)
+  if (p->lowres_upcat && p->fuse_ubstats && !p->debug_conv && L.h * L.w <= 128 * 128) {
+    ConvLayer& cons = last ? L.d2 : p->lv[i + 1].u2;
+    ub.cons_raw = cons.raw.ptr;
+    ub.cons_bn = conv_bn(p, cons, params);
+    ub.cons_bstats = acc + cons.bstats_off;
+    cons.bstats_ready = true;
+  }
   if (p->lowres_upcat) {
     DSR_TRY(launch_upcat_bwd_gather(ub, s));
     DSR_TRY(launch_upcat_bwd_apply_lowres(ub, ddeep, s));
@@ -1319,6 +1332,7 @@ int dsr_plan_bind(dsr_plan_t* p, void* workspace, size_t bytes, void* stream) {
   p->fuse_top = getenv("DSR_NO_FUSE_TOP") ? 0 : 1;
   p->lowres_upcat = getenv("DSR_NO_LOWRES_UPCAT") ? 0 : 1;
   p->fuse_skip = getenv("DSR_NO_FUSE_SKIP") ? 0 : 1;
+  p->fuse_ubstats = getenv("DSR_NO_FUSE_UBSTATS") ? 0 : 1;
   p->bound = true;
   p->have_forward = false;
   return 0;
