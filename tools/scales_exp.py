@@ -1,0 +1,49 @@
+"""Where does the iteration time go by LEVEL?  Times dsr_dip_run (graph replay) at one size for num_scales = 1..5:
+the difference between consecutive lines is the in-graph cost of one more (4x smaller) level.
+    python tools/scales_exp.py [size] [iters]"""
+import os, sys, ctypes as C
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, 'deep-super-resolution_b200'))
+import torch, dsr_b200
+from dsr_b200._lib import lib, check, StepBuffers
+from dsr_b200 import _lib
+
+size = int(sys.argv[1]) if len(sys.argv) > 1 else 512
+iters = int(sys.argv[2]) if len(sys.argv) > 2 else 100
+scales_list = [int(s) for s in sys.argv[3].split(',')] if len(sys.argv) > 3 else [1, 2, 3, 4, 5]
+dev = torch.device('cuda', 0)
+torch.cuda.set_stream(torch.cuda.Stream(device=dev))
+for scales in scales_list:
+    torch.manual_seed(0)
+    ds = dsr_b200.Downsampler(3, 4, 'lanczos2', phase=0.5, preserve_size=True)
+    hr = torch.rand(1, 3, size, size).to(dev)
+    lr_img = ds(hr)[0].contiguous()
+    net = dsr_b200.get_net(32, 'skip', 'reflection', skip_n33d=128, skip_n33u=128, skip_n11=4, num_scales=scales,
+                           upsample_mode='bilinear').to(dev)
+    z_saved = dsr_b200.get_noise(32, 'noise', (size, size)).to(dev).contiguous()
+    z = z_saved.clone()
+    net(z)
+    net.zero_grad()
+    plan = net._plans[(size, size)]
+    tables = ds._tables_for(size, size, dev)
+    oh, ow = ds.out_size(size, size)
+    flat, gflat = net.flat_buffers()
+    f32 = dict(dtype=torch.float32, device=dev)
+    m, v = torch.zeros_like(flat), torch.zeros_like(flat)
+    out_hr = torch.empty((1, 3, size, size), **f32)
+    out_lr, g_lr, g_hr = torch.empty((3, oh, ow), **f32), torch.empty((3, oh, ow), **f32), torch.empty((1, 3, size, size), **f32)
+    losses = torch.zeros(iters + 64, **f32)
+    b = StepBuffers(flat.data_ptr(), gflat.data_ptr(), m.data_ptr(), v.data_ptr(), net._bnflat.data_ptr(),
+                    z_saved.data_ptr(), z.data_ptr(), lr_img.data_ptr(), out_hr.data_ptr(), out_lr.data_ptr(),
+                    g_lr.data_ptr(), g_hr.data_ptr(), losses.data_ptr())
+    stream = _lib.stream_ptr()
+    check(lib.dsr_dip_run(plan.handle, tables.handle, C.byref(b), 0.01, 0.05, 7, 1, 5, stream), 'run')
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    check(lib.dsr_dip_run(plan.handle, tables.handle, C.byref(b), 0.01, 0.05, 7, 6, iters, stream), 'run')
+    e1.record()
+    torch.cuda.synchronize()
+    print(f'size {size} num_scales {scales}: {e0.elapsed_time(e1) / iters * 1e3:8.1f} us / iteration, '
+          f'{lib.dsr_plan_last_launches(plan.handle)} launches, loss {float(losses[iters + 4]):.5f}', flush=True)
+    del net, plan, tables
