@@ -522,15 +522,61 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
 // floor).  Both CTAs stream A with pair-TMA loads accounted on CTA 0's barriers; MMA completion is multicast to
 // both CTAs' barriers; both CTAs' epilogue warps release the accumulator stage on CTA 0's barrier.
 // =============================================================================================
+// Generator epilogue (EP = 1): out = [residual +] prelu(acc + bias), 16 channels of one pixel, fp16, one 32-byte store.
+__device__ __forceinline__ void halo_epilogue_fused(const HaloParams& p, const uint32_t (&v)[16], int c, bool valid,
+                                                    long long obase, float slope) {
+  const int ch = c * 16;
+  if (!valid || ch >= p.n_store) return;
+  float f[16];
+  const float4* b4 = reinterpret_cast<const float4*>(p.ep_bias + ch);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 b = __ldg(b4 + i);
+    f[4 * i + 0] = __uint_as_float(v[4 * i + 0]) + b.x;
+    f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + b.y;
+    f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + b.z;
+    f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + b.w;
+  }
+  if (p.ep_slope != nullptr) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) f[i] = f[i] > 0.f ? f[i] : slope * f[i];
+  }
+  if (p.ep_res != nullptr) {
+    const uint4* r = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.ep_res) + obase + ch);
+    const uint4 r0 = __ldg(r), r1 = __ldg(r + 1);
+    const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const __half2 h = *reinterpret_cast<const __half2*>(&rw[i]);
+      f[2 * i] += __low2float(h);
+      f[2 * i + 1] += __high2float(h);
+    }
+  }
+  uint32_t packed[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    __half2 h = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+    packed[i] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  uint16_t* dst = reinterpret_cast<uint16_t*>(p.out) + obase + ch;
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(packed[0]), "r"(packed[1]),
+               "r"(packed[2]), "r"(packed[3]), "r"(packed[4]), "r"(packed[5]), "r"(packed[6]), "r"(packed[7])
+               : "memory");
+}
+
+// EP: 0 = DIP step (raw fp16 output + BatchNorm sums), 1 = generator 3x3 / 1x1 (fused bias, PReLU, residual; tall
+// batch grid), 2 = generator 9x9 output conv (81 shifted views of one 16 x 24 halo tile, tanh, fp32 NCHW planes).
+template <int EP>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHalo2Threads, 1)
     conv_halo2_kernel(const __grid_constant__ HaloParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int wb = p.n_part * 128, nb = p.n_part * 32;                    // bytes of one resident weight block
+  const int slot_bytes = (EP == 0) ? kHaloWideSlot : p.wide_slot_bytes;
   uint8_t* bres_w = smem;
   uint8_t* bres_n = bres_w + p.ntaps * p.n_wide * wb;
   uint8_t* a_wide = bres_n + ((p.ntaps * p.n_narrow * nb + 1023) & ~1023);
-  uint8_t* a_narrow = a_wide + p.wide_slots * kHaloWideSlot;
+  uint8_t* a_narrow = a_wide + p.wide_slots * slot_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(a_narrow + (p.n_narrow ? 2 * kHaloNarrowSlot : 0));
   uint64_t* wfull = bars;                 // [3]  (CTA 0's copy is the live one)
   uint64_t* wempty = bars + 3;            // [3]  (each CTA waits on its own copy; multicast commit)
@@ -572,7 +618,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHalo2Threads, 1)
     const uint32_t bbytes = static_cast<uint32_t>(p.ntaps * (p.n_wide * wb + p.n_narrow * nb));
     if (rank == 0) mbar_arrive_expect_tx(bres_bar, 2 * bbytes);
     for (int t = 0; t < p.ntaps; ++t) {
-      const int row = p.taps[t].b_row + static_cast<int>(rank) * p.n_part;
+      const int row = (EP == 2 ? t * 2 * p.n_part : p.taps[t].b_row) + static_cast<int>(rank) * p.n_part;
       for (int c = 0; c < p.n_wide; ++c)
         tma_load_2d_pair(&p.b64, bres_bar, bres_w + (t * p.n_wide + c) * wb, c * 64, row);
       if (p.n_narrow) tma_load_2d_pair(&p.b16, bres_bar, bres_n + t * nb, p.n_wide * 64, row);
@@ -592,7 +638,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHalo2Threads, 1)
         for (int c = 0; c < p.n_wide; ++c) {
           mbar_wait(&wempty[ws], wph ^ 1, p.err, 31);
           if (rank == 0) mbar_arrive_expect_tx(&wfull[ws], 2 * p.halo_w * p.halo_h * 128);
-          tma_load_5d_pair(&p.a64, &wfull[ws], a_wide + ws * kHaloWideSlot, c * 64, 0, x0, 0, y0);
+          tma_load_5d_pair(&p.a64, &wfull[ws], a_wide + ws * slot_bytes, c * 64, 0, x0, 0, y0);
           if (++ws == p.wide_slots) { ws = 0; wph ^= 1; }
         }
         if (p.n_narrow) {
@@ -633,18 +679,33 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHalo2Threads, 1)
         for (int c = 0; c < p.n_wide; ++c) {
           mbar_wait(&wfull[ws], wph, p.err, 35);
           tc_fence_after();
-          const uint32_t a_lo = aw_lo0 | ((smem_u32(a_wide + ws * kHaloWideSlot) & 0x3FFFF) >> 4);
+          const uint32_t a_lo = aw_lo0 | ((smem_u32(a_wide + ws * slot_bytes) & 0x3FFFF) >> 4);
           const uint32_t b_lo = bw_lo0 | (((bw_addr + static_cast<uint32_t>(c * wb)) & 0x3FFFF) >> 4);
           if (elect_one()) {
+            if (EP == 2) {                 // 9 x 9: tap (ky, kx) is the view shifted by ky * halo_w + kx pixel rows
+              uint32_t db_lo = b_lo;
+              for (int ky = 0; ky < 9; ++ky) {
+                uint32_t da_lo = a_lo + static_cast<uint32_t>(ky * p.halo_w) * 8u;
 #pragma unroll
-            for (int t = 0; t < 9; ++t) {
-              if (t >= p.ntaps) break;
-              const uint32_t da_lo = a_lo + tap_row[t] * 8u;
-              const uint32_t db_lo = b_lo + static_cast<uint32_t>(t) * b_tap_step;
+                for (int kx = 0; kx < 9; ++kx, da_lo += 8u, db_lo += b_tap_step) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j)
-                umma_f16_pair(tmem_d, (static_cast<uint64_t>(aw_hi) << 32) | (da_lo + 2u * j),
-                              (static_cast<uint64_t>(bw_hi) << 32) | (db_lo + 2u * j), idw, (t | j) ? 1u : accum);
+                  for (int j = 0; j < 4; ++j)
+                    umma_f16_pair(tmem_d, (static_cast<uint64_t>(aw_hi) << 32) | (da_lo + 2u * j),
+                                  (static_cast<uint64_t>(bw_hi) << 32) | (db_lo + 2u * j), idw,
+                                  (ky | kx | j) ? 1u : accum);
+                }
+              }
+            } else {
+#pragma unroll
+              for (int t = 0; t < 9; ++t) {
+                if (t >= p.ntaps) break;
+                const uint32_t da_lo = a_lo + tap_row[t] * 8u;
+                const uint32_t db_lo = b_lo + static_cast<uint32_t>(t) * b_tap_step;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  umma_f16_pair(tmem_d, (static_cast<uint64_t>(aw_hi) << 32) | (da_lo + 2u * j),
+                                (static_cast<uint64_t>(bw_hi) << 32) | (db_lo + 2u * j), idw, (t | j) ? 1u : accum);
+              }
             }
             umma_commit_pair(&wempty[ws]);
           }
@@ -692,13 +753,45 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHalo2Threads, 1)
       const uint32_t aph = (it / kAcc) & 1;
       const int tile = 2 * pair + static_cast<int>(rank);
       const int x = (tile % p.tiles_x) * kHaloTW + (row & (kHaloTW - 1));
-      const int y = (tile / p.tiles_x) * kHaloTH + (row / kHaloTW);
-      const bool valid = (tile < ntiles) && (x < p.out_w) && (y < p.out_h);
+      int y = (tile / p.tiles_x) * kHaloTH + (row / kHaloTW);
+      bool valid = (tile < ntiles) && (x < p.out_w) && (y < p.out_h);
+      long long obase = 0;
+      if (EP != 0) {                       // tall batch grid: rows between images are padding, not outputs
+        const int img = y / p.img_rows;
+        y -= img * p.img_rows;
+        valid = valid && (y < p.img_h);
+        obase = static_cast<long long>(img) * p.out_img_stride;
+      }
       mbar_wait(&tfull[as], aph, p.err, 37);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(as * 256);
-      const long long obase = static_cast<long long>(y) * p.out_sy + static_cast<long long>(x) * p.out_sx;
-      if (!(p.dbg & 2)) {
+      obase += static_cast<long long>(y) * p.out_sy + static_cast<long long>(x) * p.out_sx;
+      if (EP == 1) {
+        const float slope = (p.ep_slope != nullptr) ? __ldg(p.ep_slope) : 0.f;
+        uint32_t v[2][16];
+        tmem_ld16(taddr + static_cast<uint32_t>(c_begin * 16), v[0]);
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+          const int c = c_begin + i;
+          if (c < c_end) {
+            tmem_ld_wait();
+            if (c + 1 < c_end) tmem_ld16(taddr + static_cast<uint32_t>((c + 1) * 16), v[(i + 1) & 1]);
+            halo_epilogue_fused(p, v[i & 1], c, valid, obase, slope);
+          }
+        }
+      } else if (EP == 2) {
+        if (half == 0) {                   // N = 16: one chunk; the first n_store columns are the image planes
+          uint32_t v[16];
+          tmem_ld16(taddr, v);
+          tmem_ld_wait();
+          if (valid) {
+            float* o = reinterpret_cast<float*>(p.out) + obase;
+#pragma unroll
+            for (int n = 0; n < 4; ++n)
+              if (n < p.n_store) o[n * p.ep_plane] = tanhf(__uint_as_float(v[n]) + __ldg(p.ep_bias + n));
+          }
+        }
+      } else if (!(p.dbg & 2)) {
         uint32_t v[2][16];
         tmem_ld16(taddr + static_cast<uint32_t>(c_begin * 16), v[0]);
 #pragma unroll
@@ -1095,9 +1188,9 @@ int launch_conv_gemm(const ConvGemmParams& p, int num_sms, cudaStream_t stream) 
   return static_cast<int>(cudaGetLastError());
 }
 
-int halo_smem_bytes(int n_part, int n_wide, int n_narrow, int wide_slots, int ntaps) {
+int halo_smem_bytes(int n_part, int n_wide, int n_narrow, int wide_slots, int ntaps, int slot_bytes) {
   const int bres = ntaps * n_wide * n_part * 128 + ((ntaps * n_narrow * n_part * 32 + 1023) & ~1023);
-  return bres + wide_slots * kHaloWideSlot + (n_narrow ? 2 * kHaloNarrowSlot : 0) + 256 + 1024;
+  return bres + wide_slots * (slot_bytes ? slot_bytes : kHaloWideSlot) + (n_narrow ? 2 * kHaloNarrowSlot : 0) + 256 + 1024;
 }
 
 int launch_conv_halo(const HaloParams& p, int num_sms, cudaStream_t stream) {
@@ -1105,7 +1198,11 @@ int launch_conv_halo(const HaloParams& p, int num_sms, cudaStream_t stream) {
   if (p.smem_bytes > configured) {
     cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem_bytes);
     if (e != cudaSuccess) return static_cast<int>(e);
-    e = cudaFuncSetAttribute(conv_halo2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem_bytes);
+    e = cudaFuncSetAttribute(conv_halo2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem_bytes);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    e = cudaFuncSetAttribute(conv_halo2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem_bytes);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    e = cudaFuncSetAttribute(conv_halo2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem_bytes);
     if (e != cudaSuccess) return static_cast<int>(e);
     configured = p.smem_bytes;
   }
@@ -1115,7 +1212,9 @@ int launch_conv_halo(const HaloParams& p, int num_sms, cudaStream_t stream) {
     const int npairs = (ntiles + 1) / 2;
     int clusters = num_sms / 2;
     if (clusters > npairs) clusters = npairs;
-    launch_k(conv_halo2_kernel, dim3(2 * clusters), dim3(kHalo2Threads), p.smem_bytes, stream, p);
+    if (p.ep_mode == 0) launch_k(conv_halo2_kernel<0>, dim3(2 * clusters), dim3(kHalo2Threads), p.smem_bytes, stream, p);
+    else if (p.ep_mode == 1) launch_k(conv_halo2_kernel<1>, dim3(2 * clusters), dim3(kHalo2Threads), p.smem_bytes, stream, p);
+    else launch_k(conv_halo2_kernel<2>, dim3(2 * clusters), dim3(kHalo2Threads), p.smem_bytes, stream, p);
     return static_cast<int>(cudaGetLastError());
   }
   int grid = (num_sms / p.parts) * p.parts;

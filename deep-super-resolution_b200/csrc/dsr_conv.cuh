@@ -96,6 +96,20 @@ struct alignas(64) HaloParams {
   int pair;                  // 1: CTA-pair kernel (cta_group::2; parts must be 2, n_part = N / 2)
   int dbg;                   // experiments only (DSR_HALO_DBG): bit 0 skip the A loads, bit 1 skip the epilogue work
   int* err;
+  // ---- SRResNet generator (dsr_gan.cu; pair kernel only).  ep_mode 0: DIP epilogue (raw fp16 + BatchNorm sums).
+  //      1: out = [residual +] prelu(acc + bias[n]) as fp16;  2: 9 x 9 taps (ntaps = 81, tap (ky, kx) = view
+  //      ky * halo_w + kx, weight block ky * 9 + kx), out_f32[plane n][pixel] = tanh(acc + bias[n]) for n < n_store.
+  //      Batches are TALL grids: image b occupies rows [b * img_rows, b * img_rows + img_h) of the pixel grid, the
+  //      rows between images stay zero (the convolution's zero padding; left / right / top / bottom come from
+  //      TMA's out-of-bounds zero fill), and output rows that fall into a gap are not stored.
+  int ep_mode;
+  int wide_slot_bytes;       // A ring slot size for ep_mode != 0 (halo_w * halo_h * 128 rounded up to 1024)
+  int img_rows, img_h;       // tall-grid period (H + gap) and image height
+  long long out_img_stride;  // output elements between consecutive images
+  long long ep_plane;        // ep_mode 2: elements between output channel planes (NCHW fp32)
+  const float* ep_bias;      // [N] fp32 (folded conv bias + eval-mode BatchNorm shift)
+  const float* ep_slope;     // device scalar: PReLU slope, or nullptr for no activation
+  const void* ep_res;        // fp16 residual tensor with the output's addressing, or nullptr
 };
 
 // ---------------------------------------------------------------------------------------------

@@ -20,7 +20,7 @@ int launch_conv_gemm(const ConvGemmParams& p, int num_sms, cudaStream_t stream);
 int launch_wgrad(const WgradParams& p, cudaStream_t stream);
 int launch_wgrad_halo(const WgHaloParams& p, cudaStream_t stream);
 int launch_conv_halo(const HaloParams& p, int num_sms, cudaStream_t stream);
-int halo_smem_bytes(int n_part, int n_wide, int n_narrow, int wide_slots, int ntaps);
+int halo_smem_bytes(int n_part, int n_wide, int n_narrow, int wide_slots, int ntaps, int slot_bytes = 0);
 
 // Element formats of the 16-bit tensors (tcgen05 kind::f16 operand format codes).
 enum : uint32_t { FMT_F16 = 0, FMT_BF16 = 1 };

@@ -66,6 +66,19 @@ SIGNATURES = {
     'dsr_plan_profile_dump': (i32, [vp, C.c_char_p, sz]),
     'dsr_plan_device_error': (i32, [vp, C.POINTER(i32)]),
     'dsr_debug_copy': (i32, [vp, vp, sz, vp]),
+    'dsr_gen_plan_create': (i32, [C.POINTER(vp), i32, i32, i32, i32, i32]),
+    'dsr_gen_plan_destroy': (None, [vp]),
+    'dsr_gen_state_numel': (i64, [vp]),
+    'dsr_gen_num_tensors': (i32, [vp]),
+    'dsr_gen_tensor_info': (i32, [vp, i32, C.c_char_p, i32, C.POINTER(i64), C.POINTER(i64)]),
+    'dsr_gen_workspace_bytes': (sz, [vp]),
+    'dsr_gen_bind': (i32, [vp, vp, sz, vp]),
+    'dsr_gen_load_weights': (i32, [vp, vp, vp]),
+    'dsr_gen_forward': (i32, [vp, vp, vp, vp]),
+    'dsr_gen_last_launches': (i32, [vp]),
+    'dsr_gen_debug_tensor': (i32, [vp, C.c_char_p, C.POINTER(vp), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32),
+                                   C.POINTER(i32)]),
+    'dsr_gen_device_error': (i32, [vp, C.POINTER(i32)]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

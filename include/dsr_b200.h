@@ -147,6 +147,33 @@ int dsr_plan_device_error(dsr_plan_t* p, int* host_code);
 /* Device-to-device copy on `stream` (lets ctypes callers read an introspected tensor into their own buffer). */
 int dsr_debug_copy(void* dst, const void* src, size_t bytes, void* stream);
 
+/* ---- SRResNet generator, inference ------------------------------------------------------------
+ * Replaces models/GAN/generator.py:4-81 (Generator / ResidualBlock / PixelShuffleBlock) in EVAL mode as
+ * eval_GAN.py:87-94 runs it: y[B][3][f h][f w] = tanh(conv3(shuffle blocks(x0 + bn1(conv2(residual blocks(x0))))))
+ * with x0 = prelu1(conv1(x)), BatchNorm using its running statistics.  factor 8 (3 PixelShuffle blocks) or 16 (4) --
+ * the only two the reference constructs (generator.py:55-58).  One plan per (factor, blocks, batch, h, w). */
+typedef struct dsr_gen_plan dsr_gen_plan_t;
+int dsr_gen_plan_create(dsr_gen_plan_t** out, int factor, int residual_blocks, int batch, int h, int w);
+void dsr_gen_plan_destroy(dsr_gen_plan_t* p);
+/* Flat fp32 state: the float tensors of the reference module's state_dict() in order (num_batches_tracked
+ * omitted).  tensor_info gives the idx-th key, its offset and element count. */
+long long dsr_gen_state_numel(const dsr_gen_plan_t* p);
+int dsr_gen_num_tensors(const dsr_gen_plan_t* p);
+int dsr_gen_tensor_info(const dsr_gen_plan_t* p, int idx, char* name, int name_cap, long long* offset, long long* numel);
+size_t dsr_gen_workspace_bytes(const dsr_gen_plan_t* p);
+/* Binds (and zero-fills) the caller-owned workspace (1024-byte aligned) and builds the TMA descriptors. */
+int dsr_gen_bind(dsr_gen_plan_t* p, void* workspace, size_t bytes, void* stream);
+/* Folds eval-mode BatchNorm into the convolutions and packs fp16 GEMM weights from the flat state (device pointer);
+ * call again after the weights change (load_state_dict).  Synchronises `stream` once. */
+int dsr_gen_load_weights(dsr_gen_plan_t* p, const float* state, void* stream);
+/* y = Generator(x).  x: [B][3][h][w] fp32, y: [B][3][f h][f w] fp32, both NCHW device buffers. */
+int dsr_gen_forward(dsr_gen_plan_t* p, const float* x, float* y, void* stream);
+int dsr_gen_last_launches(const dsr_gen_plan_t* p);
+/* Tests: intermediate activation ("x0", "t1", "xa", "xb", "s0".."s3"): fp16 [rows][W][64], image b at rows
+ * [b * img_rows, b * img_rows + H). */
+int dsr_gen_debug_tensor(const dsr_gen_plan_t* p, const char* name, void** ptr, int* rows, int* img_rows, int* H, int* W);
+int dsr_gen_device_error(dsr_gen_plan_t* p, int* host_code);
+
 #ifdef __cplusplus
 }
 #endif

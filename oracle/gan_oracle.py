@@ -11,7 +11,7 @@ unmodified ``models.GAN.generator.Generator`` from ``/root/reference`` (build co
 """
 from __future__ import annotations
 
-from typing import Dict
+from typing import Dict, Optional
 
 import torch
 import torch.nn.functional as F
@@ -91,24 +91,32 @@ def _bn_eval(x: Tensor, sd: Dict[str, Tensor], name: str) -> Tensor:
                         sd[name + '.bias'], training=False, momentum=0.1, eps=BN_EPS)
 
 
-def generator_forward(sd: Dict[str, Tensor], x: Tensor, factor: int = 8, residual_blocks: int = 16) -> Tensor:
+def generator_forward(sd: Dict[str, Tensor], x: Tensor, factor: int = 8, residual_blocks: int = 16,
+                      record: Optional[Dict[str, Tensor]] = None) -> Tensor:
     """``Generator.forward`` (generator.py:68-81) with BatchNorm in eval mode (eval_GAN.py:94).
-    x: [B, 3, h, w] in [0, 1] -> [B, 3, factor*h, factor*w] in (-1, 1)."""
+    x: [B, 3, h, w] in [0, 1] -> [B, 3, factor*h, factor*w] in (-1, 1).  ``record`` (tests) receives the
+    intermediates x0, block{i}_t, block{i}, trunk, s{i}."""
+    rec = record if record is not None else {}
     z = F.conv2d(x, sd['conv1.weight'], sd['conv1.bias'], padding=4)                       # :70
     x0 = F.prelu(z, sd['prelu1.weight'])                                                   # :71
+    rec['x0'] = x0
     z = x0
     for i in range(residual_blocks):                                                      # :72, ResidualBlock.forward :14-25
         p = f'residual_blocks.{i}.'
         t = F.conv2d(z, sd[p + 'conv1.weight'], sd[p + 'conv1.bias'], padding=1)
         t = F.prelu(_bn_eval(t, sd, p + 'bn1'), sd[p + 'prelu1.weight'])
+        rec[f'block{i}_t'] = t
         t = F.conv2d(t, sd[p + 'conv2.weight'], sd[p + 'conv2.bias'], padding=1)
         z = z + _bn_eval(t, sd, p + 'bn2')
+        rec[f'block{i}'] = z
     z = F.conv2d(z, sd['conv2.weight'], sd['conv2.bias'], padding=1)                       # :73
     z = x0 + _bn_eval(z, sd, 'bn1')                                                        # :74-76
+    rec['trunk'] = z
     for i in range(SHUFFLES[factor]):                                                      # :78, PixelShuffleBlock.forward :36-41
         p = f'pixel_shuffle_blocks.{i}.'
         z = F.conv2d(z, sd[p + 'conv1.weight'], sd[p + 'conv1.bias'], padding=1)
         z = F.prelu(F.pixel_shuffle(z, 2), sd[p + 'prelu1.weight'])
+        rec[f's{i}'] = z
     z = F.conv2d(z, sd['conv3.weight'], sd['conv3.bias'], padding=4)                       # :80
     return torch.tanh(z)                                                                   # :82
 
