@@ -454,10 +454,136 @@ def run_e2e(args, rank, world, dev, net, ds, lr_img, z_saved, barrier):
                     'out_HR/out_LR/loss read back each step (D2H on a side stream during the backward pass)'}
 
 
+# -------------------------------------------------------------------------------------------------
+# secondary workload: SRResNet generator inference (BASELINE configs[3])
+# -------------------------------------------------------------------------------------------------
+GAN_FLOPS_96 = 98.131378176e9        # per 96 x 96 image at x8 (oracle.gan_oracle.flops_per_image)
+
+
+def gan_cpu_images_per_s(n_img, budget_s):
+    """The CPU restatement of the reference generator (oracle/gan_oracle.py, eval mode, fp32, all host threads) on a
+    bounded sample: n_img single-image forwards at 96 x 96 (eval_GAN.py uses batch size 1, :81)."""
+    from oracle import gan_oracle as G
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    sd = G.init_state_dict(8)
+    times = []
+    t_begin = time.time()
+    with torch.no_grad():
+        for i in range(n_img + 1):
+            x = torch.rand(1, 3, 96, 96)
+            t0 = time.time()
+            G.generator_forward(sd, x, 8)
+            if i > 0:
+                times.append(time.time() - t0)
+            if time.time() - t_begin > budget_s and len(times) >= 2:
+                break
+    times.sort()
+    return 1.0 / times[len(times) // 2], len(times), cores
+
+
+def run_gan_reference(args, rank, world):
+    if rank != 0:
+        return
+    ips, n, cores = gan_cpu_images_per_s(max(args.steps, 3), budget_s=120.0)
+    line = {'impl': 'reference', 'metric': 'SRGAN generator images/s (96x96 LR patches, x8)', 'value': ips,
+            'unit': 'images/s', 'n_gpus': args.gpus, 'steps': n, 'warmup': 1, 'ms_per_step': 1000.0 / ips,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': 'SRResNet generator inference, 96x96 LR patches -> 768x768 (BASELINE configs[3]); '
+                                   'one image per step on the host cores', 'factor': 8},
+            'cpu_baseline': {'value': ips, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
+                             'sample': f'{n} single-image forwards (median), oracle/gan_oracle.py on torch CPU'},
+            'e2e': {'value': ips, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_gan(args, rank, local_rank, world):
+    """One step = Generator(factor 8).eval() on a batch of `--batch` (256) LR patches of 96 x 96 -> 768 x 768."""
+    import torch.distributed as dist
+    import dsr_b200
+    dev = torch.device('cuda', local_rank)
+    torch.cuda.set_device(dev)
+    B, hw = args.batch, 96
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    torch.manual_seed(rank)
+    g = dsr_b200.Generator(8).to(dev).eval()
+    x = torch.rand(B, 3, hw, hw, device=dev)
+    for _ in range(args.warmup):
+        y = g(x)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        y = g(x)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if sampler else None
+    # ---- end to end: LR batch from pinned host memory, SR batch read back to pinned host memory ----
+    hx = torch.rand(B, 3, hw, hw).pin_memory()
+    hy = torch.empty((B, 3, 8 * hw, 8 * hw), dtype=torch.float32).pin_memory()
+    for _ in range(2):
+        hy.copy_(g(hx.to(dev, non_blocking=True)), non_blocking=True)
+    barrier()
+    n_e2e = max(2, min(args.steps, 5))
+    t0 = time.time()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(n_e2e):
+        hy.copy_(g(hx.to(dev, non_blocking=True)), non_blocking=True)
+    f1.record()
+    barrier()
+    ms_e2e = max(f0.elapsed_time(f1), (time.time() - t0) * 1e3)
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        return
+    from dsr_b200._lib import lib
+    plan = next(iter(g._plans.values()))
+    launches = lib.dsr_gen_last_launches(plan.handle) * ((B + g.max_chunk - 1) // g.max_chunk)
+    pk = peaks()
+    ips = world * args.steps * B / (ms * 1e-3)
+    tfl = GAN_FLOPS_96 * B * args.steps / (ms * 1e-3) / 1e12
+    line = {'metric': 'SRGAN generator images/s (96x96 LR patches, x8, batch 256)', 'value': ips, 'unit': 'images/s',
+            'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f16 operands / f32 accumulate (tcgen05 kind::f16), eval-mode BatchNorm folded', 'data': 'synthetic',
+            'config': {'workload': f'SRResNet generator inference (eval_GAN), batch {B} of 96x96 LR patches -> 768x768 '
+                                   f'per GPU (BASELINE configs[3]; the reference Generator builds x8 / x16 only), '
+                                   f'chunks of {g.max_chunk} images per library call',
+                       'batch': B, 'factor': 8, 'l2': 'activations of a 32-image chunk are 0.3-2.4 GB >> 126 MB L2'},
+            'roofline': {'bound': 'tensor', 'kernel': 'whole forward: conv_halo2_kernel<1> (3x3 64->64 / 64->256+shuffle) '
+                         'and conv_halo2_kernel<2> (9x9 64->3)', 'achieved': tfl, 'peak': pk['tflops'], 'unit': 'TFLOP/s',
+                         'frac': tfl / pk['tflops'] if pk['tflops'] else None, 'traffic': None, 'peak_source': pk['src'],
+                         'gflop_per_image': GAN_FLOPS_96 / 1e9},
+            'e2e': {'value': world * n_e2e * B / (ms_e2e * 1e-3), 'unit': 'images/s', 'h2d_bytes_per_step': hx.numel() * 4,
+                    'd2h_bytes_per_step': hy.numel() * 4, 'ms_per_step': ms_e2e / n_e2e,
+                    'path': 'dsr_b200.Generator.__call__ on a pinned host batch, SR batch copied back to pinned host memory'},
+            'gpu_launches': launches * args.steps, 'clocks': clocks}
+    if world == 1 and not args.no_cpu:
+        ips_cpu, n, cores = gan_cpu_images_per_s(8, budget_s=30.0)
+        line['cpu_baseline'] = {'value': ips_cpu, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
+                                'sample': f'{n} single-image forwards at 96x96 (median), oracle/gan_oracle.py on torch CPU'}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument('--workload', default='dip', choices=['dip', 'gan_eval'],
+                    help='dip: the headline DIP iteration (BASELINE configs[1]); gan_eval: SRResNet generator inference (configs[3])')
+    ap.add_argument('--batch', type=int, default=256, help='gan_eval: LR patches per step')
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--steps', type=int, default=None)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--size', type=int, default=512)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
@@ -466,11 +592,13 @@ def main():
     ap.add_argument('--no-cpu', action='store_true')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if args.steps is None:
+        args.steps = 200 if args.workload == 'dip' else (10 if args.impl == 'ours' else 8)
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     if args.impl == 'reference':
-        run_reference(args, rank, world)
+        (run_reference if args.workload == 'dip' else run_gan_reference)(args, rank, world)
         return
     if not torch.cuda.is_available():
         raise SystemExit('bench.py: no CUDA device (the product path has no CPU fallback; use --impl reference for the CPU arm)')
@@ -479,7 +607,7 @@ def main():
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     try:
-        run_ours(args, rank, local_rank, world)
+        (run_ours if args.workload == 'dip' else run_gan)(args, rank, local_rank, world)
     finally:
         if world > 1:
             import torch.distributed as dist

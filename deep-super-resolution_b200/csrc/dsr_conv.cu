@@ -828,6 +828,198 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHalo2Threads, 1)
 }
 
 // =============================================================================================
+// conv9_out_kernel: the generator's 9 x 9, 64 -> 3 output convolution + tanh (generator.py:63,80-82) on CTA pairs.
+//
+// With N = 3 real output channels a tap-by-tap implicit GEMM (conv_halo2_kernel<2>) issues 81 x 4 MMAs of N = 16 per
+// 256 pixels and is bound by the A-operand fetch of each MMA (measured 43 clk / MMA, 83 TFLOP/s).  Here the kx taps
+// are folded into N:   S[p'][kx * 3 + co] = sum_ky sum_ci X[p' + (ky, 0)][ci] * W[ky][kx][co][ci]      (N = 27 -> 32)
+// is accumulated over the 9 ky taps (row-shifted views of one halo tile) in TMEM -- 9 x 4 MMAs -- and the epilogue
+// finishes  out[y][x][co] = sum_kx S[(y, x + kx)][kx * 3 + co]  through shared memory (an x-shift within one row).
+// Geometry per CTA: halo tile 32 x 16 pixels x 64 ch (one TMA box, 64 KB, rows contiguous so a 128-row MMA operand
+// is 4 whole halo rows: SBO = 1024); two M = 128 units (4 rows x 32 S-positions each) give 24 x 8 output pixels.
+// 72 MMAs (pair: M = 256, N = 32, K = 16) per 384 output pixels instead of 486.
+// =============================================================================================
+constexpr int kC9Threads = 192;            // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+constexpr int kC9OutW = 24, kC9OutH = 8;   // output pixels per CTA tile
+constexpr int kC9HaloW = 32, kC9HaloH = 16;
+constexpr int kC9Slot = kC9HaloW * kC9HaloH * 128;          // 65536
+constexpr int kC9Slots = 2;
+constexpr int kC9WBlock = 16 * 128;                         // one ky block of this CTA's 16 weight rows
+constexpr int kC9SStride = 27;                              // floats per S row in the staging buffer (odd: no bank conflicts)
+constexpr int kC9Stage = 128 * kC9SStride * 4;              // 13824
+constexpr int kC9Smem = 9 * kC9WBlock + kC9Slots * kC9Slot + 2 * kC9Stage + 256 + 1024 + 1024;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kC9Threads, 1)
+    conv9_out_kernel(const __grid_constant__ HaloParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* a_slots = smem;                                  // [kC9Slots][64 KB]
+  uint8_t* bres = a_slots + kC9Slots * kC9Slot;             // [9][16 rows][128 B]
+  float* stage = reinterpret_cast<float*>(bres + ((9 * kC9WBlock + 1023) & ~1023));   // [2][128][27]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(stage) + 2 * kC9Stage);
+  uint64_t* wfull = bars;                 // [2]  (CTA 0's copy is the live one)
+  uint64_t* wempty = bars + 2;            // [2]
+  uint64_t* tfull = bars + 4;             // [2]
+  uint64_t* tempty = bars + 6;            // [2]  (CTA 0's copy: 4 epilogue warps x 2 CTAs)
+  uint64_t* bres_bar = bars + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair0 = blockIdx.x >> 1, pair_stride = gridDim.x >> 1;
+  const int ntiles = p.tiles_x * p.tiles_y;
+  const int npairs = (ntiles + 1) >> 1;
+  constexpr int kAcc = 2;                 // accumulator stages, 64 TMEM columns each (2 units x N = 32)
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.a64);
+    tma_prefetch_desc(&p.b64);
+    for (int i = 0; i < kC9Slots; ++i) { mbar_init(&wfull[i], 1); mbar_init(&wempty[i], 1); }
+    for (int i = 0; i < kAcc; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
+    mbar_init(bres_bar, 1);
+    fence_barrier_init();
+  }
+  cluster_sync_all();
+  if (warp == 1) {
+    tmem_alloc_pair(tmem_slot, 128);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (warp == 0 && lane == 0) {          // resident weights (packed at load time), fetched before the PDL wait
+    if (rank == 0) mbar_arrive_expect_tx(bres_bar, 2 * 9 * kC9WBlock);
+    for (int ky = 0; ky < 9; ++ky)
+      tma_load_2d_pair(&p.b64, bres_bar, bres + ky * kC9WBlock, 0, ky * 32 + static_cast<int>(rank) * 16);
+  }
+  pdl_sync();
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int ws = 0;
+      uint32_t wph = 0;
+      for (int pair = pair0; pair < npairs; pair += pair_stride) {
+        const int tile = 2 * pair + static_cast<int>(rank);       // == ntiles for an odd count: coordinates still valid
+        const int x0 = (tile % p.tiles_x) * kC9OutW - 4;
+        const int y0 = (tile / p.tiles_x) * kC9OutH - 4;
+        mbar_wait(&wempty[ws], wph ^ 1, p.err, 41);
+        if (rank == 0) mbar_arrive_expect_tx(&wfull[ws], 2 * kC9Slot);
+        tma_load_5d_pair(&p.a64, &wfull[ws], a_slots + ws * kC9Slot, 0, 0, x0, 0, y0);
+        if (++ws == kC9Slots) { ws = 0; wph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (CTA 0 only) =====================
+    if (rank == 0) {
+      mbar_wait(bres_bar, 0, p.err, 43);
+      int ws = 0, it = 0;
+      uint32_t wph = 0;
+      const uint64_t dsc = make_smem_desc(0, 16, 1024, SWZ_128B);
+      const uint32_t d_hi = static_cast<uint32_t>(dsc >> 32), d_lo0 = static_cast<uint32_t>(dsc);
+      const uint32_t b_lo = d_lo0 | ((smem_u32(bres) & 0x3FFFF) >> 4);
+      const uint32_t idesc = p.idesc_wide;
+      for (int pair = pair0; pair < npairs; pair += pair_stride, ++it) {
+        const int as = it % kAcc;
+        const uint32_t aph = (it / kAcc) & 1;
+        mbar_wait(&tempty[as], aph ^ 1, p.err, 44);
+        mbar_wait(&wfull[ws], wph, p.err, 45);
+        tc_fence_after();
+        const uint32_t a_lo = d_lo0 | ((smem_u32(a_slots + ws * kC9Slot) & 0x3FFFF) >> 4);
+        if (elect_one()) {
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * 64 + u * 32);
+#pragma unroll
+            for (int ky = 0; ky < 9; ++ky) {
+              // rows (4 u + ky) * 32 .. + 127 of the halo tile: 128 B per row, descriptor units of 16 B
+              const uint32_t da_lo = a_lo + static_cast<uint32_t>((4 * u + ky) * 32 * 8);
+              const uint32_t db_lo = b_lo + static_cast<uint32_t>(ky * (kC9WBlock >> 4));
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                umma_f16_pair(tmem_d, (static_cast<uint64_t>(d_hi) << 32) | (da_lo + 2u * j),
+                              (static_cast<uint64_t>(d_hi) << 32) | (db_lo + 2u * j), idesc, (ky | j) ? 1u : 0u);
+            }
+          }
+          umma_commit_pair(&wempty[ws]);
+          umma_commit_pair(&tfull[as]);
+        }
+        __syncwarp();
+        if (++ws == kC9Slots) { ws = 0; wph ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue (both CTAs: 4 warps = 128 S-positions per unit) =====================
+    const int quarter = warp & 3;
+    const int m = quarter * 32 + lane;            // TMEM lane = S-position: row m / 32 (0..3), x' = m % 32
+    const int et = threadIdx.x - 64;              // 0..127 among the epilogue warps
+    const float b0 = __ldg(p.ep_bias), b1 = __ldg(p.ep_bias + 1), b2 = __ldg(p.ep_bias + 2);
+    int it = 0;
+    for (int pair = pair0; pair < npairs; pair += pair_stride, ++it) {
+      const int as = it % kAcc;
+      const uint32_t aph = (it / kAcc) & 1;
+      const int tile = 2 * pair + static_cast<int>(rank);
+      const int tx0 = (tile % p.tiles_x) * kC9OutW, ty0 = (tile / p.tiles_x) * kC9OutH;
+      mbar_wait(&tfull[as], aph, p.err, 47);
+      tc_fence_after();
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(as * 64 + u * 32);
+        uint32_t v0[16], v1[16];
+        tmem_ld16(taddr, v0);
+        tmem_ld16(taddr + 16, v1);
+        tmem_ld_wait();
+        float* srow = stage + u * (128 * kC9SStride) + m * kC9SStride;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) srow[i] = __uint_as_float(v0[i]);
+#pragma unroll
+        for (int i = 0; i < 11; ++i) srow[16 + i] = __uint_as_float(v1[i]);
+        if (u == 1) {                              // both units are out of TMEM: release the accumulator stage
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(&tempty[as], 0);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        // 96 output pixels of this unit (4 rows x 24), one thread each
+        if (et < 4 * kC9OutW) {
+          const int yy = et / kC9OutW, xo = et % kC9OutW;
+          const float* sp = stage + u * (128 * kC9SStride) + (yy * 32 + xo) * kC9SStride;
+          float o0 = b0, o1 = b1, o2 = b2;
+#pragma unroll
+          for (int kx = 0; kx < 9; ++kx) {
+            o0 += sp[kx * (kC9SStride + 3)];
+            o1 += sp[kx * (kC9SStride + 3) + 1];
+            o2 += sp[kx * (kC9SStride + 3) + 2];
+          }
+          int y = ty0 + 4 * u + yy;
+          const int x = tx0 + xo;
+          bool valid = (tile < ntiles) && (x < p.out_w) && (y < p.out_h);
+          const int img = y / p.img_rows;
+          y -= img * p.img_rows;
+          valid = valid && (y < p.img_h);
+          if (valid) {
+            float* o = reinterpret_cast<float*>(p.out) + static_cast<long long>(img) * p.out_img_stride +
+                       static_cast<long long>(y) * p.out_sy + x;
+            o[0] = tanhf(o0);
+            o[p.ep_plane] = tanhf(o1);
+            o[2 * p.ep_plane] = tanhf(o2);
+          }
+        }
+      }
+      // staging buffer u is rewritten one tile later, after the next bar.sync of the other unit: every thread has
+      // finished reading it by then (its reads precede its arrival at that barrier)
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc_pair(tmem_base, 128);
+}
+
+// =============================================================================================
 // wgrad_kernel
 // =============================================================================================
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
@@ -1212,6 +1404,16 @@ int launch_conv_halo(const HaloParams& p, int num_sms, cudaStream_t stream) {
     const int npairs = (ntiles + 1) / 2;
     int clusters = num_sms / 2;
     if (clusters > npairs) clusters = npairs;
+    if (p.ep_mode == 3) {                 // generator output conv: its own tile geometry (tiles_x/y count 24 x 8 tiles)
+      static bool c9_done = false;
+      if (!c9_done) {
+        cudaError_t e = cudaFuncSetAttribute(conv9_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kC9Smem);
+        if (e != cudaSuccess) return static_cast<int>(e);
+        c9_done = true;
+      }
+      launch_k(conv9_out_kernel, dim3(2 * clusters), dim3(kC9Threads), kC9Smem, stream, p);
+      return static_cast<int>(cudaGetLastError());
+    }
     if (p.ep_mode == 0) launch_k(conv_halo2_kernel<0>, dim3(2 * clusters), dim3(kHalo2Threads), p.smem_bytes, stream, p);
     else if (p.ep_mode == 1) launch_k(conv_halo2_kernel<1>, dim3(2 * clusters), dim3(kHalo2Threads), p.smem_bytes, stream, p);
     else launch_k(conv_halo2_kernel<2>, dim3(2 * clusters), dim3(kHalo2Threads), p.smem_bytes, stream, p);

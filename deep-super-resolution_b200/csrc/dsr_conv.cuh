@@ -102,6 +102,7 @@ struct alignas(64) HaloParams {
   //      Batches are TALL grids: image b occupies rows [b * img_rows, b * img_rows + img_h) of the pixel grid, the
   //      rows between images stay zero (the convolution's zero padding; left / right / top / bottom come from
   //      TMA's out-of-bounds zero fill), and output rows that fall into a gap are not stored.
+  //      3: conv9_out_kernel (the 9 x 9 output conv with the kx taps folded into N; 24 x 8 pixel tiles).
   int ep_mode;
   int wide_slot_bytes;       // A ring slot size for ep_mode != 0 (halo_w * halo_h * 128 rounded up to 1024)
   int img_rows, img_h;       // tall-grid period (H + gap) and image height

@@ -36,12 +36,13 @@ constexpr float kGenBnEps = 1e-5f;
 // ---------------------------------------------------------------------------------------------
 // weight packing (load time): fold eval-mode BatchNorm, convert to fp16 GEMM layout [tap][n][ci]
 //   mode 0: n = co;  mode 1 (PixelShuffle conv, 2 launches dy): out [dy][tap][128][ci], co = (n & 63) * 4 + dy * 2 + (n >> 6);
-//   mode 2 (9x9 output conv): [tap][16][ci], rows n >= cout are zero.
+//   mode 2 (9x9 output conv, tap-by-tap kernel): [tap][16][ci], rows n >= cout are zero;
+//   mode 3 (9x9 output conv, conv9_out_kernel): ktaps = 9 row taps, [ky][32][ci] with n = kx * 3 + co (27 rows used).
 // ---------------------------------------------------------------------------------------------
 __global__ void gen_pack_conv_kernel(const float* __restrict__ w, const float* __restrict__ b,
                                      const float* __restrict__ bn, __half* __restrict__ wout, float* __restrict__ bout,
                                      int cout, int cin, int ktaps, int mode) {
-  const int n_rows = (mode == 1) ? 128 : (mode == 2 ? 16 : cout);
+  const int n_rows = (mode == 1) ? 128 : (mode == 2 ? 16 : (mode == 3 ? 32 : cout));
   const int n_dy = (mode == 1) ? 2 : 1;
   const long long total = static_cast<long long>(n_dy) * ktaps * n_rows * cin;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -53,7 +54,12 @@ __global__ void gen_pack_conv_kernel(const float* __restrict__ w, const float* _
     int co = n;
     if (mode == 1) co = (n & 63) * 4 + dy * 2 + (n >> 6);
     float v = 0.f;
-    if (co < cout) {
+    if (mode == 3) {
+      const int kx = n / 3;
+      co = n - 3 * kx;
+      if (n < 27) v = w[(static_cast<long long>(co) * cin + ci) * 81 + tap * 9 + kx];
+      if (n >= 3) co = cout;                        // bias slots: n < 3 only
+    } else if (co < cout) {
       v = w[(static_cast<long long>(co) * cin + ci) * ktaps + tap];
       if (bn != nullptr) v *= bn[co] * rsqrtf(bn[3 * cout + co] + kGenBnEps);
     }
@@ -184,6 +190,7 @@ struct dsr_gen_plan {
   size_t ws_bytes = 0;
   uint8_t* ws = nullptr;
   bool bound = false, loaded = false;
+  bool conv3_taps = false;       // DSR_GEN_CONV3_TAPS=1: tap-by-tap 9x9 kernel (conv_halo2_kernel<2>) instead of conv9_out_kernel
   GenTall x0, xa, xb, t1, s[4];
   size_t off_w33 = 0, off_wsh = 0, off_w3 = 0, off_bias = 0, off_w1 = 0, off_slopes = 0, off_slope_offs = 0, off_err = 0;
   __half *w33 = nullptr, *wsh = nullptr, *w3 = nullptr;
@@ -323,6 +330,7 @@ int dsr_gen_plan_create(dsr_gen_plan_t** out, int factor, int residual_blocks, i
   cudaDeviceProp prop;
   if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&prop, dev) == cudaSuccess)
     p->num_sms = prop.multiProcessorCount;
+  p->conv3_taps = getenv("DSR_GEN_CONV3_TAPS") != nullptr;
   gen_layout(p);
   size_t off = 0;
   auto take = [&](size_t bytes) {
@@ -333,8 +341,8 @@ int dsr_gen_plan_create(dsr_gen_plan_t** out, int factor, int residual_blocks, i
   p->off_err = take(256);
   p->off_w33 = take(static_cast<size_t>(2 * p->nres + 1) * 9 * kGF * kGF * 2);
   p->off_wsh = take(static_cast<size_t>(p->nshuf) * 2 * 9 * 128 * kGF * 2);
-  p->off_w3 = take(static_cast<size_t>(81) * 16 * kGF * 2);
-  p->off_bias = take(static_cast<size_t>(bias_off_3(p) + 16) * 4);
+  p->off_w3 = take(static_cast<size_t>(81) * 16 * kGF * 2);          // either layout: [81][16][64] or [9][32][64]
+  p->off_bias = take(static_cast<size_t>(bias_off_3(p) + 32) * 4);
   p->off_w1 = take(static_cast<size_t>(243 + 1) * kGF * 4);          // [243][64] weights + [64] bias
   p->off_slopes = take(static_cast<size_t>(1 + p->nres + p->nshuf) * 4);
   p->off_slope_offs = take(static_cast<size_t>(1 + p->nres + p->nshuf) * 8);
@@ -438,7 +446,18 @@ int dsr_gen_bind(dsr_gen_plan_t* p, void* workspace, size_t bytes, void* stream)
     cur = &p->s[i];
   }
   // y = tanh(conv3(.))           (generator.py:80-82); output pointer patched per call
-  if ((rc = gen_make_conv(p, hp, *cur, p->w3, 16, 9, 2))) return rc;
+  if (p->conv3_taps) {
+    if ((rc = gen_make_conv(p, hp, *cur, p->w3, 16, 9, 2))) return rc;
+  } else {                       // conv9_out_kernel: kx folded into N, 24 x 8 pixel tiles, 32 x 16 halo boxes
+    if ((rc = gen_make_conv(p, hp, *cur, p->w3, 16, 9, 3))) return rc;
+    if ((rc = make_act_map(&hp.a64, cur->ptr, 1, kGF, cur->W, cur->rows, 1, 64, 32, 16))) return rc;
+    if ((rc = make_wgt_map(&hp.b64, p->w3, kGF, 9 * 32, 64, 16))) return rc;
+    hp.a16 = hp.a64;
+    hp.b16 = hp.b64;
+    hp.tiles_x = (cur->W + 23) / 24;
+    hp.tiles_y = (cur->rows + 7) / 8;
+    hp.idesc_wide = hp.idesc_narrow = make_idesc_f16(256, 32, FMT_F16, FMT_F16, 0, 0);
+  }
   hp.out = nullptr;
   hp.out_img_stride = 3LL * cur->H * cur->W;
   hp.out_sy = cur->W;
@@ -458,7 +477,7 @@ int dsr_gen_load_weights(dsr_gen_plan_t* p, const float* st, void* stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const size_t w33_stride = static_cast<size_t>(9) * kGF * kGF;
   auto pack = [&](const float* w, const float* b, const float* bn, __half* wout, float* bout, int cout, int ktaps, int mode) {
-    const long long total = static_cast<long long>(mode == 1 ? 2 * 128 : (mode == 2 ? 16 : cout)) * ktaps * kGF;
+    const long long total = static_cast<long long>(mode == 1 ? 2 * 128 : (mode == 2 ? 16 : (mode == 3 ? 32 : cout))) * ktaps * kGF;
     const int blocks = static_cast<int>((total + 255) / 256);
     gen_pack_conv_kernel<<<blocks, 256, 0, s>>>(w, b, bn, wout, bout, cout, kGF, ktaps, mode);
   };
@@ -473,7 +492,8 @@ int dsr_gen_load_weights(dsr_gen_plan_t* p, const float* st, void* stream) {
   for (int i = 0; i < p->nshuf; ++i)
     pack(st + p->o_sc_w[i], st + p->o_sc_b[i], nullptr, p->wsh + static_cast<size_t>(2 * i) * 9 * 128 * kGF,
          p->bias + bias_off_sh(p, i, 0), 4 * kGF, 9, 1);
-  pack(st + p->o_conv3_w, st + p->o_conv3_b, nullptr, p->w3, p->bias + bias_off_3(p), 3, 81, 2);
+  if (p->conv3_taps) pack(st + p->o_conv3_w, st + p->o_conv3_b, nullptr, p->w3, p->bias + bias_off_3(p), 3, 81, 2);
+  else pack(st + p->o_conv3_w, st + p->o_conv3_b, nullptr, p->w3, p->bias + bias_off_3(p), 3, 9, 3);
   gen_pack_conv1_kernel<<<(243 * kGF + 255) / 256, 256, 0, s>>>(st + p->o_conv1_w, p->w1);
   std::vector<long long> offs;
   offs.push_back(p->o_prelu1);
@@ -511,7 +531,7 @@ int dsr_gen_forward(dsr_gen_plan_t* p, const float* x, float* y, void* stream) {
   ++n;
   for (size_t i = 0; i < p->launches.size(); ++i) {
     HaloParams hp = p->launches[i];
-    if (hp.ep_mode == 2) hp.out = y;
+    if (hp.ep_mode >= 2) hp.out = y;
     const int rc = launch_conv_halo(hp, p->num_sms, s);
     if (rc) return rc;
     ++n;

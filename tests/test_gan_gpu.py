@@ -37,6 +37,14 @@ def test_generator_matches_reference_fixture(golden, name):
     assert float((y - fx['y']).abs().max()) <= 5e-3          # outputs are tanh values in (-1, 1)
 
 
+def test_generator_tap_by_tap_output_conv(golden, monkeypatch):
+    """The 81-tap variant of the 9 x 9 output convolution (conv_halo2_kernel<2>, kept for A/B) gives the same image."""
+    monkeypatch.setenv('DSR_GEN_CONV3_TAPS', '1')
+    fx = golden('gan_f8_1x17x23.pt')
+    y = build(fx)(fx['x'].cuda()).cpu()
+    assert rel_l2(y, fx['y']) <= REL_L2_TOL
+
+
 def test_generator_intermediates_match_oracle(golden):
     """Every stage (conv1, residual trunk, each PixelShuffle block) against the oracle's recorded intermediates."""
     from dsr_b200._lib import lib, check
