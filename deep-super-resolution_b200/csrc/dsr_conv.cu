@@ -566,6 +566,11 @@ __device__ __forceinline__ void halo_epilogue_fused(const HaloParams& p, const u
 
 // EP: 0 = DIP step (raw fp16 output + BatchNorm sums), 1 = generator 3x3 / 1x1 (fused bias, PReLU, residual; tall
 // batch grid), 2 = generator 9x9 output conv (81 shifted views of one 16 x 24 halo tile, tanh, fp32 NCHW planes).
+#ifndef DSR_EARLY_RELEASE0
+#define DSR_EARLY_RELEASE0 1
+#endif
+constexpr bool kEarlyRelease0 = DSR_EARLY_RELEASE0 != 0;   // DIP epilogue: drain the stage into registers first
+constexpr bool kRelaxedRelease = true;    // accumulator hand-back without release semantics (see dsr_ptx.cuh)
 template <int EP>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHalo2Threads, 1)
     conv_halo2_kernel(const __grid_constant__ HaloParams p) {
@@ -767,18 +772,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHalo2Threads, 1)
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(as * 256);
       obase += static_cast<long long>(y) * p.out_sy + static_cast<long long>(x) * p.out_sx;
       if (EP == 1) {
+        // all of this warp's accumulator columns (<= 64) go to registers in one TMEM round trip, the stage is handed
+        // back to the MMA warp at once, and only then the bias / PReLU / residual / store work starts
         const float slope = (p.ep_slope != nullptr) ? __ldg(p.ep_slope) : 0.f;
-        uint32_t v[2][16];
-        tmem_ld16(taddr + static_cast<uint32_t>(c_begin * 16), v[0]);
+        uint32_t v[4][16];
 #pragma unroll
-        for (int i = 0; i < 5; ++i) {
-          const int c = c_begin + i;
-          if (c < c_end) {
-            tmem_ld_wait();
-            if (c + 1 < c_end) tmem_ld16(taddr + static_cast<uint32_t>((c + 1) * 16), v[(i + 1) & 1]);
-            halo_epilogue_fused(p, v[i & 1], c, valid, obase, slope);
-          }
-        }
+        for (int i = 0; i < 4; ++i)
+          if (c_begin + i < c_end) tmem_ld16(taddr + static_cast<uint32_t>((c_begin + i) * 16), v[i]);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster_relaxed(&tempty[as], 0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (c_begin + i < c_end) halo_epilogue_fused(p, v[i], c_begin + i, valid, obase, slope);
+        continue;
       } else if (EP == 2) {
         if (half == 0) {                   // N = 16: one chunk; the first n_store columns are the image planes
           uint32_t v[16];
@@ -791,6 +799,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHalo2Threads, 1)
               if (n < p.n_store) o[n * p.ep_plane] = tanhf(__uint_as_float(v[n]) + __ldg(p.ep_bias + n));
           }
         }
+      } else if (kEarlyRelease0 && !(p.dbg & 2)) {
+        // DIP epilogue: the warp's <= 80 accumulator columns in one TMEM round trip, stage handed back at once
+        uint32_t v[5][16];
+#pragma unroll
+        for (int i = 0; i < 5; ++i)
+          if (c_begin + i < c_end) tmem_ld16(taddr + static_cast<uint32_t>((c_begin + i) * 16), v[i]);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster_relaxed(&tempty[as], 0);
+#pragma unroll
+        for (int i = 0; i < 5; ++i)
+          if (c_begin + i < c_end) halo_epilogue_process(p, v[i], c_begin + i, 0, valid, obase, lane, acc_s[i], acc_q[i]);
+        continue;
       } else if (!(p.dbg & 2)) {
         uint32_t v[2][16];
         tmem_ld16(taddr + static_cast<uint32_t>(c_begin * 16), v[0]);
@@ -806,7 +828,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHalo2Threads, 1)
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(&tempty[as], 0);
+      if (lane == 0) {
+        if (kRelaxedRelease) mbar_arrive_cluster_relaxed(&tempty[as], 0);
+        else mbar_arrive_cluster(&tempty[as], 0);
+      }
     }
     if (p.stats != nullptr && (lane & 1) == 0) {
       const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
