@@ -1344,8 +1344,21 @@ static int net_forward_impl(dsr_plan_t* p, const float* params, const float* z, 
   p->launches = 0;
   cudaError_t e = cudaMemsetAsync(p->base + p->acc_fwd_off, 0, p->acc_fwd_floats * 4, s);
   if (e != cudaSuccess) return static_cast<int>(e);
+  // The fp16 weight packing (25 us) depends only on the parameters and the input packing (29 us) only on z and the
+  // fp32 skip weights: they run side by side (pack on the side stream, joined before the first convolution).
+  const bool fork_head = p->side != nullptr && p->use_side && p->profile != 2 && !getenv("DSR_NO_HEAD_FORK");
+  if (fork_head) {
+    e = cudaEventRecord(p->ev_fork, s);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    e = cudaStreamWaitEvent(p->side, p->ev_fork, 0);
+    if (e != cudaSuccess) return static_cast<int>(e);
+  }
   DSR_TRY(launch_pack_weights(params, p->warena.ptr, static_cast<const PackDesc*>(p->pack_table.ptr),
-                              static_cast<int>(p->pack_host.size()), s));
+                              static_cast<int>(p->pack_host.size()), fork_head ? p->side : s));
+  if (fork_head) {
+    e = cudaEventRecord(p->ev_join, p->side);
+    if (e != cudaSuccess) return static_cast<int>(e);
+  }
   Level& L0 = p->lv[0];
   {
     // level 0's skip conv and (whole-step path) the input perturbation ride on the packing pass when it has the
@@ -1361,6 +1374,10 @@ static int net_forward_impl(dsr_plan_t* p, const float* params, const float* z, 
                               fskip ? reinterpret_cast<float*>(p->base) + L0.skip_stats_off : nullptr,
                               fast ? p->pz_saved : nullptr, p->psigma, p->pseed,
                               static_cast<const float*>(p->stepstate.ptr)));
+  }
+  if (fork_head) {
+    e = cudaStreamWaitEvent(s, p->ev_join, 0);
+    if (e != cudaSuccess) return static_cast<int>(e);
   }
   int rc = forward_level(p, 0, params, s);
   if (rc) return rc;
