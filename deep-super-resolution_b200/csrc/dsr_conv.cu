@@ -595,7 +595,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHalo2Threads, 1)
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
-  const int pair0 = blockIdx.x >> 1, pair_stride = gridDim.x >> 1;
+  const int nsl = (EP == 0 && p.nsplit > 1) ? p.nsplit : 1;
+  const int cluster_id = blockIdx.x >> 1;
+  const int slice = cluster_id % nsl;                        // this cluster's slice of the output channels
+  const int pair0 = cluster_id / nsl, pair_stride = (gridDim.x >> 1) / nsl;
+  const int ch0 = slice * 2 * p.n_part;
   const int ntiles = p.tiles_x * p.tiles_y;
   const int npairs = (ntiles + 1) >> 1;
   constexpr int kAcc = 2;                 // accumulator stages, 256 TMEM columns apart
@@ -623,7 +627,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHalo2Threads, 1)
     const uint32_t bbytes = static_cast<uint32_t>(p.ntaps * (p.n_wide * wb + p.n_narrow * nb));
     if (rank == 0) mbar_arrive_expect_tx(bres_bar, 2 * bbytes);
     for (int t = 0; t < p.ntaps; ++t) {
-      const int row = (EP == 2 ? t * 2 * p.n_part : p.taps[t].b_row) + static_cast<int>(rank) * p.n_part;
+      const int row = (EP == 2 ? t * 2 * p.n_part : p.taps[t].b_row) + ch0 + static_cast<int>(rank) * p.n_part;
       for (int c = 0; c < p.n_wide; ++c)
         tma_load_2d_pair(&p.b64, bres_bar, bres_w + (t * p.n_wide + c) * wb, c * 64, row);
       if (p.n_narrow) tma_load_2d_pair(&p.b16, bres_bar, bres_n + t * nb, p.n_wide * 64, row);
@@ -811,7 +815,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHalo2Threads, 1)
         if (lane == 0) mbar_arrive_cluster_relaxed(&tempty[as], 0);
 #pragma unroll
         for (int i = 0; i < 5; ++i)
-          if (c_begin + i < c_end) halo_epilogue_process(p, v[i], c_begin + i, 0, valid, obase, lane, acc_s[i], acc_q[i]);
+          if (c_begin + i < c_end) halo_epilogue_process(p, v[i], c_begin + i, ch0, valid, obase, lane, acc_s[i], acc_q[i]);
         continue;
       } else if (!(p.dbg & 2)) {
         uint32_t v[2][16];
@@ -822,7 +826,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHalo2Threads, 1)
           if (c < c_end) {
             tmem_ld_wait();
             if (c + 1 < c_end) tmem_ld16(taddr + static_cast<uint32_t>((c + 1) * 16), v[(i + 1) & 1]);
-            halo_epilogue_process(p, v[i & 1], c, 0, valid, obase, lane, acc_s[i], acc_q[i]);
+            halo_epilogue_process(p, v[i & 1], c, ch0, valid, obase, lane, acc_s[i], acc_q[i]);
           }
         }
       }
@@ -839,8 +843,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHalo2Threads, 1)
       for (int i = 0; i < 5; ++i) {
         const int c = c_begin + i;
         if (c < c_end) {
-          atomicAdd(&p.stats[c * 16 + col], acc_s[i]);
-          atomicAdd(&p.stats[p.stats_stride + c * 16 + col], acc_q[i]);
+          atomicAdd(&p.stats[ch0 + c * 16 + col], acc_s[i]);
+          atomicAdd(&p.stats[p.stats_stride + ch0 + c * 16 + col], acc_q[i]);
         }
       }
     }
@@ -1428,7 +1432,13 @@ int launch_conv_halo(const HaloParams& p, int num_sms, cudaStream_t stream) {
   if (p.pair) {                          // CTA pairs: one pair per two tiles, every CTA keeps half of the weights
     const int npairs = (ntiles + 1) / 2;
     int clusters = num_sms / 2;
-    if (clusters > npairs) clusters = npairs;
+    if (p.ep_mode == 0 && p.nsplit > 1) {          // N split: every group of nsplit clusters walks the same tile pairs
+      int groups = clusters / p.nsplit;
+      if (groups > npairs) groups = npairs;
+      clusters = groups * p.nsplit;
+    } else if (clusters > npairs) {
+      clusters = npairs;
+    }
     if (p.ep_mode == 3) {                 // generator output conv: its own tile geometry (tiles_x/y count 24 x 8 tiles)
       static bool c9_done = false;
       if (!c9_done) {

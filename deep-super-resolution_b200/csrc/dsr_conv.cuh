@@ -111,6 +111,12 @@ struct alignas(64) HaloParams {
   const float* ep_bias;      // [N] fp32 (folded conv bias + eval-mode BatchNorm shift)
   const float* ep_slope;     // device scalar: PReLU slope, or nullptr for no activation
   const void* ep_res;        // fp16 residual tensor with the output's addressing, or nullptr
+  // ---- N split across clusters (pair kernel, DIP epilogue; latency-bound small levels): cluster k owns output
+  //      channels [slice * 2 n_part, (slice + 1) * 2 n_part) with slice = k % nsplit for the whole launch (its
+  //      resident weights are that slice only) and walks tile pairs k / nsplit, k / nsplit + clusters / nsplit, ...
+  //      A level with a handful of tiles then spreads over nsplit x more SMs, each with a 1 / nsplit as long MMA
+  //      chain per tile.  0 or 1: no split.
+  int nsplit;
 };
 
 // ---------------------------------------------------------------------------------------------

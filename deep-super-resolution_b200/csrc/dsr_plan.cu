@@ -632,6 +632,14 @@ int build_conv(dsr_plan* p, ConvLayer& c) {
       h.n_narrow = (c.cin_pad - 128) / 16;
       h.n_part = 64;
       h.parts = 2;
+      h.nsplit = 1;
+      if (!getenv("DSR_HALO_1CTA") && !getenv("DSR_NO_NSPLIT") && c.k == 3) {
+        // small levels: spread the output channels over 2 or 4 clusters per tile pair (see HaloParams::nsplit)
+        const int np = (((c.outW + kHaloTW - 1) / kHaloTW) * ((c.outH + kHaloTH - 1) / kHaloTH) + 1) / 2;
+        for (int d = 4; d >= 2; d >>= 1)
+          if (np * d <= p->num_sms / 2) { h.nsplit = d; break; }
+        h.n_part = 64 / h.nsplit;
+      }
       h.wide_slots = h.n_narrow ? 2 : 3;
       h.ntaps = c.k * c.k;
       h.halo_w = kHaloTW + (c.k - 1);
@@ -670,6 +678,7 @@ int build_conv(dsr_plan* p, ConvLayer& c) {
       h.dbg = getenv("DSR_HALO_DBG") ? atoi(getenv("DSR_HALO_DBG")) : 0;
       h.pair = getenv("DSR_HALO_1CTA") ? 0 : 1;
       if (h.pair) h.idesc_wide = h.idesc_narrow = make_idesc_f16(256, 2 * h.n_part, FMT_F16, FMT_F16, 0, 0);
+      h.wide_slot_bytes = kHaloWideSlot;
       h.err = static_cast<int*>(p->errword.ptr);
     }
     if (c.need_dgrad) {
@@ -682,6 +691,17 @@ int build_conv(dsr_plan* p, ConvLayer& c) {
       h.pair = getenv("DSR_HALO_1CTA") ? 0 : 1;
       h.parts = (h.pair || c.n_rows == 128) ? 2 : 3;
       h.n_part = c.n_rows / h.parts;                    // 64 / 72 (pairs) or 64 / 48
+      h.nsplit = 1;
+      if (h.pair && !getenv("DSR_NO_NSPLIT") && c.k == 3) {
+        const int np = (((iWp + kHaloTW - 1) / kHaloTW) * ((iHp + kHaloTH - 1) / kHaloTH) + 1) / 2;
+        if (c.n_rows == 144) {
+          if (np * 3 <= p->num_sms / 2) h.nsplit = 3;   // 3 x 48 channels
+        } else {
+          for (int d = 4; d >= 2; d >>= 1)
+            if (np * d <= p->num_sms / 2) { h.nsplit = d; break; }
+        }
+        h.n_part = c.n_rows / (2 * h.nsplit);
+      }
       h.wide_slots = (h.n_part > 64) ? 2 : 3;           // 72-row weight slices leave room for two halo slots only
       h.ntaps = c.k * c.k;
       h.halo_w = kHaloTW + (c.k - 1);
