@@ -523,15 +523,18 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
 // both CTAs' barriers; both CTAs' epilogue warps release the accumulator stage on CTA 0's barrier.
 // =============================================================================================
 // Generator epilogue (EP = 1): out = [residual +] prelu(acc + bias), 16 channels of one pixel, fp16, one 32-byte store.
+// The bias vector sits in shared memory (copied once per CTA) and the residual values were fetched before the
+// accumulator wait, so nothing here waits on a global load.
 __device__ __forceinline__ void halo_epilogue_fused(const HaloParams& p, const uint32_t (&v)[16], int c, bool valid,
-                                                    long long obase, float slope) {
+                                                    long long obase, float slope, const float* sbias,
+                                                    const uint4 (&res)[2]) {
   const int ch = c * 16;
   if (!valid || ch >= p.n_store) return;
   float f[16];
-  const float4* b4 = reinterpret_cast<const float4*>(p.ep_bias + ch);
+  const float4* b4 = reinterpret_cast<const float4*>(sbias + ch);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const float4 b = __ldg(b4 + i);
+    const float4 b = b4[i];
     f[4 * i + 0] = __uint_as_float(v[4 * i + 0]) + b.x;
     f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + b.y;
     f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + b.z;
@@ -542,9 +545,7 @@ __device__ __forceinline__ void halo_epilogue_fused(const HaloParams& p, const u
     for (int i = 0; i < 16; ++i) f[i] = f[i] > 0.f ? f[i] : slope * f[i];
   }
   if (p.ep_res != nullptr) {
-    const uint4* r = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.ep_res) + obase + ch);
-    const uint4 r0 = __ldg(r), r1 = __ldg(r + 1);
-    const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+    const uint32_t rw[8] = {res[0].x, res[0].y, res[0].z, res[0].w, res[1].x, res[1].y, res[1].z, res[1].w};
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const __half2 h = *reinterpret_cast<const __half2*>(&rw[i]);
@@ -591,10 +592,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHalo2Threads, 1)
   uint64_t* tempty = bars + 14;           // [2]  (CTA 0's copy: 8 arrivals = 4 epilogue warps x 2 CTAs)
   uint64_t* bres_bar = bars + 18;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
+  float* sbias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // EP 1: [N] bias (<= 128 floats)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
+  if (EP == 1 && static_cast<int>(threadIdx.x) < 2 * p.n_part) sbias[threadIdx.x] = __ldg(p.ep_bias + threadIdx.x);   // load-time constant
   const int nsl = (EP == 0 && p.nsplit > 1) ? p.nsplit : 1;
   const int cluster_id = blockIdx.x >> 1;
   const int slice = cluster_id % nsl;                        // this cluster's slice of the output channels
@@ -756,6 +759,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHalo2Threads, 1)
     float acc_s[5], acc_q[5];
 #pragma unroll
     for (int c = 0; c < 5; ++c) { acc_s[c] = 0.f; acc_q[c] = 0.f; }
+    const float slope = (EP == 1 && p.ep_slope != nullptr) ? __ldg(p.ep_slope) : 0.f;
     int it = 0;
     for (int pair = pair0; pair < npairs; pair += pair_stride, ++it) {
       const int as = it % kAcc;
@@ -771,14 +775,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHalo2Threads, 1)
         valid = valid && (y < p.img_h);
         obase = static_cast<long long>(img) * p.out_img_stride;
       }
+      obase += static_cast<long long>(y) * p.out_sy + static_cast<long long>(x) * p.out_sx;
+      uint4 res[4][2];
+      if (EP == 1 && p.ep_res != nullptr && valid) {      // residual values: in flight while the MMAs of this tile run
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (c_begin + i < c_end) {
+            const uint4* r = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.ep_res) + obase +
+                                                            (c_begin + i) * 16);
+            res[i][0] = __ldg(r);
+            res[i][1] = __ldg(r + 1);
+          }
+      }
       mbar_wait(&tfull[as], aph, p.err, 37);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(as * 256);
-      obase += static_cast<long long>(y) * p.out_sy + static_cast<long long>(x) * p.out_sx;
       if (EP == 1) {
         // all of this warp's accumulator columns (<= 64) go to registers in one TMEM round trip, the stage is handed
         // back to the MMA warp at once, and only then the bias / PReLU / residual / store work starts
-        const float slope = (p.ep_slope != nullptr) ? __ldg(p.ep_slope) : 0.f;
         uint32_t v[4][16];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -789,7 +803,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHalo2Threads, 1)
         if (lane == 0) mbar_arrive_cluster_relaxed(&tempty[as], 0);
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-          if (c_begin + i < c_end) halo_epilogue_fused(p, v[i], c_begin + i, valid, obase, slope);
+          if (c_begin + i < c_end) halo_epilogue_fused(p, v[i], c_begin + i, valid, obase, slope, sbias, res[i]);
         continue;
       } else if (EP == 2) {
         if (half == 0) {                   // N = 16: one chunk; the first n_store columns are the image planes
@@ -1411,7 +1425,8 @@ int launch_conv_gemm(const ConvGemmParams& p, int num_sms, cudaStream_t stream) 
 
 int halo_smem_bytes(int n_part, int n_wide, int n_narrow, int wide_slots, int ntaps, int slot_bytes) {
   const int bres = ntaps * n_wide * n_part * 128 + ((ntaps * n_narrow * n_part * 32 + 1023) & ~1023);
-  return bres + wide_slots * (slot_bytes ? slot_bytes : kHaloWideSlot) + (n_narrow ? 2 * kHaloNarrowSlot : 0) + 256 + 1024;
+  return bres + wide_slots * (slot_bytes ? slot_bytes : kHaloWideSlot) + (n_narrow ? 2 * kHaloNarrowSlot : 0) + 256 + 512 +
+         1024;                                  // barriers (256) + epilogue bias vector (512) + alignment slack
 }
 
 int launch_conv_halo(const HaloParams& p, int num_sms, cudaStream_t stream) {
