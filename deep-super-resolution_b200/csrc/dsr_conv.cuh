@@ -162,7 +162,13 @@ struct alignas(64) WgradParams {
 // Shared-memory fill per 64 pixels drops from 70 KB to 39 KB (stride 1, 144 channels).  Layers narrower than 8
 // pixels keep the per-tap kernel above.
 // ---------------------------------------------------------------------------------------------
-constexpr int kWgHStages = 4;
+#ifndef DSR_WGH_STAGES
+#define DSR_WGH_STAGES 3
+#endif
+// 3 stages = 157 KB: leaves ~70 KB of the SM's shared memory to the MAIN stream's kernels that run beside the
+// weight-gradient stream (with 4 stages = 209 KB, upcat_bwd_a's 46 KB CTAs could not co-reside and waited for whole
+// wgrad CTAs to retire: 136 us in the replayed graph instead of 48 us alone)
+constexpr int kWgHStages = DSR_WGH_STAGES;
 constexpr int kWgHStageA = 64 * 128 * 2;          // dR: 2 chunks of [64 px][64 co]            = 16 KB
 constexpr int kWgHStageBox = 36 * 1024;           // X boxes of one stage (max: stride 2, 128 ch = 34 KB)
 constexpr int kWgHStageBytes = kWgHStageA + kWgHStageBox;

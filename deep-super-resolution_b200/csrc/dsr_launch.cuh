@@ -37,6 +37,44 @@ inline bool pdl_enabled() {
   return on;
 }
 
+// ---- in-graph timeline (diagnostics, DSR_TIMELINE=1): a one-thread stamp kernel after every launch writes
+// %globaltimer into a slot; consecutive stamps bracket each kernel as it runs inside the replayed graph (warm caches,
+// real dependencies; the stamp costs ~1 us and ends the programmatic overlap with the next launch).
+struct Timeline {
+  unsigned long long* buf = nullptr;     // device, kTimelineSlots entries
+  int n = 0;
+  const void* fn[2048];
+  unsigned grid[2048];
+  cudaStream_t stream[2048];
+};
+constexpr int kTimelineSlots = 2048;
+inline Timeline g_timeline;
+inline bool timeline_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("DSR_TIMELINE");
+    return e != nullptr && e[0] == '1';
+  }();
+  return on;
+}
+static __global__ void timeline_stamp_kernel(unsigned long long* buf, int idx) {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  buf[idx] = t;
+}
+inline void timeline_stamp(const void* fn, unsigned grid, cudaStream_t s) {
+  Timeline& t = g_timeline;
+  if (t.buf == nullptr) {
+    if (cudaMalloc(&t.buf, kTimelineSlots * sizeof(unsigned long long)) != cudaSuccess) return;
+    cudaMemset(t.buf, 0, kTimelineSlots * sizeof(unsigned long long));
+  }
+  if (t.n >= kTimelineSlots) return;
+  t.fn[t.n] = fn;
+  t.grid[t.n] = grid;
+  t.stream[t.n] = s;
+  timeline_stamp_kernel<<<1, 1, 0, s>>>(t.buf, t.n);
+  ++t.n;
+}
+
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
                             Args&&... args) {
@@ -50,7 +88,9 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+  if (timeline_enabled()) timeline_stamp(reinterpret_cast<const void*>(kernel), grid.x * grid.y * grid.z, s);
+  return e;
 }
 
 }  // namespace dsr

@@ -20,6 +20,7 @@
 #include "dsr_debug.h"
 #include "dsr_elem.cuh"
 #include "dsr_host.h"
+#include "dsr_launch.cuh"
 #include "dsr_ptx.cuh"
 
 namespace dsr {
@@ -1542,6 +1543,7 @@ static int enqueue_step(dsr_plan_t* p, const dsr_downsampler_t* d, const dsr_ste
   float* st = static_cast<float*>(p->stepstate.ptr);
   const long long nz = static_cast<long long>(p->input_depth) * p->H * p->W;
   int total = 0;
+  if (timeline_enabled()) g_timeline.n = 0;          // every (eager or captured) iteration stamps slots 0 .. n - 1
   int rc = launch_step_begin(st, losses, t_set, lr, 0.9f, 0.999f, s);
   if (rc) return rc;
   total += 1;
@@ -1637,6 +1639,32 @@ int dsr_dip_run(dsr_plan_t* p, const dsr_downsampler_t* d, const dsr_step_buffer
     if (e != cudaSuccess) return static_cast<int>(e);
   }
   return 0;
+}
+
+// ---- in-graph timeline (DSR_TIMELINE=1; see dsr_launch.cuh) -------------------------------------------
+int dsr_timeline_dump(char* buf, size_t cap) {
+  if (buf == nullptr || cap == 0) return -1;
+  buf[0] = 0;
+  Timeline& t = g_timeline;
+  if (!timeline_enabled() || t.buf == nullptr || t.n == 0) return 0;
+  if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+  std::vector<unsigned long long> h(t.n);
+  if (cudaMemcpy(h.data(), t.buf, t.n * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  size_t off = 0;
+  for (int i = 1; i < t.n; ++i) {
+    const char* name = "?";
+    cudaFuncGetName(&name, t.fn[i]);
+    // duration = time since the previous stamp ON THE SAME STREAM (the side stream runs beside the main one); the
+    // first launch of a stream after a fork is measured from the launch that preceded the fork
+    int prev = i - 1;
+    while (prev > 0 && t.stream[prev] != t.stream[i]) --prev;
+    double us = (static_cast<double>(h[i]) - static_cast<double>(h[prev])) * 1e-3;
+    if (t.stream[i] != t.stream[0]) us = -us;               // side-stream launches are reported with a minus sign
+    const int w = snprintf(buf + off, cap - off, "%d\t%.2f\t%u\t%s\n", i, us, t.grid[i], name);
+    if (w < 0 || static_cast<size_t>(w) >= cap - off) break;
+    off += w;
+  }
+  return static_cast<int>(off);
 }
 
 // ---- introspection ------------------------------------------------------------------------------

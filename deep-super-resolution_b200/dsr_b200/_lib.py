@@ -66,6 +66,7 @@ SIGNATURES = {
     'dsr_plan_profile_dump': (i32, [vp, C.c_char_p, sz]),
     'dsr_plan_device_error': (i32, [vp, C.POINTER(i32)]),
     'dsr_debug_copy': (i32, [vp, vp, sz, vp]),
+    'dsr_timeline_dump': (i32, [C.c_char_p, sz]),
     'dsr_gen_plan_create': (i32, [C.POINTER(vp), i32, i32, i32, i32, i32]),
     'dsr_gen_plan_destroy': (None, [vp]),
     'dsr_gen_state_numel': (i64, [vp]),

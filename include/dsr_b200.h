@@ -142,6 +142,10 @@ int dsr_plan_profile_read(dsr_plan_t* p, int cls, double* ms_total, double* flop
 int dsr_plan_profile_dump(dsr_plan_t* p, char* buf, size_t cap);
 /* The largest recorded launch (by algorithmic FLOPs) of class cls: mean milliseconds over its occurrences, its FLOPs. */
 int dsr_plan_profile_top(dsr_plan_t* p, int cls, double* ms_mean, double* flops);
+/* Diagnostics (process started with DSR_TIMELINE=1): every kernel launch of an iteration is followed by a stamp
+ * kernel that records %globaltimer; dump writes "<index>\t<microseconds since the previous stamp>\t<grid>\t<kernel>"
+ * lines for the most recent (replayed) iteration into buf and returns the number of bytes. */
+int dsr_timeline_dump(char* buf, size_t cap);
 /* Device error word written by a kernel whose mbarrier wait timed out (0 = none). */
 int dsr_plan_device_error(dsr_plan_t* p, int* host_code);
 /* Device-to-device copy on `stream` (lets ctypes callers read an introspected tensor into their own buffer). */

@@ -46,4 +46,21 @@ for scales in scales_list:
     torch.cuda.synchronize()
     print(f'size {size} num_scales {scales}: {e0.elapsed_time(e1) / iters * 1e3:8.1f} us / iteration, '
           f'{lib.dsr_plan_last_launches(plan.handle)} launches, loss {float(losses[iters + 4]):.5f}', flush=True)
+    if os.environ.get('DSR_TIMELINE') == '1':
+        buf = C.create_string_buffer(1 << 20)
+        nbytes = lib.dsr_timeline_dump(buf, 1 << 20)
+        import collections, re
+        rows = [l.split('\t') for l in buf.value.decode().splitlines()]
+        agg, cnt = collections.OrderedDict(), collections.Counter()
+        for _i, us, _g, name in rows:
+            k = re.sub(r'\(.*', '', name).replace('void ', '').replace('dsr::', '')
+            if float(us) < 0:
+                k = '[side stream] ' + k
+            agg[k] = agg.get(k, 0.0) + abs(float(us)); cnt[k] += 1
+        print(f'--- in-graph timeline, {len(rows)} stamped launches, sum {sum(agg.values()):.1f} us')
+        for k, v in sorted(agg.items(), key=lambda kv: -kv[1]):
+            print(f'{v:9.1f} us  n={cnt[k]:3d}  mean {v / cnt[k]:6.2f}  {k}')
+        if os.environ.get('DSR_TIMELINE_ORDER'):
+            for i, us, g, name in rows:
+                print(f'{int(i):4d} {float(us):7.2f} {g:>6s}  ' + re.sub(r'\(.*', '', name).replace('void ', '').replace('dsr::', ''))
     del net, plan, tables
