@@ -53,9 +53,9 @@ def peaks():
 
 def ncu_traffic():
     """DRAM bytes (read + write) of the dominant kernel's largest launch (L0 decoder 3x3 fprop) from the committed
-    `ncu --set full` capture, profiles/r01_halo2_full_raw_v2.csv; None if the file is missing."""
+    `ncu --set full` capture, profiles/r01_halo2_full_raw_v3.csv; None if the file is missing."""
     import csv
-    path = os.path.join(ROOT, 'profiles', 'r01_halo2_full_raw_v2.csv')
+    path = os.path.join(ROOT, 'profiles', 'r01_halo2_full_raw_v3.csv')
     try:
         rows = list(csv.reader(open(path)))
         hdr, units, row = rows[0], rows[1], rows[2]
@@ -281,7 +281,7 @@ def run_ours(args, rank, local_rank, world):
                 'achieved': a['tflops'], 'peak': pk['tflops'], 'unit': 'TFLOP/s',
                 'frac': a['tflops'] / pk['tflops'] if pk['tflops'] else None, 'traffic': ncu_traffic(),
                 'traffic_note': 'DRAM read+write bytes of the largest launch (L0 decoder 3x3 fprop, 79.7 GFLOP, '
-                                'algorithmic 76.1 MB in + 67.1 MB out) from profiles/r01_halo2_full_raw_v2.csv',
+                                'algorithmic 76.1 MB in + 67.1 MB out) from profiles/r01_halo2_full_raw_v3.csv',
                 'peak_source': pk['src'],
                 'kernel_ms_per_step': a['ms_per_step'], 'launches_per_step': a['launches_per_step'],
                 'gflop_per_step': a['gflop_per_step'], 'largest_launch': top, 'wgrad_halo_kernel': res['wgrad_halo_kernel'],
