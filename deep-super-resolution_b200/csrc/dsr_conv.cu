@@ -584,14 +584,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHalo2Threads, 1)
   uint8_t* a_wide = bres_n + ((p.ntaps * p.n_narrow * nb + 1023) & ~1023);
   uint8_t* a_narrow = a_wide + p.wide_slots * slot_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(a_narrow + (p.n_narrow ? 2 * kHaloNarrowSlot : 0));
-  uint64_t* wfull = bars;                 // [3]  (CTA 0's copy is the live one)
-  uint64_t* wempty = bars + 3;            // [3]  (each CTA waits on its own copy; multicast commit)
-  uint64_t* nfull = bars + 6;             // [2]
-  uint64_t* nempty = bars + 8;            // [2]
-  uint64_t* tfull = bars + 10;            // [2]  (multicast commit)
-  uint64_t* tempty = bars + 14;           // [2]  (CTA 0's copy: 8 arrivals = 4 epilogue warps x 2 CTAs)
-  uint64_t* bres_bar = bars + 18;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
+  uint64_t* wfull = bars;                 // [8]  (CTA 0's copy is the live one); wide_slots <= 8 are used
+  uint64_t* wempty = bars + 8;            // [8]  (each CTA waits on its own copy; multicast commit)
+  uint64_t* nfull = bars + 16;            // [2]
+  uint64_t* nempty = bars + 18;           // [2]
+  uint64_t* tfull = bars + 20;            // [2]  (multicast commit)
+  uint64_t* tempty = bars + 24;           // [2]  (CTA 0's copy: 8 arrivals = 4 epilogue warps x 2 CTAs)
+  uint64_t* bres_bar = bars + 28;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 29);
   float* sbias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // EP 1: [N] bias (<= 128 floats)
 
   const int warp = threadIdx.x >> 5;
@@ -611,7 +611,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHalo2Threads, 1)
     tma_prefetch_desc(&p.a64);
     tma_prefetch_desc(&p.b64);
     if (p.n_narrow) { tma_prefetch_desc(&p.a16); tma_prefetch_desc(&p.b16); }
-    for (int i = 0; i < 3; ++i) { mbar_init(&wfull[i], 1); mbar_init(&wempty[i], 1); }
+    for (int i = 0; i < 8; ++i) { mbar_init(&wfull[i], 1); mbar_init(&wempty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&nfull[i], 1); mbar_init(&nempty[i], 1); }
     for (int i = 0; i < kAcc; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 16); }   // 8 epilogue warps x 2 CTAs
     mbar_init(bres_bar, 1);

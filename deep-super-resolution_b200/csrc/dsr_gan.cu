@@ -275,7 +275,10 @@ int gen_make_conv(dsr_gen_plan* p, HaloParams& h, const GenTall& in, const __hal
   h.halo_w = kHaloTW + (k - 1);
   h.halo_h = kHaloTH + (k - 1);
   h.wide_slot_bytes = static_cast<int>(up1k(static_cast<size_t>(h.halo_w) * h.halo_h * 128));
-  h.wide_slots = (k == 3) ? 3 : 2;
+  // one 64-channel chunk per tile: the A ring depth is the number of TILES in flight -- deep enough to cover the TMA
+  // latency at ~0.7 us of MMA work per tile (DSR_GEN_SLOTS for A/B)
+  h.wide_slots = (k == 3) ? (N <= 64 ? 6 : 4) : 2;
+  if (k == 3 && getenv("DSR_GEN_SLOTS")) h.wide_slots = atoi(getenv("DSR_GEN_SLOTS"));
   if ((rc = make_act_map(&h.a64, in.ptr, 1, kGF, in.W, in.rows, 1, 64, h.halo_w, h.halo_h))) return rc;
   h.a16 = h.a64;
   if ((rc = make_wgt_map(&h.b64, wts, kGF, h.ntaps * N, 64, h.n_part))) return rc;

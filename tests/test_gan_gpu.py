@@ -105,3 +105,22 @@ def test_generator_weights_reload_and_chunking(golden):
     g.load_state_dict(sd)
     y2 = g(x)
     assert float((y2 - y1).abs().mean()) > 1e-2
+
+
+def test_generator_config4_patch_size_matches_oracle():
+    """BASELINE configs[3] geometry (96 x 96 LR patches, x8 -> 768 x 768), three images, against the CPU oracle."""
+    import dsr_b200
+    torch.manual_seed(21)
+    g = dsr_b200.Generator(8)
+    sd = g.state_dict()
+    go.perturb_trained_state(sd, 4)
+    g.load_state_dict(sd)
+    x = torch.rand(3, 3, 96, 96, generator=torch.Generator().manual_seed(8))
+    want = go.generator_forward({k: v.clone() for k, v in g.state_dict().items()}, x, 8)
+    got = g.cuda().eval()(x.cuda()).cpu()
+    assert got.shape == (3, 3, 768, 768)
+    assert rel_l2(got, want) <= REL_L2_TOL
+    # images of a batch are independent: permuting the batch permutes the outputs (tall-grid gaps hold)
+    perm = torch.tensor([2, 0, 1])
+    got_p = g(x[perm].cuda()).cpu()
+    assert rel_l2(got_p, got[perm]) <= 1e-6
