@@ -156,3 +156,60 @@ def test_drop_in_module_names_resolve_to_this_package():
     assert importlib.import_module('utils.downsampler').Downsampler is dsr_b200.Downsampler
     m = importlib.import_module('utils.DIP')
     assert m.optimize is dsr_b200.optimize and m.get_noise is dsr_b200.get_noise and m.get_params is dsr_b200.get_params
+
+
+# ---- SRResNet generator (dsr_gen_*): host-side checks, no GPU work ------------------------------------------
+@pytest.mark.parametrize('name', ['gan_f8_1x17x23.pt', 'gan_f16_1x16x16.pt'])
+def test_generator_plan_layout_and_same_seed_init(golden, name):
+    """The C plan's flat state layout lists the reference module's float state_dict entries in order, and
+    dsr_b200.Generator reproduces the reference's same-seed initialisation (checksums recorded from the reference)."""
+    import ctypes as C
+    import torch
+    import dsr_b200
+    from dsr_b200._lib import lib, check
+    from oracle import gan_oracle as go
+    fx = golden(name)
+    torch.manual_seed(fx['seed'])
+    g = dsr_b200.Generator(fx['factor'])
+    sd = g.state_dict()
+    assert list(sd.keys()) == fx['keys']
+    go.perturb_trained_state(sd, fx['perturb_seed'])
+    for k, v in sd.items():
+        t = v.detach().double().flatten()
+        assert (float(t.sum()), float(t.abs().sum())) == pytest.approx(fx['checksums'][k], rel=1e-12, abs=1e-12), k
+    plan = C.c_void_p()
+    check(lib.dsr_gen_plan_create(C.byref(plan), fx['factor'], 16, 2, 24, 32))
+    try:
+        names, total = [], 0
+        buf = C.create_string_buffer(128)
+        off, n = C.c_longlong(), C.c_longlong()
+        for i in range(lib.dsr_gen_num_tensors(plan)):
+            check(lib.dsr_gen_tensor_info(plan, i, buf, 128, C.byref(off), C.byref(n)))
+            assert off.value == total
+            names.append(buf.value.decode())
+            assert sd[names[-1]].numel() == n.value
+            total += n.value
+        assert names == [k for k in fx['keys'] if not k.endswith('num_batches_tracked')]
+        assert lib.dsr_gen_state_numel(plan) == total
+        assert lib.dsr_gen_workspace_bytes(plan) > 0
+    finally:
+        lib.dsr_gen_plan_destroy(plan)
+
+
+def test_generator_unsupported_configurations():
+    import ctypes as C
+    import torch
+    import dsr_b200
+    from dsr_b200._lib import lib
+    plan = C.c_void_p()
+    assert lib.dsr_gen_plan_create(C.byref(plan), 4, 16, 1, 24, 24) == -5      # the reference builds x8 / x16 only
+    assert lib.dsr_gen_plan_create(C.byref(plan), 8, 16, 0, 24, 24) == -1
+    with pytest.raises(NotImplementedError):
+        dsr_b200.Generator(2)
+    g = dsr_b200.Generator(8)
+    with pytest.raises(NotImplementedError):
+        g(torch.rand(1, 3, 16, 16))                       # training mode is not built
+    with pytest.raises(RuntimeError):
+        g.eval()(torch.rand(1, 3, 16, 16))                # CPU tensor: no fallback
+    from models.GAN.generator import Generator as DropIn   # drop-in module name (eval_GAN.py:11)
+    assert DropIn is dsr_b200.Generator
