@@ -81,6 +81,7 @@ class Generator(nn.Module):
     """``Generator(factor=8, residual_blocks_count=16)`` of generator.py:44-66."""
 
     max_chunk = 32        # images per library call (bounds the workspace: ~105 MB per 96 x 96 image at x8)
+    max_plans = 4         # plans (one per batch / image size, each with its workspace) kept alive; least recently used go
 
     def __init__(self, factor: int = 8, residual_blocks_count: int = 16):
         super().__init__()
@@ -104,9 +105,12 @@ class Generator(nn.Module):
 
     def _plan_for(self, batch: int, h: int, w: int, device: torch.device) -> _GenPlan:
         key = (batch, h, w, device.index if device.index is not None else torch.cuda.current_device())
-        plan = self._plans.get(key)
+        plan = self._plans.pop(key, None)
         if plan is None:
-            plan = self._plans[key] = _GenPlan(self.factor, self.blocks, batch, h, w, device)
+            while len(self._plans) >= self.max_plans:          # eval_GAN.py feeds images of many different sizes
+                self._plans.pop(next(iter(self._plans)))
+            plan = _GenPlan(self.factor, self.blocks, batch, h, w, device)
+        self._plans[key] = plan                                # most recently used last
         skey = self._state_key()
         if plan.loaded_key != skey:
             sd = self.state_dict()

@@ -124,3 +124,19 @@ def test_generator_config4_patch_size_matches_oracle():
     perm = torch.tensor([2, 0, 1])
     got_p = g(x[perm].cuda()).cpu()
     assert rel_l2(got_p, got[perm]) <= 1e-6
+
+
+def test_generator_plan_cache_is_bounded():
+    """eval_GAN.py feeds images of many sizes: plans (and their workspaces) beyond max_plans are dropped, LRU first."""
+    import dsr_b200
+    g = dsr_b200.Generator(8).cuda().eval()
+    g.max_plans = 2
+    outs = {}
+    for hw in [(16, 16), (16, 24), (24, 16), (16, 16)]:
+        x = torch.rand(1, 3, *hw, generator=torch.Generator().manual_seed(hw[0] * 100 + hw[1])).cuda()
+        y = g(x)
+        assert y.shape == (1, 3, 8 * hw[0], 8 * hw[1]) and torch.isfinite(y).all()
+        if hw in outs:
+            assert rel_l2(y.cpu(), outs[hw]) <= 1e-6       # a re-created plan gives the same image
+        outs[hw] = y.cpu()
+        assert len(g._plans) <= 2
