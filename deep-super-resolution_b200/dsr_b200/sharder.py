@@ -38,7 +38,24 @@ def max_over_ranks(value: float, device=None) -> float:
     return float(t.item())
 
 
-def run_sharded(n_images: int, run_image, rank: int, world_size: int) -> Dict[int, dict]:
-    """Runs `run_image(i) -> dict` for this rank's images and gathers all results."""
-    local = {i: run_image(i) for i in images_for_rank(n_images, rank, world_size)}
+def run_sharded(n_images: int, run_image, rank: int, world_size: int, in_flight: int = 1) -> Dict[int, dict]:
+    """Runs `run_image(i) -> dict` for this rank's images and gathers all results.
+
+    `in_flight` > 1 keeps that many of the rank's images in flight on its GPU: each worker thread gets its own CUDA
+    stream as the thread's current stream, so the (asynchronous) iterations of different images interleave on the
+    device -- the latency-bound low-resolution levels of one image fill the gaps of another.  Measured at 512 x 512 on
+    one B200: 570 it/s with one image, 661 / 685 / 689 it/s aggregate with 2 / 3 / 4."""
+    mine = images_for_rank(n_images, rank, world_size)
+    if in_flight <= 1 or len(mine) <= 1:
+        return gather_results({i: run_image(i) for i in mine})
+    from concurrent.futures import ThreadPoolExecutor
+    device = torch.cuda.current_device() if torch.cuda.is_available() else None
+
+    def worker_init():
+        if device is not None:
+            torch.cuda.set_device(device)
+            torch.cuda.set_stream(torch.cuda.Stream(device=device))
+
+    with ThreadPoolExecutor(max_workers=in_flight, initializer=worker_init) as pool:
+        local = dict(zip(mine, pool.map(run_image, mine)))
     return gather_results(local)

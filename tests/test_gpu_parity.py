@@ -379,3 +379,41 @@ def test_dip_isr_driver_and_drop_in_module_names():
     assert len(metrics['psnrs']) == 3 and metrics['ssims'] == [] and metrics['lpipss'] == []
     assert metrics['psnrs'][-1] > metrics['psnrs'][0]                            # the fit improves
     assert next(net.parameters()).device.type == 'cpu'                           # DIP.py:109 moves the net back
+
+
+@pytest.mark.gpu
+def test_images_in_flight_on_one_gpu():
+    """BASELINE configs[2] scheduling: two independent images optimised concurrently on one GPU (worker threads,
+    one stream each) follow the same loss trajectories as when they run one after the other."""
+    import dsr_b200
+    from dsr_b200 import sharder
+    from oracle import dip_oracle as O
+    cfg = {'learning_rate': 0.01, 'num_iter': 12, 'reg_noise_std': 0.05}
+
+    def make(i):                        # torch's global RNG is shared by threads: build nets / inputs up front
+        lr_img, _hr = O.synthetic_pair(i, 64)
+        torch.manual_seed(i)
+        net = dsr_b200.get_net(32, 'skip', 'reflection', skip_n33d=128, skip_n33u=128, skip_n11=4, num_scales=5,
+                               upsample_mode='bilinear')
+        return net, lr_img, dsr_b200.get_noise(32, 'noise', (64, 64))
+
+    jobs = {}
+
+    def run_image(i):
+        net, lr_img, z = jobs[i]
+        out, losses = dsr_b200.dip_sr_fused(net, lr_img, (64, 64), 4, cfg, 'cuda:0', seed=100 + i, net_input=z)
+        torch.cuda.current_stream().synchronize()
+        return {'losses': losses.cpu(), 'out': out.cpu()}
+
+    jobs = {i: make(i) for i in range(3)}
+    seq = sharder.run_sharded(3, run_image, 0, 1)
+    jobs = {i: make(i) for i in range(3)}
+    par = sharder.run_sharded(3, run_image, 0, 1, in_flight=3)
+    for i in range(3):
+        a, b = seq[i]['losses'], par[i]['losses']
+        assert torch.isfinite(b).all()
+        # the first iteration is the same computation; later ones drift apart like any two runs of this chaotic
+        # early optimisation do (fp32 atomics commute differently, DESIGN.md section 5) and meet again as it settles
+        assert abs(float(a[0]) - float(b[0])) <= 2e-3 * float(a[0])
+        assert abs(float(a[-1]) - float(b[-1])) <= 0.15 * float(a[-1])
+        assert float(b[-1]) < float(b[0])

@@ -54,3 +54,23 @@ def test_partition_is_exact():
             parts = [sharder.images_for_rank(n, r, w) for r in range(w)]
             assert sorted(i for p in parts for i in p) == list(range(n))
             assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+
+
+def test_run_sharded_in_flight_matches_sequential():
+    """in_flight > 1 runs the rank's images on worker threads (each with its own current stream on a GPU box); the
+    gathered results are those of the sequential loop."""
+    import sys
+    import threading
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, 'deep-super-resolution_b200'))
+    from dsr_b200 import sharder
+    seen = set()
+
+    def run_image(i):
+        seen.add(threading.get_ident())
+        return {'index': i, 'value': float(torch.full((4,), float(i)).sum())}
+
+    seq = sharder.run_sharded(9, run_image, rank=1, world_size=2)
+    par = sharder.run_sharded(9, run_image, rank=1, world_size=2, in_flight=3)
+    assert seq == par and sorted(par) == [1, 3, 5, 7]
+    assert len(seen) >= 2
