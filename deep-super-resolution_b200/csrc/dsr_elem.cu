@@ -1110,22 +1110,40 @@ __global__ void __launch_bounds__(kThreads, 3) bn_bwd_top_kernel(TopBwdArgs a) {
     }
   }
   if (!APPLY) {
-    __shared__ float red[256 + 3 * 128 + 3];
-    for (int i = threadIdx.x; i < 256 + 3 * 128 + 3; i += blockDim.x) red[i] = 0.f;
-    __syncthreads();
+    // block sums without shared-memory float atomics (CAS loops, 8-way contended): per-warp partials, then a tree
+    __shared__ float scr[kThreads / 32][20][32];
+    __shared__ float scr_b[kThreads / 32][3];
+    const int w = threadIdx.x >> 5;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      atomicAdd(&red[c0 + j], s1[j]);
-      atomicAdd(&red[128 + c0 + j], rstd_[j] * (s2[j] - mean_[j] * s1[j]));      // sum dy * xhat
+      scr[w][j][lane] = s1[j];
+      scr[w][4 + j][lane] = rstd_[j] * (s2[j] - mean_[j] * s1[j]);               // sum dy * xhat
 #pragma unroll
-      for (int o = 0; o < 3; ++o) atomicAdd(&red[256 + o * 128 + c0 + j], aw[o][j]);
+      for (int o = 0; o < 3; ++o) scr[w][8 + o * 4 + j][lane] = aw[o][j];
     }
 #pragma unroll
-    for (int o = 0; o < 3; ++o) atomicAdd(&red[256 + 384 + o], ab[o]);
+    for (int o = 0; o < 3; ++o) {
+      float v = ab[o];
+#pragma unroll
+      for (int d = 16; d >= 1; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+      if (lane == 0) scr_b[w][o] = v;
+    }
     __syncthreads();
-    atomicAdd(&a.bstats[threadIdx.x], red[threadIdx.x]);
-    for (int i = threadIdx.x; i < 3 * 128; i += blockDim.x) atomicAdd(&a.dw[i], red[256 + i] * invS);
-    if (threadIdx.x < 3) atomicAdd(&a.db[threadIdx.x], red[256 + 384 + threadIdx.x] * invS);
+    for (int idx = threadIdx.x; idx < 20 * 32; idx += blockDim.x) {
+      // idx = q * 128 + c (q: 0 sum dy, 1 sum dy xhat, 2..4 final-conv dW rows), c = 4 l + j -> partials [q * 4 + j][l];
+      // consecutive threads -> consecutive global addresses (coalesced atomics)
+      const int q = idx >> 7, cch = idx & 127, n = q * 4 + (cch & 3), l = cch >> 2;
+      float t = 0.f;
+#pragma unroll
+      for (int ww = 0; ww < kThreads / 32; ++ww) t += scr[ww][n][l];
+      if (q < 2) atomicAdd(&a.bstats[idx], t);
+      else atomicAdd(&a.dw[idx - 256], t * invS);
+    }
+    if (threadIdx.x < 3) {
+      float t = 0.f;
+      for (int ww = 0; ww < kThreads / 32; ++ww) t += scr_b[ww][threadIdx.x];
+      atomicAdd(&a.db[threadIdx.x], t * invS);
+    }
   } else {
     const float amax = fmaxf(__low2float(amax2), __high2float(amax2));
     track_amax(a.gs, isfinite(amax) ? amax : 0.f, !isfinite(amax));
@@ -1425,16 +1443,23 @@ __global__ void __launch_bounds__(kThreads, 3) bn_bwd_fast_kernel(BnBwdArgs a) {
     }
   }
   if (!APPLY) {
-    __shared__ float red[256];
-    red[threadIdx.x] = 0.f;
-    __syncthreads();
+    // Block sums without shared-memory float atomics (those are CAS loops -- ATOMS.CAST.SPIN -- and all 8 warps hit
+    // the same 256 addresses): every warp parks its per-lane partials, then thread (n, l) adds the 8 warps' values.
+    __shared__ float scr[kThreads / 32][8][32];
+    const int w = threadIdx.x >> 5;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      atomicAdd(&red[c0 + j], s1[j]);
-      atomicAdd(&red[128 + c0 + j], rstd_[j] * (s2[j] - mean_[j] * s1[j]));     // sum dy * xhat
+      scr[w][j][lane] = s1[j];
+      scr[w][4 + j][lane] = rstd_[j] * (s2[j] - mean_[j] * s1[j]);              // sum dy * xhat
     }
     __syncthreads();
-    atomicAdd(&a.bstats[threadIdx.x], red[threadIdx.x]);
+    // thread t owns bstats[t] (consecutive addresses per warp: the global atomics stay coalesced):
+    // t = q * 128 + c, channel c = 4 l + j  ->  partials [q * 4 + j][l]
+    const int cch = threadIdx.x & 127, n = (threadIdx.x >> 7) * 4 + (cch & 3), l = cch >> 2;
+    float t = 0.f;
+#pragma unroll
+    for (int ww = 0; ww < kThreads / 32; ++ww) t += scr[ww][n][l];
+    atomicAdd(&a.bstats[threadIdx.x], t);
   } else {
     const float amax = fmaxf(__low2float(amax2), __high2float(amax2));
     track_amax(a.gs, isfinite(amax) ? amax : 0.f, !isfinite(amax));
