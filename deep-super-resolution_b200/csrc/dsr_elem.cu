@@ -109,6 +109,28 @@ __device__ __forceinline__ void track_amax(float* gs, float local_max, bool bad)
   }
 }
 
+// Block sums of per-lane partials WITHOUT shared-memory float atomics (atomicAdd(float) on shared memory is a CAS
+// loop, ATOMS.CAST.SPIN, and here every warp of the block hits the same addresses).  Thread (warp w, lane l) holds
+// NQ groups of 4 values, vals[q][j] belonging to channel 4 l + j of group q; on return red[q * qstride + c] (shared)
+// holds the sum over the block's warps for c < 128.  scr: shared scratch [warps][NQ * 4][32].  Contains barriers.
+template <int NQ>
+__device__ __forceinline__ void block_sum_lane4(const float (&vals)[NQ][4], float* red, int qstride,
+                                                float (*scr)[NQ * 4][32]) {
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int q = 0; q < NQ; ++q)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) scr[w][q * 4 + j][lane] = vals[q][j];
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < NQ * 128; idx += blockDim.x) {
+    const int q = idx >> 7, c = idx & 127, n = q * 4 + (c & 3), l = c >> 2;
+    float t = 0.f;
+    for (int ww = 0; ww < nw; ++ww) t += scr[ww][n][l];
+    red[q * qstride + c] = t;
+  }
+  __syncthreads();
+}
+
 __device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
 #pragma unroll
   for (int r = 0; r < 10; ++r) {
@@ -285,14 +307,19 @@ __global__ void __launch_bounds__(kThreads) input_pack32_kernel(float* __restric
     if (ok && g == 0)
       *reinterpret_cast<float4*>(sraw + (static_cast<long long>(y) * W + x) * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
     __shared__ float red[8];
-    if (threadIdx.x < 8) red[threadIdx.x] = 0.f;
-    __syncthreads();
+    __shared__ float scr8[32][8];                    // per-warp totals: no shared-memory float atomics (CAS loops)
 #pragma unroll
     for (int o = 0; o < 4; ++o) {
       float v = ss[o], u = sq[o];
 #pragma unroll
       for (int d = 16; d >= 4; d >>= 1) { v += __shfl_xor_sync(0xffffffffu, v, d); u += __shfl_xor_sync(0xffffffffu, u, d); }
-      if ((threadIdx.x & 31) == 0) { atomicAdd(&red[o], v); atomicAdd(&red[4 + o], u); }
+      if ((threadIdx.x & 31) == 0) { scr8[threadIdx.x >> 5][o] = v; scr8[threadIdx.x >> 5][4 + o] = u; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+      float t = 0.f;
+      for (int ww = 0; ww < static_cast<int>(blockDim.x >> 5); ++ww) t += scr8[ww][threadIdx.x];
+      red[threadIdx.x] = t;
     }
     __syncthreads();
     if (threadIdx.x < 8) atomicAdd(&skip_stats[threadIdx.x], red[threadIdx.x]);
@@ -439,16 +466,26 @@ __global__ void __launch_bounds__(kThreads) bn_act_kernel(const __half* __restri
     }
   }
   if (SKIP) {
-    __shared__ float red[8];
-    if (threadIdx.x < 8) red[threadIdx.x] = 0.f;
-    __syncthreads();
-    if ((lane & 1) == 0) {
+    // lanes that hold the same output (bits 1, 2 of the lane) meet by shuffle, then one value per warp and output is
+    // parked in shared memory: no shared-memory float atomics (CAS loops, here 32-way contended)
+    __shared__ float scr8[kThreads / 32][8];
+    float v = (lane & 1) == 0 ? ss : 0.f, u = (lane & 1) == 0 ? sq : 0.f;
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    u += __shfl_xor_sync(0xffffffffu, u, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 16);
+    u += __shfl_xor_sync(0xffffffffu, u, 16);
+    if ((lane & 0x19) == 0) {
       const int o = (((lane >> 2) & 1) * 2 + ((lane >> 1) & 1));
-      atomicAdd(&red[o], ss);
-      atomicAdd(&red[4 + o], sq);
+      scr8[threadIdx.x >> 5][o] = v;
+      scr8[threadIdx.x >> 5][4 + o] = u;
     }
     __syncthreads();
-    if (threadIdx.x < 8) atomicAdd(&sf.stats[threadIdx.x], red[threadIdx.x]);
+    if (threadIdx.x < 8) {
+      float t = 0.f;
+#pragma unroll
+      for (int ww = 0; ww < kThreads / 32; ++ww) t += scr8[ww][threadIdx.x];
+      atomicAdd(&sf.stats[threadIdx.x], t);
+    }
   }
 }
 
@@ -1328,19 +1365,20 @@ __global__ void __launch_bounds__(kThreads, HAS_DS ? 2 : 3) bn_bwd_kernel(BnBwdA
     }
   }
   if (!APPLY) {
-    __shared__ float red[HAS_DS ? 256 + 512 : 256];
-    for (int i = threadIdx.x; i < (HAS_DS ? 256 + 512 : 256); i += blockDim.x) red[i] = 0.f;
-    __syncthreads();
+    constexpr int kQ = HAS_DS ? 6 : 2;
+    __shared__ float red[kQ * 128];
+    __shared__ float scr[kThreads / 32][kQ * 4][32];
+    float vals[kQ][4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      atomicAdd(&red[c0 + j], s1[j]);
-      atomicAdd(&red[128 + c0 + j], s2[j]);
+      vals[0][j] = s1[j];
+      vals[1][j] = s2[j];
       if (HAS_DS) {
 #pragma unroll
-        for (int oo = 0; oo < 4; ++oo) atomicAdd(&red[256 + oo * 128 + c0 + j], aw[oo][j]);
+        for (int oo = 0; oo < 4; ++oo) vals[2 + oo][j] = aw[oo][j];
       }
     }
-    __syncthreads();
+    block_sum_lane4<kQ>(vals, red, 128, scr);
     atomicAdd(&a.bstats[threadIdx.x], red[threadIdx.x]);
     if (HAS_DS) {
       const float invS = a.gs[1];
@@ -1740,17 +1778,22 @@ __global__ void skip_bwd_kernel(const float* __restrict__ dsy, const float* __re
     for (int o = 0; o < 4; ++o)
 #pragma unroll
       for (int j = 0; j < 8; ++j) aw[o][j] += __shfl_xor_sync(0xffffffffu, aw[o][j], sh);
-  __shared__ float red[4 * CIN];
-  for (int i = threadIdx.x; i < 4 * CIN; i += blockDim.x) red[i] = 0.f;
-  __syncthreads();
+  // per-warp totals parked in shared memory, added by one thread per weight: no shared-memory float atomics
+  __shared__ float scr[kThreads / 32][32][G];
   if ((threadIdx.x & 31) < G) {
 #pragma unroll
     for (int o = 0; o < 4; ++o)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) atomicAdd(&red[o * CIN + g * 8 + j], aw[o][j]);
+      for (int j = 0; j < 8; ++j) scr[threadIdx.x >> 5][o * 8 + j][g] = aw[o][j];
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 4 * CIN; i += blockDim.x) atomicAdd(&dw[i], red[i] * invS);
+  for (int i = threadIdx.x; i < 4 * CIN; i += blockDim.x) {
+    const int o = i / CIN, c = i - o * CIN;
+    float t = 0.f;
+#pragma unroll
+    for (int ww = 0; ww < kThreads / 32; ++ww) t += scr[ww][o * 8 + (c & 7)][c >> 3];
+    atomicAdd(&dw[i], t * invS);
+  }
   if (blockIdx.x == 0 && threadIdx.x < 4) {
     dbeta[threadIdx.x] = sbstats[threadIdx.x] * invS;
     dgamma[threadIdx.x] = sbstats[4 + threadIdx.x] * invS;
@@ -1861,14 +1904,11 @@ __device__ __forceinline__ void upcat_stats_lowres_body(const UpcatArgs& a, int 
     }
   }
   __shared__ float red[256];
-  red[threadIdx.x] = 0.f;
-  __syncthreads();
+  __shared__ float scr[kThreads / 32][8][32];
+  float vals[2][4];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    atomicAdd(&red[lane * 4 + j], s[j]);
-    atomicAdd(&red[128 + lane * 4 + j], q[j]);
-  }
-  __syncthreads();
+  for (int j = 0; j < 4; ++j) { vals[0][j] = s[j]; vals[1][j] = q[j]; }
+  block_sum_lane4<2>(vals, red, 128, scr);
   if (threadIdx.x < 128) atomicAdd(&a.cat_stats[threadIdx.x], red[threadIdx.x]);
   else atomicAdd(&a.cat_stats[144 + threadIdx.x - 128], red[threadIdx.x]);
 }
@@ -1887,14 +1927,19 @@ __device__ __forceinline__ void skipcat_stats_body(const UpcatArgs& a, int vbloc
     for (int o = 0; o < 4; ++o) { s4[o] += sv[o]; q4[o] = fmaf(sv[o], sv[o], q4[o]); }
   }
   __shared__ float red[8];
-  if (threadIdx.x < 8) red[threadIdx.x] = 0.f;
-  __syncthreads();
+  __shared__ float scr8[32][8];                    // per-warp totals: no shared-memory float atomics (CAS loops)
 #pragma unroll
   for (int o = 0; o < 4; ++o) {
     float v = s4[o], u = q4[o];
 #pragma unroll
     for (int dd = 16; dd >= 1; dd >>= 1) { v += __shfl_xor_sync(0xffffffffu, v, dd); u += __shfl_xor_sync(0xffffffffu, u, dd); }
-    if ((threadIdx.x & 31) == 0) { atomicAdd(&red[o], v); atomicAdd(&red[4 + o], u); }
+    if ((threadIdx.x & 31) == 0) { scr8[threadIdx.x >> 5][o] = v; scr8[threadIdx.x >> 5][4 + o] = u; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float t = 0.f;
+    for (int ww = 0; ww < static_cast<int>(blockDim.x >> 5); ++ww) t += scr8[ww][threadIdx.x];
+    red[threadIdx.x] = t;
   }
   __syncthreads();
   if (threadIdx.x < 4) atomicAdd(&a.cat_stats[128 + threadIdx.x], red[threadIdx.x]);
@@ -2096,10 +2141,28 @@ __device__ __forceinline__ void upT_gather_tile_body(const UpcatBwdArgs& a, uint
     }
   }
   __syncthreads();
+  {
+    // channel sums without shared-memory float atomics (16 threads of the block share every address): the two lanes
+    // of a warp that hold the same 8 channels meet by shuffle, then the 8 warps' values are added by one thread each
+    float (*scr)[16][16] = reinterpret_cast<float (*)[16][16]>(smem_raw);   // the staging buffer is free now (8 KB used)
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    atomicAdd(&red[c0 + j], s1[j]);
-    atomicAdd(&red[128 + c0 + j], s2[j]);
+    for (int j = 0; j < 8; ++j) {
+      const float v1 = s1[j] + __shfl_xor_sync(0xffffffffu, s1[j], 16);
+      const float v2 = s2[j] + __shfl_xor_sync(0xffffffffu, s2[j], 16);
+      if (lane < 16) {
+        scr[w][j][g] = v1;
+        scr[w][8 + j][g] = v2;
+      }
+    }
+    __syncthreads();
+    {
+      const int q = threadIdx.x >> 7, c = threadIdx.x & 127, n = q * 8 + (c & 7), gg = c >> 3;
+      float t = 0.f;
+#pragma unroll
+      for (int ww = 0; ww < kThreads / 32; ++ww) t += scr[ww][n][gg];
+      red[threadIdx.x] = t;                       // red[0..255]: zero until here, nobody else writes these entries
+    }
   }
   if (threadIdx.x < 4 * kGtW * kGtH) {
 #pragma unroll
@@ -2150,14 +2213,19 @@ __device__ __forceinline__ void skipcat_bwd_body(const UpcatBwdArgs& a, int vblo
     if (APPLY) *reinterpret_cast<float4*>(a.dsy + pix * 4) = make_float4(dsy[0], dsy[1], dsy[2], dsy[3]);
   }
   __shared__ float red[8];
-  if (threadIdx.x < 8) red[threadIdx.x] = 0.f;
-  __syncthreads();
+  __shared__ float scr8[32][8];                    // per-warp totals: no shared-memory float atomics (CAS loops)
 #pragma unroll
   for (int o = 0; o < 4; ++o) {
     float v = t1[o], u = t2[o];
 #pragma unroll
     for (int dd = 16; dd >= 1; dd >>= 1) { v += __shfl_xor_sync(0xffffffffu, v, dd); u += __shfl_xor_sync(0xffffffffu, u, dd); }
-    if ((threadIdx.x & 31) == 0) { atomicAdd(&red[o], v); atomicAdd(&red[4 + o], u); }
+    if ((threadIdx.x & 31) == 0) { scr8[threadIdx.x >> 5][o] = v; scr8[threadIdx.x >> 5][4 + o] = u; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float t = 0.f;
+    for (int ww = 0; ww < static_cast<int>(blockDim.x >> 5); ++ww) t += scr8[ww][threadIdx.x];
+    red[threadIdx.x] = t;
   }
   __syncthreads();
   if (!APPLY) {
