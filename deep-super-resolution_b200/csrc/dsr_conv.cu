@@ -1402,8 +1402,9 @@ int make_wgt_map(CUtensorMap* m, const void* base, int K, int rows, int box_k, i
   return r == CUDA_SUCCESS ? 0 : -(300 + static_cast<int>(r));
 }
 
-static bool g_attr_done = false;
 static int set_attrs() {
+  static bool done_dev[kMaxDevices] = {};
+  bool& g_attr_done = done_dev[device_slot()];
   if (g_attr_done) return 0;
   cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmemBytes);
   if (e != cudaSuccess) return static_cast<int>(e);
@@ -1430,7 +1431,8 @@ int halo_smem_bytes(int n_part, int n_wide, int n_narrow, int wide_slots, int nt
 }
 
 int launch_conv_halo(const HaloParams& p, int num_sms, cudaStream_t stream) {
-  static int configured = 0;
+  static int configured_dev[kMaxDevices] = {};
+  int& configured = configured_dev[device_slot()];
   if (p.smem_bytes > configured) {
     cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem_bytes);
     if (e != cudaSuccess) return static_cast<int>(e);
@@ -1455,7 +1457,8 @@ int launch_conv_halo(const HaloParams& p, int num_sms, cudaStream_t stream) {
       clusters = npairs;
     }
     if (p.ep_mode == 3) {                 // generator output conv: its own tile geometry (tiles_x/y count 24 x 8 tiles)
-      static bool c9_done = false;
+      static bool c9_done_dev[kMaxDevices] = {};
+      bool& c9_done = c9_done_dev[device_slot()];
       if (!c9_done) {
         cudaError_t e = cudaFuncSetAttribute(conv9_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kC9Smem);
         if (e != cudaSuccess) return static_cast<int>(e);
@@ -1476,7 +1479,8 @@ int launch_conv_halo(const HaloParams& p, int num_sms, cudaStream_t stream) {
 }
 
 int launch_wgrad_halo(const WgHaloParams& p, cudaStream_t stream) {
-  static bool done = false;
+  static bool done_dev[kMaxDevices] = {};
+  bool& done = done_dev[device_slot()];
   if (!done) {
     cudaError_t e = cudaFuncSetAttribute(wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgHSmemBytes);
     if (e != cudaSuccess) return static_cast<int>(e);

@@ -123,7 +123,10 @@ static int ds_launch(const float* x, const float* target, float* y, float* gy, f
                      int oh, int ow, DsTables t, cudaStream_t s, const float* state = nullptr) {
   const size_t smem = ds_smem(t);
   if (smem > 200 * 1024) return -4;
-  static size_t configured = 0;
+  static size_t configured_dev[64] = {};            // function attributes are per device
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+  size_t& configured = configured_dev[dev];
   if (smem > 48 * 1024 && smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(downsample_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem));

@@ -520,7 +520,8 @@ int dsr_gen_forward(dsr_gen_plan_t* p, const float* x, float* y, void* stream) {
   if (p == nullptr || x == nullptr || y == nullptr) return -1;
   if (!p->bound || !p->loaded) return -6;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  static bool attr_done = false;
+  static bool attr_done_dev[kMaxDevices] = {};
+  bool& attr_done = attr_done_dev[device_slot()];
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(gen_conv1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kC1Smem);
     if (e != cudaSuccess) return static_cast<int>(e);

@@ -12,6 +12,15 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+// Function attributes (opt-in shared memory) are per device: "configured once" flags are kept per device ordinal so
+// that one process can use the library on several GPUs.
+constexpr int kMaxDevices = 64;
+inline int device_slot() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = 0;
+  return dev;
+}
+
 int ensure_driver_api();
 int make_act_map(CUtensorMap* m, const void* base, int elem_is_16bit, int C, int Wp, int Hp, int step, int box_c,
                  int box_w, int box_h);
