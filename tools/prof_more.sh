@@ -1,3 +1,10 @@
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:wgrad_halo -s 23 -c 1 -o gpurun_out/v4_wgrad_l1u1 -f python tools/one_iter.py 512 2 > gpurun_out/p9.log 2>&1
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:conv_gemm -s 9 -c 1 -o gpurun_out/v4_gemm_l0d1 -f python tools/one_iter.py 512 2 > gpurun_out/p10.log 2>&1
-timeout 300 ncu --set full --clock-control none --import-source on -k "regex:bn_bwd_fast_kernel<true>|bn_bwd_fast_kernelILb1" -s 15 -c 1 -o gpurun_out/v4_bnbwd_apply -f python tools/one_iter.py 512 2 > gpurun_out/p11.log 2>&1
+#!/bin/bash
+# ncu --set full captures of the L0 instances of the element-wise kernels (second iteration of tools/one_iter.py)
+cap() {  # name regex skip
+  timeout 300 ncu --set full --clock-control none --import-source on -k "regex:$2" -s $3 -c 1 -o gpurun_out/v5_$1 -f python tools/one_iter.py 512 2 > gpurun_out/p_$1.log 2>&1
+}
+cap upcat_apply upcat_apply_kernel 9
+cap upcat_bwd_c upcat_bwd_c_kernel 5
+cap upcat_stats upcat_stats_merged 9
+cap bn_act "bn_act_kernel" 38
+cap input_pack input_pack32 1
