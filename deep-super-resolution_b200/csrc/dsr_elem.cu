@@ -1861,25 +1861,37 @@ __device__ __forceinline__ void q_stencil(const __half* d, long long sy, int h, 
                                           const float (&Qx)[3], int lane, float (&qd)[4], float (&center)[4]) {
 #pragma unroll
   for (int j = 0; j < 4; ++j) qd[j] = 0.f;
+  // Branch-free: neighbours outside the tensor are clamped onto the border pixel and get weight 0 (the Q weight
+  // vanishes there anyway), so all nine loads are issued back to back before the first one is consumed.
+  uint2 v[3][3];
+  float wq[3][3];
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
     const int y = qy - 1 + a;
-    if (y < 0 || y >= h) continue;            // the corresponding Q weight is 0 there as well
+    const bool oky = (y >= 0 && y < h);
+    const int yc = min(max(y, 0), h - 1);
 #pragma unroll
     for (int b = 0; b < 3; ++b) {
       const int x = qx - 1 + b;
-      if (x < 0 || x >= w) continue;
-      float f[4];
-      cvt4h(ldg8(d + y * sy + static_cast<long long>(x) * 128 + lane * 4), f);
-      const float ww = Qy[a] * Qx[b];
+      const bool okx = (x >= 0 && x < w);
+      const int xc = min(max(x, 0), w - 1);
+      v[a][b] = ldg8(d + yc * sy + static_cast<long long>(xc) * 128 + lane * 4);
+      wq[a][b] = (oky && okx) ? Qy[a] * Qx[b] : 0.f;
+    }
+  }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) qd[j] = fmaf(ww, f[j], qd[j]);
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      float f[4];
+      cvt4h(v[a][b], f);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) qd[j] = fmaf(wq[a][b], f[j], qd[j]);
       if (a == 1 && b == 1) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) center[j] = f[j];
       }
     }
-  }
 }
 
 __device__ __forceinline__ void upcat_stats_lowres_body(const UpcatArgs& a, int vblock, int vgrid) {
