@@ -421,8 +421,9 @@ def run_e2e(args, rank, world, dev, net, ds, lr_img, z_saved, barrier):
             host_lr.copy_(out_lr.detach(), non_blocking=True)
             host_loss.copy_(loss.detach(), non_blocking=True)
         loss.backward()
+        # the host blocks until this step's results have ARRIVED in host memory, as the reference's .cpu() calls do
+        # (DIP.py:90-91); like the reference it does not wait for the backward pass, which the next step queues behind
         d2h_stream.synchronize()
-        torch.cuda.current_stream().synchronize()                          # the reference's .cpu() blocks here
         state['i'] += 1
         return loss
 
@@ -451,7 +452,8 @@ def run_e2e(args, rank, world, dev, net, ds, lr_img, z_saved, barrier):
     return {'value': world * args.steps / (ms * 1e-3), 'unit': 'it/s', 'h2d_bytes_per_step': h2d,
             'd2h_bytes_per_step': d2h, 'ms_per_step': ms / args.steps,
             'path': 'get_net/Downsampler/get_params/optimize + DIP.py-style closure; z from pinned host memory, '
-                    'out_HR/out_LR/loss read back each step (D2H on a side stream during the backward pass)'}
+                    'out_HR/out_LR/loss read back each step (D2H on a side stream during the backward pass; the host blocks '
+                    'on their arrival every step)'}
 
 
 # -------------------------------------------------------------------------------------------------
