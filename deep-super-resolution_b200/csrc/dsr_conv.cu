@@ -235,8 +235,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
 #pragma unroll
       for (int c = 0; c < 9; ++c) {
         if (c < nchunks) {
-          atomicAdd(&p.stats[c * 16 + col], acc_s[c]);
-          atomicAdd(&p.stats[p.n_mma + c * 16 + col], acc_q[c]);
+          acc_add_f(&p.stats[c * 16 + col], acc_s[c]);
+          acc_add_f(&p.stats[p.n_mma + c * 16 + col], acc_q[c]);
         }
       }
     }
@@ -502,8 +502,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         if (c < nchunks) {
-          atomicAdd(&p.stats[col0 + c * 16 + col], acc_s[c]);
-          atomicAdd(&p.stats[p.stats_stride + col0 + c * 16 + col], acc_q[c]);
+          acc_add_f(&p.stats[col0 + c * 16 + col], acc_s[c]);
+          acc_add_f(&p.stats[p.stats_stride + col0 + c * 16 + col], acc_q[c]);
         }
       }
     }
@@ -857,8 +857,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHalo2Threads, 1)
       for (int i = 0; i < 5; ++i) {
         const int c = c_begin + i;
         if (c < c_end) {
-          atomicAdd(&p.stats[ch0 + c * 16 + col], acc_s[i]);
-          atomicAdd(&p.stats[p.stats_stride + ch0 + c * 16 + col], acc_q[i]);
+          acc_add_f(&p.stats[ch0 + c * 16 + col], acc_s[i]);
+          acc_add_f(&p.stats[p.stats_stride + ch0 + c * 16 + col], acc_q[i]);
         }
       }
     }
@@ -1068,6 +1068,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kC9Threads, 1)
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
+// split-K epilogue: fp32 atomics into the gradient (default), or -- deterministic mode -- a plain store into this
+// split's private partial, summed in split order by wgrad_reduce_kernel
+__device__ __forceinline__ void wg_emit_v4(float* addr, bool plain, float a, float b, float c, float d) {
+  if (plain) *reinterpret_cast<float4*>(addr) = make_float4(a, b, c, d);
+  else red_add_v4(addr, a, b, c, d);
+}
+
+// dw[i] = sum over splits (in split order) of part[s * stride + i]: the fixed-order second stage of the split-K
+__global__ void wgrad_reduce_kernel(const float* __restrict__ part, long long stride, int nsplit, float* __restrict__ dw,
+                                    long long n4) {
+  pdl_sync();
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int sp = 0; sp < nsplit; ++sp) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(part + sp * stride) + i);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    reinterpret_cast<float4*>(dw)[i] = acc;
+  }
+}
 
 __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_constant__ WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -1182,7 +1203,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
     tc_fence_after();
     for (int t = 0; t < p.ntaps; ++t) {
       const int w_tap = p.taps[group][t].w_tap;
-      float* drow = p.dw + (static_cast<long long>(w_tap) * 128 + co) * p.ldw;
+      float* drow = (p.part ? p.part + split * p.part_stride : p.dw) + (static_cast<long long>(w_tap) * 128 + co) * p.ldw;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(t * kWgTapCols);
       for (int c = 0; c * 16 < ncols; ++c) {
         uint32_t v[16];
@@ -1190,7 +1211,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-          red_add_v4(drow + c * 16 + i * 4, __uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+          wg_emit_v4(drow + c * 16 + i * 4, p.part != nullptr, __uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
                      __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
       }
     }
@@ -1326,14 +1347,14 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_halo_kernel(const __grid_
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     for (int j = 0; j < p.ncolchunks; ++j) {
       const WgCol cc = p.cols[group][j];
-      float* drow = p.dw + (static_cast<long long>(cc.w_tap) * 128 + co) * p.ldw + cc.ci0;
+      float* drow = (p.part ? p.part + split * p.part_stride : p.dw) + (static_cast<long long>(cc.w_tap) * 128 + co) * p.ldw + cc.ci0;
       uint32_t v[16];
       tmem_ld16(taddr + static_cast<uint32_t>(j * 16), v);
       tmem_ld_wait();
 #pragma unroll
       for (int i = 0; i < 4; ++i)
-        red_add_v4(drow + i * 4, __uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
-                   __uint_as_float(v[4 * i + 3]));
+        wg_emit_v4(drow + i * 4, p.part != nullptr, __uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                   __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
     }
   }
 
@@ -1478,6 +1499,13 @@ int launch_conv_halo(const HaloParams& p, int num_sms, cudaStream_t stream) {
   return static_cast<int>(cudaGetLastError());
 }
 
+static void launch_wgrad_reduce(const float* part, long long stride, int nsplit, float* dw, cudaStream_t stream) {
+  const long long n4 = stride / 4;                  // the layer's packed gradient, whole float4s (stride % 4 == 0)
+  long long blocks = (n4 + 255) / 256;
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  launch_k(wgrad_reduce_kernel, dim3(static_cast<int>(blocks)), dim3(256), 0, stream, part, stride, nsplit, dw, n4);
+}
+
 int launch_wgrad_halo(const WgHaloParams& p, cudaStream_t stream) {
   static bool done_dev[kMaxDevices] = {};
   bool& done = done_dev[device_slot()];
@@ -1489,6 +1517,7 @@ int launch_wgrad_halo(const WgHaloParams& p, cudaStream_t stream) {
   const int grid = p.ngroups * p.nsplit;
   if (grid <= 0) return 0;
   launch_k(wgrad_halo_kernel, dim3(grid), dim3(kWgThreads), kWgHSmemBytes, stream, p);
+  if (p.part != nullptr) launch_wgrad_reduce(p.part, p.part_stride, p.nsplit, p.dw, stream);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -1498,6 +1527,7 @@ int launch_wgrad(const WgradParams& p, cudaStream_t stream) {
   const int grid = p.ngroups * p.nsplit;
   if (grid <= 0) return 0;
   launch_k(wgrad_kernel, dim3(grid), dim3(kWgThreads), kWgSmemBytes, stream, p);
+  if (p.part != nullptr) launch_wgrad_reduce(p.part, p.part_stride, p.nsplit, p.dw, stream);
   return static_cast<int>(cudaGetLastError());
 }
 

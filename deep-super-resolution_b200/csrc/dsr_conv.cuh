@@ -9,6 +9,8 @@
 #include <cuda.h>
 #include <stdint.h>
 
+#include "dsr_acc.cuh"
+
 namespace dsr {
 
 constexpr int kConvThreads = 192;       // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue
@@ -49,7 +51,7 @@ struct alignas(64) ConvGemmParams {
   int n_mma;              // UMMA N (multiple of 16, <= 144)
   int n_store;            // channels stored per pixel (multiple of 8, <= n_mma)
   int out_bf16;           // 0: convert accumulators to fp16, 1: to bf16
-  float* stats;           // optional [2][n_mma]: per-channel sum and sum of squares of the STORED values
+  acc_t* stats;           // optional [2][n_mma] (fixed point, dsr_acc.cuh): per-channel sum and sum of squares of the STORED values
   uint32_t idesc;
   int* err;
 };
@@ -88,7 +90,7 @@ struct alignas(64) HaloParams {
   long long out_sy, out_sx;  // output strides (elements)
   void* out;                 // fp16
   int n_store;               // channels actually stored per pixel (<= n_part * parts)
-  float* stats;              // optional [2][stats_stride]
+  acc_t* stats;              // optional [2][stats_stride] (fixed point, dsr_acc.cuh)
   int stats_stride;
   int wide_slots;            // A ring depth for 64-channel chunks (2 or 3)
   uint32_t idesc_wide, idesc_narrow;
@@ -150,6 +152,8 @@ struct alignas(64) WgradParams {
   int c16_base;              // first channel of the 16-wide chunks
   int ldw;                   // row pitch (floats) of the packed gradient = padded ci count
   float* dw;                 // [ntaps_total][128][ldw] fp32, accumulated with red.add
+  float* part;               // deterministic mode: [nsplit][part_stride] private partials (plain stores), else nullptr
+  long long part_stride;     // = ntaps_total * 128 * ldw
   uint32_t idesc64, idesc16;
   int* err;
 };
@@ -192,6 +196,8 @@ struct alignas(64) WgHaloParams {
   int nsplit, pb_x, pb_y;
   int n64, n16, c16_base, ldw;
   float* dw;
+  float* part;                 // deterministic mode: [nsplit][part_stride] private partials, else nullptr
+  long long part_stride;
   uint32_t idesc_base;         // kind::f16, both operands MN-major, M = 128, N field left 0
   int* err;
 };

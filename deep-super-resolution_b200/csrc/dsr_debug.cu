@@ -54,8 +54,8 @@ __global__ void conv_ref_kernel(ConvGemmParams p, ActRef a, WgtRef b) {
       stored = __half2float(h);
     }
     if (p.stats != nullptr) {
-      atomicAdd(&p.stats[n], stored);
-      atomicAdd(&p.stats[p.n_mma + n], stored * stored);
+      acc_add_f(&p.stats[n], stored);
+      acc_add_f(&p.stats[p.n_mma + n], stored * stored);
     }
   }
 }

@@ -17,6 +17,8 @@ namespace dsr {
 
 namespace {
 
+constexpr float kLossScale = 1099511627776.f;      // 2^40: loss quanta of 9e-13, range +-8e6
+
 // outputs per block: 16 x 8 (factor <= 8; 384 blocks at 512^2 / factor 4) or 16 x 4 (larger factors, to keep the staged patch in smem)
 inline void ds_tile(int factor, int& tox, int& toy) {
   if (factor <= 8) { tox = 16; toy = 8; } else { tox = 16; toy = 4; }
@@ -74,14 +76,27 @@ __global__ void downsample_fwd_kernel(const float* __restrict__ x, const float* 
     }
   }
   if (target != nullptr) {
-    __shared__ float red;
-    if (threadIdx.x == 0) red = 0.f;
+    // The loss is summed in 64-bit fixed point (2^-40 quanta) so that it does not depend on the order in which the
+    // blocks finish: every block adds its sum to t.loss_acc; the last one to arrive (ticket) converts the total,
+    // adds it to *loss and re-arms the two words for the next launch.
+    __shared__ acc_t red;
+    if (threadIdx.x == 0) red = 0ull;
     __syncthreads();
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, d);
-    if ((threadIdx.x & 31) == 0) atomicAdd(&red, lsum);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&red, acc_fix(lsum, kLossScale));
     __syncthreads();
-    if (threadIdx.x == 0) atomicAdd(loss, red);
+    if (threadIdx.x == 0) {
+      atomicAdd(t.loss_acc, red);
+      __threadfence();
+      const unsigned nblocks = gridDim.x * gridDim.y * gridDim.z;
+      if (atomicAdd(t.loss_ticket, 1u) == nblocks - 1) {
+        __threadfence();
+        const acc_t total = atomicExch(t.loss_acc, 0ull);
+        *t.loss_ticket = 0u;
+        *loss += acc_val(total, 1.f / kLossScale);
+      }
+    }
   }
 }
 

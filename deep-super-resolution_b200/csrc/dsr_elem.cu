@@ -68,8 +68,8 @@ __device__ __forceinline__ int halo_coords(int i, int n, int (&o)[3]) {
 }
 
 __device__ __forceinline__ void bn_coeffs(const BnRef& bn, int c, float& mean, float& rstd, float& gamma, float& beta) {
-  const float s = bn.stats[c];
-  const float q = bn.stats[bn.cstride + c];
+  const float s = acc_get_f(&bn.stats[c]);
+  const float q = acc_get_f(&bn.stats[bn.cstride + c]);
   mean = s * bn.inv_n;
   const float var = fmaxf(q * bn.inv_n - mean * mean, 0.f);
   rstd = rsqrtf(var + kBnEps);
@@ -223,7 +223,7 @@ struct PerturbSpec {
 template <bool SKIP, bool PERTURB>
 __global__ void __launch_bounds__(kThreads) input_pack32_kernel(float* __restrict__ z, __half* __restrict__ xpad, int H,
                                                                 int W, const float* __restrict__ skip_w,
-                                                                float* __restrict__ sraw, float* __restrict__ skip_stats,
+                                                                float* __restrict__ sraw, acc_t* __restrict__ skip_stats,
                                                                 PerturbSpec ps) {
   pdl_sync();
   constexpr int C = 32;
@@ -322,13 +322,13 @@ __global__ void __launch_bounds__(kThreads) input_pack32_kernel(float* __restric
       red[threadIdx.x] = t;
     }
     __syncthreads();
-    if (threadIdx.x < 8) atomicAdd(&skip_stats[threadIdx.x], red[threadIdx.x]);
+    if (threadIdx.x < 8) acc_add_f(&skip_stats[threadIdx.x], red[threadIdx.x]);
   }
 }
 
 // z: input (perturb_zs == nullptr) or OUTPUT of the fused perturbation z = perturb_zs + sigma N(0,1)
 int launch_input_pack(float* z, void* xpad, int C, int H, int W, cudaStream_t s, const float* skip_w, float* sraw,
-                      float* skip_stats, const float* perturb_zs, float sigma, unsigned long long seed,
+                      acc_t* skip_stats, const float* perturb_zs, float sigma, unsigned long long seed,
                       const float* state) {
   const int tiles_x = (W + 63) / 64;
   const bool fast = (C == 32) && (W % 4 == 0);
@@ -374,7 +374,7 @@ __device__ __forceinline__ void pix_advance(int y0, int x0, int u, int W, int& y
 struct SkipFuse {
   const float* w;          // [4][128] fp32
   float* sraw;             // [H][W][4]
-  float* stats;            // [2][4]
+  acc_t* stats;            // [2][4]
 };
 template <bool SKIP>
 __global__ void __launch_bounds__(kThreads) bn_act_kernel(const __half* __restrict__ raw, BnRef bn,
@@ -484,7 +484,7 @@ __global__ void __launch_bounds__(kThreads) bn_act_kernel(const __half* __restri
       float t = 0.f;
 #pragma unroll
       for (int ww = 0; ww < kThreads / 32; ++ww) t += scr8[ww][threadIdx.x];
-      atomicAdd(&sf.stats[threadIdx.x], t);
+      acc_add_f(&sf.stats[threadIdx.x], t);
     }
   }
 }
@@ -498,7 +498,7 @@ inline int warp_grid(int H, int W, int cap_blocks) {      // one warp per kPixUn
 }
 
 int launch_bn_act(const void* raw, BnRef bn, void* act_pad, int H, int W, int halo, cudaStream_t s,
-                  const float* skip_w, float* skip_sraw, float* skip_stats) {
+                  const float* skip_w, float* skip_sraw, acc_t* skip_stats) {
   SkipFuse sf{skip_w, skip_sraw, skip_stats};
   if (skip_w != nullptr)
     launch_k(bn_act_kernel<true>, dim3(warp_grid(H, W, 148 * 8)), dim3(kThreads), 0, s,
@@ -514,7 +514,7 @@ int launch_bn_act(const void* raw, BnRef bn, void* act_pad, int H, int W, int ha
 // =============================================================================================
 template <int CIN>
 __global__ void skip_conv_kernel(const __half* __restrict__ xpad, const float* __restrict__ w, float* __restrict__ sraw,
-                                 float* __restrict__ stats, int H, int W) {
+                                 acc_t* __restrict__ stats, int H, int W) {
   pdl_sync();
   constexpr int G = CIN / 8;   // lanes per pixel
   const int g = threadIdx.x % G;
@@ -551,18 +551,18 @@ __global__ void skip_conv_kernel(const __half* __restrict__ xpad, const float* _
       for (int o = 0; o < 4; ++o) { ss[o] += acc[o]; sq[o] += acc[o] * acc[o]; }
     }
   }
-  __shared__ float red[8];
-  if (threadIdx.x < 8) red[threadIdx.x] = 0.f;
+  __shared__ acc_t red[8];                 // fixed point: the block sum does not depend on the arrival order
+  if (threadIdx.x < 8) red[threadIdx.x] = 0ull;
   __syncthreads();
   if (g == 0) {
 #pragma unroll
-    for (int o = 0; o < 4; ++o) { atomicAdd(&red[o], ss[o]); atomicAdd(&red[4 + o], sq[o]); }
+    for (int o = 0; o < 4; ++o) { acc_add_f(&red[o], ss[o]); acc_add_f(&red[4 + o], sq[o]); }
   }
   __syncthreads();
   if (threadIdx.x < 8) atomicAdd(&stats[threadIdx.x], red[threadIdx.x]);
 }
 
-int launch_skip_conv(const void* xpad, int Cin, const float* w, float* sraw, float* stats, int H, int W,
+int launch_skip_conv(const void* xpad, int Cin, const float* w, float* sraw, acc_t* stats, int H, int W,
                      cudaStream_t s) {
   const long long items = static_cast<long long>(H) * W * (Cin / 8);
   const int grid = grid_for(items, kThreads, 148 * 8);
@@ -628,7 +628,7 @@ struct SkipConst {
   float cxa[4], cxb[4], ck1[4], cc1[4], cc2[4], csh[4];   // BN(132) skip channels: xhat = s * cxa + cxb; k1 = gamma * rstd;
                                                           // c1, c2 = backward means; csh = beta - mean * k1
 };
-__device__ __forceinline__ void skip_const_init(SkipConst* sc, const UpcatArgs& a, const float* cbstats, bool have_cat) {
+__device__ __forceinline__ void skip_const_init(SkipConst* sc, const UpcatArgs& a, const acc_t* cbstats, bool have_cat) {
   if (threadIdx.x < 4) {
     const int o = threadIdx.x;
     float mean, rstd, ga, be;
@@ -636,13 +636,13 @@ __device__ __forceinline__ void skip_const_init(SkipConst* sc, const UpcatArgs& 
     sc->xa[o] = rstd; sc->xb[o] = -mean * rstd; sc->ga[o] = ga; sc->be[o] = be;
     if (have_cat) {
       const float inv_n = 1.f / (static_cast<float>(a.H) * static_cast<float>(a.W));
-      const float su = a.cat_stats[128 + o], sq = a.cat_stats[144 + 128 + o];
+      const float su = acc_get_f(&a.cat_stats[128 + o]), sq = acc_get_f(&a.cat_stats[144 + 128 + o]);
       const float m4 = su * inv_n;
       const float r4 = rsqrtf(fmaxf(sq * inv_n - m4 * m4, 0.f) + kBnEps);
       const float g4 = a.cat_gamma[o], b4 = a.cat_beta[o];      // reference channels 0..3 are the skip channels
       sc->cxa[o] = r4; sc->cxb[o] = -m4 * r4; sc->ck1[o] = g4 * r4; sc->csh[o] = b4 - m4 * g4 * r4;
-      sc->cc1[o] = cbstats ? cbstats[128 + o] * inv_n : 0.f;
-      sc->cc2[o] = cbstats ? cbstats[144 + 128 + o] * inv_n : 0.f;
+      sc->cc1[o] = cbstats ? acc_get_b(&cbstats[128 + o]) * inv_n : 0.f;
+      sc->cc2[o] = cbstats ? acc_get_b(&cbstats[144 + 128 + o]) * inv_n : 0.f;
     }
   }
   __syncthreads();
@@ -704,19 +704,19 @@ __global__ void __launch_bounds__(kThreads, 3) upcat_stats_kernel(UpcatArgs a) {
       }
     }
   }
-  __shared__ float red[2 * 144];
-  for (int i = threadIdx.x; i < 2 * 144; i += blockDim.x) red[i] = 0.f;
+  __shared__ acc_t red[2 * 144];
+  for (int i = threadIdx.x; i < 2 * 144; i += blockDim.x) red[i] = 0ull;
   __syncthreads();
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    atomicAdd(&red[lane * 4 + j], s[j]);
-    atomicAdd(&red[144 + lane * 4 + j], q[j]);
+    acc_add_f(&red[lane * 4 + j], s[j]);
+    acc_add_f(&red[144 + lane * 4 + j], q[j]);
   }
   if (lane < 4) {
 #pragma unroll
     for (int o = 0; o < 4; ++o) {
-      atomicAdd(&red[128 + o], s4[o]);
-      atomicAdd(&red[144 + 128 + o], q4[o]);
+      acc_add_f(&red[128 + o], s4[o]);
+      acc_add_f(&red[144 + 128 + o], q4[o]);
     }
   }
   __syncthreads();
@@ -727,7 +727,7 @@ __global__ void __launch_bounds__(kThreads, 3) upcat_stats_kernel(UpcatArgs a) {
 // BN(132) coefficients for packed channel c (0..127 upsampled <-> reference 4+c; 128..131 skip <-> c-128)
 __device__ __forceinline__ void cat_coeffs(const UpcatArgs& a, int c, float& mean, float& rstd, float& ga, float& be) {
   const float inv_n = 1.f / (static_cast<float>(a.H) * static_cast<float>(a.W));
-  const float su = a.cat_stats[c], sq = a.cat_stats[144 + c];
+  const float su = acc_get_f(&a.cat_stats[c]), sq = acc_get_f(&a.cat_stats[144 + c]);
   mean = su * inv_n;
   rstd = rsqrtf(fmaxf(sq * inv_n - mean * mean, 0.f) + kBnEps);
   const int rc = (c < 128) ? c + 4 : c - 128;
@@ -891,12 +891,12 @@ __global__ void __launch_bounds__(kThreads, 3) final_bwd_kernel(const float* __r
                                                                 const float* __restrict__ out,
                                                                 const __half* __restrict__ act,
                                                                 const float* __restrict__ w, __half* __restrict__ dact,
-                                                                float* __restrict__ dw, float* __restrict__ db,
+                                                                acc_t* __restrict__ dw, acc_t* __restrict__ db,
                                                                 const float* __restrict__ gs, int H, int W) {
   pdl_sync();
   const int lane = threadIdx.x & 31;
   const int c0 = lane * 4;
-  const float S = gs[0], invS = gs[1];
+  const float S = gs[0];
   float wr[3][4], aw[3][4], ab[3] = {0, 0, 0};
 #pragma unroll
   for (int o = 0; o < 3; ++o)
@@ -949,22 +949,22 @@ __global__ void __launch_bounds__(kThreads, 3) final_bwd_kernel(const float* __r
       }
     }
   }
-  __shared__ float red[3 * 128 + 3];
-  for (int i = threadIdx.x; i < 3 * 128 + 3; i += blockDim.x) red[i] = 0.f;
+  __shared__ acc_t red[3 * 128 + 3];
+  for (int i = threadIdx.x; i < 3 * 128 + 3; i += blockDim.x) red[i] = 0ull;
   __syncthreads();
 #pragma unroll
   for (int o = 0; o < 3; ++o) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) atomicAdd(&red[o * 128 + c0 + j], aw[o][j]);
-    atomicAdd(&red[384 + o], ab[o]);
+    for (int j = 0; j < 4; ++j) acc_add_b(&red[o * 128 + c0 + j], aw[o][j]);
+    acc_add_b(&red[384 + o], ab[o]);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 3 * 128; i += blockDim.x) atomicAdd(&dw[i], red[i] * invS);
-  if (threadIdx.x < 3) atomicAdd(&db[threadIdx.x], red[384 + threadIdx.x] * invS);
+  for (int i = threadIdx.x; i < 3 * 128; i += blockDim.x) atomicAdd(&dw[i], red[i]);       // S * gradient units
+  if (threadIdx.x < 3) atomicAdd(&db[threadIdx.x], red[384 + threadIdx.x]);
 }
 
 int launch_final_bwd(const float* gout, const float* out, const void* act_pad, const float* w, void* dact_pad,
-                     float* dw, float* db, const float* gs, int H, int W, cudaStream_t s) {
+                     acc_t* dw, acc_t* db, const float* gs, int H, int W, cudaStream_t s) {
   const long long npix = static_cast<long long>(H) * W;
   long long blocks = (npix + 255) / 256;
   if (blocks > 148 * 6) blocks = 148 * 6;
@@ -1071,7 +1071,7 @@ __global__ void __launch_bounds__(kThreads, 3) bn_bwd_top_kernel(TopBwdArgs a) {
     mean_[j] = mean;
     rstd_[j] = rstd;
     if (APPLY) {
-      const float c1 = a.bstats[c0 + j] * a.bn.inv_n, c2 = a.bstats[128 + c0 + j] * a.bn.inv_n;
+      const float c1 = acc_get_b(&a.bstats[c0 + j]) * a.bn.inv_n, c2 = acc_get_b(&a.bstats[128 + c0 + j]) * a.bn.inv_n;
       B[j] = -k1[j] * c2 * rstd;
       A[j] = -k1[j] * (c1 - c2 * mean * rstd);
     }
@@ -1173,20 +1173,20 @@ __global__ void __launch_bounds__(kThreads, 3) bn_bwd_top_kernel(TopBwdArgs a) {
       float t = 0.f;
 #pragma unroll
       for (int ww = 0; ww < kThreads / 32; ++ww) t += scr[ww][n][l];
-      if (q < 2) atomicAdd(&a.bstats[idx], t);
-      else atomicAdd(&a.dw[idx - 256], t * invS);
+      if (q < 2) acc_add_b(&a.bstats[idx], t);
+      else acc_add_b(&a.dw[idx - 256], t);
     }
     if (threadIdx.x < 3) {
       float t = 0.f;
       for (int ww = 0; ww < kThreads / 32; ++ww) t += scr_b[ww][threadIdx.x];
-      atomicAdd(&a.db[threadIdx.x], t * invS);
+      acc_add_b(&a.db[threadIdx.x], t);
     }
   } else {
     const float amax = fmaxf(__low2float(amax2), __high2float(amax2));
     track_amax(a.gs, isfinite(amax) ? amax : 0.f, !isfinite(amax));
     if (blockIdx.x == 0 && threadIdx.x < 128) {
-      a.dbeta[threadIdx.x] = a.bstats[threadIdx.x] * invS;
-      a.dgamma[threadIdx.x] = a.bstats[128 + threadIdx.x] * invS;
+      a.dbeta[threadIdx.x] = acc_get_b(&a.bstats[threadIdx.x]) * invS;
+      a.dgamma[threadIdx.x] = acc_get_b(&a.bstats[128 + threadIdx.x]) * invS;
     }
   }
 }
@@ -1208,14 +1208,14 @@ int launch_bn_bwd_top_apply(const TopBwdArgs& a, cudaStream_t s) {
 
 // second BN-backward sum of channel c: bstats[128 + c] holds sum dy*xhat, or (bstats_raw) sum dy*r to be converted
 __device__ __forceinline__ float bn_bwd_s2(const BnBwdArgs& a, int c, float mean, float rstd) {
-  const float v = a.bstats[128 + c];
-  return a.bstats_raw ? rstd * (v - mean * a.bstats[c]) : v;
+  const float v = acc_get_b(&a.bstats[128 + c]);
+  return a.bstats_raw ? rstd * (v - mean * acc_get_b(&a.bstats[c])) : v;
 }
 __device__ __forceinline__ void bn_bwd_write_param_grads(const BnBwdArgs& a) {
   if (blockIdx.x == 0 && threadIdx.x < 128) {
     float mean, rstd, ga, be;
     bn_coeffs(a.bn, threadIdx.x, mean, rstd, ga, be);
-    a.dbeta[threadIdx.x] = a.bstats[threadIdx.x] * a.gs[1];
+    a.dbeta[threadIdx.x] = acc_get_b(&a.bstats[threadIdx.x]) * a.gs[1];
     a.dgamma[threadIdx.x] = bn_bwd_s2(a, threadIdx.x, mean, rstd) * a.gs[1];
   }
 }
@@ -1242,13 +1242,13 @@ __global__ void __launch_bounds__(kThreads, HAS_DS ? 2 : 3) bn_bwd_kernel(BnBwdA
       const int o = threadIdx.x;
       float mean, rstd, g4, b4;
       bn_coeffs(a.bn_skip, o, mean, rstd, g4, b4);
-      const float k = g4 * rstd, c1s = a.sbstats[o] * a.bn_skip.inv_n, c2s = a.sbstats[4 + o] * a.bn_skip.inv_n;
+      const float k = g4 * rstd, c1s = acc_get_b(&a.sbstats[o]) * a.bn_skip.inv_n, c2s = acc_get_b(&a.sbstats[4 + o]) * a.bn_skip.inv_n;
       skc[0][o] = k;                                   // xhat = (sraw - mean) rstd
       skc[1][o] = -k * c2s * rstd;
       skc[2][o] = -k * (c1s - c2s * mean * rstd);
       if (APPLY && blockIdx.x == 0) {
-        a.dskip_beta[o] = a.sbstats[o] * a.gs[1];
-        a.dskip_gamma[o] = a.sbstats[4 + o] * a.gs[1];
+        a.dskip_beta[o] = acc_get_b(&a.sbstats[o]) * a.gs[1];
+        a.dskip_gamma[o] = acc_get_b(&a.sbstats[4 + o]) * a.gs[1];
       }
     }
     if (!APPLY) {
@@ -1266,7 +1266,7 @@ __global__ void __launch_bounds__(kThreads, HAS_DS ? 2 : 3) bn_bwd_kernel(BnBwdA
     xa[j] = rstd;
     xb[j] = -mean * rstd;
     k1[j] = ga[j] * rstd;
-    c1[j] = APPLY ? a.bstats[c0 + j] * a.bn.inv_n : 0.f;
+    c1[j] = APPLY ? acc_get_b(&a.bstats[c0 + j]) * a.bn.inv_n : 0.f;
     c2[j] = APPLY ? bn_bwd_s2(a, c0 + j, mean, rstd) * a.bn.inv_n : 0.f;
     s1[j] = 0.f;
     s2[j] = 0.f;
@@ -1379,10 +1379,9 @@ __global__ void __launch_bounds__(kThreads, HAS_DS ? 2 : 3) bn_bwd_kernel(BnBwdA
       }
     }
     block_sum_lane4<kQ>(vals, red, 128, scr);
-    atomicAdd(&a.bstats[threadIdx.x], red[threadIdx.x]);
+    acc_add_b(&a.bstats[threadIdx.x], red[threadIdx.x]);
     if (HAS_DS) {
-      const float invS = a.gs[1];
-      for (int i = threadIdx.x; i < 512; i += blockDim.x) atomicAdd(&a.dwskip[i], red[256 + i] * invS);
+      for (int i = threadIdx.x; i < 512; i += blockDim.x) acc_add_b(&a.dwskip[i], red[256 + i]);    // S * gradient units
     }
   } else {
     const float amax = fmaxf(__low2float(amax2), __high2float(amax2));
@@ -1414,7 +1413,7 @@ __global__ void __launch_bounds__(kThreads, 3) bn_bwd_fast_kernel(BnBwdArgs a) {
     mean_[j] = mean;
     rstd_[j] = rstd;
     if (APPLY) {
-      const float c1 = a.bstats[c0 + j] * a.bn.inv_n, c2 = bn_bwd_s2(a, c0 + j, mean, rstd) * a.bn.inv_n;
+      const float c1 = acc_get_b(&a.bstats[c0 + j]) * a.bn.inv_n, c2 = bn_bwd_s2(a, c0 + j, mean, rstd) * a.bn.inv_n;
       B[j] = -k1[j] * c2 * rstd;
       A[j] = -k1[j] * (c1 - c2 * mean * rstd);
     }
@@ -1497,7 +1496,7 @@ __global__ void __launch_bounds__(kThreads, 3) bn_bwd_fast_kernel(BnBwdArgs a) {
     float t = 0.f;
 #pragma unroll
     for (int ww = 0; ww < kThreads / 32; ++ww) t += scr[ww][n][l];
-    atomicAdd(&a.bstats[threadIdx.x], t);
+    acc_add_b(&a.bstats[threadIdx.x], t);
   } else {
     const float amax = fmaxf(__low2float(amax2), __high2float(amax2));
     track_amax(a.gs, isfinite(amax) ? amax : 0.f, !isfinite(amax));
@@ -1572,8 +1571,8 @@ __global__ void __launch_bounds__(kThreads, 2) upcat_bwd_kernel(UpcatBwdArgs a) 
     xa[j] = rstd;
     xb[j] = -mean * rstd;
     k1[j] = ga * rstd;
-    c1[j] = APPLY ? a.cbstats[c0 + j] * inv_n : 0.f;
-    c2[j] = APPLY ? a.cbstats[144 + c0 + j] * inv_n : 0.f;
+    c1[j] = APPLY ? acc_get_b(&a.cbstats[c0 + j]) * inv_n : 0.f;
+    c2[j] = APPLY ? acc_get_b(&a.cbstats[144 + c0 + j]) * inv_n : 0.f;
     s1[j] = 0.f;
     s2[j] = 0.f;
   }
@@ -1649,33 +1648,33 @@ __global__ void __launch_bounds__(kThreads, 2) upcat_bwd_kernel(UpcatBwdArgs a) 
     }
   }
   if (!APPLY) {
-    __shared__ float red[2 * 144];
-    for (int i = threadIdx.x; i < 2 * 144; i += blockDim.x) red[i] = 0.f;
+    __shared__ acc_t red[2 * 144];
+    for (int i = threadIdx.x; i < 2 * 144; i += blockDim.x) red[i] = 0ull;
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      atomicAdd(&red[c0 + j], s1[j]);
-      atomicAdd(&red[144 + c0 + j], s2[j]);
+      acc_add_b(&red[c0 + j], s1[j]);
+      acc_add_b(&red[144 + c0 + j], s2[j]);
     }
     if (lane < 4) {
 #pragma unroll
       for (int o = 0; o < 4; ++o) {
-        atomicAdd(&red[128 + o], t1[o]);
-        atomicAdd(&red[144 + 128 + o], t2[o]);
+        acc_add_b(&red[128 + o], t1[o]);
+        acc_add_b(&red[144 + 128 + o], t2[o]);
       }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < 2 * 144; i += blockDim.x)
       if ((i % 144) < 132) atomicAdd(&a.cbstats[i], red[i]);
   } else {
-    __shared__ float red4[8];
-    if (threadIdx.x < 8) red4[threadIdx.x] = 0.f;
+    __shared__ acc_t red4[8];
+    if (threadIdx.x < 8) red4[threadIdx.x] = 0ull;
     __syncthreads();
     if (lane < 4) {
 #pragma unroll
       for (int o = 0; o < 4; ++o) {
-        atomicAdd(&red4[o], t1[o]);
-        atomicAdd(&red4[4 + o], t2[o]);
+        acc_add_b(&red4[o], t1[o]);
+        acc_add_b(&red4[4 + o], t2[o]);
       }
     }
     __syncthreads();
@@ -1683,8 +1682,8 @@ __global__ void __launch_bounds__(kThreads, 2) upcat_bwd_kernel(UpcatBwdArgs a) 
     if (blockIdx.x == 0 && threadIdx.x < 132) {
       const int c = threadIdx.x;                        // packed channel
       const int rc = (c < 128) ? c + 4 : c - 128;       // reference channel
-      a.dcat_beta[rc] = a.cbstats[c] * a.gs[1];
-      a.dcat_gamma[rc] = a.cbstats[144 + c] * a.gs[1];
+      a.dcat_beta[rc] = acc_get_b(&a.cbstats[c]) * a.gs[1];
+      a.dcat_gamma[rc] = acc_get_b(&a.cbstats[144 + c]) * a.gs[1];
     }
   }
 }
@@ -1709,8 +1708,8 @@ int launch_upcat_bwd_apply(const UpcatBwdArgs& a, cudaStream_t s) {
 // =============================================================================================
 template <int CIN>
 __global__ void skip_bwd_kernel(const float* __restrict__ dsy, const float* __restrict__ sraw, BnRef bn,
-                                const float* __restrict__ sbstats, const __half* __restrict__ xpad,
-                                float* __restrict__ dsraw, float* __restrict__ dw, float* __restrict__ dgamma,
+                                const acc_t* __restrict__ sbstats, const __half* __restrict__ xpad,
+                                float* __restrict__ dsraw, acc_t* __restrict__ dw, float* __restrict__ dgamma,
                                 float* __restrict__ dbeta, const float* __restrict__ gs, int H, int W) {
   pdl_sync();
   constexpr int G = CIN / 8;
@@ -1720,8 +1719,8 @@ __global__ void skip_bwd_kernel(const float* __restrict__ dsy, const float* __re
 #pragma unroll
   for (int o = 0; o < 4; ++o) {
     bn_coeffs(bn, o, mean[o], rstd[o], ga[o], be[o]);
-    c1[o] = sbstats[o] * bn.inv_n;
-    c2[o] = sbstats[4 + o] * bn.inv_n;
+    c1[o] = acc_get_b(&sbstats[o]) * bn.inv_n;
+    c2[o] = acc_get_b(&sbstats[4 + o]) * bn.inv_n;
   }
   float aw[4][8];
 #pragma unroll
@@ -1792,16 +1791,16 @@ __global__ void skip_bwd_kernel(const float* __restrict__ dsy, const float* __re
     float t = 0.f;
 #pragma unroll
     for (int ww = 0; ww < kThreads / 32; ++ww) t += scr[ww][o * 8 + (c & 7)][c >> 3];
-    atomicAdd(&dw[i], t * invS);
+    acc_add_b(&dw[i], t);               // S * gradient units
   }
   if (blockIdx.x == 0 && threadIdx.x < 4) {
-    dbeta[threadIdx.x] = sbstats[threadIdx.x] * invS;
-    dgamma[threadIdx.x] = sbstats[4 + threadIdx.x] * invS;
+    dbeta[threadIdx.x] = acc_get_b(&sbstats[threadIdx.x]) * invS;
+    dgamma[threadIdx.x] = acc_get_b(&sbstats[4 + threadIdx.x]) * invS;
   }
 }
 
-int launch_skip_bwd(const float* dsy, const float* sraw, BnRef bn_skip, const float* sbstats, const void* xpad, int Cin,
-                    float* dsraw, float* dw, float* dgamma, float* dbeta, const float* gs, int H, int W,
+int launch_skip_bwd(const float* dsy, const float* sraw, BnRef bn_skip, const acc_t* sbstats, const void* xpad, int Cin,
+                    float* dsraw, acc_t* dw, float* dgamma, float* dbeta, const float* gs, int H, int W,
                     cudaStream_t s) {
   const long long items = static_cast<long long>(H) * W * (Cin / 8);
   const int grid = grid_for(items, kThreads, 148 * 4);
@@ -1921,8 +1920,8 @@ __device__ __forceinline__ void upcat_stats_lowres_body(const UpcatArgs& a, int 
 #pragma unroll
   for (int j = 0; j < 4; ++j) { vals[0][j] = s[j]; vals[1][j] = q[j]; }
   block_sum_lane4<2>(vals, red, 128, scr);
-  if (threadIdx.x < 128) atomicAdd(&a.cat_stats[threadIdx.x], red[threadIdx.x]);
-  else atomicAdd(&a.cat_stats[144 + threadIdx.x - 128], red[threadIdx.x]);
+  if (threadIdx.x < 128) acc_add_f(&a.cat_stats[threadIdx.x], red[threadIdx.x]);
+  else acc_add_f(&a.cat_stats[144 + threadIdx.x - 128], red[threadIdx.x]);
 }
 
 // forward statistics of the 4 skip channels of the concat tensor (one thread per pixel)
@@ -1954,8 +1953,8 @@ __device__ __forceinline__ void skipcat_stats_body(const UpcatArgs& a, int vbloc
     red[threadIdx.x] = t;
   }
   __syncthreads();
-  if (threadIdx.x < 4) atomicAdd(&a.cat_stats[128 + threadIdx.x], red[threadIdx.x]);
-  else if (threadIdx.x < 8) atomicAdd(&a.cat_stats[144 + 128 + threadIdx.x - 4], red[threadIdx.x]);
+  if (threadIdx.x < 4) acc_add_f(&a.cat_stats[128 + threadIdx.x], red[threadIdx.x]);
+  else if (threadIdx.x < 8) acc_add_f(&a.cat_stats[144 + 128 + threadIdx.x - 4], red[threadIdx.x]);
 }
 
 // one launch: blocks [0, nb_lo) take the 128 upsampled channels (low-resolution domain), the rest the 4 skip channels
@@ -2035,6 +2034,8 @@ __device__ __forceinline__ void upT_gather_tile_body(const UpcatBwdArgs& a, uint
   __shared__ SkipConst sc;
   __shared__ float wy_s[kGtH][4], wx_s[kGtW][4];
   __shared__ float red[264];
+  __shared__ acc_t red8[8];                     // skip-channel sums of the block's warps (fixed point: order-free)
+  if (threadIdx.x < 8) red8[threadIdx.x] = 0ull;
   skip_const_init(&sc, f, nullptr, true);
   for (int i = threadIdx.x; i < 264; i += blockDim.x) red[i] = 0.f;
   __half* S = reinterpret_cast<__half*>(smem_raw);
@@ -2182,13 +2183,14 @@ __device__ __forceinline__ void upT_gather_tile_body(const UpcatBwdArgs& a, uint
       float v = t1[o], u = t2[o];
 #pragma unroll
       for (int dd = 16; dd >= 1; dd >>= 1) { v += __shfl_xor_sync(0xffffffffu, v, dd); u += __shfl_xor_sync(0xffffffffu, u, dd); }
-      if ((threadIdx.x & 31) == 0) { atomicAdd(&red[256 + o], v); atomicAdd(&red[260 + o], u); }
+      if ((threadIdx.x & 31) == 0) { acc_add_b(&red8[o], v); acc_add_b(&red8[4 + o], u); }
     }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 264; i += blockDim.x) {
     const int dst = i < 128 ? i : i < 256 ? 144 + i - 128 : i < 260 ? 128 + i - 256 : 144 + 128 + i - 260;
-    atomicAdd(&a.cbstats[dst], red[i]);
+    if (i < 256) acc_add_b(&a.cbstats[dst], red[i]);
+    else atomicAdd(&a.cbstats[dst], red8[i - 256]);
   }
 }
 
@@ -2241,13 +2243,13 @@ __device__ __forceinline__ void skipcat_bwd_body(const UpcatBwdArgs& a, int vblo
   }
   __syncthreads();
   if (!APPLY) {
-    if (threadIdx.x < 4) atomicAdd(&a.cbstats[128 + threadIdx.x], red[threadIdx.x]);
-    else if (threadIdx.x < 8) atomicAdd(&a.cbstats[144 + 128 + threadIdx.x - 4], red[threadIdx.x]);
+    if (threadIdx.x < 4) acc_add_b(&a.cbstats[128 + threadIdx.x], red[threadIdx.x]);
+    else if (threadIdx.x < 8) acc_add_b(&a.cbstats[144 + 128 + threadIdx.x - 4], red[threadIdx.x]);
   } else {
-    if (threadIdx.x < 8) atomicAdd(&a.sbstats[threadIdx.x], red[threadIdx.x]);
+    if (threadIdx.x < 8) acc_add_b(&a.sbstats[threadIdx.x], red[threadIdx.x]);
     if (vblock == 0 && threadIdx.x < 4) {       // skip channels are reference channels 0..3
-      a.dcat_beta[threadIdx.x] = a.cbstats[128 + threadIdx.x] * a.gs[1];
-      a.dcat_gamma[threadIdx.x] = a.cbstats[144 + 128 + threadIdx.x] * a.gs[1];
+      a.dcat_beta[threadIdx.x] = acc_get_b(&a.cbstats[128 + threadIdx.x]) * a.gs[1];
+      a.dcat_gamma[threadIdx.x] = acc_get_b(&a.cbstats[144 + 128 + threadIdx.x]) * a.gs[1];
     }
   }
 }
@@ -2273,8 +2275,8 @@ __device__ __forceinline__ void upcat_bwd_elem_body(const UpcatBwdArgs& a, __hal
     float mean, rstd, ga, be;
     cat_coeffs(f, c0 + j, mean, rstd, ga, be);
     k1[j] = ga * rstd;
-    const float S1 = a.cbstats[c0 + j];
-    const float S2 = rstd * (a.cbstats[144 + c0 + j] - mean * S1);      // sum dc * xhat
+    const float S1 = acc_get_b(&a.cbstats[c0 + j]);
+    const float S2 = rstd * (acc_get_b(&a.cbstats[144 + c0 + j]) - mean * S1);      // sum dc * xhat
     const float c1 = S1 * inv_n, c2r = S2 * inv_n * rstd;
     B[j] = -k1[j] * c2r;
     A[j] = -k1[j] * (c1 - c2r * mean);
@@ -2358,14 +2360,14 @@ __device__ __forceinline__ void upcat_bwd_elem_body(const UpcatBwdArgs& a, __hal
       cs1[j] += __shfl_xor_sync(0xffffffffu, cs1[j], 16);
       cs2[j] += __shfl_xor_sync(0xffffffffu, cs2[j], 16);
     }
-    __shared__ float cred[256];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) cred[i] = 0.f;
+    __shared__ acc_t cred[256];                  // fixed point: the block sum does not depend on the arrival order
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) cred[i] = 0ull;
     __syncthreads();
     if ((threadIdx.x & 31) < 16) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        atomicAdd(&cred[c0 + j], cs1[j]);
-        atomicAdd(&cred[128 + c0 + j], cs2[j]);
+        acc_add_b(&cred[c0 + j], cs1[j]);
+        acc_add_b(&cred[128 + c0 + j], cs2[j]);
       }
     }
     __syncthreads();
@@ -2565,6 +2567,23 @@ int launch_unpack_wgrad(const float* garena, float* grads, const PackDesc* table
 }
 
 // =============================================================================================
+// small-layer gradients: fixed-point S * gradient accumulators -> flat gradient buffer
+// =============================================================================================
+__global__ void small_grads_finish_kernel(const SmallGradDesc* __restrict__ table, const acc_t* __restrict__ ws,
+                                          float* __restrict__ grads, const float* __restrict__ gs) {
+  pdl_sync();
+  const SmallGradDesc d = table[blockIdx.x];
+  const float invS = gs[1];
+  for (int i = threadIdx.x; i < d.n; i += blockDim.x) grads[d.g_off + i] = acc_get_b(&ws[d.acc_off + i]) * invS;
+}
+int launch_small_grads_finish(const SmallGradDesc* table_dev, int n, const acc_t* ws_acc, float* grads, const float* gs,
+                              cudaStream_t s) {
+  if (n <= 0) return 0;
+  launch_k(small_grads_finish_kernel, dim3(n), dim3(128), 0, s, table_dev, ws_acc, grads, gs);
+  DSR_LAUNCH_CHECK();
+}
+
+// =============================================================================================
 // gradient-scale maintenance: zero the gradients of a pass that produced non-finite values, then
 // adapt S for the next pass (max |S dR| kept within [2^9, 2^14], fp16 max is 65504)
 // =============================================================================================
@@ -2591,6 +2610,7 @@ __global__ void grad_scale_update_kernel(float* __restrict__ gs) {
   gs[3] = 0.f;
   gs[4] = amax;                // last pass, for inspection
   gs[5] = bad ? gs[5] + 1.f : gs[5];
+  gs[7] = bad ? 1.f : 0.f;     // the pass that just finished overflowed: its optimiser step is skipped (adam_kernel)
 }
 int launch_grad_scale_finish(float* grads, long long n, float* gs, cudaStream_t s) {
   launch_k(grad_sanitize_kernel, dim3(148 * 4), dim3(kThreads), 0, s, grads, n, gs);
@@ -2603,33 +2623,37 @@ int launch_grad_scale_finish(float* grads, long long n, float* gs, cudaStream_t 
 // graph replay): state[0] = t (int bits), state[1] = lr / (1 - b1^t), state[2] = 1 / sqrt(1 - b2^t)
 // =============================================================================================
 __global__ void step_begin_kernel(float* __restrict__ state, float* __restrict__ loss_base, int t_set, float lr,
-                                  float b1, float b2) {
+                                  float b1, float b2, const float* __restrict__ gs) {
   pdl_sync();
   const int t = (t_set > 0) ? t_set : __float_as_int(state[0]) + 1;
   state[0] = __int_as_float(t);
-  state[1] = static_cast<float>(static_cast<double>(lr) / (1.0 - pow(static_cast<double>(b1), static_cast<double>(t))));
-  state[2] = static_cast<float>(1.0 / sqrt(1.0 - pow(static_cast<double>(b2), static_cast<double>(t))));
+  // Adam's own step count: iterations whose update was skipped (gs[5] counts the overflowed passes) do not advance it
+  int ta = t - (gs != nullptr ? static_cast<int>(gs[5]) : 0);
+  if (ta < 1) ta = 1;
+  state[1] = static_cast<float>(static_cast<double>(lr) / (1.0 - pow(static_cast<double>(b1), static_cast<double>(ta))));
+  state[2] = static_cast<float>(1.0 / sqrt(1.0 - pow(static_cast<double>(b2), static_cast<double>(ta))));
   if (loss_base != nullptr) loss_base[t - 1] = 0.f;
 }
-int launch_step_begin(float* state, float* loss_base, int t_set, float lr, float b1, float b2, cudaStream_t s) {
-  launch_k(step_begin_kernel, dim3(1), dim3(1), 0, s, state, loss_base, t_set, lr, b1, b2);
+int launch_step_begin(float* state, float* loss_base, int t_set, float lr, float b1, float b2, cudaStream_t s,
+                      const float* gs) {
+  launch_k(step_begin_kernel, dim3(1), dim3(1), 0, s, state, loss_base, t_set, lr, b1, b2, gs);
   DSR_LAUNCH_CHECK();
 }
 
 // =============================================================================================
 // running statistics
 // =============================================================================================
-__global__ void bn_running_kernel(const BnRunDesc* __restrict__ table, const float* __restrict__ ws,
+__global__ void bn_running_kernel(const BnRunDesc* __restrict__ table, const acc_t* __restrict__ ws,
                                   const float* __restrict__ params, float* __restrict__ bnbuf, float momentum) {
   pdl_sync();
   const BnRunDesc d = table[blockIdx.x];
-  const float* stats = ws + d.stats_off;
+  const acc_t* stats = ws + d.stats_off;
   float* rm = bnbuf + d.rm_off;
   float* rv = bnbuf + d.rv_off;
   for (int c = threadIdx.x; c < d.C; c += blockDim.x) {
     const int pc = d.perm ? (c >= 4 ? c - 4 : c + 128) : c;     // reference channel c -> packed channel
-    const float mean = stats[pc] / d.n;
-    const float var_b = fmaxf(stats[d.cstride + pc] / d.n - mean * mean, 0.f);
+    const float mean = acc_get_f(&stats[pc]) / d.n;
+    const float var_b = fmaxf(acc_get_f(&stats[d.cstride + pc]) / d.n - mean * mean, 0.f);
     const float var_u = d.n > 1.f ? var_b * d.n / (d.n - 1.f) : var_b;
     const float bias = d.bias_off >= 0 ? params[d.bias_off + c] : 0.f;
     rm[c] = (1.f - momentum) * rm[c] + momentum * (mean + bias);
@@ -2637,9 +2661,9 @@ __global__ void bn_running_kernel(const BnRunDesc* __restrict__ table, const flo
   }
 }
 
-int launch_bn_running(const BnRunDesc* table_dev, int nbn, const float* ws_f32, const float* params, float* bn_buffers,
+int launch_bn_running(const BnRunDesc* table_dev, int nbn, const acc_t* ws_acc, const float* params, float* bn_buffers,
                       float momentum, cudaStream_t s) {
-  launch_k(bn_running_kernel, dim3(nbn), dim3(160), 0, s, table_dev, ws_f32, params, bn_buffers, momentum);
+  launch_k(bn_running_kernel, dim3(nbn), dim3(160), 0, s, table_dev, ws_acc, params, bn_buffers, momentum);
   DSR_LAUNCH_CHECK();
 }
 
@@ -2648,12 +2672,15 @@ int launch_bn_running(const BnRunDesc* table_dev, int nbn, const float* ws_f32, 
 // =============================================================================================
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, long long n, float step_size, float b1, float b2, float eps,
-                            float inv_sqrt_bc2, const float* __restrict__ state) {
+                            float inv_sqrt_bc2, const float* __restrict__ state, const float* __restrict__ gs) {
   pdl_sync();
   if (state != nullptr) {            // bias corrections of the device-tracked iteration (step_begin_kernel)
     step_size = state[1];
     inv_sqrt_bc2 = state[2];
   }
+  // a backward pass whose fp16 gradients overflowed has no usable gradient: standard dynamic loss scaling skips the
+  // update (moving every parameter by stale momentum would be a step the fp32 reference never takes)
+  if (gs != nullptr && gs[7] != 0.f) return;
   const long long n4 = n >> 2;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -2683,7 +2710,7 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 }
 
 int launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
-                int t, cudaStream_t s, const float* state) {
+                int t, cudaStream_t s, const float* state, const float* gs) {
   if ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
        reinterpret_cast<uintptr_t>(v)) & 15)
     return -3;
@@ -2692,7 +2719,7 @@ int launch_adam(float* p, const float* g, float* m, float* v, long long n, float
   const double bc2 = 1.0 - pow(static_cast<double>(b2), t);
   const float step_size = static_cast<float>(static_cast<double>(lr) / bc1);
   const float inv_sqrt_bc2 = static_cast<float>(1.0 / sqrt(bc2));
-  launch_k(adam_kernel, dim3(grid_for(n / 4 + 1, kThreads, 148 * 8)), dim3(kThreads), 0, s, p, g, m, v, n, step_size, b1, b2, eps, inv_sqrt_bc2, state);
+  launch_k(adam_kernel, dim3(grid_for(n / 4 + 1, kThreads, 148 * 8)), dim3(kThreads), 0, s, p, g, m, v, n, step_size, b1, b2, eps, inv_sqrt_bc2, state, gs);
   DSR_LAUNCH_CHECK();
 }
 

@@ -2,16 +2,20 @@
 //
 // Conventions: "act" tensors are fp16 NHWC on a padded pixel grid [H+2][W+2][C]; pointers passed
 // here always point at PADDED pixel (0,0) unless the argument is called *_interior or "plain"
-// (= unpadded [H][W][C]).  Gradient tensors are fp16 and hold S * gradient (S = gs[0], see launch_grad_scale_finish).  Statistics blocks are float [2][C]
-// (sum, sum of squares), accumulated with atomics and zeroed by the caller.
+// (= unpadded [H][W][C]).  Gradient tensors are fp16 and hold S * gradient (S = gs[0], see launch_grad_scale_finish).  Statistics blocks are acc_t [2][C]
+// (sum, sum of squares) in 64-bit fixed point (dsr_acc.cuh: order-independent, hence run-to-run deterministic),
+// accumulated with integer atomics and zeroed by the caller.  Forward sums use the forward scale, everything the
+// backward pass accumulates (BN-backward sums, small-layer weight gradients in S * gradient units) the backward scale.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "dsr_acc.cuh"
+
 namespace dsr {
 
 struct BnRef {            // one train-mode BatchNorm over n pixels
-  const float* stats;     // [2][cstride] forward sums of the BN input
+  const acc_t* stats;     // [2][cstride] forward sums of the BN input (fixed point, forward scale)
   const float* gamma;     // [C]
   const float* beta;      // [C]
   float inv_n;            // 1 / (H*W)
@@ -23,7 +27,7 @@ struct BnRef {            // one train-mode BatchNorm over n pixels
 // fuse level 0's skip-branch 1x1 conv (skip_w -> sraw fp32 [H][W][4], skip_stats [2][4]) and the input perturbation
 // (z = perturb_zs + sigma N(0,1), Philox counters of perturb_kernel; z is then the OUTPUT); otherwise both must be null.
 int launch_input_pack(float* z, void* xpad, int C, int H, int W, cudaStream_t s, const float* skip_w = nullptr,
-                      float* sraw = nullptr, float* skip_stats = nullptr, const float* perturb_zs = nullptr,
+                      float* sraw = nullptr, acc_t* skip_stats = nullptr, const float* perturb_zs = nullptr,
                       float sigma = 0.f, unsigned long long seed = 0, const float* state = nullptr);
 int input_pack_fast(int C, int W);
 
@@ -31,10 +35,10 @@ int input_pack_fast(int C, int W);
 // optional fusion of the NEXT level's skip-branch 1x1 conv (128 -> 4) on the activation being written:
 // skip_w fp32 [4][128] -> skip_sraw fp32 plain [H][W][4], skip_stats [2][4] (accumulated)
 int launch_bn_act(const void* raw, BnRef bn, void* act_pad, int H, int W, int halo, cudaStream_t s,
-                  const float* skip_w = nullptr, float* skip_sraw = nullptr, float* skip_stats = nullptr);
+                  const float* skip_w = nullptr, float* skip_sraw = nullptr, acc_t* skip_stats = nullptr);
 
 // skip branch 1x1 conv: x padded [H+2][W+2][Cin] (fp16) * w fp32 [4][Cin] -> sraw fp32 plain [H][W][4], stats [2][4]
-int launch_skip_conv(const void* xpad, int Cin, const float* w, float* sraw, float* stats, int H, int W,
+int launch_skip_conv(const void* xpad, int Cin, const float* w, float* sraw, acc_t* stats, int H, int W,
                      cudaStream_t s);
 
 // Upsample x2 (bilinear, align_corners=False) of `deep` + skip activation -> concat statistics / apply.
@@ -45,7 +49,7 @@ struct UpcatArgs {
   int H, W;                // concat extent (H <= 2h, W <= 2w; centre-crop offset is 0)
   const float* sraw;       // fp32 plain [H][W][4]
   BnRef bn_skip;           // BN(4) of the skip branch
-  float* cat_stats;        // [2][144]: packed channel order (0..127 upsampled, 128..131 skip)
+  acc_t* cat_stats;        // [2][144]: packed channel order (0..127 upsampled, 128..131 skip)
   const float* cat_gamma;  // BN(132) affine, REFERENCE channel order (0..3 skip, 4..131 upsampled)
   const float* cat_beta;
   void* cat_pad;           // fp16 padded [H+2][W+2][144], reflected halo
@@ -58,9 +62,10 @@ int launch_upcat_apply(const UpcatArgs& a, cudaStream_t s);
 int launch_final_conv(const void* act_pad, const float* w, const float* b, float* out, int H, int W, cudaStream_t s);
 
 // ---- backward ------------------------------------------------------------------------------
-// d(out) fp32 NCHW, out fp32 NCHW -> dA fp16 padded interior [H+2][W+2][128]; dW [3][128] and db [3] accumulated.
+// d(out) fp32 NCHW, out fp32 NCHW -> dA fp16 padded interior [H+2][W+2][128]; S * dW [3][128] and S * db [3]
+// accumulated in fixed point (converted into the gradient buffer by launch_small_grads_finish).
 int launch_final_bwd(const float* gout, const float* out, const void* act_pad, const float* w, void* dact_pad,
-                     float* dw, float* db, const float* gs, int H, int W, cudaStream_t s);
+                     acc_t* dw, acc_t* db, const float* gs, int H, int W, cudaStream_t s);
 
 // fused top of the network (level 0): see dsr_elem.cu
 int launch_bn_act_final(const void* raw, BnRef bn, const float* w, const float* b, float* out, int H, int W,
@@ -71,10 +76,10 @@ struct TopBwdArgs {
   const void* raw;         // fp16 plain [H][W][128]: BN input of the last decoder conv
   BnRef bn;
   const float* w;          // final conv weight [3][128]
-  float* bstats;           // [2][128]
+  acc_t* bstats;           // [2][128]
   void* dr_pad;            // fp16 padded [H+2][W+2][128]
   float* dgamma; float* dbeta;       // BN parameter gradients
-  float* dw; float* db;              // final conv weight / bias gradients (accumulated)
+  acc_t* dw; acc_t* db;              // S * final conv weight / bias gradients (fixed point, accumulated)
   float* gs;
   int H, W;
 };
@@ -90,15 +95,15 @@ struct BnBwdArgs {
   const float* dsy;        // fp32 plain [H][W][4]: gradient w.r.t. the skip BN(4) output (null: no skip branch)
   const float* sraw;       // fp32 plain [H][W][4]: skip conv output saved by the forward
   BnRef bn_skip;           // BN(4)
-  const float* sbstats;    // [2][4]: sum dsy, sum dsy * xhat
+  const acc_t* sbstats;    // [2][4]: sum dsy, sum dsy * xhat
   const float* wskip;      // fp32 [4][128]
-  float* dwskip;           // [4][128] accumulated
+  acc_t* dwskip;           // [4][128] S * gradient, fixed point, accumulated
   float* dskip_gamma;      // [4]
   float* dskip_beta;       // [4]
   float* dsraw;            // fp32 plain [H][W][4]: written for inspection (diagnostics)
   const void* raw;         // fp16 plain [H][W][128]: BN input saved by the forward
   BnRef bn;
-  float* bstats;           // [2][128]: sum dy, sum dy*xhat (bstats_raw: sum dy, sum dy*r -- see below)
+  acc_t* bstats;           // [2][128]: sum dy, sum dy*xhat (bstats_raw: sum dy, sum dy*r -- see below)
   int bstats_raw;          // 1: the sums were accumulated by the kernel that PRODUCED g (no separate statistics pass),
                            //    in raw form: [1] = sum dy * r; sum dy*xhat = rstd ([1] - mean [0])
   void* dr_pad;            // fp16 padded [H+2][W+2][128] (interior written; halo stays zero)
@@ -113,10 +118,10 @@ int launch_bn_bwd_apply(const BnBwdArgs& a, cudaStream_t s);
 struct UpcatBwdArgs {
   UpcatArgs f;             // forward description (deep, sraw, stats ...)
   const void* gcat;        // fp16 padded grid [H+2][W+2][144]: data-gradient of the 3x3 conv reading cat (to fold)
-  float* cbstats;          // [2][144] packed order: sum dc, sum dc*xhat
+  acc_t* cbstats;          // [2][144] packed order: sum dc, sum dc*xhat
   void* dup_pad;           // fp16 padded [H+2][W+2][128]: gradient w.r.t. the upsampled tensor (interior)
   float* dsy;              // fp32 plain [H][W][4]: gradient w.r.t. BN(4) output (after LeakyReLU')
-  float* sbstats;          // [2][4]
+  acc_t* sbstats;          // [2][4]
   float* dcat_gamma;       // [132] reference channel order
   float* dcat_beta;
   const float* gs;
@@ -124,7 +129,7 @@ struct UpcatBwdArgs {
   // last level's second encoder conv), accumulated by pass C while ddeep is in registers: sum dy, sum dy * r
   const void* cons_raw;    // fp16 plain [h][w][128]: that layer's BN input (null: no fusion)
   BnRef cons_bn;
-  float* cons_bstats;      // [2][128]
+  acc_t* cons_bstats;      // [2][128]
 };
 // source-domain formulation (see dsr_elem.cu): forward statistics of the concat tensor, and the whole backward of
 // upsample + concat + BN(132) (a.dup_pad is used as the [h][w][128] scratch tensor t = U^T dc)
@@ -135,8 +140,8 @@ int launch_upcat_bwd_stats(const UpcatBwdArgs& a, cudaStream_t s);
 int launch_upcat_bwd_apply(const UpcatBwdArgs& a, cudaStream_t s);
 
 // BN(4)+skip conv backward: dsy -> dsraw fp32 [H][W][4]; dWskip [4][Cin] (accumulated), dgamma4/dbeta4.
-int launch_skip_bwd(const float* dsy, const float* sraw, BnRef bn_skip, const float* sbstats, const void* xpad, int Cin,
-                    float* dsraw, float* dw, float* dgamma, float* dbeta, const float* gs, int H, int W,
+int launch_skip_bwd(const float* dsy, const float* sraw, BnRef bn_skip, const acc_t* sbstats, const void* xpad, int Cin,
+                    float* dsraw, acc_t* dw, float* dgamma, float* dbeta, const float* gs, int H, int W,
                     cudaStream_t s);
 
 // transpose of the bilinear x2 upsample: dup padded-interior [H][W][128] (fp16) -> ddeep fp16 padded interior [h][w][128]
@@ -155,24 +160,31 @@ struct PackDesc {           // one conv layer's weight (OIHW fp32 in the flat pa
 int launch_pack_weights(const float* params, void* arena, const PackDesc* table_dev, int nlayers, cudaStream_t s);
 int launch_unpack_wgrad(const float* garena, float* grads, const PackDesc* table_dev, int nlayers, const float* gs,
                         cudaStream_t s);
+// Gradients of the small 1x1 layers (skip-branch convs, final conv) are accumulated by the element-wise kernels as
+// S * gradient in fixed point; this converts them into the flat gradient buffer: grads[g_off + i] = acc[acc_off + i] / S.
+struct SmallGradDesc { long long acc_off; long long g_off; int n; int pad_; };   // acc_off: acc_t index from the workspace base
+int launch_small_grads_finish(const SmallGradDesc* table_dev, int n, const acc_t* ws_acc, float* grads, const float* gs,
+                              cudaStream_t s);
 // zero `grads` if the pass saw a non-finite gradient, then adapt the scale for the next pass
 int launch_grad_scale_finish(float* grads, long long n, float* gs, cudaStream_t s);
 
 struct BnRunDesc {          // running-statistics update of one BatchNorm (all offsets in floats)
-  long long stats_off;      // into the plan workspace viewed as float*: [2][cstride] forward sums
+  long long stats_off;      // into the plan workspace viewed as acc_t*: [2][cstride] forward sums
   int cstride; int C; float n;
   long long rm_off, rv_off; // into the flat BatchNorm buffer: running_mean[C], running_var[C]
   long long bias_off;       // into the flat parameter buffer: bias of the conv feeding this BN (the kernels drop
                             // it because BN cancels it, but torch's running_mean contains it), or -1
   int perm;                 // 1: stats are in packed concat order
 };
-int launch_bn_running(const BnRunDesc* table_dev, int nbn, const float* ws_f32, const float* params, float* bn_buffers,
+int launch_bn_running(const BnRunDesc* table_dev, int nbn, const acc_t* ws_acc, const float* params, float* bn_buffers,
                       float momentum, cudaStream_t s);
 
+// gs (optional): gradient-scale block of the plan; the update is skipped when the last backward pass overflowed (gs[7])
 int launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
-                int t, cudaStream_t s, const float* state = nullptr);
+                int t, cudaStream_t s, const float* state = nullptr, const float* gs = nullptr);
 // t_set > 0: state.t = t_set; t_set == 0: state.t += 1.  Also zeroes loss_base[t - 1] (if given).
-int launch_step_begin(float* state, float* loss_base, int t_set, float lr, float b1, float b2, cudaStream_t s);
+int launch_step_begin(float* state, float* loss_base, int t_set, float lr, float b1, float b2, cudaStream_t s,
+                      const float* gs = nullptr);
 
 // ---- Lanczos downsampler (fp32 NCHW) -------------------------------------------------------
 struct DsTables {           // device tables built by the plan (dsr_downsampler.cu)
@@ -182,6 +194,9 @@ struct DsTables {           // device tables built by the plan (dsr_downsampler.
   const int* by0; const float* bwy;   // [H], [H][nw]
   const int* bx0; const float* bwx;   // [W], [W][nw]
   int nw;
+  // fused-MSE launches: fixed-point loss accumulator + arrival ticket (both zero between launches; ONE launch at a
+  // time per table set -- launches that share a downsampler must be stream-ordered)
+  acc_t* loss_acc; unsigned int* loss_ticket;
 };
 int launch_downsample_fwd(const float* x, float* y, int C, int H, int W, int oh, int ow, DsTables t, cudaStream_t s);
 int launch_downsample_bwd(const float* gy, float* gx, int C, int H, int W, int oh, int ow, DsTables t, cudaStream_t s);

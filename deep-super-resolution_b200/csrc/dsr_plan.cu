@@ -80,7 +80,7 @@ struct ConvLayer {
   Buf raw;                         // fp16 plain [outH][outW][128]
   Buf act;                         // fp16 padded [outH+2][outW+2][128]
   int act_halo = 0;                // write the reflected halo of `act`
-  size_t stats_off = 0;            // floats into the accumulator block: [2][128] forward sums
+  size_t stats_off = 0;            // acc_t index from the workspace base: [2][128] forward sums (fixed point)
   size_t bstats_off = 0;           // [2][128] backward sums
   Buf dr;                          // fp16 padded [outH+2][outW+2][128]   gradient w.r.t. raw
   Buf gin;                         // fp16 padded [inH+2][inW+2][n_rows]  data gradient (to fold)
@@ -107,8 +107,9 @@ struct Level {
   const Buf* x_pad = nullptr;       // fp16 padded [H+2][W+2][Cin]
   Buf sraw;                         // fp32 [H][W][4]
   Buf cat;                          // fp16 padded [H+2][W+2][144]
-  size_t skip_stats_off = 0, cat_stats_off = 0;     // forward accumulators ([2][4], [2][144])
+  size_t skip_stats_off = 0, cat_stats_off = 0;     // forward accumulators ([2][4], [2][144]), acc_t indices
   size_t sbstats_off = 0, cbstats_off = 0;          // backward accumulators
+  size_t skip_dw_acc = 0;                           // backward: S * d(skip conv weight) [4][Cin], fixed point
   Buf g_u2a;                        // fp16 padded [H+2][W+2][128]: gradient w.r.t. this level's output
   Buf dup;                          // fp16 padded [H+2][W+2][128]
   Buf dsy, dsraw;                   // fp32 [H][W][4]
@@ -122,6 +123,8 @@ using namespace dsr;
 
 struct dsr_downsampler {
   int factor, support, H, W, oh, ow, k, pad, nw_y, nw_x;
+  unsigned long long serial = 0;   // unique per created object: a graph captured for a destroyed downsampler is never
+                                   // replayed for a new one that happens to land at the same host address
   std::vector<float> taps;
   std::vector<int> by0, bx0;
   std::vector<float> bwy, bwx;
@@ -137,11 +140,19 @@ struct dsr_plan {
   long long fin_w = 0, fin_b = 0;
   // workspace
   size_t ws_bytes = 0;
-  size_t acc_fwd_off = 0, acc_fwd_floats = 0;     // zeroed at the start of every forward
-  size_t acc_bwd_off = 0, acc_bwd_floats = 0;     // zeroed at the start of every backward (incl. wgrad arena)
-  size_t garena_off = 0;                          // floats, inside the backward accumulator block
+  size_t acc_fwd_off = 0, acc_fwd_bytes = 0;      // zeroed at the start of every forward (fixed-point accumulators)
+  size_t acc_bwd_off = 0, acc_bwd_bytes = 0;      // zeroed at the start of every backward (incl. the fp32 wgrad arena)
+  size_t garena_off = 0;                          // FLOAT index from the workspace base, inside the backward block
+  size_t fin_dw_acc = 0;                          // acc_t index: S * d(final conv weight [3][128], bias [3]) at +384
+  Buf small_table;                                // SmallGradDesc[]: fixed-point small-layer gradients -> flat gradients
+  std::vector<SmallGradDesc> small_host;
   Buf warena;                                     // packed 16-bit weights
   Buf pack_table, bnrun_table, errword, gscale, stepstate;
+  // DSR_DETERMINISTIC=1: the split-K weight-gradient kernels store per-split partials here (plain stores) and a
+  // second kernel adds them in split order, instead of fp32 atomics whose order varies from run to run.  With the
+  // fixed-point statistics (dsr_acc.cuh) two runs of one binary are then bit-identical.
+  int det = 0;
+  Buf wg_part;
   Buf g_final;                                    // unused placeholder (level 0 g_u2a is the final-conv gradient)
   std::vector<PackDesc> pack_host;
   std::vector<BnRunDesc> bnrun_host;
@@ -161,6 +172,7 @@ struct dsr_plan {
   cudaGraphExec_t graph_exec = nullptr;
   dsr_step_buffers_t graph_bufs{};
   const dsr_downsampler* graph_ds = nullptr;
+  unsigned long long graph_ds_serial = 0;
   float graph_lr = 0.f, graph_sigma = 0.f;
   unsigned long long graph_seed = 0;
   int use_graph = 1;
@@ -199,10 +211,10 @@ struct Bump {
     b.bytes = bytes;
     off += bytes;
   }
-  size_t take_floats(size_t n) {   // returns a float index
+  size_t take_acc(size_t n) {      // n fixed-point accumulators (acc_t); returns an acc_t index
     off = align_up(off, 1024);
-    const size_t r = off / 4;
-    off += n * 4;
+    const size_t r = off / sizeof(acc_t);
+    off += n * sizeof(acc_t);
     return r;
   }
 };
@@ -282,8 +294,8 @@ void setup_conv(dsr_plan* p, Bump& ws, Bump& accf, Bump& accb, ConvLayer& c, con
   ws.take(c.act, (static_cast<size_t>(c.outH + 3) * (c.outW + 2) + 1) * kNC * 2);
   ws.take(c.dr, static_cast<size_t>(c.outH + 2) * (c.outW + 2) * kNC * 2);
   if (need_dgrad) ws.take(c.gin, static_cast<size_t>(inH + 2) * (inW + 2) * c.n_rows * 2);
-  c.stats_off = accf.take_floats(2 * kNC);
-  c.bstats_off = accb.take_floats(2 * kNC);
+  c.stats_off = accf.take_acc(2 * kNC);
+  c.bstats_off = accb.take_acc(2 * kNC);
   const int taps = k * k;
   c.pack.w_off = c.w_off;
   c.pack.cout = kNC;
@@ -325,7 +337,7 @@ void push_kblocks(ConvGemmParams& g, int c_total, int px, int dx, int py, int dy
 // Builds the launch descriptions of one conv layer (needs resolved pointers).
 int build_conv(dsr_plan* p, ConvLayer& c) {
   __half* warena = static_cast<__half*>(p->warena.ptr);
-  float* acc = reinterpret_cast<float*>(p->base);
+  acc_t* acc = reinterpret_cast<acc_t*>(p->base);
   int rc;
   // ---------------- fprop ----------------
   {
@@ -510,9 +522,16 @@ int build_conv(dsr_plan* p, ConvLayer& c) {
     if (nsplit > npb / kWgMinBlocks) nsplit = npb / kWgMinBlocks;
     if (nsplit > npb) nsplit = npb;
     if (nsplit < 1) nsplit = 1;
-    g.nsplit = nsplit;
     g.ldw = c.cin_pad;
-    g.dw = acc + p->garena_off + c.pack.g_off;
+    g.dw = reinterpret_cast<float*>(p->base) + p->garena_off + c.pack.g_off;
+    g.part_stride = static_cast<long long>(c.k) * c.k * kNC * c.cin_pad;
+    g.part = nullptr;
+    if (p->det) {
+      g.part = static_cast<float*>(p->wg_part.ptr);
+      const long long cap = static_cast<long long>(p->wg_part.bytes / 4) / g.part_stride;
+      if (nsplit > cap) nsplit = static_cast<int>(cap);
+    }
+    g.nsplit = nsplit;
     g.idesc64 = make_idesc_f16(128, 128, FMT_F16, FMT_F16, 1, 1);
     g.idesc16 = make_idesc_f16(128, 16 * (g.n16 > 0 ? g.n16 : 1), FMT_F16, FMT_F16, 1, 1);   // n16 chunks, LBO apart
     g.err = static_cast<int*>(p->errword.ptr);
@@ -620,6 +639,12 @@ int build_conv(dsr_plan* p, ConvLayer& c) {
     if (nsplit > npb / kWgMinBlocks) nsplit = npb / kWgMinBlocks;
     if (nsplit > npb) nsplit = npb;
     if (nsplit < 1) nsplit = 1;
+    g.part_stride = o.part_stride;
+    g.part = o.part;
+    if (p->det) {
+      const long long cap = static_cast<long long>(p->wg_part.bytes / 4) / g.part_stride;
+      if (nsplit > cap) nsplit = static_cast<int>(cap);
+    }
     g.nsplit = nsplit;
   }
   // ---------------- halo-tile variants ----------------
@@ -744,7 +769,7 @@ int build_conv(dsr_plan* p, ConvLayer& c) {
 
 BnRef conv_bn(const dsr_plan* p, const ConvLayer& c, const float* params) {
   BnRef b;
-  b.stats = reinterpret_cast<const float*>(p->base) + c.stats_off;
+  b.stats = reinterpret_cast<const acc_t*>(p->base) + c.stats_off;
   b.gamma = params + c.g_off;
   b.beta = params + c.be_off;
   b.inv_n = 1.f / (static_cast<float>(c.outH) * static_cast<float>(c.outW));
@@ -753,7 +778,7 @@ BnRef conv_bn(const dsr_plan* p, const ConvLayer& c, const float* params) {
 }
 BnRef skip_bn(const dsr_plan* p, const Level& L, const float* params) {
   BnRef b;
-  b.stats = reinterpret_cast<const float*>(p->base) + L.skip_stats_off;
+  b.stats = reinterpret_cast<const acc_t*>(p->base) + L.skip_stats_off;
   b.gamma = params + L.skip_g;
   b.beta = params + L.skip_be;
   b.inv_n = 1.f / (static_cast<float>(L.H) * static_cast<float>(L.W));
@@ -833,7 +858,7 @@ int conv_bn_act(dsr_plan* p, ConvLayer& c, const float* params, cudaStream_t s, 
   if (next != nullptr && p->fuse_skip) {
     DSR_TRY(launch_bn_act(c.raw.ptr, conv_bn(p, c, params), c.act.ptr, c.outH, c.outW, c.act_halo, s,
                           params + next->skip_w, static_cast<float*>(next->sraw.ptr),
-                          reinterpret_cast<float*>(p->base) + next->skip_stats_off));
+                          reinterpret_cast<acc_t*>(p->base) + next->skip_stats_off));
   } else {
     DSR_TRY(launch_bn_act(c.raw.ptr, conv_bn(p, c, params), c.act.ptr, c.outH, c.outW, c.act_halo, s));
   }
@@ -853,7 +878,7 @@ UpcatArgs upcat_args(dsr_plan* p, int i, const float* params) {
   a.W = L.W;
   a.sraw = static_cast<const float*>(L.sraw.ptr);
   a.bn_skip = skip_bn(p, L, params);
-  a.cat_stats = reinterpret_cast<float*>(p->base) + L.cat_stats_off;
+  a.cat_stats = reinterpret_cast<acc_t*>(p->base) + L.cat_stats_off;
   a.cat_gamma = params + L.cat_g;
   a.cat_beta = params + L.cat_be;
   a.cat_pad = L.cat.ptr;
@@ -864,7 +889,7 @@ UpcatArgs upcat_args(dsr_plan* p, int i, const float* params) {
 
 int forward_level(dsr_plan* p, int i, const float* params, cudaStream_t s) {
   Level& L = p->lv[i];
-  float* acc = reinterpret_cast<float*>(p->base);
+  acc_t* acc = reinterpret_cast<acc_t*>(p->base);
   if (!p->fuse_skip || (i == 0 && !input_pack_fast(L.Cin, L.W)))   // otherwise produced by the pass that wrote this level's input
     DSR_TRY(launch_skip_conv(L.x_pad->ptr, L.Cin, params + L.skip_w, static_cast<float*>(L.sraw.ptr),
                              acc + L.skip_stats_off, L.H, L.W, s));
@@ -897,16 +922,16 @@ int bn_backward(dsr_plan* p, ConvLayer& c, const float* params, float* grads, co
     a.dsy = static_cast<const float*>(next->dsy.ptr);
     a.sraw = static_cast<const float*>(next->sraw.ptr);
     a.bn_skip = skip_bn(p, *next, params);
-    a.sbstats = reinterpret_cast<float*>(p->base) + next->sbstats_off;
+    a.sbstats = reinterpret_cast<acc_t*>(p->base) + next->sbstats_off;
     a.wskip = params + next->skip_w;
-    a.dwskip = grads + next->skip_w;
+    a.dwskip = reinterpret_cast<acc_t*>(p->base) + next->skip_dw_acc;
     a.dskip_gamma = grads + next->skip_g;
     a.dskip_beta = grads + next->skip_be;
     a.dsraw = static_cast<float*>(next->dsraw.ptr);
   }
   a.raw = c.raw.ptr;
   a.bn = conv_bn(p, c, params);
-  a.bstats = reinterpret_cast<float*>(p->base) + c.bstats_off;
+  a.bstats = reinterpret_cast<acc_t*>(p->base) + c.bstats_off;
   a.dr_pad = c.dr.ptr;
   a.dgamma = grads + c.g_off;
   a.dbeta = grads + c.be_off;
@@ -939,7 +964,7 @@ int conv_backward(dsr_plan* p, ConvLayer& c, cudaStream_t s) {
 int backward_level(dsr_plan* p, int i, const float* params, float* grads, cudaStream_t s) {
   Level& L = p->lv[i];
   const bool last = (i + 1 == p->num_scales);
-  float* acc = reinterpret_cast<float*>(p->base);
+  acc_t* acc = reinterpret_cast<acc_t*>(p->base);
   int rc;
   // ---- decoder ----
   if (!(i == 0 && p->fuse_top) &&        // level 0: done by the fused top kernels (dsr_net_backward)
@@ -978,7 +1003,7 @@ int backward_level(dsr_plan* p, int i, const float* params, float* grads, cudaSt
   if (i == 0)       // levels >= 1: the skip branch's backward rides on the BN backward of the activation it reads
   DSR_TRY(launch_skip_bwd(static_cast<const float*>(L.dsy.ptr), static_cast<const float*>(L.sraw.ptr),
                           skip_bn(p, L, params), acc + L.sbstats_off, L.x_pad->ptr, L.Cin,
-                          static_cast<float*>(L.dsraw.ptr), grads + L.skip_w, grads + L.skip_g, grads + L.skip_be,
+                          static_cast<float*>(L.dsraw.ptr), acc + L.skip_dw_acc, grads + L.skip_g, grads + L.skip_be,
                           static_cast<const float*>(p->gscale.ptr), L.H, L.W, s));
   if (!p->lowres_upcat) DSR_TRY(launch_upsample_bwd(L.dup.ptr, L.H, L.W, ddeep, L.h, L.w, s));
   if (!last && (rc = backward_level(p, i + 1, params, grads, s))) return rc;
@@ -999,8 +1024,9 @@ int backward_level(dsr_plan* p, int i, const float* params, float* grads, cudaSt
 void reg_tensor(dsr_plan* p, const std::string& name, const Buf* b, int kind, int padded, int H, int W, int C) {
   p->tensors.push_back(TensorInfo{name, b, 0, kind, padded, H, W, C});
 }
-void reg_acc(dsr_plan* p, const std::string& name, size_t acc_off, int H, int W, int C) {
-  p->tensors.push_back(TensorInfo{name, nullptr, acc_off, 2, 0, H, W, C});
+// acc_off: FLOAT index from the workspace base (fixed-point accumulators: 2 x their acc_t index)
+void reg_acc(dsr_plan* p, const std::string& name, size_t acc_off, int H, int W, int C, int kind = 2) {
+  p->tensors.push_back(TensorInfo{name, nullptr, acc_off, kind, 0, H, W, C});
 }
 
 }  // namespace
@@ -1067,7 +1093,7 @@ size_t dsr_downsampler_table_bytes(int factor, int support, int H, int W) {
   if (ds_geometry(factor, support, H, W, k, pad, oh, ow)) return 0;
   // generous bound: taps + per-row / per-column (index + up to k/f + 2 weights)
   const size_t nwmax = static_cast<size_t>(k) + 2;
-  return 1024 + 4 * (static_cast<size_t>(k) + (H + W) * (1 + nwmax));
+  return 1024 + 64 + 4 * (static_cast<size_t>(k) + (H + W) * (1 + nwmax));
 }
 
 int dsr_downsampler_create(dsr_downsampler_t** out, int factor, int support, int H, int W, void* table_ws,
@@ -1076,6 +1102,10 @@ int dsr_downsampler_create(dsr_downsampler_t** out, int factor, int support, int
   int k, pad, oh, ow;
   if (ds_geometry(factor, support, H, W, k, pad, oh, ow)) return -1;
   dsr_downsampler* d = new dsr_downsampler();
+  {
+    static unsigned long long next_serial = 0;
+    d->serial = __atomic_add_fetch(&next_serial, 1ull, __ATOMIC_RELAXED);
+  }
   d->factor = factor; d->support = support; d->H = H; d->W = W; d->oh = oh; d->ow = ow; d->k = k; d->pad = pad;
   std::vector<double> t64;
   lanczos_taps(factor, support, t64);
@@ -1096,11 +1126,15 @@ int dsr_downsampler_create(dsr_downsampler_t** out, int factor, int support, int
   };
   widen(d->bwy, H, d->nw_y);
   widen(d->bwx, W, d->nw_x);
-  const size_t need = 4 * (static_cast<size_t>(k) + H + W + static_cast<size_t>(H + W) * nw) + 256;
+  const size_t need = 4 * (static_cast<size_t>(k) + H + W + static_cast<size_t>(H + W) * nw) + 256 + 64;
   if (need > table_bytes) { delete d; return -8; }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   char* base = static_cast<char*>(table_ws);
-  size_t off = 0;
+  if (reinterpret_cast<uintptr_t>(base) & 15) { delete d; return -3; }
+  cudaMemsetAsync(base, 0, 64, s);                 // loss accumulator + ticket of the fused-MSE kernel
+  d->t.loss_acc = reinterpret_cast<acc_t*>(base);
+  d->t.loss_ticket = reinterpret_cast<unsigned int*>(base + 16);
+  size_t off = 64;
   auto put = [&](const void* src, size_t bytes) -> void* {
     void* dst = base + off;
     cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s);
@@ -1185,10 +1219,11 @@ int dsr_plan_create(dsr_plan_t** out, int H, int W, int input_depth, int num_sca
     ws.take(L.dsy, static_cast<size_t>(L.H) * L.W * kNS * 4);
     ws.take(L.dsraw, static_cast<size_t>(L.H) * L.W * kNS * 4);
     if (last) ws.take(L.g_d2a, static_cast<size_t>(L.h + 2) * (L.w + 2) * kNC * 2);
-    L.skip_stats_off = accf.take_floats(2 * kNS);
-    L.cat_stats_off = accf.take_floats(2 * kCat);
-    L.sbstats_off = accb.take_floats(2 * kNS);
-    L.cbstats_off = accb.take_floats(2 * kCat);
+    L.skip_stats_off = accf.take_acc(2 * kNS);
+    L.cat_stats_off = accf.take_acc(2 * kCat);
+    L.sbstats_off = accb.take_acc(2 * kNS);
+    L.cbstats_off = accb.take_acc(2 * kCat);
+    L.skip_dw_acc = accb.take_acc(static_cast<size_t>(kNS) * L.Cin);
     setup_conv(p, ws, accf, accb, L.d1, "d1", L.Cin, L.Cin, 3, 2, L.H, L.W, L.x_pad, i > 0, 1, 0, warena_elems,
                garena_floats);
     setup_conv(p, ws, accf, accb, L.d2, "d2", kNC, kNC, 3, 1, L.h, L.w, &L.d1.act, true, 1, 0, warena_elems,
@@ -1199,27 +1234,44 @@ int dsr_plan_create(dsr_plan_t** out, int H, int W, int input_depth, int num_sca
                garena_floats);
   }
   ws.take(p->warena, warena_elems * 2);
+  p->det = (getenv("DSR_DETERMINISTIC") && atoi(getenv("DSR_DETERMINISTIC"))) ? 1 : 0;
+  if (p->det) {
+    // room for the per-split partials of the largest layer: up to 160 / groups splits of [taps][128][cin_pad] floats
+    size_t need = 0;
+    for (Level& L : p->lv)
+      for (ConvLayer* c : {&L.d1, &L.d2, &L.u1, &L.u2}) {
+        const size_t npb = static_cast<size_t>((c->outW + 7) / 8) * ((c->outH + 7) / 8);
+        size_t splits = 160 / (c->k == 1 ? 1 : 3);
+        if (splits > npb) splits = npb;
+        const size_t b = splits * c->k * c->k * kNC * c->cin_pad * 4;
+        if (b > need) need = b;
+      }
+    ws.take(p->wg_part, need);
+  }
   ws.take(p->pack_table, sizeof(PackDesc) * 4 * num_scales);
   ws.take(p->bnrun_table, sizeof(BnRunDesc) * 6 * num_scales);
+  ws.take(p->small_table, sizeof(SmallGradDesc) * (num_scales + 2));
   ws.take(p->errword, 256);
   ws.take(p->gscale, 256);
   ws.take(p->stepstate, 256);
   // place the accumulator blocks
   ws.off = align_up(ws.off, 1024);
+  p->fin_dw_acc = accb.take_acc(3 * kNC + 8);
   p->acc_fwd_off = ws.off;
-  p->acc_fwd_floats = align_up(accf.off, 1024) / 4;
-  ws.off += p->acc_fwd_floats * 4;
+  p->acc_fwd_bytes = align_up(accf.off, 1024);
+  ws.off += p->acc_fwd_bytes;
   p->acc_bwd_off = ws.off;
-  const size_t accb_floats = align_up(accb.off, 1024) / 4;
-  p->garena_off = p->acc_bwd_off / 4 + accb_floats;
-  p->acc_bwd_floats = accb_floats + garena_floats;
-  ws.off += p->acc_bwd_floats * 4;
+  const size_t accb_bytes = align_up(accb.off, 1024);
+  p->garena_off = (p->acc_bwd_off + accb_bytes) / 4;
+  p->acc_bwd_bytes = accb_bytes + garena_floats * 4;
+  ws.off += p->acc_bwd_bytes;
   p->ws_bytes = align_up(ws.off, 1024);
   // rebase accumulator indices to the workspace base
-  const size_t fbase = p->acc_fwd_off / 4, bbase = p->acc_bwd_off / 4;
+  const size_t fbase = p->acc_fwd_off / sizeof(acc_t), bbase = p->acc_bwd_off / sizeof(acc_t);
+  p->fin_dw_acc += bbase;
   for (Level& L : p->lv) {
     L.skip_stats_off += fbase; L.cat_stats_off += fbase;
-    L.sbstats_off += bbase; L.cbstats_off += bbase;
+    L.sbstats_off += bbase; L.cbstats_off += bbase; L.skip_dw_acc += bbase;
     for (ConvLayer* c : {&L.d1, &L.d2, &L.u1, &L.u2}) { c->stats_off += fbase; c->bstats_off += bbase; }
   }
   // tables
@@ -1242,6 +1294,11 @@ int dsr_plan_create(dsr_plan_t** out, int H, int W, int input_depth, int num_sca
     for (ConvLayer* c : {&L.d1, &L.d2, &L.u1, &L.u2})
       add_run(c->stats_off, kNC, kNC, static_cast<float>(c->outH) * c->outW, c->bn_off, c->b_off, 0);
   }
+  // small-layer gradients accumulated in fixed point by the element-wise kernels
+  for (Level& L : p->lv)
+    p->small_host.push_back(SmallGradDesc{static_cast<long long>(L.skip_dw_acc), L.skip_w, kNS * L.Cin, 0});
+  p->small_host.push_back(SmallGradDesc{static_cast<long long>(p->fin_dw_acc), p->fin_w, n_out * kNC, 0});
+  p->small_host.push_back(SmallGradDesc{static_cast<long long>(p->fin_dw_acc) + 3 * kNC, p->fin_b, n_out, 0});
   // introspection table
   for (int i = 0; i < num_scales; ++i) {
     Level& L = p->lv[i];
@@ -1261,7 +1318,7 @@ int dsr_plan_create(dsr_plan_t** out, int H, int W, int input_depth, int num_sca
       reg_tensor(p, T + "_act", &c->act, 0, 1, c->outH, c->outW, kNC);
       reg_tensor(p, T + "_dr", &c->dr, 0, 1, c->outH, c->outW, kNC);
       if (c->need_dgrad) reg_tensor(p, T + "_gin", &c->gin, 0, 1, c->inH, c->inW, c->n_rows);
-      reg_acc(p, T + "_stats", c->stats_off, 1, 2, kNC);
+      reg_acc(p, T + "_stats", c->stats_off * 2, 1, 2, kNC, 3);      // kind 3: 64-bit fixed point, forward scale
       reg_acc(p, T + "_dw", p->garena_off + c->pack.g_off, c->k * c->k, kNC, c->cin_pad);
     }
   }
@@ -1311,6 +1368,9 @@ int dsr_plan_bind(dsr_plan_t* p, void* workspace, size_t bytes, void* stream) {
   if (bytes < p->ws_bytes) return -8;
   if (reinterpret_cast<uintptr_t>(workspace) & 1023) return -3;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (p->graph_exec) { cudaGraphExecDestroy(p->graph_exec); p->graph_exec = nullptr; }     // captured pointers are stale
+  for (auto& g : p->pass_graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+  p->pass_graphs.clear();
   p->base = static_cast<char*>(workspace);
   cudaError_t e = cudaMemsetAsync(workspace, 0, p->ws_bytes, s);   // zero halos of gradient tensors, pad channels
   if (e != cudaSuccess) return static_cast<int>(e);
@@ -1324,11 +1384,14 @@ int dsr_plan_bind(dsr_plan_t* p, void* workspace, size_t bytes, void* stream) {
     resolve(L.dsraw); resolve(L.g_d2a);
     for (ConvLayer* c : {&L.d1, &L.d2, &L.u1, &L.u2}) { resolve(c->raw); resolve(c->act); resolve(c->dr); resolve(c->gin); }
   }
-  resolve(p->warena); resolve(p->pack_table); resolve(p->bnrun_table); resolve(p->errword); resolve(p->gscale); resolve(p->stepstate);
+  resolve(p->warena); resolve(p->pack_table); resolve(p->bnrun_table); resolve(p->small_table); resolve(p->wg_part); resolve(p->errword); resolve(p->gscale); resolve(p->stepstate);
   e = cudaMemcpyAsync(p->pack_table.ptr, p->pack_host.data(), sizeof(PackDesc) * p->pack_host.size(),
                       cudaMemcpyHostToDevice, s);
   if (e != cudaSuccess) return static_cast<int>(e);
   e = cudaMemcpyAsync(p->bnrun_table.ptr, p->bnrun_host.data(), sizeof(BnRunDesc) * p->bnrun_host.size(),
+                      cudaMemcpyHostToDevice, s);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  e = cudaMemcpyAsync(p->small_table.ptr, p->small_host.data(), sizeof(SmallGradDesc) * p->small_host.size(),
                       cudaMemcpyHostToDevice, s);
   if (e != cudaSuccess) return static_cast<int>(e);
   const float gs0[8] = {65536.f, 1.f / 65536.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // initial gradient scale 2^16
@@ -1363,7 +1426,7 @@ static int net_forward_impl(dsr_plan_t* p, const float* params, const float* z, 
                             void* stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   p->launches = 0;
-  cudaError_t e = cudaMemsetAsync(p->base + p->acc_fwd_off, 0, p->acc_fwd_floats * 4, s);
+  cudaError_t e = cudaMemsetAsync(p->base + p->acc_fwd_off, 0, p->acc_fwd_bytes, s);
   if (e != cudaSuccess) return static_cast<int>(e);
   // The fp16 weight packing (25 us) depends only on the parameters and the input packing (29 us) only on z and the
   // fp32 skip weights: they run side by side (pack on the side stream, joined before the first convolution).
@@ -1392,7 +1455,7 @@ static int net_forward_impl(dsr_plan_t* p, const float* params, const float* z, 
       DSR_TRY(launch_perturb(p->pz_saved, zw, nz, p->psigma, p->pseed, 0, s, static_cast<float*>(p->stepstate.ptr)));
     DSR_TRY(launch_input_pack(zw, L0.xin.ptr, L0.Cin, L0.H, L0.W, s, fskip ? params + L0.skip_w : nullptr,
                               fskip ? static_cast<float*>(L0.sraw.ptr) : nullptr,
-                              fskip ? reinterpret_cast<float*>(p->base) + L0.skip_stats_off : nullptr,
+                              fskip ? reinterpret_cast<acc_t*>(p->base) + L0.skip_stats_off : nullptr,
                               fast ? p->pz_saved : nullptr, p->psigma, p->pseed,
                               static_cast<const float*>(p->stepstate.ptr)));
   }
@@ -1409,7 +1472,7 @@ static int net_forward_impl(dsr_plan_t* p, const float* params, const float* z, 
     DSR_TRY(launch_final_conv(L0.u2.act.ptr, params + p->fin_w, params + p->fin_b, out, L0.H, L0.W, s));
   if (bn_buffers != nullptr)
     DSR_TRY(launch_bn_running(static_cast<const BnRunDesc*>(p->bnrun_table.ptr), static_cast<int>(p->bnrun_host.size()),
-                              reinterpret_cast<const float*>(p->base), params, bn_buffers, kMomentum, s));
+                              reinterpret_cast<const acc_t*>(p->base), params, bn_buffers, kMomentum, s));
   p->have_forward = true;
   return 0;
 }
@@ -1418,7 +1481,7 @@ static int net_backward_impl(dsr_plan_t* p, const float* params, const float* ou
                              void* stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   p->launches = 0;
-  cudaError_t e = cudaMemsetAsync(p->base + p->acc_bwd_off, 0, p->acc_bwd_floats * 4, s);
+  cudaError_t e = cudaMemsetAsync(p->base + p->acc_bwd_off, 0, p->acc_bwd_bytes, s);
   if (e != cudaSuccess) return static_cast<int>(e);
   e = cudaMemsetAsync(grads, 0, static_cast<size_t>(p->nparam) * 4, s);
   if (e != cudaSuccess) return static_cast<int>(e);
@@ -1430,20 +1493,22 @@ static int net_backward_impl(dsr_plan_t* p, const float* params, const float* ou
     ta.raw = L0.u2.raw.ptr;
     ta.bn = conv_bn(p, L0.u2, params);
     ta.w = params + p->fin_w;
-    ta.bstats = reinterpret_cast<float*>(p->base) + L0.u2.bstats_off;
+    ta.bstats = reinterpret_cast<acc_t*>(p->base) + L0.u2.bstats_off;
     ta.dr_pad = L0.u2.dr.ptr;
     ta.dgamma = grads + L0.u2.g_off;
     ta.dbeta = grads + L0.u2.be_off;
-    ta.dw = grads + p->fin_w;
-    ta.db = grads + p->fin_b;
+    ta.dw = reinterpret_cast<acc_t*>(p->base) + p->fin_dw_acc;
+    ta.db = ta.dw + 3 * kNC;
     ta.gs = static_cast<float*>(p->gscale.ptr);
     ta.H = L0.H;
     ta.W = L0.W;
     DSR_TRY(launch_bn_bwd_top_stats(ta, s));
     DSR_TRY(launch_bn_bwd_top_apply(ta, s));
   } else {
-    DSR_TRY(launch_final_bwd(grad_out, out, L0.u2.act.ptr, params + p->fin_w, L0.g_u2a.ptr, grads + p->fin_w,
-                             grads + p->fin_b, static_cast<const float*>(p->gscale.ptr), L0.H, L0.W, s));
+    DSR_TRY(launch_final_bwd(grad_out, out, L0.u2.act.ptr, params + p->fin_w, L0.g_u2a.ptr,
+                             reinterpret_cast<acc_t*>(p->base) + p->fin_dw_acc,
+                             reinterpret_cast<acc_t*>(p->base) + p->fin_dw_acc + 3 * kNC,
+                             static_cast<const float*>(p->gscale.ptr), L0.H, L0.W, s));
   }
   if (p->side != nullptr && p->use_side && p->profile != 2) {     // the side stream must see the zeroed accumulators
     e = cudaEventRecord(p->ev_fork, s);
@@ -1462,6 +1527,9 @@ static int net_backward_impl(dsr_plan_t* p, const float* params, const float* ou
   DSR_TRY(launch_unpack_wgrad(reinterpret_cast<const float*>(p->base) + p->garena_off, grads,
                               static_cast<const PackDesc*>(p->pack_table.ptr), static_cast<int>(p->pack_host.size()),
                               static_cast<const float*>(p->gscale.ptr), s));
+  DSR_TRY(launch_small_grads_finish(static_cast<const SmallGradDesc*>(p->small_table.ptr),
+                                    static_cast<int>(p->small_host.size()), reinterpret_cast<const acc_t*>(p->base), grads,
+                                    static_cast<const float*>(p->gscale.ptr), s));
   DSR_TRY(launch_grad_scale_finish(grads, p->nparam, static_cast<float*>(p->gscale.ptr), s));
   ++p->launches;
   return 0;
@@ -1544,7 +1612,7 @@ static int enqueue_step(dsr_plan_t* p, const dsr_downsampler_t* d, const dsr_ste
   const long long nz = static_cast<long long>(p->input_depth) * p->H * p->W;
   int total = 0;
   if (timeline_enabled()) g_timeline.n = 0;          // every (eager or captured) iteration stamps slots 0 .. n - 1
-  int rc = launch_step_begin(st, losses, t_set, lr, 0.9f, 0.999f, s);
+  int rc = launch_step_begin(st, losses, t_set, lr, 0.9f, 0.999f, s, static_cast<const float*>(p->gscale.ptr));
   if (rc) return rc;
   total += 1;
   p->in_step = 1;
@@ -1567,7 +1635,8 @@ static int enqueue_step(dsr_plan_t* p, const dsr_downsampler_t* d, const dsr_ste
   p->in_step = 0;
   if (rc) return rc;
   total += p->launches;
-  if ((rc = launch_adam(b->params, b->grads, b->adam_m, b->adam_v, p->nparam, lr, 0.9f, 0.999f, 1e-8f, 1, s, st)))
+  if ((rc = launch_adam(b->params, b->grads, b->adam_m, b->adam_v, p->nparam, lr, 0.9f, 0.999f, 1e-8f, 1, s, st,
+                        static_cast<const float*>(p->gscale.ptr))))
     return rc;
   p->launches = total + 1;
   return 0;
@@ -1591,6 +1660,7 @@ int dsr_dip_run(dsr_plan_t* p, const dsr_downsampler_t* d, const dsr_step_buffer
   float* losses = b->loss_out;           // base of the loss array: iteration t writes losses[t - 1]
   int done = 0;
   const bool same = p->graph_exec != nullptr && memcmp(&p->graph_bufs, b, sizeof(*b)) == 0 && p->graph_ds == d &&
+                    p->graph_ds_serial == d->serial &&
                     p->graph_lr == lr && p->graph_sigma == sigma && p->graph_seed == seed;
   // the legacy default stream cannot be captured: callers that want graph replay pass a non-default stream
   const bool capturable = (s != nullptr && s != cudaStreamLegacy && s != cudaStreamPerThread);
@@ -1620,6 +1690,7 @@ int dsr_dip_run(dsr_plan_t* p, const dsr_downsampler_t* d, const dsr_step_buffer
     if (e != cudaSuccess) { p->graph_exec = nullptr; return static_cast<int>(e); }
     p->graph_bufs = *b;
     p->graph_ds = d;
+    p->graph_ds_serial = d->serial;
     p->graph_lr = lr;
     p->graph_sigma = sigma;
     p->graph_seed = seed;
@@ -1704,7 +1775,7 @@ int dsr_plan_debug_replay(dsr_plan_t* p, const char* layer, int what, int use_ch
       int rc = 0;
       float* acc = reinterpret_cast<float*>(p->base);
       if (what == 0) {
-        cudaMemsetAsync(acc + c->stats_off, 0, 2 * kNC * 4, s);
+        cudaMemsetAsync(reinterpret_cast<acc_t*>(p->base) + c->stats_off, 0, 2 * kNC * sizeof(acc_t), s);
         rc = run_fprop(p, *c, s);
       } else if (what == 1) {
         if (!c->need_dgrad) rc = -1;

@@ -262,11 +262,12 @@ class SkipNet(nn.Module):
         ptr, kind, padded, H, W, Cc = C.c_void_p(), C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_int()
         check(lib.dsr_plan_tensor(plan.handle, name.encode(), C.byref(ptr), C.byref(kind), C.byref(padded), C.byref(H),
                                   C.byref(W), C.byref(Cc)), f'dsr_plan_tensor({name})')
-        dt = {0: torch.float16, 1: torch.bfloat16, 2: torch.float32}[kind.value]
+        # kind 3: 64-bit fixed-point accumulators (csrc/dsr_acc.cuh, forward scale 2^-20), returned as float64
+        dt = {0: torch.float16, 1: torch.bfloat16, 2: torch.float32, 3: torch.int64}[kind.value]
         hh, ww = (H.value + 2, W.value + 2) if padded.value else (H.value, W.value)
         t = torch.empty((hh, ww, Cc.value), dtype=dt, device=self._flat.device)
         check(lib.dsr_debug_copy(t.data_ptr(), ptr, t.numel() * t.element_size(), _lib.stream_ptr()), 'dsr_debug_copy')
-        return t
+        return t.double() / float(1 << 20) if kind.value == 3 else t
 
     def set_debug_conv(self, on: bool) -> None:
         for plan in self._plans.values():
