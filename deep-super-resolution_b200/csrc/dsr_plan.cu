@@ -1755,6 +1755,7 @@ int dsr_plan_tensor(const dsr_plan_t* p, const char* name, void** ptr, int* kind
   return -1;
 }
 int dsr_plan_last_launches(const dsr_plan_t* p) { return p ? p->launches : -1; }
+int dsr_plan_deterministic(const dsr_plan_t* p) { return p ? p->det : -1; }
 int dsr_plan_set_debug_conv(dsr_plan_t* p, int use_checker_kernels) {
   if (!p) return -1;
   // 0: product kernels; 1: CUDA-core checker kernels; 2: product path but with the generic implicit-GEMM kernel

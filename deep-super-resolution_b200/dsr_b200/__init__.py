@@ -10,3 +10,4 @@ from .downsampler import Downsampler, get_kernel     # noqa: F401
 from .optim import optimize, get_params, get_noise, fill_noise   # noqa: F401
 from .dip import DIP_ISR, dip_sr_fused                # noqa: F401
 from .gan import Generator                            # noqa: F401
+from .metrics import PeakSignalNoiseRatio, StructuralSimilarityIndexMeasure   # noqa: F401

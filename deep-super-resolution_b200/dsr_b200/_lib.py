@@ -80,6 +80,10 @@ SIGNATURES = {
     'dsr_gen_debug_tensor': (i32, [vp, C.c_char_p, C.POINTER(vp), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32),
                                    C.POINTER(i32)]),
     'dsr_gen_device_error': (i32, [vp, C.POINTER(i32)]),
+    'dsr_metric_workspace_bytes': (sz, []),
+    'dsr_psnr': (i32, [vp, vp, i64, f32, vp, vp, vp]),
+    'dsr_ssim': (i32, [vp, vp, i32, i32, i32, f32, vp, vp, vp]),
+    'dsr_plan_deterministic': (i32, [vp]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

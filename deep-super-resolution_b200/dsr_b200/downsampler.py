@@ -86,6 +86,10 @@ class Downsampler(nn.Module):
         self.n_planes, self.factor = int(n_planes), int(factor)
         self.support = 2 if kernel_type == 'lanczos2' else 3
         self.kernel = get_kernel(self.factor, 'lanczos', 0.5, 2 * self.support * self.factor + 1, support=self.support)
+        # The reference builds an nn.Conv2d here and overwrites its weights (utils/downsampler.py:44-46); its random
+        # initialisation consumes the global CPU generator between get_net and get_noise (DIP.py:29,32).  Draw the same
+        # numbers so that a run with the same torch.manual_seed sees the same net_input / noise as the reference.
+        nn.Conv2d(self.n_planes, self.n_planes, kernel_size=self.kernel.shape, stride=self.factor, padding=0)
         self.preserve_size = preserve_size
         self._tables: Dict[Tuple[int, int, str], _Tables] = {}
 

@@ -118,7 +118,8 @@ int dsr_dip_run(dsr_plan_t* p, const dsr_downsampler_t* d, const dsr_step_buffer
 
 /* ---- introspection for tests / profiling --------------------------------------------------
  * Named intermediate of the last forward/backward (e.g. "L0.d1_raw"): device pointer, element
- * kind (0 fp16, 1 bf16, 2 fp32), padded-grid flag, H, W, C.  Returns 0 or -1 if unknown. */
+ * kind (0 fp16, 1 bf16, 2 fp32, 3 = 64-bit fixed-point accumulator in 2^-20 units), padded-grid flag, H, W, C.
+ * Returns 0 or -1 if unknown. */
 int dsr_plan_tensor(const dsr_plan_t* p, const char* name, void** ptr, int* kind, int* padded, int* H, int* W,
                     int* C);
 /* Kernel launches enqueued by the last forward / backward / step call on this plan. */
@@ -177,6 +178,24 @@ int dsr_gen_last_launches(const dsr_gen_plan_t* p);
  * [b * img_rows, b * img_rows + H). */
 int dsr_gen_debug_tensor(const dsr_gen_plan_t* p, const char* name, void** ptr, int* rows, int* img_rows, int* H, int* W);
 int dsr_gen_device_error(dsr_gen_plan_t* p, int* host_code);
+
+/* ---- image-quality metrics of the logging branch (DIP.py:71-87,183-185) ---------------------------------
+ * Replace the torchmetrics objects DIP.py:157-158 constructs -- PeakSignalNoiseRatio() and
+ * StructuralSimilarityIndexMeasure(data_range=1.) (third-party torchmetrics, not part of the reference checkout;
+ * algorithm restated in csrc/dsr_metrics.cu) -- by one kernel launch each that leaves a
+ * single float on the device.  workspace: dsr_metric_workspace_bytes() bytes, zeroed once by the caller (the kernels
+ * re-arm it), 16-byte aligned, used by one launch at a time.  pred / target: fp32, same shape. */
+size_t dsr_metric_workspace_bytes(void);
+/* out[0] = 10 log10(range^2 / mean((pred - target)^2)); data_range <= 0: range = max(target) - min(min(target), 0)
+ * (torchmetrics' data_range=None on a single update). */
+int dsr_psnr(const float* pred, const float* target, long long n, float data_range, void* workspace, float* out,
+             void* stream);
+/* out[0] = mean SSIM over `planes` (batch x channels) H x W planes: 11 x 11 Gaussian window (sigma 1.5), k1 0.01,
+ * k2 0.03, averaged over the pixels whose window lies inside the image. */
+int dsr_ssim(const float* pred, const float* target, int planes, int H, int W, float data_range, void* workspace,
+             float* out, void* stream);
+/* 1 when the plan was created with DSR_DETERMINISTIC=1 (two-stage split-K weight gradients: bit-identical runs). */
+int dsr_plan_deterministic(const dsr_plan_t* p);
 
 #ifdef __cplusplus
 }

@@ -187,18 +187,49 @@ def dead_param_keys(num_scales: int = 5) -> List[str]:
 Quant = Optional[Callable[[Tensor, str], Tensor]]
 
 
+class _RoundSTE(torch.autograd.Function):
+    """Round to a 16-bit format in the forward pass, identity in the backward pass."""
+
+    @staticmethod
+    def forward(ctx, t, dtype):
+        return t.to(dtype).to(t.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, None
+
+
+def fp16_points(dtype: torch.dtype = torch.float16) -> Callable[[Tensor, str], Tensor]:
+    """Quantisation hook that rounds where the CUDA path stores 16-bit values (DESIGN.md "Numerics"): the operands of
+    the 20 tensor-core convolutions ('conv_in', 'conv_w'), their raw outputs -- the BatchNorm inputs, whose statistics
+    are taken from the rounded values ('raw') -- and every BatchNorm + LeakyReLU activation ('act': it feeds the
+    bilinear upsample as well as the next convolution).  The skip-branch and final 1x1 convolutions keep fp32
+    weights ('skip_w', 'final_w').  Gradients pass straight through the rounding (the CUDA backward pass
+    differentiates the same rounded forward values)."""
+    def q(t: Tensor, tag: str) -> Tensor:
+        if tag in ('skip_w', 'final_w'):
+            return t
+        return _RoundSTE.apply(t, dtype)
+    q.drop_bn_bias = True
+    return q
+
+
 def _q(q: Quant, t: Tensor, tag: str) -> Tensor:
     return t if q is None else q(t, tag)
 
 
-def _conv(x: Tensor, w: Tensor, b: Optional[Tensor], stride: int, q: Quant) -> Tensor:
+def _conv(x: Tensor, w: Tensor, b: Optional[Tensor], stride: int, q: Quant, w_tag: str = 'conv_w') -> Tensor:
     """conv() of models/DIP/utils.py:83-105 with pad='reflection': ReflectionPad2d((k-1)/2)
-    then Conv2d(padding=0)."""
+    then Conv2d(padding=0).  ``w_tag`` names the weight operand for the quantisation hook: 'conv_w' for the 20
+    tensor-core layers, 'skip_w' / 'final_w' for the small 1x1 layers (whose weights the CUDA path keeps in fp32)."""
     k = w.shape[-1]
     p = (k - 1) // 2
     if p:
         x = F.pad(x, (p, p, p, p), mode='reflect')
-    return F.conv2d(_q(q, x, 'conv_in'), _q(q, w, 'conv_w'), b, stride=stride)
+    if q is not None and getattr(q, 'drop_bn_bias', False) and w_tag == 'conv_w':
+        b = None      # a bias in front of a train-mode BatchNorm is cancelled by the mean subtraction; the CUDA kernels
+                      # never add it, so their 16-bit rounding of the raw output happens WITHOUT it
+    return F.conv2d(_q(q, x, 'conv_in'), _q(q, w, w_tag), b, stride=stride)
 
 
 def _bn(x: Tensor, g: Tensor, b: Tensor) -> Tensor:
@@ -236,21 +267,21 @@ def skip_forward(sd: Dict[str, Tensor], z: Tensor, num_scales: int = 5, quant: Q
         n = layer_names(i)
         P = lambda name: sd[name]
         # skip branch (skip.py:54-56)
-        s_raw = _conv(x, P(n['skip_conv'] + '.weight'), P(n['skip_conv'] + '.bias'), 1, quant)
+        s_raw = _conv(x, P(n['skip_conv'] + '.weight'), P(n['skip_conv'] + '.bias'), 1, quant, 'skip_w')
         s = _act(_bn(s_raw, P(n['skip_bn'] + '.weight'), P(n['skip_bn'] + '.bias')))
         # deeper branch (skip.py:60-66)
         d1_raw = _conv(x, P(n['d1_conv'] + '.weight'), P(n['d1_conv'] + '.bias'), 2, quant)
-        d1 = _act(_bn(_q(quant, d1_raw, 'raw'), P(n['d1_bn'] + '.weight'), P(n['d1_bn'] + '.bias')))
+        d1 = _q(quant, _act(_bn(_q(quant, d1_raw, 'raw'), P(n['d1_bn'] + '.weight'), P(n['d1_bn'] + '.bias'))), 'act')
         d2_raw = _conv(d1, P(n['d2_conv'] + '.weight'), P(n['d2_conv'] + '.bias'), 1, quant)
-        d2 = _act(_bn(_q(quant, d2_raw, 'raw'), P(n['d2_bn'] + '.weight'), P(n['d2_bn'] + '.bias')))
+        d2 = _q(quant, _act(_bn(_q(quant, d2_raw, 'raw'), P(n['d2_bn'] + '.weight'), P(n['d2_bn'] + '.bias'))), 'act')
         deep = rec(i + 1, d2) if i < num_scales - 1 else d2        # skip.py:70-75
         up = F.interpolate(deep, scale_factor=2, mode='bilinear')  # skip.py:77 (align_corners False)
         cat = _center_crop_cat(s, up)                              # Concat(1, skip, deeper), skip.py:47
         c = _bn(cat, P(n['cat_bn'] + '.weight'), P(n['cat_bn'] + '.bias'))   # skip.py:51
         u1_raw = _conv(c, P(n['u1_conv'] + '.weight'), P(n['u1_conv'] + '.bias'), 1, quant)
-        u1 = _act(_bn(_q(quant, u1_raw, 'raw'), P(n['u1_bn'] + '.weight'), P(n['u1_bn'] + '.bias')))
+        u1 = _q(quant, _act(_bn(_q(quant, u1_raw, 'raw'), P(n['u1_bn'] + '.weight'), P(n['u1_bn'] + '.bias'))), 'act')
         u2_raw = _conv(u1, P(n['u2_conv'] + '.weight'), P(n['u2_conv'] + '.bias'), 1, quant)
-        u2 = _act(_bn(_q(quant, u2_raw, 'raw'), P(n['u2_bn'] + '.weight'), P(n['u2_bn'] + '.bias')))
+        u2 = _q(quant, _act(_bn(_q(quant, u2_raw, 'raw'), P(n['u2_bn'] + '.weight'), P(n['u2_bn'] + '.bias'))), 'act')
         if taps is not None:
             for k_, v_ in (('skip_raw', s_raw), ('d1_raw', d1_raw), ('d2_raw', d2_raw), ('x_next', d2),
                            ('up', up), ('cat', c), ('u1_raw', u1_raw), ('u2_raw', u2_raw), ('out', u2)):
@@ -258,7 +289,7 @@ def skip_forward(sd: Dict[str, Tensor], z: Tensor, num_scales: int = 5, quant: Q
         return u2
 
     y = rec(0, z)
-    pre = _conv(y, sd[FINAL_CONV + '.weight'], sd[FINAL_CONV + '.bias'], 1, quant)   # skip.py:92
+    pre = _conv(y, sd[FINAL_CONV + '.weight'], sd[FINAL_CONV + '.bias'], 1, quant, 'final_w')   # skip.py:92
     if taps is not None:
         taps['final_pre'] = pre
     return torch.sigmoid(pre)                                                          # skip.py:93-94

@@ -33,3 +33,14 @@ def golden():
     def load(name):
         return torch.load(os.path.join(GOLDEN, name))
     return load
+
+
+def rebuild_z0(fx):
+    """Perturbed input of a large fixture (oracle/make_golden_large.py keeps the seed, not the 33.5 MB tensor):
+    the CPU draws that follow get_net in the reference flow -- get_noise's uniform (utils/DIP.py:92-96), the
+    Downsampler's throw-away Conv2d initialisation (utils/downsampler.py:44) and the closure's noise.normal_()
+    (DIP.py:52).  Call right after building the network under torch.manual_seed(fx['seed'])."""
+    import torch
+    ni = torch.zeros(1, 32, fx['H'], fx['W']).uniform_() * 0.1
+    torch.nn.Conv2d(3, 3, kernel_size=4 * fx['factor'], stride=fx['factor'])
+    return ni + ni.clone().normal_() * fx['reg_noise_std']

@@ -108,19 +108,37 @@ def test_tensor_core_kernels_match_checker(size):
     assert code.value == 0
 
 
+def live_keys(fx):
+    from oracle import dip_oracle as O
+    dead = set(O.dead_param_keys())
+    floor = 1e-6 * max(fx['grad_norms'].values())
+    return [k for k in fx['grad_norms'] if k not in dead and fx['grad_norms'][k] >= floor]
+
+
+def grad_cosines(mine, theirs, keys):
+    """(cosine over the concatenated live gradient, minimum per-tensor cosine)"""
+    a = torch.cat([mine[k].detach().flatten().cpu() for k in keys])
+    b = torch.cat([theirs[k].detach().flatten().cpu() for k in keys])
+    return cosine(a, b), min(cosine(mine[k], theirs[k]) for k in keys)
+
+
 # ---------------------------------------------------------------------------------------------
-# One teacher-forced DIP step against the REFERENCE fixture (same weights, same noise)
-# gates: output rel L2 <= 1e-2 and loss rel <= 1e-2 (BASELINE.json north_star).  Gradients: the freshly initialised
-# net is chaotic -- 16-bit rounding of the activations (fp16 here, 10-bit mantissa like TF32) moves the forward by
-# ~2e-2 inside the decoder, which flips ~1.5 % of the LeakyReLU masks and bounds the gradient cosine near 0.98-0.99
-# at 64x64; the CPU oracle run with the SAME rounding points shows the same figures (DESIGN.md "Numerics").  The
-# gate is therefore cosine >= 0.90 per live tensor and >= 0.98 over the whole live gradient against the fp32 reference, plus bit-level agreement of every
-# tensor-core launch with its checker kernel (test_tensor_core_kernels_match_checker).
+# One teacher-forced DIP step against the REFERENCE fixture (same weights, same noise).
+# North-star gates: output rel L2 <= 1e-2, loss rel <= 1e-2.  Gradients: the freshly initialised net is chaotic --
+# 16-bit rounding of the activations (fp16 here, 10-bit mantissa like TF32) flips ~1.5 % of the LeakyReLU masks, which
+# bounds the gradient cosine against the fp32 reference near 0.98-0.99 at 64x64 and 0.997 at 256x256 / 512x512.  The
+# CPU oracle run with fp16 rounding at the SAME storage points (O.fp16_points; tests/test_oracle.py pins it at
+# cosine 0.992 / output 4.7e-3 of the reference on step_64x64) is the tighter yardstick: the CUDA path must agree
+# with IT more closely than with the fp32 reference.  What is left between the two (the tcgen05 accumulator adds its
+# products with truncation: 5 % of the raw outputs of a K = 1152 layer land one fp16 ulp away from the exactly
+# rounded value, measured with tools/dump_step.py) is the same noise class again.  All runs use DSR_DETERMINISTIC=1,
+# so the measured figures below are reproduced bit for bit and the gates sit right above them.
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize('name', ['step_64x64.pt', 'step_64x96.pt', 'step_72x88.pt'])   # last: odd level sizes, Concat crop
-def test_teacher_forced_step_matches_reference(golden, name):
+def test_teacher_forced_step_matches_reference(golden, name, monkeypatch):
     import dsr_b200
     from oracle import dip_oracle as O
+    monkeypatch.setenv('DSR_DETERMINISTIC', '1')
     fx = golden(name)
     net = make_net(fx['seed'])
     sd0 = {k: v.clone() for k, v in net.state_dict().items()}
@@ -134,29 +152,120 @@ def test_teacher_forced_step_matches_reference(golden, name):
     assert rel(out_lr, fx['out_lr']) < 1e-2
     assert float(loss) == pytest.approx(fx['losses'][0], rel=1e-2)
     _, _, grads = O.step_loss_and_grads(sd0, fx['z0'], fx['lr_img'], fx['factor'])
-    dead = set(O.dead_param_keys())
-    floor = 1e-6 * max(fx['grad_norms'].values())
-    checked = 0
-    mine, theirs = [], []
-    for k, p in net.named_parameters():
-        if k in dead or fx['grad_norms'][k] < floor:
-            if k in dead and k.endswith('1.bias'):
-                assert float(p.grad.abs().max()) == 0.0      # conv bias feeding a BatchNorm: exact zero
-            continue
-        assert cosine(p.grad, grads[k]) > 0.90, k        # per tensor (small ones are the noisiest: observed >= 0.975)
+    loss_q, out_q, grads_q = O.step_loss_and_grads(sd0, fx['z0'], fx['lr_img'], fx['factor'], quant=O.fp16_points())
+    mine = {k: p.grad for k, p in net.named_parameters()}
+    for k in O.dead_param_keys():
+        if k.endswith('1.bias'):
+            assert float(mine[k].abs().max()) == 0.0      # conv bias feeding a BatchNorm: exact zero
+    keys = live_keys(fx)
+    assert len(keys) >= 60
+    for k in keys:
         if fx['grad_norms'][k] > 1e-3 * max(fx['grad_norms'].values()):      # tiny tensors: cosine only (noise)
-            assert float(p.grad.double().norm().cpu()) == pytest.approx(fx['grad_norms'][k], rel=0.25), k
-        mine.append(p.grad.detach().flatten().cpu())
-        theirs.append(grads[k].flatten())
-        checked += 1
-    assert checked >= 60
-    assert cosine(torch.cat(mine), torch.cat(theirs)) > 0.96     # whole live gradient: 0.97-0.995; two runs of the SAME binary agree to 0.977 at 64x64 (tools/ab_upcat.py)
+            assert float(mine[k].double().norm().cpu()) == pytest.approx(fx['grad_norms'][k], rel=0.25), k
+    whole, worst = grad_cosines(mine, grads, keys)             # vs the fp32 reference arithmetic
+    whole_q, worst_q = grad_cosines(mine, grads_q, keys)       # vs the same arithmetic with fp16 storage points
+    print(f'{name}: out rel {rel(out, fx["out_hr"]):.2e} (vs fp16-point oracle {rel(out, out_q):.2e}); gradient cosine '
+          f'whole / worst tensor: {whole:.4f} / {worst:.4f} vs fp32, {whole_q:.4f} / {worst_q:.4f} vs fp16-point oracle')
+    # measured (deterministic): 64x64 0.9841 / 0.9723 and 0.9935 / 0.9879; 72x88 0.9931 / 0.9756 and 0.9957 / 0.9879
+    assert whole > 0.975 and worst > 0.95
+    assert whole_q > 0.99 and worst_q > 0.98 and whole_q > whole
+    assert rel(out, out_q) < 6e-3 and rel(out, out_q) < rel(out, fx['out_hr'])
+    assert float(loss) == pytest.approx(float(loss_q), rel=3e-3)
     # BatchNorm running statistics follow torch (momentum 0.1, unbiased variance, conv bias in the mean)
     sd1 = net.state_dict()
     assert int(sd1['1.0.2.num_batches_tracked']) == 1
     for k, v in fx['post_adam_small'].items():
         if k.endswith('running_mean') or k.endswith('running_var'):
             assert torch.allclose(sd1[k].cpu(), v, rtol=3e-2, atol=3e-3), k
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE sizes: one teacher-forced step at 256x256 (configs[0]) and 512x512 (configs[1]) against the fixture written
+# by the unmodified reference (oracle/make_golden_large.py) and against the oracle run on this box's CPU
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('name', ['step_256.pt', 'step_512.pt'])
+def test_teacher_forced_step_at_baseline_sizes(golden, name, monkeypatch):
+    import dsr_b200
+    from conftest import rebuild_z0
+    from oracle import dip_oracle as O
+    from oracle.make_golden_large import probe
+    monkeypatch.setenv('DSR_DETERMINISTIC', '1')
+    fx = golden(name)
+    net = make_net(fx['seed'])
+    z0 = rebuild_z0(fx)
+    sd0 = {k: v.clone() for k, v in net.state_dict().items()}
+    net = net.cuda()
+    ds = dsr_b200.Downsampler(3, fx['factor'], 'lanczos2', phase=0.5, preserve_size=True).cuda()
+    out = net(z0.cuda())
+    out_lr = ds(out)
+    loss = torch.nn.MSELoss()(out_lr, fx['lr_img'].cuda())
+    loss.backward()
+    # --- against the reference fixture (north-star gates are 1e-2; measured 1.3e-3 / 1.1e-3 and 2e-5 / 6e-5)
+    assert rel(out, fx['out_hr']) < 3e-3
+    assert rel(out_lr, fx['out_lr']) < 3e-3
+    assert float(loss) == pytest.approx(fx['loss'], rel=1e-3)
+    mine = {k: p.grad for k, p in net.named_parameters()}
+    keys = live_keys(fx)
+    top = max(fx['grad_norms'].values())
+    for k in keys:
+        if fx['grad_norms'][k] > 1e-3 * top:
+            assert float(mine[k].double().norm().cpu()) == pytest.approx(fx['grad_norms'][k], rel=0.1), k
+    for k, g in fx['grad_full'].items():
+        if k in keys:
+            assert cosine(mine[k], g) > 0.985, k
+    for k, g in fx['grad_slices'].items():
+        assert cosine(mine[k][:8, :8], g) > 0.97, k
+    # 112-number fingerprint of the whole gradient: projections on fixed pseudo-random directions
+    pm = torch.tensor([float((mine[k].double().cpu() * probe(k, mine[k].shape)).sum()) for k in keys])
+    pr = torch.tensor([fx['grad_probe'][k] for k in keys])
+    assert cosine(pm, pr) > 0.99           # measured 0.9990 (256), 0.9937 (512)
+    # --- against the oracle on this box (fp32, and with fp16 rounding at the CUDA path's storage points)
+    _, _, grads = O.step_loss_and_grads(sd0, z0, fx['lr_img'], fx['factor'])
+    loss_q, out_q, grads_q = O.step_loss_and_grads(sd0, z0, fx['lr_img'], fx['factor'], quant=O.fp16_points())
+    whole, worst = grad_cosines(mine, grads, keys)
+    whole_q, worst_q = grad_cosines(mine, grads_q, keys)
+    print(f'{name}: out rel {rel(out, fx["out_hr"]):.2e} (vs fp16-point oracle {rel(out, out_q):.2e}), loss rel '
+          f'{abs(float(loss) - fx["loss"]) / fx["loss"]:.1e}; gradient cosine whole / worst tensor: {whole:.4f} / '
+          f'{worst:.4f} vs fp32, {whole_q:.4f} / {worst_q:.4f} vs fp16-point oracle')
+    # measured (deterministic): 256: 0.9974 / 0.9948 and 0.9983 / 0.9954; 512: 0.9969 / 0.9924 and 0.9980 / 0.9887
+    assert whole > 0.995 and worst > 0.985
+    assert whole_q > 0.997 and worst_q > 0.985 and whole_q > whole
+    assert rel(out, out_q) < 2e-3 and rel(out, out_q) < rel(out, fx['out_hr'])
+
+
+def test_deterministic_mode_is_bit_identical(monkeypatch):
+    """DSR_DETERMINISTIC=1: every cross-CTA sum is order-independent (64-bit fixed-point statistics, two-stage split-K
+    weight gradients, fixed-point loss), so two runs of one binary -- fresh plans, fresh workspaces -- agree bit for
+    bit: output, loss, every gradient, and the parameters after 5 fused iterations."""
+    import dsr_b200
+    from oracle import dip_oracle as O
+    monkeypatch.setenv('DSR_DETERMINISTIC', '1')
+    g = torch.Generator().manual_seed(4)
+    z = (torch.rand(1, 32, 136, 200, generator=g) * 0.1).cuda()
+    gout = (torch.randn(1, 3, 136, 200, generator=g) * 1e-6).cuda()
+    runs = []
+    for _ in range(2):
+        net = make_net(6).cuda()
+        out = net(z)
+        out.backward(gout)
+        runs.append((out.detach().clone(), net.flat_buffers()[1].clone()))
+    assert torch.equal(runs[0][0], runs[1][0]) and torch.equal(runs[0][1], runs[1][1])
+    lr_img, _ = O.synthetic_pair(3, 128)
+    cfg = {'learning_rate': 0.01, 'num_iter': 5, 'reg_noise_std': 0.05}
+    fused = []
+    for _ in range(2):
+        net = make_net(7)
+        out, losses = dsr_b200.dip_sr_fused(net, lr_img, (128, 128), 4, cfg, 'cuda:0', seed=3)
+        torch.cuda.synchronize()
+        fused.append((out.clone(), losses.clone(), net.flat_buffers()[0].clone()))
+    for a, b in zip(fused[0], fused[1]):
+        assert torch.equal(a, b)
+    # without the switch only the split-K weight-gradient atomics remain order-dependent: same forward, dW to 1e-6
+    monkeypatch.delenv('DSR_DETERMINISTIC')
+    net = make_net(6).cuda()
+    out = net(z)
+    out.backward(gout)
+    assert torch.equal(out, runs[0][0]) and rel(net.flat_buffers()[1], runs[0][1]) < 1e-5
 
 
 def test_fused_adam_matches_torch():
@@ -246,9 +355,8 @@ def test_fused_step_tracks_the_closure_path():
     _, l1 = dsr_b200.dip_sr_fused(net_a, lr_img, (64, 64), 4, cfg0, 'cuda:0', net_input=z)
     ds = dsr_b200.Downsampler(3, 4, 'lanczos2', phase=0.5, preserve_size=True)
     l2 = torch.nn.MSELoss()(ds(net_b(z.cuda())), lr_img.unsqueeze(0).cuda())
-    # not bit-equal: BatchNorm sums are accumulated with fp32 atomics whose order varies run to run, and the chaotic
-    # freshly-initialised net amplifies that (see test_full_size_properties_512)
-    assert float(l1[0]) == pytest.approx(float(l2), rel=2e-2)
+    # the forward passes are bit-identical (fixed-point statistics); the two losses are summed by different kernels
+    assert float(l1[0]) == pytest.approx(float(l2), rel=1e-5)
 
 
 def test_fused_step_draws_the_counter_based_noise():
@@ -295,9 +403,11 @@ def test_full_size_properties_512():
     net.zero_grad()
     out2 = net(z)
     out2.backward(gout)
-    # run-to-run: fp32 atomic accumulation order of the BatchNorm sums differs (1e-7), fp16 rounding of a few
-    # activations flips, and the untrained net amplifies it ~100x; measured 8e-4 / 0.995 on B200
-    assert rel(o1, out2) < 5e-3 and cosine(g1, net.flat_buffers()[1]) > 0.98
+    # run-to-run: every statistic is accumulated in fixed point (csrc/dsr_acc.cuh), so the forward pass and all
+    # activation gradients are bit-identical; only the split-K weight-gradient atomics still commute differently
+    # (last bits of dW; DSR_DETERMINISTIC=1 removes that too, see test_deterministic_mode_is_bit_identical)
+    assert torch.equal(o1, out2)
+    assert rel(net.flat_buffers()[1], g1) < 1e-5
     lr_img, hr = O.synthetic_pair(0, 512)
     cfg = {'learning_rate': 0.01, 'num_iter': 30, 'reg_noise_std': 0.05}
     res, losses = dsr_b200.dip_sr_fused(make_net(0), lr_img, (512, 512), 4, cfg, 'cuda:0')
@@ -318,8 +428,10 @@ def test_whole_step_tensor_core_vs_checker_256():
     net.zero_grad()
     out2 = net(z)
     out2.backward(gout)
+    # the checker kernels accumulate with sequential fp32 FMAs, tcgen05 adds its products with truncation: a few
+    # percent of the fp16 outputs of a layer differ by one ulp, which the untrained net amplifies to ~1e-3
     assert rel(o_tc, out2) < 5e-3
-    assert cosine(g_tc, net.flat_buffers()[1]) > 0.98       # same run-to-run bound as above
+    assert cosine(g_tc, net.flat_buffers()[1]) > 0.98
 
 
 def test_long_run_psnr_matches_reference(golden):
@@ -412,7 +524,7 @@ def test_images_in_flight_on_one_gpu():
     for i in range(3):
         a, b = seq[i]['losses'], par[i]['losses']
         assert torch.isfinite(b).all()
-        # the first iteration is the same computation; later ones drift apart like any two runs of this chaotic
-        # early optimisation do (fp32 atomics commute differently)
-        assert abs(float(a[0]) - float(b[0])) <= 1e-2 * float(a[0])      # run-to-run spread of one step is ~3e-3
+        # the first iteration is the same computation (bit-identical forward: fixed-point statistics); later ones drift
+        # apart because the split-K weight-gradient atomics commute differently
+        assert abs(float(a[0]) - float(b[0])) <= 1e-5 * float(a[0])
         assert float(b[-3:].mean()) < float(b[:3].mean())              # and it optimises

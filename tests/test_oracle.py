@@ -123,3 +123,69 @@ def test_psnr_and_synthetic_pair():
     assert hr.shape == (3, 64, 64) and lr.shape == (3, 16, 16)
     assert 0 <= float(hr.min()) and float(hr.max()) <= 1
     assert O.psnr(hr, hr + 0.1) == pytest.approx(20.0, abs=1e-3)
+
+
+@pytest.mark.parametrize('name', ['step_256.pt', 'step_512.pt'])
+def test_step_matches_reference_at_baseline_sizes(golden, name):
+    """BASELINE configs[0] / configs[1] sizes: the oracle against one teacher-forced step of the unmodified reference
+    (oracle/make_golden_large.py).  z0 is rebuilt from the seed and must hit the stored checksum."""
+    from conftest import rebuild_z0
+    from oracle.make_golden_large import probe
+    fx = golden(name)
+    torch.manual_seed(fx['seed'])
+    sd = O.init_params()
+    z0 = rebuild_z0(fx)
+    assert checksum(z0) == pytest.approx(fx['z0_checksum'], rel=1e-9)
+    loss, out, grads = O.step_loss_and_grads(sd, z0, fx['lr_img'], fx['factor'])
+    assert rel(out, fx['out_hr']) < 1e-5          # multi-threaded reduction order differs from the fixture's: ~3e-7
+    assert float(loss) == pytest.approx(fx['loss'], rel=1e-5)
+    assert rel(O.downsample(out, fx['factor']), fx['out_lr']) < 1e-5
+    dead = set(O.dead_param_keys())
+    top = max(fx['grad_norms'].values())
+    for k, n in fx['grad_norms'].items():
+        if k in dead or n < 1e-6 * top:
+            continue
+        assert float(grads[k].double().norm()) == pytest.approx(n, rel=1e-3), k
+        pr = float((grads[k].double() * probe(k, grads[k].shape)).sum())
+        assert pr == pytest.approx(fx['grad_probe'][k], rel=2e-2, abs=2e-3 * n * grads[k].numel() ** 0.5), k
+    for k, g in fx['grad_slices'].items():
+        assert rel(grads[k][:8, :8], g) < 1e-3, k
+
+
+def test_quantised_oracle_precision_class(golden):
+    """What 16-bit operands cost on the freshly initialised (chaotic) network, measured on the CPU with the oracle's
+    rounding hook at the points where the CUDA path stores 16-bit values (O.fp16_points): fp16 moves the output by
+    ~4e-3 and the gradient to cosine ~0.99 of the fp32 reference, bf16 is an order of magnitude worse (why the CUDA
+    path uses fp16 operands with a loss scale).  The GPU parity tests gate the CUDA path against THIS oracle."""
+    fx = golden('step_64x64.pt')
+    torch.manual_seed(fx['seed'])
+    sd = O.init_params()
+    _, out32, g32 = O.step_loss_and_grads(sd, fx['z0'], fx['lr_img'], fx['factor'])
+    dead = set(O.dead_param_keys())
+    live = [k for k in g32 if k not in dead and fx['grad_norms'][k] > 1e-6 * max(fx['grad_norms'].values())]
+
+    def whole(g):
+        return torch.cat([g[k].flatten() for k in live]).double()
+
+    a = whole(g32)
+    res = {}
+    for tag, dt in (('fp16', torch.float16), ('bf16', torch.bfloat16)):
+        loss, out, g = O.step_loss_and_grads(sd, fx['z0'], fx['lr_img'], fx['factor'], quant=O.fp16_points(dt))
+        b = whole(g)
+        res[tag] = (rel(out, out32), float(a @ b / (a.norm() * b.norm())), abs(float(loss) - fx['losses'][0]) / fx['losses'][0])
+    assert res['fp16'][0] < 8e-3 and res['fp16'][1] > 0.985 and res['fp16'][2] < 1e-2     # measured 4.7e-3 / 0.992
+    assert res['bf16'][0] > 3 * res['fp16'][0] and res['bf16'][1] < res['fp16'][1]        # measured 3.6e-2 / 0.45
+
+
+def test_drop_in_downsampler_consumes_the_reference_rng_draws():
+    """utils/downsampler.py:44 builds (and then overwrites) an nn.Conv2d: its initialisation advances the global CPU
+    generator between get_net and get_noise (DIP.py:29,32).  The mirror draws the same numbers, so identical seeds
+    give identical net_input / noise tensors."""
+    import dsr_b200
+    torch.manual_seed(5)
+    dsr_b200.Downsampler(3, 4, 'lanczos2', phase=0.5, preserve_size=True)
+    a = torch.rand(4)
+    torch.manual_seed(5)
+    torch.nn.Conv2d(3, 3, kernel_size=(16, 16), stride=4, padding=0)
+    b = torch.rand(4)
+    assert torch.equal(a, b)

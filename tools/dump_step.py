@@ -23,10 +23,14 @@ def run(fx, keep_taps):
         z0 = fx['z0']
     else:        # large fixtures keep the seed only (oracle/make_golden_large.py): same CPU draws as the reference
         ni = torch.zeros(1, 32, fx['H'], fx['W']).uniform_() * 0.1
+        ds = dsr_b200.Downsampler(3, fx['factor'], 'lanczos2', phase=0.5, preserve_size=True)   # draws like the reference's
         z0 = ni + ni.clone().normal_() * fx['reg_noise_std']
     net = net.cuda()
     ds = dsr_b200.Downsampler(3, fx['factor'], 'lanczos2', phase=0.5, preserve_size=True).cuda()
     z = z0.cuda()
+    if os.environ.get('DSR_DUMP_CHECKER'):     # CUDA-core checker kernels (sequential fp32 FMA) instead of tcgen05
+        net(z)
+        net.set_debug_conv(True)
     out = net(z)
     out_lr = ds(out)
     loss = torch.nn.MSELoss()(out_lr, fx['lr_img'].cuda())
@@ -53,7 +57,7 @@ def main():
     os.makedirs(out_dir, exist_ok=True)
     for name in sys.argv[1:]:
         fx = torch.load(os.path.join(ROOT, 'tests', 'golden', name))
-        a = run(fx, True)
+        a = run(fx, fx['H'] <= 128)
         b = run(fx, False)
         same_out = torch.equal(a['out_hr'], b['out_hr'])
         ga = torch.cat([v.flatten() for v in a['grads'].values()]).double()
@@ -64,7 +68,7 @@ def main():
               f'cos {cos:.9f}  max|dg| {float((ga - gb).abs().max()):.3e}', flush=True)
         rel = float((a['out_hr'] - fx['out_hr']).norm() / fx['out_hr'].norm())
         print(f'   out rel L2 vs reference {rel:.3e}', flush=True)
-        tag = 'det' if os.environ.get('DSR_DETERMINISTIC') else 'def'
+        tag = 'chk' if os.environ.get('DSR_DUMP_CHECKER') else 'det' if os.environ.get('DSR_DETERMINISTIC') else 'def'
         torch.save(a, os.path.join(out_dir, f'cuda_{tag}_{name}'))
 
 
