@@ -31,7 +31,12 @@ import tempfile
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-for p in (os.path.join(ROOT, 'deep-super-resolution_b200'), ROOT):
+PKG = os.path.join(ROOT, 'deep-super-resolution_b200')
+REF = os.path.join(ROOT, 'baseline', '_ref')          # unmodified reference checkout, staged by __graft_entry__.build()
+# The reference arm imports the reference's OWN models/ and utils/ packages; our arm imports the drop-in ones.  The two
+# share module names, so the path order is decided by --impl before anything is imported.
+_REFERENCE_ARM = '--impl' in sys.argv and sys.argv[sys.argv.index('--impl') + 1:][:1] == ['reference']
+for p in ((REF, ROOT) if _REFERENCE_ARM and os.path.isdir(REF) else (PKG, ROOT)):
     if p not in sys.path:
         sys.path.insert(0, p)
 
@@ -43,19 +48,22 @@ LR_RATE, SIGMA = 0.01, 0.05                          # DIP.py:318,323
 
 
 def peaks():
+    """Roofline denominators.  Kernel classes are timed per launch (CUDA events, the GPU otherwise idle), so the BURST
+    bf16 figure is the tensor peak; the whole-step figure is also quoted against the sustained one."""
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(path):
         d = json.load(open(path))
-        return dict(tflops=d.get('bf16_tflops_sustained', d.get('bf16_tflops')), tflops_burst=d.get('bf16_tflops'),
-                    hbm=d.get('hbm_gbs'), src='measured (MEASURED_PEAKS.json, sustained bf16)')
-    return dict(tflops=1590.0, tflops_burst=1590.0, hbm=6650.0, src='fallback (B200_PROFILING.md)')
+        return dict(tflops=d.get('bf16_tflops', d.get('bf16_tflops_sustained')),
+                    tflops_sustained=d.get('bf16_tflops_sustained', d.get('bf16_tflops')),
+                    hbm=d.get('hbm_gbs'), src='measured (MEASURED_PEAKS.json: burst bf16, HBM copy)')
+    return dict(tflops=1590.0, tflops_sustained=1590.0, hbm=6650.0, src='fallback (B200_PROFILING.md)')
 
 
-def ncu_traffic():
-    """DRAM bytes (read + write) of the dominant kernel's largest launch (L0 decoder 3x3 fprop) from the committed
-    `ncu --set full` capture, profiles/r01_halo2_full_raw_v3.csv; None if the file is missing."""
+def ncu_traffic(name):
+    """DRAM bytes (read + write) of one launch from a committed `ncu --set full` capture under profiles/ (ARCHIVED, not
+    measured by this run -- ncu cannot run inside the bench); None if the file is missing."""
     import csv
-    path = os.path.join(ROOT, 'profiles', 'r01_halo2_full_raw_v3.csv')
+    path = os.path.join(ROOT, 'profiles', name)
     try:
         rows = list(csv.reader(open(path)))
         hdr, units, row = rows[0], rows[1], rows[2]
@@ -125,9 +133,78 @@ class ClockSampler:
 
 
 # -------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference path
+# Reference arm: the UNMODIFIED reference modules (baseline/_ref: models/DIP, utils/downsampler.py, utils/DIP.py)
+# driven by a closure that repeats DIP.py:47-69 -- on the host cores (the CPU baseline) or, harness only, on the GPU
+# with stock PyTorch CUDA eager, fp32, TF32 off (the like-for-like GPU comparator of BASELINE.md section 3).
+# Falls back to the oracle port (oracle/dip_oracle.py) only where baseline/_ref was not staged.
 # -------------------------------------------------------------------------------------------------
-def cpu_steps(size, warmup, steps, budget_s):
+WORKLOAD = 'DIP 4x SR of one synthetic {s}x{s} image, skip net fwd+bwd+Adam (BASELINE configs[1])'
+
+
+def reference_steps(size, warmup, steps, budget_s, device='cpu', predrawn=False):
+    """it/s (median step) of the reference's own modules; returns (it/s, steps timed, cores, kind)."""
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    if not os.path.isdir(REF) or not _REFERENCE_ARM:
+        its, n, cores = port_steps(size, warmup, steps, budget_s)
+        return its, n, cores, 'port'
+    from models.DIP import get_net                        # the reference's own files (REF is first on sys.path)
+    from utils.downsampler import Downsampler
+    from utils.DIP import get_noise, get_params, optimize
+    import models.DIP as _m
+    assert os.path.realpath(_m.__file__).startswith(os.path.realpath(REF)), _m.__file__
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    dev = torch.device(device)
+    hr = synthetic_pair(0, size)
+    ds = Downsampler(n_planes=3, factor=FACTOR, kernel_type='lanczos2', phase=0.5, preserve_size=True)
+    with torch.no_grad():
+        lr_img = ds(hr.unsqueeze(0)).to(dev)
+    ds = ds.to(dev)
+    torch.manual_seed(0)
+    net = get_net(32, 'skip', 'reflection', skip_n33d=128, skip_n33u=128, skip_n11=4, num_scales=5,
+                  upsample_mode='bilinear').to(dev)                                   # DIP.py:169-174
+    net_input = get_noise(32, 'noise', (size, size)).detach()                        # DIP.py:32 (a CPU tensor)
+    saved, noise = net_input.detach().clone(), net_input.detach().clone()
+    mse = torch.nn.MSELoss()
+    times, t_begin = [], time.time()
+    state = {'t0': 0.0}
+
+    ring = [(saved + torch.randn(saved.shape) * SIGMA).pin_memory() for _ in range(4)] if predrawn else None
+
+    def closure():
+        if predrawn:      # comparator for `e2e`: the perturbed inputs are drawn ahead, like the ring our e2e arm reads
+            z = ring[len(times) % 4]
+        else:
+            z = saved + (noise.normal_() * SIGMA)                                     # DIP.py:52 (host RNG)
+        z = z.to(dev)                                                                 # DIP.py:57
+        out_hr = net(z)
+        out_lr = ds(out_hr)
+        loss = mse(out_lr, lr_img)
+        loss.backward()
+        out_hr.detach().cpu()                                                         # DIP.py:90-91
+        out_lr.detach().cpu()
+        return loss
+
+    params = get_params('net', net, net_input)
+    optim = torch.optim.Adam(params, lr=LR_RATE)                                      # utils/DIP.py:34
+    for i in range(warmup + steps):
+        t0 = time.time()
+        optim.zero_grad()                                                             # utils/DIP.py:36-38
+        closure()
+        optim.step()
+        if dev.type == 'cuda':
+            torch.cuda.synchronize()
+        dt = time.time() - t0
+        if i >= warmup:
+            times.append(dt)
+        if time.time() - t_begin > budget_s and len(times) >= 2:
+            break
+    times.sort()
+    return 1.0 / times[len(times) // 2], len(times), cores, 'reference'
+
+
+def port_steps(size, warmup, steps, budget_s):
     """Times DIP iterations of the CPU restatement (fp32, all host threads).  Returns (it/s, steps timed, cores)."""
     from oracle import dip_oracle as O
     cores = os.cpu_count() or 1
@@ -159,19 +236,36 @@ def cpu_steps(size, warmup, steps, budget_s):
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    its, n, cores = cpu_steps(args.size, min(args.warmup, 2), args.steps, budget_s=150.0)
+    dev = args.ref_device
+    its, n, cores, kind = reference_steps(args.size, args.warmup, args.steps, budget_s=150.0, device=dev,
+                                          predrawn=args.ref_predrawn)
+    what = ('unmodified reference modules (baseline/_ref: models/DIP, utils/downsampler.py, utils/DIP.py) + a '
+            'DIP.py:47-69 closure + torch.optim.Adam' if kind == 'reference' else 'oracle/dip_oracle.py on torch CPU')
+    where = f'{cores} host cores' if dev == 'cpu' else 'stock PyTorch CUDA eager, fp32, TF32 off (harness only)'
     line = {
         'impl': 'reference', 'metric': 'DIP iters/s (512^2 4x SR)', 'value': its, 'unit': 'it/s', 'n_gpus': args.gpus,
-        'steps': n, 'warmup': min(args.warmup, 2), 'ms_per_step': 1000.0 / its, 'higher_is_better': True,
+        'steps': n, 'warmup': args.warmup, 'ms_per_step': 1000.0 / its, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': f'DIP 4x SR of one synthetic {args.size}x{args.size} image, skip net fwd+bwd+Adam',
-                   'size': args.size, 'factor': FACTOR},
-        'cpu_baseline': {'value': its, 'unit': 'it/s', 'cores': cores, 'kind': 'port',
-                         'sample': f'{n} full iterations at {args.size}^2 (median), oracle/dip_oracle.py on torch CPU'},
+        'config': {'workload': WORKLOAD.format(s=args.size), 'size': args.size, 'factor': FACTOR},
+        'cpu_baseline': {'value': its, 'unit': 'it/s', 'cores': cores, 'kind': kind, 'device': dev,
+                         'sample': f'{n} full iterations at {args.size}^2 (median step time), {what}, on {where}'},
         'e2e': {'value': its, 'unit': 'it/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def reference_subprocess(size, device, steps, warmup, predrawn=False):
+    """Runs `bench.py --impl reference` in a child process (the reference's models/ and utils/ packages share their
+    names with the drop-in ones, so the two cannot be imported side by side) and returns its JSON line."""
+    cmd = [sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--ref-device', device, '--size', str(size),
+           '--steps', str(steps), '--warmup', str(warmup)] + (['--ref-predrawn'] if predrawn else [])
+    env = {k: v for k, v in os.environ.items() if k not in ('RANK', 'LOCAL_RANK', 'WORLD_SIZE')}
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env).stdout
+        return json.loads(out.strip().splitlines()[-1])
+    except Exception as e:            # noqa: BLE001
+        return {'unavailable': repr(e)[:200]}
 
 
 # -------------------------------------------------------------------------------------------------
@@ -247,7 +341,9 @@ def run_ours(args, rank, local_rank, world):
         ms = float(t.item())
     loss_first, loss_last = float(losses[args.warmup]), float(losses[args.warmup + args.steps - 1])
 
-    # ---- roofline of the conv kernel: profiled pass (CUDA events around every launch) ----
+    # ---- roofline: profiled passes (CUDA events around every tensor-core launch, the host enqueueing ahead of the
+    #      GPU behind a busy-wait, so the intervals are GPU time).  Four kernel classes; the DOMINANT one is the class
+    #      with the largest time per iteration.  Per-launch timings -> burst bf16 peak.
     roof = None
     if rank == 0:
         check(lib.dsr_plan_set_profile(plan.handle, 1))
@@ -255,38 +351,55 @@ def run_ours(args, rank, local_rank, world):
         step(nprof)
         torch.cuda.synchronize()
         pk = peaks()
+        # conv-side algorithmic bytes per iteration of each class at this size (every operand / result read or
+        # written once at its storage dtype), used for the HBM-bound 1x1 class: 2 x 128 channels x 2 B per pixel and pass
         res = {}
-        for cls, name in ((0, 'conv_halo2_kernel'), (1, 'wgrad_halo_kernel'), (2, 'conv_gemm_kernel'),
-                          (3, 'conv_halo2_kernel_1x1')):
+        for cls, name, what in (
+                (0, 'conv_halo2_kernel', '3x3 stride-1 fprop + dgrad, halo-tile implicit GEMM, tcgen05 cta_group::2'),
+                (1, 'wgrad_halo_kernel', 'all weight gradients (split-K over pixels, both operands MN-major)'),
+                (2, 'conv_gemm_kernel', 'stride-2 layers + 32-channel first layer, generic implicit GEMM'),
+                (3, 'conv_halo2_kernel_1x1', '1x1 launches of the halo-tile kernel: 64 FLOP/B, HBM-bound')):
             msx, fl, n = C.c_double(), C.c_double(), C.c_int()
             check(lib.dsr_plan_profile_read(plan.handle, cls, C.byref(msx), C.byref(fl), C.byref(n)))
-            res[name] = dict(ms_per_step=msx.value / nprof, tflops=(fl.value / (msx.value * 1e-3) / 1e12) if msx.value else 0.0,
-                             launches_per_step=n.value // nprof, gflop_per_step=fl.value / nprof / 1e9)
-        tms, tfl = C.c_double(), C.c_double()
-        check(lib.dsr_plan_profile_top(plan.handle, 0, C.byref(tms), C.byref(tfl)))
-        top = {'gflop': tfl.value / 1e9, 'us': tms.value * 1e3,
-               'tflops': (tfl.value / (tms.value * 1e-3) / 1e12) if tms.value else 0.0}
-        top['frac'] = top['tflops'] / pk['tflops'] if pk['tflops'] else None
-        check(lib.dsr_plan_set_profile(plan.handle, 0))
-        a = res['conv_halo2_kernel']
-        # the same kernel on the 1x1 layers moves 2 x 128 channels x 2 B per pixel for 2 x 128 x 128 FLOP: 64 FLOP/B,
-        # HBM-bound (<= ~410 TFLOP/s at the measured copy bandwidth); reported against the HBM roof
+            tf = (fl.value / (msx.value * 1e-3) / 1e12) if msx.value else 0.0
+            res[name] = dict(what=what, ms_per_step=msx.value / nprof, launches_per_step=n.value // nprof,
+                             gflop_per_step=fl.value / nprof / 1e9, tflops=tf, bound='tensor',
+                             frac=tf / pk['tflops'] if pk['tflops'] else None)
         one = res['conv_halo2_kernel_1x1']
         one_gbs = (one['gflop_per_step'] / 64.0) / (one['ms_per_step'] * 1e-3) if one['ms_per_step'] else 0.0
         one.update({'bound': 'hbm', 'achieved_gbs': one_gbs, 'peak_gbs': pk['hbm'],
                     'frac': one_gbs / pk['hbm'] if pk['hbm'] else None})
-        roof = {'bound': 'tensor',
-                'kernel': 'conv_halo2_kernel, 3x3 launches (halo-tile implicit-GEMM, stride-1 fprop + dgrad, tcgen05 '
-                          'cta_group::2 kind::f16; all 5 levels incl. the latency-bound 16^2..64^2 ones)',
-                'achieved': a['tflops'], 'peak': pk['tflops'], 'unit': 'TFLOP/s',
-                'frac': a['tflops'] / pk['tflops'] if pk['tflops'] else None, 'traffic': ncu_traffic(),
-                'traffic_note': 'DRAM read+write bytes of the largest launch (L0 decoder 3x3 fprop, 79.7 GFLOP, '
-                                'algorithmic 76.1 MB in + 67.1 MB out) from profiles/r01_halo2_full_raw_v3.csv',
-                'peak_source': pk['src'],
-                'kernel_ms_per_step': a['ms_per_step'], 'launches_per_step': a['launches_per_step'],
-                'gflop_per_step': a['gflop_per_step'], 'largest_launch': top, 'wgrad_halo_kernel': res['wgrad_halo_kernel'],
-                'conv_gemm_kernel': res['conv_gemm_kernel'], 'conv_halo2_kernel_1x1': one,
-                'step_tflops_all_convs': FLOPS_PER_ITER.get(size, 0) / (ms / args.steps * 1e-3) / 1e12}
+        tops = {}
+        for cls, name in ((0, 'conv_halo2_kernel'), (1, 'wgrad_halo_kernel')):
+            tms, tfl = C.c_double(), C.c_double()
+            check(lib.dsr_plan_profile_top(plan.handle, cls, C.byref(tms), C.byref(tfl)))
+            tf = (tfl.value / (tms.value * 1e-3) / 1e12) if tms.value else 0.0
+            tops[name] = {'gflop': tfl.value / 1e9, 'us': tms.value * 1e3, 'tflops': tf,
+                          'frac': tf / pk['tflops'] if pk['tflops'] else None}
+        check(lib.dsr_plan_set_profile(plan.handle, 0))
+        dom = max(res, key=lambda k: res[k]['ms_per_step'])
+        d = res[dom]
+        arch = {'wgrad_halo_kernel': ('r02_wgrad_full_raw.csv', 'r01_wgrad_full_raw.csv'),
+                'conv_halo2_kernel': ('r02_halo2_full_raw.csv', 'r01_halo2_full_raw_v3.csv')}.get(dom, ())
+        traffic, tsrc = None, None
+        for f in arch:
+            traffic = ncu_traffic(f)
+            if traffic is not None:
+                tsrc = f'ARCHIVED ncu --set full capture profiles/{f} (largest launch of the class), not measured by this run'
+                break
+        step_tf = FLOPS_PER_ITER.get(size, 0) / (ms / args.steps * 1e-3) / 1e12
+        roof = {'bound': d['bound'], 'kernel': f'{dom}: {d["what"]} (the class with the largest time per iteration)',
+                'achieved': d['tflops'] if d['bound'] == 'tensor' else d['achieved_gbs'],
+                'peak': pk['tflops'] if d['bound'] == 'tensor' else pk['hbm'],
+                'unit': 'TFLOP/s' if d['bound'] == 'tensor' else 'GB/s', 'frac': d['frac'],
+                'traffic': traffic, 'traffic_source': tsrc, 'peak_source': pk['src'],
+                'timing': 'in-kernel %globaltimer stamps (dependencies satisfied -> last CTA done) of every tensor-core '
+                          'launch over 3 profiled iterations run eagerly with their programmatic-dependent-launch overlap; '
+                          'per-launch => burst peak',
+                'classes': res, 'largest_launch': tops,
+                'whole_step': {'tflops_all_convs': step_tf, 'frac_of_burst': step_tf / pk['tflops'] if pk['tflops'] else None,
+                               'frac_of_sustained': step_tf / pk['tflops_sustained'] if pk['tflops_sustained'] else None,
+                               'gflop_per_step': FLOPS_PER_ITER.get(size, 0) / 1e9}}
 
     # ---- configs[2] flavour: two independent images in flight on this GPU (separate nets / plans / streams):
     #      the latency-bound low-resolution levels of one image overlap the tensor-bound levels of the other ----
@@ -298,6 +411,8 @@ def run_ours(args, rank, local_rank, world):
     e2e = None
     if not args.no_e2e:
         e2e = run_e2e(args, rank, world, dev, net, ds, lr_img, z_saved, barrier)
+        if world == 1:
+            e2e['pipelined_readback_variant'] = run_e2e(args, rank, world, dev, net, ds, lr_img, z_saved, barrier, True)
 
     if rank != 0:
         return
@@ -307,19 +422,30 @@ def run_ours(args, rank, local_rank, world):
         'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f16 operands / f32 accumulate (tcgen05 kind::f16), f32 master weights + Adam',
         'data': 'synthetic',
-        'config': {'workload': f'DIP 4x SR of one synthetic {size}x{size} image per GPU, skip net fwd+bwd+Adam '
-                               f'(BASELINE configs[1]); {world} independent image(s), no collective',
-                   'size': size, 'factor': FACTOR, 'noise': 'device Philox (value) / pinned host buffer (e2e)',
+        'config': {'workload': WORKLOAD.format(s=size), 'size': size, 'factor': FACTOR,
+                   'images': f'{world} independent image(s), one per GPU, no collective',
+                   'noise': 'device Philox (value) / pre-drawn pinned host ring (e2e)',
                    'l2': 'working set per iteration ~1 GB >> 126 MB L2: no flush needed'},
         'roofline': roof, 'e2e': e2e, 'gpu_launches': launches_per_step * args.steps, 'clocks': clocks,
         'loss_first_last': [loss_first, loss_last], 'concurrent_images': conc,
         'conv_tflops_per_gpu': FLOPS_PER_ITER.get(size, 0) * (args.steps / (ms * 1e-3)) / 1e12,
     }
     if world == 1 and not args.no_cpu:
-        its_cpu, n, cores = cpu_steps(size, 1, 3, budget_s=40.0)
-        line['cpu_baseline'] = {'value': its_cpu, 'unit': 'it/s', 'cores': cores, 'kind': 'port',
-                                'sample': f'{n} full iterations at {size}^2 after 1 warm-up (median), '
-                                          'oracle/dip_oracle.py on torch CPU'}
+        # the reference's own modules on this box: host cores (the CPU baseline) and stock PyTorch CUDA eager (the
+        # like-for-like GPU comparator); both in child processes (same module names as the drop-in)
+        torch.cuda.synchronize()
+        r = reference_subprocess(size, 'cpu', 6, 2)
+        line['cpu_baseline'] = r.get('cpu_baseline', r)
+        g = reference_subprocess(size, 'cuda', 30, 5)
+        g2 = reference_subprocess(size, 'cuda', 30, 5, predrawn=True)
+        line['gpu_eager_baseline'] = ({'value': g['value'], 'unit': 'it/s', 'sample': g['cpu_baseline']['sample'],
+                                       'kind': g['cpu_baseline']['kind'],
+                                       'value_predrawn_noise': g2.get('value'),
+                                       'note': 'value: exactly the closure of DIP.py (8 M normals drawn on the host per '
+                                               'step); value_predrawn_noise: inputs drawn ahead in pinned host memory, as '
+                                               'in our e2e arm'} if 'value' in g else g)
+        if not args.no_secondary:
+            line['secondary'] = secondary_gan_eval(dev)
     print(json.dumps(line), flush=True)
 
 
@@ -375,7 +501,7 @@ def run_concurrent(args, dev, n_img):
             'ms_per_round': dt / args.steps * 1e3}
 
 
-def run_e2e(args, rank, world, dev, net, ds, lr_img, z_saved, barrier):
+def run_e2e(args, rank, world, dev, net, ds, lr_img, z_saved, barrier, pipelined=False):
     """Closure path of DIP.py:47-95 through get_params / optimize with HOST buffers for the step's input and
     results.  A ring of pre-drawn perturbed inputs lives in pinned host memory (drawing 8M normals per step on
     the CPU is the reference's 71 ms host cost and is not part of this metric); the copy of step t+1's input is
@@ -414,16 +540,24 @@ def run_e2e(args, rank, world, dev, net, ds, lr_img, z_saved, barrier):
         prefetch(i + 2)
         out_lr = ds(out_hr)
         loss = mse(out_lr, target)
-        fwd_done.record()
-        with torch.cuda.stream(d2h_stream):                                # DIP.py:90-91 reads: the three results leave
-            d2h_stream.wait_event(fwd_done)                                # over PCIe while the backward pass runs
+        if pipelined:
+            # variant: the three results leave over PCIe on a side stream WHILE the backward pass runs; the host blocks
+            # on their arrival only
+            fwd_done.record()
+            with torch.cuda.stream(d2h_stream):
+                d2h_stream.wait_event(fwd_done)
+                host_hr.copy_(out_hr.detach(), non_blocking=True)
+                host_lr.copy_(out_lr.detach(), non_blocking=True)
+                host_loss.copy_(loss.detach(), non_blocking=True)
+            loss.backward()
+            d2h_stream.synchronize()
+        else:
+            # reference order (DIP.py:68 then :90-91): backward first, then the blocking reads on the compute stream
+            loss.backward()
             host_hr.copy_(out_hr.detach(), non_blocking=True)
             host_lr.copy_(out_lr.detach(), non_blocking=True)
             host_loss.copy_(loss.detach(), non_blocking=True)
-        loss.backward()
-        # the host blocks until this step's results have ARRIVED in host memory, as the reference's .cpu() calls do
-        # (DIP.py:90-91); like the reference it does not wait for the backward pass, which the next step queues behind
-        d2h_stream.synchronize()
+            torch.cuda.current_stream().synchronize()
         state['i'] += 1
         return loss
 
@@ -451,9 +585,12 @@ def run_e2e(args, rank, world, dev, net, ds, lr_img, z_saved, barrier):
     d2h = host_hr.numel() * 4 + host_lr.numel() * 4 + 4
     return {'value': world * args.steps / (ms * 1e-3), 'unit': 'it/s', 'h2d_bytes_per_step': h2d,
             'd2h_bytes_per_step': d2h, 'ms_per_step': ms / args.steps,
-            'path': 'get_net/Downsampler/get_params/optimize + DIP.py-style closure; z from pinned host memory, '
-                    'out_HR/out_LR/loss read back each step (D2H on a side stream during the backward pass; the host blocks '
-                    'on their arrival every step)'}
+            'path': 'get_net/Downsampler/get_params/optimize + DIP.py-style closure; z copied from a pre-drawn ring of '
+                    'perturbed inputs in pinned host memory (the reference draws 8 M normals on the CPU per step: 71 ms, '
+                    'not part of this metric); out_HR/out_LR/loss read back each step ' +
+                    ('on a side stream during the backward pass, the host blocks on their arrival (pipelined variant)'
+                     if pipelined else 'AFTER the backward pass on the compute stream, the host blocks (reference order, '
+                     'DIP.py:68,90-91)')}
 
 
 # -------------------------------------------------------------------------------------------------
@@ -596,6 +733,32 @@ def run_gan(args, rank, local_rank, world):
     print(json.dumps(line), flush=True)
 
 
+def secondary_gan_eval(dev):
+    """BASELINE configs[3] beside the headline: a short SRResNet generator inference run (batch 64 of 96x96 LR patches,
+    x8) through dsr_b200.Generator; the full batch-256 line is `--workload gan_eval`."""
+    import dsr_b200
+    B, hw, steps = 64, 96, 3
+    torch.manual_seed(0)
+    g = dsr_b200.Generator(8).to(dev).eval()
+    x = torch.rand(B, 3, hw, hw, device=dev)
+    for _ in range(2):
+        g(x)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        g(x)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    ips = B / (ms * 1e-3)
+    pk = peaks()
+    tf = GAN_FLOPS_96 * ips / 1e12
+    return {'workload': f'SRResNet generator inference (eval_GAN), batch {B} of 96x96 LR patches -> 768x768 (BASELINE '
+                        f'configs[3]), {steps} steps', 'value': ips, 'unit': 'images/s', 'ms_per_step': ms,
+            'tflops': tf, 'frac_of_burst_bf16': tf / pk['tflops'] if pk['tflops'] else None}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--workload', default='dip', choices=['dip', 'gan_eval'],
@@ -609,6 +772,10 @@ def main():
     ap.add_argument('--concurrent', type=int, default=2, help='also time this many images in flight on the GPU')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--no-secondary', action='store_true')
+    ap.add_argument('--ref-predrawn', action='store_true', help='--impl reference: perturbed inputs drawn ahead of the loop')
+    ap.add_argument('--ref-device', default='cpu', choices=['cpu', 'cuda'],
+                    help='--impl reference: host cores (the CPU baseline) or stock PyTorch CUDA eager (harness only)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.steps is None:

@@ -17,6 +17,20 @@
 
 namespace dsr {
 
+// In-kernel profiling stamps (bench.py roofline): the span from the moment the kernel's dependencies are satisfied
+// (after griddepcontrol.wait) to its last CTA's exit, as it runs inside the pipelined iteration.
+__device__ __forceinline__ unsigned long long prof_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void prof_begin(unsigned long long* prof) {
+  if (prof != nullptr && threadIdx.x == 0) atomicMin(prof, prof_now());
+}
+__device__ __forceinline__ void prof_end(unsigned long long* prof) {
+  if (prof != nullptr && threadIdx.x == 0) atomicMax(prof + 1, prof_now());
+}
+
 // =============================================================================================
 // conv_gemm_kernel
 // =============================================================================================
@@ -81,6 +95,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_sync();
+  prof_begin(p.prof);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -244,6 +259,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
 
   tc_fence_before();
   __syncthreads();
+  prof_end(p.prof);
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
@@ -637,6 +653,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHalo2Threads, 1)
     }
   }
   pdl_sync();
+  prof_begin(p.prof);
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
@@ -867,6 +884,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHalo2Threads, 1)
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();                     // the peer may still be reading our shared memory / signalling our barriers
+  prof_end(p.prof);
   if (warp == 1) tmem_dealloc_pair(tmem_base, 512);
 }
 
@@ -1130,6 +1148,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_sync();
+  prof_begin(p.prof);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -1219,6 +1238,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
 
   tc_fence_before();
   __syncthreads();
+  prof_end(p.prof);
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
@@ -1263,6 +1283,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_halo_kernel(const __grid_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_sync();
+  prof_begin(p.prof);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -1360,6 +1381,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_halo_kernel(const __grid_
 
   tc_fence_before();
   __syncthreads();
+  prof_end(p.prof);
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 

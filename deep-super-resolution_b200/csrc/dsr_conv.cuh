@@ -54,6 +54,7 @@ struct alignas(64) ConvGemmParams {
   acc_t* stats;           // optional [2][n_mma] (fixed point, dsr_acc.cuh): per-channel sum and sum of squares of the STORED values
   uint32_t idesc;
   int* err;
+  unsigned long long* prof;   // profiling (bench.py roofline): {min start, max end} in %globaltimer ns, or nullptr
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -119,6 +120,7 @@ struct alignas(64) HaloParams {
   //      A level with a handful of tiles then spreads over nsplit x more SMs, each with a 1 / nsplit as long MMA
   //      chain per tile.  0 or 1: no split.
   int nsplit;
+  unsigned long long* prof;  // profiling: {min start, max end} in %globaltimer ns, or nullptr
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -156,6 +158,7 @@ struct alignas(64) WgradParams {
   long long part_stride;     // = ntaps_total * 128 * ldw
   uint32_t idesc64, idesc16;
   int* err;
+  unsigned long long* prof;  // profiling: {min start, max end} in %globaltimer ns, or nullptr
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -200,6 +203,7 @@ struct alignas(64) WgHaloParams {
   long long part_stride;
   uint32_t idesc_base;         // kind::f16, both operands MN-major, M = 128, N field left 0
   int* err;
+  unsigned long long* prof;    // profiling: {min start, max end} in %globaltimer ns, or nullptr
 };
 
 }  // namespace dsr

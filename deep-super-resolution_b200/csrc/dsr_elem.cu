@@ -2641,6 +2641,23 @@ int launch_step_begin(float* state, float* loss_base, int t_set, float lr, float
 }
 
 // =============================================================================================
+// profiling gate: keeps the stream busy for `ns` nanoseconds so that the host can enqueue a whole profiled iteration
+// (every launch bracketed by events) AHEAD of the GPU -- the event intervals then hold GPU time only, not the host's
+// launch latency
+// =============================================================================================
+__global__ void spin_kernel(unsigned long long ns) {
+  unsigned long long t0, t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  do {
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  } while (t - t0 < ns);
+}
+int launch_spin(unsigned long long ns, cudaStream_t s) {
+  spin_kernel<<<1, 1, 0, s>>>(ns);
+  DSR_LAUNCH_CHECK();
+}
+
+// =============================================================================================
 // running statistics
 // =============================================================================================
 __global__ void bn_running_kernel(const BnRunDesc* __restrict__ table, const acc_t* __restrict__ ws,

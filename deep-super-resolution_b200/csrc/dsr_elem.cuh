@@ -186,6 +186,9 @@ int launch_adam(float* p, const float* g, float* m, float* v, long long n, float
 int launch_step_begin(float* state, float* loss_base, int t_set, float lr, float b1, float b2, cudaStream_t s,
                       const float* gs = nullptr);
 
+// busy-waits `ns` nanoseconds on the stream (profiling: lets the host run ahead of the GPU)
+int launch_spin(unsigned long long ns, cudaStream_t s);
+
 // ---- Lanczos downsampler (fp32 NCHW) -------------------------------------------------------
 struct DsTables {           // device tables built by the plan (dsr_downsampler.cu)
   const float* taps;        // [k] normalised 1-D taps (fp32)

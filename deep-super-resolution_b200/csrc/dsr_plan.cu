@@ -35,6 +35,7 @@ constexpr int kNC = 128;       // n33d = n33u (DIP.py:170-171)
 constexpr int kNS = 4;         // skip_n11   (DIP.py:172)
 constexpr int kCat = 144;      // packed concat channel pitch: 128 upsampled + 4 skip + 12 zero
 constexpr float kMomentum = 0.1f;
+constexpr int kProfSlots = 2048;
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -193,7 +194,8 @@ struct dsr_plan {
   // optional per-launch timing of the tensor-core kernels (bench.py roofline): class 0 = halo-tile conv (3x3
   // stride-1 fprop + dgrad), 1 = wgrad, 2 = generic implicit-GEMM conv (stride-2 layers, 32-channel input), 3 = halo-tile
   // conv on 1x1 layers (memory-bound)
-  struct ProfRec { int cls; cudaEvent_t a, b; double flops; };
+  struct ProfRec { int cls; cudaEvent_t a, b; double flops; int slot; };
+  Buf prof_slots;                // kProfSlots x {min start, max end} %globaltimer stamps written by the kernels themselves
   std::vector<ProfRec> prof;
   struct AllRec { const char* what; cudaEvent_t a, b; };
   std::vector<AllRec> allprof;
@@ -813,10 +815,13 @@ struct ProfScope {
   dsr_plan* p;
   cudaStream_t s;
   dsr_plan::ProfRec r;
+  unsigned long long* slot = nullptr;      // device {min start, max end} pair the kernel stamps, or nullptr
   ProfScope(dsr_plan* p_, int cls, double flops, cudaStream_t s_) : p(p_), s(s_) {
     if (!p->profile) return;
     r.cls = cls;
     r.flops = flops;
+    r.slot = static_cast<int>(p->prof.size()) < kProfSlots ? static_cast<int>(p->prof.size()) : -1;
+    if (r.slot >= 0 && p->profile == 1) slot = static_cast<unsigned long long*>(p->prof_slots.ptr) + 2 * r.slot;
     cudaEventCreate(&r.a);
     cudaEventCreate(&r.b);
     cudaEventRecord(r.a, s);
@@ -830,25 +835,52 @@ struct ProfScope {
 int run_fprop(dsr_plan* p, ConvLayer& c, cudaStream_t s) {
   if (p->debug_conv) return launch_conv_ref(c.fprop, c.ref_in, c.ref_wf, s);
   ProfScope ps(p, (c.has_halo && p->use_halo) ? (c.k == 1 ? 3 : 0) : 2, conv_flops(c), s);
-  if (c.has_halo && p->use_halo) return launch_conv_halo(c.hfprop, p->num_sms, s);
-  return launch_conv_gemm(c.fprop, p->num_sms, s);
+  if (c.has_halo && p->use_halo) {
+    if (ps.slot == nullptr) return launch_conv_halo(c.hfprop, p->num_sms, s);
+    HaloParams hp = c.hfprop;
+    hp.prof = ps.slot;
+    return launch_conv_halo(hp, p->num_sms, s);
+  }
+  if (ps.slot == nullptr) return launch_conv_gemm(c.fprop, p->num_sms, s);
+  ConvGemmParams gp = c.fprop;
+  gp.prof = ps.slot;
+  return launch_conv_gemm(gp, p->num_sms, s);
 }
 int run_dgrad(dsr_plan* p, ConvLayer& c, int i, cudaStream_t s) {
   if (p->debug_conv) return launch_conv_ref(c.dgrad[i], c.ref_dr, c.ref_wd, s);
   if (c.has_merged && !getenv("DSR_NO_MERGE")) {        // one launch covers all parity classes
     if (i > 0) return 0;
     ProfScope ps(p, 2, conv_flops(c), s);
-    return launch_conv_gemm(c.dgrad_merged, p->num_sms, s);
+    if (ps.slot == nullptr) return launch_conv_gemm(c.dgrad_merged, p->num_sms, s);
+    ConvGemmParams gp = c.dgrad_merged;
+    gp.prof = ps.slot;
+    return launch_conv_gemm(gp, p->num_sms, s);
   }
   ProfScope ps(p, (c.has_halo && p->use_halo) ? (c.k == 1 ? 3 : 0) : 2, conv_flops(c) / c.ndgrad, s);
-  if (c.has_halo && p->use_halo) return launch_conv_halo(c.hdgrad, p->num_sms, s);
-  return launch_conv_gemm(c.dgrad[i], p->num_sms, s);
+  if (c.has_halo && p->use_halo) {
+    if (ps.slot == nullptr) return launch_conv_halo(c.hdgrad, p->num_sms, s);
+    HaloParams hp = c.hdgrad;
+    hp.prof = ps.slot;
+    return launch_conv_halo(hp, p->num_sms, s);
+  }
+  if (ps.slot == nullptr) return launch_conv_gemm(c.dgrad[i], p->num_sms, s);
+  ConvGemmParams gp = c.dgrad[i];
+  gp.prof = ps.slot;
+  return launch_conv_gemm(gp, p->num_sms, s);
 }
 int run_wgrad(dsr_plan* p, ConvLayer& c, cudaStream_t s) {
   if (p->debug_conv) return launch_wgrad_ref(c.wgrad, c.ref_dr, c.ref_in, s);
   ProfScope ps(p, 1, conv_flops(c), s);
-  if (c.has_hwgrad) return launch_wgrad_halo(c.hwgrad, s);
-  return launch_wgrad(c.wgrad, s);
+  if (c.has_hwgrad) {
+    if (ps.slot == nullptr) return launch_wgrad_halo(c.hwgrad, s);
+    WgHaloParams wp = c.hwgrad;
+    wp.prof = ps.slot;
+    return launch_wgrad_halo(wp, s);
+  }
+  if (ps.slot == nullptr) return launch_wgrad(c.wgrad, s);
+  WgradParams wp = c.wgrad;
+  wp.prof = ps.slot;
+  return launch_wgrad(wp, s);
 }
 
 // `next` != nullptr: c is the last encoder conv of a level whose activation feeds level `next`'s skip branch; the
@@ -1251,6 +1283,7 @@ int dsr_plan_create(dsr_plan_t** out, int H, int W, int input_depth, int num_sca
   ws.take(p->pack_table, sizeof(PackDesc) * 4 * num_scales);
   ws.take(p->bnrun_table, sizeof(BnRunDesc) * 6 * num_scales);
   ws.take(p->small_table, sizeof(SmallGradDesc) * (num_scales + 2));
+  ws.take(p->prof_slots, sizeof(unsigned long long) * 2 * kProfSlots);
   ws.take(p->errword, 256);
   ws.take(p->gscale, 256);
   ws.take(p->stepstate, 256);
@@ -1384,7 +1417,7 @@ int dsr_plan_bind(dsr_plan_t* p, void* workspace, size_t bytes, void* stream) {
     resolve(L.dsraw); resolve(L.g_d2a);
     for (ConvLayer* c : {&L.d1, &L.d2, &L.u1, &L.u2}) { resolve(c->raw); resolve(c->act); resolve(c->dr); resolve(c->gin); }
   }
-  resolve(p->warena); resolve(p->pack_table); resolve(p->bnrun_table); resolve(p->small_table); resolve(p->wg_part); resolve(p->errword); resolve(p->gscale); resolve(p->stepstate);
+  resolve(p->warena); resolve(p->pack_table); resolve(p->bnrun_table); resolve(p->small_table); resolve(p->prof_slots); resolve(p->wg_part); resolve(p->errword); resolve(p->gscale); resolve(p->stepstate);
   e = cudaMemcpyAsync(p->pack_table.ptr, p->pack_host.data(), sizeof(PackDesc) * p->pack_host.size(),
                       cudaMemcpyHostToDevice, s);
   if (e != cudaSuccess) return static_cast<int>(e);
@@ -1612,6 +1645,9 @@ static int enqueue_step(dsr_plan_t* p, const dsr_downsampler_t* d, const dsr_ste
   const long long nz = static_cast<long long>(p->input_depth) * p->H * p->W;
   int total = 0;
   if (timeline_enabled()) g_timeline.n = 0;          // every (eager or captured) iteration stamps slots 0 .. n - 1
+  // profiled pass: the launches are enqueued eagerly, each bracketed by events; a busy-wait in front lets the host
+  // get ahead so that the intervals measure the GPU, not the host's launch rate
+  if (p->profile == 1 && launch_spin(4000000ull, s)) return -1;
   int rc = launch_step_begin(st, losses, t_set, lr, 0.9f, 0.999f, s, static_cast<const float*>(p->gscale.ptr));
   if (rc) return rc;
   total += 1;
@@ -1794,6 +1830,21 @@ int dsr_plan_debug_replay(dsr_plan_t* p, const char* layer, int what, int use_ch
   }
   return -1;
 }
+// in-kernel stamps of the recorded launches (device -> host after a full synchronisation)
+static int prof_stamps(dsr_plan_t* p, std::vector<unsigned long long>& out) {
+  out.assign(2 * kProfSlots, 0ull);
+  if (!p->bound || p->prof_slots.ptr == nullptr) return 0;
+  if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+  return cudaMemcpy(out.data(), p->prof_slots.ptr, out.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -1;
+}
+// milliseconds of one recorded launch: the kernel's own stamps (dependencies satisfied -> last CTA done) when it
+// wrote them, else the event interval around the launch
+static double prof_ms(const std::vector<unsigned long long>& st, int slot, float event_ms) {
+  if (slot >= 0 && st[2 * slot + 1] > st[2 * slot] && st[2 * slot] != ~0ull)
+    return static_cast<double>(st[2 * slot + 1] - st[2 * slot]) * 1e-6;
+  return event_ms;
+}
+
 int dsr_plan_set_profile(dsr_plan_t* p, int on) {
   if (!p) return -1;
   for (auto& r : p->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
@@ -1801,6 +1852,12 @@ int dsr_plan_set_profile(dsr_plan_t* p, int on) {
   for (auto& r : p->allprof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   p->allprof.clear();
   p->profile = (on == 2) ? 2 : (on ? 1 : 0);
+  if (p->profile == 1 && p->bound) {               // re-arm the in-kernel stamp slots: {min start = max, max end = 0}
+    std::vector<unsigned long long> init(2 * kProfSlots);
+    for (int i = 0; i < kProfSlots; ++i) { init[2 * i] = ~0ull; init[2 * i + 1] = 0ull; }
+    cudaError_t e = cudaMemcpy(p->prof_slots.ptr, init.data(), init.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return static_cast<int>(e);
+  }
   return 0;
 }
 // profile mode 2: writes "<microseconds>\t<call site>" lines for every launch recorded since set_profile(2)
@@ -1826,6 +1883,8 @@ int dsr_plan_profile_read(dsr_plan_t* p, int cls, double* ms_total, double* flop
   if (!p) return -1;
   double ms = 0.0, fl = 0.0;
   int n = 0;
+  std::vector<unsigned long long> stamps;
+  if (prof_stamps(p, stamps)) return -1;
   for (auto& r : p->prof) {
     if (r.cls != cls) continue;
     cudaError_t e = cudaEventSynchronize(r.b);
@@ -1833,7 +1892,7 @@ int dsr_plan_profile_read(dsr_plan_t* p, int cls, double* ms_total, double* flop
     float t = 0.f;
     e = cudaEventElapsedTime(&t, r.a, r.b);
     if (e != cudaSuccess) return static_cast<int>(e);
-    ms += t;
+    ms += prof_ms(stamps, r.slot, t);
     fl += r.flops;
     ++n;
   }
@@ -1848,6 +1907,8 @@ int dsr_plan_profile_top(dsr_plan_t* p, int cls, double* ms_mean, double* flops)
   if (!p) return -1;
   double best = 0.0, ms = 0.0;
   int n = 0;
+  std::vector<unsigned long long> stamps;
+  if (prof_stamps(p, stamps)) return -1;
   for (auto& r : p->prof)
     if (r.cls == cls && r.flops > best) best = r.flops;
   for (auto& r : p->prof) {
@@ -1855,7 +1916,7 @@ int dsr_plan_profile_top(dsr_plan_t* p, int cls, double* ms_mean, double* flops)
     if (cudaEventSynchronize(r.b) != cudaSuccess) return -1;
     float t = 0.f;
     cudaEventElapsedTime(&t, r.a, r.b);
-    ms += t;
+    ms += prof_ms(stamps, r.slot, t);
     ++n;
   }
   if (ms_mean) *ms_mean = n ? ms / n : 0.0;

@@ -136,6 +136,9 @@ int dsr_plan_debug_replay(dsr_plan_t* p, const char* layer, int what, int use_ch
  * conv kernel, 3x3 stride-1 fprop + dgrad launches (tensor-bound), 1 = wgrad kernels, 2 = generic implicit-GEMM conv
  * kernel: stride-2 layers, 3 = halo-tile conv kernel, 1x1 launches (64 FLOP per byte: HBM-bound)), the event-measured milliseconds, the algorithmic FLOPs
  * (2*M*N*K per pass, true channel counts) and the number of launches recorded since; it synchronises on them. */
+/* set_profile(p, 1): the tensor-core kernels stamp %globaltimer themselves -- the span from the moment their
+ * dependencies are satisfied to their last CTA's exit, with the pipeline's programmatic overlap intact -- and
+ * profile_read / profile_top report those spans (event intervals only for launches without stamps). */
 int dsr_plan_set_profile(dsr_plan_t* p, int on);
 int dsr_plan_profile_read(dsr_plan_t* p, int cls, double* ms_total, double* flops_total, int* launches);
 /* set_profile(p, 2): every launch of forward / backward is bracketed by events on the main stream (side stream and

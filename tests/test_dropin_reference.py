@@ -31,5 +31,5 @@ def test_reference_driver_over_the_drop_in_modules():
     print(f"reference DIP.DIP_ISR over dsr_b200 at 256^2: {r['it_per_s']:.1f} it/s incl. set-up; PSNR {r['psnrs']}")
     assert r['modules'].startswith('deep-super-resolution_b200/')
     assert r['resolved_shape'] == [1, 3, 256, 256] and len(r['psnrs']) == 4 and len(r['ssims']) == 4
-    assert r['psnrs'][-1] > r['psnrs'][0] + 1.0 and r['ssims'][-1] > r['ssims'][0]      # the fit improves
+    assert r['psnrs'][-1] > r['psnrs'][0] + 0.5 and r['ssims'][-1] > r['ssims'][0]      # the fit improves (logged at it 0 .. 75)
     assert r['final_psnr'] > r['psnrs'][0]
