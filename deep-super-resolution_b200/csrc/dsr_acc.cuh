@@ -28,7 +28,16 @@ __device__ __forceinline__ acc_t acc_fix(float v, float scale) {
   // saturating conversion (cvt.rni.s64.f32 saturates; NaN -> 0)
   return static_cast<acc_t>(__float2ll_rn(v * scale));
 }
-__device__ __forceinline__ float acc_val(acc_t a, float inv) { return __ll2float_rn(static_cast<long long>(a)) * inv; }
+// 64-bit integer -> float through two 32-bit conversions (I2F.S64 is a slow multi-instruction sequence and sits at the
+// head of every consumer kernel's dependency chain): |value| = hi * 2^32 + lo
+// of the magnitude (sign handled separately: the pieces of a small negative number would cancel catastrophically)
+__device__ __forceinline__ float acc_val(acc_t a, float inv) {
+  const long long sv = static_cast<long long>(a);
+  const unsigned long long mag = static_cast<unsigned long long>(sv < 0 ? -sv : sv);
+  const unsigned int hi = static_cast<unsigned int>(mag >> 32), lo = static_cast<unsigned int>(mag);
+  const float m = fmaf(static_cast<float>(hi), 4294967296.f, static_cast<float>(lo)) * inv;
+  return sv < 0 ? -m : m;
+}
 
 __device__ __forceinline__ void acc_add_f(acc_t* p, float v) { atomicAdd(p, acc_fix(v, kAccFwdScale)); }
 __device__ __forceinline__ void acc_add_b(acc_t* p, float v) { atomicAdd(p, acc_fix(v, kAccBwdScale)); }

@@ -260,6 +260,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
   tc_fence_before();
   __syncthreads();
   prof_end(p.prof);
+  ks_end();
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
@@ -885,6 +886,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHalo2Threads, 1)
   __syncthreads();
   cluster_sync_all();                     // the peer may still be reading our shared memory / signalling our barriers
   prof_end(p.prof);
+  ks_end();
   if (warp == 1) tmem_dealloc_pair(tmem_base, 512);
 }
 
@@ -1239,6 +1241,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
   tc_fence_before();
   __syncthreads();
   prof_end(p.prof);
+  ks_end();
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
@@ -1382,6 +1385,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_halo_kernel(const __grid_
   tc_fence_before();
   __syncthreads();
   prof_end(p.prof);
+  ks_end();
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
@@ -1552,5 +1556,7 @@ int launch_wgrad(const WgradParams& p, cudaStream_t stream) {
   if (p.part != nullptr) launch_wgrad_reduce(p.part, p.part_stride, p.nsplit, p.dw, stream);
   return static_cast<int>(cudaGetLastError());
 }
+
+DSR_KSTAMP_SETTER(kstamp_set_conv)
 
 }  // namespace dsr

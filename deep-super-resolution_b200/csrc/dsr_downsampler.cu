@@ -232,4 +232,6 @@ void ds_bwd_table(int n, int on, int factor, int k, int pad, const std::vector<f
   }
 }
 
+DSR_KSTAMP_SETTER(kstamp_set_ds)
+
 }  // namespace dsr

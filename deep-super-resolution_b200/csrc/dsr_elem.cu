@@ -487,6 +487,7 @@ __global__ void __launch_bounds__(kThreads) bn_act_kernel(const __half* __restri
       acc_add_f(&sf.stats[threadIdx.x], t);
     }
   }
+  ks_end();
 }
 
 inline int warp_grid(int H, int W, int cap_blocks) {      // one warp per kPixUnroll pixels per iteration
@@ -2360,18 +2361,25 @@ __device__ __forceinline__ void upcat_bwd_elem_body(const UpcatBwdArgs& a, __hal
       cs1[j] += __shfl_xor_sync(0xffffffffu, cs1[j], 16);
       cs2[j] += __shfl_xor_sync(0xffffffffu, cs2[j], 16);
     }
-    __shared__ acc_t cred[256];                  // fixed point: the block sum does not depend on the arrival order
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) cred[i] = 0ull;
-    __syncthreads();
+    // per-warp partials parked in shared memory, added in warp order by one thread per channel: no shared-memory
+    // atomics (CAS loops, and their arrival order would make the sum run-dependent)
+    __shared__ float cscr[kThreads / 32][16][16];
+    const int w = threadIdx.x >> 5, g16 = threadIdx.x & 15;
     if ((threadIdx.x & 31) < 16) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        acc_add_b(&cred[c0 + j], cs1[j]);
-        acc_add_b(&cred[128 + c0 + j], cs2[j]);
+        cscr[w][j][g16] = cs1[j];
+        cscr[w][8 + j][g16] = cs2[j];
       }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) atomicAdd(&a.cons_bstats[i], cred[i]);
+    {
+      const int q = threadIdx.x >> 7, c = threadIdx.x & 127, n = q * 8 + (c & 7), gg = c >> 3;     // channel c = 8 gg + (c & 7)
+      float t = 0.f;
+#pragma unroll
+      for (int ww = 0; ww < kThreads / 32; ++ww) t += cscr[ww][n][gg];
+      acc_add_b(&a.cons_bstats[threadIdx.x], t);
+    }
   }
 }
 
@@ -2766,5 +2774,7 @@ int launch_perturb(const float* z_saved, float* z, long long n, float sigma, uns
   launch_k(perturb_kernel, dim3(grid_for((n + 3) / 4, kThreads, 148 * 8)), dim3(kThreads), 0, s, z_saved, z, n, sigma, seed, offset, state);
   DSR_LAUNCH_CHECK();
 }
+
+DSR_KSTAMP_SETTER(kstamp_set_elem)
 
 }  // namespace dsr

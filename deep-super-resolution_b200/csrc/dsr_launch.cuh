@@ -24,10 +24,55 @@ namespace dsr {
 
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// ---- in-kernel stamps (diagnostics, -DDSR_KSTAMP builds only; DSR_TIMELINE=2 at run time): thread 0 of block 0 of
+// every kernel records %globaltimer at entry and after its griddepcontrol.wait (record index = arrival order), and
+// ks_end() adds the time at which block 0 finished its body.  No extra launches, so the programmatic overlap of the
+// replayed graph is untouched.
+#ifdef DSR_KSTAMP
+static __device__ unsigned long long* g_ks_buf = nullptr;   // [0] counter, then 4 words per record
+__device__ __forceinline__ unsigned long long ks_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+static __device__ unsigned int g_ks_slot;                    // record index of the running kernel (block 0 writes it)
+#endif
 __device__ __forceinline__ void pdl_sync() {
+#ifdef DSR_KSTAMP
+  const bool rec = (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) && g_ks_buf != nullptr;
+  unsigned long long t0 = 0;
+  if (rec) t0 = ks_now();
+#endif
   pdl_wait();
+#ifdef DSR_KSTAMP
+  if (rec) {
+    const unsigned long long t1 = ks_now();
+    const unsigned long long idx = atomicAdd(g_ks_buf, 1ull) % 4000ull;     // ring: the dump reads the last iteration
+    {
+      g_ks_buf[1 + 4 * idx] = t0;
+      g_ks_buf[2 + 4 * idx] = t1;
+      g_ks_buf[3 + 4 * idx] = 0;
+      g_ks_buf[4 + 4 * idx] = (static_cast<unsigned long long>(gridDim.x * gridDim.y * gridDim.z) << 32) | blockDim.x;
+      g_ks_slot = static_cast<unsigned int>(idx);
+    }
+  }
+#endif
   pdl_trigger();
 }
+// end-of-body stamp of block 0 (call where every thread of the block is done, thread 0 records)
+__device__ __forceinline__ void ks_end() {
+#ifdef DSR_KSTAMP
+  if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && g_ks_buf != nullptr && g_ks_slot < 4000)
+    g_ks_buf[3 + 4 * g_ks_slot] = ks_now();
+#endif
+}
+#ifdef DSR_KSTAMP
+#define DSR_KSTAMP_SETTER(name) \
+  void name(unsigned long long* buf) { cudaMemcpyToSymbol(g_ks_buf, &buf, sizeof(buf)); }
+#else
+#define DSR_KSTAMP_SETTER(name) \
+  void name(unsigned long long*) {}
+#endif
 
 inline bool pdl_enabled() {
   static const bool on = [] {
@@ -49,13 +94,14 @@ struct Timeline {
 };
 constexpr int kTimelineSlots = 2048;
 inline Timeline g_timeline;
-inline bool timeline_enabled() {
-  static const bool on = [] {
+inline int timeline_mode() {
+  static const int mode = [] {
     const char* e = getenv("DSR_TIMELINE");
-    return e != nullptr && e[0] == '1';
+    return e != nullptr ? atoi(e) : 0;
   }();
-  return on;
+  return mode;
 }
+inline bool timeline_enabled() { return timeline_mode() != 0; }
 static __global__ void timeline_stamp_kernel(unsigned long long* buf, int idx) {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -71,7 +117,7 @@ inline void timeline_stamp(const void* fn, unsigned grid, cudaStream_t s) {
   t.fn[t.n] = fn;
   t.grid[t.n] = grid;
   t.stream[t.n] = s;
-  timeline_stamp_kernel<<<1, 1, 0, s>>>(t.buf, t.n);
+  if (timeline_mode() == 1) timeline_stamp_kernel<<<1, 1, 0, s>>>(t.buf, t.n);
   ++t.n;
 }
 

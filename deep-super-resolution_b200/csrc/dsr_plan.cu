@@ -1396,6 +1396,7 @@ int dsr_plan_bn_info(const dsr_plan_t* p, int idx, char* name, int name_cap, lon
 }
 size_t dsr_plan_workspace_bytes(const dsr_plan_t* p) { return p ? p->ws_bytes : 0; }
 
+static void kstamp_arm();
 int dsr_plan_bind(dsr_plan_t* p, void* workspace, size_t bytes, void* stream) {
   if (!p || !workspace) return -1;
   if (bytes < p->ws_bytes) return -8;
@@ -1444,6 +1445,7 @@ int dsr_plan_bind(dsr_plan_t* p, void* workspace, size_t bytes, void* stream) {
       cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming);
     }
   }
+  kstamp_arm();
   p->use_side = getenv("DSR_NO_SIDE_STREAM") ? 0 : 1;
   p->use_graph = getenv("DSR_NO_GRAPH") ? 0 : 1;
   p->fuse_top = getenv("DSR_NO_FUSE_TOP") ? 0 : 1;
@@ -1749,9 +1751,54 @@ int dsr_dip_run(dsr_plan_t* p, const dsr_downsampler_t* d, const dsr_step_buffer
 }
 
 // ---- in-graph timeline (DSR_TIMELINE=1; see dsr_launch.cuh) -------------------------------------------
+extern "C++" {
+namespace dsr {
+void kstamp_set_conv(unsigned long long*);
+void kstamp_set_elem(unsigned long long*);
+void kstamp_set_ds(unsigned long long*);
+}
+}
+static unsigned long long* g_ks_dev = nullptr;
+static void kstamp_arm() {                       // DSR_TIMELINE=2 (-DDSR_KSTAMP builds): in-kernel stamps
+  if (timeline_mode() != 2 || g_ks_dev != nullptr) return;
+  if (cudaMalloc(&g_ks_dev, (1 + 4 * 4000) * sizeof(unsigned long long)) != cudaSuccess) { g_ks_dev = nullptr; return; }
+  cudaMemset(g_ks_dev, 0, (1 + 4 * 4000) * sizeof(unsigned long long));
+  kstamp_set_conv(g_ks_dev);
+  kstamp_set_elem(g_ks_dev);
+  kstamp_set_ds(g_ks_dev);
+}
+// one line per launch of the LAST iteration: index, entry -> wait-done (us), wait-done -> next launch's wait-done (us),
+// wait-done -> end of block 0's body (us, 0 if the kernel has no end stamp), grid, name
+static int kstamp_dump(char* buf, size_t cap) {
+  Timeline& t = g_timeline;
+  if (g_ks_dev == nullptr || t.n == 0) return 0;
+  if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+  std::vector<unsigned long long> h(1 + 4 * 4000);
+  if (cudaMemcpy(h.data(), g_ks_dev, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  const long long total = static_cast<long long>(h[0]);
+  size_t off = 0;
+  int w = snprintf(buf + off, cap - off, "# records %lld, launches per iteration (host list) %d\n", total, t.n);
+  off += w;
+  if (total < t.n) return static_cast<int>(off);
+  for (int i = 0; i < t.n; ++i) {
+    const long long r = (total - t.n + i) % 4000, rn = (total - t.n + i + 1) % 4000;
+    const unsigned long long t0 = h[1 + 4 * r], t1 = h[2 + 4 * r], te = h[3 + 4 * r], gb = h[4 + 4 * r];
+    const unsigned long long t1n = (i + 1 < t.n) ? h[2 + 4 * rn] : t1;
+    const char* name = "?";
+    cudaFuncGetName(&name, t.fn[i]);
+    w = snprintf(buf + off, cap - off, "%d\t%.2f\t%.2f\t%.2f\t%u/%u\t%u\t%s\n", i, (double)(t1 - t0) * 1e-3,
+                 (double)(t1n - t1) * 1e-3, te > t1 ? (double)(te - t1) * 1e-3 : 0.0, (unsigned)(gb >> 32),
+                 (unsigned)(gb & 0xffffffffu), t.grid[i], name);
+    if (w < 0 || static_cast<size_t>(w) >= cap - off) break;
+    off += w;
+  }
+  return static_cast<int>(off);
+}
+
 int dsr_timeline_dump(char* buf, size_t cap) {
   if (buf == nullptr || cap == 0) return -1;
   buf[0] = 0;
+  if (timeline_mode() == 2) return kstamp_dump(buf, cap);
   Timeline& t = g_timeline;
   if (!timeline_enabled() || t.buf == nullptr || t.n == 0) return 0;
   if (cudaDeviceSynchronize() != cudaSuccess) return -1;

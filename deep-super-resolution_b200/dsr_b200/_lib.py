@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), 'libdsr_b200.so')
+# DSR_B200_LIB: another build of the same library (diagnostics builds such as `make kstamp`)
+LIB_PATH = os.environ.get('DSR_B200_LIB') or os.path.join(os.path.dirname(_HERE), 'libdsr_b200.so')
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(

@@ -46,6 +46,17 @@ for scales in scales_list:
     torch.cuda.synchronize()
     print(f'size {size} num_scales {scales}: {e0.elapsed_time(e1) / iters * 1e3:8.1f} us / iteration, '
           f'{lib.dsr_plan_last_launches(plan.handle)} launches, loss {float(losses[iters + 4]):.5f}', flush=True)
+    if os.environ.get('DSR_TIMELINE') == '2':          # in-kernel stamps (make kstamp; DSR_B200_LIB=...kstamp.so)
+        buf = C.create_string_buffer(1 << 20)
+        lib.dsr_timeline_dump(buf, 1 << 20)
+        import re
+        print('  #  lead  total   body  grid  name     (lead: entry -> wait done; total: wait done -> next wait done; body: block 0)')
+        for l in buf.value.decode().splitlines():
+            if l.startswith('#'):
+                print(l); continue
+            i, lead, tot, body, gb, g, name = l.split('\t')
+            print(f'{int(i):4d} {float(lead):6.2f} {float(tot):6.2f} {float(body):6.2f} {gb:>9s}  ' +
+                  re.sub(r'\(.*', '', name).replace('void ', '').replace('dsr::', '')[:60])
     if os.environ.get('DSR_TIMELINE') == '1':
         buf = C.create_string_buffer(1 << 20)
         nbytes = lib.dsr_timeline_dump(buf, 1 << 20)
