@@ -1259,24 +1259,25 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_halo_kernel(const __grid_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int group = blockIdx.x / p.nsplit;
-  const int split = blockIdx.x % p.nsplit;
+  const int cl3 = p.cl3;
+  const int group = cl3 ? static_cast<int>(cluster_ctarank()) : static_cast<int>(blockIdx.x) / p.nsplit;
+  const int split = cl3 ? static_cast<int>(blockIdx.x) / 3 : static_cast<int>(blockIdx.x) % p.nsplit;
   const int npb = p.pb_x * p.pb_y;
   const int pb_begin = static_cast<int>((static_cast<long long>(npb) * split) / p.nsplit);
   const int pb_end = static_cast<int>((static_cast<long long>(npb) * (split + 1)) / p.nsplit);
   const int nkb = pb_end - pb_begin;
-  const int ncols = p.n64 * 64 + p.n16 * 16;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.a64);
-    tma_prefetch_desc(&p.b64[0]);
+    tma_prefetch_desc(&p.b64[cl3 ? 1 : 0]);
     for (int s = 0; s < kWgHStages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], cl3 ? 3 : 1);       // cl3: a stage is rewritten in all three CTAs at once
     }
     mbar_init(tfull_bar, 1);
     fence_barrier_init();
   }
+  if (cl3) cluster_sync_all();                      // every CTA's barriers exist before anyone multicasts into them
   if (warp == 1) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
@@ -1288,7 +1289,33 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_halo_kernel(const __grid_
   pdl_sync();
   prof_begin(p.prof);
 
-  if (warp == 0) {
+  if (warp == 0 && cl3) {
+    if (lane == 0) {
+      // every CTA of the cluster receives the whole stage; this CTA issues its third of the (multicast) loads
+      const uint32_t stage_bytes = kWgHStageA + static_cast<uint32_t>(kWgC3Rows * (p.n64 * 128 + p.n16 * 32));
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int pb = pb_begin; pb < pb_end; ++pb) {
+        const int x0 = (pb % p.pb_x) * 8;
+        const int y0 = (pb / p.pb_x) * 8;
+        mbar_wait(&empty_bar[stage], phase ^ 1, p.err, 44);
+        uint8_t* sa = smem + stage * kWgHStageBytes;
+        uint8_t* sb = sa + kWgHStageA;
+        mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
+        if (group == 0) {
+          tma_load_5d_mc(&p.a64, &full_bar[stage], sa, 0, 0, x0 + 1, 0, y0 + 1, 7);
+          tma_load_5d_mc(&p.a64, &full_bar[stage], sa + 64 * 128, 64, 0, x0 + 1, 0, y0 + 1, 7);
+        } else if (group == 1) {
+          tma_load_5d_mc(&p.b64[1], &full_bar[stage], sb, 0, 0, x0, 0, y0, 7);
+          if (p.n16)
+            tma_load_5d_mc(&p.b16[1], &full_bar[stage], sb + 2 * kWgC3Chunk, p.c16_base, 0, x0, 0, y0, 7);
+        } else {
+          tma_load_5d_mc(&p.b64[1], &full_bar[stage], sb + kWgC3Chunk, 64, 0, x0, 0, y0, 7);
+        }
+        if (++stage == kWgHStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 0) {
     if (lane == 0) {
       uint32_t stage_bytes = kWgHStageA;
       for (int b = 0; b < p.nbox; ++b)
@@ -1329,8 +1356,12 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_halo_kernel(const __grid_
         const WgRun rn = p.runs[group][r];
         const WgBox bx = p.box[group][rn.box];
         const uint32_t rows = static_cast<uint32_t>(bx.width * 8);
-        const uint32_t sb = sa + kWgHStageA + static_cast<uint32_t>(bx.off16 * 16);
-        const uint32_t sb16 = sb + static_cast<uint32_t>(p.n64) * rows * 128;
+        const uint32_t cstride = cl3 ? static_cast<uint32_t>(kWgC3Chunk) : rows * 128;     // between 64-channel chunks
+        // cl3: one 10 x 10 halo for all tap rows, this CTA's views start `group` halo rows down
+        const uint32_t row0 = cl3 ? static_cast<uint32_t>(group * bx.width) : 0u;
+        const uint32_t sb = sa + kWgHStageA + static_cast<uint32_t>(bx.off16 * 16) + row0 * 128;
+        const uint32_t sb16 = sa + kWgHStageA + static_cast<uint32_t>(bx.off16 * 16) + static_cast<uint32_t>(p.n64) * cstride +
+                              row0 * 32;
         // wide: N-chunks = taps (LBO = 1 pixel row); 8-pixel groups one box row apart
         const uint64_t hi_b = make_smem_desc(0, 128, static_cast<uint32_t>(bx.width) * 128, SWZ_128B);
         const uint64_t hi_b16 = p.merge_narrow ? make_smem_desc(0, 32, static_cast<uint32_t>(bx.width) * 32, SWZ_32B)
@@ -1345,7 +1376,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_halo_kernel(const __grid_
           for (int ks = 0; ks < 4; ++ks) {
             const uint64_t da = hi_a | static_cast<uint64_t>(((sa + ks * 2048) & 0x3FFFF) >> 4);
             for (int c = 0; c < p.n64; ++c) {
-              const uint64_t db = hi_b | static_cast<uint64_t>(((b0 + c * rows * 128 + ks * kstep * 128) & 0x3FFFF) >> 4);
+              const uint64_t db = hi_b | static_cast<uint64_t>(((b0 + c * cstride + ks * kstep * 128) & 0x3FFFF) >> 4);
               umma_f16(cw + static_cast<uint32_t>(c * rn.r * 64), da, db, id_w, (k | ks) != 0);
             }
             if (p.n16) {
@@ -1357,7 +1388,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_halo_kernel(const __grid_
         __syncwarp();
       }
       if (elect_one()) {
-        umma_commit(&empty_bar[stage]);
+        if (cl3) umma_commit_mc(&empty_bar[stage], 7);
+        else umma_commit(&empty_bar[stage]);
         if (k == nkb - 1) umma_commit(tfull_bar);
       }
       __syncwarp();
@@ -1384,6 +1416,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_halo_kernel(const __grid_
 
   tc_fence_before();
   __syncthreads();
+  if (cl3) cluster_sync_all();            // peers may still multicast into this CTA's barriers until their last commit
   prof_end(p.prof);
   ks_end();
   if (warp == 1) tmem_dealloc(tmem_base, 512);
@@ -1532,6 +1565,30 @@ static void launch_wgrad_reduce(const float* part, long long stride, int nsplit,
   launch_k(wgrad_reduce_kernel, dim3(static_cast<int>(blocks)), dim3(256), 0, stream, part, stride, nsplit, dw, n4);
 }
 
+// how many 3-CTA clusters of wgrad_halo_kernel the device can hold at once (clusters live inside one GPC: 148 SMs do not
+// hold 49 of them, and a 49th cluster would run as a second wave)
+int wgrad_cluster_capacity() {
+  static int cap_dev[kMaxDevices] = {};
+  int& cap = cap_dev[device_slot()];
+  if (cap > 0) return cap;
+  if (cudaFuncSetAttribute(wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgHSmemBytes) != cudaSuccess) return 0;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(3 * 64);
+  cfg.blockDim = dim3(kWgThreads);
+  cfg.dynamicSmemBytes = kWgHSmemBytes;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 3;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, wgrad_halo_kernel, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+  cap = n;
+  return cap;
+}
+
 int launch_wgrad_halo(const WgHaloParams& p, cudaStream_t stream) {
   static bool done_dev[kMaxDevices] = {};
   bool& done = done_dev[device_slot()];
@@ -1542,7 +1599,8 @@ int launch_wgrad_halo(const WgHaloParams& p, cudaStream_t stream) {
   }
   const int grid = p.ngroups * p.nsplit;
   if (grid <= 0) return 0;
-  launch_k(wgrad_halo_kernel, dim3(grid), dim3(kWgThreads), kWgHSmemBytes, stream, p);
+  if (p.cl3) launch_k_cluster(wgrad_halo_kernel, dim3(grid), dim3(kWgThreads), kWgHSmemBytes, stream, 3, p);
+  else launch_k(wgrad_halo_kernel, dim3(grid), dim3(kWgThreads), kWgHSmemBytes, stream, p);
   if (p.part != nullptr) launch_wgrad_reduce(p.part, p.part_stride, p.nsplit, p.dw, stream);
   return static_cast<int>(cudaGetLastError());
 }

@@ -180,6 +180,9 @@ constexpr int kWgHStageA = 64 * 128 * 2;          // dR: 2 chunks of [64 px][64 
 constexpr int kWgHStageBox = 36 * 1024;           // X boxes of one stage (max: stride 2, 128 ch = 34 KB)
 constexpr int kWgHStageBytes = kWgHStageA + kWgHStageBox;
 constexpr int kWgHSmemBytes = kWgHStages * kWgHStageBytes + 1024 + 256;
+constexpr int kWgC3Rows = 100;                    // cl3: the X halo of a pixel block, 10 x 10 pixels
+constexpr int kWgC3Chunk = 13 * 1024;             // 100 rows x 128 B rounded up to the swizzle period
+static_assert(2 * kWgC3Chunk + kWgC3Rows * 32 <= kWgHStageBox, "cluster halo fits the X area of a stage");
 
 struct WgBox { int8_t px, py, dx, dy; int16_t width; int16_t off16; };   // off16: offset in the box area / 16
 // A RUN = taps of one tap row that are consecutive 1-pixel shifts of the same box.  One MMA per 64-channel chunk
@@ -195,6 +198,12 @@ struct alignas(64) WgHaloParams {
   WgRun runs[3][3];            // [group][run]
   WgCol cols[3][28];           // [group][TMEM 16-column chunk]
   int nbox, nruns, ncolchunks, ngroups;
+  // cl3 = 1 (3 x 3, stride 1): the three tap-row CTAs of one pixel range form a CLUSTER.  Per 8 x 8 pixel block the dR
+  // tile and ONE 10 x 10-pixel X halo (maps b64[1] / b16[1]) are fetched once and multicast to all three CTAs (each
+  // issues a third of the loads); tap row ky uses the views that start ky halo rows down.  L2 -> SM traffic per block:
+  // 45 KB for the cluster instead of 3 x 39 KB -- the un-clustered kernel is bound by exactly that fill rate
+  // (tensor pipe 49 % at 512 x 512).
+  int cl3;
   int merge_narrow;            // 1: narrow part of a run is one MMA (N = r x 16, LBO = 32 B); 0: n16 chunks, LBO = chunk
   int nsplit, pb_x, pb_y;
   int n64, n16, c16_base, ldw;

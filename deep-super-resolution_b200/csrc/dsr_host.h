@@ -28,6 +28,7 @@ int make_wgt_map(CUtensorMap* m, const void* base, int K, int rows, int box_k, i
 int launch_conv_gemm(const ConvGemmParams& p, int num_sms, cudaStream_t stream);
 int launch_wgrad(const WgradParams& p, cudaStream_t stream);
 int launch_wgrad_halo(const WgHaloParams& p, cudaStream_t stream);
+int wgrad_cluster_capacity();
 int launch_conv_halo(const HaloParams& p, int num_sms, cudaStream_t stream);
 int halo_smem_bytes(int n_part, int n_wide, int n_narrow, int wide_slots, int ntaps, int slot_bytes = 0);
 

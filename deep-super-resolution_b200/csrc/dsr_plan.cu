@@ -632,6 +632,12 @@ int build_conv(dsr_plan* p, ConvLayer& c) {
         return rc;
     }
     if (g.nbox == 1) { g.b64[1] = g.b64[0]; g.b16[1] = g.b16[0]; }
+    // 3 x 3 stride 1: tap-row CTAs as a cluster around one multicast 10 x 10 halo (maps in slot 1)
+    g.cl3 = (c.k == 3 && c.stride == 1 && g.merge_narrow && g.n64 == 2 && !getenv("DSR_WG_NO_CL3")) ? 1 : 0;
+    if (g.cl3) {
+      if ((rc = make_act_map(&g.b64[1], c.in_pad->ptr, 1, c.cin_pad, Wp, Hp, 1, 64, 10, 10))) return rc;
+      if (g.n16 && (rc = make_act_map(&g.b16[1], c.in_pad->ptr, 1, c.cin_pad, Wp, Hp, 1, 16, 10, 10))) return rc;
+    }
     const int npb = g.pb_x * g.pb_y;
     // split-K over pixel ranges: every CTA ends with a full-size fp32 atomic epilogue (128 x up to 432 values), so
     // small layers get few CTAs (>= kWgMinBlocks pixel blocks each) -- less atomic traffic, and SMs left free for
@@ -646,6 +652,11 @@ int build_conv(dsr_plan* p, ConvLayer& c) {
     if (p->det) {
       const long long cap = static_cast<long long>(p->wg_part.bytes / 4) / g.part_stride;
       if (nsplit > cap) nsplit = static_cast<int>(cap);
+    }
+    if (g.cl3) {
+      const int cap = getenv("DSR_WG_CL3_CAP") ? atoi(getenv("DSR_WG_CL3_CAP")) : wgrad_cluster_capacity();
+      if (cap <= 0) g.cl3 = 0;
+      else if (nsplit > cap) nsplit = cap;
     }
     g.nsplit = nsplit;
   }
@@ -870,6 +881,10 @@ int run_dgrad(dsr_plan* p, ConvLayer& c, int i, cudaStream_t s) {
 }
 int run_wgrad(dsr_plan* p, ConvLayer& c, cudaStream_t s) {
   if (p->debug_conv) return launch_wgrad_ref(c.wgrad, c.ref_dr, c.ref_in, s);
+  {                  // diagnostics only (WRONG gradients): the main stream's timeline without the weight-gradient stream
+    static const bool skip = getenv("DSR_EXP_SKIP_WGRAD") != nullptr;
+    if (skip) return 0;
+  }
   ProfScope ps(p, 1, conv_flops(c), s);
   if (c.has_hwgrad) {
     if (ps.slot == nullptr) return launch_wgrad_halo(c.hwgrad, s);

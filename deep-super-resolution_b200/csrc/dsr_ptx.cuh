@@ -236,6 +236,27 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
 }
 
 // ------------------------------------------------------------------------------------------
+// Cluster multicast (cta_group::1 kernels): one TMA load lands at the same shared-memory offset of every CTA in
+// `mask` and completes the bytes on the mbarrier at the same offset in each of them; an MMA-completion arrive can be
+// multicast the same way.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_5d_mc(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1, int c2,
+                                               int c3, int c4, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, "
+      "%5, %6, %7}], [%2], %8;" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(mask)
+      : "memory");
+}
+
+// ------------------------------------------------------------------------------------------
 // Descriptors
 // ------------------------------------------------------------------------------------------
 // Shared-memory matrix descriptor (sm_100 "version 1").  Offsets are in bytes here and stored
