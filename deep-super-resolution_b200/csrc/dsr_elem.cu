@@ -59,11 +59,12 @@ __device__ __forceinline__ void stg8(__half* p, uint2 v) { *reinterpret_cast<uin
 // Padded coordinates an interior index i in [0, n) occupies under ReflectionPad(1): itself and,
 // for i == 1 / i == n-2, the mirrored halo cell.  The same list is the set of padded cells whose
 // data-gradient folds back onto i.
-__device__ __forceinline__ int halo_coords(int i, int n, int (&o)[3]) {
+// (reflect == 0: zero padding, the halo is never written: the index occupies its own cell only)
+__device__ __forceinline__ int halo_coords(int i, int n, int (&o)[3], int reflect = 1) {
   int c = 0;
   o[c++] = i + 1;
-  if (i == 1) o[c++] = 0;
-  if (i == n - 2) o[c++] = n + 1;
+  if (reflect && i == 1) o[c++] = 0;
+  if (reflect && i == n - 2) o[c++] = n + 1;
   return c;
 }
 
@@ -80,7 +81,15 @@ __device__ __forceinline__ void bn_coeffs(const BnRef& bn, int c, float& mean, f
 __device__ __forceinline__ float lrelu(float y) { return y > 0.f ? y : kSlope * y; }
 
 // bilinear x2, align_corners = False: source index and weights for output index o
-__device__ __forceinline__ void up_src(int o, int n, int& i0, int& i1, float& l0, float& l1) {
+// (nearest != 0: nn.Upsample(mode='nearest'), source floor(o / 2) with weight 1)
+__device__ __forceinline__ void up_src(int o, int n, int& i0, int& i1, float& l0, float& l1, int nearest = 0) {
+  if (nearest) {
+    i0 = min(o >> 1, n - 1);
+    i1 = i0;
+    l0 = 1.f;
+    l1 = 0.f;
+    return;
+  }
   float src = fmaxf(0.f, 0.5f * static_cast<float>(o) - 0.25f);
   i0 = static_cast<int>(src);
   if (i0 > n - 1) i0 = n - 1;
@@ -175,7 +184,8 @@ inline int grid_for(long long items, int threads, int cap_blocks) {
 // input pack: fp32 NCHW -> fp16 padded NHWC with reflected halo
 // =============================================================================================
 // Generic packer (any C multiple of 8).
-__global__ void input_pack_kernel(const float* __restrict__ z, __half* __restrict__ xpad, int C, int H, int W) {
+__global__ void input_pack_kernel(const float* __restrict__ z, __half* __restrict__ xpad, int C, int H, int W,
+                                  int reflect) {
   pdl_sync();
   // block: 64 consecutive x of one row y; smem tile [C][65]
   extern __shared__ float tile[];
@@ -191,7 +201,7 @@ __global__ void input_pack_kernel(const float* __restrict__ z, __half* __restric
   const int groups = C >> 3;
   const int Wp = W + 2;
   int ys[3];
-  const int ny = halo_coords(y, H, ys);
+  const int ny = halo_coords(y, H, ys, reflect);
   for (int i = threadIdx.x; i < 64 * groups; i += blockDim.x) {
     const int dx = i / groups, g = i % groups;
     const int x = x0 + dx;
@@ -200,7 +210,7 @@ __global__ void input_pack_kernel(const float* __restrict__ z, __half* __restric
 #pragma unroll
     for (int j = 0; j < 8; ++j) f[j] = tile[(g * 8 + j) * 65 + dx];
     int xs[3];
-    const int nx = halo_coords(x, W, xs);
+    const int nx = halo_coords(x, W, xs, reflect);
     for (int a = 0; a < ny; ++a)
       for (int b = 0; b < nx; ++b)
         store8h(xpad + (static_cast<long long>(ys[a]) * Wp + xs[b]) * C + g * 8, f);
@@ -219,6 +229,7 @@ struct PerturbSpec {
   unsigned long long seed;
   const float* state;         // device iteration counter (state[0] = t as int bits)
   long long n4;               // ceil(C H W / 4)
+  int pad_zero;               // 1: zero padding, no reflected halo
 };
 template <bool SKIP, bool PERTURB>
 __global__ void __launch_bounds__(kThreads) input_pack32_kernel(float* __restrict__ z, __half* __restrict__ xpad, int H,
@@ -268,7 +279,7 @@ __global__ void __launch_bounds__(kThreads) input_pack32_kernel(float* __restric
   __syncthreads();
   const int Wp = W + 2;
   int ys[3];
-  const int ny = halo_coords(y, H, ys);
+  const int ny = halo_coords(y, H, ys, !ps.pad_zero);
   const int dx = threadIdx.x >> 2, g = threadIdx.x & 3;       // 64 pixels x 4 channel groups = one pass
   const int x = x0 + dx;
   const bool ok = x < W;
@@ -277,7 +288,7 @@ __global__ void __launch_bounds__(kThreads) input_pack32_kernel(float* __restric
   for (int j = 0; j < 8; ++j) f[j] = tile[(g * 8 + j) * 65 + dx];
   if (ok) {
     int xs[3];
-    const int nx = halo_coords(x, W, xs);
+    const int nx = halo_coords(x, W, xs, !ps.pad_zero);
     for (int a = 0; a < ny; ++a)
       for (int b = 0; b < nx; ++b)
         store8h(xpad + (static_cast<long long>(ys[a]) * Wp + xs[b]) * C + g * 8, f);
@@ -329,16 +340,16 @@ __global__ void __launch_bounds__(kThreads) input_pack32_kernel(float* __restric
 // z: input (perturb_zs == nullptr) or OUTPUT of the fused perturbation z = perturb_zs + sigma N(0,1)
 int launch_input_pack(float* z, void* xpad, int C, int H, int W, cudaStream_t s, const float* skip_w, float* sraw,
                       acc_t* skip_stats, const float* perturb_zs, float sigma, unsigned long long seed,
-                      const float* state) {
+                      const float* state, int pad_zero) {
   const int tiles_x = (W + 63) / 64;
   const bool fast = (C == 32) && (W % 4 == 0);
   if (!fast) {
     if (skip_w != nullptr || perturb_zs != nullptr) return -2;      // caller launches those separately
     launch_k(input_pack_kernel, dim3(H * tiles_x), dim3(kThreads), C * 65 * sizeof(float), s, z,
-             static_cast<__half*>(xpad), C, H, W);
+             static_cast<__half*>(xpad), C, H, W, pad_zero ? 0 : 1);
     DSR_LAUNCH_CHECK();
   }
-  PerturbSpec ps{perturb_zs, sigma, seed, state, (static_cast<long long>(C) * H * W + 3) / 4};
+  PerturbSpec ps{perturb_zs, sigma, seed, state, (static_cast<long long>(C) * H * W + 3) / 4, pad_zero};
   const dim3 grid(H * tiles_x), block(kThreads);
   __half* xp = static_cast<__half*>(xpad);
   if (skip_w != nullptr && perturb_zs != nullptr)
@@ -608,9 +619,15 @@ __device__ __forceinline__ UpRaw up_load(const UpBlock& t) {
   return r;
 }
 // u[r][c][j]: the four output pixels of the block, 4 channels each
-__device__ __forceinline__ void up_eval(const UpRaw& r, float (&u)[2][2][4]) {
+// (nearest: the same 2 x 2 block structure with the weights {1, 0}: output (r, c) copies source (r, c))
+__device__ __forceinline__ void up_eval(const UpRaw& r, float (&u)[2][2][4], int nearest = 0) {
   float f00[4], f01[4], f10[4], f11[4];
   cvt4h(r.v00, f00); cvt4h(r.v01, f01); cvt4h(r.v10, f10); cvt4h(r.v11, f11);
+  if (nearest) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { u[0][0][j] = f00[j]; u[0][1][j] = f01[j]; u[1][0][j] = f10[j]; u[1][1][j] = f11[j]; }
+    return;
+  }
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const float t0 = 0.75f * f00[j] + 0.25f * f01[j], t1 = 0.25f * f00[j] + 0.75f * f01[j];   // source row 0, c = 0, 1
@@ -684,7 +701,7 @@ __global__ void __launch_bounds__(kThreads, 3) upcat_stats_kernel(UpcatArgs a) {
     for (int u = 0; u < kUpUnroll; ++u) {
       if (base + u >= nblk) break;
       float v[2][2][4];
-      up_eval(r[u], v);
+      up_eval(r[u], v, a.nearest);
 #pragma unroll
       for (int rr = 0; rr < 2; ++rr)
 #pragma unroll
@@ -766,7 +783,7 @@ __global__ void __launch_bounds__(kThreads, 3) upcat_apply_kernel(UpcatArgs a) {
     for (int u = 0; u < kUpUnroll; ++u) {
       if (base + u >= nblk) break;
       float v[2][2][4];
-      up_eval(r[u], v);
+      up_eval(r[u], v, a.nearest);
       // the 16 tail channels [128, 144) of the block's four pixels: lane l < 4 evaluates the skip channels of pixel l
       uint2 mytail = make_uint2(0u, 0u);
       if (lane < 4) {
@@ -797,7 +814,7 @@ __global__ void __launch_bounds__(kThreads, 3) upcat_apply_kernel(UpcatArgs a) {
           int ny = 1, nx = 1;
           ys[0] = y + 1;
           xs[0] = x + 1;
-          if (x == 1 || x == a.W - 2 || y == 1 || y == a.H - 2) {           // warp-uniform: reflected halo copies
+          if (!a.pad_zero && (x == 1 || x == a.W - 2 || y == 1 || y == a.H - 2)) {   // warp-uniform: reflected halo copies
             ny = halo_coords(y, a.H, ys);
             nx = halo_coords(x, a.W, xs);
           }
@@ -1537,9 +1554,9 @@ int launch_bn_bwd_apply(const BnBwdArgs& a, cudaStream_t s) {
 // =============================================================================================
 // folded data-gradient of 4 channels at interior pixel (y, x) of a padded-grid tensor with channel pitch C
 __device__ __forceinline__ void fold_gather4(const __half* gp, int C, int H, int W, int y, int x, int coff, uint2 main,
-                                             float (&da)[4]) {
+                                             float (&da)[4], int fold = 1) {
   cvt4h(main, da);
-  if (x == 1 || x == W - 2 || y == 1 || y == H - 2) {
+  if (fold && (x == 1 || x == W - 2 || y == 1 || y == H - 2)) {
     int ys[3], xs[3];
     const int ny = halo_coords(y, H, ys), nx = halo_coords(x, W, xs);
     const int Wp = W + 2;
@@ -1595,7 +1612,7 @@ __global__ void __launch_bounds__(kThreads, 2) upcat_bwd_kernel(UpcatBwdArgs a) 
         vg[rr][cc] = ldg8(gc + (static_cast<long long>(y + 1) * Wp + (x + 1)) * 144 + c0);
       }
     float v[2][2][4];
-    up_eval(r, v);
+    up_eval(r, v, f.nearest);
 #pragma unroll
     for (int rr = 0; rr < 2; ++rr)
 #pragma unroll
@@ -1603,7 +1620,7 @@ __global__ void __launch_bounds__(kThreads, 2) upcat_bwd_kernel(UpcatBwdArgs a) 
         const int y = t.oy0 + rr, x = t.ox0 + cc;
         if (y < 0 || x < 0 || y >= f.H || x >= f.W) continue;               // warp-uniform
         float dc[4];
-        fold_gather4(gc, 144, f.H, f.W, y, x, c0, vg[rr][cc], dc);
+        fold_gather4(gc, 144, f.H, f.W, y, x, c0, vg[rr][cc], dc, !f.pad_zero);
         if (!APPLY) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -1627,7 +1644,7 @@ __global__ void __launch_bounds__(kThreads, 2) upcat_bwd_kernel(UpcatBwdArgs a) 
         const long long pix = static_cast<long long>(y) * f.W + x;
         float d4[4];
         fold_gather4(gc, 144, f.H, f.W, y, x, 128,
-                     ldg8(gc + (static_cast<long long>(y + 1) * Wp + (x + 1)) * 144 + 128), d4);
+                     ldg8(gc + (static_cast<long long>(y + 1) * Wp + (x + 1)) * 144 + 128), d4, !f.pad_zero);
         float sv[4], xh4[4], yv[4];
         skip_act4(sc, f.sraw, pix, sv, xh4, yv);
         float dsy[4];
@@ -1828,8 +1845,15 @@ int launch_skip_bwd(const float* dsy, const float* sraw, BnRef bn_skip, const ac
 // =============================================================================================
 // 1-D pieces for source index q (n_src sources, n_out outputs): cw[t] = U[2q-1+t][q] (t = 0..3), w = sum_t cw[t],
 // Q[k] = sum_t U[o_t][q] U[o_t][q-1+k] (k = 0..2)
-__device__ __forceinline__ void up_q(int q, int n_src, int n_out, float (&cw)[4], float& w, float (&Q)[3]) {
+__device__ __forceinline__ void up_q(int q, int n_src, int n_out, float (&cw)[4], float& w, float (&Q)[3],
+                                     int nearest = 0) {
   if (q >= 1 && 2 * q + 2 < n_out && q + 1 < n_src) {      // interior: no clamped source, all 4 outputs exist
+    if (nearest) {
+      cw[0] = 0.f; cw[1] = 1.f; cw[2] = 1.f; cw[3] = 0.f;
+      w = 2.f;
+      Q[0] = 0.f; Q[1] = 2.f; Q[2] = 0.f;
+      return;
+    }
     cw[0] = 0.25f; cw[1] = 0.75f; cw[2] = 0.75f; cw[3] = 0.25f;
     w = 2.f;
     Q[0] = 0.375f; Q[1] = 1.25f; Q[2] = 0.375f;
@@ -1844,7 +1868,7 @@ __device__ __forceinline__ void up_q(int q, int n_src, int n_out, float (&cw)[4]
     if (o >= 0 && o < n_out) {
       int i0, i1;
       float l0, l1;
-      up_src(o, n_src, i0, i1, l0, l1);
+      up_src(o, n_src, i0, i1, l0, l1, nearest);
       float c[3];
 #pragma unroll
       for (int k = 0; k < 3; ++k) c[k] = (i0 == q - 1 + k ? l0 : 0.f) + (i1 == q - 1 + k ? l1 : 0.f);
@@ -1903,8 +1927,8 @@ __device__ __forceinline__ void upcat_stats_lowres_body(const UpcatArgs& a, int 
   for (int pix = ((vblock * blockDim.x) + threadIdx.x) >> 5; pix < npix; pix += warps) {
     const int qy = pix / a.w, qx = pix - qy * a.w;
     float cwy[4], cwx[4], wy, wx, Qy[3], Qx[3];
-    up_q(qy, a.h, a.H, cwy, wy, Qy);
-    up_q(qx, a.w, a.W, cwx, wx, Qx);
+    up_q(qy, a.h, a.H, cwy, wy, Qy, a.nearest);
+    up_q(qx, a.w, a.W, cwx, wx, Qx, a.nearest);
     float qd[4], c[4] = {0, 0, 0, 0};
     q_stencil(d, a.deep_sy, a.h, a.w, qy, qx, Qy, Qx, lane, qd, c);
     stg8(static_cast<__half*>(a.qd) + static_cast<long long>(pix) * 128 + lane * 4, pack4h(qd));   // for the backward
@@ -1978,10 +2002,10 @@ int launch_upcat_stats_lowres(const UpcatArgs& a, cudaStream_t s) {
 }
 
 // weight of high-resolution index o on low-resolution index q (forward: out[o] = l0 in[i0] + l1 in[i1])
-__device__ __forceinline__ float up_weight(int o, int q, int n_src) {
+__device__ __forceinline__ float up_weight(int o, int q, int n_src, int nearest = 0) {
   int i0, i1;
   float l0, l1;
-  up_src(o, n_src, i0, i1, l0, l1);
+  up_src(o, n_src, i0, i1, l0, l1, nearest);
   return (i0 == q ? l0 : 0.f) + (i1 == q ? l1 : 0.f);
 }
 
@@ -2003,10 +2027,11 @@ constexpr int kGtRH = 2 * kGtH + 2;
 constexpr int kGtSmem = kGtRW * kGtRH * 128 * 2;          // 46 080 bytes
 
 // folded gradient of 8 channels at interior pixel (y, x): own cell + the reflected halo cells whose source it is
-__device__ __forceinline__ uint4 fold_gather8(const __half* __restrict__ gp, int C, int H, int W, int y, int x, int coff) {
+__device__ __forceinline__ uint4 fold_gather8(const __half* __restrict__ gp, int C, int H, int W, int y, int x, int coff,
+                                              int fold = 1) {
   const int Wp = W + 2;
   uint4 m = __ldg(reinterpret_cast<const uint4*>(gp + (static_cast<long long>(y + 1) * Wp + (x + 1)) * C + coff));
-  if (x == 1 || x == W - 2 || y == 1 || y == H - 2) {
+  if (fold && (x == 1 || x == W - 2 || y == 1 || y == H - 2)) {
     float acc[8];
     {
       const __half2* h = reinterpret_cast<const __half2*>(&m);
@@ -2085,7 +2110,7 @@ __device__ __forceinline__ void upT_gather_tile_body(const UpcatBwdArgs& a, uint
         const int oy = oy0 + ry, ox = ox0 + rx;
         v[u] = make_uint4(0u, 0u, 0u, 0u);
         if (i0 + u * kThreads < kItems && oy >= 0 && oy < f.H && ox >= 0 && ox < f.W)
-          v[u] = fold_gather8(gc, 144, f.H, f.W, oy, ox, c0);
+          v[u] = fold_gather8(gc, 144, f.H, f.W, oy, ox, c0, !f.pad_zero);
       }
 #pragma unroll
       for (int u = 0; u < kBatch; ++u)
@@ -2095,18 +2120,18 @@ __device__ __forceinline__ void upT_gather_tile_body(const UpcatBwdArgs& a, uint
       if (threadIdx.x < kGtH * 4) {
         const int ly = threadIdx.x >> 2, aa = threadIdx.x & 3;
         const int oy = 2 * (qy0 + ly) - 1 + aa;
-        wy_s[ly][aa] = (oy >= 0 && oy < f.H && qy0 + ly < f.h) ? up_weight(oy, qy0 + ly, f.h) : 0.f;
+        wy_s[ly][aa] = (oy >= 0 && oy < f.H && qy0 + ly < f.h) ? up_weight(oy, qy0 + ly, f.h, f.nearest) : 0.f;
       } else {
         const int t = threadIdx.x - kGtH * 4;
         const int lx = t >> 2, bb = t & 3;
         const int ox = 2 * (qx0 + lx) - 1 + bb;
-        wx_s[lx][bb] = (ox >= 0 && ox < f.W && qx0 + lx < f.w) ? up_weight(ox, qx0 + lx, f.w) : 0.f;
+        wx_s[lx][bb] = (ox >= 0 && ox < f.W && qx0 + lx < f.w) ? up_weight(ox, qx0 + lx, f.w, f.nearest) : 0.f;
       }
     }
     // skip channels: one owned high-resolution pixel per thread (2 kGtW x 2 kGtH = 128 of them)
     if (sk_ok) {
       float d4[4];
-      fold_gather4(gc, 144, f.H, f.W, soy, sox, 128, sk_g, d4);
+      fold_gather4(gc, 144, f.H, f.W, soy, sox, 128, sk_g, d4, !f.pad_zero);
       const float rr[4] = {sk_r.x, sk_r.y, sk_r.z, sk_r.w};
 #pragma unroll
       for (int o = 0; o < 4; ++o) {
@@ -2209,7 +2234,8 @@ __device__ __forceinline__ void skipcat_bwd_body(const UpcatBwdArgs& a, int vblo
        pix += static_cast<long long>(vgrid) * blockDim.x) {
     const int y = static_cast<int>(pix / f.W), x = static_cast<int>(pix - static_cast<long long>(y) * f.W);
     float d4[4];
-    fold_gather4(gc, 144, f.H, f.W, y, x, 128, ldg8(gc + (static_cast<long long>(y + 1) * Wp + (x + 1)) * 144 + 128), d4);
+    fold_gather4(gc, 144, f.H, f.W, y, x, 128, ldg8(gc + (static_cast<long long>(y + 1) * Wp + (x + 1)) * 144 + 128), d4,
+                 !f.pad_zero);
     float sv[4], xh4[4], yv[4], dsy[4];
     skip_act4(sc, f.sraw, pix, sv, xh4, yv);
 #pragma unroll
@@ -2258,10 +2284,10 @@ __device__ __forceinline__ void skipcat_bwd_body(const UpcatBwdArgs& a, int vblo
 // backward, pass C, element-wise form: with Q d saved by the forward pass,
 //     ddeep = k1 t + B (Q d) + A w,   B = -k1 c2 rstd,  A = -k1 (c1 - c2 rstd mean),  w = wy(qy) wx(qx)
 // thread = 8 channels of one low-resolution pixel (16-byte accesses), two pixels in flight per thread
-__device__ __forceinline__ float up_wsum(int q, int n_src, int n_out) {
+__device__ __forceinline__ float up_wsum(int q, int n_src, int n_out, int nearest = 0) {
   if (q >= 1 && 2 * q + 2 < n_out && q + 1 < n_src) return 2.f;
   float cw[4], w, Q[3];
-  up_q(q, n_src, n_out, cw, w, Q);
+  up_q(q, n_src, n_out, cw, w, Q, nearest);
   return w;
 }
 __device__ __forceinline__ void upcat_bwd_elem_body(const UpcatBwdArgs& a, __half* __restrict__ ddeep, int vblock,
@@ -2321,7 +2347,7 @@ __device__ __forceinline__ void upcat_bwd_elem_body(const UpcatBwdArgs& a, __hal
     }
     {
       const int qy = base / f.w, qx = base - qy * f.w;
-      const float w2 = up_wsum(qy, f.h, f.H) * up_wsum(qx, f.w, f.W);
+      const float w2 = up_wsum(qy, f.h, f.H, f.nearest) * up_wsum(qx, f.w, f.W, f.nearest);
       float o[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = fmaf(k1[j], t0[j], fmaf(B[j], q0[j], A[j] * w2));
@@ -2338,7 +2364,7 @@ __device__ __forceinline__ void upcat_bwd_elem_body(const UpcatBwdArgs& a, __hal
     }
     if (ok1) {
       const int qy = pix1 / f.w, qx = pix1 - qy * f.w;
-      const float w2 = up_wsum(qy, f.h, f.H) * up_wsum(qx, f.w, f.W);
+      const float w2 = up_wsum(qy, f.h, f.H, f.nearest) * up_wsum(qx, f.w, f.W, f.nearest);
       float o[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = fmaf(k1[j], t1[j], fmaf(B[j], q1[j], A[j] * w2));
@@ -2438,7 +2464,7 @@ __device__ __forceinline__ void upcat_bwd_elem_lean(const UpcatBwdArgs& a, __hal
       const int pix = base + u * ppb;
       if (pix >= npix) continue;
       const int qy = pix / f.w, qx = pix - qy * f.w;
-      const float w2 = up_wsum(qy, f.h, f.H) * up_wsum(qx, f.w, f.W);
+      const float w2 = up_wsum(qy, f.h, f.H, f.nearest) * up_wsum(qx, f.w, f.W, f.nearest);
       const __half2* th = reinterpret_cast<const __half2*>(&tv[u]);
       const __half2* qh = reinterpret_cast<const __half2*>(&qv[u]);
       uint4 ov;

@@ -28,7 +28,7 @@ struct BnRef {            // one train-mode BatchNorm over n pixels
 // (z = perturb_zs + sigma N(0,1), Philox counters of perturb_kernel; z is then the OUTPUT); otherwise both must be null.
 int launch_input_pack(float* z, void* xpad, int C, int H, int W, cudaStream_t s, const float* skip_w = nullptr,
                       float* sraw = nullptr, acc_t* skip_stats = nullptr, const float* perturb_zs = nullptr,
-                      float sigma = 0.f, unsigned long long seed = 0, const float* state = nullptr);
+                      float sigma = 0.f, unsigned long long seed = 0, const float* state = nullptr, int pad_zero = 0);
 int input_pack_fast(int C, int W);
 
 // raw fp16 plain [H][W][128] -> LeakyReLU(BN(raw)) fp16 padded (interior + reflected halo if halo != 0)
@@ -54,6 +54,8 @@ struct UpcatArgs {
   const float* cat_beta;
   void* cat_pad;           // fp16 padded [H+2][W+2][144], reflected halo
   void* qd;                // fp16 plain [h][w][128]: (U^T U d), written by the forward statistics, read by the backward
+  int nearest;             // 1: nn.Upsample(mode='nearest') instead of bilinear (skip.py:77)
+  int pad_zero;            // 1: zero padding (models/DIP/utils.py:96-102): no reflected halo is written or folded back
 };
 int launch_upcat_stats(const UpcatArgs& a, cudaStream_t s);
 int launch_upcat_apply(const UpcatArgs& a, cudaStream_t s);

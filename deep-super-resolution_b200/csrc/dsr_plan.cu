@@ -134,6 +134,8 @@ struct dsr_downsampler {
 
 struct dsr_plan {
   int H, W, input_depth, num_scales, n_out;
+  int pad_zero = 0;     // get_net(pad='zero'): Conv2d zero padding instead of ReflectionPad2d (models/DIP/utils.py:96-102)
+  int nearest = 0;      // get_net(upsample_mode='nearest') (models/DIP/skip.py:77)
   std::vector<Level> lv;
   std::vector<ParamInfo> params;
   std::vector<BnInfo> bns;
@@ -255,17 +257,20 @@ void name_level(dsr_plan* p, int i) {
   Level& L = p->lv[i];
   std::string P;
   for (int j = 0; j < i; ++j) P += "1.1.7.";
-  add_conv_params(p, P + "1.0.1.1", L.skip_w, L.skip_b, kNS, L.Cin, 1);
+  // models/DIP/utils.py:103-104: a conv is Sequential(ReflectionPad2d, Conv2d) -> "....1.weight"; with pad='zero'
+  // there is no padder module and the Conv2d is child 0
+  const std::string ci = p->pad_zero ? ".0" : ".1";
+  add_conv_params(p, P + "1.0.1" + ci, L.skip_w, L.skip_b, kNS, L.Cin, 1);
   add_bn(p, P + "1.0.2", L.skip_g, L.skip_be, L.skip_bn, kNS);
-  add_conv_params(p, P + "1.1.1.1", L.d1.w_off, L.d1.b_off, kNC, L.Cin, 3);
+  add_conv_params(p, P + "1.1.1" + ci, L.d1.w_off, L.d1.b_off, kNC, L.Cin, 3);
   add_bn(p, P + "1.1.2", L.d1.g_off, L.d1.be_off, L.d1.bn_off, kNC);
-  add_conv_params(p, P + "1.1.4.1", L.d2.w_off, L.d2.b_off, kNC, kNC, 3);
+  add_conv_params(p, P + "1.1.4" + ci, L.d2.w_off, L.d2.b_off, kNC, kNC, 3);
   add_bn(p, P + "1.1.5", L.d2.g_off, L.d2.be_off, L.d2.bn_off, kNC);
   if (i + 1 < p->num_scales) name_level(p, i + 1);
   add_bn(p, P + "2", L.cat_g, L.cat_be, L.cat_bn, kNS + kNC);
-  add_conv_params(p, P + "3.1", L.u1.w_off, L.u1.b_off, kNC, kNS + kNC, 3);
+  add_conv_params(p, P + "3" + ci, L.u1.w_off, L.u1.b_off, kNC, kNS + kNC, 3);
   add_bn(p, P + "4", L.u1.g_off, L.u1.be_off, L.u1.bn_off, kNC);
-  add_conv_params(p, P + "6.1", L.u2.w_off, L.u2.b_off, kNC, kNC, 1);
+  add_conv_params(p, P + "6" + ci, L.u2.w_off, L.u2.b_off, kNC, kNC, 1);
   add_bn(p, P + "7", L.u2.g_off, L.u2.be_off, L.u2.bn_off, kNC);
 }
 
@@ -903,11 +908,11 @@ int run_wgrad(dsr_plan* p, ConvLayer& c, cudaStream_t s) {
 int conv_bn_act(dsr_plan* p, ConvLayer& c, const float* params, cudaStream_t s, Level* next = nullptr) {
   DSR_TRY(run_fprop(p, c, s));
   if (next != nullptr && p->fuse_skip) {
-    DSR_TRY(launch_bn_act(c.raw.ptr, conv_bn(p, c, params), c.act.ptr, c.outH, c.outW, c.act_halo, s,
+    DSR_TRY(launch_bn_act(c.raw.ptr, conv_bn(p, c, params), c.act.ptr, c.outH, c.outW, p->pad_zero ? 0 : c.act_halo, s,
                           params + next->skip_w, static_cast<float*>(next->sraw.ptr),
                           reinterpret_cast<acc_t*>(p->base) + next->skip_stats_off));
   } else {
-    DSR_TRY(launch_bn_act(c.raw.ptr, conv_bn(p, c, params), c.act.ptr, c.outH, c.outW, c.act_halo, s));
+    DSR_TRY(launch_bn_act(c.raw.ptr, conv_bn(p, c, params), c.act.ptr, c.outH, c.outW, p->pad_zero ? 0 : c.act_halo, s));
   }
   return 0;
 }
@@ -931,6 +936,8 @@ UpcatArgs upcat_args(dsr_plan* p, int i, const float* params) {
   a.cat_pad = L.cat.ptr;
   // second quarter of the (otherwise backward-only) scratch tensor dup: [0, h w 128) holds t = U^T dc, then Q d
   a.qd = static_cast<__half*>(L.dup.ptr) + static_cast<size_t>(L.h) * L.w * kNC;
+  a.nearest = p->nearest;
+  a.pad_zero = p->pad_zero;
   return a;
 }
 
@@ -963,7 +970,7 @@ int bn_backward(dsr_plan* p, ConvLayer& c, const float* params, float* grads, co
   BnBwdArgs a{};
   a.g = g;
   a.gC = gC;
-  a.fold = fold;
+  a.fold = p->pad_zero ? 0 : fold;
   a.bstats_raw = c.bstats_ready ? 1 : 0;
   if (next != nullptr) {
     a.dsy = static_cast<const float*>(next->dsy.ptr);
@@ -1219,7 +1226,12 @@ int dsr_downsample_mse(const dsr_downsampler_t* d, const float* x, const float* 
 
 // ---- plan ---------------------------------------------------------------------------------------
 int dsr_plan_create(dsr_plan_t** out, int H, int W, int input_depth, int num_scales, int n_out) {
+  return dsr_plan_create_ex(out, H, W, input_depth, num_scales, n_out, 0);
+}
+
+int dsr_plan_create_ex(dsr_plan_t** out, int H, int W, int input_depth, int num_scales, int n_out, int flags) {
   if (out == nullptr) return -1;
+  if (flags & ~(DSR_PLAN_PAD_ZERO | DSR_PLAN_UP_NEAREST)) return -5;
   if (num_scales < 1 || num_scales > 6 || n_out != 3) return -5;
   if (input_depth != 32 && input_depth != 128) return -5;
   {  // any H, W whose level sizes stay >= 2 (ReflectionPad2d(1) needs two pixels): stride-2 convs give ceil(n / 2),
@@ -1235,6 +1247,8 @@ int dsr_plan_create(dsr_plan_t** out, int H, int W, int input_depth, int num_sca
   }
   dsr_plan* p = new dsr_plan();
   p->H = H; p->W = W; p->input_depth = input_depth; p->num_scales = num_scales; p->n_out = n_out;
+  p->pad_zero = (flags & DSR_PLAN_PAD_ZERO) ? 1 : 0;
+  p->nearest = (flags & DSR_PLAN_UP_NEAREST) ? 1 : 0;
   p->lv.resize(num_scales);
   for (int i = 0, h = H, w = W; i < num_scales; ++i) {
     Level& L = p->lv[i];
@@ -1244,7 +1258,7 @@ int dsr_plan_create(dsr_plan_t** out, int H, int W, int input_depth, int num_sca
     w = L.w;
   }
   name_level(p, 0);
-  add_conv_params(p, "9.1", p->fin_w, p->fin_b, n_out, kNC, 1);
+  add_conv_params(p, p->pad_zero ? "9.0" : "9.1", p->fin_w, p->fin_b, n_out, kNC, 1);
 
   Bump ws, accf, accb;
   size_t warena_elems = 0, garena_floats = 0;
@@ -1464,7 +1478,7 @@ int dsr_plan_bind(dsr_plan_t* p, void* workspace, size_t bytes, void* stream) {
   p->use_side = getenv("DSR_NO_SIDE_STREAM") ? 0 : 1;
   p->use_graph = getenv("DSR_NO_GRAPH") ? 0 : 1;
   p->fuse_top = getenv("DSR_NO_FUSE_TOP") ? 0 : 1;
-  p->lowres_upcat = getenv("DSR_NO_LOWRES_UPCAT") ? 0 : 1;
+  p->lowres_upcat = (getenv("DSR_NO_LOWRES_UPCAT") && !p->nearest) ? 0 : 1;    // the A/B path is bilinear only
   p->fuse_skip = getenv("DSR_NO_FUSE_SKIP") ? 0 : 1;
   p->fuse_ubstats = getenv("DSR_NO_FUSE_UBSTATS") ? 0 : 1;
   p->bound = true;
@@ -1507,7 +1521,7 @@ static int net_forward_impl(dsr_plan_t* p, const float* params, const float* z, 
                               fskip ? static_cast<float*>(L0.sraw.ptr) : nullptr,
                               fskip ? reinterpret_cast<acc_t*>(p->base) + L0.skip_stats_off : nullptr,
                               fast ? p->pz_saved : nullptr, p->psigma, p->pseed,
-                              static_cast<const float*>(p->stepstate.ptr)));
+                              static_cast<const float*>(p->stepstate.ptr), p->pad_zero));
   }
   if (fork_head) {
     e = cudaStreamWaitEvent(s, p->ev_join, 0);

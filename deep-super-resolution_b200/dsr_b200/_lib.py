@@ -41,6 +41,7 @@ SIGNATURES = {
     'dsr_downsample_bwd': (i32, [vp, vp, vp, i32, vp]),
     'dsr_downsample_mse': (i32, [vp, vp, vp, vp, vp, vp, i32, vp]),
     'dsr_plan_create': (i32, [C.POINTER(vp), i32, i32, i32, i32, i32]),
+    'dsr_plan_create_ex': (i32, [C.POINTER(vp), i32, i32, i32, i32, i32, i32]),
     'dsr_plan_destroy': (None, [vp]),
     'dsr_plan_num_params': (i32, [vp]),
     'dsr_plan_param_numel': (i64, [vp]),

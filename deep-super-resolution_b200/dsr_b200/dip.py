@@ -130,5 +130,10 @@ def dip_sr_fused(net: SkipNet, LR_image: torch.Tensor, hr_size: Tuple[int, int],
         net._nbt += 1
         plan.forward_id += 1
         net._fused_keepalive = (m, v, z, z_saved, lr, out_lr, g_lr, g_hr, tables, ds)
-    torch.cuda.current_stream(device).wait_stream(run_stream)
+    caller = torch.cuda.current_stream(device)
+    caller.wait_stream(run_stream)
+    # the returned tensors were allocated on run_stream: tell the caching allocator that the caller's stream uses them
+    # too, or their blocks could be handed to later run_stream allocations while the caller still reads them
+    out_hr.record_stream(caller)
+    losses.record_stream(caller)
     return (out_hr if keep_on_device else out_hr.cpu()), losses

@@ -41,19 +41,22 @@ class _BnLeaf(nn.Module):
         self.register_buffer('num_batches_tracked', torch.zeros((), dtype=torch.long))
 
 
-def _conv_box(weight, bias) -> _Box:
+def _conv_box(weight, bias, child: str = '1') -> _Box:
     # conv() of models/DIP/utils.py:83-105 is Sequential(padder, Conv2d): the Conv2d is child '1'
+    # (pad='zero': no padder module, the Conv2d is child '0')
     b = _Box()
-    b.add_module('1', _ConvLeaf(weight, bias))
+    b.add_module(child, _ConvLeaf(weight, bias))
     return b
 
 
 class _PlanState:
     """Per-resolution execution plan + workspace."""
 
-    def __init__(self, H: int, W: int, input_depth: int, num_scales: int, n_out: int, device: torch.device):
+    def __init__(self, H: int, W: int, input_depth: int, num_scales: int, n_out: int, device: torch.device,
+                 flags: int = 0):
         self.handle = C.c_void_p()
-        check(lib.dsr_plan_create(C.byref(self.handle), H, W, input_depth, num_scales, n_out), 'dsr_plan_create')
+        check(lib.dsr_plan_create_ex(C.byref(self.handle), H, W, input_depth, num_scales, n_out, flags),
+              'dsr_plan_create_ex')
         nbytes = lib.dsr_plan_workspace_bytes(self.handle)
         self.workspace = torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
         base = (self.workspace.data_ptr() + 1023) // 1024 * 1024
@@ -110,12 +113,17 @@ class _SkipNetFn(torch.autograd.Function):
 class SkipNet(nn.Module):
     """Hourglass encoder/decoder with 4-channel skip branches (models/DIP/skip.py)."""
 
-    def __init__(self, input_depth: int = 32, n_channels: int = 3, num_scales: int = 5):
+    def __init__(self, input_depth: int = 32, n_channels: int = 3, num_scales: int = 5, pad: str = 'reflection',
+                 upsample_mode: str = 'bilinear'):
         super().__init__()
         self.input_depth, self.n_channels, self.num_scales = input_depth, n_channels, num_scales
+        self.pad, self.upsample_mode = pad, upsample_mode
+        # DSR_PLAN_PAD_ZERO = 1, DSR_PLAN_UP_NEAREST = 2 (include/dsr_b200.h)
+        self._plan_flags = (1 if pad == 'zero' else 0) | (2 if upsample_mode == 'nearest' else 0)
+        ci = '0' if pad == 'zero' else '1'          # index of the Conv2d inside conv()'s Sequential
         probe = C.c_void_p()
-        check(lib.dsr_plan_create(C.byref(probe), 2 << num_scales, 2 << num_scales, input_depth, num_scales,
-                                  n_channels), 'dsr_plan_create (configuration check)')
+        check(lib.dsr_plan_create_ex(C.byref(probe), 2 << num_scales, 2 << num_scales, input_depth, num_scales,
+                                     n_channels, self._plan_flags), 'dsr_plan_create_ex (configuration check)')
         self._layout = _read_layout(probe)
         lib.dsr_plan_destroy(probe)
 
@@ -131,13 +139,13 @@ class SkipNet(nn.Module):
         cin = input_depth
         for i in range(num_scales):
             P = '1.1.7.' * i
-            draw(P + '1.0.1.1', cin, ns, 1)
-            draw(P + '1.1.1.1', cin, nd, 3)
-            draw(P + '1.1.4.1', nd, nd, 3)
-            draw(P + '3.1', ns + nd, nd, 3)
-            draw(P + '6.1', nd, nd, 1)
+            draw(P + '1.0.1.' + ci, cin, ns, 1)
+            draw(P + '1.1.1.' + ci, cin, nd, 3)
+            draw(P + '1.1.4.' + ci, nd, nd, 3)
+            draw(P + '3.' + ci, ns + nd, nd, 3)
+            draw(P + '6.' + ci, nd, nd, 1)
             cin = nd
-        draw('9.1', nd, n_channels, 1)
+        draw('9.' + ci, nd, n_channels, 1)
 
         # --- module tree with the reference's names ---
         def level(i: int) -> _Box:
@@ -146,25 +154,25 @@ class SkipNet(nn.Module):
             model.add_module('1', concat)
             concat.add_module('0', skipb)
             concat.add_module('1', deeper)
-            skipb.add_module('1', _conv_box(init[P + '1.0.1.1.weight'], init[P + '1.0.1.1.bias']))
+            skipb.add_module('1', _conv_box(init[P + f'1.0.1.{ci}.weight'], init[P + f'1.0.1.{ci}.bias'], ci))
             skipb.add_module('2', _BnLeaf(ns))
-            deeper.add_module('1', _conv_box(init[P + '1.1.1.1.weight'], init[P + '1.1.1.1.bias']))
+            deeper.add_module('1', _conv_box(init[P + f'1.1.1.{ci}.weight'], init[P + f'1.1.1.{ci}.bias'], ci))
             deeper.add_module('2', _BnLeaf(nd))
-            deeper.add_module('4', _conv_box(init[P + '1.1.4.1.weight'], init[P + '1.1.4.1.bias']))
+            deeper.add_module('4', _conv_box(init[P + f'1.1.4.{ci}.weight'], init[P + f'1.1.4.{ci}.bias'], ci))
             deeper.add_module('5', _BnLeaf(nd))
             if i + 1 < num_scales:
                 deeper.add_module('7', level(i + 1))
             model.add_module('2', _BnLeaf(ns + nd))
-            model.add_module('3', _conv_box(init[P + '3.1.weight'], init[P + '3.1.bias']))
+            model.add_module('3', _conv_box(init[P + f'3.{ci}.weight'], init[P + f'3.{ci}.bias'], ci))
             model.add_module('4', _BnLeaf(nd))
-            model.add_module('6', _conv_box(init[P + '6.1.weight'], init[P + '6.1.bias']))
+            model.add_module('6', _conv_box(init[P + f'6.{ci}.weight'], init[P + f'6.{ci}.bias'], ci))
             model.add_module('7', _BnLeaf(nd))
             return model
 
         top = level(0)
         for name, child in top.named_children():
             self.add_module(name, child)
-        self.add_module('9', _conv_box(init['9.1.weight'], init['9.1.bias']))
+        self.add_module('9', _conv_box(init[f'9.{ci}.weight'], init[f'9.{ci}.bias'], ci))
 
         names = [n for n, _ in self.named_parameters()]
         if names != [n for n, _, _ in self._layout['params']]:
@@ -226,7 +234,8 @@ class SkipNet(nn.Module):
         key = (int(z.shape[2]), int(z.shape[3]))
         plan = self._plans.get(key)
         if plan is None or plan.workspace.device != z.device:
-            plan = _PlanState(key[0], key[1], self.input_depth, self.num_scales, self.n_channels, z.device)
+            plan = _PlanState(key[0], key[1], self.input_depth, self.num_scales, self.n_channels, z.device,
+                              self._plan_flags)
             self._plans[key] = plan
         return plan
 
@@ -297,14 +306,17 @@ def get_net(input_depth, NET_TYPE, pad, upsample_mode, n_channels=3, act_fun='Le
             skip_n33u=128, skip_n11=4, num_scales=5, downsample_mode='stride'):
     """Same signature as models/DIP/__init__.py:8.  Supported: the configuration DIP.py:169-174
     builds (NET_TYPE 'skip', pad 'reflection', upsample 'bilinear', LeakyReLU, 128/128/4 channels,
-    stride downsampling); anything else raises NotImplementedError -- there is no fallback."""
+    stride downsampling) and the two other padding / upsampling options of the signature, pad='zero'
+    (models/DIP/utils.py:96-102) and upsample_mode='nearest' (models/DIP/skip.py:77); anything else raises
+    NotImplementedError -- there is no fallback."""
     def _all(v, want):
         return (v == want) if isinstance(v, int) else all(x == want for x in v) and len(v) == num_scales
-    ok = (NET_TYPE == 'skip' and pad == 'reflection' and upsample_mode == 'bilinear' and act_fun == 'LeakyReLU'
+    ok = (NET_TYPE == 'skip' and pad in ('reflection', 'zero') and upsample_mode in ('bilinear', 'nearest')
+          and act_fun == 'LeakyReLU'
           and downsample_mode == 'stride' and _all(skip_n33d, 128) and _all(skip_n33u, 128) and _all(skip_n11, 4))
     if not ok:
         raise NotImplementedError(
-            'dsr_b200.get_net supports the DIP.py configuration only: NET_TYPE="skip", pad="reflection", '
-            'upsample_mode="bilinear", act_fun="LeakyReLU", skip_n33d=skip_n33u=128, skip_n11=4, '
+            'dsr_b200.get_net supports NET_TYPE="skip", pad="reflection"|"zero", '
+            'upsample_mode="bilinear"|"nearest", act_fun="LeakyReLU", skip_n33d=skip_n33u=128, skip_n11=4, '
             'downsample_mode="stride"')
-    return SkipNet(input_depth, n_channels, num_scales)
+    return SkipNet(input_depth, n_channels, num_scales, pad=pad, upsample_mode=upsample_mode)

@@ -62,6 +62,13 @@ int dsr_downsample_mse(const dsr_downsampler_t* d, const float* x, const float* 
  * LeakyReLU, need_sigmoid, need_bias, n33d = n33u = 128, n11 = 4, stride downsampling;
  * input_depth in {8k}, num_scales in [1, 6], any H, W that keep every level >= 2 pixels. */
 int dsr_plan_create(dsr_plan_t** out, int H, int W, int input_depth, int num_scales, int n_out);
+/* The other two get_net options reachable through its signature (models/DIP/__init__.py:8): pad='zero' -- Conv2d's own
+ * zero padding instead of ReflectionPad2d (models/DIP/utils.py:96-102; state_dict keys of the convolutions then end in
+ * ".0.weight" instead of ".1.weight") -- and upsample_mode='nearest' (models/DIP/skip.py:77).  flags = 0 is
+ * dsr_plan_create. */
+#define DSR_PLAN_PAD_ZERO 1
+#define DSR_PLAN_UP_NEAREST 2
+int dsr_plan_create_ex(dsr_plan_t** out, int H, int W, int input_depth, int num_scales, int n_out, int flags);
 void dsr_plan_destroy(dsr_plan_t* p);
 /* Flat parameter buffer: concatenation of the reference's net.named_parameters() in order. */
 int dsr_plan_num_params(const dsr_plan_t* p);                 /* number of tensors (112)    */

@@ -100,23 +100,30 @@ def level_prefix(i: int) -> str:
     return '1.1.7.' * i
 
 
-def layer_names(i: int) -> Dict[str, str]:
+def conv_child(pad: str = 'reflection') -> str:
+    """Index of the Conv2d inside conv()'s Sequential (models/DIP/utils.py:96-105): 1 behind a ReflectionPad2d,
+    0 with pad='zero' (no padder module)."""
+    return '0' if pad == 'zero' else '1'
+
+
+def layer_names(i: int, pad: str = 'reflection') -> Dict[str, str]:
     p = level_prefix(i)
+    c = conv_child(pad)
     return dict(
-        skip_conv=p + '1.0.1.1', skip_bn=p + '1.0.2',
-        d1_conv=p + '1.1.1.1', d1_bn=p + '1.1.2',
-        d2_conv=p + '1.1.4.1', d2_bn=p + '1.1.5',
+        skip_conv=p + '1.0.1.' + c, skip_bn=p + '1.0.2',
+        d1_conv=p + '1.1.1.' + c, d1_bn=p + '1.1.2',
+        d2_conv=p + '1.1.4.' + c, d2_bn=p + '1.1.5',
         cat_bn=p + '2',
-        u1_conv=p + '3.1', u1_bn=p + '4',
-        u2_conv=p + '6.1', u2_bn=p + '7',
+        u1_conv=p + '3.' + c, u1_bn=p + '4',
+        u2_conv=p + '6.' + c, u2_bn=p + '7',
     )
 
 
-FINAL_CONV = '9.1'   # skip.py:92: 9th child of the top container, conv() Sequential index 1
+FINAL_CONV = '9.1'   # skip.py:92: 9th child of the top container, conv() Sequential index 1 ('9.0' with pad='zero')
 
 
 def init_params(input_depth: int = 32, n_out: int = 3, nd: int = 128, nu: int = 128, ns: int = 4,
-                num_scales: int = 5) -> Dict[str, Tensor]:
+                num_scales: int = 5, pad: str = 'reflection') -> Dict[str, Tensor]:
     """Fresh parameters + buffers with the reference's initialisation AND RNG consumption order.
 
     skip.py:41-92 constructs, per level, the skip 1x1 conv, the stride-2 conv, the second encoder
@@ -141,17 +148,17 @@ def init_params(input_depth: int = 32, n_out: int = 3, nd: int = 128, nu: int = 
 
     cin = input_depth
     for i in range(num_scales):
-        n = layer_names(i)
+        n = layer_names(i, pad)
         conv(n['skip_conv'], cin, ns, 1)
         conv(n['d1_conv'], cin, nd, 3)
         conv(n['d2_conv'], nd, nd, 3)
         conv(n['u1_conv'], ns + (nu if i < num_scales - 1 else nd), nu, 3)
         conv(n['u2_conv'], nu, nu, 1)
         cin = nd
-    conv(FINAL_CONV, nu, n_out, 1)
+    conv('9.' + conv_child(pad), nu, n_out, 1)
     # BN entries, in any order (no RNG); keys sorted later by the caller if needed
     for i in range(num_scales):
-        n = layer_names(i)
+        n = layer_names(i, pad)
         bn(n['skip_bn'], ns)
         bn(n['d1_bn'], nd)
         bn(n['d2_bn'], nd)
@@ -166,7 +173,7 @@ def param_keys(sd: Dict[str, Tensor]) -> List[str]:
     return [k for k in sd if k.endswith('.weight') or k.endswith('.bias')]
 
 
-def dead_param_keys(num_scales: int = 5) -> List[str]:
+def dead_param_keys(num_scales: int = 5, pad: str = 'reflection') -> List[str]:
     """Parameters whose value cannot influence the output: the bias of every conv that feeds a
     train-mode BatchNorm (cancelled by the mean subtraction) and BN(cat)'s beta (a per-channel
     constant on the input of reflect-pad + conv + train-mode BN).  The reference keeps and
@@ -174,9 +181,10 @@ def dead_param_keys(num_scales: int = 5) -> List[str]:
     (SURVEY.md 7.2 item 3)."""
     out = []
     for i in range(num_scales):
-        n = layer_names(i)
+        n = layer_names(i, pad)
         out += [n[k] + '.bias' for k in ('skip_conv', 'd1_conv', 'd2_conv', 'u1_conv', 'u2_conv')]
-        out.append(n['cat_bn'] + '.bias')
+        if pad != 'zero':       # behind zero padding the constant is NOT uniform over the conv's input window
+            out.append(n['cat_bn'] + '.bias')
     return out
 
 
@@ -218,14 +226,15 @@ def _q(q: Quant, t: Tensor, tag: str) -> Tensor:
     return t if q is None else q(t, tag)
 
 
-def _conv(x: Tensor, w: Tensor, b: Optional[Tensor], stride: int, q: Quant, w_tag: str = 'conv_w') -> Tensor:
+def _conv(x: Tensor, w: Tensor, b: Optional[Tensor], stride: int, q: Quant, w_tag: str = 'conv_w',
+          pad: str = 'reflection') -> Tensor:
     """conv() of models/DIP/utils.py:83-105 with pad='reflection': ReflectionPad2d((k-1)/2)
     then Conv2d(padding=0).  ``w_tag`` names the weight operand for the quantisation hook: 'conv_w' for the 20
     tensor-core layers, 'skip_w' / 'final_w' for the small 1x1 layers (whose weights the CUDA path keeps in fp32)."""
     k = w.shape[-1]
     p = (k - 1) // 2
-    if p:
-        x = F.pad(x, (p, p, p, p), mode='reflect')
+    if p:     # pad='zero': Conv2d(padding=p) (models/DIP/utils.py:96-102)
+        x = F.pad(x, (p, p, p, p), mode='reflect') if pad != 'zero' else F.pad(x, (p, p, p, p))
     if q is not None and getattr(q, 'drop_bn_bias', False) and w_tag == 'conv_w':
         b = None      # a bias in front of a train-mode BatchNorm is cancelled by the mean subtraction; the CUDA kernels
                       # never add it, so their 16-bit rounding of the raw output happens WITHOUT it
@@ -257,30 +266,31 @@ def _center_crop_cat(a: Tensor, b: Tensor) -> Tensor:
 
 
 def skip_forward(sd: Dict[str, Tensor], z: Tensor, num_scales: int = 5, quant: Quant = None,
-                 taps: Optional[Dict[str, Tensor]] = None) -> Tensor:
+                 taps: Optional[Dict[str, Tensor]] = None, pad: str = 'reflection',
+                 upsample_mode: str = 'bilinear') -> Tensor:
     """Forward of the net built by get_net(32,'skip','reflection',...,upsample_mode='bilinear')
     (models/DIP/skip.py:41-94; per-level structure in SURVEY.md 3.2).  ``taps`` (optional dict)
     receives named intermediates: 'L{i}.skip_raw', '.d1_raw', '.d2_raw', '.x_next', '.cat',
     '.u1_raw', '.u2_raw', '.out', and 'final_pre'."""
 
     def rec(i: int, x: Tensor) -> Tensor:
-        n = layer_names(i)
+        n = layer_names(i, pad)
         P = lambda name: sd[name]
         # skip branch (skip.py:54-56)
-        s_raw = _conv(x, P(n['skip_conv'] + '.weight'), P(n['skip_conv'] + '.bias'), 1, quant, 'skip_w')
+        s_raw = _conv(x, P(n['skip_conv'] + '.weight'), P(n['skip_conv'] + '.bias'), 1, quant, 'skip_w', pad)
         s = _act(_bn(s_raw, P(n['skip_bn'] + '.weight'), P(n['skip_bn'] + '.bias')))
         # deeper branch (skip.py:60-66)
-        d1_raw = _conv(x, P(n['d1_conv'] + '.weight'), P(n['d1_conv'] + '.bias'), 2, quant)
+        d1_raw = _conv(x, P(n['d1_conv'] + '.weight'), P(n['d1_conv'] + '.bias'), 2, quant, pad=pad)
         d1 = _q(quant, _act(_bn(_q(quant, d1_raw, 'raw'), P(n['d1_bn'] + '.weight'), P(n['d1_bn'] + '.bias'))), 'act')
-        d2_raw = _conv(d1, P(n['d2_conv'] + '.weight'), P(n['d2_conv'] + '.bias'), 1, quant)
+        d2_raw = _conv(d1, P(n['d2_conv'] + '.weight'), P(n['d2_conv'] + '.bias'), 1, quant, pad=pad)
         d2 = _q(quant, _act(_bn(_q(quant, d2_raw, 'raw'), P(n['d2_bn'] + '.weight'), P(n['d2_bn'] + '.bias'))), 'act')
         deep = rec(i + 1, d2) if i < num_scales - 1 else d2        # skip.py:70-75
-        up = F.interpolate(deep, scale_factor=2, mode='bilinear')  # skip.py:77 (align_corners False)
+        up = F.interpolate(deep, scale_factor=2, mode=upsample_mode)  # skip.py:77 (bilinear: align_corners False)
         cat = _center_crop_cat(s, up)                              # Concat(1, skip, deeper), skip.py:47
         c = _bn(cat, P(n['cat_bn'] + '.weight'), P(n['cat_bn'] + '.bias'))   # skip.py:51
-        u1_raw = _conv(c, P(n['u1_conv'] + '.weight'), P(n['u1_conv'] + '.bias'), 1, quant)
+        u1_raw = _conv(c, P(n['u1_conv'] + '.weight'), P(n['u1_conv'] + '.bias'), 1, quant, pad=pad)
         u1 = _q(quant, _act(_bn(_q(quant, u1_raw, 'raw'), P(n['u1_bn'] + '.weight'), P(n['u1_bn'] + '.bias'))), 'act')
-        u2_raw = _conv(u1, P(n['u2_conv'] + '.weight'), P(n['u2_conv'] + '.bias'), 1, quant)
+        u2_raw = _conv(u1, P(n['u2_conv'] + '.weight'), P(n['u2_conv'] + '.bias'), 1, quant, pad=pad)
         u2 = _q(quant, _act(_bn(_q(quant, u2_raw, 'raw'), P(n['u2_bn'] + '.weight'), P(n['u2_bn'] + '.bias'))), 'act')
         if taps is not None:
             for k_, v_ in (('skip_raw', s_raw), ('d1_raw', d1_raw), ('d2_raw', d2_raw), ('x_next', d2),
@@ -289,7 +299,8 @@ def skip_forward(sd: Dict[str, Tensor], z: Tensor, num_scales: int = 5, quant: Q
         return u2
 
     y = rec(0, z)
-    pre = _conv(y, sd[FINAL_CONV + '.weight'], sd[FINAL_CONV + '.bias'], 1, quant, 'final_w')   # skip.py:92
+    fin = '9.' + conv_child(pad)
+    pre = _conv(y, sd[fin + '.weight'], sd[fin + '.bias'], 1, quant, 'final_w', pad)   # skip.py:92
     if taps is not None:
         taps['final_pre'] = pre
     return torch.sigmoid(pre)                                                          # skip.py:93-94
@@ -316,7 +327,8 @@ def mse(a: Tensor, b: Tensor) -> Tensor:
 
 def step_loss_and_grads(sd: Dict[str, Tensor], z: Tensor, lr_image: Tensor, factor: int,
                         num_scales: int = 5, quant: Quant = None,
-                        taps: Optional[Dict[str, Tensor]] = None
+                        taps: Optional[Dict[str, Tensor]] = None, pad: str = 'reflection',
+                        upsample_mode: str = 'bilinear'
                         ) -> Tuple[Tensor, Tensor, Dict[str, Tensor]]:
     """net forward -> downsampler -> MSE -> backward (DIP.py:60-68).  Returns (loss, out_HR,
     grads by state-dict key).  ``z`` is the already perturbed input (DIP.py:52)."""
@@ -324,7 +336,7 @@ def step_loss_and_grads(sd: Dict[str, Tensor], z: Tensor, lr_image: Tensor, fact
     leaves = {k: sd[k].detach().clone().requires_grad_(True) for k in keys}
     full = dict(sd)
     full.update(leaves)
-    out = skip_forward(full, z, num_scales, quant, taps)
+    out = skip_forward(full, z, num_scales, quant, taps, pad, upsample_mode)
     if taps is not None:
         for t in taps.values():
             if t.requires_grad:

@@ -25,6 +25,7 @@ def main():
     ap.add_argument('--size', type=int, default=128)
     ap.add_argument('--images', type=int, default=8)
     ap.add_argument('--iters', type=int, default=400)
+    ap.add_argument('--extend', action='store_true', help='add images [len(existing), --images) to the existing fixture')
     args = ap.parse_args()
     from oracle import dip_oracle as O
     sys.path.insert(0, REF)
@@ -35,6 +36,12 @@ def main():
     torch.set_num_threads(os.cpu_count() or 1)
     out = {'size': args.size, 'iters': args.iters, 'factor': 4, 'lr': 0.01, 'reg_noise_std': 0.05, 'runs': []}
     runs = [(i, i) for i in range(args.images)] + [(0, 12345)]        # (image, seed); last = spread probe
+    path = os.path.join(ROOT, 'tests', 'golden', f'psnr_{args.size}.pt')
+    if args.extend:                                                   # keep what exists, run the missing images only
+        out = torch.load(path)
+        assert out['iters'] == args.iters
+        have = {(r['image'], r['seed']) for r in out['runs']}
+        runs = [r for r in runs if r not in have]
     for img, seed in runs:
         lr_img, hr = O.synthetic_pair(img, args.size)
         torch.manual_seed(seed)
@@ -67,11 +74,13 @@ def main():
         out['runs'].append(rec)
         print(f"image {img} seed {seed}: PSNR(last 50) {rec['psnr_last50']:.3f} dB  loss {rec['loss_every50'][-1]:.3e} "
               f"({time.time() - t0:.0f} s)", flush=True)
-    main_runs = out['runs'][:args.images]
+    main_runs = [r for r in out['runs'] if r['image'] == r['seed']]
+    probe = [r for r in out['runs'] if r['image'] != r['seed']][0]
+    first = [r for r in main_runs if r['image'] == probe['image']][0]
     out['mean_psnr_last50'] = sum(r['psnr_last50'] for r in main_runs) / len(main_runs)
-    out['seed_spread_image0'] = abs(out['runs'][-1]['psnr_last50'] - out['runs'][0]['psnr_last50'])
+    out['seed_spread_image0'] = abs(probe['psnr_last50'] - first['psnr_last50'])
     print('mean', out['mean_psnr_last50'], 'spread(image 0, other seed)', out['seed_spread_image0'])
-    torch.save(out, os.path.join(ROOT, 'tests', 'golden', f'psnr_{args.size}.pt'))
+    torch.save(out, path)
 
 
 if __name__ == '__main__':

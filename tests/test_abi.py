@@ -103,9 +103,11 @@ def test_get_net_same_seed_init_and_state_dict(golden, seed):
 def test_unsupported_configurations_raise():
     import dsr_b200
     with pytest.raises(NotImplementedError):
-        dsr_b200.get_net(32, 'skip', 'zero', 'bilinear')
+        dsr_b200.get_net(32, 'skip', 'replicate', 'bilinear')
     with pytest.raises(NotImplementedError):
-        dsr_b200.get_net(32, 'skip', 'reflection', 'nearest')
+        dsr_b200.get_net(32, 'skip', 'reflection', 'bicubic')
+    with pytest.raises(NotImplementedError):
+        dsr_b200.get_net(32, 'skip', 'reflection', 'bilinear', downsample_mode='avg')
     with pytest.raises(NotImplementedError):
         dsr_b200.get_net(32, 'skip', 'reflection', 'bilinear', skip_n33d=64)
     with pytest.raises(NotImplementedError):
@@ -116,6 +118,20 @@ def test_unsupported_configurations_raise():
         dsr_b200.optimize('LBFGS', [], lambda: None, 0.01, 1)
     with pytest.raises(NotImplementedError):
         dsr_b200.get_noise(2, 'meshgrid', (8, 8))
+
+
+def test_pad_zero_and_nearest_keep_the_reference_state_dict_keys():
+    """get_net(pad='zero') drops conv()'s padder module, so the Conv2d becomes child '0' of its Sequential
+    (models/DIP/utils.py:96-105); the drop-in follows, and same-seed initial values are unchanged."""
+    import dsr_b200
+    torch.manual_seed(4)
+    a = dsr_b200.get_net(32, 'skip', 'reflection', 'bilinear', num_scales=2)
+    torch.manual_seed(4)
+    b = dsr_b200.get_net(32, 'skip', 'zero', 'nearest', num_scales=2)
+    ka, kb = list(a.state_dict().keys()), list(b.state_dict().keys())
+    assert len(ka) == len(kb) and '1.0.1.1.weight' in ka and '1.0.1.0.weight' in kb and '9.0.bias' in kb
+    for x, y in zip(ka, kb):
+        assert torch.equal(a.state_dict()[x], b.state_dict()[y])
 
 
 def test_no_cpu_fallback():

@@ -110,7 +110,7 @@ def test_tensor_core_kernels_match_checker(size):
 
 def live_keys(fx):
     from oracle import dip_oracle as O
-    dead = set(O.dead_param_keys())
+    dead = set(O.dead_param_keys(pad=fx.get('pad', 'reflection')))
     floor = 1e-6 * max(fx['grad_norms'].values())
     return [k for k in fx['grad_norms'] if k not in dead and fx['grad_norms'][k] >= floor]
 
@@ -134,6 +134,57 @@ def grad_cosines(mine, theirs, keys):
 # rounded value, measured with tools/dump_step.py) is the same noise class again.  All runs use DSR_DETERMINISTIC=1,
 # so the measured figures below are reproduced bit for bit and the gates sit right above them.
 # ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('name', ['step_zero_nearest_72x88.pt', 'step_zero_bilinear_64x64.pt',
+                                  'step_reflection_nearest_64x96.pt'])
+def test_teacher_forced_step_other_pad_and_upsample_modes(golden, name, monkeypatch):
+    """get_net(pad='zero') and get_net(upsample_mode='nearest') against fixtures of the unmodified reference
+    (oracle/make_golden_modes.py): same gates as the default configuration."""
+    import dsr_b200
+    from oracle import dip_oracle as O
+    monkeypatch.setenv('DSR_DETERMINISTIC', '1')
+    fx = golden(name)
+    pad, up = fx['pad'], fx['upsample_mode']
+    torch.manual_seed(fx['seed'])
+    net = dsr_b200.get_net(32, 'skip', pad, skip_n33d=128, skip_n33u=128, skip_n11=4, num_scales=5, upsample_mode=up)
+    assert list(net.state_dict().keys()) == fx['keys']
+    sd0 = {k: v.clone() for k, v in net.state_dict().items()}
+    net = net.cuda()
+    ds = dsr_b200.Downsampler(3, fx['factor'], 'lanczos2', phase=0.5, preserve_size=True).cuda()
+    out = net(fx['z0'].cuda())
+    out_lr = ds(out)
+    loss = torch.nn.MSELoss()(out_lr, fx['lr_img'].cuda())
+    loss.backward()
+    assert rel(out, fx['out_hr']) < 1e-2
+    assert rel(out_lr, fx['out_lr']) < 1e-2
+    assert float(loss) == pytest.approx(fx['losses'][0], rel=1e-2)
+    _, _, grads = O.step_loss_and_grads(sd0, fx['z0'], fx['lr_img'], fx['factor'], pad=pad, upsample_mode=up)
+    loss_q, out_q, grads_q = O.step_loss_and_grads(sd0, fx['z0'], fx['lr_img'], fx['factor'], quant=O.fp16_points(),
+                                                   pad=pad, upsample_mode=up)
+    mine = {k: p.grad for k, p in net.named_parameters()}
+    keys = live_keys(fx)
+    assert len(keys) >= 60
+    for k in keys:
+        if fx['grad_norms'][k] > 1e-3 * max(fx['grad_norms'].values()):
+            assert float(mine[k].double().norm().cpu()) == pytest.approx(fx['grad_norms'][k], rel=0.25), k
+    for k, g in fx['grad_slices'].items():                       # wgrad layouts
+        assert cosine(mine[k][:8, :8], g) > 0.9, k
+    # per-tensor figure over the tensors that carry gradient mass (a 4-element BatchNorm beta with 1e-3 of the largest
+    # norm is rounding noise in both arithmetics)
+    big = [k for k in keys if fx['grad_norms'][k] > 2e-3 * max(fx['grad_norms'].values())]
+    whole, _ = grad_cosines(mine, grads, keys)
+    whole_q, _ = grad_cosines(mine, grads_q, keys)
+    _, worst = grad_cosines(mine, grads, big)
+    _, worst_q = grad_cosines(mine, grads_q, big)
+    print(f'{name}: out rel {rel(out, fx["out_hr"]):.2e} (vs fp16-point oracle {rel(out, out_q):.2e}); gradient cosine '
+          f'whole / worst tensor: {whole:.4f} / {worst:.4f} vs fp32, {whole_q:.4f} / {worst_q:.4f} vs fp16-point oracle')
+    # measured (deterministic): whole-gradient cosine vs the fp16-point oracle 0.986 / 0.990 / 0.991, worst tensor
+    # (the 128 BatchNorm betas of the deepest level, norm 5e-4) 0.936 / 0.966 / 0.959; output 1.4e-3 / 1.9e-3 / 2.0e-3
+    assert whole > 0.97 and worst > 0.9
+    assert whole_q > 0.98 and worst_q > 0.92
+    assert rel(out, out_q) < 6e-3
+    assert float(loss) == pytest.approx(float(loss_q), rel=3e-3)
+
+
 @pytest.mark.parametrize('name', ['step_64x64.pt', 'step_64x96.pt', 'step_72x88.pt'])   # last: odd level sizes, Concat crop
 def test_teacher_forced_step_matches_reference(golden, name, monkeypatch):
     import dsr_b200
@@ -436,7 +487,8 @@ def test_whole_step_tensor_core_vs_checker_256():
     assert cosine(g_tc, net.flat_buffers()[1]) > 0.98
 
 
-def test_long_run_psnr_matches_reference(golden):
+@pytest.mark.parametrize('fixture', ['psnr_128.pt', 'psnr_256.pt'])
+def test_long_run_psnr_matches_reference(golden, fixture, monkeypatch):
     """North-star gate: mean final PSNR within 0.1 dB of the reference -- evaluated, as SURVEY.md 7.2.2 prescribes,
     on the MEAN over a batch of images (a single DIP run moves by ~0.1 dB under a 1e-7 weight perturbation).
     Reference curves: oracle/make_golden_psnr.py (the unmodified reference on CPU, 8 images, 128x128, 400 iterations).
@@ -444,7 +496,12 @@ def test_long_run_psnr_matches_reference(golden):
     implied by the reference's own seed-to-seed spread on one image."""
     import dsr_b200
     from oracle import dip_oracle as O
-    g = golden('psnr_128.pt')
+    if not os.path.exists(os.path.join(os.path.dirname(__file__), 'golden', fixture)):
+        pytest.skip(f'{fixture} not generated')
+    # fixed-order reductions: the (chaotic) 400-iteration runs are then reproduced bit for bit from run to run, so the
+    # strict 0.1 dB gate below is a property of the code, not of the atomics' arrival order
+    monkeypatch.setenv('DSR_DETERMINISTIC', '1')
+    g = golden(fixture)
     size, iters = g['size'], g['iters']
     cfg = {'learning_rate': g['lr'], 'num_iter': iters, 'reg_noise_std': g['reg_noise_std']}
     runs = [r for r in g['runs'] if r['image'] == r['seed']]
@@ -470,7 +527,18 @@ def test_long_run_psnr_matches_reference(golden):
     print(f'PSNR mean ours {mean_ours:.3f} dB, reference {mean_ref:.3f} dB, reference seed spread {spread:.3f} dB, '
           f'tolerance {tol:.3f} dB; per image ours {[round(v, 2) for v in ours]} '
           f'ref {[round(r["psnr_last50"], 2) for r in runs]}')
+    # evidence file (profiles/r02_psnr_<size>.json is a copy of a GPU run's output)
+    ev_dir = os.path.join(os.path.dirname(os.path.dirname(__file__)), 'gpurun_out')
+    if os.path.isdir(ev_dir):
+        import json
+        with open(os.path.join(ev_dir, f'r02_psnr_{size}.json'), 'w') as f:
+            json.dump({'size': size, 'iters': iters, 'images': len(runs), 'mean_ours_db': mean_ours,
+                       'mean_reference_db': mean_ref, 'diff_db': mean_ours - mean_ref, 'tolerance_db': tol,
+                       'reference_seed_spread_db': spread, 'ours': ours,
+                       'reference': [r['psnr_last50'] for r in runs]}, f)
     assert abs(mean_ours - mean_ref) < tol
+    if len(runs) >= 16:      # the mean of 16 images has a standard error of ~0.08 dB on each side: the north-star's 0.1 dB
+        assert abs(mean_ours - mean_ref) < 0.1        # (measured: +0.012 dB at 128 x 128, deterministic mode)
 
 
 def test_dip_isr_driver_and_drop_in_module_names():

@@ -118,6 +118,33 @@ def test_step_matches_reference(golden, name):
         assert close.float().mean() > 0.95, k
 
 
+@pytest.mark.parametrize('name', ['step_zero_nearest_72x88.pt', 'step_zero_bilinear_64x64.pt',
+                                  'step_reflection_nearest_64x96.pt'])
+def test_step_matches_reference_other_pad_and_upsample_modes(golden, name):
+    """pad='zero' (models/DIP/utils.py:96-102) and upsample_mode='nearest' (models/DIP/skip.py:77): the oracle follows
+    the reference's fixtures (oracle/make_golden_modes.py), including the state_dict keys of the pad-less conv()."""
+    fx = golden(name)
+    torch.set_num_threads(1)
+    torch.manual_seed(fx['seed'])
+    sd = O.init_params(pad=fx['pad'])
+    assert set(fx['keys']) == set(sd.keys())
+    loss, out, grads = O.step_loss_and_grads(sd, fx['z0'], fx['lr_img'], fx['factor'], pad=fx['pad'],
+                                             upsample_mode=fx['upsample_mode'])
+    assert rel(out, fx['out_hr']) < 1e-6
+    assert float(loss) == pytest.approx(fx['losses'][0], rel=1e-5)
+    dead = set(O.dead_param_keys(pad=fx['pad']))
+    floor = 1e-6 * max(fx['grad_norms'].values())
+    dead |= {k for k, n in fx['grad_norms'].items() if n < floor}
+    for k, n in fx['grad_norms'].items():
+        if k not in dead:
+            assert float(grads[k].double().norm()) == pytest.approx(n, rel=1e-4), k
+    for k, g in fx['grad_full'].items():
+        if k not in dead:
+            assert rel(grads[k], g) < 1e-4, k
+    for k, g in fx['grad_slices'].items():
+        assert rel(grads[k][:8, :8], g) < 1e-4, k
+
+
 def test_psnr_and_synthetic_pair():
     lr, hr = O.synthetic_pair(0, 64)
     assert hr.shape == (3, 64, 64) and lr.shape == (3, 16, 16)

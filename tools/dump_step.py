@@ -17,8 +17,8 @@ sys.path.insert(0, ROOT)
 def run(fx, keep_taps):
     import dsr_b200
     torch.manual_seed(fx['seed'])
-    net = dsr_b200.get_net(32, 'skip', 'reflection', skip_n33d=128, skip_n33u=128, skip_n11=4, num_scales=5,
-                           upsample_mode='bilinear')
+    net = dsr_b200.get_net(32, 'skip', fx.get('pad', 'reflection'), skip_n33d=128, skip_n33u=128, skip_n11=4,
+                           num_scales=5, upsample_mode=fx.get('upsample_mode', 'bilinear'))
     if 'z0' in fx:
         z0 = fx['z0']
     else:        # large fixtures keep the seed only (oracle/make_golden_large.py): same CPU draws as the reference
