@@ -736,7 +736,7 @@ def run_gan(args, rank, local_rank, world):
                                    f'chunks of {g.max_chunk} images per library call',
                        'batch': B, 'factor': 8, 'l2': 'activations of a 32-image chunk are 0.3-2.4 GB >> 126 MB L2'},
             'roofline': {'bound': 'tensor', 'kernel': 'whole forward: conv_halo2_kernel<1> (3x3 64->64 / 64->256+shuffle) '
-                         'and conv_halo2_kernel<2> (9x9 64->3)', 'achieved': tfl, 'peak': pk['tflops'], 'unit': 'TFLOP/s',
+                         'conv9_out_kernel (9x9 64->3 + tanh, kx taps folded into N) and gen_conv1_kernel (9x9 3->64, CUDA cores)', 'achieved': tfl, 'peak': pk['tflops'], 'unit': 'TFLOP/s',
                          'frac': tfl / pk['tflops'] if pk['tflops'] else None, 'traffic': None, 'peak_source': pk['src'],
                          'gflop_per_image': GAN_FLOPS_96 / 1e9},
             'e2e': {'value': world * n_e2e * B / (ms_e2e * 1e-3), 'unit': 'images/s', 'h2d_bytes_per_step': hx.numel() * 4,
