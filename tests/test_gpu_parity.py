@@ -410,6 +410,31 @@ def test_fused_step_tracks_the_closure_path():
     assert float(l1[0]) == pytest.approx(float(l2), rel=1e-5)
 
 
+@pytest.mark.parametrize('pad,up', [('zero', 'nearest'), ('zero', 'bilinear'), ('reflection', 'nearest')])
+def test_fused_step_in_the_other_pad_and_upsample_modes(pad, up):
+    """The whole-iteration path (input packing with the in-place noise draw, CUDA-graph replay) with pad='zero' /
+    upsample_mode='nearest': sigma = 0 first iteration equals the closure path, and the loop converges."""
+    import dsr_b200
+    from oracle import dip_oracle as O
+    lr_img, hr = O.synthetic_pair(4, 72)
+
+    def mk(seed):
+        torch.manual_seed(seed)
+        return dsr_b200.get_net(32, 'skip', pad, skip_n33d=128, skip_n33u=128, skip_n11=4, num_scales=5, upsample_mode=up)
+    net_a, net_b = mk(2), mk(2).cuda()
+    z = dsr_b200.get_noise(32, 'noise', (72, 72))
+    cfg0 = {'learning_rate': 0.01, 'num_iter': 1, 'reg_noise_std': 0.0}
+    _, l1 = dsr_b200.dip_sr_fused(net_a, lr_img, (72, 72), 4, cfg0, 'cuda:0', net_input=z)
+    ds = dsr_b200.Downsampler(3, 4, 'lanczos2', phase=0.5, preserve_size=True)
+    l2 = torch.nn.MSELoss()(ds(net_b(z.cuda())), lr_img.unsqueeze(0).cuda())
+    assert float(l1[0]) == pytest.approx(float(l2), rel=1e-5)
+    cfg = {'learning_rate': 0.01, 'num_iter': 60, 'reg_noise_std': 0.05}
+    out, losses = dsr_b200.dip_sr_fused(mk(1), lr_img, (72, 72), 4, cfg, 'cuda:0', seed=5)
+    ls = losses.cpu()
+    assert bool(torch.isfinite(ls).all()) and float(ls[-5:].mean()) < 0.5 * float(ls[:5].mean())
+    assert 0 <= float(out.min()) and float(out.max()) <= 1
+
+
 def test_fused_step_draws_the_counter_based_noise():
     """The whole-step path draws z inside the input-packing pass; it must be the stream dsr_perturb defines:
     iteration t uses counters (t - 1) * ceil(n / 4) + i."""
