@@ -829,6 +829,122 @@ __global__ void __launch_bounds__(kThreads, 3) upcat_apply_kernel(UpcatArgs a) {
   }
 }
 
+// upcat_apply, wide form.  The kernel above runs issue-bound (IPC 2.5, ~26 instructions per output element at 512 x 512:
+// 8-byte accesses, two shuffles per pixel for the skip channels, whose evaluation on lanes 0..3 the whole warp waits
+// for).  Here a thread owns 8 channels (16-byte accesses) of one 2 x 2 output block, so the per-block address / bounds
+// work is spread over twice the outputs, and the 16 tail channels [128, 144) -- 4 skip channels + 12 zeros -- are
+// written by separate blocks of the same launch (one thread per high-resolution pixel, 2 x 16 bytes).
+__device__ __forceinline__ void upcat_apply8_main(const UpcatArgs& a, int vblock, int vgrid) {
+  const int g = threadIdx.x & 15, c0 = g * 8;
+  // BN(132) coefficients once per block (thread c < 128 <-> channel c), then 8 per thread from shared memory: a
+  // per-thread evaluation (32 loads + 8 rsqrt) costs more than the one or two 2 x 2 blocks a thread has at <= 256 x 256
+  __shared__ __align__(16) float cs_scale[128], cs_shift[128];
+  if (threadIdx.x < 128) {
+    float mean, rstd, ga, be;
+    cat_coeffs(a, threadIdx.x, mean, rstd, ga, be);
+    cs_scale[threadIdx.x] = ga * rstd;
+    cs_shift[threadIdx.x] = be - mean * ga * rstd;
+  }
+  __syncthreads();
+  float scale[8], shift[8];
+#pragma unroll
+  for (int j = 0; j < 8; j += 4) {
+    const float4 sc4 = *reinterpret_cast<const float4*>(&cs_scale[c0 + j]);
+    const float4 sh4 = *reinterpret_cast<const float4*>(&cs_shift[c0 + j]);
+    scale[j] = sc4.x; scale[j + 1] = sc4.y; scale[j + 2] = sc4.z; scale[j + 3] = sc4.w;
+    shift[j] = sh4.x; shift[j + 1] = sh4.y; shift[j + 2] = sh4.z; shift[j + 3] = sh4.w;
+  }
+  const int bw = a.w + 1;
+  const int nblk = (a.h + 1) * bw;
+  const int Wp = a.W + 2;
+  __half* out = static_cast<__half*>(a.cat_pad) + c0;
+  const __half* d = static_cast<const __half*>(a.deep) + c0;
+  const float wa = a.nearest ? 1.f : 0.75f, wb = a.nearest ? 0.f : 0.25f;
+  const int bpp = blockDim.x >> 4;                       // 2 x 2 blocks per thread-block pass
+  for (int blk = vblock * bpp + (threadIdx.x >> 4); blk < nblk; blk += vgrid * bpp) {
+    const int by = blk / bw - 1, bx = blk - (blk / bw) * bw - 1;
+    const int sy0 = max(by, 0), sy1 = min(by + 1, a.h - 1), sx0 = max(bx, 0), sx1 = min(bx + 1, a.w - 1);
+    const uint4 v00 = __ldg(reinterpret_cast<const uint4*>(d + sy0 * a.deep_sy + static_cast<long long>(sx0) * 128));
+    const uint4 v01 = __ldg(reinterpret_cast<const uint4*>(d + sy0 * a.deep_sy + static_cast<long long>(sx1) * 128));
+    const uint4 v10 = __ldg(reinterpret_cast<const uint4*>(d + sy1 * a.deep_sy + static_cast<long long>(sx0) * 128));
+    const uint4 v11 = __ldg(reinterpret_cast<const uint4*>(d + sy1 * a.deep_sy + static_cast<long long>(sx1) * 128));
+    const __half2* h00 = reinterpret_cast<const __half2*>(&v00);
+    const __half2* h01 = reinterpret_cast<const __half2*>(&v01);
+    const __half2* h10 = reinterpret_cast<const __half2*>(&v10);
+    const __half2* h11 = reinterpret_cast<const __half2*>(&v11);
+    uint4 o[2][2];
+    __half2* oh[2][2] = {{reinterpret_cast<__half2*>(&o[0][0]), reinterpret_cast<__half2*>(&o[0][1])},
+                         {reinterpret_cast<__half2*>(&o[1][0]), reinterpret_cast<__half2*>(&o[1][1])}};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f00 = __half22float2(h00[i]), f01 = __half22float2(h01[i]);
+      const float2 f10 = __half22float2(h10[i]), f11 = __half22float2(h11[i]);
+      // the same association as up_eval: rows first (source row 0 -> t, row 1 -> b), then columns
+      const float t0x = wa * f00.x + wb * f01.x, t1x = wb * f00.x + wa * f01.x;
+      const float b0x = wa * f10.x + wb * f11.x, b1x = wb * f10.x + wa * f11.x;
+      const float t0y = wa * f00.y + wb * f01.y, t1y = wb * f00.y + wa * f01.y;
+      const float b0y = wa * f10.y + wb * f11.y, b1y = wb * f10.y + wa * f11.y;
+      const float sx = scale[2 * i], hx = shift[2 * i], sy = scale[2 * i + 1], hy = shift[2 * i + 1];
+      oh[0][0][i] = __floats2half2_rn(fmaf(wa * t0x + wb * b0x, sx, hx), fmaf(wa * t0y + wb * b0y, sy, hy));
+      oh[0][1][i] = __floats2half2_rn(fmaf(wa * t1x + wb * b1x, sx, hx), fmaf(wa * t1y + wb * b1y, sy, hy));
+      oh[1][0][i] = __floats2half2_rn(fmaf(wb * t0x + wa * b0x, sx, hx), fmaf(wb * t0y + wa * b0y, sy, hy));
+      oh[1][1][i] = __floats2half2_rn(fmaf(wb * t1x + wa * b1x, sx, hx), fmaf(wb * t1y + wa * b1y, sy, hy));
+    }
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const int y = 2 * by + 1 + rr, x = 2 * bx + 1 + cc;
+        if (y < 0 || x < 0 || y >= a.H || x >= a.W) continue;
+        *reinterpret_cast<uint4*>(out + (static_cast<long long>(y + 1) * Wp + (x + 1)) * 144) = o[rr][cc];
+        if (!a.pad_zero && (x == 1 || x == a.W - 2 || y == 1 || y == a.H - 2)) {        // reflected halo copies
+          int ys[3], xs[3];
+          const int ny = halo_coords(y, a.H, ys), nx = halo_coords(x, a.W, xs);
+          for (int i = 0; i < ny; ++i)
+            for (int k = 0; k < nx; ++k)
+              if (i | k) *reinterpret_cast<uint4*>(out + (static_cast<long long>(ys[i]) * Wp + xs[k]) * 144) = o[rr][cc];
+        }
+      }
+  }
+}
+// the 16 tail channels of every pixel: BN(132) of the skip branch's LeakyReLU(BN(4)(sraw)) + 12 zeros
+__device__ __forceinline__ void upcat_apply8_tail(const UpcatArgs& a, int vblock, int vgrid) {
+  __shared__ SkipConst sc;
+  skip_const_init(&sc, a, nullptr, true);
+  const long long npix = static_cast<long long>(a.H) * a.W;
+  const int Wp = a.W + 2;
+  __half* out = static_cast<__half*>(a.cat_pad) + 128;
+  for (long long pix = static_cast<long long>(vblock) * blockDim.x + threadIdx.x; pix < npix;
+       pix += static_cast<long long>(vgrid) * blockDim.x) {
+    const int y = static_cast<int>(pix / a.W), x = static_cast<int>(pix - static_cast<long long>(y) * a.W);
+    float sv[4], xh[4], yv[4], t0[4];
+    skip_act4(sc, a.sraw, pix, sv, xh, yv);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) t0[k] = fmaf(sv[k], sc.ck1[k], sc.csh[k]);
+    const uint2 pk = pack4h(t0);
+    const uint4 lo = make_uint4(pk.x, pk.y, 0u, 0u), hi = make_uint4(0u, 0u, 0u, 0u);
+    int ys[3], xs[3];
+    int ny = 1, nx = 1;
+    ys[0] = y + 1;
+    xs[0] = x + 1;
+    if (!a.pad_zero && (x == 1 || x == a.W - 2 || y == 1 || y == a.H - 2)) {
+      ny = halo_coords(y, a.H, ys);
+      nx = halo_coords(x, a.W, xs);
+    }
+    for (int i = 0; i < ny; ++i)
+      for (int k = 0; k < nx; ++k) {
+        uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<long long>(ys[i]) * Wp + xs[k]) * 144);
+        dst[0] = lo;
+        dst[1] = hi;
+      }
+  }
+}
+__global__ void __launch_bounds__(kThreads, 3) upcat_apply8_kernel(UpcatArgs a, int nb_tail) {
+  pdl_sync();
+  if (static_cast<int>(blockIdx.x) < nb_tail) upcat_apply8_tail(a, blockIdx.x, nb_tail);
+  else upcat_apply8_main(a, blockIdx.x - nb_tail, gridDim.x - nb_tail);
+}
+
 static int up_grid(const UpcatArgs& a, int cap) {
   const long long nblk = static_cast<long long>(a.h + 1) * (a.w + 1);
   long long blocks = (nblk + 8 * kUpUnroll - 1) / (8 * kUpUnroll);
@@ -840,7 +956,19 @@ int launch_upcat_stats(const UpcatArgs& a, cudaStream_t s) {
   DSR_LAUNCH_CHECK();
 }
 int launch_upcat_apply(const UpcatArgs& a, cudaStream_t s) {
-  launch_k(upcat_apply_kernel, dim3(up_grid(a, 148 * 12)), dim3(kThreads), 0, s, a);
+  static const bool old_form = getenv("DSR_UPAPPLY_OLD") != nullptr;        // A/B
+  if (old_form) {
+    launch_k(upcat_apply_kernel, dim3(up_grid(a, 148 * 12)), dim3(kThreads), 0, s, a);
+    DSR_LAUNCH_CHECK();
+  }
+  const long long nblk = static_cast<long long>(a.h + 1) * (a.w + 1);
+  long long nb_main = (nblk + 15) / 16;                                     // 16 blocks of 2 x 2 per thread block and pass
+  const long long per = (nb_main + 148 * 8 - 1) / (148 * 8);               // equal passes per block
+  nb_main = (nb_main + per - 1) / per;
+  long long nb_tail = (static_cast<long long>(a.H) * a.W + kThreads - 1) / kThreads;
+  if (nb_tail > 148 * 2) nb_tail = 148 * 2;
+  launch_k(upcat_apply8_kernel, dim3(static_cast<int>(nb_main + nb_tail)), dim3(kThreads), 0, s, a,
+           static_cast<int>(nb_tail));
   DSR_LAUNCH_CHECK();
 }
 
