@@ -80,6 +80,36 @@ __device__ __forceinline__ void bn_coeffs(const BnRef& bn, int c, float& mean, f
 
 __device__ __forceinline__ float lrelu(float y) { return y > 0.f ? y : kSlope * y; }
 
+// Block-shared coefficient table of one 128-channel BatchNorm: thread c < 128 evaluates channel c ONCE per block
+// (two 64-bit fixed-point sums, gamma, beta, an rsqrt; with `bstats` also the two backward means), every thread then
+// reads its 4 channels as float4s.  Evaluated per thread -- 4 channels x (4-6 loads + conversions + rsqrt), ~150-250
+// instructions -- this prologue was a third to a half of an element-wise kernel's instructions at <= 256 x 256 pixels.
+struct BnTab {
+  float mean[128], rstd[128], ga[128], be[128], c1[128], c2[128];
+};
+// contains a barrier; blockDim.x >= 128.  bstats: [2][128] backward sums (or nullptr), raw2: second sum is sum dy * r
+__device__ __forceinline__ void bn_tab_fill(BnTab& t, const BnRef& bn, const acc_t* bstats = nullptr, int raw2 = 0) {
+  if (threadIdx.x < 128) {
+    const int c = threadIdx.x;
+    float mean, rstd, ga, be;
+    bn_coeffs(bn, c, mean, rstd, ga, be);
+    t.mean[c] = mean;
+    t.rstd[c] = rstd;
+    t.ga[c] = ga;
+    t.be[c] = be;
+    if (bstats != nullptr) {
+      const float s1 = acc_get_b(&bstats[c]), v = acc_get_b(&bstats[128 + c]);
+      t.c1[c] = s1 * bn.inv_n;
+      t.c2[c] = (raw2 ? rstd * (v - mean * s1) : v) * bn.inv_n;
+    }
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ void tab4(const float* arr, int c0, float (&v)[4]) {
+  const float4 f = *reinterpret_cast<const float4*>(arr + c0);
+  v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+}
+
 // bilinear x2, align_corners = False: source index and weights for output index o
 // (nearest != 0: nn.Upsample(mode='nearest'), source floor(o / 2) with weight 1)
 __device__ __forceinline__ void up_src(int o, int n, int& i0, int& i1, float& l0, float& l1, int nearest = 0) {
@@ -393,14 +423,21 @@ __global__ void __launch_bounds__(kThreads) bn_act_kernel(const __half* __restri
                                                           SkipFuse sf) {
   pdl_sync();
   const int lane = threadIdx.x & 31;
+  __shared__ __align__(16) BnTab tab;
+  bn_tab_fill(tab, bn);
   float scale[4], shift[4];
   float wr[SKIP ? 4 : 1][4];
+  {
+    float mean[4], rstd[4], ga[4], be[4];
+    tab4(tab.mean, lane * 4, mean); tab4(tab.rstd, lane * 4, rstd); tab4(tab.ga, lane * 4, ga); tab4(tab.be, lane * 4, be);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      scale[j] = ga[j] * rstd[j];
+      shift[j] = be[j] - mean[j] * scale[j];
+    }
+  }
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    float mean, rstd, ga, be;
-    bn_coeffs(bn, lane * 4 + j, mean, rstd, ga, be);
-    scale[j] = ga * rstd;
-    shift[j] = be - mean * scale[j];
     if (SKIP) {
 #pragma unroll
       for (int o = 0; o < 4; ++o) wr[o][j] = sf.w[o * 128 + lane * 4 + j];
@@ -1550,21 +1587,23 @@ __global__ void __launch_bounds__(kThreads, 3) bn_bwd_fast_kernel(BnBwdArgs a) {
   const int lane = threadIdx.x & 31;
   const int c0 = lane * 4;
   float k1[4], sh[4], A[4], B[4], s1[4], s2[4], mean_[4], rstd_[4];
+  __shared__ __align__(16) BnTab tab;
+  bn_tab_fill(tab, a.bn, APPLY ? a.bstats : nullptr, a.bstats_raw);
+  {
+    float ga[4], be[4], c1[4], c2[4];
+    tab4(tab.mean, c0, mean_); tab4(tab.rstd, c0, rstd_); tab4(tab.ga, c0, ga); tab4(tab.be, c0, be);
+    if (APPLY) { tab4(tab.c1, c0, c1); tab4(tab.c2, c0, c2); }
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    float mean, rstd, ga, be;
-    bn_coeffs(a.bn, c0 + j, mean, rstd, ga, be);
-    k1[j] = ga * rstd;
-    sh[j] = be - mean * k1[j];
-    mean_[j] = mean;
-    rstd_[j] = rstd;
-    if (APPLY) {
-      const float c1 = acc_get_b(&a.bstats[c0 + j]) * a.bn.inv_n, c2 = bn_bwd_s2(a, c0 + j, mean, rstd) * a.bn.inv_n;
-      B[j] = -k1[j] * c2 * rstd;
-      A[j] = -k1[j] * (c1 - c2 * mean * rstd);
+    for (int j = 0; j < 4; ++j) {
+      k1[j] = ga[j] * rstd_[j];
+      sh[j] = be[j] - mean_[j] * k1[j];
+      if (APPLY) {
+        B[j] = -k1[j] * c2[j] * rstd_[j];
+        A[j] = -k1[j] * (c1[j] - c2[j] * mean_[j] * rstd_[j]);
+      }
+      s1[j] = 0.f;
+      s2[j] = 0.f;
     }
-    s1[j] = 0.f;
-    s2[j] = 0.f;
   }
   const int H = a.H, W = a.W, Wp = W + 2, gpr = W >> 2, ngroups = H * gpr;
   const int gC = a.gC;
