@@ -1174,14 +1174,18 @@ __global__ void __launch_bounds__(kThreads, 3) bn_act_final_kernel(const __half*
   const int lane = threadIdx.x & 31;
   const int c0 = lane * 4;
   float scale[4], shift[4], wr[3][4];
+  __shared__ __align__(16) BnTab tab;
+  bn_tab_fill(tab, bn);
+  {
+    float mean[4], rstd[4], ga[4], be[4];
+    tab4(tab.mean, c0, mean); tab4(tab.rstd, c0, rstd); tab4(tab.ga, c0, ga); tab4(tab.be, c0, be);
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    float mean, rstd, ga, be;
-    bn_coeffs(bn, c0 + j, mean, rstd, ga, be);
-    scale[j] = ga * rstd;
-    shift[j] = be - mean * scale[j];
+    for (int j = 0; j < 4; ++j) {
+      scale[j] = ga[j] * rstd[j];
+      shift[j] = be[j] - mean[j] * scale[j];
 #pragma unroll
-    for (int o = 0; o < 3; ++o) wr[o][j] = w[o * 128 + c0 + j];
+      for (int o = 0; o < 3; ++o) wr[o][j] = w[o * 128 + c0 + j];
+    }
   }
   const int my_o = lane & 3;
   const float my_b = my_o < 3 ? b[my_o] : 0.f;
@@ -1245,16 +1249,18 @@ __global__ void __launch_bounds__(kThreads, 3) bn_bwd_top_kernel(TopBwdArgs a) {
   const int c0 = lane * 4;
   const float S = a.gs[0], invS = a.gs[1];
   float k1[4], sh[4], A[4], B[4], s1[4], s2[4], wr[3][4], aw[3][4], ab[3] = {0.f, 0.f, 0.f}, mean_[4], rstd_[4];
+  __shared__ __align__(16) BnTab tab;
+  bn_tab_fill(tab, a.bn, APPLY ? a.bstats : nullptr, 0);
+  float tga[4], tbe[4], tc1[4], tc2[4];
+  tab4(tab.mean, c0, mean_); tab4(tab.rstd, c0, rstd_); tab4(tab.ga, c0, tga); tab4(tab.be, c0, tbe);
+  if (APPLY) { tab4(tab.c1, c0, tc1); tab4(tab.c2, c0, tc2); }
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    float mean, rstd, ga, be;
-    bn_coeffs(a.bn, c0 + j, mean, rstd, ga, be);
-    k1[j] = ga * rstd;
-    sh[j] = be - mean * k1[j];
-    mean_[j] = mean;
-    rstd_[j] = rstd;
+    const float mean = mean_[j], rstd = rstd_[j];
+    k1[j] = tga[j] * rstd;
+    sh[j] = tbe[j] - mean * k1[j];
     if (APPLY) {
-      const float c1 = acc_get_b(&a.bstats[c0 + j]) * a.bn.inv_n, c2 = acc_get_b(&a.bstats[128 + c0 + j]) * a.bn.inv_n;
+      const float c1 = tc1[j], c2 = tc2[j];
       B[j] = -k1[j] * c2 * rstd;
       A[j] = -k1[j] * (c1 - c2 * mean * rstd);
     }
@@ -1442,17 +1448,21 @@ __global__ void __launch_bounds__(kThreads, HAS_DS ? 2 : 3) bn_bwd_kernel(BnBwdA
     }
     __syncthreads();
   }
+  {
+    __shared__ __align__(16) BnTab tab;
+    bn_tab_fill(tab, a.bn, APPLY ? a.bstats : nullptr, a.bstats_raw);
+    float tmean[4], trstd[4];
+    tab4(tab.mean, c0, tmean); tab4(tab.rstd, c0, trstd); tab4(tab.ga, c0, ga); tab4(tab.be, c0, be);
+    if (APPLY) { tab4(tab.c1, c0, c1); tab4(tab.c2, c0, c2); }
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    float mean, rstd;
-    bn_coeffs(a.bn, c0 + j, mean, rstd, ga[j], be[j]);
-    xa[j] = rstd;
-    xb[j] = -mean * rstd;
-    k1[j] = ga[j] * rstd;
-    c1[j] = APPLY ? acc_get_b(&a.bstats[c0 + j]) * a.bn.inv_n : 0.f;
-    c2[j] = APPLY ? bn_bwd_s2(a, c0 + j, mean, rstd) * a.bn.inv_n : 0.f;
-    s1[j] = 0.f;
-    s2[j] = 0.f;
+    for (int j = 0; j < 4; ++j) {
+      xa[j] = trstd[j];
+      xb[j] = -tmean[j] * trstd[j];
+      k1[j] = ga[j] * trstd[j];
+      if (!APPLY) { c1[j] = 0.f; c2[j] = 0.f; }
+      s1[j] = 0.f;
+      s2[j] = 0.f;
+    }
   }
   const int H = a.H, W = a.W, Wp = W + 2;
   const __half* __restrict__ gp = static_cast<const __half*>(a.g);
@@ -2463,21 +2473,34 @@ __device__ __forceinline__ void upcat_bwd_elem_body(const UpcatBwdArgs& a, __hal
   const int g = threadIdx.x & 15;
   const int c0 = g * 8;
   const float inv_n = 1.f / (static_cast<float>(f.H) * static_cast<float>(f.W));
+  // per-channel coefficients once per block (thread c < 128 <-> packed channel c), 8 per thread from shared memory
+  __shared__ __align__(16) float ct_k1[128], ct_A[128], ct_B[128];
+  if (threadIdx.x < 128) {
+    const int c = threadIdx.x;
+    float mean, rstd, ga, be;
+    cat_coeffs(f, c, mean, rstd, ga, be);
+    const float kk = ga * rstd;
+    const float S1 = acc_get_b(&a.cbstats[c]);
+    const float S2 = rstd * (acc_get_b(&a.cbstats[144 + c]) - mean * S1);      // sum dc * xhat
+    const float c1 = S1 * inv_n, c2r = S2 * inv_n * rstd;
+    ct_k1[c] = kk;
+    ct_B[c] = -kk * c2r;
+    ct_A[c] = -kk * (c1 - c2r * mean);
+    if (vblock == 0) {
+      a.dcat_beta[c + 4] = S1 * a.gs[1];       // packed channel c <-> reference channel c + 4
+      a.dcat_gamma[c + 4] = S2 * a.gs[1];
+    }
+  }
+  __syncthreads();
   float k1[8], A[8], B[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    float mean, rstd, ga, be;
-    cat_coeffs(f, c0 + j, mean, rstd, ga, be);
-    k1[j] = ga * rstd;
-    const float S1 = acc_get_b(&a.cbstats[c0 + j]);
-    const float S2 = rstd * (acc_get_b(&a.cbstats[144 + c0 + j]) - mean * S1);      // sum dc * xhat
-    const float c1 = S1 * inv_n, c2r = S2 * inv_n * rstd;
-    B[j] = -k1[j] * c2r;
-    A[j] = -k1[j] * (c1 - c2r * mean);
-    if (vblock == 0 && threadIdx.x < 16) {
-      a.dcat_beta[c0 + j + 4] = S1 * a.gs[1];       // packed channel c <-> reference channel c + 4
-      a.dcat_gamma[c0 + j + 4] = S2 * a.gs[1];
-    }
+  for (int j = 0; j < 8; j += 4) {
+    const float4 kv = *reinterpret_cast<const float4*>(&ct_k1[c0 + j]);
+    const float4 av = *reinterpret_cast<const float4*>(&ct_A[c0 + j]);
+    const float4 bv = *reinterpret_cast<const float4*>(&ct_B[c0 + j]);
+    k1[j] = kv.x; k1[j + 1] = kv.y; k1[j + 2] = kv.z; k1[j + 3] = kv.w;
+    A[j] = av.x; A[j + 1] = av.y; A[j + 2] = av.z; A[j + 3] = av.w;
+    B[j] = bv.x; B[j + 1] = bv.y; B[j + 2] = bv.z; B[j + 3] = bv.w;
   }
   const int npix = f.h * f.w;
   const int wp = f.w + 2;
@@ -2486,18 +2509,21 @@ __device__ __forceinline__ void upcat_bwd_elem_body(const UpcatBwdArgs& a, __hal
   const bool cons = a.cons_raw != nullptr;
   const __half* __restrict__ rb = static_cast<const __half*>(a.cons_raw) + c0;
   float ck1[8], csh[8], cs1[8], cs2[8];
+  __shared__ __align__(16) float ct_ck1[128], ct_csh[128];
+  if (cons && threadIdx.x >= 128) {          // block-uniform condition on `cons`; the other half of the block
+    const int c = threadIdx.x - 128;
+    float mean, rstd, ga, be;
+    bn_coeffs(a.cons_bn, c, mean, rstd, ga, be);
+    ct_ck1[c] = ga * rstd;
+    ct_csh[c] = be - mean * ga * rstd;
+  }
+  __syncthreads();
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     cs1[j] = 0.f;
     cs2[j] = 0.f;
-    ck1[j] = 0.f;
-    csh[j] = 0.f;
-    if (cons) {
-      float mean, rstd, ga, be;
-      bn_coeffs(a.cons_bn, c0 + j, mean, rstd, ga, be);
-      ck1[j] = ga * rstd;
-      csh[j] = be - mean * ck1[j];
-    }
+    ck1[j] = cons ? ct_ck1[c0 + j] : 0.f;
+    csh[j] = cons ? ct_csh[c0 + j] : 0.f;
   }
   const int ppb = blockDim.x >> 4;                   // pixels per block per pass
   for (int base = vblock * ppb * 2 + (threadIdx.x >> 4); base < npix; base += vgrid * ppb * 2) {
@@ -2594,21 +2620,34 @@ __device__ __forceinline__ void upcat_bwd_elem_lean(const UpcatBwdArgs& a, __hal
   const int g = threadIdx.x & 15;
   const int c0 = g * 8;
   const float inv_n = 1.f / (static_cast<float>(f.H) * static_cast<float>(f.W));
+  // per-channel coefficients once per block (thread c < 128 <-> packed channel c), 8 per thread from shared memory
+  __shared__ __align__(16) float ct_k1[128], ct_A[128], ct_B[128];
+  if (threadIdx.x < 128) {
+    const int c = threadIdx.x;
+    float mean, rstd, ga, be;
+    cat_coeffs(f, c, mean, rstd, ga, be);
+    const float kk = ga * rstd;
+    const float S1 = acc_get_b(&a.cbstats[c]);
+    const float S2 = rstd * (acc_get_b(&a.cbstats[144 + c]) - mean * S1);      // sum dc * xhat
+    const float c1 = S1 * inv_n, c2r = S2 * inv_n * rstd;
+    ct_k1[c] = kk;
+    ct_B[c] = -kk * c2r;
+    ct_A[c] = -kk * (c1 - c2r * mean);
+    if (vblock == 0) {
+      a.dcat_beta[c + 4] = S1 * a.gs[1];       // packed channel c <-> reference channel c + 4
+      a.dcat_gamma[c + 4] = S2 * a.gs[1];
+    }
+  }
+  __syncthreads();
   float k1[8], A[8], B[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    float mean, rstd, ga, be;
-    cat_coeffs(f, c0 + j, mean, rstd, ga, be);
-    k1[j] = ga * rstd;
-    const float S1 = acc_get_b(&a.cbstats[c0 + j]);
-    const float S2 = rstd * (acc_get_b(&a.cbstats[144 + c0 + j]) - mean * S1);      // sum dc * xhat
-    const float c1 = S1 * inv_n, c2r = S2 * inv_n * rstd;
-    B[j] = -k1[j] * c2r;
-    A[j] = -k1[j] * (c1 - c2r * mean);
-    if (vblock == 0 && threadIdx.x < 16) {
-      a.dcat_beta[c0 + j + 4] = S1 * a.gs[1];       // packed channel c <-> reference channel c + 4
-      a.dcat_gamma[c0 + j + 4] = S2 * a.gs[1];
-    }
+  for (int j = 0; j < 8; j += 4) {
+    const float4 kv = *reinterpret_cast<const float4*>(&ct_k1[c0 + j]);
+    const float4 av = *reinterpret_cast<const float4*>(&ct_A[c0 + j]);
+    const float4 bv = *reinterpret_cast<const float4*>(&ct_B[c0 + j]);
+    k1[j] = kv.x; k1[j + 1] = kv.y; k1[j + 2] = kv.z; k1[j + 3] = kv.w;
+    A[j] = av.x; A[j + 1] = av.y; A[j + 2] = av.z; A[j + 3] = av.w;
+    B[j] = bv.x; B[j + 1] = bv.y; B[j + 2] = bv.z; B[j + 3] = bv.w;
   }
   const int npix = f.h * f.w;
   const int wp = f.w + 2;
