@@ -1708,7 +1708,8 @@ static int fast_grid(int H, int W, int cap) {
 int launch_bn_bwd_stats(const BnBwdArgs& a, cudaStream_t s) {
   const int grid = warp_grid(a.H, a.W, 148 * 4);
   if (a.dsy == nullptr && (a.W & 3) == 0 && a.W >= 4) {
-    launch_k(bn_bwd_fast_kernel<false>, dim3(fast_grid(a.H, a.W, 148 * 8)), dim3(kThreads), 0, s, a);
+    static const int cap = getenv("DSR_STATS_CAP") ? atoi(getenv("DSR_STATS_CAP")) : 148 * 3;   // one resident wave: fewer same-address atomics (measured +0.7 %)
+    launch_k(bn_bwd_fast_kernel<false>, dim3(fast_grid(a.H, a.W, cap)), dim3(kThreads), 0, s, a);
     DSR_LAUNCH_CHECK();
   }
   if (a.dsy != nullptr) launch_k(bn_bwd_kernel<false, true>, dim3(grid), dim3(kThreads), 0, s, a);
@@ -2277,22 +2278,31 @@ __device__ __forceinline__ void upT_gather_tile_body(const UpcatBwdArgs& a, uint
                        : make_uint4(0u, 0u, 0u, 0u);
     }
     // ---- phase 1: stage the folded gradient region ----
-    constexpr int kItems = kGtRW * kGtRH * 16, kBatch = 12;    // 11.25 items per thread: one round trip
-    for (int i0 = threadIdx.x; i0 < kItems; i0 += kBatch * kThreads) {     // kBatch independent loads in flight
-      uint4 v[kBatch];
-#pragma unroll
-      for (int u = 0; u < kBatch; ++u) {
-        const int pixr = (i0 + u * kThreads) >> 4;
-        const int ry = pixr / kGtRW, rx = pixr - ry * kGtRW;
-        const int oy = oy0 + ry, ox = ox0 + rx;
-        v[u] = make_uint4(0u, 0u, 0u, 0u);
-        if (i0 + u * kThreads < kItems && oy >= 0 && oy < f.H && ox >= 0 && ox < f.W)
-          v[u] = fold_gather8(gc, 144, f.H, f.W, oy, ox, c0, !f.pad_zero);
+    // global -> shared memory with cp.async (no register staging: the 12 x 16-byte batch per thread cost 48 registers
+    // and held the kernel at 2 blocks per SM, whose load / compute phases ran in lockstep); the few pixels that fold a
+    // reflected halo cell onto themselves take the register path
+    constexpr int kItems = kGtRW * kGtRH * 16;                 // 11.25 items per thread
+    const int Wp144 = (f.W + 2) * 144;
+#pragma unroll 4
+    for (int i = threadIdx.x; i < kItems; i += kThreads) {
+      const int pixr = i >> 4;
+      const int ry = pixr / kGtRW, rx = pixr - ry * kGtRW;
+      const int oy = oy0 + ry, ox = ox0 + rx;
+      __half* dst = S + pixr * 128 + c0;
+      if (oy >= 0 && oy < f.H && ox >= 0 && ox < f.W) {
+        if (!f.pad_zero && (ox == 1 || ox == f.W - 2 || oy == 1 || oy == f.H - 2)) {
+          *reinterpret_cast<uint4*>(dst) = fold_gather8(gc, 144, f.H, f.W, oy, ox, c0, 1);
+        } else {
+          const __half* src = gc + static_cast<long long>(oy + 1) * Wp144 + (ox + 1) * 144 + c0;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(dst))),
+                       "l"(src)
+                       : "memory");
+        }
+      } else {
+        *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
       }
-#pragma unroll
-      for (int u = 0; u < kBatch; ++u)
-        if (i0 + u * kThreads < kItems) *reinterpret_cast<uint4*>(S + ((i0 + u * kThreads) >> 4) * 128 + c0) = v[u];
     }
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
     if (threadIdx.x < kGtH * 4 + kGtW * 4) {                  // transposed-bilinear weights of this tile
       if (threadIdx.x < kGtH * 4) {
         const int ly = threadIdx.x >> 2, aa = threadIdx.x & 3;
@@ -2700,7 +2710,7 @@ int launch_upcat_bwd_gather(const UpcatBwdArgs& a, cudaStream_t s) {
   const UpcatArgs& f = a.f;
   const long long tiles = static_cast<long long>((f.w + kGtW - 1) / kGtW) * ((f.h + kGtH - 1) / kGtH);
   long long grid = tiles;
-  if (grid > 148 * 2) grid = 148 * 2;
+  if (grid > 148 * 2) grid = 148 * 2;        // (3 or 4 blocks per SM at 80 registers: measured no gain)
   if (grid < 1) grid = 1;
   launch_k(upcat_bwd_a_kernel, dim3(static_cast<int>(grid)), dim3(kThreads), kGtSmem, s, a);
   DSR_LAUNCH_CHECK();

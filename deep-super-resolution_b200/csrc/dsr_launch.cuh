@@ -29,7 +29,7 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 // ks_end() adds the time at which block 0 finished its body.  No extra launches, so the programmatic overlap of the
 // replayed graph is untouched.
 #ifdef DSR_KSTAMP
-static __device__ unsigned long long* g_ks_buf = nullptr;   // [0] counter, then 4 words per record
+static __device__ unsigned long long* g_ks_buf = nullptr;   // [0] counter, then 8 words per record (entry, wait done, end, grid|block, 4 marks)
 __device__ __forceinline__ unsigned long long ks_now() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -49,10 +49,11 @@ __device__ __forceinline__ void pdl_sync() {
     const unsigned long long t1 = ks_now();
     const unsigned long long idx = atomicAdd(g_ks_buf, 1ull) % 4000ull;     // ring: the dump reads the last iteration
     {
-      g_ks_buf[1 + 4 * idx] = t0;
-      g_ks_buf[2 + 4 * idx] = t1;
-      g_ks_buf[3 + 4 * idx] = 0;
-      g_ks_buf[4 + 4 * idx] = (static_cast<unsigned long long>(gridDim.x * gridDim.y * gridDim.z) << 32) | blockDim.x;
+      g_ks_buf[1 + 8 * idx] = t0;
+      g_ks_buf[2 + 8 * idx] = t1;
+      g_ks_buf[3 + 8 * idx] = 0;
+      for (int m = 0; m < 4; ++m) g_ks_buf[5 + 8 * idx + m] = 0;
+      g_ks_buf[4 + 8 * idx] = (static_cast<unsigned long long>(gridDim.x * gridDim.y * gridDim.z) << 32) | blockDim.x;
       g_ks_slot = static_cast<unsigned int>(idx);
     }
   }
@@ -63,7 +64,16 @@ __device__ __forceinline__ void pdl_sync() {
 __device__ __forceinline__ void ks_end() {
 #ifdef DSR_KSTAMP
   if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && g_ks_buf != nullptr && g_ks_slot < 4000)
-    g_ks_buf[3 + 4 * g_ks_slot] = ks_now();
+    g_ks_buf[3 + 8 * g_ks_slot] = ks_now();
+#endif
+}
+// intermediate stamp m (0..3) of block 0 (diagnostics of one kernel's phases; call from thread 0's control path)
+__device__ __forceinline__ void ks_mark(int m) {
+#ifdef DSR_KSTAMP
+  if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && g_ks_buf != nullptr && g_ks_slot < 4000)
+    g_ks_buf[5 + 8 * g_ks_slot + m] = ks_now();
+#else
+  (void)m;
 #endif
 }
 #ifdef DSR_KSTAMP

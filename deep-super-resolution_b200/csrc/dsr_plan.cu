@@ -1790,8 +1790,8 @@ void kstamp_set_ds(unsigned long long*);
 static unsigned long long* g_ks_dev = nullptr;
 static void kstamp_arm() {                       // DSR_TIMELINE=2 (-DDSR_KSTAMP builds): in-kernel stamps
   if (timeline_mode() != 2 || g_ks_dev != nullptr) return;
-  if (cudaMalloc(&g_ks_dev, (1 + 4 * 4000) * sizeof(unsigned long long)) != cudaSuccess) { g_ks_dev = nullptr; return; }
-  cudaMemset(g_ks_dev, 0, (1 + 4 * 4000) * sizeof(unsigned long long));
+  if (cudaMalloc(&g_ks_dev, (1 + 8 * 4000) * sizeof(unsigned long long)) != cudaSuccess) { g_ks_dev = nullptr; return; }
+  cudaMemset(g_ks_dev, 0, (1 + 8 * 4000) * sizeof(unsigned long long));
   kstamp_set_conv(g_ks_dev);
   kstamp_set_elem(g_ks_dev);
   kstamp_set_ds(g_ks_dev);
@@ -1802,7 +1802,7 @@ static int kstamp_dump(char* buf, size_t cap) {
   Timeline& t = g_timeline;
   if (g_ks_dev == nullptr || t.n == 0) return 0;
   if (cudaDeviceSynchronize() != cudaSuccess) return -1;
-  std::vector<unsigned long long> h(1 + 4 * 4000);
+  std::vector<unsigned long long> h(1 + 8 * 4000);
   if (cudaMemcpy(h.data(), g_ks_dev, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
   const long long total = static_cast<long long>(h[0]);
   size_t off = 0;
@@ -1811,13 +1811,21 @@ static int kstamp_dump(char* buf, size_t cap) {
   if (total < t.n) return static_cast<int>(off);
   for (int i = 0; i < t.n; ++i) {
     const long long r = (total - t.n + i) % 4000, rn = (total - t.n + i + 1) % 4000;
-    const unsigned long long t0 = h[1 + 4 * r], t1 = h[2 + 4 * r], te = h[3 + 4 * r], gb = h[4 + 4 * r];
-    const unsigned long long t1n = (i + 1 < t.n) ? h[2 + 4 * rn] : t1;
+    const unsigned long long t0 = h[1 + 8 * r], t1 = h[2 + 8 * r], te = h[3 + 8 * r], gb = h[4 + 8 * r];
+    const unsigned long long t1n = (i + 1 < t.n) ? h[2 + 8 * rn] : t1;
     const char* name = "?";
     cudaFuncGetName(&name, t.fn[i]);
-    w = snprintf(buf + off, cap - off, "%d\t%.2f\t%.2f\t%.2f\t%u/%u\t%u\t%s\n", i, (double)(t1 - t0) * 1e-3,
+    char marks[96] = "";
+    {
+      int mo = 0;
+      for (int m = 0; m < 4; ++m) {
+        const unsigned long long tm = h[5 + 8 * r + m];
+        if (tm > t1) mo += snprintf(marks + mo, sizeof(marks) - mo, " m%d=%.2f", m, (double)(tm - t1) * 1e-3);
+      }
+    }
+    w = snprintf(buf + off, cap - off, "%d\t%.2f\t%.2f\t%.2f\t%u/%u\t%u\t%s%s\n", i, (double)(t1 - t0) * 1e-3,
                  (double)(t1n - t1) * 1e-3, te > t1 ? (double)(te - t1) * 1e-3 : 0.0, (unsigned)(gb >> 32),
-                 (unsigned)(gb & 0xffffffffu), t.grid[i], name);
+                 (unsigned)(gb & 0xffffffffu), t.grid[i], name, marks);
     if (w < 0 || static_cast<size_t>(w) >= cap - off) break;
     off += w;
   }

@@ -54,9 +54,11 @@ for scales in scales_list:
         for l in buf.value.decode().splitlines():
             if l.startswith('#'):
                 print(l); continue
-            i, lead, tot, body, gb, g, name = l.split('\t')
+            i, lead, tot, body, gb, g, name = l.split('\t')[:7]
+            marks = name[name.index(' m'):] if ' m' in name else ''
+            name = name.split(' ')[0]
             print(f'{int(i):4d} {float(lead):6.2f} {float(tot):6.2f} {float(body):6.2f} {gb:>9s}  ' +
-                  re.sub(r'\(.*', '', name).replace('void ', '').replace('dsr::', '')[:60])
+                  re.sub(r'\(.*', '', name).replace('void ', '').replace('dsr::', '')[:60] + marks)
     if os.environ.get('DSR_TIMELINE') == '1':
         buf = C.create_string_buffer(1 << 20)
         nbytes = lib.dsr_timeline_dump(buf, 1 << 20)
