@@ -683,6 +683,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHalo2Threads, 1)
     // ===================== MMA issuer (CTA 0 only; warp-uniform loop, one elected lane issues) =====================
     if (rank == 0) {
       mbar_wait(bres_bar, 0, p.err, 33);
+      if (lane == 0) ks_mark_here(0);
       int ws = 0, ns = 0, it = 0;
       uint32_t wph = 0, nph = 0;
       const uint32_t bw_addr = smem_u32(bres_w), bn_addr = smem_u32(bres_n);
@@ -708,6 +709,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHalo2Threads, 1)
         uint32_t accum = 0;
         for (int c = 0; c < p.n_wide; ++c) {
           mbar_wait(&wfull[ws], wph, p.err, 35);
+          if (lane == 0 && it == 0 && c == 0) ks_mark_here(1);
           tc_fence_after();
           const uint32_t a_lo = aw_lo0 | ((smem_u32(a_wide + ws * slot_bytes) & 0x3FFFF) >> 4);
           const uint32_t b_lo = bw_lo0 | (((bw_addr + static_cast<uint32_t>(c * wb)) & 0x3FFFF) >> 4);
@@ -806,6 +808,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHalo2Threads, 1)
           }
       }
       mbar_wait(&tfull[as], aph, p.err, 37);
+      if (warp == 2 && lane == 0 && it == 0) ks_mark_here(2);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(as * 256);
       if (EP == 1) {
@@ -884,6 +887,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHalo2Threads, 1)
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) ks_mark_here(3);
   cluster_sync_all();                     // the peer may still be reading our shared memory / signalling our barriers
   prof_end(p.prof);
   ks_end();

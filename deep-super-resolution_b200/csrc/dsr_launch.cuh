@@ -76,6 +76,15 @@ __device__ __forceinline__ void ks_mark(int m) {
   (void)m;
 #endif
 }
+// the same from any ONE thread of block 0 chosen by the caller (warp-specialised kernels)
+__device__ __forceinline__ void ks_mark_here(int m) {
+#ifdef DSR_KSTAMP
+  if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && g_ks_buf != nullptr && g_ks_slot < 4000)
+    g_ks_buf[5 + 8 * g_ks_slot + m] = ks_now();
+#else
+  (void)m;
+#endif
+}
 #ifdef DSR_KSTAMP
 #define DSR_KSTAMP_SETTER(name) \
   void name(unsigned long long* buf) { cudaMemcpyToSymbol(g_ks_buf, &buf, sizeof(buf)); }
