@@ -86,6 +86,27 @@ SIGNATURES = {
     'dsr_psnr': (i32, [vp, vp, i64, f32, vp, vp, vp]),
     'dsr_ssim': (i32, [vp, vp, i32, i32, i32, f32, vp, vp, vp]),
     'dsr_plan_deterministic': (i32, [vp]),
+    'dsr_gant_create': (i32, [C.POINTER(vp), i32, i32, i32, i32, i32, i32]),
+    'dsr_gant_destroy': (None, [vp]),
+    'dsr_gant_param_numel': (i64, [vp, i32]),
+    'dsr_gant_buffer_numel': (i64, [vp, i32]),
+    'dsr_gant_num_params': (i32, [vp, i32]),
+    'dsr_gant_num_buffers': (i32, [vp, i32]),
+    'dsr_gant_param_info': (i32, [vp, i32, i32, C.c_char_p, i32, C.POINTER(i64), C.POINTER(i64)]),
+    'dsr_gant_buffer_info': (i32, [vp, i32, i32, C.c_char_p, i32, C.POINTER(i64), C.POINTER(i64)]),
+    'dsr_gant_workspace_bytes': (sz, [vp]),
+    'dsr_gant_bind': (i32, [vp, vp, sz, vp]),
+    'dsr_gant_pack': (i32, [vp, i32, vp, vp]),
+    'dsr_gant_g_forward': (i32, [vp, vp, vp, vp, vp, i32, vp]),
+    'dsr_gant_g_backward': (i32, [vp, vp, vp, vp, vp]),
+    'dsr_gant_d_forward': (i32, [vp, i32, vp, vp, vp, vp, vp]),
+    'dsr_gant_d_backward': (i32, [vp, i32, vp, vp, f32, vp, vp]),
+    'dsr_gant_bce': (i32, [vp, vp, f32, i32, vp, i32, vp]),
+    'dsr_gant_vgg_loss': (i32, [vp, vp, vp, vp, i32, vp, vp]),
+    'dsr_gant_device_error': (i32, [vp, C.POINTER(i32)]),
+    'dsr_gant_last_launches': (i32, [vp]),
+    'dsr_gant_tensor': (i32, [vp, C.c_char_p, C.POINTER(vp), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32),
+                             C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

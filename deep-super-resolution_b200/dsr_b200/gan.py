@@ -6,8 +6,9 @@ shapes, construction order, hence ``state_dict()`` keys and same-seed initialisa
 sub-modules are parameter containers only -- ``forward`` is one call into libdsr_b200.so (``dsr_gen_forward``: tcgen05
 convolutions with eval-mode BatchNorm folded in, PReLU / residual adds / PixelShuffle fused into the conv epilogues).
 
-Inference only: calling the module in training mode raises (train-mode BatchNorm statistics and the backward pass of
-train_GAN.py are not built), CPU tensors raise, there is no eager fallback.
+In ``.train()`` mode (train_GAN.py) ``forward`` is the training pass of dsr_b200/gan_train.py: batch-statistics
+BatchNorm, activations kept for ``backward()`` (``dsr_gant_g_forward`` / ``dsr_gant_g_backward``).  CPU tensors raise,
+there is no eager fallback.
 """
 from __future__ import annotations
 
@@ -98,6 +99,21 @@ class Generator(nn.Module):
         self.conv3 = nn.Conv2d(64, 3, 9, 1, 4)
         self.out = nn.Tanh()
         self._plans: Dict[Tuple[int, int, int, int], _GenPlan] = {}
+        from .gan_train import FlatParams, NET_G
+        self._fp = FlatParams(self, NET_G)
+
+    # ---- training mode (train_GAN.py) ----------------------------------------------------------
+    def _train_state(self, lr: torch.Tensor):
+        from .gan_train import get_trainer
+        B, _, h, w = lr.shape
+        tr = get_trainer(B, h * self.factor, w * self.factor, lr.device, self.factor, self.blocks)
+        self._fp.ensure(tr, lr.device)
+        return tr, self._fp
+
+    def zero_grad(self, set_to_none: bool = True) -> None:
+        self._fp.invalidate()
+        for p in self.parameters():
+            p.grad = None
 
     # ------------------------------------------------------------------------------------------
     def _state_key(self):
@@ -127,9 +143,13 @@ class Generator(nn.Module):
         return plan
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        if self.training:
-            raise NotImplementedError('dsr_b200.Generator is the inference path (eval_GAN.py): call .eval() first; '
-                                      'training-mode BatchNorm / backward (train_GAN.py) is not built')
+        if not x.is_cuda:
+            raise RuntimeError('dsr_b200.Generator needs a CUDA tensor (sm_100a); there is no CPU fallback')
+        if self.training:                  # train_GAN.py: batch-statistics BatchNorm + backward (dsr_gant_*)
+            if x.dim() != 4 or x.shape[1] != 3:
+                raise ValueError('expected [B, 3, h, w]')
+            from .gan_train import generator_train_forward
+            return generator_train_forward(self, x)
         if not x.is_cuda:
             raise RuntimeError('dsr_b200.Generator needs a CUDA tensor (sm_100a); there is no CPU fallback')
         if x.dim() != 4 or x.shape[1] != 3:

@@ -1,0 +1,514 @@
+"""SRGAN training step: the call surface of train_GAN.py / utils/GAN.py / models/GAN/discriminator.py of the reference
+over libdsr_b200.so (``dsr_gant_*``: bf16 tcgen05 convolutions, hand-written element-wise kernels, no cuDNN, no eager
+fallback).
+
+Two ways in, both backed by the same C entry points:
+
+* drop-in modules -- ``Discriminator(HR_image_shape)`` (discriminator.py:21), ``Generator(factor)`` in ``.train()``
+  mode (generator.py:44), ``Vgg19Loss`` / ``PerceptualLoss`` / ``get_loss_D`` / ``get_adversarial_loss``
+  (utils/GAN.py:6-123).  Their ``forward`` is a ``torch.autograd.Function`` around one library call, their parameters
+  are views of one flat fp32 buffer per network, so the reference's own ``do_epoch`` (train_GAN.py:38-71) with its
+  ``loss.backward()`` / ``torch.optim.Adam`` runs over them unchanged;
+* ``GanTrainStep.do_epoch(LR, HR)`` -- the same step as one fused sequence (one generator forward instead of two
+  identical ones, BCE fused into the discriminator backward, fused flat Adam) and, under ``torch.distributed``, the
+  data-parallel version: per-replica BatchNorm statistics, NCCL all-reduce (mean) of the flat discriminator gradient
+  (80 M floats) overlapped with the generator phase, then of the generator gradient.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import weakref
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import lib, check
+
+NET_G, NET_D, NET_VGG = 0, 1, 2
+_VGG_CONV_IDX = (0, 2, 5, 7, 10, 12, 14, 16, 19, 21, 23, 25, 28, 30, 32, 34)
+
+
+# =================================================================================================
+# trainer object (one per batch / patch size / device): workspace + C handle
+# =================================================================================================
+class Trainer:
+    def __init__(self, batch: int, lr_h: int, lr_w: int, factor: int, blocks: int, device: torch.device,
+                 with_vgg: bool = True):
+        _lib.require_cuda()
+        self.key = (batch, lr_h, lr_w, factor, blocks)
+        self.B, self.lr_h, self.lr_w, self.factor, self.blocks = batch, lr_h, lr_w, factor, blocks
+        self.H, self.W = lr_h * factor, lr_w * factor
+        self.device = device
+        self.handle = C.c_void_p()
+        check(lib.dsr_gant_create(C.byref(self.handle), batch, lr_h, lr_w, factor, blocks, int(with_vgg)), 'dsr_gant_create')
+        nbytes = lib.dsr_gant_workspace_bytes(self.handle)
+        with torch.cuda.device(device):
+            self.workspace = torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
+            base = (self.workspace.data_ptr() + 1023) // 1024 * 1024
+            check(lib.dsr_gant_bind(self.handle, base, nbytes, _lib.stream_ptr()), 'dsr_gant_bind')
+        self.d_slot = 0
+        self.d_gen = [0, 0]          # generation counter per discriminator activation slot
+        self.g_gen = 0
+        self._packed: Dict[int, Tuple[int, int]] = {}
+
+    def layout(self, net: int):
+        name = C.create_string_buffer(160)
+        off, n = C.c_longlong(), C.c_longlong()
+        params, bufs = [], []
+        for i in range(lib.dsr_gant_num_params(self.handle, net)):
+            check(lib.dsr_gant_param_info(self.handle, net, i, name, 160, C.byref(off), C.byref(n)))
+            params.append((name.value.decode(), off.value, n.value))
+        for i in range(lib.dsr_gant_num_buffers(self.handle, net)):
+            check(lib.dsr_gant_buffer_info(self.handle, net, i, name, 160, C.byref(off), C.byref(n)))
+            bufs.append((name.value.decode(), off.value, n.value))
+        return dict(params=params, buffers=bufs, nparam=lib.dsr_gant_param_numel(self.handle, net),
+                    nbuf=lib.dsr_gant_buffer_numel(self.handle, net))
+
+    # ---- thin wrappers -------------------------------------------------------------------------
+    def pack(self, net: int, flat: torch.Tensor, force: bool = False) -> None:
+        key = (flat.data_ptr(), flat._version)
+        if not force and self._packed.get(net) == key:
+            return
+        check(lib.dsr_gant_pack(self.handle, net, flat.data_ptr(), _lib.stream_ptr()), 'dsr_gant_pack')
+        self._packed[net] = key
+
+    def g_forward(self, params, buffers, lr, bn_updates: int = 1) -> torch.Tensor:
+        out = torch.empty((self.B, 3, self.H, self.W), dtype=torch.float32, device=lr.device)
+        check(lib.dsr_gant_g_forward(self.handle, params.data_ptr(), buffers.data_ptr() if buffers is not None else None,
+                                     lr.data_ptr(), out.data_ptr(), bn_updates, _lib.stream_ptr()), 'dsr_gant_g_forward')
+        self.g_gen += 1
+        return out
+
+    def g_backward(self, params, dout, grads) -> None:
+        check(lib.dsr_gant_g_backward(self.handle, params.data_ptr(), dout.data_ptr(), grads.data_ptr(), _lib.stream_ptr()),
+              'dsr_gant_g_backward')
+
+    def d_forward(self, slot: int, params, buffers, img) -> torch.Tensor:
+        prob = torch.empty((self.B,), dtype=torch.float32, device=img.device)
+        check(lib.dsr_gant_d_forward(self.handle, slot, params.data_ptr(),
+                                     buffers.data_ptr() if buffers is not None else None, img.data_ptr(), prob.data_ptr(),
+                                     _lib.stream_ptr()), 'dsr_gant_d_forward')
+        self.d_gen[slot] += 1
+        return prob
+
+    def d_backward(self, slot: int, params, grads, dprob: Optional[torch.Tensor] = None, target: float = 0.0) -> None:
+        check(lib.dsr_gant_d_backward(self.handle, slot, params.data_ptr(), dprob.data_ptr() if dprob is not None else None,
+                                      float(target), grads.data_ptr(), _lib.stream_ptr()), 'dsr_gant_d_backward')
+
+    def bce(self, prob, target: float, loss, accumulate: bool) -> None:
+        check(lib.dsr_gant_bce(self.handle, prob.data_ptr(), float(target), prob.numel(), loss.data_ptr(), int(accumulate),
+                               _lib.stream_ptr()), 'dsr_gant_bce')
+
+    def vgg_loss(self, fake, real, loss, accumulate: bool, want_grad: bool) -> Optional[torch.Tensor]:
+        dfake = torch.empty_like(fake) if want_grad else None
+        check(lib.dsr_gant_vgg_loss(self.handle, fake.data_ptr(), real.data_ptr(), loss.data_ptr(), int(accumulate),
+                                    dfake.data_ptr() if want_grad else None, _lib.stream_ptr()), 'dsr_gant_vgg_loss')
+        return dfake
+
+    def device_error(self) -> int:
+        code = C.c_int()
+        check(lib.dsr_gant_device_error(self.handle, C.byref(code)))
+        return code.value
+
+    def tensor(self, name: str) -> torch.Tensor:
+        """Named activation of the last pass as [B, H, W, C] float32 (tests)."""
+        ptr = C.c_void_p()
+        cc, w, h, p, b, f32 = (C.c_int() for _ in range(6))
+        check(lib.dsr_gant_tensor(self.handle, name.encode(), C.byref(ptr), C.byref(cc), C.byref(w), C.byref(h), C.byref(p),
+                                  C.byref(b), C.byref(f32)), f'dsr_gant_tensor({name})')
+        dt = torch.float32 if f32.value else torch.bfloat16
+        t = torch.empty((b.value * p.value, w.value, cc.value), dtype=dt, device=self.device)
+        check(lib.dsr_debug_copy(t.data_ptr(), ptr, t.numel() * t.element_size(), _lib.stream_ptr()), 'dsr_debug_copy')
+        return t.view(b.value, p.value, w.value, cc.value)[:, :h.value].float()
+
+    def __del__(self):
+        try:
+            if self.handle:
+                lib.dsr_gant_destroy(self.handle)
+        except Exception:
+            pass
+
+
+_TRAINERS: Dict[Tuple, Trainer] = {}
+
+
+def get_trainer(batch: int, H: int, W: int, device: torch.device, factor: Optional[int] = None, blocks: int = 16) -> Trainer:
+    """The trainer whose HR patch size is (H, W); the generator states its factor, the discriminator / VGG side take
+    whichever trainer of that HR size exists (or a factor-8 one)."""
+    dev = device.index if device.index is not None else torch.cuda.current_device()
+    for (b, h, w, d, f, k), t in _TRAINERS.items():
+        if (b, h, w, d) == (batch, H, W, dev) and (factor is None or (f == factor and k == blocks)):
+            return t
+    f = factor or 8
+    if H % f or W % f:
+        raise ValueError(f'patch size {H} x {W} is no multiple of the factor {f}')
+    t = Trainer(batch, H // f, W // f, f, blocks, torch.device('cuda', dev))
+    _TRAINERS[(batch, H, W, dev, f, blocks)] = t
+    return t
+
+
+# =================================================================================================
+# flat parameter storage shared by the drop-in modules
+# =================================================================================================
+class FlatParams:
+    """Re-points a module's parameters (and BatchNorm running statistics) at views of flat fp32 device buffers laid out
+    as the library expects; gradients are views of a second flat buffer."""
+
+    def __init__(self, module: nn.Module, net: int, key_prefix: str = ''):
+        self.module = weakref.ref(module)
+        self.net = net
+        self.flat = self.gflat = self.bflat = None
+        self.grad_views: List[torch.Tensor] = []
+        self.grads_valid = False
+        self.layout = None
+
+    def ensure(self, trainer: Trainer, device: torch.device) -> None:
+        m = self.module()
+        named = list(m.named_parameters())
+        if self.flat is not None and self.flat.device == device and named[0][1].data_ptr() == self.flat.data_ptr():
+            return
+        lay = trainer.layout(self.net)
+        if [n for n, _ in named] != [n for n, _, _ in lay['params']]:
+            raise RuntimeError('dsr_b200: parameter order of the module and of the library disagree')
+        flat = torch.empty(lay['nparam'], dtype=torch.float32, device=device)
+        gflat = torch.zeros(lay['nparam'], dtype=torch.float32, device=device)
+        views = []
+        with torch.no_grad():
+            for (name, p), (_, off, n) in zip(named, lay['params']):
+                if p.numel() != n:
+                    raise RuntimeError(f'dsr_b200: {name} has {p.numel()} elements, the library expects {n}')
+                v = flat[off:off + n].view(p.shape)
+                v.copy_(p.data)
+                p.data = v
+                p.grad = None
+                views.append(gflat[off:off + n].view(p.shape))
+            bflat = torch.empty(max(lay['nbuf'], 1), dtype=torch.float32, device=device)
+            bufs = dict(m.named_buffers())
+            for name, off, n in lay['buffers']:
+                v = bflat[off:off + n]
+                v.copy_(bufs[name])
+                mod_name, _, leaf = name.rpartition('.')
+                setattr(m.get_submodule(mod_name), leaf, v)
+        self.flat, self.gflat, self.bflat, self.grad_views, self.layout = flat, gflat, bflat, views, lay
+        self.grads_valid = False
+
+    def begin_backward(self) -> None:
+        if not self.grads_valid:
+            self.gflat.zero_()
+            self.grads_valid = True
+
+    def publish_grads(self) -> None:
+        for (_, p), v in zip(self.module().named_parameters(), self.grad_views):
+            if p.requires_grad and p.grad is None:
+                p.grad = v
+
+    def invalidate(self) -> None:
+        self.grads_valid = False
+
+
+def _bump_batches_tracked(module: nn.Module, times: int = 1) -> None:
+    for m in module.modules():
+        if isinstance(m, nn.BatchNorm2d) and m.num_batches_tracked is not None:
+            m.num_batches_tracked += times
+
+
+# =================================================================================================
+# Discriminator (models/GAN/discriminator.py)
+# =================================================================================================
+class DiscriminatorConvBlock(nn.Module):
+    """Parameter container with the keys of discriminator.py:4-12 (conv1, bn1)."""
+
+    def __init__(self, in_channels: int, out_channels: int, stride: int):
+        super().__init__()
+        self.conv1 = nn.Conv2d(in_channels, out_channels, 3, stride, 1)
+        self.bn1 = nn.BatchNorm2d(out_channels)
+        self.leakyrelu = nn.LeakyReLU(0.2)
+
+    def forward(self, x):  # pragma: no cover
+        raise RuntimeError('dsr_b200: blocks are parameter containers; call the Discriminator')
+
+
+class _DiscFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img, anchor, module):
+        tr, fp = module._trainer_for(img)
+        slot = tr.d_slot
+        tr.d_slot ^= 1
+        tr.pack(NET_D, fp.flat, force=True)
+        prob = tr.d_forward(slot, fp.flat, fp.bflat, img)
+        _bump_batches_tracked(module)
+        ctx.module, ctx.trainer, ctx.slot, ctx.gen = module, tr, slot, tr.d_gen[slot]
+        return prob.view(-1, 1)
+
+    @staticmethod
+    def backward(ctx, dprob):
+        tr, module = ctx.trainer, ctx.module
+        if tr.d_gen[ctx.slot] != ctx.gen:
+            raise RuntimeError('dsr_b200.Discriminator: the activations of this forward pass were overwritten by two later '
+                               'passes before backward() (two passes are kept, as do_epoch needs)')
+        fp = module._fp
+        fp.begin_backward()
+        tr.d_backward(ctx.slot, fp.flat, fp.gflat, dprob=dprob.contiguous().view(-1).float())
+        fp.publish_grads()
+        return None, None, None
+
+
+class Discriminator(nn.Module):
+    """``Discriminator(HR_image_shape)`` of discriminator.py:21-74: same module tree, names, construction order (hence
+    state_dict keys and same-seed initialisation).  Train mode only (train_GAN.py:164 never leaves it)."""
+
+    def __init__(self, HR_image_shape):
+        super().__init__()
+        self.conv = nn.Conv2d(3, 64, 3, 1, 1)
+        self.leakyrelu1 = nn.LeakyReLU(0.2)
+        self.convblocks = nn.Sequential(*[DiscriminatorConvBlock(a, b, s) for a, b, s in
+                                          ((64, 64, 2), (64, 128, 1), (128, 128, 2), (128, 256, 1), (256, 256, 2),
+                                           (256, 512, 1), (512, 512, 2))])
+        self.dense1 = nn.Linear(self.fc_input_shape(HR_image_shape), 1024)
+        self.leakyrelu2 = nn.LeakyReLU(0.2)
+        self.dense2 = nn.Linear(1024, 1)
+        self.sigmoid = nn.Sigmoid()
+        self.hr_shape = (int(HR_image_shape[0]), int(HR_image_shape[1]))
+        self._fp = FlatParams(self, NET_D)
+
+    def fc_input_shape(self, HR_image_shape):
+        """discriminator.py:47-55, construction time only: a batch of ones goes through conv / convblocks in TRAIN mode
+        (so the BatchNorm running statistics take one update before training starts -- kept, it is part of the
+        reference's same-seed initial state) to read off dense1's input width.  Stock torch ops on the CPU, once."""
+        with torch.no_grad():
+            x = torch.ones(1, 3, int(HR_image_shape[0]), int(HR_image_shape[1]))
+            x = self.leakyrelu1(self.conv(x))
+            for blk in self.convblocks:
+                x = blk.leakyrelu(blk.bn1(blk.conv1(x)))
+            return x.view(x.size(0), -1).shape[1]
+
+    def _trainer_for(self, img):
+        B, _, H, W = img.shape
+        tr = get_trainer(B, H, W, img.device)
+        self._fp.ensure(tr, img.device)
+        return tr, self._fp
+
+    def zero_grad(self, set_to_none: bool = True) -> None:
+        self._fp.invalidate()
+        for p in self.parameters():
+            p.grad = None
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if not x.is_cuda:
+            raise RuntimeError('dsr_b200.Discriminator needs a CUDA tensor (sm_100a); there is no CPU fallback')
+        if not self.training:
+            raise NotImplementedError('dsr_b200.Discriminator: eval mode is not built (train_GAN.py keeps it in train mode)')
+        if x.dim() != 4 or x.shape[1] != 3 or tuple(x.shape[2:]) != self.hr_shape:
+            raise ValueError(f'expected [B, 3, {self.hr_shape[0]}, {self.hr_shape[1]}], got {tuple(x.shape)}')
+        if x.requires_grad:
+            raise NotImplementedError('dsr_b200.Discriminator: the gradient w.r.t. the input image is not built -- do_epoch '
+                                      'detaches the generated image in front of the discriminator (train_GAN.py:46,58)')
+        x = x.detach().to(torch.float32).contiguous()
+        return _DiscFn.apply(x, next(self.parameters()), self)
+
+
+# =================================================================================================
+# Generator in train mode (the module itself lives in gan.py; this is its training forward)
+# =================================================================================================
+class _GenTrainFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, lr, anchor, module):
+        tr, fp = module._train_state(lr)
+        tr.pack(NET_G, fp.flat, force=True)
+        out = tr.g_forward(fp.flat, fp.bflat, lr, 1)
+        _bump_batches_tracked(module)
+        ctx.module, ctx.trainer, ctx.gen = module, tr, tr.g_gen
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        tr, module = ctx.trainer, ctx.module
+        if tr.g_gen != ctx.gen:
+            raise RuntimeError('dsr_b200.Generator: a later forward pass overwrote the activations of this one before '
+                               'backward()')
+        fp = module._fp
+        fp.begin_backward()
+        tr.g_backward(fp.flat, dout.contiguous().float(), fp.gflat)
+        fp.publish_grads()
+        return None, None, None
+
+
+def generator_train_forward(module, x: torch.Tensor) -> torch.Tensor:
+    if x.requires_grad:
+        raise NotImplementedError('dsr_b200.Generator: the gradient w.r.t. the LR input is not built')
+    x = x.detach().to(torch.float32).contiguous()
+    return _GenTrainFn.apply(x, module.conv1.weight, module)
+
+
+# =================================================================================================
+# losses (utils/GAN.py)
+# =================================================================================================
+class _VggLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, fake, real, module):
+        tr = module._trainer_for(fake)
+        loss = torch.empty((), dtype=torch.float32, device=fake.device)
+        want = fake.requires_grad
+        dfake = tr.vgg_loss(fake.detach().contiguous().float(), real.detach().contiguous().float(), loss, False, want)
+        ctx.dfake = dfake
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        return (ctx.dfake * g if ctx.dfake is not None else None), None, None
+
+
+class Vgg19Loss(nn.Module):
+    """utils/GAN.py:6-88.  ``self.net`` holds torchvision's ``vgg19().features[:36]`` as a frozen parameter container
+    (keys ``net.0.<idx>.weight``); the forward pass -- transform, 16 convolutions, 4 max-pools, feature MSE and the
+    gradient w.r.t. the first image -- is one library call.  The reference downloads the IMAGENET1K_V1 weights; with no
+    cached copy (no network here) the container keeps torchvision's default random initialisation unless a state dict
+    is loaded into it."""
+
+    def __init__(self, pretrained: bool = True):
+        super().__init__()
+        from torchvision.models import vgg19
+        layers = None
+        if pretrained:
+            try:
+                from torchvision.models import VGG19_Weights
+                layers = vgg19(weights=VGG19_Weights.IMAGENET1K_V1).features
+            except Exception:                           # no cache and no network: random weights
+                layers = None
+        if layers is None:
+            layers = vgg19(weights=None).features
+        self.net = nn.Sequential(layers[:36])
+        self.mse = nn.MSELoss()
+        for p in self.net.parameters():
+            p.requires_grad = False
+        self._flat = None
+
+    def _trainer_for(self, img):
+        B, _, H, W = img.shape
+        tr = get_trainer(B, H, W, img.device)
+        key = tuple((p.data_ptr(), p._version) for p in self.net.parameters())
+        if self._flat is None or self._flat[0] != key or self._flat[1].device != img.device:
+            flat = torch.cat([p.detach().to(device=img.device, dtype=torch.float32).reshape(-1)
+                              for p in self.net.parameters()]).contiguous()
+            assert flat.numel() == lib.dsr_gant_param_numel(tr.handle, NET_VGG)
+            self._flat = (key, flat)
+        tr.pack(NET_VGG, self._flat[1])
+        return tr
+
+    def forward(self, image1, image2):
+        if not image1.is_cuda:
+            raise RuntimeError('dsr_b200.Vgg19Loss needs CUDA tensors (sm_100a); there is no CPU fallback')
+        return _VggLossFn.apply(image1, image2, self)
+
+
+def get_adversarial_loss(fake_output, bce_loss):            # utils/GAN.py:96-98
+    return bce_loss(fake_output, torch.ones_like(fake_output))
+
+
+def get_loss_D(real_output, fake_output, bce_loss):         # utils/GAN.py:101-107
+    real_loss = bce_loss(real_output, torch.ones_like(real_output))
+    fake_loss = bce_loss(fake_output, torch.zeros_like(fake_output))
+    return real_loss + fake_loss
+
+
+class PerceptualLoss(nn.Module):                            # utils/GAN.py:110-123
+    def __init__(self, pretrained: bool = True):
+        super().__init__()
+        self.vgg_loss = Vgg19Loss(pretrained)
+
+    def forward(self, fake_output_G, HR_images, fake_output_D, bce_loss):
+        content_loss = self.vgg_loss(fake_output_G, HR_images)
+        adversarial_loss_ = get_adversarial_loss(fake_output_D, bce_loss)
+        return content_loss + adversarial_loss_
+
+
+# =================================================================================================
+# fused / data-parallel step
+# =================================================================================================
+class GanTrainStep:
+    """``do_epoch`` of train_GAN.py:38-71 as one fused sequence over flat buffers, optionally data-parallel.
+
+    ``gan_G`` / ``gan_D`` are the drop-in modules (their parameters become views of the flat buffers this object
+    updates), ``vgg`` a ``Vgg19Loss``.  With an initialised ``torch.distributed`` process group (``data_parallel=True``)
+    every rank holds a replica, rank 0's initial parameters are broadcast, each rank processes its own batch shard with
+    per-replica BatchNorm statistics (what DistributedDataParallel does), and the flat gradients are averaged with NCCL
+    all-reduce: the discriminator's 321 MB on a side stream while the generator phase (VGG + generator backward) runs,
+    the generator's 6 MB after it."""
+
+    def __init__(self, gan_G, gan_D, vgg: Vgg19Loss, lr: float, batch: int, lr_hw: Tuple[int, int], device,
+                 data_parallel: bool = False):
+        device = torch.device(device)
+        self.G, self.D, self.vgg, self.lr = gan_G, gan_D, vgg, float(lr)
+        self.tr = get_trainer(batch, lr_hw[0] * gan_G.factor, lr_hw[1] * gan_G.factor, device, gan_G.factor, gan_G.blocks)
+        with torch.cuda.device(device):
+            gan_G.to(device); gan_D.to(device)
+            gan_G._fp.ensure(self.tr, device)
+            gan_D._fp.ensure(self.tr, device)
+            self.fg, self.fd = gan_G._fp, gan_D._fp
+            self.mG, self.vG = torch.zeros_like(self.fg.flat), torch.zeros_like(self.fg.flat)
+            self.mD, self.vD = torch.zeros_like(self.fd.flat), torch.zeros_like(self.fd.flat)
+            self.loss_D = torch.zeros((), device=device)
+            self.loss_G = torch.zeros((), device=device)
+            self.comm_stream = torch.cuda.Stream(device=device)
+        self.t = 0
+        self.dp = bool(data_parallel)
+        self.world = 1
+        self.allreduce_bytes = 0
+        if self.dp:
+            import torch.distributed as dist
+            self.dist = dist
+            self.world = dist.get_world_size()
+            for f in (self.fg, self.fd):
+                dist.broadcast(f.flat, 0)
+                dist.broadcast(f.bflat, 0)
+        self.device = device
+
+    def _adam(self, p, g, m, v) -> None:
+        check(lib.dsr_adam_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), self.lr, 0.9, 0.999,
+                                1e-8, self.t, _lib.stream_ptr()), 'dsr_adam_step')
+
+    def do_epoch(self, LR_patches: torch.Tensor, HR_patches: torch.Tensor):
+        tr, fg, fd = self.tr, self.fg, self.fd
+        LR = LR_patches.to(self.device, non_blocking=True).float().contiguous()
+        HR = HR_patches.to(self.device, non_blocking=True).float().contiguous()
+        self.t += 1
+        cur = torch.cuda.current_stream(self.device)
+        # ---- discriminator step (train_GAN.py:43-53)
+        tr.pack(NET_D, fd.flat, force=True)
+        tr.pack(NET_G, fg.flat, force=True)
+        p_real = tr.d_forward(0, fd.flat, fd.bflat, HR)
+        fake = tr.g_forward(fg.flat, fg.bflat, LR, bn_updates=2)        # the two generator passes of do_epoch are identical
+        p_fake = tr.d_forward(1, fd.flat, fd.bflat, fake)
+        tr.bce(p_real, 1.0, self.loss_D, False)
+        tr.bce(p_fake, 0.0, self.loss_D, True)
+        fd.gflat.zero_()
+        tr.d_backward(0, fd.flat, fd.gflat, target=1.0)
+        tr.d_backward(1, fd.flat, fd.gflat, target=0.0)
+        work = None
+        if self.dp:
+            self.comm_stream.wait_stream(cur)
+            with torch.cuda.stream(self.comm_stream):
+                work = self.dist.all_reduce(fd.gflat, async_op=True)
+            self.allreduce_bytes = fd.gflat.numel() * 4 + fg.gflat.numel() * 4
+        # ---- generator phase, independent of the discriminator: content loss and generator backward (:56-66)
+        dfake = tr.vgg_loss(fake, HR, self.loss_G, False, True)
+        fg.gflat.zero_()
+        tr.g_backward(fg.flat, dfake, fg.gflat)
+        # ---- discriminator update, then its pass on the generated batch for the adversarial term of loss_G (:58-59)
+        if work is not None:
+            work.wait()
+            cur.wait_stream(self.comm_stream)
+            fd.gflat.mul_(1.0 / self.world)
+        self._adam(fd.flat, fd.gflat, self.mD, self.vD)
+        tr.pack(NET_D, fd.flat, force=True)
+        p_fake2 = tr.d_forward(0, fd.flat, fd.bflat, fake)
+        tr.bce(p_fake2, 1.0, self.loss_G, True)
+        if self.dp:
+            self.dist.all_reduce(fg.gflat)
+            fg.gflat.mul_(1.0 / self.world)
+        self._adam(fg.flat, fg.gflat, self.mG, self.vG)
+        _bump_batches_tracked(self.G, 2)
+        _bump_batches_tracked(self.D, 3)
+        return self.loss_D, self.loss_G

@@ -207,6 +207,50 @@ int dsr_ssim(const float* pred, const float* target, int planes, int H, int W, f
 /* 1 when the plan was created with DSR_DETERMINISTIC=1 (two-stage split-K weight gradients: bit-identical runs). */
 int dsr_plan_deterministic(const dsr_plan_t* p);
 
+/* ---- SRGAN training step (train_GAN.py:38-71, do_epoch) ---------------------------------------------------
+ * Replaces, for one batch of B <= 8 patches: Generator (models/GAN/generator.py:44-81) in TRAIN mode with its backward
+ * pass, Discriminator (models/GAN/discriminator.py:21-74) forward / backward, nn.BCELoss against constant targets
+ * (utils/GAN.py:96-107) and the VGG19 content loss behind the IMAGENET1K_V1 transform (utils/GAN.py:62-88) with its
+ * gradient w.r.t. the generated image.  bf16 tensor-core convolutions (gconv_kernel / gwgrad_kernel), fp32 master
+ * parameters.  net: 0 generator, 1 discriminator, 2 VGG19 features[:36].  Parameters / gradients of a net are ONE flat
+ * fp32 array in named_parameters() order (param_info gives name, offset, numel); BatchNorm running statistics are a
+ * second flat array (buffer_info; num_batches_tracked is the caller's).  Gradients are ACCUMULATED (+=) into `grads`.
+ * The optimiser is dsr_adam_step on the flat arrays; data-parallel training all-reduces the flat gradient arrays. */
+typedef struct dsr_gant dsr_gant_t;
+int dsr_gant_create(dsr_gant_t** out, int batch, int lr_h, int lr_w, int factor, int residual_blocks, int with_vgg);
+void dsr_gant_destroy(dsr_gant_t* p);
+long long dsr_gant_param_numel(const dsr_gant_t* p, int net);
+long long dsr_gant_buffer_numel(const dsr_gant_t* p, int net);
+int dsr_gant_num_params(const dsr_gant_t* p, int net);
+int dsr_gant_num_buffers(const dsr_gant_t* p, int net);
+int dsr_gant_param_info(const dsr_gant_t* p, int net, int idx, char* name, int name_cap, long long* offset, long long* numel);
+int dsr_gant_buffer_info(const dsr_gant_t* p, int net, int idx, char* name, int name_cap, long long* offset, long long* numel);
+size_t dsr_gant_workspace_bytes(const dsr_gant_t* p);
+/* Binds (and zero-fills) the caller-owned workspace (1024-byte aligned). */
+int dsr_gant_bind(dsr_gant_t* p, void* workspace, size_t bytes, void* stream);
+/* bf16 GEMM layouts of one net's convolution weights from its flat parameters; call after every parameter update. */
+int dsr_gant_pack(dsr_gant_t* p, int net, const float* params, void* stream);
+/* out = Generator(lr) in train mode.  lr [B][3][h][w], out [B][3][f h][f w] fp32 NCHW.  buffers (may be NULL): running
+ * statistics, updated bn_updates times with this batch (do_epoch runs the generator twice on identical inputs). */
+int dsr_gant_g_forward(dsr_gant_t* p, const float* params, float* buffers, const float* lr_nchw, float* out_nchw,
+                       int bn_updates, void* stream);
+int dsr_gant_g_backward(dsr_gant_t* p, const float* params, const float* dout_nchw, float* grads, void* stream);
+/* prob[B] = Discriminator(img); slot 0 / 1 = which activation set keeps the pass for dsr_gant_d_backward. */
+int dsr_gant_d_forward(dsr_gant_t* p, int slot, const float* params, float* buffers, const float* img_nchw, float* prob,
+                       void* stream);
+/* dprob [B] = d(loss)/d(prob), or NULL: BCE(prob, target) with mean reduction fused in. */
+int dsr_gant_d_backward(dsr_gant_t* p, int slot, const float* params, const float* dprob, float target, float* grads,
+                        void* stream);
+/* loss[0] (= | +=) nn.BCELoss()(prob[0..n), target) */
+int dsr_gant_bce(dsr_gant_t* p, const float* prob, float target, int n, float* loss, int accumulate, void* stream);
+/* loss[0] (= | +=) MSE(VGG(T(fake)), VGG(T(real))); dfake (may be NULL) = its gradient w.r.t. fake. */
+int dsr_gant_vgg_loss(dsr_gant_t* p, const float* fake_nchw, const float* real_nchw, float* loss, int accumulate,
+                      float* dfake_nchw, void* stream);
+int dsr_gant_device_error(dsr_gant_t* p, int* host_code);
+int dsr_gant_last_launches(const dsr_gant_t* p);
+/* Tests: a named activation of the last pass (bf16 / fp32 [B * P][W][C] tall grid, image b at rows [b P, b P + H)). */
+int dsr_gant_tensor(const dsr_gant_t* p, const char* name, void** ptr, int* C, int* W, int* H, int* P, int* B, int* f32);
+
 #ifdef __cplusplus
 }
 #endif
