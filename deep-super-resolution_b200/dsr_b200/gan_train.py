@@ -371,7 +371,8 @@ class Vgg19Loss(nn.Module):
         super().__init__()
         from torchvision.models import vgg19
         layers = None
-        if pretrained:
+        import os
+        if pretrained and not os.environ.get('DSR_VGG_RANDOM'):
             try:
                 from torchvision.models import VGG19_Weights
                 layers = vgg19(weights=VGG19_Weights.IMAGENET1K_V1).features
@@ -385,16 +386,21 @@ class Vgg19Loss(nn.Module):
             p.requires_grad = False
         self._flat = None
 
-    def _trainer_for(self, img):
-        B, _, H, W = img.shape
-        tr = get_trainer(B, H, W, img.device)
+    def pack_into(self, tr: Trainer, device) -> None:
+        """Flat fp32 copy of the (frozen) weights in library order, packed into the trainer's GEMM layouts; redone only
+        when a weight tensor changed (load_state_dict)."""
         key = tuple((p.data_ptr(), p._version) for p in self.net.parameters())
-        if self._flat is None or self._flat[0] != key or self._flat[1].device != img.device:
-            flat = torch.cat([p.detach().to(device=img.device, dtype=torch.float32).reshape(-1)
+        if self._flat is None or self._flat[0] != key or self._flat[1].device != torch.device(device):
+            flat = torch.cat([p.detach().to(device=device, dtype=torch.float32).reshape(-1)
                               for p in self.net.parameters()]).contiguous()
             assert flat.numel() == lib.dsr_gant_param_numel(tr.handle, NET_VGG)
             self._flat = (key, flat)
         tr.pack(NET_VGG, self._flat[1])
+
+    def _trainer_for(self, img):
+        B, _, H, W = img.shape
+        tr = get_trainer(B, H, W, img.device)
+        self.pack_into(tr, img.device)
         return tr
 
     def forward(self, image1, image2):
@@ -425,6 +431,48 @@ class PerceptualLoss(nn.Module):                            # utils/GAN.py:110-1
 
 
 # =================================================================================================
+# data-parallel gradient exchange (the one collective of the repository's data paths)
+# =================================================================================================
+class GradExchange:
+    """Mean all-reduce of flat gradient buffers over the default process group (NCCL over NVLink / NVSwitch on a GPU
+    box, gloo in the CPU tests) and the initial broadcast of rank 0's state.  ``start`` enqueues the collective -- for
+    CUDA tensors on a side stream that first waits for the producer stream, so that it overlaps whatever the caller
+    launches next; ``finish`` makes the caller's stream wait for it and divides by the world size (DDP's averaging)."""
+
+    def __init__(self, device=None):
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            raise RuntimeError('GradExchange needs an initialised torch.distributed process group')
+        self.dist = dist
+        self.world = dist.get_world_size()
+        self.rank = dist.get_rank()
+        self.device = torch.device(device) if device is not None else None
+        self.stream = torch.cuda.Stream(device=self.device) if (self.device is not None and self.device.type == 'cuda') else None
+        self.bytes = 0
+
+    def broadcast(self, *tensors: torch.Tensor, src: int = 0) -> None:
+        for t in tensors:
+            self.dist.broadcast(t, src)
+
+    def start(self, flat: torch.Tensor):
+        self.bytes += flat.numel() * flat.element_size()
+        if self.stream is not None:
+            self.stream.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(self.stream):
+                return self.dist.all_reduce(flat, async_op=True)
+        return self.dist.all_reduce(flat, async_op=True)
+
+    def finish(self, work, flat: torch.Tensor) -> None:
+        work.wait()
+        if self.stream is not None:
+            torch.cuda.current_stream(self.device).wait_stream(self.stream)
+        flat.mul_(1.0 / self.world)
+
+    def allreduce_mean(self, flat: torch.Tensor) -> None:
+        self.finish(self.start(flat), flat)
+
+
+# =================================================================================================
 # fused / data-parallel step
 # =================================================================================================
 class GanTrainStep:
@@ -451,19 +499,25 @@ class GanTrainStep:
             self.mD, self.vD = torch.zeros_like(self.fd.flat), torch.zeros_like(self.fd.flat)
             self.loss_D = torch.zeros((), device=device)
             self.loss_G = torch.zeros((), device=device)
-            self.comm_stream = torch.cuda.Stream(device=device)
         self.t = 0
         self.dp = bool(data_parallel)
         self.world = 1
-        self.allreduce_bytes = 0
+        self.xch = None
         if self.dp:
-            import torch.distributed as dist
-            self.dist = dist
-            self.world = dist.get_world_size()
-            for f in (self.fg, self.fd):
-                dist.broadcast(f.flat, 0)
-                dist.broadcast(f.bflat, 0)
+            self.xch = GradExchange(device)
+            self.world = self.xch.world
+            self.xch.broadcast(self.fg.flat, self.fg.bflat, self.fd.flat, self.fd.bflat)
         self.device = device
+        self._pending_batches = [0, 0]
+        with torch.cuda.device(device):
+            vgg.pack_into(self.tr, device)
+
+    def flush_counters(self) -> None:
+        """num_batches_tracked of the BatchNorm modules (2 generator / 3 discriminator passes per step) is kept on the
+        host during the fused loop and written to the modules here (before state_dict() / saving)."""
+        _bump_batches_tracked(self.G, self._pending_batches[0])
+        _bump_batches_tracked(self.D, self._pending_batches[1])
+        self._pending_batches = [0, 0]
 
     def _adam(self, p, g, m, v) -> None:
         check(lib.dsr_adam_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), self.lr, 0.9, 0.999,
@@ -474,7 +528,6 @@ class GanTrainStep:
         LR = LR_patches.to(self.device, non_blocking=True).float().contiguous()
         HR = HR_patches.to(self.device, non_blocking=True).float().contiguous()
         self.t += 1
-        cur = torch.cuda.current_stream(self.device)
         # ---- discriminator step (train_GAN.py:43-53)
         tr.pack(NET_D, fd.flat, force=True)
         tr.pack(NET_G, fg.flat, force=True)
@@ -486,29 +539,21 @@ class GanTrainStep:
         fd.gflat.zero_()
         tr.d_backward(0, fd.flat, fd.gflat, target=1.0)
         tr.d_backward(1, fd.flat, fd.gflat, target=0.0)
-        work = None
-        if self.dp:
-            self.comm_stream.wait_stream(cur)
-            with torch.cuda.stream(self.comm_stream):
-                work = self.dist.all_reduce(fd.gflat, async_op=True)
-            self.allreduce_bytes = fd.gflat.numel() * 4 + fg.gflat.numel() * 4
+        work = self.xch.start(fd.gflat) if self.dp else None
         # ---- generator phase, independent of the discriminator: content loss and generator backward (:56-66)
         dfake = tr.vgg_loss(fake, HR, self.loss_G, False, True)
         fg.gflat.zero_()
         tr.g_backward(fg.flat, dfake, fg.gflat)
         # ---- discriminator update, then its pass on the generated batch for the adversarial term of loss_G (:58-59)
         if work is not None:
-            work.wait()
-            cur.wait_stream(self.comm_stream)
-            fd.gflat.mul_(1.0 / self.world)
+            self.xch.finish(work, fd.gflat)
         self._adam(fd.flat, fd.gflat, self.mD, self.vD)
         tr.pack(NET_D, fd.flat, force=True)
         p_fake2 = tr.d_forward(0, fd.flat, fd.bflat, fake)
         tr.bce(p_fake2, 1.0, self.loss_G, True)
         if self.dp:
-            self.dist.all_reduce(fg.gflat)
-            fg.gflat.mul_(1.0 / self.world)
+            self.xch.allreduce_mean(fg.gflat)
         self._adam(fg.flat, fg.gflat, self.mG, self.vG)
-        _bump_batches_tracked(self.G, 2)
-        _bump_batches_tracked(self.D, 3)
+        self._pending_batches[0] += 2
+        self._pending_batches[1] += 3
         return self.loss_D, self.loss_G

@@ -223,9 +223,64 @@ def test_generator_unsupported_configurations():
     with pytest.raises(NotImplementedError):
         dsr_b200.Generator(2)
     g = dsr_b200.Generator(8)
-    with pytest.raises(NotImplementedError):
-        g(torch.rand(1, 3, 16, 16))                       # training mode is not built
+    with pytest.raises(RuntimeError):
+        g(torch.rand(1, 3, 16, 16))                       # training mode, CPU tensor: no fallback
     with pytest.raises(RuntimeError):
         g.eval()(torch.rand(1, 3, 16, 16))                # CPU tensor: no fallback
     from models.GAN.generator import Generator as DropIn   # drop-in module name (eval_GAN.py:11)
     assert DropIn is dsr_b200.Generator
+
+
+def test_gan_training_surface_without_gpu():
+    """Host logic of the SRGAN training step that needs no GPU: trainer creation, parameter layout == the drop-in
+    modules' named_parameters(), same-seed initial state == the oracle's (i.e. the reference's), unsupported
+    configurations and CPU tensors raise."""
+    import ctypes as C
+    import torch
+    import dsr_b200
+    from dsr_b200 import gan_train as GT
+    from dsr_b200._lib import lib
+    from oracle import gan_oracle as GO, gan_train_oracle as O
+    h = C.c_void_p()
+    assert lib.dsr_gant_create(C.byref(h), 9, 24, 24, 8, 16, 1) == -1          # batch <= 8
+    assert lib.dsr_gant_create(C.byref(h), 8, 24, 24, 4, 16, 1) == -1          # factor 8 / 16 only
+    assert lib.dsr_gant_create(C.byref(h), 8, 40, 40, 8, 16, 1) == -5          # VGG transform only enlarges (patch <= 256)
+    assert lib.dsr_gant_create(C.byref(h), 8, 24, 24, 8, 16, 1) == 0
+    name = C.create_string_buffer(160)
+    off, n = C.c_longlong(), C.c_longlong()
+    torch.manual_seed(4)
+    G = dsr_b200.Generator(8)
+    D = GT.Discriminator((192, 192))
+    for net, mod in ((0, G), (1, D)):
+        named = list(mod.named_parameters())
+        assert lib.dsr_gant_num_params(h, net) == len(named)
+        total = 0
+        for i, (k, p) in enumerate(named):
+            assert lib.dsr_gant_param_info(h, net, i, name, 160, C.byref(off), C.byref(n)) == 0
+            assert (name.value.decode(), off.value, n.value) == (k, total, p.numel())
+            total += p.numel()
+        assert lib.dsr_gant_param_numel(h, net) == total
+        bufs = [(k, b) for k, b in mod.named_buffers() if not k.endswith('num_batches_tracked')]
+        assert lib.dsr_gant_num_buffers(h, net) == len(bufs)
+        for i, (k, b) in enumerate(bufs):
+            assert lib.dsr_gant_buffer_info(h, net, i, name, 160, C.byref(off), C.byref(n)) == 0
+            assert (name.value.decode(), n.value) == (k, b.numel())
+    assert lib.dsr_gant_param_numel(h, 2) == 20024384                            # VGG19 features[:36]
+    assert lib.dsr_gant_workspace_bytes(h) > 0
+    assert lib.dsr_gant_g_forward(h, None, None, None, None, 1, None) == -1     # unbound / null arguments
+    lib.dsr_gant_destroy(h)
+    # same seed -> the reference's initial state (incl. the running statistics fc_input_shape leaves behind)
+    torch.manual_seed(4)
+    sdG = GO.init_state_dict(8)
+    sdD = O.init_discriminator((192, 192))
+    for k, v in G.state_dict().items():
+        assert torch.equal(v, sdG[k]), k
+    for k, v in D.state_dict().items():
+        assert torch.equal(v, sdD[k]), k
+    with pytest.raises(RuntimeError):
+        D(torch.rand(2, 3, 192, 192))
+    with pytest.raises(RuntimeError):
+        GT.Vgg19Loss(pretrained=False)(torch.rand(1, 3, 64, 64), torch.rand(1, 3, 64, 64))
+    from models.GAN.discriminator import Discriminator as DropD
+    from utils.GAN import PerceptualLoss, get_loss_D                          # noqa: F401
+    assert DropD is GT.Discriminator
