@@ -751,6 +751,154 @@ def run_gan(args, rank, local_rank, world):
     print(json.dumps(line), flush=True)
 
 
+# -------------------------------------------------------------------------------------------------
+# SRGAN training step (BASELINE configs[4]): do_epoch of train_GAN.py:38-71
+# -------------------------------------------------------------------------------------------------
+GT_B, GT_LR = 8, 24                       # train_GAN.py:168 batch size, :269 HR patch 192 = 8 x 24
+# algorithmic conv FLOPs per patch: generator 6.133 GF (98.13 / 16), discriminator 7.07 GF, VGG19 features[:36]
+# at 224 x 224 39.01 GF; one step = G fwd + bwd (3x), D 3 fwd + 2 bwd (7x), VGG 2 fwd + 1 data-gradient (3x)
+GT_FLOPS_PER_PATCH = (3 * 6.1332 + 7 * 7.07 + 3 * 39.01) * 1e9
+
+
+def _gan_train_objects(dev, seed):
+    import dsr_b200
+    from dsr_b200 import gan_train as GT
+    torch.manual_seed(seed)
+    G = dsr_b200.Generator(8).train()
+    D = GT.Discriminator((GT_LR * 8, GT_LR * 8)).train()
+    torch.manual_seed(seed + 1000)
+    V = GT.Vgg19Loss(pretrained=False).to(dev)          # no pretrained file offline: random VGG19
+    return G, D, V, GT
+
+
+def run_gan_train_reference(args, rank, world):
+    """The reference's own do_epoch (train_GAN.GAN_ISR_train of the unmodified checkout in baseline/_ref, its own
+    modules, torch CPU fp32, all host threads; `--ref-device cuda`: stock CUDA eager, TF32 off) on one batch of 8."""
+    if rank != 0:
+        return
+    import subprocess
+    steps = max(2, min(args.steps, 3)) if args.ref_device == 'cpu' else max(args.steps, 3)
+    cmd = [sys.executable, os.path.join(ROOT, 'tools', 'run_reference_gan.py'), '--impl', 'reference', '--device',
+           args.ref_device, '--batch', str(GT_B), '--lr-size', str(GT_LR), '--epochs', str(steps)]
+    out = subprocess.run(cmd, capture_output=True, text=True).stdout.strip().splitlines()
+    r = json.loads(out[-1]) if out else {'unavailable': 'tools/run_reference_gan.py produced no output'}
+    if 'unavailable' in r:
+        print(json.dumps({'impl': 'reference', 'unavailable': r['unavailable']}), flush=True)
+        return
+    pps = GT_B * r['steps_per_s']
+    cores = os.cpu_count() or 1
+    line = {'impl': 'reference', 'metric': 'SRGAN training patches/s (do_epoch: G, D, VGG19 loss, two Adam steps)',
+            'value': pps, 'unit': 'patches/s', 'n_gpus': args.gpus, 'steps': steps, 'warmup': 0,
+            'ms_per_step': 1000.0 / r['steps_per_s'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': f'SRGAN training step (train_GAN.do_epoch), batch {GT_B} of {GT_LR}x{GT_LR} -> 192x192 '
+                                   f'patches per GPU, random-weight VGG19 (BASELINE configs[4])', 'batch': GT_B, 'factor': 8},
+            'cpu_baseline': {'value': pps, 'unit': 'patches/s', 'cores': cores if args.ref_device == 'cpu' else 0,
+                             'kind': 'reference', 'device': args.ref_device,
+                             'sample': f'{steps} do_epoch calls of the unmodified reference (incl. module construction and '
+                                       f'one logging pass), {r["seconds"]:.1f} s'},
+            'e2e': {'value': pps, 'unit': 'patches/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'losses': [r['loss_D'], r['loss_G']], 'gpu_launches': 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_gan_train(args, rank, local_rank, world):
+    """One step = GanTrainStep.do_epoch on this rank's batch of 8 patches; world > 1: data-parallel replicas, NCCL
+    all-reduce (mean) of the flat discriminator (321 MB) and generator (6.8 MB) gradients."""
+    import torch.distributed as dist
+    dev = torch.device('cuda', local_rank)
+    torch.cuda.set_device(dev)
+    from oracle import gan_train_oracle as O          # harness only: the synthetic LR / HR batch recipe
+    G, D, V, GT = _gan_train_objects(dev, 0)
+    step = GT.GanTrainStep(G, D, V, 1e-4, GT_B, (GT_LR, GT_LR), dev, data_parallel=world > 1)
+    LR, HR = O.synthetic_batch(100 + rank, GT_B, (GT_LR, GT_LR), 8)          # every rank its own shard of the global batch
+    dLR, dHR = LR.to(dev), HR.to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step.do_epoch(dLR, dHR)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        lD, lG = step.do_epoch(dLR, dHR)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if sampler else None
+    # ---- end to end: the batch comes from pinned host memory, both losses are read back every step (train_GAN.py:99-100)
+    hLR, hHR = LR.pin_memory(), HR.pin_memory()
+    for _ in range(2):
+        a, b = step.do_epoch(hLR, hHR)
+        a.item(), b.item()
+    barrier()
+    n_e2e = max(3, min(args.steps, 10))
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    f0.record()
+    for _ in range(n_e2e):
+        a, b = step.do_epoch(hLR, hHR)
+        losses = (a.item(), b.item())
+    f1.record()
+    barrier()
+    ms_e2e = max(f0.elapsed_time(f1), (time.time() - t0) * 1e3)
+    # ---- the collective alone: mean all-reduce of the two flat gradient buffers
+    ar = None
+    if world > 1:
+        x = step.xch
+        for _ in range(2):
+            x.allreduce_mean(step.fd.gflat)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(5):
+            x.allreduce_mean(step.fd.gflat)
+            x.allreduce_mean(step.fg.gflat)
+        g1.record()
+        barrier()
+        ar_ms = g0.elapsed_time(g1) / 5
+        nbytes = (step.fd.gflat.numel() + step.fg.gflat.numel()) * 4
+        t = torch.tensor([ms, ms_e2e, ar_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e, ar_ms = float(t[0]), float(t[1]), float(t[2])
+        ar = {'ms_per_step': ar_ms, 'bytes_per_step': nbytes, 'algbw_GBps': nbytes / (ar_ms * 1e-3) / 1e9,
+              'busbw_GBps': 2 * (world - 1) / world * nbytes / (ar_ms * 1e-3) / 1e9,
+              'note': 'timed alone; inside the step the discriminator all-reduce runs on a side stream under the VGG / '
+                      'generator-backward phase'}
+    if rank != 0:
+        return
+    pk = peaks()
+    pps = world * GT_B * args.steps / (ms * 1e-3)
+    tfl = GT_FLOPS_PER_PATCH * GT_B * args.steps / (ms * 1e-3) / 1e12
+    line = {'metric': 'SRGAN training patches/s (do_epoch: G, D, VGG19 loss, two Adam steps)', 'value': pps,
+            'unit': 'patches/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'bf16 operands / f32 accumulate (tcgen05 kind::f16), f32 master weights and Adam', 'data': 'synthetic',
+            'config': {'workload': f'SRGAN training step (train_GAN.do_epoch), batch {GT_B} of {GT_LR}x{GT_LR} -> 192x192 '
+                                   f'patches per GPU, random-weight VGG19 (BASELINE configs[4])', 'batch': GT_B, 'factor': 8,
+                       'parallelism': f'dp{world}' if world > 1 else 'single',
+                       'l2': 'activations of one step are ~1.4 GB >> 126 MB L2'},
+            'roofline': {'bound': 'tensor', 'kernel': 'whole step: gconv_kernel / gwgrad_kernel (bf16 implicit GEMM) + element-wise family',
+                         'achieved': tfl, 'peak': pk['tflops'], 'unit': 'TFLOP/s',
+                         'frac': tfl / pk['tflops'] if pk['tflops'] else None, 'traffic': None, 'peak_source': pk['src'],
+                         'gflop_per_patch': GT_FLOPS_PER_PATCH / 1e9},
+            'e2e': {'value': world * GT_B * n_e2e / (ms_e2e * 1e-3), 'unit': 'patches/s',
+                    'h2d_bytes_per_step': (LR.numel() + HR.numel()) * 4, 'd2h_bytes_per_step': 8,
+                    'ms_per_step': ms_e2e / n_e2e,
+                    'path': 'GanTrainStep.do_epoch(LR, HR) with the batch in pinned host memory; both losses read back with '
+                            '.item() every step (train_GAN.py:99-100)'},
+            'losses': list(losses), 'allreduce': ar,
+            'gpu_launches': None, 'clocks': clocks}
+    line['gpu_launches'] = step.launches_per_step * args.steps
+    print(json.dumps(line), flush=True)
+
+
+
 def secondary_gan_eval(dev):
     """BASELINE configs[3] beside the headline: a short SRResNet generator inference run (batch 64 of 96x96 LR patches,
     x8) through dsr_b200.Generator; the full batch-256 line is `--workload gan_eval`."""
@@ -779,8 +927,9 @@ def secondary_gan_eval(dev):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument('--workload', default='dip', choices=['dip', 'gan_eval'],
-                    help='dip: the headline DIP iteration (BASELINE configs[1]); gan_eval: SRResNet generator inference (configs[3])')
+    ap.add_argument('--workload', default='dip', choices=['dip', 'gan_eval', 'gan_train'],
+                    help='dip: the headline DIP iteration (BASELINE configs[1]); gan_eval: SRResNet generator inference (configs[3]); '
+                         'gan_train: SRGAN training step, data-parallel over the ranks (configs[4])')
     ap.add_argument('--batch', type=int, default=256, help='gan_eval: LR patches per step')
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=None)
@@ -797,12 +946,12 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.steps is None:
-        args.steps = 200 if args.workload == 'dip' else (10 if args.impl == 'ours' else 8)
+        args.steps = {'dip': 200, 'gan_eval': 10 if args.impl == 'ours' else 8, 'gan_train': 20}[args.workload]
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     if args.impl == 'reference':
-        (run_reference if args.workload == 'dip' else run_gan_reference)(args, rank, world)
+        {'dip': run_reference, 'gan_eval': run_gan_reference, 'gan_train': run_gan_train_reference}[args.workload](args, rank, world)
         return
     if not torch.cuda.is_available():
         raise SystemExit('bench.py: no CUDA device (the product path has no CPU fallback; use --impl reference for the CPU arm)')
@@ -811,7 +960,7 @@ def main():
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     try:
-        (run_ours if args.workload == 'dip' else run_gan)(args, rank, local_rank, world)
+        {'dip': run_ours, 'gan_eval': run_gan, 'gan_train': run_gan_train}[args.workload](args, rank, local_rank, world)
     finally:
         if world > 1:
             import torch.distributed as dist

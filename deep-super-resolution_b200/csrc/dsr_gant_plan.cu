@@ -39,6 +39,18 @@ struct ConvL {
 };
 struct BnL { int C = 0; long long g_off = 0, b_off = 0, rm_off = 0, rv_off = 0; };
 
+// The launch sequence of an entry point is fixed once the workspace is bound (same tensors, same tensor maps, same
+// epilogue pointers every call): the parameter blocks (two cuTensorMapEncodeTiled calls each) are built on the first call
+// and replayed afterwards.
+struct Tape {
+  std::vector<GConvParams> convs;
+  std::vector<GWgradParams> wgs;
+  size_t ci = 0, wi = 0;
+  bool built = false;
+  void rewind() { ci = 0; wi = 0; }
+  void clear() { convs.clear(); wgs.clear(); built = false; rewind(); }
+};
+
 struct Arena {
   uint8_t* base = nullptr;
   size_t off = 0;
@@ -103,6 +115,8 @@ struct dsr_gant {
   float* dw_arena[2] = {nullptr, nullptr}; // packed weight gradients of G / D
   size_t dw_bytes[2] = {0, 0};
   int launches = 0;
+  Tape tp_gf, tp_gb, tp_df[2], tp_db[2], tp_v, tp_vl;
+  Tape* tape = nullptr;                    // the running entry point's tape
 };
 
 namespace {
@@ -283,31 +297,58 @@ size_t layout(dsr_gant* p, uint8_t* base) {
 
 int run_fprop(dsr_gant* p, const ConvL& c, const GT& in, const GT& out, bool bias, int act, float slope, double* stats,
               cudaStream_t s) {
-  GConvParams g;
-  int rc = make_gconv_fprop(&g, in, out, c.w_f, c.cin_pad, c.cout_pad, c.ks, c.stride, p->err);
-  if (rc) return rc;
-  g.bias = bias ? c.bias_pad : nullptr;
-  g.act = act; g.slope = slope; g.stats = stats;
-  return launch_gconv(g, p->num_sms, s);
+  Tape& t = *p->tape;
+  if (!t.built) {
+    GConvParams g;
+    int rc = make_gconv_fprop(&g, in, out, c.w_f, c.cin_pad, c.cout_pad, c.ks, c.stride, p->err);
+    if (rc) return rc;
+    g.bias = bias ? c.bias_pad : nullptr;
+    g.act = act; g.slope = slope; g.stats = stats;
+    t.convs.push_back(g);
+  }
+  return launch_gconv(t.convs[t.ci++], p->num_sms, s);
 }
 int run_dgrad(dsr_gant* p, const ConvL& c, const GT& dy, const GT& dx, const bf16_t* addend, const bf16_t* mask, float slope,
               cudaStream_t s) {
-  GConvParams g[4];
-  int n = 0;
-  int rc = make_gconv_dgrad(g, &n, dy, dx, c.w_d, c.cin_pad, c.cout_pad, c.ks, c.stride, p->err);
-  if (rc) return rc;
+  Tape& t = *p->tape;
+  const int n = (c.stride == 1) ? 1 : 4;
+  if (!t.built) {
+    GConvParams g[4];
+    int nn = 0;
+    int rc = make_gconv_dgrad(g, &nn, dy, dx, c.w_d, c.cin_pad, c.cout_pad, c.ks, c.stride, p->err);
+    if (rc) return rc;
+    for (int i = 0; i < nn; ++i) {
+      g[i].addend = addend; g[i].mask = mask; g[i].slope = slope;
+      t.convs.push_back(g[i]);
+    }
+  }
   for (int i = 0; i < n; ++i) {
-    g[i].addend = addend; g[i].mask = mask; g[i].slope = slope;
-    if ((rc = launch_gconv(g[i], p->num_sms, s))) return rc;
+    const int rc = launch_gconv(t.convs[t.ci++], p->num_sms, s);
+    if (rc) return rc;
   }
   return 0;
 }
 int run_wgrad(dsr_gant* p, const ConvL& c, const GT& dy, const GT& x, cudaStream_t s) {
-  GWgradParams g;
-  int rc = make_gwgrad(&g, dy, x, c.dw, c.cin, c.cout, c.stride, p->num_sms, p->err);
-  if (rc) return rc;
-  return launch_gwgrad(g, s);
+  Tape& t = *p->tape;
+  if (!t.built) {
+    GWgradParams g;
+    int rc = make_gwgrad(&g, dy, x, c.dw, c.cin, c.cout, c.stride, p->num_sms, p->err);
+    if (rc) return rc;
+    t.wgs.push_back(g);
+  }
+  return launch_gwgrad(t.wgs[t.wi++], s);
 }
+struct TapeScope {                       // selects an entry point's tape; marks it built when the call got to its end
+  dsr_gant* p;
+  Tape* t;
+  bool ok = false;
+  TapeScope(dsr_gant* pp, Tape* tt) : p(pp), t(tt) { t->rewind(); p->tape = t; }
+  ~TapeScope() {
+    if (ok) t->built = true;
+    else if (!t->built) t->clear();
+    p->tape = nullptr;
+  }
+};
 int pack_conv(const ConvL& c, const float* params, bool with_bias, cudaStream_t s) {
   return gl_pack_weight(params + c.w_off, with_bias ? params + c.b_off : nullptr, c.cout, c.cin, c.ks, c.cout_pad, c.cin_pad,
                         c.w_f, c.w_d, c.bias_pad, s);
@@ -415,6 +456,7 @@ int dsr_gant_bind(dsr_gant_t* p, void* workspace, size_t bytes, void* stream) {
   cudaError_t e = cudaMemsetAsync(workspace, 0, p->ws_bytes, s);      // gap rows and padded channels stay zero from here on
   if (e != cudaSuccess) return static_cast<int>(e);
   layout(p, static_cast<uint8_t*>(workspace));
+  for (Tape* t : {&p->tp_gf, &p->tp_gb, &p->tp_df[0], &p->tp_df[1], &p->tp_db[0], &p->tp_db[1], &p->tp_v, &p->tp_vl}) t->clear();
   p->bound = true;
   return ensure_driver_api();
 }
@@ -459,6 +501,7 @@ int dsr_gant_g_forward(dsr_gant_t* p, const float* params, float* buffers, const
   if (!p || !p->bound || !params || !lr_nchw || !out_nchw) return -1;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   p->launches = 0;
+  TapeScope scope(p, &p->tp_gf);
   const double count = static_cast<double>(p->B) * p->lh * p->lw;
   cudaMemsetAsync(p->g_stats, 0, static_cast<size_t>(2 * p->blocks + 1) * 128 * sizeof(double), s);
   GCHK(gl_pack_image(lr_nchw, p->g_lr16, s));
@@ -496,6 +539,7 @@ int dsr_gant_g_forward(dsr_gant_t* p, const float* params, float* buffers, const
   GCHK(run_fprop(p, p->g_conv3, *cur, p->g_z, true, 0, 0.f, nullptr, s));
   GCHK(gl_tanh_out(p->g_z, out_nchw, s));
   cudaMemcpyAsync(p->g_out, out_nchw, static_cast<size_t>(p->B) * 3 * p->H * p->W * 4, cudaMemcpyDeviceToDevice, s);
+  scope.ok = true;
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -504,6 +548,7 @@ int dsr_gant_g_backward(dsr_gant_t* p, const float* params, const float* dout_nc
   if (!p || !p->bound || !params || !dout_nchw || !grads) return -1;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   p->launches = 0;
+  TapeScope scope(p, &p->tp_gb);
   cudaMemsetAsync(p->dw_arena[0], 0, p->dw_bytes[0], s);
   const int last = p->nshuf - 1;
   GCHK(gl_tanh_bwd(dout_nchw, p->g_out, p->g_dz16, grads + p->g_conv3.b_off, s));
@@ -550,6 +595,7 @@ int dsr_gant_g_backward(dsr_gant_t* p, const float* params, const float* dout_nc
   }
   GCHK(gl_unpack_wgrad(p->g_conv2.dw, grads + p->g_conv2.w_off, 64, 64, 3, s));
   for (int j = 0; j < p->nshuf; ++j) GCHK(gl_unpack_wgrad(p->g_cs[j].dw, grads + p->g_cs[j].w_off, 256, 64, 3, s));
+  scope.ok = true;
   return 0;
 }
 
@@ -562,6 +608,7 @@ int dsr_gant_d_forward(dsr_gant_t* p, int slot, const float* params, float* buff
   if (!p || !p->bound || !params || !img_nchw || !prob || slot < 0 || slot > 1) return -1;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   p->launches = 0;
+  TapeScope scope(p, &p->tp_df[slot]);
   cudaMemsetAsync(p->d_stats[slot], 0, 7 * 1024 * sizeof(double), s);
   GCHK(gl_pack_image(img_nchw, p->d_img[slot], s));
   GCHK(run_fprop(p, p->d_conv0, p->d_img[slot], p->d_h0[slot], true, 1, 0.2f, nullptr, s));
@@ -581,6 +628,7 @@ int dsr_gant_d_forward(dsr_gant_t* p, int slot, const float* params, float* buff
   GCHK(gl_dense1_fwd(params + p->d_w1, params + p->d_b1, p->d_flat[slot], p->d_z1[slot], p->B, p->d_K, 1024, s));
   GCHK(gl_dense2_fwd(p->d_z1[slot], params + p->d_w2, params + p->d_b2, p->d_prob[slot], p->B, 1024, s));
   cudaMemcpyAsync(prob, p->d_prob[slot], static_cast<size_t>(p->B) * 4, cudaMemcpyDeviceToDevice, s);
+  scope.ok = true;
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -591,6 +639,7 @@ int dsr_gant_d_backward(dsr_gant_t* p, int slot, const float* params, const floa
   if (!p || !p->bound || !params || !grads || slot < 0 || slot > 1) return -1;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   p->launches = 0;
+  TapeScope scope(p, &p->tp_db[slot]);
   cudaMemsetAsync(p->dw_arena[1], 0, p->dw_bytes[1], s);
   GCHK(gl_dense2_bwd(p->d_prob[slot], dprob, target, p->d_z1[slot], params + p->d_w2, p->d_dz1, grads + p->d_w2,
                      grads + p->d_b2, p->B, 1024, s));
@@ -616,6 +665,7 @@ int dsr_gant_d_backward(dsr_gant_t* p, int slot, const float* params, const floa
   GCHK(gl_wgrad_in3(p->d_dz0, p->d_img[slot], grads + p->d_conv0.w_off, 3, s));
   GCHK(gl_chan_sum(p->d_dz0, grads + p->d_conv0.b_off, s));
   for (int k = 0; k < 7; ++k) GCHK(gl_unpack_wgrad(p->d_c[k].dw, grads + p->d_c[k].w_off, p->d_c[k].cout, p->d_c[k].cin, 3, s));
+  scope.ok = true;
   return 0;
 }
 
@@ -648,6 +698,7 @@ int dsr_gant_vgg_loss(dsr_gant_t* p, const float* fake_nchw, const float* real_n
   if (!p || !p->bound || !p->with_vgg || !fake_nchw || !real_nchw || !loss) return -1;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   p->launches = 0;
+  TapeScope scope(p, dfake_nchw ? &p->tp_v : &p->tp_vl);
   int rc;
   if ((rc = vgg_forward(p, real_nchw, s))) return rc;
   cudaMemcpyAsync(p->v_freal.ptr, p->v_y[15].ptr, p->v_freal.bytes(), cudaMemcpyDeviceToDevice, s);
@@ -657,7 +708,7 @@ int dsr_gant_vgg_loss(dsr_gant_t* p, const float* fake_nchw, const float* real_n
   GCHK(gl_feat_mse(p->v_y[15], p->v_freal, p->v_gb[top], p->loss_acc, s));
   const GT& f = p->v_y[15];
   GCHK(gl_finish_double(p->loss_acc, loss, 1.f / (static_cast<float>(f.B) * f.H * f.W * f.C), accumulate, s));
-  if (dfake_nchw == nullptr) return 0;
+  if (dfake_nchw == nullptr) { scope.ok = true; return 0; }
   // v_gb[level] holds d(loss)/d(pre-activation) of the current conv, v_ga[level] is the other buffer of the level
   int level = top;
   GT dz = p->v_gb[level];
@@ -681,6 +732,7 @@ int dsr_gant_vgg_loss(dsr_gant_t* p, const float* fake_nchw, const float* real_n
   }
   GCHK(run_dgrad(p, p->v_c[0], dz, p->v_dpre, nullptr, nullptr, 0.f, s));
   GCHK(gl_vgg_pre_bwd(p->v_dpre, p->H, p->W, p->v_Hr, p->v_Wr, p->v_top, p->v_left, dfake_nchw, 0, s));
+  scope.ok = true;
   return 0;
 }
 

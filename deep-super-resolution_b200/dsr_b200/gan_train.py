@@ -52,6 +52,10 @@ class Trainer:
         self.d_gen = [0, 0]          # generation counter per discriminator activation slot
         self.g_gen = 0
         self._packed: Dict[int, Tuple[int, int]] = {}
+        self.launch_count = 0        # kernels launched through this trainer (dsr_gant_last_launches per call)
+
+    def _count(self) -> None:
+        self.launch_count += max(0, lib.dsr_gant_last_launches(self.handle))
 
     def layout(self, net: int):
         name = C.create_string_buffer(160)
@@ -73,17 +77,20 @@ class Trainer:
             return
         check(lib.dsr_gant_pack(self.handle, net, flat.data_ptr(), _lib.stream_ptr()), 'dsr_gant_pack')
         self._packed[net] = key
+        self._count()
 
     def g_forward(self, params, buffers, lr, bn_updates: int = 1) -> torch.Tensor:
         out = torch.empty((self.B, 3, self.H, self.W), dtype=torch.float32, device=lr.device)
         check(lib.dsr_gant_g_forward(self.handle, params.data_ptr(), buffers.data_ptr() if buffers is not None else None,
                                      lr.data_ptr(), out.data_ptr(), bn_updates, _lib.stream_ptr()), 'dsr_gant_g_forward')
         self.g_gen += 1
+        self._count()
         return out
 
     def g_backward(self, params, dout, grads) -> None:
         check(lib.dsr_gant_g_backward(self.handle, params.data_ptr(), dout.data_ptr(), grads.data_ptr(), _lib.stream_ptr()),
               'dsr_gant_g_backward')
+        self._count()
 
     def d_forward(self, slot: int, params, buffers, img) -> torch.Tensor:
         prob = torch.empty((self.B,), dtype=torch.float32, device=img.device)
@@ -91,20 +98,24 @@ class Trainer:
                                      buffers.data_ptr() if buffers is not None else None, img.data_ptr(), prob.data_ptr(),
                                      _lib.stream_ptr()), 'dsr_gant_d_forward')
         self.d_gen[slot] += 1
+        self._count()
         return prob
 
     def d_backward(self, slot: int, params, grads, dprob: Optional[torch.Tensor] = None, target: float = 0.0) -> None:
         check(lib.dsr_gant_d_backward(self.handle, slot, params.data_ptr(), dprob.data_ptr() if dprob is not None else None,
                                       float(target), grads.data_ptr(), _lib.stream_ptr()), 'dsr_gant_d_backward')
+        self._count()
 
     def bce(self, prob, target: float, loss, accumulate: bool) -> None:
         check(lib.dsr_gant_bce(self.handle, prob.data_ptr(), float(target), prob.numel(), loss.data_ptr(), int(accumulate),
                                _lib.stream_ptr()), 'dsr_gant_bce')
+        self.launch_count += 1
 
     def vgg_loss(self, fake, real, loss, accumulate: bool, want_grad: bool) -> Optional[torch.Tensor]:
         dfake = torch.empty_like(fake) if want_grad else None
         check(lib.dsr_gant_vgg_loss(self.handle, fake.data_ptr(), real.data_ptr(), loss.data_ptr(), int(accumulate),
                                     dfake.data_ptr() if want_grad else None, _lib.stream_ptr()), 'dsr_gant_vgg_loss')
+        self._count()
         return dfake
 
     def device_error(self) -> int:
@@ -522,12 +533,14 @@ class GanTrainStep:
     def _adam(self, p, g, m, v) -> None:
         check(lib.dsr_adam_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), self.lr, 0.9, 0.999,
                                 1e-8, self.t, _lib.stream_ptr()), 'dsr_adam_step')
+        self.tr.launch_count += 1
 
     def do_epoch(self, LR_patches: torch.Tensor, HR_patches: torch.Tensor):
         tr, fg, fd = self.tr, self.fg, self.fd
         LR = LR_patches.to(self.device, non_blocking=True).float().contiguous()
         HR = HR_patches.to(self.device, non_blocking=True).float().contiguous()
         self.t += 1
+        n0 = tr.launch_count
         # ---- discriminator step (train_GAN.py:43-53)
         tr.pack(NET_D, fd.flat, force=True)
         tr.pack(NET_G, fg.flat, force=True)
@@ -554,6 +567,7 @@ class GanTrainStep:
         if self.dp:
             self.xch.allreduce_mean(fg.gflat)
         self._adam(fg.flat, fg.gflat, self.mG, self.vG)
+        self.launches_per_step = tr.launch_count - n0
         self._pending_batches[0] += 2
         self._pending_batches[1] += 3
         return self.loss_D, self.loss_G
