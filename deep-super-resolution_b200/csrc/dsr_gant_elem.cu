@@ -141,10 +141,31 @@ __device__ __forceinline__ void bn_tab_fill_g(BnTabG& t, const double* stats, co
 template <int ACT>
 __global__ void g_bn_apply_kernel(const bf16_t* __restrict__ raw, bf16_t* __restrict__ out, const bf16_t* __restrict__ res,
                                   const double* __restrict__ stats, const float* __restrict__ gamma,
-                                  const float* __restrict__ beta, const float* __restrict__ slope_p, TG g, double inv_count) {
+                                  const float* __restrict__ beta, const float* __restrict__ slope_p, TG g, double inv_count,
+                                  const float* __restrict__ conv_bias, float* __restrict__ rm, float* __restrict__ rv,
+                                  int run_times) {
   __shared__ BnTabG tab;
   pdl_sync();
   bn_tab_fill_g(tab, stats, gamma, beta, g.C, inv_count);
+  if (blockIdx.x == 0 && rm != nullptr && run_times > 0) {
+    // running_mean / running_var as torch.nn.BatchNorm2d updates them (momentum 0.1, unbiased variance), `run_times`
+    // times with the same batch statistics; the conv bias dropped by the conv kernels is added back to the mean
+    const double count = 1.0 / inv_count;
+    for (int c = threadIdx.x; c < g.C; c += kT) {
+      const double m = stats[c] * inv_count;
+      double var = stats[g.C + c] * inv_count - m * m;
+      if (var < 0.0) var = 0.0;
+      const float mean = static_cast<float>(m) + (conv_bias ? conv_bias[c] : 0.f);
+      const float uvar = static_cast<float>(var * (count / (count - 1.0)));
+      float a = rm[c], b = rv[c];
+      for (int t = 0; t < run_times; ++t) {
+        a = 0.9f * a + 0.1f * mean;
+        b = 0.9f * b + 0.1f * uvar;
+      }
+      rm[c] = a;
+      rv[c] = b;
+    }
+  }
   const float slope = (ACT == GACT_PRELU) ? slope_p[0] : kLrelu;
   const int g8 = g.C >> 3;
   const long long total = static_cast<long long>(g.B) * g.H * g.W * g8;
@@ -168,27 +189,6 @@ __global__ void g_bn_apply_kernel(const bf16_t* __restrict__ raw, bf16_t* __rest
     }
     store8(out + off, x);
   }
-}
-
-// running_mean / running_var as torch.nn.BatchNorm2d updates them (momentum 0.1, unbiased variance), `times` times
-// with the same batch statistics; the conv bias dropped by the kernels is added back to the mean.
-__global__ void g_bn_running_kernel(const double* __restrict__ stats, const float* __restrict__ conv_bias,
-                                    float* __restrict__ rm, float* __restrict__ rv, int C, double count, int times) {
-  pdl_sync();
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  const double m = stats[c] / count;
-  double var = stats[C + c] / count - m * m;
-  if (var < 0.0) var = 0.0;
-  const float mean = static_cast<float>(m) + (conv_bias ? conv_bias[c] : 0.f);
-  const float uvar = static_cast<float>(var * (count / (count - 1.0)));
-  float a = rm[c], b = rv[c];
-  for (int t = 0; t < times; ++t) {
-    a = 0.9f * a + 0.1f * mean;
-    b = 0.9f * b + 0.1f * uvar;
-  }
-  rm[c] = a;
-  rv[c] = b;
 }
 
 // pass 1 of the backward: sums[c] = sum g, sums[C + c] = sum g * xhat, sums[2 C] = d(loss)/d(PReLU slope),
@@ -248,14 +248,21 @@ template <int ACT>
 __global__ void g_bn_bwd_apply_kernel(const bf16_t* __restrict__ dy, const bf16_t* __restrict__ raw, bf16_t* __restrict__ draw,
                                       const double* __restrict__ stats, const float* __restrict__ gamma,
                                       const float* __restrict__ beta, const float* __restrict__ slope_p, TG g,
-                                      double inv_count, const double* __restrict__ sums) {
+                                      double inv_count, const double* __restrict__ sums, float* __restrict__ dgamma,
+                                      float* __restrict__ dbeta, float* __restrict__ dslope) {
   __shared__ BnTabG tab;
   __shared__ float s_mg[512], s_mgx[512];
   pdl_sync();
   for (int c = threadIdx.x; c < g.C; c += kT) {
     s_mg[c] = static_cast<float>(sums[c] * inv_count);
     s_mgx[c] = static_cast<float>(sums[g.C + c] * inv_count);
+    if (blockIdx.x == 0) {               // parameter gradients (+=): d gamma = sum g xhat, d beta = sum g
+      dgamma[c] += static_cast<float>(sums[g.C + c]);
+      dbeta[c] += static_cast<float>(sums[c]);
+    }
   }
+  if (ACT == GACT_PRELU && blockIdx.x == 0 && threadIdx.x == 0 && dslope != nullptr)
+    dslope[0] += static_cast<float>(sums[2 * g.C]);
   bn_tab_fill_g(tab, stats, gamma, beta, g.C, inv_count);
   const float slope = (ACT == GACT_PRELU) ? slope_p[0] : kLrelu;
   const int g8 = g.C >> 3;
@@ -279,17 +286,6 @@ __global__ void g_bn_bwd_apply_kernel(const bf16_t* __restrict__ dy, const bf16_
     }
     store8(draw + off, x);
   }
-}
-
-__global__ void g_bn_param_grad_kernel(const double* __restrict__ sums, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                       float* __restrict__ dslope, int C) {
-  pdl_sync();
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c < C) {
-    dgamma[c] += static_cast<float>(sums[C + c]);
-    dbeta[c] += static_cast<float>(sums[c]);
-  }
-  if (c == 0 && dslope != nullptr) dslope[0] += static_cast<float>(sums[2 * C]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -670,37 +666,38 @@ __global__ void g_unflatten_kernel(const float* __restrict__ dflat, bf16_t* __re
   }
 }
 
-// z1[b][j] = bias[j] + sum_k W[j][k] x[b][k]; a block owns 4 rows of W (read once, fp32), B <= 8
+// z1[b][j] = bias[j] + sum_k W[j][k] x[b][k]; a block owns kD1Rows rows of W (read once, fp32, streaming), B <= 8
+constexpr int kD1Rows = 8;
 __global__ void __launch_bounds__(kT) g_dense1_fwd_kernel(const float* __restrict__ W, const float* __restrict__ bias,
                                                           const float* __restrict__ x, float* __restrict__ z1, int B, int K,
                                                           int J) {
-  __shared__ float sm[8][32];
+  __shared__ float sm[8][kD1Rows * 8];
   pdl_sync();
-  const int j0 = blockIdx.x * 4;
-  float acc[4][8];
+  const int j0 = blockIdx.x * kD1Rows;
+  float acc[kD1Rows][8];
 #pragma unroll
-  for (int r = 0; r < 4; ++r)
+  for (int r = 0; r < kD1Rows; ++r)
 #pragma unroll
     for (int b = 0; b < 8; ++b) acc[r][b] = 0.f;
   const int k4n = K >> 2;
   for (int k4 = threadIdx.x; k4 < k4n; k4 += kT) {
-    float4 w[4];
+    float4 w[kD1Rows];
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
-      w[r] = (j0 + r < J) ? __ldg(reinterpret_cast<const float4*>(W + static_cast<long long>(j0 + r) * K) + k4)
+    for (int r = 0; r < kD1Rows; ++r)
+      w[r] = (j0 + r < J) ? __ldcs(reinterpret_cast<const float4*>(W + static_cast<long long>(j0 + r) * K) + k4)
                           : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int b = 0; b < 8; ++b) {
       if (b < B) {
         const float4 xv = __ldg(reinterpret_cast<const float4*>(x + static_cast<long long>(b) * K) + k4);
 #pragma unroll
-        for (int r = 0; r < 4; ++r) acc[r][b] += w[r].x * xv.x + w[r].y * xv.y + w[r].z * xv.z + w[r].w * xv.w;
+        for (int r = 0; r < kD1Rows; ++r) acc[r][b] += w[r].x * xv.x + w[r].y * xv.y + w[r].z * xv.z + w[r].w * xv.w;
       }
     }
   }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
-  for (int r = 0; r < 4; ++r)
+  for (int r = 0; r < kD1Rows; ++r)
 #pragma unroll
     for (int b = 0; b < 8; ++b) {
       float v = acc[r][b];
@@ -709,7 +706,7 @@ __global__ void __launch_bounds__(kT) g_dense1_fwd_kernel(const float* __restric
       if (lane == 0) sm[warp][r * 8 + b] = v;
     }
   __syncthreads();
-  if (threadIdx.x < 32) {
+  if (threadIdx.x < kD1Rows * 8) {
     const int r = threadIdx.x >> 3, b = threadIdx.x & 7;
     float v = 0.f;
     for (int w = 0; w < 8; ++w) v += sm[w][threadIdx.x];
@@ -1017,21 +1014,16 @@ int gl_tanh_bwd(const float* dout, const float* out, const GT& dz, float* dbias3
 }
 
 int gl_bn_apply(const GT& raw, const GT& out, const bf16_t* res, const double* stats, const float* gamma, const float* beta,
-                int act, const float* slope, cudaStream_t s) {
+                int act, const float* slope, const float* conv_bias, float* rm, float* rv, int run_times, cudaStream_t s) {
   const long long items = static_cast<long long>(raw.B) * raw.H * raw.W * (raw.C / 8);
   const double inv = 1.0 / (static_cast<double>(raw.B) * raw.H * raw.W);
   const dim3 grid(grid_for(items));
   const bf16_t* r = static_cast<const bf16_t*>(raw.ptr);
   bf16_t* o = static_cast<bf16_t*>(out.ptr);
   if (raw.C > 512 || (raw.C & 7)) return -51;
-  if (act == GACT_NONE) launch_k(g_bn_apply_kernel<GACT_NONE>, grid, dim3(kT), 0, s, r, o, res, stats, gamma, beta, slope, tg_of(raw), inv);
-  else if (act == GACT_LRELU) launch_k(g_bn_apply_kernel<GACT_LRELU>, grid, dim3(kT), 0, s, r, o, res, stats, gamma, beta, slope, tg_of(raw), inv);
-  else launch_k(g_bn_apply_kernel<GACT_PRELU>, grid, dim3(kT), 0, s, r, o, res, stats, gamma, beta, slope, tg_of(raw), inv);
-  GL_CHECK();
-}
-int gl_bn_running(const double* stats, const float* conv_bias, float* rm, float* rv, int C, double count, int times,
-                  cudaStream_t s) {
-  launch_k(g_bn_running_kernel, dim3((C + 127) / 128), dim3(128), 0, s, stats, conv_bias, rm, rv, C, count, times);
+  if (act == GACT_NONE) launch_k(g_bn_apply_kernel<GACT_NONE>, grid, dim3(kT), 0, s, r, o, res, stats, gamma, beta, slope, tg_of(raw), inv, conv_bias, rm, rv, run_times);
+  else if (act == GACT_LRELU) launch_k(g_bn_apply_kernel<GACT_LRELU>, grid, dim3(kT), 0, s, r, o, res, stats, gamma, beta, slope, tg_of(raw), inv, conv_bias, rm, rv, run_times);
+  else launch_k(g_bn_apply_kernel<GACT_PRELU>, grid, dim3(kT), 0, s, r, o, res, stats, gamma, beta, slope, tg_of(raw), inv, conv_bias, rm, rv, run_times);
   GL_CHECK();
 }
 int gl_bn_bwd(const GT& dy, const GT& raw, const GT& draw, const double* stats, const float* gamma, const float* beta,
@@ -1048,16 +1040,14 @@ int gl_bn_bwd(const GT& dy, const GT& raw, const GT& draw, const double* stats, 
   const TG g = tg_of(raw);
   if (act == GACT_NONE) {
     launch_k(g_bn_bwd_stats_kernel<GACT_NONE>, g1, dim3(kT), 0, s, d, r, stats, gamma, beta, slope, g, inv, sums);
-    launch_k(g_bn_bwd_apply_kernel<GACT_NONE>, g2, dim3(kT), 0, s, d, r, o, stats, gamma, beta, slope, g, inv, sums);
+    launch_k(g_bn_bwd_apply_kernel<GACT_NONE>, g2, dim3(kT), 0, s, d, r, o, stats, gamma, beta, slope, g, inv, static_cast<const double*>(sums), dgamma, dbeta, dslope);
   } else if (act == GACT_LRELU) {
     launch_k(g_bn_bwd_stats_kernel<GACT_LRELU>, g1, dim3(kT), 0, s, d, r, stats, gamma, beta, slope, g, inv, sums);
-    launch_k(g_bn_bwd_apply_kernel<GACT_LRELU>, g2, dim3(kT), 0, s, d, r, o, stats, gamma, beta, slope, g, inv, sums);
+    launch_k(g_bn_bwd_apply_kernel<GACT_LRELU>, g2, dim3(kT), 0, s, d, r, o, stats, gamma, beta, slope, g, inv, static_cast<const double*>(sums), dgamma, dbeta, dslope);
   } else {
     launch_k(g_bn_bwd_stats_kernel<GACT_PRELU>, g1, dim3(kT), 0, s, d, r, stats, gamma, beta, slope, g, inv, sums);
-    launch_k(g_bn_bwd_apply_kernel<GACT_PRELU>, g2, dim3(kT), 0, s, d, r, o, stats, gamma, beta, slope, g, inv, sums);
+    launch_k(g_bn_bwd_apply_kernel<GACT_PRELU>, g2, dim3(kT), 0, s, d, r, o, stats, gamma, beta, slope, g, inv, static_cast<const double*>(sums), dgamma, dbeta, dslope);
   }
-  launch_k(g_bn_param_grad_kernel, dim3((C + 127) / 128), dim3(128), 0, s, static_cast<const double*>(sums), dgamma, dbeta,
-           act == GACT_PRELU ? dslope : static_cast<float*>(nullptr), C);
   GL_CHECK();
 }
 
@@ -1142,7 +1132,7 @@ int gl_unflatten(const float* dflat, const GT& dh, cudaStream_t s) {
 }
 int gl_dense1_fwd(const float* W, const float* bias, const float* x, float* z1, int B, int K, int J, cudaStream_t s) {
   if (B > 8 || (K & 3)) return -54;
-  launch_k(g_dense1_fwd_kernel, dim3((J + 3) / 4), dim3(kT), 0, s, W, bias, x, z1, B, K, J);
+  launch_k(g_dense1_fwd_kernel, dim3((J + kD1Rows - 1) / kD1Rows), dim3(kT), 0, s, W, bias, x, z1, B, K, J);
   GL_CHECK();
 }
 int gl_dense2_fwd(const float* z1, const float* w2, const float* b2, float* prob, int B, int J, cudaStream_t s) {

@@ -15,10 +15,9 @@ int gl_pack_image(const float* nchw, const GT& out, cudaStream_t s);            
 int gl_tanh_out(const GT& z_f32, float* out_nchw, cudaStream_t s);                         // tanh(z) -> fp32 [B][3][H][W]
 int gl_tanh_bwd(const float* dout_nchw, const float* out_nchw, const GT& dz, float* dbias3, cudaStream_t s);
 // BatchNorm (batch statistics), activation, residual
+// rm / rv (may be nullptr): running statistics, updated run_times times by block 0 (conv_bias: the bias the conv dropped)
 int gl_bn_apply(const GT& raw, const GT& out, const bf16_t* res, const double* stats, const float* gamma, const float* beta,
-                int act, const float* slope, cudaStream_t s);
-int gl_bn_running(const double* stats, const float* conv_bias, float* running_mean, float* running_var, int C,
-                  double count, int times, cudaStream_t s);
+                int act, const float* slope, const float* conv_bias, float* rm, float* rv, int run_times, cudaStream_t s);
 // backward of out = act(bn(raw)): dy -> draw, dgamma / dbeta / dslope accumulated (+=); sums = scratch [2][C] + 1 doubles
 int gl_bn_bwd(const GT& dy, const GT& raw, const GT& draw, const double* stats, const float* gamma, const float* beta,
               int act, const float* slope, double* sums, float* dgamma, float* dbeta, float* dslope, cudaStream_t s);

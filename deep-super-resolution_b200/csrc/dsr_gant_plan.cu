@@ -502,7 +502,6 @@ int dsr_gant_g_forward(dsr_gant_t* p, const float* params, float* buffers, const
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   p->launches = 0;
   TapeScope scope(p, &p->tp_gf);
-  const double count = static_cast<double>(p->B) * p->lh * p->lw;
   cudaMemsetAsync(p->g_stats, 0, static_cast<size_t>(2 * p->blocks + 1) * 128 * sizeof(double), s);
   GCHK(gl_pack_image(lr_nchw, p->g_lr16, s));
   GCHK(run_fprop(p, p->g_conv1, p->g_lr16, p->g_z1, true, 0, 0.f, nullptr, s));
@@ -513,23 +512,21 @@ int dsr_gant_g_forward(dsr_gant_t* p, const float* params, float* buffers, const
     const BnL& ba = p->g_bna[k];
     const BnL& bb = p->g_bnb[k];
     GCHK(run_fprop(p, p->g_ca[k], p->g_x[k], p->g_r1[k], false, 0, 0.f, sa, s));
+    const bool upd = buffers && bn_updates > 0;
     GCHK(gl_bn_apply(p->g_r1[k], p->g_a1[k], nullptr, sa, params + ba.g_off, params + ba.b_off, GACT_PRELU,
-                     params + p->g_prelu_blk[k], s));
+                     params + p->g_prelu_blk[k], params + p->g_ca[k].b_off, upd ? buffers + ba.rm_off : nullptr,
+                     upd ? buffers + ba.rv_off : nullptr, bn_updates, s));
     GCHK(run_fprop(p, p->g_cb[k], p->g_a1[k], p->g_r2[k], false, 0, 0.f, sb, s));
     GCHK(gl_bn_apply(p->g_r2[k], p->g_x[k + 1], static_cast<const bf16_t*>(p->g_x[k].ptr), sb, params + bb.g_off,
-                     params + bb.b_off, GACT_NONE, nullptr, s));
-    if (buffers && bn_updates > 0) {
-      GCHK(gl_bn_running(sa, params + p->g_ca[k].b_off, buffers + ba.rm_off, buffers + ba.rv_off, 64, count, bn_updates, s));
-      GCHK(gl_bn_running(sb, params + p->g_cb[k].b_off, buffers + bb.rm_off, buffers + bb.rv_off, 64, count, bn_updates, s));
-    }
+                     params + bb.b_off, GACT_NONE, nullptr, params + p->g_cb[k].b_off, upd ? buffers + bb.rm_off : nullptr,
+                     upd ? buffers + bb.rv_off : nullptr, bn_updates, s));
   }
   double* st = p->g_stats + (2 * p->blocks) * 128;
   GCHK(run_fprop(p, p->g_conv2, p->g_x[p->blocks], p->g_rt, false, 0, 0.f, st, s));
+  const bool updt = buffers && bn_updates > 0;
   GCHK(gl_bn_apply(p->g_rt, p->g_t, static_cast<const bf16_t*>(p->g_x0.ptr), st, params + p->g_bn.g_off,
-                   params + p->g_bn.b_off, GACT_NONE, nullptr, s));
-  if (buffers && bn_updates > 0)
-    GCHK(gl_bn_running(st, params + p->g_conv2.b_off, buffers + p->g_bn.rm_off, buffers + p->g_bn.rv_off, 64, count,
-                       bn_updates, s));
+                   params + p->g_bn.b_off, GACT_NONE, nullptr, params + p->g_conv2.b_off,
+                   updt ? buffers + p->g_bn.rm_off : nullptr, updt ? buffers + p->g_bn.rv_off : nullptr, bn_updates, s));
   const GT* cur = &p->g_t;
   for (int j = 0; j < p->nshuf; ++j) {
     GCHK(run_fprop(p, p->g_cs[j], *cur, p->g_s[j], true, 0, 0.f, nullptr, s));
@@ -618,10 +615,9 @@ int dsr_gant_d_forward(dsr_gant_t* p, int slot, const float* params, float* buff
     const BnL& b = p->d_bn[k];
     const GT& raw = p->d_raw[slot][k];
     GCHK(run_fprop(p, p->d_c[k], *cur, raw, false, 0, 0.f, st, s));
-    GCHK(gl_bn_apply(raw, p->d_h[slot][k], nullptr, st, params + b.g_off, params + b.b_off, GACT_LRELU, nullptr, s));
-    if (buffers)
-      GCHK(gl_bn_running(st, params + p->d_c[k].b_off, buffers + b.rm_off, buffers + b.rv_off, b.C,
-                         static_cast<double>(p->B) * raw.H * raw.W, 1, s));
+    GCHK(gl_bn_apply(raw, p->d_h[slot][k], nullptr, st, params + b.g_off, params + b.b_off, GACT_LRELU, nullptr,
+                     params + p->d_c[k].b_off, buffers ? buffers + b.rm_off : nullptr, buffers ? buffers + b.rv_off : nullptr,
+                     1, s));
     cur = &p->d_h[slot][k];
   }
   GCHK(gl_flatten(*cur, p->d_flat[slot], s));

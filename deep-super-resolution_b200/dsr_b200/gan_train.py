@@ -520,6 +520,7 @@ class GanTrainStep:
             self.xch.broadcast(self.fg.flat, self.fg.bflat, self.fd.flat, self.fd.bflat)
         self.device = device
         self._pending_batches = [0, 0]
+        self._need_pack = True           # set it again after changing parameters outside do_epoch (load_state_dict)
         with torch.cuda.device(device):
             vgg.pack_into(self.tr, device)
 
@@ -541,9 +542,12 @@ class GanTrainStep:
         HR = HR_patches.to(self.device, non_blocking=True).float().contiguous()
         self.t += 1
         n0 = tr.launch_count
-        # ---- discriminator step (train_GAN.py:43-53)
-        tr.pack(NET_D, fd.flat, force=True)
-        tr.pack(NET_G, fg.flat, force=True)
+        # ---- discriminator step (train_GAN.py:43-53).  The bf16 GEMM copies of the weights are refreshed right after each
+        # Adam step below (and here on the first step / after an outside change of the parameters)
+        if self._need_pack:
+            tr.pack(NET_D, fd.flat, force=True)
+            tr.pack(NET_G, fg.flat, force=True)
+            self._need_pack = False
         p_real = tr.d_forward(0, fd.flat, fd.bflat, HR)
         fake = tr.g_forward(fg.flat, fg.bflat, LR, bn_updates=2)        # the two generator passes of do_epoch are identical
         p_fake = tr.d_forward(1, fd.flat, fd.bflat, fake)
@@ -567,6 +571,7 @@ class GanTrainStep:
         if self.dp:
             self.xch.allreduce_mean(fg.gflat)
         self._adam(fg.flat, fg.gflat, self.mG, self.vG)
+        tr.pack(NET_G, fg.flat, force=True)
         self.launches_per_step = tr.launch_count - n0
         self._pending_batches[0] += 2
         self._pending_batches[1] += 3
