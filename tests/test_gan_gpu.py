@@ -82,8 +82,10 @@ def test_generator_intermediates_match_oracle(golden):
 def test_generator_protocol_errors():
     import dsr_b200
     g = dsr_b200.Generator(8).cuda()
+    y = g(torch.rand(1, 3, 16, 16, device='cuda'))          # training mode (train_GAN.py): batch-statistics BatchNorm
+    assert y.shape == (1, 3, 128, 128) and y.requires_grad and bool(torch.isfinite(y).all())
     with pytest.raises(NotImplementedError):
-        g(torch.rand(1, 3, 16, 16, device='cuda'))           # training mode: not built
+        g(torch.rand(1, 3, 16, 16, device='cuda').requires_grad_(True))   # gradient w.r.t. the LR input is not built
     with pytest.raises(RuntimeError):
         g.eval()(torch.rand(1, 3, 16, 16))                   # CPU tensor: no fallback
     with pytest.raises(NotImplementedError):
