@@ -28,7 +28,14 @@ constexpr int kGcStages = 5;
 constexpr int kGcStageA = 128 * 128;     // 128 pixels x 64 ch x 2 B
 constexpr int kGcStageB = 128 * 128;     // up to 128 weight rows x 64 ch x 2 B
 constexpr int kGcStageBytes = kGcStageA + kGcStageB;
-constexpr int kGcSmemBytes = kGcStages * kGcStageBytes + 1024 + 256;
+// ROW-HALO mode (stride-1 convolutions, 8 x 16 pixel tiles): per tap ROW ky and 64-channel chunk ONE input box of
+// (8 + ks - 1) x 16 pixels is loaded; the ks taps of the row are column-shifted descriptor views of it (start address
+// + shift pixel rows, stride between 8-row groups = the box width; the swizzle follows the absolute shared-memory
+// address, tools/umma_probe.cu) -- L2 -> SM traffic for the input drops 2.4 x (3 x 3) / 4.5 x (9 x 9).
+constexpr int kGrStages = 3;
+constexpr int kGrMaxStage = 68 * 1024;   // 3 x 3, N = 128: 20 KB input box + 3 x 16 KB weights
+constexpr int kGcRingBytes = kGrStages * kGrMaxStage;        // 204 KB >= kGcStages * kGcStageBytes (160 KB)
+constexpr int kGcSmemBytes = kGcRingBytes + 1024 + 256;
 
 struct GTap { int8_t px, dx, py, dy; int32_t b_row; };
 
@@ -40,6 +47,8 @@ struct alignas(64) GConvParams {
   int proc_ks;             // ... or, > 0, generated: tap t = (ky, kx) = (t / ks, t % ks), offsets sign * (k - pad),
   int proc_pad, proc_sign; //     weight rows t * rows_per_tap
   int rows_per_tap;
+  int rowhalo;             // 1: row-halo mode (proc_ks taps, tw = 8, th = 16); a_slot / b_slot = bytes of a stage's parts
+  int a_slot, b_slot;
   int narrow;              // 1: K of a tap = ONE 16-channel chunk (32 B swizzle); 0: kchunks chunks of 64 (128 B swizzle)
   int kchunks;
   int nt, ntiles_n;        // UMMA N (16, 64 or 128) and number of N tiles

@@ -14,6 +14,8 @@
 #include "dsr_host.h"
 #include "dsr_launch.cuh"
 
+#include <stdlib.h>
+
 namespace dsr {
 
 __device__ __forceinline__ GTap gc_tap(const GConvParams& p, int t) {
@@ -51,12 +53,15 @@ __device__ __forceinline__ void gc_flush_stats(const GConvParams& p, int ntile, 
 __global__ void __launch_bounds__(kGcThreads, 1) gconv_kernel(const __grid_constant__ GConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kGcStages * kGcStageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kGcRingBytes);    // same offset in both modes
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kGcStages;
   uint64_t* tfull_bar = bars + 2 * kGcStages;
   uint64_t* tempty_bar = bars + 2 * kGcStages + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kGcStages + 4);
+  const int nstages = p.rowhalo ? kGrStages : kGcStages;
+  const int stage_bytes = p.rowhalo ? (p.a_slot + p.b_slot) : kGcStageBytes;
+  const int a_off = p.rowhalo ? p.a_slot : kGcStageA;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -77,6 +82,7 @@ __global__ void __launch_bounds__(kGcThreads, 1) gconv_kernel(const __grid_const
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], 4);
     }
+    (void)nstages;
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -98,6 +104,23 @@ __global__ void __launch_bounds__(kGcThreads, 1) gconv_kernel(const __grid_const
         const int ntile = item / ntiles_pix;
         const int x0 = (tile % p.tiles_x) * p.tw;
         const int y0 = (tile / p.tiles_x) * p.th;
+        if (p.rowhalo) {
+          const int ks = p.proc_ks;
+          const uint32_t box_bytes = static_cast<uint32_t>((8 + ks - 1) * 16) * (p.narrow ? 32u : 128u);
+          for (int ky = 0; ky < ks; ++ky) {
+            for (int kc = 0; kc < kper; ++kc) {
+              mbar_wait(&empty_bar[stage], phase ^ 1, p.err, 21);
+              uint8_t* sa = smem + stage * stage_bytes;
+              uint8_t* sb = sa + a_off;
+              mbar_arrive_expect_tx(&full_bar[stage], box_bytes + static_cast<uint32_t>(ks) * b_bytes);
+              tma_load_5d(&p.a, &full_bar[stage], sa, kc * 64, 0, x0 - p.proc_pad, 0, y0 + p.proc_sign * (ky - p.proc_pad));
+              for (int kx = 0; kx < ks; ++kx)
+                tma_load_2d(&p.b, &full_bar[stage], sb + kx * b_bytes, kc * 64, (ky * ks + kx) * p.rows_per_tap + ntile * p.nt);
+              if (++stage == kGrStages) { stage = 0; phase ^= 1; }
+            }
+          }
+          continue;
+        }
         for (int t = 0; t < p.ntaps; ++t) {
           const GTap tp = gc_tap(p, t);
           for (int kc = 0; kc < kper; ++kc) {
@@ -119,13 +142,47 @@ __global__ void __launch_bounds__(kGcThreads, 1) gconv_kernel(const __grid_const
     const uint64_t hi_w = make_smem_desc(0, 16, 1024, SWZ_128B);
     const uint64_t hi_n = make_smem_desc(0, 16, 256, SWZ_32B);
     const uint64_t hi = p.narrow ? hi_n : hi_w;
-    const int nk = p.ntaps * kper;
+    const int nk = p.rowhalo ? p.proc_ks * kper : p.ntaps * kper;
+    const uint32_t rowb = p.narrow ? 32u : 128u;
+    // row-halo views: 8-row groups are one box row (8 + ks - 1 pixels) apart
+    const uint64_t hi_r = make_smem_desc(0, 16, static_cast<uint32_t>(8 + p.proc_ks - 1) * rowb, p.narrow ? SWZ_32B : SWZ_128B);
     for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       mbar_wait(&tempty_bar[as], aphase ^ 1, p.err, 22);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * 128);
+      if (p.rowhalo) {
+        const int ks = p.proc_ks;
+        for (int k = 0; k < nk; ++k) {
+          mbar_wait(&full_bar[stage], phase, p.err, 23);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+          const uint32_t sb = sa + static_cast<uint32_t>(a_off);
+          for (int kx = 0; kx < ks; ++kx) {
+            const uint32_t shift = static_cast<uint32_t>(p.proc_sign > 0 ? kx : ks - 1 - kx);
+            const uint64_t da = hi_r | static_cast<uint64_t>(((sa + shift * rowb) & 0x3FFFF) >> 4);
+            const uint64_t db = hi | static_cast<uint64_t>(((sb + static_cast<uint32_t>(kx) * b_bytes) & 0x3FFFF) >> 4);
+            if (elect_one()) {
+              if (!p.narrow) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  umma_f16(tmem_d, da + static_cast<uint64_t>(j * 2), db + static_cast<uint64_t>(j * 2), p.idesc, (k | kx | j) != 0);
+              } else {
+                umma_f16(tmem_d, da, db, p.idesc, (k | kx) != 0);
+              }
+            }
+            __syncwarp();
+          }
+          if (elect_one()) {
+            umma_commit(&empty_bar[stage]);
+            if (k == nk - 1) umma_commit(&tfull_bar[as]);
+          }
+          __syncwarp();
+          if (++stage == kGrStages) { stage = 0; phase ^= 1; }
+        }
+        continue;
+      }
       for (int k = 0; k < nk; ++k) {
         mbar_wait(&full_bar[stage], phase, p.err, 23);
         tc_fence_after();
@@ -444,6 +501,17 @@ int make_gconv_fprop(GConvParams* g, const GT& in, const GT& out, const void* w_
   g->ntiles_n = cout_pad / g->nt;
   pick_tile(out.W, &g->tw, &g->th);
   int rc;
+  const int rowb = g->narrow ? 32 : 128;
+  g->rowhalo = (stride == 1 && (out.W % 8) == 0 && !getenv("DSR_GANT_NO_ROWHALO")) ? 1 : 0;
+  if (g->rowhalo) {
+    g->tw = 8; g->th = 16;
+    g->a_slot = (((8 + ks - 1) * 16 * rowb) + 1023) & ~1023;
+    g->b_slot = ((ks * g->nt * rowb) + 1023) & ~1023;
+    if (g->a_slot + g->b_slot > kGrMaxStage) g->rowhalo = 0;
+  }
+  if (g->rowhalo) {
+    if ((rc = make_act_map(&g->a, in.ptr, 1, in.C, in.W, in.rows(), 1, g->narrow ? 16 : 64, 8 + ks - 1, 16))) return rc;
+  } else
   if ((rc = make_act_map(&g->a, in.ptr, 1, in.C, in.W, in.rows(), stride, g->narrow ? 16 : 64, g->tw, g->th))) return rc;
   if ((rc = make_wgt_map(&g->b, w_pack, cin_pad, ks * ks * cout_pad, g->narrow ? 16 : 64, g->nt))) return rc;
   g->ntaps = ks * ks;
@@ -491,6 +559,17 @@ int make_gconv_dgrad(GConvParams* g, int* nlaunch, const GT& dy, const GT& dx, c
     q->ntiles_n = cin_pad / q->nt;
     pick_tile(dy.W, &q->tw, &q->th);
     int rc;
+    const int rowb = q->narrow ? 32 : 128;
+    q->rowhalo = (stride == 1 && (dy.W % 8) == 0 && !getenv("DSR_GANT_NO_ROWHALO")) ? 1 : 0;
+    if (q->rowhalo) {
+      q->tw = 8; q->th = 16;
+      q->a_slot = (((8 + ks - 1) * 16 * rowb) + 1023) & ~1023;
+      q->b_slot = ((ks * q->nt * rowb) + 1023) & ~1023;
+      if (q->a_slot + q->b_slot > kGrMaxStage) q->rowhalo = 0;
+    }
+    if (q->rowhalo) {
+      if ((rc = make_act_map(&q->a, dy.ptr, 1, dy.C, dy.W, dy.rows(), 1, q->narrow ? 16 : 64, 8 + ks - 1, 16))) return rc;
+    } else
     if ((rc = make_act_map(&q->a, dy.ptr, 1, dy.C, dy.W, dy.rows(), 1, q->narrow ? 16 : 64, q->tw, q->th))) return rc;
     if ((rc = make_wgt_map(&q->b, w_pack_d, cout_pad, ks * ks * cin_pad, q->narrow ? 16 : 64, q->nt))) return rc;
     if (stride == 1) {
