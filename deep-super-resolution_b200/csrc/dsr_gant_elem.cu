@@ -666,8 +666,9 @@ __global__ void g_unflatten_kernel(const float* __restrict__ dflat, bf16_t* __re
   }
 }
 
-// z1[b][j] = bias[j] + sum_k W[j][k] x[b][k]; a block owns kD1Rows rows of W (read once, fp32, streaming), B <= 8
-constexpr int kD1Rows = 8;
+// z1[b][j] = bias[j] + sum_k W[j][k] x[b][k].  grid (J / kD1Rows, kD1KSplit): a block owns kD1Rows rows of W (fp32,
+// streamed once) and a quarter of the columns; partial sums are added atomically into z1 (zeroed first), B <= 8
+constexpr int kD1Rows = 8, kD1KSplit = 4;
 __global__ void __launch_bounds__(kT) g_dense1_fwd_kernel(const float* __restrict__ W, const float* __restrict__ bias,
                                                           const float* __restrict__ x, float* __restrict__ z1, int B, int K,
                                                           int J) {
@@ -680,7 +681,9 @@ __global__ void __launch_bounds__(kT) g_dense1_fwd_kernel(const float* __restric
 #pragma unroll
     for (int b = 0; b < 8; ++b) acc[r][b] = 0.f;
   const int k4n = K >> 2;
-  for (int k4 = threadIdx.x; k4 < k4n; k4 += kT) {
+  const int kb = static_cast<int>((static_cast<long long>(k4n) * blockIdx.y) / gridDim.y);
+  const int ke = static_cast<int>((static_cast<long long>(k4n) * (blockIdx.y + 1)) / gridDim.y);
+  for (int k4 = kb + threadIdx.x; k4 < ke; k4 += kT) {
     float4 w[kD1Rows];
 #pragma unroll
     for (int r = 0; r < kD1Rows; ++r)
@@ -710,7 +713,8 @@ __global__ void __launch_bounds__(kT) g_dense1_fwd_kernel(const float* __restric
     const int r = threadIdx.x >> 3, b = threadIdx.x & 7;
     float v = 0.f;
     for (int w = 0; w < 8; ++w) v += sm[w][threadIdx.x];
-    if (j0 + r < J && b < B) z1[b * J + j0 + r] = v + bias[j0 + r];
+    if (blockIdx.y == 0 && j0 + r < J) v += bias[j0 + r];
+    if (j0 + r < J && b < B) atomicAdd(&z1[b * J + j0 + r], v);
   }
 }
 
@@ -1132,7 +1136,8 @@ int gl_unflatten(const float* dflat, const GT& dh, cudaStream_t s) {
 }
 int gl_dense1_fwd(const float* W, const float* bias, const float* x, float* z1, int B, int K, int J, cudaStream_t s) {
   if (B > 8 || (K & 3)) return -54;
-  launch_k(g_dense1_fwd_kernel, dim3((J + kD1Rows - 1) / kD1Rows), dim3(kT), 0, s, W, bias, x, z1, B, K, J);
+  cudaMemsetAsync(z1, 0, static_cast<size_t>(B) * J * sizeof(float), s);
+  launch_k(g_dense1_fwd_kernel, dim3((J + kD1Rows - 1) / kD1Rows, kD1KSplit), dim3(kT), 0, s, W, bias, x, z1, B, K, J);
   GL_CHECK();
 }
 int gl_dense2_fwd(const float* z1, const float* w2, const float* b2, float* prob, int B, int J, cudaStream_t s) {
