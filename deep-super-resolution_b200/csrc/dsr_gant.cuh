@@ -59,8 +59,8 @@ struct alignas(64) GConvParams {
   int ox_mul, ox_add, oy_mul, oy_add;
   int out_w, out_h, out_period, out_rows;
   int out_c;               // channel pitch of the output tensor
-  void* out;               // bf16, or fp32 when out_f32
-  int out_f32;
+  void* out;               // bf16, or fp32 when out_f32, or fp16 when out_f16 (the VGG19 forward pass)
+  int out_f32, out_f16;
   const float* bias;       // [ntiles_n * nt] or nullptr
   const bf16_t* addend;    // tensor with the output's addressing added before the activation / mask, or nullptr
   const bf16_t* mask;      // data gradient through (Leaky)ReLU: value *= (mask > 0 ? 1 : slope); or nullptr
@@ -102,12 +102,13 @@ struct GT {                // tall-grid tensor
   void* ptr = nullptr;
   int C = 0, W = 0, H = 0, P = 0, B = 0;
   int f32 = 0;
+  int f16 = 0;             // 16-bit elements are IEEE half instead of bf16 (VGG19 forward activations)
   int rows() const { return B * P; }
   size_t bytes() const { return static_cast<size_t>(rows()) * W * C * (f32 ? 4 : 2); }
 };
 
 int make_gconv_fprop(GConvParams* g, const GT& in, const GT& out, const void* w_pack, int cin_pad, int cout_pad, int ks,
-                     int stride, int* err);
+                     int stride, int* err);   // operand format (bf16 / fp16) follows in.f16
 int make_gconv_dgrad(GConvParams* g, int* nlaunch, const GT& dy, const GT& dx, const void* w_pack_d, int cin_pad,
                      int cout_pad, int ks, int stride, int* err);
 int make_gwgrad(GWgradParams* g, const GT& dy, const GT& x, float* dw, int cin, int cout, int stride, int num_sms,

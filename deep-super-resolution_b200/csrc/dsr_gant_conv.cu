@@ -283,12 +283,22 @@ __global__ void __launch_bounds__(kGcThreads, 1) gconv_kernel(const __grid_const
             }
           } else {
             uint32_t packed[8];
+            if (p.out_f16) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-              packed[i] = *reinterpret_cast<uint32_t*>(&h);
-              f[2 * i] = __low2float(h);
-              f[2 * i + 1] = __high2float(h);
+              for (int i = 0; i < 8; ++i) {
+                __half2 h = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+                packed[i] = *reinterpret_cast<uint32_t*>(&h);
+                f[2 * i] = __low2float(h);
+                f[2 * i + 1] = __high2float(h);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+                packed[i] = *reinterpret_cast<uint32_t*>(&h);
+                f[2 * i] = __low2float(h);
+                f[2 * i + 1] = __high2float(h);
+              }
             }
             if (valid) {
               uint4* dst = reinterpret_cast<uint4*>(static_cast<bf16_t*>(p.out) + obase + c * 16);
@@ -534,7 +544,9 @@ int make_gconv_fprop(GConvParams* g, const GT& in, const GT& out, const void* w_
   g->out_c = out.C;
   g->out = out.ptr;
   g->out_f32 = out.f32;
-  g->idesc = make_idesc_f16(128, g->nt, FMT_BF16, FMT_BF16, 0, 0);
+  g->out_f16 = out.f16;
+  if (in.f16 != out.f16 && !out.f32) return -50;
+  g->idesc = in.f16 ? make_idesc_f16(128, g->nt, FMT_F16, FMT_F16, 0, 0) : make_idesc_f16(128, g->nt, FMT_BF16, FMT_BF16, 0, 0);
   g->err = err;
   return 0;
 }

@@ -5,6 +5,8 @@
 // dense head of the discriminator, BCE, weight packing and the weight gradients of the 3-channel layers.
 // Tensor convention: dsr_gant.cuh (bf16 NHWC tall grid, gap rows never written).
 #include "dsr_gant_elem.cuh"
+#include <cuda_fp16.h>
+
 #include "dsr_launch.cuh"
 
 namespace dsr {
@@ -34,6 +36,19 @@ __device__ __forceinline__ void store8(bf16_t* p, const float (&f)[8]) {
   __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&q);
 #pragma unroll
   for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = q;
+}
+__device__ __forceinline__ void load8h(const bf16_t* p, float (&f)[8]) {       // the same 16 bytes read as IEEE half
+  const uint4 q = *reinterpret_cast<const uint4*>(p);
+  const __half2* h = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { f[2 * i] = __low2float(h[i]); f[2 * i + 1] = __high2float(h[i]); }
+}
+__device__ __forceinline__ void store8h(bf16_t* p, const float (&f)[8]) {
+  uint4 q;
+  __half2* h = reinterpret_cast<__half2*>(&q);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
   *reinterpret_cast<uint4*>(p) = q;
 }
 inline int grid_for(long long items, int per_sm = 4) {
@@ -465,7 +480,7 @@ __device__ __forceinline__ void bil_src(int d, float scale, int n, int* i0, int*
 }
 
 __global__ void g_vgg_pre_fwd_kernel(const float* __restrict__ img, bf16_t* __restrict__ out, TG g, int Hi, int Wi, int Hr,
-                                     int Wr, int top, int left) {
+                                     int Wr, int top, int left, int f16) {
   pdl_sync();
   const float sy = static_cast<float>(Hi) / static_cast<float>(Hr), sx = static_cast<float>(Wi) / static_cast<float>(Wr);
   const long long np = static_cast<long long>(g.B) * g.H * g.W;
@@ -488,7 +503,8 @@ __global__ void g_vgg_pre_fwd_kernel(const float* __restrict__ img, bf16_t* __re
     }
     const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     bf16_t* o = out + tg_pix_off(g, q);
-    store8(o, f);
+    if (f16) store8h(o, f);
+    else store8(o, f);
     store8(o + 8, z);
   }
 }
@@ -598,7 +614,7 @@ __global__ void g_maxpool_bwd_kernel(const bf16_t* __restrict__ dout, const bf16
 
 // loss_acc += sum (f1 - f2)^2 ;  dz = 2 (f1 - f2) / N * [f1 > 0]   (nn.MSELoss on the relu5_4 maps + the ReLU in front)
 __global__ void g_feat_mse_kernel(const bf16_t* __restrict__ f1, const bf16_t* __restrict__ f2, bf16_t* __restrict__ dz, TG g,
-                                  float two_over_n, double* __restrict__ loss_acc) {
+                                  float two_over_n, double* __restrict__ loss_acc, int f16) {
   __shared__ float sm[kT];
   pdl_sync();
   const int g8 = g.C >> 3;
@@ -608,8 +624,8 @@ __global__ void g_feat_mse_kernel(const bf16_t* __restrict__ f1, const bf16_t* _
     const long long q = i / g8;
     const long long off = tg_pix_off(g, q) + static_cast<int>(i - q * g8) * 8;
     float a[8], b[8];
-    load8(f1 + off, a);
-    load8(f2 + off, b);
+    if (f16) { load8h(f1 + off, a); load8h(f2 + off, b); }
+    else { load8(f1 + off, a); load8(f2 + off, b); }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float d = a[j] - b[j];
@@ -843,7 +859,7 @@ __global__ void g_bce_kernel(const float* __restrict__ prob, float target, int B
 // ---------------------------------------------------------------------------------------------
 __global__ void g_pack_weight_kernel(const float* __restrict__ w, const float* __restrict__ bias, int cout, int cin, int ks,
                                      int cout_pad, int cin_pad, bf16_t* __restrict__ w_f, bf16_t* __restrict__ w_d,
-                                     float* __restrict__ bias_pad) {
+                                     float* __restrict__ bias_pad, int f16_fwd) {
   pdl_sync();
   const long long total = static_cast<long long>(ks) * ks * cout_pad * cin_pad;
   for (long long i = static_cast<long long>(blockIdx.x) * kT + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * kT) {
@@ -854,7 +870,10 @@ __global__ void g_pack_weight_kernel(const float* __restrict__ w, const float* _
     float v = 0.f;
     if (co < cout && ci < cin) v = w[(static_cast<long long>(co) * cin + ci) * ks * ks + tap];
     const bf16_t h = __float2bfloat16_rn(v);
-    if (w_f != nullptr) w_f[i] = h;
+    if (w_f != nullptr) {
+      if (f16_fwd) reinterpret_cast<__half*>(w_f)[i] = __float2half_rn(v);
+      else w_f[i] = h;
+    }
     if (w_d != nullptr) w_d[(static_cast<long long>(tap) * cin_pad + ci) * cout_pad + co] = h;
     if (bias_pad != nullptr && tap == 0 && ci == 0) bias_pad[co] = (bias != nullptr && co < cout) ? bias[co] : 0.f;
   }
@@ -1091,7 +1110,7 @@ int gl_chan_sum(const GT& t, float* out_c, cudaStream_t s) {
 
 int gl_vgg_pre_fwd(const float* img, int Hi, int Wi, int Hr, int Wr, int top, int left, const GT& out, cudaStream_t s) {
   launch_k(g_vgg_pre_fwd_kernel, dim3(grid_for(static_cast<long long>(out.B) * out.H * out.W)), dim3(kT), 0, s, img,
-           static_cast<bf16_t*>(out.ptr), tg_of(out), Hi, Wi, Hr, Wr, top, left);
+           static_cast<bf16_t*>(out.ptr), tg_of(out), Hi, Wi, Hr, Wr, top, left, out.f16);
   GL_CHECK();
 }
 int gl_vgg_pre_bwd(const GT& dpre, int Hi, int Wi, int Hr, int Wr, int top, int left, float* dimg, int accumulate,
@@ -1116,7 +1135,7 @@ int gl_maxpool_bwd(const GT& dout, const GT& y_in, const GT& dz_in, cudaStream_t
 int gl_feat_mse(const GT& f1, const GT& f2, const GT& dz, double* loss_acc, cudaStream_t s) {
   const long long n = static_cast<long long>(f1.B) * f1.H * f1.W * f1.C;
   launch_k(g_feat_mse_kernel, dim3(grid_for(n / 8, 2)), dim3(kT), 0, s, static_cast<const bf16_t*>(f1.ptr),
-           static_cast<const bf16_t*>(f2.ptr), static_cast<bf16_t*>(dz.ptr), tg_of(f1), 2.f / static_cast<float>(n), loss_acc);
+           static_cast<const bf16_t*>(f2.ptr), static_cast<bf16_t*>(dz.ptr), tg_of(f1), 2.f / static_cast<float>(n), loss_acc, f1.f16);
   GL_CHECK();
 }
 int gl_finish_double(const double* acc, float* out, float scale, int accumulate, cudaStream_t s) {
@@ -1165,9 +1184,9 @@ int gl_bce(const float* prob, float target, int B, float* loss_out, int accumula
 }
 
 int gl_pack_weight(const float* w, const float* bias, int cout, int cin, int ks, int cout_pad, int cin_pad, bf16_t* w_f,
-                   bf16_t* w_d, float* bias_pad, cudaStream_t s) {
+                   bf16_t* w_d, float* bias_pad, int f16_fwd, cudaStream_t s) {
   launch_k(g_pack_weight_kernel, dim3(grid_for(static_cast<long long>(ks) * ks * cout_pad * cin_pad)), dim3(kT), 0, s, w,
-           bias, cout, cin, ks, cout_pad, cin_pad, w_f, w_d, bias_pad);
+           bias, cout, cin, ks, cout_pad, cin_pad, w_f, w_d, bias_pad, f16_fwd);
   GL_CHECK();
 }
 int gl_unpack_wgrad(const float* dw_pack, float* g, int cout, int cin, int ks, cudaStream_t s) {

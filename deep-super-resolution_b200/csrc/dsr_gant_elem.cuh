@@ -50,7 +50,7 @@ int gl_dense1_bwd(const float* W, const float* x, const float* dz1, float* dW, f
 int gl_bce(const float* prob, float target, int B, float* loss_out, int accumulate, cudaStream_t s);
 // weights
 int gl_pack_weight(const float* w_oihw, const float* bias, int cout, int cin, int ks, int cout_pad, int cin_pad,
-                   bf16_t* w_f, bf16_t* w_d, float* bias_pad, cudaStream_t s);
+                   bf16_t* w_f, bf16_t* w_d, float* bias_pad, int f16_fwd, cudaStream_t s);   // f16_fwd: w_f as IEEE half
 int gl_unpack_wgrad(const float* dw_pack, float* g_oihw, int cout, int cin, int ks, cudaStream_t s);
 // CUDA-core weight gradients of the 3-channel layers
 int gl_wgrad_in3(const GT& dy64, const GT& x16, float* g_oihw, int ks, cudaStream_t s);     // dW[64][3][ks][ks] +=

@@ -262,24 +262,32 @@ size_t layout(dsr_gant* p, uint8_t* base) {
   // ---------------- VGG19 ----------------
   if (p->with_vgg) {
     int h = 224, w = 224;
+    // The VGG19 FORWARD pass runs in fp16 (tensors marked f16, fp16 weight copies): the content loss is a difference
+    // of two nearly equal feature maps, so the 3 extra mantissa bits matter (gradient w.r.t. the image: cosine 0.79
+    // with bf16 features at 192 x 192); the frozen network has no weight gradient, so no kernel
+    // ever mixes the fp16 activations with the bf16 gradients of the backward chain.
     p->v_pre = mk(a, 16, w, h, h + 2, B);
+    p->v_pre.f16 = 1;
     p->v_dpre = mk(a, 16, w, h, h + 2, B, 1);
     p->v_y.resize(16); p->v_pool.clear(); p->v_dpool.clear(); p->v_ga.clear(); p->v_gb.clear();
     int level_c = 64;
     for (int i = 0; i < 16; ++i) {
       p->v_y[i] = mk(a, kVggCout[i], w, h, h + 2, B);
+      p->v_y[i].f16 = 1;
       level_c = kVggCout[i];
       if (kVggPoolAfter[i]) {
         p->v_ga.push_back(mk(a, level_c, w, h, h + 2, B));
         p->v_gb.push_back(mk(a, level_c, w, h, h + 2, B));
         h /= 2; w /= 2;
         p->v_pool.push_back(mk(a, level_c, w, h, h + 2, B));
+        p->v_pool.back().f16 = 1;
         p->v_dpool.push_back(mk(a, level_c, w, h, h + 2, B));
       }
     }
     p->v_ga.push_back(mk(a, 512, w, h, h + 2, B));
     p->v_gb.push_back(mk(a, 512, w, h, h + 2, B));
     p->v_freal = mk(a, 512, w, h, h + 2, B);
+    p->v_freal.f16 = 1;
     for (int i = 0; i < 16; ++i) {
       p->v_c[i].need_d = true;
       layout_pack(a, p->v_c[i]);
@@ -349,9 +357,9 @@ struct TapeScope {                       // selects an entry point's tape; marks
     p->tape = nullptr;
   }
 };
-int pack_conv(const ConvL& c, const float* params, bool with_bias, cudaStream_t s) {
+int pack_conv(const ConvL& c, const float* params, bool with_bias, cudaStream_t s, int f16_fwd = 0) {
   return gl_pack_weight(params + c.w_off, with_bias ? params + c.b_off : nullptr, c.cout, c.cin, c.ks, c.cout_pad, c.cin_pad,
-                        c.w_f, c.w_d, c.bias_pad, s);
+                        c.w_f, c.w_d, c.bias_pad, f16_fwd, s);
 }
 
 }  // namespace
@@ -487,7 +495,7 @@ int dsr_gant_pack(dsr_gant_t* p, int net, const float* params, void* stream) {
     for (int k = 0; k < 7; ++k) GCHK(pack_conv(p->d_c[k], params, false, s));
   } else {
     if (!p->with_vgg) return -5;
-    for (int i = 0; i < 16; ++i) GCHK(pack_conv(p->v_c[i], params, true, s));
+    for (int i = 0; i < 16; ++i) GCHK(pack_conv(p->v_c[i], params, true, s, 1));    // forward copies in fp16 (see layout)
   }
   return 0;
 }
@@ -755,7 +763,7 @@ int dsr_gant_tensor(const dsr_gant_t* p, const char* name, void** ptr, int* C, i
   if (H) *H = t->H;
   if (P) *P = t->P;
   if (B) *B = t->B;
-  if (f32) *f32 = t->f32;
+  if (f32) *f32 = t->f32 ? 1 : (t->f16 ? 2 : 0);     // 0 bf16, 1 fp32, 2 fp16
   return 0;
 }
 

@@ -129,7 +129,7 @@ class Trainer:
         cc, w, h, p, b, f32 = (C.c_int() for _ in range(6))
         check(lib.dsr_gant_tensor(self.handle, name.encode(), C.byref(ptr), C.byref(cc), C.byref(w), C.byref(h), C.byref(p),
                                   C.byref(b), C.byref(f32)), f'dsr_gant_tensor({name})')
-        dt = torch.float32 if f32.value else torch.bfloat16
+        dt = {0: torch.bfloat16, 1: torch.float32, 2: torch.float16}[f32.value]
         t = torch.empty((b.value * p.value, w.value, cc.value), dtype=dt, device=self.device)
         check(lib.dsr_debug_copy(t.data_ptr(), ptr, t.numel() * t.element_size(), _lib.stream_ptr()), 'dsr_debug_copy')
         return t.view(b.value, p.value, w.value, cc.value)[:, :h.value].float()

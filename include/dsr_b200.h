@@ -248,7 +248,8 @@ int dsr_gant_vgg_loss(dsr_gant_t* p, const float* fake_nchw, const float* real_n
                       float* dfake_nchw, void* stream);
 int dsr_gant_device_error(dsr_gant_t* p, int* host_code);
 int dsr_gant_last_launches(const dsr_gant_t* p);
-/* Tests: a named activation of the last pass (bf16 / fp32 [B * P][W][C] tall grid, image b at rows [b P, b P + H)). */
+/* Tests: a named activation of the last pass ([B * P][W][C] tall grid, image b at rows [b P, b P + H)); *f32 receives
+ * the element type: 0 bf16, 1 fp32, 2 fp16. */
 int dsr_gant_tensor(const dsr_gant_t* p, const char* name, void** ptr, int* C, int* W, int* H, int* P, int* B, int* f32);
 
 #ifdef __cplusplus
