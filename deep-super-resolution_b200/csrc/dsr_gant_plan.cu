@@ -264,7 +264,7 @@ size_t layout(dsr_gant* p, uint8_t* base) {
     int h = 224, w = 224;
     // The VGG19 FORWARD pass runs in fp16 (tensors marked f16, fp16 weight copies): the content loss is a difference
     // of two nearly equal feature maps, so the 3 extra mantissa bits matter (gradient w.r.t. the image: cosine 0.79
-    // with bf16 features at 192 x 192, see DESIGN.md 11); the frozen network has no weight gradient, so no kernel
+    // with bf16 features at 192 x 192, see DESIGN.md 10); the frozen network has no weight gradient, so no kernel
     // ever mixes the fp16 activations with the bf16 gradients of the backward chain.
     p->v_pre = mk(a, 16, w, h, h + 2, B);
     p->v_pre.f16 = 1;

@@ -1,6 +1,6 @@
 """SRGAN training step on the GPU (BASELINE configs[4]) against the oracle, the reference
 fixtures and the reference's own training loop.  bf16 operands / fp32 accumulation: the gates are the measured bf16
-class (DESIGN.md 11), stated per assertion."""
+class (DESIGN.md 10), stated per assertion."""
 import json
 import os
 import subprocess
