@@ -464,6 +464,7 @@ def run_ours(args, rank, local_rank, world):
                                                'in our e2e arm'} if 'value' in g else g)
         if not args.no_secondary:
             line['secondary'] = secondary_gan_eval(dev)
+            line['secondary_gan_train'] = secondary_gan_train(dev)
     print(json.dumps(line), flush=True)
 
 
@@ -897,6 +898,37 @@ def run_gan_train(args, rank, local_rank, world):
     line['gpu_launches'] = step.launches_per_step * args.steps
     print(json.dumps(line), flush=True)
 
+
+
+def secondary_gan_train(dev):
+    """BASELINE configs[4] beside the headline: a short single-GPU run of the fused SRGAN training step (batch 8 of
+    24x24 -> 192x192 patches, random-weight VGG19); the full line incl. data parallelism is `--workload gan_train`."""
+    try:
+        from oracle import gan_train_oracle as O          # harness only: the synthetic LR / HR batch recipe
+        G, D, V, GT = _gan_train_objects(dev, 0)
+        step = GT.GanTrainStep(G, D, V, 1e-4, GT_B, (GT_LR, GT_LR), dev)
+        LR, HR = O.synthetic_batch(100, GT_B, (GT_LR, GT_LR), 8)
+        LR, HR = LR.to(dev), HR.to(dev)
+        steps = 10
+        for _ in range(3):
+            step.do_epoch(LR, HR)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step.do_epoch(LR, HR)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        pk = peaks()
+        tf = GT_FLOPS_PER_PATCH * GT_B / (ms * 1e-3) / 1e12
+        return {'workload': f'SRGAN training step (train_GAN.do_epoch), batch {GT_B} of {GT_LR}x{GT_LR} -> 192x192 patches, '
+                            f'random-weight VGG19 (BASELINE configs[4]), {steps} steps', 'value': GT_B / (ms * 1e-3),
+                'unit': 'patches/s', 'ms_per_step': ms, 'tflops': tf,
+                'frac_of_burst_bf16': tf / pk['tflops'] if pk['tflops'] else None,
+                'gpu_launches_per_step': step.launches_per_step}
+    except Exception as e:                                 # never let the secondary figure take the headline down
+        return {'workload': 'SRGAN training step', 'error': repr(e)[:200]}
 
 
 def secondary_gan_eval(dev):

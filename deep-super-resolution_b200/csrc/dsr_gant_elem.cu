@@ -784,60 +784,71 @@ __global__ void g_dense2_bwd_kernel(const float* __restrict__ prob, const float*
   }
 }
 
-// dW[j][k] += sum_b dz1[b][j] x[b][k];  dx[b][k] = sum_j dz1[b][j] W[j][k];  db1[j] += sum_b dz1[b][j].
-// grid (ceil(K / 1024), JS): a block owns 1024 columns and J / JS rows; dx partials are added atomically (dx zeroed first)
+// dW[j][k] += sum_b dz1[b][j] x[b][k];  dx[b][k] = sum_j dz1[b][j] W[j][k];  db1[j] += sum_b dz1[b][j], for NG groups
+// of B <= 8 samples in ONE sweep over W / dW (the real and the fake pass of do_epoch: the 302 MB matrix and its gradient
+// are streamed once instead of twice).  grid (ceil(K / 1024), JS): a block owns 1024 columns and J / JS rows; dx
+// partials are added atomically (dx zeroed first).
 constexpr int kD1Split = 8;
-__global__ void __launch_bounds__(kT) g_dense1_bwd_kernel(const float* __restrict__ W, const float* __restrict__ x,
-                                                          const float* __restrict__ dz1, float* __restrict__ dW,
-                                                          float* __restrict__ db1, float* __restrict__ dx, int B, int K,
+struct D1Grp { const float* x; const float* dz1; float* dx; };
+template <int NG>
+__global__ void __launch_bounds__(kT) g_dense1_bwd_kernel(const float* __restrict__ W, D1Grp g0, D1Grp g1,
+                                                          float* __restrict__ dW, float* __restrict__ db1, int B, int K,
                                                           int J) {
-  extern __shared__ float dzs[];                 // [jn][8]
+  extern __shared__ float dzs[];                 // [jn][8 * NG]
   pdl_sync();
+  const D1Grp grp[2] = {g0, g1};
   const int jn = (J + kD1Split - 1) / kD1Split;
   const int jb = blockIdx.y * jn;
   const int je = (jb + jn < J) ? jb + jn : J;
-  for (int i = threadIdx.x; i < jn * 8; i += kT) {
-    const int j = jb + (i >> 3), b = i & 7;
-    dzs[i] = (j < J && b < B) ? dz1[b * J + j] : 0.f;
+  for (int i = threadIdx.x; i < jn * 8 * NG; i += kT) {
+    const int j = jb + i / (8 * NG), r = i % (8 * NG), g = r >> 3, b = r & 7;
+    dzs[i] = (j < J && b < B) ? grp[g].dz1[b * J + j] : 0.f;
   }
   __syncthreads();
   if (blockIdx.x == 0) {
     for (int j = jb + threadIdx.x; j < je; j += kT) {
       float t = 0.f;
-      for (int b = 0; b < 8; ++b) t += dzs[(j - jb) * 8 + b];
+      for (int b = 0; b < 8 * NG; ++b) t += dzs[(j - jb) * 8 * NG + b];
       db1[j] += t;
     }
   }
   const int k4 = blockIdx.x * kT + threadIdx.x;
   if (k4 * 4 >= K) return;
-  float4 xv[8], da[8];
+  float4 xv[NG][8], da[NG][8];
 #pragma unroll
-  for (int b = 0; b < 8; ++b) {
-    xv[b] = (b < B) ? __ldg(reinterpret_cast<const float4*>(x + static_cast<long long>(b) * K) + k4) : make_float4(0.f, 0.f, 0.f, 0.f);
-    da[b] = make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-  for (int j = jb; j < je; ++j) {
-    const float4 w = __ldg(reinterpret_cast<const float4*>(W + static_cast<long long>(j) * K) + k4);
-    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float* dzj = &dzs[(j - jb) * 8];
+  for (int g = 0; g < NG; ++g)
 #pragma unroll
     for (int b = 0; b < 8; ++b) {
-      const float d = dzj[b];
-      da[b].x += d * w.x; da[b].y += d * w.y; da[b].z += d * w.z; da[b].w += d * w.w;
-      g.x += d * xv[b].x; g.y += d * xv[b].y; g.z += d * xv[b].z; g.w += d * xv[b].w;
+      xv[g][b] = (b < B) ? __ldg(reinterpret_cast<const float4*>(grp[g].x + static_cast<long long>(b) * K) + k4)
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
+      da[g][b] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
+  for (int j = jb; j < je; ++j) {
+    const float4 w = __ldcs(reinterpret_cast<const float4*>(W + static_cast<long long>(j) * K) + k4);
+    float4 gsum = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* dzj = &dzs[(j - jb) * 8 * NG];
+#pragma unroll
+    for (int g = 0; g < NG; ++g)
+#pragma unroll
+      for (int b = 0; b < 8; ++b) {
+        const float d = dzj[g * 8 + b];
+        da[g][b].x += d * w.x; da[g][b].y += d * w.y; da[g][b].z += d * w.z; da[g][b].w += d * w.w;
+        gsum.x += d * xv[g][b].x; gsum.y += d * xv[g][b].y; gsum.z += d * xv[g][b].z; gsum.w += d * xv[g][b].w;
+      }
     float4* gp = reinterpret_cast<float4*>(dW + static_cast<long long>(j) * K) + k4;
     float4 o = *gp;
-    o.x += g.x; o.y += g.y; o.z += g.z; o.w += g.w;
+    o.x += gsum.x; o.y += gsum.y; o.z += gsum.z; o.w += gsum.w;
     *gp = o;
   }
 #pragma unroll
-  for (int b = 0; b < 8; ++b) {
-    if (b < B) {
-      float* o = dx + static_cast<long long>(b) * K + k4 * 4;
-      atomicAdd(o, da[b].x); atomicAdd(o + 1, da[b].y); atomicAdd(o + 2, da[b].z); atomicAdd(o + 3, da[b].w);
+  for (int g = 0; g < NG; ++g)
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+      if (b < B) {
+        float* o = grp[g].dx + static_cast<long long>(b) * K + k4 * 4;
+        atomicAdd(o, da[g][b].x); atomicAdd(o + 1, da[g][b].y); atomicAdd(o + 2, da[g][b].z); atomicAdd(o + 3, da[g][b].w);
+      }
     }
-  }
 }
 
 // nn.BCELoss (mean reduction, log clamped at -100) against a constant target (utils/GAN.py:96-107)
@@ -1174,8 +1185,20 @@ int gl_dense1_bwd(const float* W, const float* x, const float* dz1, float* dW, f
   if (B > 8 || (K & 3)) return -54;
   cudaMemsetAsync(dx, 0, static_cast<size_t>(B) * K * sizeof(float), s);
   const int jn = (J + kD1Split - 1) / kD1Split;
-  launch_k(g_dense1_bwd_kernel, dim3((K / 4 + kT - 1) / kT, kD1Split), dim3(kT), static_cast<size_t>(jn) * 8 * sizeof(float), s,
-           W, x, dz1, dW, db1, dx, B, K, J);
+  const D1Grp g0{x, dz1, dx};
+  launch_k(g_dense1_bwd_kernel<1>, dim3((K / 4 + kT - 1) / kT, kD1Split), dim3(kT), static_cast<size_t>(jn) * 8 * sizeof(float),
+           s, W, g0, g0, dW, db1, B, K, J);
+  GL_CHECK();
+}
+int gl_dense1_bwd2(const float* W, const float* x0, const float* dz0, float* dx0, const float* x1, const float* dz1,
+                   float* dx1, float* dW, float* db1, int B, int K, int J, cudaStream_t s) {
+  if (B > 8 || (K & 3)) return -54;
+  cudaMemsetAsync(dx0, 0, static_cast<size_t>(B) * K * sizeof(float), s);
+  cudaMemsetAsync(dx1, 0, static_cast<size_t>(B) * K * sizeof(float), s);
+  const int jn = (J + kD1Split - 1) / kD1Split;
+  const D1Grp g0{x0, dz0, dx0}, g1{x1, dz1, dx1};
+  launch_k(g_dense1_bwd_kernel<2>, dim3((K / 4 + kT - 1) / kT, kD1Split), dim3(kT), static_cast<size_t>(jn) * 16 * sizeof(float),
+           s, W, g0, g1, dW, db1, B, K, J);
   GL_CHECK();
 }
 int gl_bce(const float* prob, float target, int B, float* loss_out, int accumulate, cudaStream_t s) {

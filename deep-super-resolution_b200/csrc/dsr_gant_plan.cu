@@ -101,7 +101,7 @@ struct dsr_gant {
   GT d_dz0;
   double* d_stats[2] = {nullptr, nullptr}; // [7][2 * 512]
   float *d_flat[2] = {nullptr, nullptr}, *d_z1[2] = {nullptr, nullptr}, *d_prob[2] = {nullptr, nullptr};
-  float *d_dz1 = nullptr, *d_dflat = nullptr;
+  float *d_dz1[2] = {nullptr, nullptr}, *d_dflat[2] = {nullptr, nullptr};
   // ---- VGG19
   std::vector<ConvL> v_c;
   std::vector<GT> v_y;                     // 16 conv outputs (post-ReLU)
@@ -250,8 +250,10 @@ size_t layout(dsr_gant* p, uint8_t* base) {
       p->d_gb[k] = mk(a, o.C, o.W, o.H, o.P, B);     // gradient w.r.t. raw[k]
     }
     p->d_dz0 = mk(a, 64, p->W, p->H, P0, B);
-    p->d_dz1 = static_cast<float*>(a.take(static_cast<size_t>(B) * 1024 * 4));
-    p->d_dflat = static_cast<float*>(a.take(static_cast<size_t>(B) * p->d_K * 4));
+    for (int s2 = 0; s2 < 2; ++s2) {
+      p->d_dz1[s2] = static_cast<float*>(a.take(static_cast<size_t>(B) * 1024 * 4));
+      p->d_dflat[s2] = static_cast<float*>(a.take(static_cast<size_t>(B) * p->d_K * 4));
+    }
     std::vector<ConvL*> tc;
     for (auto& c : p->d_c) tc.push_back(&c);
     p->dw_arena[1] = layout_dw(a, tc, &p->dw_bytes[1]);
@@ -369,7 +371,7 @@ extern "C" {
 int dsr_gant_create(dsr_gant_t** out, int batch, int lr_h, int lr_w, int factor, int residual_blocks, int with_vgg) {
   if (!out || batch < 1 || batch > 8 || lr_h < 8 || lr_w < 8 || (factor != 8 && factor != 16) || residual_blocks < 1)
     return -1;
-  if ((lr_w % 8) || (lr_h % 2)) return -5;
+  if ((lr_w % 2) || (lr_h % 2)) return -5;
   dsr_gant* p = new dsr_gant();
   p->B = batch; p->lh = lr_h; p->lw = lr_w; p->factor = factor; p->blocks = residual_blocks;
   p->nshuf = factor == 8 ? 3 : 4;
@@ -636,27 +638,18 @@ int dsr_gant_d_forward(dsr_gant_t* p, int slot, const float* params, float* buff
   return static_cast<int>(cudaGetLastError());
 }
 
-// grads += gradient of the pass in `slot`.  dprob: d(loss)/d(prob) [B] (autograd path), or nullptr for the fused
-// BCE against the constant `target` with mean reduction (utils/GAN.py:96-107): d(loss)/d(logit) = (p - target) / B.
-int dsr_gant_d_backward(dsr_gant_t* p, int slot, const float* params, const float* dprob, float target, float* grads,
-                        void* stream) {
-  if (!p || !p->bound || !params || !grads || slot < 0 || slot > 1) return -1;
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  p->launches = 0;
+// the convolutional part of the discriminator backward, from the gradient of the flattened features on
+static int d_convs_backward(dsr_gant* p, int slot, const float* params, float* grads, cudaStream_t s) {
   TapeScope scope(p, &p->tp_db[slot]);
   cudaMemsetAsync(p->dw_arena[1], 0, p->dw_bytes[1], s);
-  GCHK(gl_dense2_bwd(p->d_prob[slot], dprob, target, p->d_z1[slot], params + p->d_w2, p->d_dz1, grads + p->d_w2,
-                     grads + p->d_b2, p->B, 1024, s));
-  GCHK(gl_dense1_bwd(params + p->d_w1, p->d_flat[slot], p->d_dz1, grads + p->d_w1, grads + p->d_b1, p->d_dflat, p->B, p->d_K,
-                     1024, s));
-  GCHK(gl_unflatten(p->d_dflat, p->d_ga[6], s));
+  GCHK(gl_unflatten(p->d_dflat[slot], p->d_ga[6], s));
   for (int k = 6; k >= 0; --k) {
     double* st = p->d_stats[slot] + k * 1024;
     const BnL& b = p->d_bn[k];
     const GT& in = (k == 0) ? p->d_h0[slot] : p->d_h[slot][k - 1];
     GCHK(gl_bn_bwd(p->d_ga[k], p->d_raw[slot][k], p->d_gb[k], st, params + b.g_off, params + b.b_off, GACT_LRELU, nullptr,
                    p->sums, grads + b.g_off, grads + b.b_off, nullptr, s));
-    p->launches += 3;
+    p->launches += 1;
     GCHK(run_wgrad(p, p->d_c[k], p->d_gb[k], in, s));
     if (k > 0) {
       GCHK(run_dgrad(p, p->d_c[k], p->d_gb[k], p->d_ga[k - 1], nullptr, nullptr, 0.f, s));
@@ -671,6 +664,41 @@ int dsr_gant_d_backward(dsr_gant_t* p, int slot, const float* params, const floa
   for (int k = 0; k < 7; ++k) GCHK(gl_unpack_wgrad(p->d_c[k].dw, grads + p->d_c[k].w_off, p->d_c[k].cout, p->d_c[k].cin, 3, s));
   scope.ok = true;
   return 0;
+}
+
+// grads += gradient of the pass in `slot`.  dprob: d(loss)/d(prob) [B] (autograd path), or nullptr for the fused
+// BCE against the constant `target` with mean reduction (utils/GAN.py:96-107): d(loss)/d(logit) = (p - target) / B.
+int dsr_gant_d_backward(dsr_gant_t* p, int slot, const float* params, const float* dprob, float target, float* grads,
+                        void* stream) {
+  if (!p || !p->bound || !params || !grads || slot < 0 || slot > 1) return -1;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  p->launches = 0;
+  GCHK(gl_dense2_bwd(p->d_prob[slot], dprob, target, p->d_z1[slot], params + p->d_w2, p->d_dz1[slot], grads + p->d_w2,
+                     grads + p->d_b2, p->B, 1024, s));
+  GCHK(gl_dense1_bwd(params + p->d_w1, p->d_flat[slot], p->d_dz1[slot], grads + p->d_w1, grads + p->d_b1, p->d_dflat[slot],
+                     p->B, p->d_K, 1024, s));
+  return d_convs_backward(p, slot, params, grads, s);
+}
+
+// Both kept passes at once (loss_D.backward() of do_epoch, train_GAN.py:52): slot 0 against target0, slot 1 against
+// target1, BCE fused; the dense head's weight matrix and its gradient are swept once for the two passes.
+int dsr_gant_d_backward_pair(dsr_gant_t* p, const float* params, float target0, float target1, float* grads, void* stream) {
+  if (!p || !p->bound || !params || !grads) return -1;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  p->launches = 0;
+  const float tg[2] = {target0, target1};
+  for (int slot = 0; slot < 2; ++slot)
+    GCHK(gl_dense2_bwd(p->d_prob[slot], nullptr, tg[slot], p->d_z1[slot], params + p->d_w2, p->d_dz1[slot], grads + p->d_w2,
+                       grads + p->d_b2, p->B, 1024, s));
+  GCHK(gl_dense1_bwd2(params + p->d_w1, p->d_flat[0], p->d_dz1[0], p->d_dflat[0], p->d_flat[1], p->d_dz1[1], p->d_dflat[1],
+                      grads + p->d_w1, grads + p->d_b1, p->B, p->d_K, 1024, s));
+  const int n = p->launches;
+  int rc = d_convs_backward(p, 0, params, grads, s);
+  if (rc) return rc;
+  const int n0 = p->launches;
+  rc = d_convs_backward(p, 1, params, grads, s);
+  p->launches += n0 - n;
+  return rc;
 }
 
 int dsr_gant_bce(dsr_gant_t* p, const float* prob, float target, int n, float* loss, int accumulate, void* stream) {

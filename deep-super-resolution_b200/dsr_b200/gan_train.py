@@ -106,6 +106,11 @@ class Trainer:
                                       float(target), grads.data_ptr(), _lib.stream_ptr()), 'dsr_gant_d_backward')
         self._count()
 
+    def d_backward_pair(self, params, grads, target0: float, target1: float) -> None:
+        check(lib.dsr_gant_d_backward_pair(self.handle, params.data_ptr(), float(target0), float(target1), grads.data_ptr(),
+                                           _lib.stream_ptr()), 'dsr_gant_d_backward_pair')
+        self._count()
+
     def bce(self, prob, target: float, loss, accumulate: bool) -> None:
         check(lib.dsr_gant_bce(self.handle, prob.data_ptr(), float(target), prob.numel(), loss.data_ptr(), int(accumulate),
                                _lib.stream_ptr()), 'dsr_gant_bce')
@@ -554,8 +559,7 @@ class GanTrainStep:
         tr.bce(p_real, 1.0, self.loss_D, False)
         tr.bce(p_fake, 0.0, self.loss_D, True)
         fd.gflat.zero_()
-        tr.d_backward(0, fd.flat, fd.gflat, target=1.0)
-        tr.d_backward(1, fd.flat, fd.gflat, target=0.0)
+        tr.d_backward_pair(fd.flat, fd.gflat, 1.0, 0.0)
         work = self.xch.start(fd.gflat) if self.dp else None
         # ---- generator phase, independent of the discriminator: content loss and generator backward (:56-66)
         dfake = tr.vgg_loss(fake, HR, self.loss_G, False, True)

@@ -241,6 +241,9 @@ int dsr_gant_d_forward(dsr_gant_t* p, int slot, const float* params, float* buff
 /* dprob [B] = d(loss)/d(prob), or NULL: BCE(prob, target) with mean reduction fused in. */
 int dsr_gant_d_backward(dsr_gant_t* p, int slot, const float* params, const float* dprob, float target, float* grads,
                         void* stream);
+/* Both kept passes in one call (loss_D.backward() of do_epoch): slot 0 against target0, slot 1 against target1, BCE fused;
+ * the dense head's 73 728 x 1024 matrix and its gradient are swept once for the two passes. */
+int dsr_gant_d_backward_pair(dsr_gant_t* p, const float* params, float target0, float target1, float* grads, void* stream);
 /* loss[0] (= | +=) nn.BCELoss()(prob[0..n), target) */
 int dsr_gant_bce(dsr_gant_t* p, const float* prob, float target, int n, float* loss, int accumulate, void* stream);
 /* loss[0] (= | +=) MSE(VGG(T(fake)), VGG(T(real))); dfake (may be NULL) = its gradient w.r.t. fake. */

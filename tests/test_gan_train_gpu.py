@@ -179,6 +179,33 @@ def test_fused_step_against_reference_fixture(env, golden, case):
     assert step.tr.device_error() == 0
 
 
+def test_factor16_step_with_12x12_patches(env):
+    """train_GAN.py --downsample: factor 16, HR patch 192 -> LR patch 12 x 12 (train_GAN.py:240-270); four PixelShuffle
+    blocks and level widths that are no multiple of the 8-pixel tiles.  One fused step against the oracle."""
+    dsr_b200, GT, O, dev = env
+    torch.manual_seed(17)
+    G = dsr_b200.Generator(16).train()
+    D = GT.Discriminator((192, 192)).train()
+    torch.manual_seed(1017)
+    V = GT.Vgg19Loss(pretrained=False)
+    sdG, sdD, sdV = ({k: v.detach().clone().to(dev) for k, v in m.state_dict().items()} for m in (G, D, V))
+    LR, HR = O.synthetic_batch(18, 2, (12, 12), 16)
+    step = GT.GanTrainStep(G, D, V.to(dev), 1e-4, 2, (12, 12), dev)
+    lD, lG = step.do_epoch(LR, HR)
+    torch.cuda.synchronize()
+    o = O.do_epoch(sdG, sdD, sdV, LR.to(dev), HR.to(dev), 1e-4, 16)
+    namedG, namedD = list(G.named_parameters()), list(D.named_parameters())
+    dead = [k for k, _ in namedG + namedD if k.endswith(('conv1.bias', 'conv2.bias')) and ('blocks' in k or k == 'conv2.bias')]
+    cG, rG = whole(namedG, step.fg.grad_views, o['gG'], dead)
+    cD, rD = whole(namedD, step.fd.grad_views, o['gD'], dead)
+    print(f'x16: loss_D {float(lD):.5f} vs {float(o["loss_D"]):.5f}  loss_G {float(lG):.5f} vs {float(o["loss_G"]):.5f}  '
+          f'gradient cosine G {cG:.4f} D {cD:.4f}')
+    assert abs(float(lD) - float(o['loss_D'])) < 1e-2 * float(o['loss_D'])
+    assert abs(float(lG) - float(o['loss_G'])) < 2e-2 * float(o['loss_G'])
+    assert cG > 0.99 and cD > 0.97 and abs(rG - 1) < 3e-2 and abs(rD - 1) < 3e-2
+    assert step.tr.device_error() == 0
+
+
 @pytest.mark.skipif(not os.path.isdir(REF), reason='baseline/_ref not staged (no /root/reference at build time)')
 def test_reference_training_loop_over_the_drop_in_modules():
     """The reference's own GAN_ISR_train / do_epoch (unmodified, baseline/_ref/train_GAN.py) with loss.backward() and
