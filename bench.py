@@ -803,6 +803,29 @@ def run_gan_train_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def gan_train_eager_baseline():
+    """Like-for-like GPU comparator (harness only): the UNMODIFIED reference's own loop over its own modules on this GPU
+    in stock PyTorch CUDA eager (fp32, TF32 off, cuDNN), tools/run_reference_gan.py --impl reference.  Steady-state rate
+    = the difference of a 13-step and a 3-step run (module construction, cuDNN start-up and the one logging pass cancel)."""
+    import subprocess
+
+    def run(epochs):
+        cmd = [sys.executable, os.path.join(ROOT, 'tools', 'run_reference_gan.py'), '--impl', 'reference', '--device', 'cuda',
+               '--batch', str(GT_B), '--lr-size', str(GT_LR), '--epochs', str(epochs)]
+        out = subprocess.run(cmd, capture_output=True, text=True).stdout.strip().splitlines()
+        return json.loads(out[-1]) if out else {'unavailable': 'no output'}
+    try:
+        a, b = run(3), run(13)
+        if 'unavailable' in a or 'unavailable' in b:
+            return {'unavailable': a.get('unavailable') or b.get('unavailable')}
+        sps = 10.0 / max(b['seconds'] - a['seconds'], 1e-6)
+        return {'value': GT_B * sps, 'unit': 'patches/s', 'ms_per_step': 1000.0 / sps, 'kind': 'reference',
+                'what': 'unmodified train_GAN.GAN_ISR_train over the reference modules, stock PyTorch CUDA eager fp32 (TF32 '
+                        'off), same batch; (13-step run - 3-step run) / 10'}
+    except Exception as e:
+        return {'unavailable': repr(e)[:200]}
+
+
 def run_gan_train(args, rank, local_rank, world):
     """One step = GanTrainStep.do_epoch on this rank's batch of 8 patches; world > 1: data-parallel replicas, NCCL
     all-reduce (mean) of the flat discriminator (321 MB) and generator (6.8 MB) gradients."""
@@ -896,6 +919,8 @@ def run_gan_train(args, rank, local_rank, world):
             'losses': list(losses), 'allreduce': ar,
             'gpu_launches': None, 'clocks': clocks}
     line['gpu_launches'] = step.launches_per_step * args.steps
+    if world == 1 and not args.no_cpu:
+        line['gpu_eager_baseline'] = gan_train_eager_baseline()
     print(json.dumps(line), flush=True)
 
 

@@ -42,6 +42,8 @@ struct GTap { int8_t px, dx, py, dy; int32_t b_row; };
 struct alignas(64) GConvParams {
   CUtensorMap a;           // input: box (64 | 16, 1, tw, 1, th)
   CUtensorMap b;           // packed weights [rows][K]: box (64 | 16, nt)
+  CUtensorMap b2;          // row-halo mode with one N tile: box (64 | 16, b2_rows) -- the ks taps of a row in b2_loads loads
+  int b2_rows, b2_loads;
   GTap taps[9];            // explicit taps (ntaps <= 9) ...
   int ntaps;
   int proc_ks;             // ... or, > 0, generated: tap t = (ky, kx) = (t / ks, t % ks), offsets sign * (k - pad),

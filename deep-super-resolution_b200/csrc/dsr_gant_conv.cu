@@ -74,6 +74,7 @@ __global__ void __launch_bounds__(kGcThreads, 1) gconv_kernel(const __grid_const
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.a);
     tma_prefetch_desc(&p.b);
+    if (p.b2_loads > 0) tma_prefetch_desc(&p.b2);
     for (int s = 0; s < kGcStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -114,8 +115,14 @@ __global__ void __launch_bounds__(kGcThreads, 1) gconv_kernel(const __grid_const
               uint8_t* sb = sa + a_off;
               mbar_arrive_expect_tx(&full_bar[stage], box_bytes + static_cast<uint32_t>(ks) * b_bytes);
               tma_load_5d(&p.a, &full_bar[stage], sa, kc * 64, 0, x0 - p.proc_pad, 0, y0 + p.proc_sign * (ky - p.proc_pad));
-              for (int kx = 0; kx < ks; ++kx)
-                tma_load_2d(&p.b, &full_bar[stage], sb + kx * b_bytes, kc * 64, (ky * ks + kx) * p.rows_per_tap + ntile * p.nt);
+              if (p.b2_loads > 0) {        // one N tile: the row's ks weight blocks are contiguous rows of the pack
+                const uint32_t part = static_cast<uint32_t>(p.b2_rows) * (p.narrow ? 32u : 128u);
+                for (int l = 0; l < p.b2_loads; ++l)
+                  tma_load_2d(&p.b2, &full_bar[stage], sb + l * part, kc * 64, ky * ks * p.rows_per_tap + l * p.b2_rows);
+              } else {
+                for (int kx = 0; kx < ks; ++kx)
+                  tma_load_2d(&p.b, &full_bar[stage], sb + kx * b_bytes, kc * 64, (ky * ks + kx) * p.rows_per_tap + ntile * p.nt);
+              }
               if (++stage == kGrStages) { stage = 0; phase ^= 1; }
             }
           }
@@ -524,6 +531,12 @@ int make_gconv_fprop(GConvParams* g, const GT& in, const GT& out, const void* w_
   } else
   if ((rc = make_act_map(&g->a, in.ptr, 1, in.C, in.W, in.rows(), stride, g->narrow ? 16 : 64, g->tw, g->th))) return rc;
   if ((rc = make_wgt_map(&g->b, w_pack, cin_pad, ks * ks * cout_pad, g->narrow ? 16 : 64, g->nt))) return rc;
+  if (g->rowhalo && g->ntiles_n == 1) {
+    g->b2_loads = (ks * g->nt + 255) / 256;
+    g->b2_rows = ks * g->nt / g->b2_loads;
+    if (g->b2_rows * g->b2_loads != ks * g->nt || (g->b2_rows & 7)) g->b2_loads = 0;
+    else if ((rc = make_wgt_map(&g->b2, w_pack, cin_pad, ks * ks * cout_pad, g->narrow ? 16 : 64, g->b2_rows))) return rc;
+  }
   g->ntaps = ks * ks;
   if (stride == 1) {
     g->proc_ks = ks; g->proc_pad = (ks - 1) / 2; g->proc_sign = 1; g->rows_per_tap = cout_pad;
@@ -584,6 +597,12 @@ int make_gconv_dgrad(GConvParams* g, int* nlaunch, const GT& dy, const GT& dx, c
     } else
     if ((rc = make_act_map(&q->a, dy.ptr, 1, dy.C, dy.W, dy.rows(), 1, q->narrow ? 16 : 64, q->tw, q->th))) return rc;
     if ((rc = make_wgt_map(&q->b, w_pack_d, cout_pad, ks * ks * cin_pad, q->narrow ? 16 : 64, q->nt))) return rc;
+    if (q->rowhalo && q->ntiles_n == 1) {
+      q->b2_loads = (ks * q->nt + 255) / 256;
+      q->b2_rows = ks * q->nt / q->b2_loads;
+      if (q->b2_rows * q->b2_loads != ks * q->nt || (q->b2_rows & 7)) q->b2_loads = 0;
+      else if ((rc = make_wgt_map(&q->b2, w_pack_d, cout_pad, ks * ks * cin_pad, q->narrow ? 16 : 64, q->b2_rows))) return rc;
+    }
     if (stride == 1) {
       q->ntaps = ks * ks;
       q->proc_ks = ks; q->proc_pad = (ks - 1) / 2; q->proc_sign = -1; q->rows_per_tap = cin_pad;
