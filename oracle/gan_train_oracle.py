@@ -90,6 +90,24 @@ def param_keys(sd: Dict[str, Tensor]) -> List[str]:
 
 
 # ---------------------------------------------------------------------------------------------
+# precision-class yardstick: the same arithmetic with bf16 rounding at the CUDA path's 16-bit storage points
+# ---------------------------------------------------------------------------------------------
+def bf16_points():
+    """``q`` for generator_train / discriminator_train: rounds to bfloat16 where libdsr_b200 stores 16-bit tensors -- the
+    packed conv weights, every convolution input / raw output, every BatchNorm + activation output -- with a
+    straight-through gradient (the CUDA backward keeps its gradients in bf16 as well, which this does not model).
+    The CUDA path must agree with THIS oracle more closely than with the fp32 one; what is left between the two is the
+    accumulation order."""
+    def q(t: Tensor) -> Tensor:
+        return t + (t.to(torch.bfloat16).to(t.dtype) - t).detach()
+    return q
+
+
+def _q(q, t):
+    return t if q is None else q(t)
+
+
+# ---------------------------------------------------------------------------------------------
 # forward passes
 # ---------------------------------------------------------------------------------------------
 def _bn_train(sd, name, x, new_stats):
@@ -103,43 +121,47 @@ def _bn_train(sd, name, x, new_stats):
     return y
 
 
-def generator_train(sd: Dict[str, Tensor], x: Tensor, factor: int = 8, blocks: int = 16, new_stats=None, taps=None) -> Tensor:
-    """generator.py:68-81 with ResidualBlock.forward (:14-25) and PixelShuffleBlock.forward (:36-41)."""
-    z = F.conv2d(x, sd['conv1.weight'], sd['conv1.bias'], padding=4)
-    x0 = F.prelu(z, sd['prelu1.weight'])
+def generator_train(sd: Dict[str, Tensor], x: Tensor, factor: int = 8, blocks: int = 16, new_stats=None, taps=None,
+                    q=None) -> Tensor:
+    """generator.py:68-81 with ResidualBlock.forward (:14-25) and PixelShuffleBlock.forward (:36-41).  q: optional
+    rounding at the 16-bit storage points (bf16_points)."""
+    def conv(name, h, pad):
+        return _q(q, F.conv2d(_q(q, h), _q(q, sd[name + '.weight']), sd[name + '.bias'], padding=pad))
+    z = conv('conv1', x, 4)
+    x0 = _q(q, F.prelu(z, sd['prelu1.weight']))
     h = x0
     if taps is not None:
         taps['g_x0'] = x0
     for i in range(blocks):
         p = f'residual_blocks.{i}.'
-        t = F.conv2d(h, sd[p + 'conv1.weight'], sd[p + 'conv1.bias'], padding=1)
-        t = F.prelu(_bn_train(sd, p + 'bn1', t, new_stats), sd[p + 'prelu1.weight'])
-        t = F.conv2d(t, sd[p + 'conv2.weight'], sd[p + 'conv2.bias'], padding=1)
-        h = h + _bn_train(sd, p + 'bn2', t, new_stats)
+        t = conv(p + 'conv1', h, 1)
+        t = _q(q, F.prelu(_bn_train(sd, p + 'bn1', t, new_stats), sd[p + 'prelu1.weight']))
+        t = conv(p + 'conv2', t, 1)
+        h = _q(q, h + _bn_train(sd, p + 'bn2', t, new_stats))
         if taps is not None:
             taps[f'g_x{i + 1}'] = h
-    t = F.conv2d(h, sd['conv2.weight'], sd['conv2.bias'], padding=1)
-    h = x0 + _bn_train(sd, 'bn1', t, new_stats)
+    t = conv('conv2', h, 1)
+    h = _q(q, x0 + _bn_train(sd, 'bn1', t, new_stats))
     if taps is not None:
         taps['g_t'] = h
     for i in range(SHUFFLES[factor]):
         p = f'pixel_shuffle_blocks.{i}.'
-        h = F.conv2d(h, sd[p + 'conv1.weight'], sd[p + 'conv1.bias'], padding=1)
-        h = F.prelu(F.pixel_shuffle(h, 2), sd[p + 'prelu1.weight'])
+        h = conv(p + 'conv1', h, 1)
+        h = _q(q, F.prelu(F.pixel_shuffle(h, 2), sd[p + 'prelu1.weight']))
         if taps is not None:
             taps[f'g_u{i}'] = h
-    return torch.tanh(F.conv2d(h, sd['conv3.weight'], sd['conv3.bias'], padding=4))
+    return torch.tanh(F.conv2d(h, _q(q, sd['conv3.weight']), sd['conv3.bias'], padding=4))
 
 
-def discriminator_train(sd: Dict[str, Tensor], x: Tensor, new_stats=None, taps=None) -> Tensor:
-    """discriminator.py:57-74 with DiscriminatorConvBlock.forward (:14-19)."""
-    h = F.leaky_relu(F.conv2d(x, sd['conv.weight'], sd['conv.bias'], padding=1), 0.2)
+def discriminator_train(sd: Dict[str, Tensor], x: Tensor, new_stats=None, taps=None, q=None) -> Tensor:
+    """discriminator.py:57-74 with DiscriminatorConvBlock.forward (:14-19).  q: see generator_train."""
+    h = _q(q, F.leaky_relu(F.conv2d(_q(q, x), _q(q, sd['conv.weight']), sd['conv.bias'], padding=1), 0.2))
     if taps is not None:
         taps['d_h0'] = h
     for i, (_, _, s) in enumerate(D_BLOCKS):
         p = f'convblocks.{i}.'
-        h = F.conv2d(h, sd[p + 'conv1.weight'], sd[p + 'conv1.bias'], stride=s, padding=1)
-        h = F.leaky_relu(_bn_train(sd, p + 'bn1', h, new_stats), 0.2)
+        h = _q(q, F.conv2d(h, _q(q, sd[p + 'conv1.weight']), sd[p + 'conv1.bias'], stride=s, padding=1))
+        h = _q(q, F.leaky_relu(_bn_train(sd, p + 'bn1', h, new_stats), 0.2))
         if taps is not None:
             taps[f'd_h{i + 1}'] = h
     h = h.reshape(h.shape[0], -1)
