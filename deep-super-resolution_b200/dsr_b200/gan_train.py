@@ -34,6 +34,8 @@ _VGG_CONV_IDX = (0, 2, 5, 7, 10, 12, 14, 16, 19, 21, 23, 25, 28, 30, 32, 34)
 # trainer object (one per batch / patch size / device): workspace + C handle
 # =================================================================================================
 class Trainer:
+    GUARD = 4096
+
     def __init__(self, batch: int, lr_h: int, lr_w: int, factor: int, blocks: int, device: torch.device,
                  with_vgg: bool = True):
         _lib.require_cuda()
@@ -45,8 +47,10 @@ class Trainer:
         check(lib.dsr_gant_create(C.byref(self.handle), batch, lr_h, lr_w, factor, blocks, int(with_vgg)), 'dsr_gant_create')
         nbytes = lib.dsr_gant_workspace_bytes(self.handle)
         with torch.cuda.device(device):
-            self.workspace = torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
+            self.workspace = torch.empty(nbytes + 1024 + self.GUARD, dtype=torch.uint8, device=device)
             base = (self.workspace.data_ptr() + 1023) // 1024 * 1024
+            self._guard = self.workspace[base - self.workspace.data_ptr() + nbytes:][:self.GUARD]
+            self._guard.fill_(0xA5)          # canary behind the workspace (guard_intact(), tests)
             check(lib.dsr_gant_bind(self.handle, base, nbytes, _lib.stream_ptr()), 'dsr_gant_bind')
         self.d_slot = 0
         self.d_gen = [0, 0]          # generation counter per discriminator activation slot
@@ -128,8 +132,11 @@ class Trainer:
         check(lib.dsr_gant_device_error(self.handle, C.byref(code)))
         return code.value
 
-    def tensor(self, name: str) -> torch.Tensor:
-        """Named activation of the last pass as [B, H, W, C] float32 (tests)."""
+    def guard_intact(self) -> bool:
+        return bool((self._guard == 0xA5).all())
+
+    def tensor(self, name: str, with_gap: bool = False) -> torch.Tensor:
+        """Named activation of the last pass as [B, H, W, C] float32 (tests); with_gap: [B, P, W, C] incl. the gap rows."""
         ptr = C.c_void_p()
         cc, w, h, p, b, f32 = (C.c_int() for _ in range(6))
         check(lib.dsr_gant_tensor(self.handle, name.encode(), C.byref(ptr), C.byref(cc), C.byref(w), C.byref(h), C.byref(p),
@@ -137,7 +144,8 @@ class Trainer:
         dt = {0: torch.bfloat16, 1: torch.float32, 2: torch.float16}[f32.value]
         t = torch.empty((b.value * p.value, w.value, cc.value), dtype=dt, device=self.device)
         check(lib.dsr_debug_copy(t.data_ptr(), ptr, t.numel() * t.element_size(), _lib.stream_ptr()), 'dsr_debug_copy')
-        return t.view(b.value, p.value, w.value, cc.value)[:, :h.value].float()
+        t = t.view(b.value, p.value, w.value, cc.value)
+        return t.float() if with_gap else t[:, :h.value].float()
 
     def __del__(self):
         try:

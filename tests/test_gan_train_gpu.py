@@ -193,6 +193,32 @@ def test_fused_step_against_reference_fixture(env, golden, case):
     assert step.tr.device_error() == 0
 
 
+def test_workspace_invariants_after_training_steps(env):
+    """The tall-grid layout rests on one invariant: the gap rows between the images of a batch (the convolutions' zero
+    padding) and the padded channels of the 3-channel tensors are never written.  After three fused steps every
+    inspectable tensor still has zero gaps, the canary behind the workspace is intact and no kernel reported a stalled
+    barrier.  (compute-sanitizer is not available on this pool.)"""
+    dsr_b200, GT, O, dev = env
+    torch.manual_seed(2)
+    G, D = dsr_b200.Generator(8).train(), GT.Discriminator((64, 96)).train()
+    V = GT.Vgg19Loss(pretrained=False).to(dev)
+    step = GT.GanTrainStep(G, D, V, 1e-4, 3, (8, 12), dev)                 # non-square, widths 12 .. 96
+    LR, HR = O.synthetic_batch(3, 3, (8, 12), 8)
+    for _ in range(3):
+        lD, lG = step.do_epoch(LR, HR)
+    torch.cuda.synchronize()
+    tr = step.tr
+    assert bool(torch.isfinite(lD)) and bool(torch.isfinite(lG))
+    names = ['g_z1', 'g_x0', 'g_x7', 'g_x16', 'g_t', 'g_u0', 'g_u1', 'g_u2', 'g_z', 'd_h0', 'd_h1', 'd_h4', 'd_h7', 'v_pre',
+             'v_y0', 'v_y1', 'v_y5', 'v_y15']
+    for n in names:
+        full, valid = tr.tensor(n, with_gap=True), tr.tensor(n)
+        assert float(full[:, valid.shape[1]:].abs().max()) == 0.0, f'{n}: gap rows written'
+        assert float(valid.abs().max()) > 0.0, n
+    assert float(tr.tensor('v_pre')[..., 3:].abs().max()) == 0.0 and float(tr.tensor('g_z')[..., 3:].abs().max()) == 0.0
+    assert tr.guard_intact() and tr.device_error() == 0
+
+
 def test_factor16_step_with_12x12_patches(env):
     """train_GAN.py --downsample: factor 16, HR patch 192 -> LR patch 12 x 12 (train_GAN.py:240-270); four PixelShuffle
     blocks and level widths that are no multiple of the 8-pixel tiles.  One fused step against the oracle."""
