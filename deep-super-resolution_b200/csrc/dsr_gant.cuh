@@ -115,6 +115,10 @@ int make_gconv_dgrad(GConvParams* g, int* nlaunch, const GT& dy, const GT& dx, c
                      int cout_pad, int ks, int stride, int* err);
 int make_gwgrad(GWgradParams* g, const GT& dy, const GT& x, float* dw, int cin, int cout, int stride, int num_sms,
                 int* err);
+int make_gconv_taps(GConvParams* g, const GT& in, const GT& out, const void* w, int k_pad, int n_pad, const GTap* taps,
+                    int ntaps, int* err);
+int make_gwgrad_taps(GWgradParams* g, const GT& dy, const GT& x, float* dw, int cin, int cout, const GTap* taps, int ntaps,
+                     int num_sms, int* err);
 int launch_gconv(const GConvParams& p, int num_sms, cudaStream_t s);
 int launch_gwgrad(const GWgradParams& p, cudaStream_t s);
 

@@ -677,6 +677,48 @@ int make_gwgrad(GWgradParams* g, const GT& dy, const GT& x, float* dw, int cin, 
   return 0;
 }
 
+// A stride-1 convolution-like GEMM over an explicit tap table (<= 9 taps, 64-channel chunks): out[p][n] = sum over taps,
+// k of in[p + (dx, dy)][k] * w[tap.b_row + n][k].
+int make_gconv_taps(GConvParams* g, const GT& in, const GT& out, const void* w, int k_pad, int n_pad, const GTap* taps,
+                    int ntaps, int* err) {
+  memset(g, 0, sizeof(*g));
+  if (in.C != k_pad || out.C != n_pad || (k_pad % 64) || ntaps > 9 || in.P != out.P || in.W != out.W) return -41;
+  g->kchunks = k_pad / 64;
+  g->nt = n_pad >= 128 ? 128 : n_pad;
+  if (n_pad % g->nt || (g->nt & 15)) return -45;
+  g->ntiles_n = n_pad / g->nt;
+  pick_tile(out.W, &g->tw, &g->th);
+  int rc;
+  if ((rc = make_act_map(&g->a, in.ptr, 1, in.C, in.W, in.rows(), 1, 64, g->tw, g->th))) return rc;
+  int max_row = 0;
+  for (int t = 0; t < ntaps; ++t) { g->taps[t] = taps[t]; if (taps[t].b_row > max_row) max_row = taps[t].b_row; }
+  if ((rc = make_wgt_map(&g->b, w, k_pad, max_row + n_pad, 64, g->nt))) return rc;
+  g->ntaps = ntaps;
+  g->tiles_x = (out.W + g->tw - 1) / g->tw;
+  g->tiles_y = (out.rows() + g->th - 1) / g->th;
+  g->ox_mul = 1; g->oy_mul = 1;
+  g->out_w = out.W; g->out_h = out.H; g->out_period = out.P; g->out_rows = out.rows();
+  g->out_c = out.C;
+  g->out = out.ptr;
+  g->out_f32 = out.f32;
+  g->idesc = make_idesc_f16(128, g->nt, FMT_BF16, FMT_BF16, 0, 0);
+  g->err = err;
+  return 0;
+}
+
+// Weight-gradient GEMM over an explicit tap table (ntaps a multiple of 3, <= 9): dw[tap.b_row][co][ci] += sum_p
+// dy[p][co] * x[p + (dx, dy)][ci].
+int make_gwgrad_taps(GWgradParams* g, const GT& dy, const GT& x, float* dw, int cin, int cout, const GTap* taps, int ntaps,
+                     int num_sms, int* err) {
+  int rc = make_gwgrad(g, dy, x, dw, cin, cout, 1, num_sms, err);
+  if (rc) return rc;
+  if (ntaps > 9 || (ntaps % 3)) return -49;
+  for (int t = 0; t < ntaps; ++t) g->taps[t] = taps[t];
+  g->ngroups = ntaps / 3;
+  g->tpg = 3;
+  return 0;
+}
+
 static int gant_set_attrs() {
   static bool done_dev[kMaxDevices] = {};
   bool& done = done_dev[device_slot()];

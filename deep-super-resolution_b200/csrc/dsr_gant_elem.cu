@@ -92,19 +92,6 @@ __global__ void g_pack_image_kernel(const float* __restrict__ in, bf16_t* __rest
   }
 }
 
-__global__ void g_tanh_out_kernel(const float* __restrict__ z, float* __restrict__ out, TG g) {
-  pdl_sync();
-  const long long np = static_cast<long long>(g.B) * g.H * g.W;
-  const long long hw = static_cast<long long>(g.H) * g.W;
-  for (long long q = static_cast<long long>(blockIdx.x) * kT + threadIdx.x; q < np; q += static_cast<long long>(gridDim.x) * kT) {
-    const long long b = q / hw, r = q - b * hw;
-    const float4 v = *reinterpret_cast<const float4*>(z + tg_pix_off(g, q));
-    out[(b * 3 + 0) * hw + r] = tanhf(v.x);
-    out[(b * 3 + 1) * hw + r] = tanhf(v.y);
-    out[(b * 3 + 2) * hw + r] = tanhf(v.z);
-  }
-}
-
 __global__ void g_tanh_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ out, bf16_t* __restrict__ dz,
                                   float* __restrict__ dbias3, TG g) {
   __shared__ float sm[kT * 3];
@@ -904,6 +891,104 @@ __global__ void g_unpack_wgrad_kernel(const float* __restrict__ dw, float* __res
 }
 
 // ---------------------------------------------------------------------------------------------
+// 9 x 9, 64 -> 3 output convolution (generator.py:60), backward: the kx taps FOLDED into the channel dimension.
+//   dz9[(y, x)][kx * 3 + co] = dz[(y, x - kx + 4)][co]      (27 of 64 channels; zero outside the image)
+// turns both gradients into 9-tap (ky) tensor-core problems with 64-channel operands:
+//   dW[co][ci][ky][kx] = sum_q dz9[q][kx*3+co] * x[q + (ky-4, 0)][ci]            -> gwgrad_kernel
+//   dx[q][ci]          = sum_ky sum_j dz9[q - (ky-4, 0)][j] * w9[ky][ci][j]      -> gconv_kernel
+// ---------------------------------------------------------------------------------------------
+__global__ void g_expand9_kernel(const bf16_t* __restrict__ dz, bf16_t* __restrict__ dz9, TG g, int zC) {
+  pdl_sync();
+  const long long np = static_cast<long long>(g.B) * g.H * g.W;
+  const int hw = g.H * g.W;
+  for (long long q = static_cast<long long>(blockIdx.x) * kT + threadIdx.x; q < np; q += static_cast<long long>(gridDim.x) * kT) {
+    const int b = static_cast<int>(q / hw);
+    const int r = static_cast<int>(q - static_cast<long long>(b) * hw);
+    const int y = r / g.W, x = r - y * g.W;
+    const bf16_t* row = dz + static_cast<long long>(b * g.P + y) * g.W * zC;
+    __align__(16) bf16_t v[32];
+#pragma unroll
+    for (int kx = 0; kx < 9; ++kx) {
+      const int xs = x - kx + 4;
+      const bool in = xs >= 0 && xs < g.W;
+#pragma unroll
+      for (int co = 0; co < 3; ++co) v[kx * 3 + co] = in ? row[static_cast<long long>(xs) * zC + co] : __float2bfloat16_rn(0.f);
+    }
+#pragma unroll
+    for (int j = 27; j < 32; ++j) v[j] = __float2bfloat16_rn(0.f);
+    uint4* dst = reinterpret_cast<uint4*>(dz9 + (static_cast<long long>(b * g.P + y) * g.W + x) * g.C);
+    const uint4* src = reinterpret_cast<const uint4*>(v);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) dst[k] = src[k];
+  }
+}
+// FORWARD of the same layer, kx folded into N:  S[q][kx*3+co] = sum_ky sum_ci x[q + (ky-4, 0)][ci] * w[co][ci][ky][kx]
+// (gconv_kernel, 9 taps, N = 32, fp32 out), then out[b][co][y][x] = tanh(bias[co] + sum_kx S[(y, x + kx - 4)][kx*3+co])
+// (S is zero outside the image columns because x is) -- the tanh / NCHW output pass does the 9-term fold.
+__global__ void g_fold9_tanh_kernel(const float* __restrict__ S, const float* __restrict__ bias, float* __restrict__ z_out,
+                                    float* __restrict__ out, TG g) {
+  pdl_sync();
+  const long long np = static_cast<long long>(g.B) * g.H * g.W;
+  const long long hw = static_cast<long long>(g.H) * g.W;
+  for (long long q = static_cast<long long>(blockIdx.x) * kT + threadIdx.x; q < np; q += static_cast<long long>(gridDim.x) * kT) {
+    const int b = static_cast<int>(q / hw);
+    const int r = static_cast<int>(q - b * hw);
+    const int y = r / g.W, x = r - y * g.W;
+    const float* row = S + static_cast<long long>(b * g.P + y) * g.W * g.C;
+    float a0 = bias[0], a1 = bias[1], a2 = bias[2];
+#pragma unroll
+    for (int kx = 0; kx < 9; ++kx) {
+      const int xs = x + kx - 4;
+      if (xs >= 0 && xs < g.W) {
+        const float* p3 = row + static_cast<long long>(xs) * g.C + kx * 3;
+        a0 += p3[0]; a1 += p3[1]; a2 += p3[2];
+      }
+    }
+    out[(static_cast<long long>(b) * 3 + 0) * hw + r] = tanhf(a0);
+    out[(static_cast<long long>(b) * 3 + 1) * hw + r] = tanhf(a1);
+    out[(static_cast<long long>(b) * 3 + 2) * hw + r] = tanhf(a2);
+    if (z_out != nullptr) {                 // pre-activation for tests: fp32, 16-channel pitch
+      float* zp = z_out + (static_cast<long long>(b * g.P + y) * g.W + x) * 16;
+      zp[0] = a0; zp[1] = a1; zp[2] = a2;
+    }
+  }
+}
+// w9f[ky][kx * 3 + co][ci] = w[co][ci][ky][kx]  (bf16 [9][32][64], rows >= 27 zero)
+__global__ void g_pack9f_kernel(const float* __restrict__ w, bf16_t* __restrict__ w9f) {
+  pdl_sync();
+  const int i = blockIdx.x * kT + threadIdx.x;
+  if (i >= 9 * 32 * 64) return;
+  const int ci = i & 63, j = (i >> 6) & 31, ky = i >> 11;
+  float v = 0.f;
+  if (j < 27) {
+    const int kx = j / 3, co = j - 3 * kx;
+    v = w[((co * 64 + ci) * 9 + ky) * 9 + kx];
+  }
+  w9f[i] = __float2bfloat16_rn(v);
+}
+// w9[ky][ci][kx * 3 + co] = w[co][ci][ky][kx]  (bf16 [9][64][64], columns >= 27 zero)
+__global__ void g_pack9_kernel(const float* __restrict__ w, bf16_t* __restrict__ w9) {
+  pdl_sync();
+  const int i = blockIdx.x * kT + threadIdx.x;
+  if (i >= 9 * 64 * 64) return;
+  const int j = i & 63, ci = (i >> 6) & 63, ky = i >> 12;
+  float v = 0.f;
+  if (j < 27) {
+    const int kx = j / 3, co = j - 3 * kx;
+    v = w[((co * 64 + ci) * 9 + ky) * 9 + kx];
+  }
+  w9[i] = __float2bfloat16_rn(v);
+}
+// g[co][ci][ky][kx] += dw9[ky][kx * 3 + co][ci]
+__global__ void g_unpack9_kernel(const float* __restrict__ dw9, float* __restrict__ g) {
+  pdl_sync();
+  const int i = blockIdx.x * kT + threadIdx.x;
+  if (i >= 3 * 64 * 81) return;
+  const int kx = i % 9, ky = (i / 9) % 9, ci = (i / 81) % 64, co = i / (81 * 64);
+  g[i] += dw9[(ky * 64 + kx * 3 + co) * 64 + ci];
+}
+
+// ---------------------------------------------------------------------------------------------
 // CUDA-core weight gradients of the 3-channel layers (0.3 % of the step's FLOPs; K = 3 is no tensor-core shape)
 // ---------------------------------------------------------------------------------------------
 // dW[co][ci][ky][kx] += sum_p dy[p][co] x[p + (ky, kx) - pad][ci];  dy: 64 channels, x: 16-channel pitch (3 used)
@@ -966,66 +1051,6 @@ __global__ void __launch_bounds__(kT) g_wgrad_in3_kernel(const bf16_t* __restric
   }
 }
 
-// dW[co][ci][ky][kx] += sum_p dz[p][co] x[p + (ky, kx) - 4][ci];  9 x 9, co < 3 (16-channel pitch), 64 input channels
-__global__ void __launch_bounds__(kT) g_wgrad_out3_kernel(const bf16_t* __restrict__ dz, const bf16_t* __restrict__ x,
-                                                          float* __restrict__ g, TG gx, int zC) {
-  constexpr int PW = 16;
-  extern __shared__ __align__(16) uint8_t dsm[];
-  bf16_t* xs = reinterpret_cast<bf16_t*>(dsm);                        // [256][64]
-  float* dzs = reinterpret_cast<float*>(dsm + PW * PW * 64 * 2);      // [64][3]
-  __shared__ short offs[81];
-  pdl_sync();
-  const int ci = threadIdx.x & 63, qd = threadIdx.x >> 6;
-  const int rows = gx.B * gx.P;
-  const int tiles_x = (gx.W + 7) / 8, tiles_y = (rows + 7) / 8;
-  for (int m = threadIdx.x; m < 81; m += kT) offs[m] = static_cast<short>(((m / 9) * PW + (m % 9)) * 64);
-  float acc[21][3];
-#pragma unroll
-  for (int i = 0; i < 21; ++i) { acc[i][0] = 0.f; acc[i][1] = 0.f; acc[i][2] = 0.f; }
-  for (int tile = blockIdx.x; tile < tiles_x * tiles_y; tile += gridDim.x) {
-    const int x0 = (tile % tiles_x) * 8, y0 = (tile / tiles_x) * 8;
-    __syncthreads();
-    for (int i = threadIdx.x; i < PW * PW * 8; i += kT) {
-      const int pix = i >> 3, part = i & 7;
-      const int yy = y0 + pix / PW - 4, xx = x0 + pix % PW - 4;
-      uint4 a = make_uint4(0, 0, 0, 0);
-      if (yy >= 0 && yy < rows && xx >= 0 && xx < gx.W)
-        a = *reinterpret_cast<const uint4*>(x + (static_cast<long long>(yy) * gx.W + xx) * 64 + part * 8);
-      *reinterpret_cast<uint4*>(&xs[pix * 64 + part * 8]) = a;
-    }
-    if (threadIdx.x < 64) {
-      const int yy = y0 + (threadIdx.x >> 3), xx = x0 + (threadIdx.x & 7);
-      float v0 = 0.f, v1 = 0.f, v2 = 0.f;
-      if (yy < rows && xx < gx.W) {
-        const bf16_t* src = dz + (static_cast<long long>(yy) * gx.W + xx) * zC;
-        v0 = __bfloat162float(src[0]); v1 = __bfloat162float(src[1]); v2 = __bfloat162float(src[2]);
-      }
-      dzs[threadIdx.x * 3] = v0; dzs[threadIdx.x * 3 + 1] = v1; dzs[threadIdx.x * 3 + 2] = v2;
-    }
-    __syncthreads();
-    for (int p = 0; p < 64; ++p) {
-      const float d0 = dzs[p * 3], d1 = dzs[p * 3 + 1], d2 = dzs[p * 3 + 2];
-      const int base = ((p >> 3) * PW + (p & 7)) * 64 + ci;
-#pragma unroll
-      for (int mm = 0; mm < 21; ++mm) {
-        const int m = qd + 4 * mm;
-        if (m < 81) {
-          const float xv = __bfloat162float(xs[base + offs[m]]);
-          acc[mm][0] += xv * d0; acc[mm][1] += xv * d1; acc[mm][2] += xv * d2;
-        }
-      }
-    }
-  }
-#pragma unroll
-  for (int mm = 0; mm < 21; ++mm) {
-    const int m = qd + 4 * mm;
-    if (m < 81) {
-#pragma unroll
-      for (int c = 0; c < 3; ++c) atomicAdd(&g[(c * 64 + ci) * 81 + m], acc[mm][c]);
-    }
-  }
-}
-
 }  // namespace
 
 // =============================================================================================
@@ -1034,11 +1059,6 @@ __global__ void __launch_bounds__(kT) g_wgrad_out3_kernel(const bf16_t* __restri
 int gl_pack_image(const float* nchw, const GT& out, cudaStream_t s) {
   launch_k(g_pack_image_kernel, dim3(grid_for(static_cast<long long>(out.B) * out.H * out.W)), dim3(kT), 0, s, nchw,
            static_cast<bf16_t*>(out.ptr), tg_of(out));
-  GL_CHECK();
-}
-int gl_tanh_out(const GT& z, float* out_nchw, cudaStream_t s) {
-  launch_k(g_tanh_out_kernel, dim3(grid_for(static_cast<long long>(z.B) * z.H * z.W)), dim3(kT), 0, s,
-           static_cast<const float*>(z.ptr), out_nchw, tg_of(z));
   GL_CHECK();
 }
 int gl_tanh_bwd(const float* dout, const float* out, const GT& dz, float* dbias3, cudaStream_t s) {
@@ -1217,6 +1237,30 @@ int gl_unpack_wgrad(const float* dw_pack, float* g, int cout, int cin, int ks, c
            cout, cin, ks);
   GL_CHECK();
 }
+int gl_expand9(const GT& dz16, const GT& dz9, cudaStream_t s) {
+  if (dz9.C != 64 || dz9.W != dz16.W || dz9.P != dz16.P || dz9.H != dz16.H) return -56;
+  launch_k(g_expand9_kernel, dim3(grid_for(static_cast<long long>(dz9.B) * dz9.H * dz9.W)), dim3(kT), 0, s,
+           static_cast<const bf16_t*>(dz16.ptr), static_cast<bf16_t*>(dz9.ptr), tg_of(dz9), dz16.C);
+  GL_CHECK();
+}
+int gl_pack9(const float* w_oihw, bf16_t* w9, cudaStream_t s) {
+  launch_k(g_pack9_kernel, dim3((9 * 64 * 64 + kT - 1) / kT), dim3(kT), 0, s, w_oihw, w9);
+  GL_CHECK();
+}
+int gl_pack9f(const float* w_oihw, bf16_t* w9f, cudaStream_t s) {
+  launch_k(g_pack9f_kernel, dim3((9 * 32 * 64 + kT - 1) / kT), dim3(kT), 0, s, w_oihw, w9f);
+  GL_CHECK();
+}
+int gl_fold9_tanh(const GT& S, const float* bias3, float* z16_f32, float* out_nchw, cudaStream_t s) {
+  if (S.C != 32 || !S.f32) return -56;
+  launch_k(g_fold9_tanh_kernel, dim3(grid_for(static_cast<long long>(S.B) * S.H * S.W)), dim3(kT), 0, s,
+           static_cast<const float*>(S.ptr), bias3, z16_f32, out_nchw, tg_of(S));
+  GL_CHECK();
+}
+int gl_unpack9(const float* dw9, float* g_oihw, cudaStream_t s) {
+  launch_k(g_unpack9_kernel, dim3((3 * 64 * 81 + kT - 1) / kT), dim3(kT), 0, s, dw9, g_oihw);
+  GL_CHECK();
+}
 int gl_wgrad_in3(const GT& dy64, const GT& x16, float* g, int ks, cudaStream_t s) {
   if (dy64.C != 64 || dy64.W != x16.W || dy64.P != x16.P) return -55;
   const int tiles = ((dy64.W + 7) / 8) * ((dy64.rows() + 7) / 8);
@@ -1228,14 +1272,4 @@ int gl_wgrad_in3(const GT& dy64, const GT& x16, float* g, int ks, cudaStream_t s
   else return -55;
   GL_CHECK();
 }
-int gl_wgrad_out3(const GT& dz16, const GT& x64, float* g, cudaStream_t s) {
-  if (x64.C != 64 || dz16.W != x64.W || dz16.P != x64.P) return -55;
-  const int tiles = ((x64.W + 7) / 8) * ((x64.rows() + 7) / 8);
-  const int grid = tiles < 296 ? tiles : 296;
-  const size_t smem = 16 * 16 * 64 * 2 + 64 * 3 * sizeof(float);
-  launch_k(g_wgrad_out3_kernel, dim3(grid), dim3(kT), smem, s, static_cast<const bf16_t*>(dz16.ptr),
-           static_cast<const bf16_t*>(x64.ptr), g, tg_of(x64), dz16.C);
-  GL_CHECK();
-}
-
 }  // namespace dsr

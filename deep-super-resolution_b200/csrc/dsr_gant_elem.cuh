@@ -12,7 +12,6 @@ enum { GACT_NONE = 0, GACT_LRELU = 1, GACT_PRELU = 2 };
 
 // images
 int gl_pack_image(const float* nchw, const GT& out, cudaStream_t s);                       // fp32 [B][3][H][W] -> NHWC16
-int gl_tanh_out(const GT& z_f32, float* out_nchw, cudaStream_t s);                         // tanh(z) -> fp32 [B][3][H][W]
 int gl_tanh_bwd(const float* dout_nchw, const float* out_nchw, const GT& dz, float* dbias3, cudaStream_t s);
 // BatchNorm (batch statistics), activation, residual
 // rm / rv (may be nullptr): running statistics, updated run_times times by block 0 (conv_bias: the bias the conv dropped)
@@ -55,9 +54,14 @@ int gl_bce(const float* prob, float target, int B, float* loss_out, int accumula
 int gl_pack_weight(const float* w_oihw, const float* bias, int cout, int cin, int ks, int cout_pad, int cin_pad,
                    bf16_t* w_f, bf16_t* w_d, float* bias_pad, int f16_fwd, cudaStream_t s);   // f16_fwd: w_f as IEEE half
 int gl_unpack_wgrad(const float* dw_pack, float* g_oihw, int cout, int cin, int ks, cudaStream_t s);
-// CUDA-core weight gradients of the 3-channel layers
+// CUDA-core weight gradients of the layers with 3 INPUT channels
 int gl_wgrad_in3(const GT& dy64, const GT& x16, float* g_oihw, int ks, cudaStream_t s);     // dW[64][3][ks][ks] +=
-int gl_wgrad_out3(const GT& dz16, const GT& x64, float* g_oihw, cudaStream_t s);            // dW[3][64][9][9] +=
+// backward of the 9 x 9 output convolution with the kx taps folded into the channels (dsr_gant_elem.cu)
+int gl_expand9(const GT& dz16, const GT& dz9, cudaStream_t s);
+int gl_pack9(const float* w_oihw, bf16_t* w9, cudaStream_t s);
+int gl_unpack9(const float* dw9, float* g_oihw, cudaStream_t s);
+int gl_pack9f(const float* w_oihw, bf16_t* w9f, cudaStream_t s);
+int gl_fold9_tanh(const GT& S_f32_32, const float* bias3, float* z16_f32, float* out_nchw, cudaStream_t s);
 int gl_finish_double(const double* acc, float* out, float scale, int accumulate, cudaStream_t s);
 
 }  // namespace dsr

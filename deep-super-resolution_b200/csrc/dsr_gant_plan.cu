@@ -83,7 +83,11 @@ struct dsr_gant {
   BnL g_bn;
   long long g_prelu1 = 0;
   std::vector<long long> g_prelu_blk, g_prelu_sh;
-  GT g_lr16, g_z1, g_x0, g_rt, g_t, g_z, g_dz16;
+  GT g_lr16, g_z1, g_x0, g_rt, g_t, g_z, g_dz16, g_dz9;
+  GT g_S;                                  // conv3 forward, kx folded into N: fp32 [.][W][32]
+  bf16_t* g_w9f = nullptr;                 // conv3 weights [ky][kx * 3 + co][ci] (forward)
+  bf16_t* g_w9 = nullptr;                  // conv3 weights with the kx taps folded into K: [ky][ci][kx * 3 + co]
+  float* g_dw9 = nullptr;                  // conv3 weight gradient in the folded layout [ky][kx * 3 + co][ci]
   std::vector<GT> g_r1, g_a1, g_r2, g_x;   // g_x[k + 1] = output of block k; g_x[0] aliases g_x0
   std::vector<GT> g_s, g_u, g_ds, g_du;    // shuffle levels
   GT g_dT, g_dX[2], g_dR, g_dA;
@@ -207,6 +211,11 @@ size_t layout(dsr_gant* p, uint8_t* base) {
     }
     p->g_z = mk(a, 16, Ws[nl - 1], Hs[nl - 1], Ps[nl - 1], B, 1);
     p->g_dz16 = mk(a, 16, Ws[nl - 1], Hs[nl - 1], Ps[nl - 1], B);
+    p->g_dz9 = mk(a, 64, Ws[nl - 1], Hs[nl - 1], Ps[nl - 1], B);
+    p->g_S = mk(a, 32, Ws[nl - 1], Hs[nl - 1], Ps[nl - 1], B, 1);
+    p->g_w9f = static_cast<bf16_t*>(a.take(9 * 32 * 64 * 2));
+    p->g_w9 = static_cast<bf16_t*>(a.take(9 * 64 * 64 * 2));
+    p->g_dw9 = static_cast<float*>(a.take(9 * 64 * 64 * 4));
     p->g_dT = mk(a, 64, Ws[0], Hs[0], Ps[0], B);
     p->g_dX[0] = mk(a, 64, Ws[0], Hs[0], Ps[0], B);
     p->g_dX[1] = mk(a, 64, Ws[0], Hs[0], Ps[0], B);
@@ -223,7 +232,6 @@ size_t layout(dsr_gant* p, uint8_t* base) {
     p->g_conv1.need_d = false;
     layout_pack(a, p->g_conv1);
     for (ConvL* c : tc) layout_pack(a, *c);
-    layout_pack(a, p->g_conv3);
   }
   // ---------------- discriminator ----------------
   {
@@ -491,7 +499,8 @@ int dsr_gant_pack(dsr_gant_t* p, int net, const float* params, void* stream) {
     }
     GCHK(pack_conv(p->g_conv2, params, false, s));
     for (int j = 0; j < p->nshuf; ++j) GCHK(pack_conv(p->g_cs[j], params, true, s));
-    GCHK(pack_conv(p->g_conv3, params, true, s));
+    GCHK(gl_pack9(params + p->g_conv3.w_off, p->g_w9, s));
+    GCHK(gl_pack9f(params + p->g_conv3.w_off, p->g_w9f, s));
   } else if (net == 1) {
     GCHK(pack_conv(p->d_conv0, params, true, s));
     for (int k = 0; k < 7; ++k) GCHK(pack_conv(p->d_c[k], params, false, s));
@@ -543,8 +552,21 @@ int dsr_gant_g_forward(dsr_gant_t* p, const float* params, float* buffers, const
     GCHK(gl_shuffle_fwd(p->g_s[j], p->g_u[j], params + p->g_prelu_sh[j], s));
     cur = &p->g_u[j];
   }
-  GCHK(run_fprop(p, p->g_conv3, *cur, p->g_z, true, 0, 0.f, nullptr, s));
-  GCHK(gl_tanh_out(p->g_z, out_nchw, s));
+  // conv3 (9 x 9, 64 -> 3) with the kx taps folded into N: a 9-tap (ky) GEMM with N = 27 -> 32, then the 9-term fold inside
+  // the tanh / NCHW output pass (dsr_gant_elem.cu) -- 9 x fewer MMAs than the tap-by-tap form
+  {
+    Tape& t = *p->tape;
+    if (!t.built) {
+      GTap tf[9];
+      for (int ky = 0; ky < 9; ++ky) tf[ky] = GTap{0, 0, 0, static_cast<int8_t>(ky - 4), ky * 32};
+      GConvParams gc;
+      const int rc = make_gconv_taps(&gc, *cur, p->g_S, p->g_w9f, 64, 32, tf, 9, p->err);
+      if (rc) return rc;
+      t.convs.push_back(gc);
+    }
+    GCHK(launch_gconv(t.convs[t.ci++], p->num_sms, s));
+  }
+  GCHK(gl_fold9_tanh(p->g_S, params + p->g_conv3.b_off, static_cast<float*>(p->g_z.ptr), out_nchw, s));
   cudaMemcpyAsync(p->g_out, out_nchw, static_cast<size_t>(p->B) * 3 * p->H * p->W * 4, cudaMemcpyDeviceToDevice, s);
   scope.ok = true;
   return static_cast<int>(cudaGetLastError());
@@ -559,8 +581,29 @@ int dsr_gant_g_backward(dsr_gant_t* p, const float* params, const float* dout_nc
   cudaMemsetAsync(p->dw_arena[0], 0, p->dw_bytes[0], s);
   const int last = p->nshuf - 1;
   GCHK(gl_tanh_bwd(dout_nchw, p->g_out, p->g_dz16, grads + p->g_conv3.b_off, s));
-  GCHK(gl_wgrad_out3(p->g_dz16, p->g_u[last], grads + p->g_conv3.w_off, s));
-  GCHK(run_dgrad(p, p->g_conv3, p->g_dz16, p->g_du[last], nullptr, nullptr, 0.f, s));
+  // conv3 (9 x 9, 64 -> 3) backward with the kx taps folded into the channels: 9-tap tensor-core problems (dsr_gant_elem.cu)
+  GCHK(gl_expand9(p->g_dz16, p->g_dz9, s));
+  cudaMemsetAsync(p->g_dw9, 0, 9 * 64 * 64 * 4, s);
+  {
+    Tape& t = *p->tape;
+    if (!t.built) {
+      GTap tw[9], td[9];
+      for (int ky = 0; ky < 9; ++ky) {
+        tw[ky] = GTap{0, 0, 0, static_cast<int8_t>(ky - 4), ky};              // x[q + (ky - 4, 0)], gradient block ky
+        td[ky] = GTap{0, 0, 0, static_cast<int8_t>(4 - ky), ky * 64};          // dz9[q - (ky - 4, 0)], weight rows ky * 64
+      }
+      GWgradParams gw;
+      int rc = make_gwgrad_taps(&gw, p->g_dz9, p->g_u[last], p->g_dw9, 64, 64, tw, 9, p->num_sms, p->err);
+      if (rc) return rc;
+      t.wgs.push_back(gw);
+      GConvParams gc;
+      if ((rc = make_gconv_taps(&gc, p->g_dz9, p->g_du[last], p->g_w9, 64, 64, td, 9, p->err))) return rc;
+      t.convs.push_back(gc);
+    }
+    GCHK(launch_gwgrad(t.wgs[t.wi++], s));
+    GCHK(launch_gconv(t.convs[t.ci++], p->num_sms, s));
+  }
+  GCHK(gl_unpack9(p->g_dw9, grads + p->g_conv3.w_off, s));
   for (int j = last; j >= 0; --j) {
     const GT& in = (j == 0) ? p->g_t : p->g_u[j - 1];
     const GT& din = (j == 0) ? p->g_dT : p->g_du[j - 1];
