@@ -897,7 +897,11 @@ __global__ void g_unpack_wgrad_kernel(const float* __restrict__ dw, float* __res
 //   dW[co][ci][ky][kx] = sum_q dz9[q][kx*3+co] * x[q + (ky-4, 0)][ci]            -> gwgrad_kernel
 //   dx[q][ci]          = sum_ky sum_j dz9[q - (ky-4, 0)][j] * w9[ky][ci][j]      -> gconv_kernel
 // ---------------------------------------------------------------------------------------------
-__global__ void g_expand9_kernel(const bf16_t* __restrict__ dz, bf16_t* __restrict__ dz9, TG g, int zC) {
+// dst[(y, x)][kx * 3 + c] = src[(y, x + sign * (kx - pad))][c], c < 3, kx < KS; the remaining channels of the first
+// 16 (KS = 3) / 32 (KS = 9) are written as zero, the rest of dst's pitch stays zero from bind time
+template <int KS>
+__global__ void g_expand_kx_kernel(const bf16_t* __restrict__ src, bf16_t* __restrict__ dst, TG g, int sC, int sign, int pad) {
+  constexpr int NV = (KS * 3 + 15) / 16 * 16;
   pdl_sync();
   const long long np = static_cast<long long>(g.B) * g.H * g.W;
   const int hw = g.H * g.W;
@@ -905,22 +909,30 @@ __global__ void g_expand9_kernel(const bf16_t* __restrict__ dz, bf16_t* __restri
     const int b = static_cast<int>(q / hw);
     const int r = static_cast<int>(q - static_cast<long long>(b) * hw);
     const int y = r / g.W, x = r - y * g.W;
-    const bf16_t* row = dz + static_cast<long long>(b * g.P + y) * g.W * zC;
-    __align__(16) bf16_t v[32];
+    const bf16_t* row = src + static_cast<long long>(b * g.P + y) * g.W * sC;
+    __align__(16) bf16_t v[NV];
 #pragma unroll
-    for (int kx = 0; kx < 9; ++kx) {
-      const int xs = x - kx + 4;
+    for (int kx = 0; kx < KS; ++kx) {
+      const int xs = x + sign * (kx - pad);
       const bool in = xs >= 0 && xs < g.W;
 #pragma unroll
-      for (int co = 0; co < 3; ++co) v[kx * 3 + co] = in ? row[static_cast<long long>(xs) * zC + co] : __float2bfloat16_rn(0.f);
+      for (int c = 0; c < 3; ++c) v[kx * 3 + c] = in ? row[static_cast<long long>(xs) * sC + c] : __float2bfloat16_rn(0.f);
     }
 #pragma unroll
-    for (int j = 27; j < 32; ++j) v[j] = __float2bfloat16_rn(0.f);
-    uint4* dst = reinterpret_cast<uint4*>(dz9 + (static_cast<long long>(b * g.P + y) * g.W + x) * g.C);
-    const uint4* src = reinterpret_cast<const uint4*>(v);
+    for (int j = KS * 3; j < NV; ++j) v[j] = __float2bfloat16_rn(0.f);
+    uint4* d4 = reinterpret_cast<uint4*>(dst + (static_cast<long long>(b * g.P + y) * g.W + x) * g.C);
+    const uint4* s4 = reinterpret_cast<const uint4*>(v);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) dst[k] = src[k];
+    for (int k = 0; k < NV / 8; ++k) d4[k] = s4[k];
   }
+}
+// discriminator conv0 (3 x 3, 3 -> 64) weight gradient from the folded layout: g[co][ci][ky][kx] += dw3[ky][co][kx * 3 + ci]
+__global__ void g_unpack3_kernel(const float* __restrict__ dw3, float* __restrict__ g) {
+  pdl_sync();
+  const int i = blockIdx.x * kT + threadIdx.x;
+  if (i >= 64 * 27) return;
+  const int kx = i % 3, ky = (i / 3) % 3, ci = (i / 9) % 3, co = i / 27;
+  g[i] += dw3[(ky * 64 + co) * 64 + kx * 3 + ci];
 }
 // FORWARD of the same layer, kx folded into N:  S[q][kx*3+co] = sum_ky sum_ci x[q + (ky-4, 0)][ci] * w[co][ci][ky][kx]
 // (gconv_kernel, 9 taps, N = 32, fp32 out), then out[b][co][y][x] = tanh(bias[co] + sum_kx S[(y, x + kx - 4)][kx*3+co])
@@ -1239,8 +1251,18 @@ int gl_unpack_wgrad(const float* dw_pack, float* g, int cout, int cin, int ks, c
 }
 int gl_expand9(const GT& dz16, const GT& dz9, cudaStream_t s) {
   if (dz9.C != 64 || dz9.W != dz16.W || dz9.P != dz16.P || dz9.H != dz16.H) return -56;
-  launch_k(g_expand9_kernel, dim3(grid_for(static_cast<long long>(dz9.B) * dz9.H * dz9.W)), dim3(kT), 0, s,
-           static_cast<const bf16_t*>(dz16.ptr), static_cast<bf16_t*>(dz9.ptr), tg_of(dz9), dz16.C);
+  launch_k(g_expand_kx_kernel<9>, dim3(grid_for(static_cast<long long>(dz9.B) * dz9.H * dz9.W)), dim3(kT), 0, s,
+           static_cast<const bf16_t*>(dz16.ptr), static_cast<bf16_t*>(dz9.ptr), tg_of(dz9), dz16.C, -1, 4);
+  GL_CHECK();
+}
+int gl_expand3(const GT& img16, const GT& x9, cudaStream_t s) {
+  if (x9.C != 64 || x9.W != img16.W || x9.P != img16.P || x9.H != img16.H) return -56;
+  launch_k(g_expand_kx_kernel<3>, dim3(grid_for(static_cast<long long>(x9.B) * x9.H * x9.W)), dim3(kT), 0, s,
+           static_cast<const bf16_t*>(img16.ptr), static_cast<bf16_t*>(x9.ptr), tg_of(x9), img16.C, 1, 1);
+  GL_CHECK();
+}
+int gl_unpack3(const float* dw3, float* g_oihw, cudaStream_t s) {
+  launch_k(g_unpack3_kernel, dim3((64 * 27 + kT - 1) / kT), dim3(kT), 0, s, dw3, g_oihw);
   GL_CHECK();
 }
 int gl_pack9(const float* w_oihw, bf16_t* w9, cudaStream_t s) {

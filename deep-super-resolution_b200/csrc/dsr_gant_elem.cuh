@@ -59,6 +59,9 @@ int gl_wgrad_in3(const GT& dy64, const GT& x16, float* g_oihw, int ks, cudaStrea
 // backward of the 9 x 9 output convolution with the kx taps folded into the channels (dsr_gant_elem.cu)
 int gl_expand9(const GT& dz16, const GT& dz9, cudaStream_t s);
 int gl_pack9(const float* w_oihw, bf16_t* w9, cudaStream_t s);
+// the same fold for a 3 x 3, 3 -> 64 layer's weight gradient: x9[(y, x)][kx * 3 + ci] = img[(y, x + kx - 1)][ci]
+int gl_expand3(const GT& img16, const GT& x9, cudaStream_t s);
+int gl_unpack3(const float* dw3, float* g_oihw, cudaStream_t s);
 int gl_unpack9(const float* dw9, float* g_oihw, cudaStream_t s);
 int gl_pack9f(const float* w_oihw, bf16_t* w9f, cudaStream_t s);
 int gl_fold9_tanh(const GT& S_f32_32, const float* bias3, float* z16_f32, float* out_nchw, cudaStream_t s);

@@ -102,7 +102,8 @@ struct dsr_gant {
   GT d_img[2], d_h0[2];
   std::vector<GT> d_raw[2], d_h[2];
   std::vector<GT> d_ga, d_gb;              // gradient scratch per block output / input
-  GT d_dz0;
+  GT d_dz0, d_x9;                          // d_x9: the input image with the kx taps folded into channels (conv0 wgrad)
+  float* d_dw3 = nullptr;                  // conv0 weight gradient in the folded layout [ky][co][kx * 3 + ci]
   double* d_stats[2] = {nullptr, nullptr}; // [7][2 * 512]
   float *d_flat[2] = {nullptr, nullptr}, *d_z1[2] = {nullptr, nullptr}, *d_prob[2] = {nullptr, nullptr};
   float *d_dz1[2] = {nullptr, nullptr}, *d_dflat[2] = {nullptr, nullptr};
@@ -258,6 +259,8 @@ size_t layout(dsr_gant* p, uint8_t* base) {
       p->d_gb[k] = mk(a, o.C, o.W, o.H, o.P, B);     // gradient w.r.t. raw[k]
     }
     p->d_dz0 = mk(a, 64, p->W, p->H, P0, B);
+    p->d_x9 = mk(a, 64, p->W, p->H, P0, B);
+    p->d_dw3 = static_cast<float*>(a.take(3 * 64 * 64 * 4));
     for (int s2 = 0; s2 < 2; ++s2) {
       p->d_dz1[s2] = static_cast<float*>(a.take(static_cast<size_t>(B) * 1024 * 4));
       p->d_dflat[s2] = static_cast<float*>(a.take(static_cast<size_t>(B) * p->d_K * 4));
@@ -702,7 +705,22 @@ static int d_convs_backward(dsr_gant* p, int slot, const float* params, float* g
     }
     if (p->d_c[k].stride == 2) p->launches += 3;
   }
-  GCHK(gl_wgrad_in3(p->d_dz0, p->d_img[slot], grads + p->d_conv0.w_off, 3, s));
+  // conv0 (3 x 3, 3 -> 64) weight gradient with the kx taps folded into the input channels: a 3-tap gwgrad_kernel
+  GCHK(gl_expand3(p->d_img[slot], p->d_x9, s));
+  cudaMemsetAsync(p->d_dw3, 0, 3 * 64 * 64 * 4, s);
+  {
+    Tape& t = *p->tape;
+    if (!t.built) {
+      GTap tw[3];
+      for (int ky = 0; ky < 3; ++ky) tw[ky] = GTap{0, 0, 0, static_cast<int8_t>(ky - 1), ky};
+      GWgradParams gw;
+      const int rc = make_gwgrad_taps(&gw, p->d_dz0, p->d_x9, p->d_dw3, 64, 64, tw, 3, p->num_sms, p->err);
+      if (rc) return rc;
+      t.wgs.push_back(gw);
+    }
+    GCHK(launch_gwgrad(t.wgs[t.wi++], s));
+  }
+  GCHK(gl_unpack3(p->d_dw3, grads + p->d_conv0.w_off, s));
   GCHK(gl_chan_sum(p->d_dz0, grads + p->d_conv0.b_off, s));
   for (int k = 0; k < 7; ++k) GCHK(gl_unpack_wgrad(p->d_c[k].dw, grads + p->d_c[k].w_off, p->d_c[k].cout, p->d_c[k].cin, 3, s));
   scope.ok = true;
