@@ -877,6 +877,51 @@ __global__ void g_pack_weight_kernel(const float* __restrict__ w, const float* _
   }
 }
 
+// One launch for all convolutions of a network (a launch at these sizes costs 4 us whatever it does; the generator has
+// 36 layers): block b works on the item whose [blk0, blk0 + nblk) holds it, grid-striding over the item's blocks.
+__global__ void g_pack_group_kernel(const float* __restrict__ params, const GPackItem* __restrict__ items, int n) {
+  pdl_sync();
+  int it = 0;
+  while (it + 1 < n && static_cast<int>(blockIdx.x) >= items[it + 1].blk0) ++it;
+  const GPackItem q = items[it];
+  const float* w = params + q.w_off;
+  const int kk = q.ks * q.ks;
+  const long long total = static_cast<long long>(kk) * q.cout_pad * q.cin_pad;
+  for (long long i = static_cast<long long>(static_cast<int>(blockIdx.x) - q.blk0) * kT + threadIdx.x; i < total;
+       i += static_cast<long long>(q.nblk) * kT) {
+    const int ci = static_cast<int>(i % q.cin_pad);
+    const long long r = i / q.cin_pad;
+    const int co = static_cast<int>(r % q.cout_pad);
+    const int tap = static_cast<int>(r / q.cout_pad);
+    float v = 0.f;
+    if (co < q.cout && ci < q.cin) v = w[(static_cast<long long>(co) * q.cin + ci) * kk + tap];
+    const bf16_t h = __float2bfloat16_rn(v);
+    if (q.w_f != nullptr) {
+      if (q.f16_fwd) reinterpret_cast<__half*>(q.w_f)[i] = __float2half_rn(v);
+      else q.w_f[i] = h;
+    }
+    if (q.w_d != nullptr) q.w_d[(static_cast<long long>(tap) * q.cin_pad + ci) * q.cout_pad + co] = h;
+    if (tap == 0 && ci == 0) q.bias_pad[co] = (q.b_off >= 0 && co < q.cout) ? params[q.b_off + co] : 0.f;
+  }
+}
+__global__ void g_unpack_group_kernel(float* __restrict__ grads, const GUnpackItem* __restrict__ items, int n) {
+  pdl_sync();
+  int it = 0;
+  while (it + 1 < n && static_cast<int>(blockIdx.x) >= items[it + 1].blk0) ++it;
+  const GUnpackItem q = items[it];
+  float* g = grads + q.g_off;
+  const int kk = q.ks * q.ks;
+  const long long total = static_cast<long long>(q.cout) * q.cin * kk;
+  for (long long i = static_cast<long long>(static_cast<int>(blockIdx.x) - q.blk0) * kT + threadIdx.x; i < total;
+       i += static_cast<long long>(q.nblk) * kT) {
+    const int tap = static_cast<int>(i % kk);
+    const long long r = i / kk;
+    const int ci = static_cast<int>(r % q.cin);
+    const int co = static_cast<int>(r / q.cin);
+    g[i] += q.dw[(static_cast<long long>(tap) * q.cout + co) * q.cin + ci];
+  }
+}
+
 __global__ void g_unpack_wgrad_kernel(const float* __restrict__ dw, float* __restrict__ g, int cout, int cin, int ks) {
   pdl_sync();
   const int kk = ks * ks;
@@ -1242,6 +1287,20 @@ int gl_pack_weight(const float* w, const float* bias, int cout, int cin, int ks,
                    bf16_t* w_d, float* bias_pad, int f16_fwd, cudaStream_t s) {
   launch_k(g_pack_weight_kernel, dim3(grid_for(static_cast<long long>(ks) * ks * cout_pad * cin_pad)), dim3(kT), 0, s, w,
            bias, cout, cin, ks, cout_pad, cin_pad, w_f, w_d, bias_pad, f16_fwd);
+  GL_CHECK();
+}
+int gl_group_blocks(long long items) {
+  long long b = (items + 4 * kT - 1) / (4 * kT);
+  return static_cast<int>(b < 1 ? 1 : (b > 1024 ? 1024 : b));
+}
+int gl_pack_group(const float* params, const GPackItem* items_dev, int n, int total_blocks, cudaStream_t s) {
+  if (n <= 0) return 0;
+  launch_k(g_pack_group_kernel, dim3(total_blocks), dim3(kT), 0, s, params, items_dev, n);
+  GL_CHECK();
+}
+int gl_unpack_group(float* grads, const GUnpackItem* items_dev, int n, int total_blocks, cudaStream_t s) {
+  if (n <= 0) return 0;
+  launch_k(g_unpack_group_kernel, dim3(total_blocks), dim3(kT), 0, s, grads, items_dev, n);
   GL_CHECK();
 }
 int gl_unpack_wgrad(const float* dw_pack, float* g, int cout, int cin, int ks, cudaStream_t s) {

@@ -54,6 +54,16 @@ int gl_bce(const float* prob, float target, int B, float* loss_out, int accumula
 int gl_pack_weight(const float* w_oihw, const float* bias, int cout, int cin, int ks, int cout_pad, int cin_pad,
                    bf16_t* w_f, bf16_t* w_d, float* bias_pad, int f16_fwd, cudaStream_t s);   // f16_fwd: w_f as IEEE half
 int gl_unpack_wgrad(const float* dw_pack, float* g_oihw, int cout, int cin, int ks, cudaStream_t s);
+// the same two operations for ALL layers of a network in one launch each: tables in device memory, built at bind time
+struct GPackItem {
+  long long w_off, b_off;        // offsets into the flat parameter array; b_off < 0: bias_pad is written as zero
+  bf16_t* w_f; bf16_t* w_d; float* bias_pad;
+  int cout, cin, ks, cout_pad, cin_pad, f16_fwd, blk0, nblk;
+};
+struct GUnpackItem { const float* dw; long long g_off; int cout, cin, ks, blk0, nblk, pad_; };
+int gl_group_blocks(long long items);
+int gl_pack_group(const float* params, const GPackItem* items_dev, int n, int total_blocks, cudaStream_t s);
+int gl_unpack_group(float* grads, const GUnpackItem* items_dev, int n, int total_blocks, cudaStream_t s);
 // CUDA-core weight gradients of the layers with 3 INPUT channels
 int gl_wgrad_in3(const GT& dy64, const GT& x16, float* g_oihw, int ks, cudaStream_t s);     // dW[64][3][ks][ks] +=
 // backward of the 9 x 9 output convolution with the kx taps folded into the channels (dsr_gant_elem.cu)

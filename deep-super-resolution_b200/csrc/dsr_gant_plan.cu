@@ -120,6 +120,12 @@ struct dsr_gant {
   float* dw_arena[2] = {nullptr, nullptr}; // packed weight gradients of G / D
   size_t dw_bytes[2] = {0, 0};
   int launches = 0;
+  // one-launch weight packing / gradient unpacking per network: item tables (host copy, device copy, grid size)
+  std::vector<GPackItem> h_pack[3];
+  std::vector<GUnpackItem> h_unpack[2];
+  GPackItem* t_pack[3] = {nullptr, nullptr, nullptr};
+  GUnpackItem* t_unpack[2] = {nullptr, nullptr};
+  int pack_blocks[3] = {0, 0, 0}, unpack_blocks[2] = {0, 0};
   Tape tp_gf, tp_gb, tp_df[2], tp_db[2], tp_v, tp_vl;
   Tape* tape = nullptr;                    // the running entry point's tape
 };
@@ -183,6 +189,8 @@ size_t layout(dsr_gant* p, uint8_t* base) {
   a.base = base;
   const int B = p->B;
   p->err = static_cast<int*>(a.take(1024));
+  for (int n = 0; n < 3; ++n) p->t_pack[n] = static_cast<GPackItem*>(a.take(48 * sizeof(GPackItem)));
+  for (int n = 0; n < 2; ++n) p->t_unpack[n] = static_cast<GUnpackItem*>(a.take(48 * sizeof(GUnpackItem)));
   p->sums = static_cast<double*>(a.take((2 * 512 + 1) * sizeof(double)));
   p->loss_acc = static_cast<double*>(a.take(64));
   // ---------------- generator ----------------
@@ -370,10 +378,6 @@ struct TapeScope {                       // selects an entry point's tape; marks
     p->tape = nullptr;
   }
 };
-int pack_conv(const ConvL& c, const float* params, bool with_bias, cudaStream_t s, int f16_fwd = 0) {
-  return gl_pack_weight(params + c.w_off, with_bias ? params + c.b_off : nullptr, c.cout, c.cin, c.ks, c.cout_pad, c.cin_pad,
-                        c.w_f, c.w_d, c.bias_pad, f16_fwd, s);
-}
 
 }  // namespace
 
@@ -469,6 +473,62 @@ int dsr_gant_buffer_info(const dsr_gant_t* p, int net, int idx, char* name, int 
 }
 size_t dsr_gant_workspace_bytes(const dsr_gant_t* p) { return p ? p->ws_bytes : 0; }
 
+static void add_pack_item(dsr_gant* p, int net, const ConvL& c, bool with_bias, int f16_fwd) {
+  GPackItem q{};
+  q.w_off = c.w_off; q.b_off = with_bias ? c.b_off : -1;
+  q.w_f = c.w_f; q.w_d = c.w_d; q.bias_pad = c.bias_pad;
+  q.cout = c.cout; q.cin = c.cin; q.ks = c.ks; q.cout_pad = c.cout_pad; q.cin_pad = c.cin_pad; q.f16_fwd = f16_fwd;
+  q.blk0 = p->pack_blocks[net];
+  q.nblk = gl_group_blocks(static_cast<long long>(c.ks) * c.ks * c.cout_pad * c.cin_pad);
+  p->pack_blocks[net] += q.nblk;
+  p->h_pack[net].push_back(q);
+}
+static void add_unpack_item(dsr_gant* p, int net, const ConvL& c) {
+  GUnpackItem q{};
+  q.dw = c.dw; q.g_off = c.w_off; q.cout = c.cout; q.cin = c.cin; q.ks = c.ks;
+  q.blk0 = p->unpack_blocks[net];
+  q.nblk = gl_group_blocks(static_cast<long long>(c.ks) * c.ks * c.cout * c.cin);
+  p->unpack_blocks[net] += q.nblk;
+  p->h_unpack[net].push_back(q);
+}
+// the item tables of the grouped pack / unpack launches (pointers known once the workspace is laid out)
+static int build_group_tables(dsr_gant* p, cudaStream_t s) {
+  for (int n = 0; n < 3; ++n) { p->h_pack[n].clear(); p->pack_blocks[n] = 0; }
+  for (int n = 0; n < 2; ++n) { p->h_unpack[n].clear(); p->unpack_blocks[n] = 0; }
+  add_pack_item(p, 0, p->g_conv1, true, 0);
+  for (int k = 0; k < p->blocks; ++k) {
+    add_pack_item(p, 0, p->g_ca[k], false, 0);
+    add_pack_item(p, 0, p->g_cb[k], false, 0);
+    add_unpack_item(p, 0, p->g_ca[k]);
+    add_unpack_item(p, 0, p->g_cb[k]);
+  }
+  add_pack_item(p, 0, p->g_conv2, false, 0);
+  add_unpack_item(p, 0, p->g_conv2);
+  for (int j = 0; j < p->nshuf; ++j) {
+    add_pack_item(p, 0, p->g_cs[j], true, 0);
+    add_unpack_item(p, 0, p->g_cs[j]);
+  }
+  add_pack_item(p, 1, p->d_conv0, true, 0);
+  for (int k = 0; k < 7; ++k) {
+    add_pack_item(p, 1, p->d_c[k], false, 0);
+    add_unpack_item(p, 1, p->d_c[k]);
+  }
+  if (p->with_vgg)
+    for (int i = 0; i < 16; ++i) add_pack_item(p, 2, p->v_c[i], true, 1);     // forward copies in fp16 (see layout)
+  for (int n = 0; n < 3; ++n) {
+    if (p->h_pack[n].size() > 48) return -57;
+    if (!p->h_pack[n].empty() &&
+        cudaMemcpyAsync(p->t_pack[n], p->h_pack[n].data(), p->h_pack[n].size() * sizeof(GPackItem), cudaMemcpyHostToDevice, s) != cudaSuccess)
+      return -58;
+  }
+  for (int n = 0; n < 2; ++n) {
+    if (p->h_unpack[n].size() > 48) return -57;
+    if (cudaMemcpyAsync(p->t_unpack[n], p->h_unpack[n].data(), p->h_unpack[n].size() * sizeof(GUnpackItem), cudaMemcpyHostToDevice, s) != cudaSuccess)
+      return -58;
+  }
+  return 0;
+}
+
 int dsr_gant_bind(dsr_gant_t* p, void* workspace, size_t bytes, void* stream) {
   if (!p || !workspace) return -1;
   if (reinterpret_cast<uintptr_t>(workspace) & 1023) return -3;
@@ -478,6 +538,8 @@ int dsr_gant_bind(dsr_gant_t* p, void* workspace, size_t bytes, void* stream) {
   if (e != cudaSuccess) return static_cast<int>(e);
   layout(p, static_cast<uint8_t*>(workspace));
   for (Tape* t : {&p->tp_gf, &p->tp_gb, &p->tp_df[0], &p->tp_df[1], &p->tp_db[0], &p->tp_db[1], &p->tp_v, &p->tp_vl}) t->clear();
+  const int rc = build_group_tables(p, s);
+  if (rc) return rc;
   p->bound = true;
   return ensure_driver_api();
 }
@@ -494,22 +556,11 @@ int dsr_gant_pack(dsr_gant_t* p, int net, const float* params, void* stream) {
   if (!p || !p->bound || !params || net < 0 || net > 2) return -1;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   p->launches = 0;
+  if (net == 2 && !p->with_vgg) return -5;
+  GCHK(gl_pack_group(params, p->t_pack[net], static_cast<int>(p->h_pack[net].size()), p->pack_blocks[net], s));
   if (net == 0) {
-    GCHK(pack_conv(p->g_conv1, params, true, s));
-    for (int k = 0; k < p->blocks; ++k) {
-      GCHK(pack_conv(p->g_ca[k], params, false, s));
-      GCHK(pack_conv(p->g_cb[k], params, false, s));
-    }
-    GCHK(pack_conv(p->g_conv2, params, false, s));
-    for (int j = 0; j < p->nshuf; ++j) GCHK(pack_conv(p->g_cs[j], params, true, s));
     GCHK(gl_pack9(params + p->g_conv3.w_off, p->g_w9, s));
     GCHK(gl_pack9f(params + p->g_conv3.w_off, p->g_w9f, s));
-  } else if (net == 1) {
-    GCHK(pack_conv(p->d_conv0, params, true, s));
-    for (int k = 0; k < 7; ++k) GCHK(pack_conv(p->d_c[k], params, false, s));
-  } else {
-    if (!p->with_vgg) return -5;
-    for (int i = 0; i < 16; ++i) GCHK(pack_conv(p->v_c[i], params, true, s, 1));    // forward copies in fp16 (see layout)
   }
   return 0;
 }
@@ -642,12 +693,7 @@ int dsr_gant_g_backward(dsr_gant_t* p, const float* params, const float* dout_nc
   GCHK(gl_prelu_bwd(p->g_dX[cur], static_cast<const bf16_t*>(p->g_dT.ptr), p->g_z1, p->g_dR, params + p->g_prelu1,
                     grads + p->g_conv1.b_off, grads + p->g_prelu1, s));
   GCHK(gl_wgrad_in3(p->g_dR, p->g_lr16, grads + p->g_conv1.w_off, 9, s));
-  for (int k = 0; k < p->blocks; ++k) {
-    GCHK(gl_unpack_wgrad(p->g_ca[k].dw, grads + p->g_ca[k].w_off, 64, 64, 3, s));
-    GCHK(gl_unpack_wgrad(p->g_cb[k].dw, grads + p->g_cb[k].w_off, 64, 64, 3, s));
-  }
-  GCHK(gl_unpack_wgrad(p->g_conv2.dw, grads + p->g_conv2.w_off, 64, 64, 3, s));
-  for (int j = 0; j < p->nshuf; ++j) GCHK(gl_unpack_wgrad(p->g_cs[j].dw, grads + p->g_cs[j].w_off, 256, 64, 3, s));
+  GCHK(gl_unpack_group(grads, p->t_unpack[0], static_cast<int>(p->h_unpack[0].size()), p->unpack_blocks[0], s));
   scope.ok = true;
   return 0;
 }
@@ -722,7 +768,7 @@ static int d_convs_backward(dsr_gant* p, int slot, const float* params, float* g
   }
   GCHK(gl_unpack3(p->d_dw3, grads + p->d_conv0.w_off, s));
   GCHK(gl_chan_sum(p->d_dz0, grads + p->d_conv0.b_off, s));
-  for (int k = 0; k < 7; ++k) GCHK(gl_unpack_wgrad(p->d_c[k].dw, grads + p->d_c[k].w_off, p->d_c[k].cout, p->d_c[k].cin, 3, s));
+  GCHK(gl_unpack_group(grads, p->t_unpack[1], static_cast<int>(p->h_unpack[1].size()), p->unpack_blocks[1], s));
   scope.ok = true;
   return 0;
 }
