@@ -669,14 +669,31 @@ __global__ void g_unflatten_kernel(const float* __restrict__ dflat, bf16_t* __re
   }
 }
 
+// 16-byte global -> shared copies that need no registers while in flight (the dense head streams a 302 MB matrix with
+// 8 warps per SM: the bytes in flight have to live somewhere else than the register file)
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst))), "l"(gsrc)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // z1[b][j] = bias[j] + sum_k W[j][k] x[b][k].  grid (J / kD1Rows, kD1KSplit): a block owns kD1Rows rows of W (fp32,
-// streamed once) and a quarter of the columns; partial sums are added atomically into z1 (zeroed first), B <= 8
-constexpr int kD1Rows = 8, kD1KSplit = 4;
-__global__ void __launch_bounds__(kT) g_dense1_fwd_kernel(const float* __restrict__ W, const float* __restrict__ bias,
-                                                          const float* __restrict__ x, float* __restrict__ z1, int B, int K,
-                                                          int J) {
-  __shared__ float sm[8][kD1Rows * 8];
+// streamed once) and a ninth of the columns; partial sums are added atomically into z1 (zeroed first), B <= 8.
+// Every thread keeps a PRIVATE ring of kD1Stages x (8 W + 8 x) 16-byte slots in shared memory, filled by cp.async: a
+// thread only ever reads the slots it copied itself, so the ring needs no barrier, and 2 blocks x 128 threads x 2 stages
+// x 256 B = 128 KB per SM are in flight (the register-staged form had 159.8 us for 304 MB = 1.9 TB/s at 22 % of
+// the warp slots, every warp waiting on its own loads: profiles/r02_gan_train_dense1_fwd_before_raw.csv).
+constexpr int kD1Rows = 8, kD1KSplit = 9, kD1T = 128, kD1Stages = 3;
+constexpr int kD1FwdSmem = kD1Stages * 16 * kD1T * 16;
+__global__ void __launch_bounds__(kD1T) g_dense1_fwd_kernel(const float* __restrict__ W, const float* __restrict__ bias,
+                                                            const float* __restrict__ x, float* __restrict__ z1, int B, int K,
+                                                            int J) {
+  extern __shared__ float4 d1ring[];               // [stage][16][kD1T]
+  __shared__ float sm[kD1T / 32][kD1Rows * 8];
   pdl_sync();
+  const int tid = threadIdx.x;
   const int j0 = blockIdx.x * kD1Rows;
   float acc[kD1Rows][8];
 #pragma unroll
@@ -686,18 +703,38 @@ __global__ void __launch_bounds__(kT) g_dense1_fwd_kernel(const float* __restric
   const int k4n = K >> 2;
   const int kb = static_cast<int>((static_cast<long long>(k4n) * blockIdx.y) / gridDim.y);
   const int ke = static_cast<int>((static_cast<long long>(k4n) * (blockIdx.y + 1)) / gridDim.y);
-  for (int k4 = kb + threadIdx.x; k4 < ke; k4 += kT) {
-    float4 w[kD1Rows];
+  const int niter = (ke - kb + kD1T - 1) / kD1T;
+  const float4* W4 = reinterpret_cast<const float4*>(W) + static_cast<long long>(j0) * k4n;
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  auto issue = [&](int it) {
+    const int k4 = kb + it * kD1T + tid;
+    if (it < niter && k4 < ke) {
+      float4* st = d1ring + (it % kD1Stages) * 16 * kD1T + tid;
 #pragma unroll
-    for (int r = 0; r < kD1Rows; ++r)
-      w[r] = (j0 + r < J) ? __ldcs(reinterpret_cast<const float4*>(W + static_cast<long long>(j0 + r) * K) + k4)
-                          : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int r = 0; r < kD1Rows; ++r) cp_async16(st + r * kD1T, W4 + static_cast<long long>(r) * k4n + k4);
 #pragma unroll
-    for (int b = 0; b < 8; ++b) {
-      if (b < B) {
-        const float4 xv = __ldg(reinterpret_cast<const float4*>(x + static_cast<long long>(b) * K) + k4);
+      for (int b = 0; b < 8; ++b)
+        if (b < B) cp_async16(st + (8 + b) * kD1T, x4 + static_cast<long long>(b) * k4n + k4);
+    }
+    cp_async_commit();
+  };
+  for (int it = 0; it < kD1Stages - 1; ++it) issue(it);
+  for (int it = 0; it < niter; ++it) {
+    issue(it + kD1Stages - 1);
+    cp_async_wait<kD1Stages - 1>();
+    const int k4 = kb + it * kD1T + tid;
+    if (k4 < ke) {
+      const float4* st = d1ring + (it % kD1Stages) * 16 * kD1T + tid;
+      float4 w[kD1Rows];
 #pragma unroll
-        for (int r = 0; r < kD1Rows; ++r) acc[r][b] += w[r].x * xv.x + w[r].y * xv.y + w[r].z * xv.z + w[r].w * xv.w;
+      for (int r = 0; r < kD1Rows; ++r) w[r] = st[r * kD1T];
+#pragma unroll
+      for (int b = 0; b < 8; ++b) {
+        if (b < B) {
+          const float4 xv = st[(8 + b) * kD1T];
+#pragma unroll
+          for (int r = 0; r < kD1Rows; ++r) acc[r][b] += w[r].x * xv.x + w[r].y * xv.y + w[r].z * xv.z + w[r].w * xv.w;
+        }
       }
     }
   }
@@ -715,9 +752,9 @@ __global__ void __launch_bounds__(kT) g_dense1_fwd_kernel(const float* __restric
   if (threadIdx.x < kD1Rows * 8) {
     const int r = threadIdx.x >> 3, b = threadIdx.x & 7;
     float v = 0.f;
-    for (int w = 0; w < 8; ++w) v += sm[w][threadIdx.x];
-    if (blockIdx.y == 0 && j0 + r < J) v += bias[j0 + r];
-    if (j0 + r < J && b < B) atomicAdd(&z1[b * J + j0 + r], v);
+    for (int w = 0; w < kD1T / 32; ++w) v += sm[w][threadIdx.x];
+    if (blockIdx.y == 0) v += bias[j0 + r];
+    if (b < B) atomicAdd(&z1[b * J + j0 + r], v);
   }
 }
 
@@ -776,12 +813,18 @@ __global__ void g_dense2_bwd_kernel(const float* __restrict__ prob, const float*
 // are streamed once instead of twice).  grid (ceil(K / 1024), JS): a block owns 1024 columns and J / JS rows; dx
 // partials are added atomically (dx zeroed first).
 constexpr int kD1Split = 8;
+constexpr int kD1BR = 4, kD1BS = 4;             // rows per ring stage, stages: 4 x 4 x (W + dW) x 16 B = 512 B per thread
+constexpr int kD1BwdRing = kD1BS * 2 * kD1BR * kT * 16;
 struct D1Grp { const float* x; const float* dz1; float* dx; };
+// W and dW rows reach the thread through a private cp.async ring (see g_dense1_fwd_kernel): 3 stages x 4 rows x 32 B x
+// 256 threads = 96 KB in flight per SM instead of the one row (32 B per thread) of the plain loop, which ran the
+// 0.9 GB sweep at 2.25 TB/s (402 us).
 template <int NG>
 __global__ void __launch_bounds__(kT) g_dense1_bwd_kernel(const float* __restrict__ W, D1Grp g0, D1Grp g1,
                                                           float* __restrict__ dW, float* __restrict__ db1, int B, int K,
                                                           int J) {
-  extern __shared__ float dzs[];                 // [jn][8 * NG]
+  extern __shared__ float4 d1bring[];            // [stage][2 * kD1BR][kT], then dzs [jn][8 * NG]
+  float* dzs = reinterpret_cast<float*>(d1bring + kD1BS * 2 * kD1BR * kT);
   pdl_sync();
   const D1Grp grp[2] = {g0, g1};
   const int jn = (J + kD1Split - 1) / kD1Split;
@@ -801,6 +844,25 @@ __global__ void __launch_bounds__(kT) g_dense1_bwd_kernel(const float* __restric
   }
   const int k4 = blockIdx.x * kT + threadIdx.x;
   if (k4 * 4 >= K) return;
+  const int k4n = K >> 2;
+  const float4* W4 = reinterpret_cast<const float4*>(W) + k4;
+  float4* G4 = reinterpret_cast<float4*>(dW) + k4;
+  const int nrg = (je - jb + kD1BR - 1) / kD1BR;
+  auto issue = [&](int rg) {
+    if (rg < nrg) {
+      float4* st = d1bring + (rg % kD1BS) * 2 * kD1BR * kT + threadIdx.x;
+#pragma unroll
+      for (int r = 0; r < kD1BR; ++r) {
+        const int j = jb + rg * kD1BR + r;
+        if (j < je) {
+          cp_async16(st + (2 * r) * kT, W4 + static_cast<long long>(j) * k4n);
+          cp_async16(st + (2 * r + 1) * kT, G4 + static_cast<long long>(j) * k4n);
+        }
+      }
+    }
+    cp_async_commit();
+  };
+  for (int rg = 0; rg < kD1BS - 1; ++rg) issue(rg);
   float4 xv[NG][8], da[NG][8];
 #pragma unroll
   for (int g = 0; g < NG; ++g)
@@ -810,22 +872,34 @@ __global__ void __launch_bounds__(kT) g_dense1_bwd_kernel(const float* __restric
                          : make_float4(0.f, 0.f, 0.f, 0.f);
       da[g][b] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-  for (int j = jb; j < je; ++j) {
-    const float4 w = __ldcs(reinterpret_cast<const float4*>(W + static_cast<long long>(j) * K) + k4);
-    float4 gsum = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float* dzj = &dzs[(j - jb) * 8 * NG];
+  for (int rg = 0; rg < nrg; ++rg) {
+    issue(rg + kD1BS - 1);
+    cp_async_wait<kD1BS - 1>();
+    const float4* st = d1bring + (rg % kD1BS) * 2 * kD1BR * kT + threadIdx.x;
 #pragma unroll
-    for (int g = 0; g < NG; ++g)
+    for (int r = 0; r < kD1BR; ++r) {
+      const int j = jb + rg * kD1BR + r;
+      if (j < je) {
+        const float4 w = st[(2 * r) * kT];
+        float4 o = st[(2 * r + 1) * kT];
+        const float4* dzj = reinterpret_cast<const float4*>(&dzs[(j - jb) * 8 * NG]);
 #pragma unroll
-      for (int b = 0; b < 8; ++b) {
-        const float d = dzj[g * 8 + b];
-        da[g][b].x += d * w.x; da[g][b].y += d * w.y; da[g][b].z += d * w.z; da[g][b].w += d * w.w;
-        gsum.x += d * xv[g][b].x; gsum.y += d * xv[g][b].y; gsum.z += d * xv[g][b].z; gsum.w += d * xv[g][b].w;
+        for (int g = 0; g < NG; ++g)
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const float4 d4 = dzj[g * 2 + h];
+            const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int b = h * 4 + q;
+              const float d = dd[q];
+              da[g][b].x += d * w.x; da[g][b].y += d * w.y; da[g][b].z += d * w.z; da[g][b].w += d * w.w;
+              o.x += d * xv[g][b].x; o.y += d * xv[g][b].y; o.z += d * xv[g][b].z; o.w += d * xv[g][b].w;
+            }
+          }
+        __stcs(G4 + static_cast<long long>(j) * k4n, o);
       }
-    float4* gp = reinterpret_cast<float4*>(dW + static_cast<long long>(j) * K) + k4;
-    float4 o = *gp;
-    o.x += gsum.x; o.y += gsum.y; o.z += gsum.z; o.w += gsum.w;
-    *gp = o;
+    }
   }
 #pragma unroll
   for (int g = 0; g < NG; ++g)
@@ -1242,9 +1316,14 @@ int gl_unflatten(const float* dflat, const GT& dh, cudaStream_t s) {
   GL_CHECK();
 }
 int gl_dense1_fwd(const float* W, const float* bias, const float* x, float* z1, int B, int K, int J, cudaStream_t s) {
-  if (B > 8 || (K & 3)) return -54;
+  if (B > 8 || (K & 3) || (J % kD1Rows)) return -54;
+  static bool attr = false;
+  if (!attr) {
+    if (cudaFuncSetAttribute(g_dense1_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kD1FwdSmem) != cudaSuccess) return -59;
+    attr = true;
+  }
   cudaMemsetAsync(z1, 0, static_cast<size_t>(B) * J * sizeof(float), s);
-  launch_k(g_dense1_fwd_kernel, dim3((J + kD1Rows - 1) / kD1Rows, kD1KSplit), dim3(kT), 0, s, W, bias, x, z1, B, K, J);
+  launch_k(g_dense1_fwd_kernel, dim3(J / kD1Rows, kD1KSplit), dim3(kD1T), kD1FwdSmem, s, W, bias, x, z1, B, K, J);
   GL_CHECK();
 }
 int gl_dense2_fwd(const float* z1, const float* w2, const float* b2, float* prob, int B, int J, cudaStream_t s) {
@@ -1257,25 +1336,38 @@ int gl_dense2_bwd(const float* prob, const float* dprob, float target, const flo
   launch_k(g_dense2_bwd_kernel, dim3((J + kT - 1) / kT), dim3(kT), 0, s, prob, dprob, target, z1, w2, dz1, dw2, db2, B, J);
   GL_CHECK();
 }
+static int dense1_bwd_attr() {
+  static bool attr = false;
+  if (attr) return 0;
+  const int cap = kD1BwdRing + 1024 * 16 * static_cast<int>(sizeof(float));
+  if (cudaFuncSetAttribute(g_dense1_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap) != cudaSuccess) return -59;
+  if (cudaFuncSetAttribute(g_dense1_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap) != cudaSuccess) return -59;
+  attr = true;
+  return 0;
+}
 int gl_dense1_bwd(const float* W, const float* x, const float* dz1, float* dW, float* db1, float* dx, int B, int K, int J,
                   cudaStream_t s) {
   if (B > 8 || (K & 3)) return -54;
-  cudaMemsetAsync(dx, 0, static_cast<size_t>(B) * K * sizeof(float), s);
   const int jn = (J + kD1Split - 1) / kD1Split;
+  if (jn > 1024) return -54;
+  if (dense1_bwd_attr()) return -59;
+  cudaMemsetAsync(dx, 0, static_cast<size_t>(B) * K * sizeof(float), s);
   const D1Grp g0{x, dz1, dx};
-  launch_k(g_dense1_bwd_kernel<1>, dim3((K / 4 + kT - 1) / kT, kD1Split), dim3(kT), static_cast<size_t>(jn) * 8 * sizeof(float),
-           s, W, g0, g0, dW, db1, B, K, J);
+  launch_k(g_dense1_bwd_kernel<1>, dim3((K / 4 + kT - 1) / kT, kD1Split), dim3(kT),
+           kD1BwdRing + static_cast<size_t>(jn) * 8 * sizeof(float), s, W, g0, g0, dW, db1, B, K, J);
   GL_CHECK();
 }
 int gl_dense1_bwd2(const float* W, const float* x0, const float* dz0, float* dx0, const float* x1, const float* dz1,
                    float* dx1, float* dW, float* db1, int B, int K, int J, cudaStream_t s) {
   if (B > 8 || (K & 3)) return -54;
+  const int jn = (J + kD1Split - 1) / kD1Split;
+  if (jn > 1024) return -54;
+  if (dense1_bwd_attr()) return -59;
   cudaMemsetAsync(dx0, 0, static_cast<size_t>(B) * K * sizeof(float), s);
   cudaMemsetAsync(dx1, 0, static_cast<size_t>(B) * K * sizeof(float), s);
-  const int jn = (J + kD1Split - 1) / kD1Split;
   const D1Grp g0{x0, dz0, dx0}, g1{x1, dz1, dx1};
-  launch_k(g_dense1_bwd_kernel<2>, dim3((K / 4 + kT - 1) / kT, kD1Split), dim3(kT), static_cast<size_t>(jn) * 16 * sizeof(float),
-           s, W, g0, g1, dW, db1, B, K, J);
+  launch_k(g_dense1_bwd_kernel<2>, dim3((K / 4 + kT - 1) / kT, kD1Split), dim3(kT),
+           kD1BwdRing + static_cast<size_t>(jn) * 16 * sizeof(float), s, W, g0, g1, dW, db1, B, K, J);
   GL_CHECK();
 }
 int gl_bce(const float* prob, float target, int B, float* loss_out, int accumulate, cudaStream_t s) {
