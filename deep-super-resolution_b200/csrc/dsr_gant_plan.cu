@@ -115,7 +115,8 @@ struct dsr_gant {
   GT v_pre, v_dpre, v_freal;
   int v_Hr = 0, v_Wr = 0, v_top = 0, v_left = 0;
   // ---- shared
-  double* sums = nullptr;                  // BatchNorm-backward scratch [2 * 512 + 1]
+  double* sums = nullptr;                  // BatchNorm-backward scratch [2 * 512 + 1] of the generator's backward pass
+  double* sums_d = nullptr;                // the discriminator's own (its backward may run on another stream, beside G's)
   double* loss_acc = nullptr;
   float* dw_arena[2] = {nullptr, nullptr}; // packed weight gradients of G / D
   size_t dw_bytes[2] = {0, 0};
@@ -192,6 +193,7 @@ size_t layout(dsr_gant* p, uint8_t* base) {
   for (int n = 0; n < 3; ++n) p->t_pack[n] = static_cast<GPackItem*>(a.take(48 * sizeof(GPackItem)));
   for (int n = 0; n < 2; ++n) p->t_unpack[n] = static_cast<GUnpackItem*>(a.take(48 * sizeof(GUnpackItem)));
   p->sums = static_cast<double*>(a.take((2 * 512 + 1) * sizeof(double)));
+  p->sums_d = static_cast<double*>(a.take((2 * 512 + 1) * sizeof(double)));
   p->loss_acc = static_cast<double*>(a.take(64));
   // ---------------- generator ----------------
   {
@@ -740,7 +742,7 @@ static int d_convs_backward(dsr_gant* p, int slot, const float* params, float* g
     const BnL& b = p->d_bn[k];
     const GT& in = (k == 0) ? p->d_h0[slot] : p->d_h[slot][k - 1];
     GCHK(gl_bn_bwd(p->d_ga[k], p->d_raw[slot][k], p->d_gb[k], st, params + b.g_off, params + b.b_off, GACT_LRELU, nullptr,
-                   p->sums, grads + b.g_off, grads + b.b_off, nullptr, s));
+                   p->sums_d, grads + b.g_off, grads + b.b_off, nullptr, s));
     p->launches += 1;
     GCHK(run_wgrad(p, p->d_c[k], p->d_gb[k], in, s));
     if (k > 0) {

@@ -17,6 +17,7 @@ Two ways in, both backed by the same C entry points:
 from __future__ import annotations
 
 import ctypes as C
+import os
 import weakref
 from typing import Dict, List, Optional, Tuple
 
@@ -534,6 +535,8 @@ class GanTrainStep:
         self.device = device
         self._pending_batches = [0, 0]
         self._need_pack = True           # set it again after changing parameters outside do_epoch (load_state_dict)
+        self._one_stream = bool(os.environ.get('DSR_GAN_ONE_STREAM'))
+        self._side = None if self._one_stream else torch.cuda.Stream(device=device)
         with torch.cuda.device(device):
             vgg.pack_into(self.tr, device)
 
@@ -555,35 +558,48 @@ class GanTrainStep:
         HR = HR_patches.to(self.device, non_blocking=True).float().contiguous()
         self.t += 1
         n0 = tr.launch_count
-        # ---- discriminator step (train_GAN.py:43-53).  The bf16 GEMM copies of the weights are refreshed right after each
-        # Adam step below (and here on the first step / after an outside change of the parameters)
+        # The step is TWO chains that only share `fake` (train_GAN.py:43-66: the discriminator sees the generated batch
+        # detached, the generator's gradient is the content loss's alone):
+        #   D chain  D(HR) | D(fake), BCE, backward of both passes, [all-reduce], Adam(D), D(fake) again, BCE -> loss_G
+        #   G chain  G(LR) | VGG loss + gradient, generator backward, [all-reduce], Adam(G)
+        # Most of their launches run at 24 x 24 .. 48 x 48 where a launch costs its latency, not its work, so the D chain
+        # goes to a second stream and the two overlap (DSR_GAN_ONE_STREAM=1: everything on the caller's stream).
+        s0 = torch.cuda.current_stream(self.device)
+        s1 = s0 if self._one_stream else self._side
         if self._need_pack:
             tr.pack(NET_D, fd.flat, force=True)
             tr.pack(NET_G, fg.flat, force=True)
             self._need_pack = False
-        p_real = tr.d_forward(0, fd.flat, fd.bflat, HR)
+        s1.wait_stream(s0)
+        with torch.cuda.stream(s1):
+            p_real = tr.d_forward(0, fd.flat, fd.bflat, HR)
         fake = tr.g_forward(fg.flat, fg.bflat, LR, bn_updates=2)        # the two generator passes of do_epoch are identical
-        p_fake = tr.d_forward(1, fd.flat, fd.bflat, fake)
-        tr.bce(p_real, 1.0, self.loss_D, False)
-        tr.bce(p_fake, 0.0, self.loss_D, True)
-        fd.gflat.zero_()
-        tr.d_backward_pair(fd.flat, fd.gflat, 1.0, 0.0)
-        work = self.xch.start(fd.gflat) if self.dp else None
-        # ---- generator phase, independent of the discriminator: content loss and generator backward (:56-66)
+        s1.wait_stream(s0)
+        with torch.cuda.stream(s1):
+            # ---- discriminator step (train_GAN.py:43-53), its update, and its pass on the generated batch for the
+            # adversarial term of loss_G (:58-59).  The bf16 GEMM copies of the weights are refreshed after each Adam step
+            p_fake = tr.d_forward(1, fd.flat, fd.bflat, fake)
+            tr.bce(p_real, 1.0, self.loss_D, False)
+            tr.bce(p_fake, 0.0, self.loss_D, True)
+            fd.gflat.zero_()
+            tr.d_backward_pair(fd.flat, fd.gflat, 1.0, 0.0)
+            if self.dp:
+                self.xch.allreduce_mean(fd.gflat)
+            self._adam(fd.flat, fd.gflat, self.mD, self.vD)
+            tr.pack(NET_D, fd.flat, force=True)
+            p_fake2 = tr.d_forward(0, fd.flat, fd.bflat, fake)
+        # ---- generator phase: content loss and generator backward (:56-66)
         dfake = tr.vgg_loss(fake, HR, self.loss_G, False, True)
+        s1.wait_stream(s0)                                              # loss_G holds the content term before BCE is added
+        with torch.cuda.stream(s1):
+            tr.bce(p_fake2, 1.0, self.loss_G, True)
         fg.gflat.zero_()
         tr.g_backward(fg.flat, dfake, fg.gflat)
-        # ---- discriminator update, then its pass on the generated batch for the adversarial term of loss_G (:58-59)
-        if work is not None:
-            self.xch.finish(work, fd.gflat)
-        self._adam(fd.flat, fd.gflat, self.mD, self.vD)
-        tr.pack(NET_D, fd.flat, force=True)
-        p_fake2 = tr.d_forward(0, fd.flat, fd.bflat, fake)
-        tr.bce(p_fake2, 1.0, self.loss_G, True)
         if self.dp:
             self.xch.allreduce_mean(fg.gflat)
         self._adam(fg.flat, fg.gflat, self.mG, self.vG)
         tr.pack(NET_G, fg.flat, force=True)
+        s0.wait_stream(s1)
         self.launches_per_step = tr.launch_count - n0
         self._pending_batches[0] += 2
         self._pending_batches[1] += 3
