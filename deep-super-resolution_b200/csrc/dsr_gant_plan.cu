@@ -127,7 +127,7 @@ struct dsr_gant {
   GPackItem* t_pack[3] = {nullptr, nullptr, nullptr};
   GUnpackItem* t_unpack[2] = {nullptr, nullptr};
   int pack_blocks[3] = {0, 0, 0}, unpack_blocks[2] = {0, 0};
-  Tape tp_gf, tp_gb, tp_df[2], tp_db[2], tp_v, tp_vl;
+  Tape tp_gf, tp_gb, tp_df[2], tp_db[2], tp_v, tp_vl, tp_vr, tp_v2, tp_vl2;
   Tape* tape = nullptr;                    // the running entry point's tape
 };
 
@@ -539,7 +539,9 @@ int dsr_gant_bind(dsr_gant_t* p, void* workspace, size_t bytes, void* stream) {
   cudaError_t e = cudaMemsetAsync(workspace, 0, p->ws_bytes, s);      // gap rows and padded channels stay zero from here on
   if (e != cudaSuccess) return static_cast<int>(e);
   layout(p, static_cast<uint8_t*>(workspace));
-  for (Tape* t : {&p->tp_gf, &p->tp_gb, &p->tp_df[0], &p->tp_df[1], &p->tp_db[0], &p->tp_db[1], &p->tp_v, &p->tp_vl}) t->clear();
+  for (Tape* t : {&p->tp_gf, &p->tp_gb, &p->tp_df[0], &p->tp_df[1], &p->tp_db[0], &p->tp_db[1], &p->tp_v, &p->tp_vl, &p->tp_vr,
+                  &p->tp_v2, &p->tp_vl2})
+    t->clear();
   const int rc = build_group_tables(p, s);
   if (rc) return rc;
   p->bound = true;
@@ -834,15 +836,32 @@ static int vgg_forward(dsr_gant* p, const float* img, cudaStream_t s) {
   return 0;
 }
 
-int dsr_gant_vgg_loss(dsr_gant_t* p, const float* fake_nchw, const float* real_nchw, float* loss, int accumulate,
-                      float* dfake_nchw, void* stream) {
-  if (!p || !p->bound || !p->with_vgg || !fake_nchw || !real_nchw || !loss) return -1;
+// The features of the REAL batch alone (they do not depend on the generator: a caller may compute them on another stream
+// while the generator's forward pass runs); dsr_gant_vgg_loss(..., real_nchw = NULL, ...) then uses them.  The pass
+// writes the VGG activation buffers, so it must be complete before that call starts and must not overlap another one.
+int dsr_gant_vgg_real(dsr_gant_t* p, const float* real_nchw, void* stream) {
+  if (!p || !p->bound || !p->with_vgg || !real_nchw) return -1;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   p->launches = 0;
-  TapeScope scope(p, dfake_nchw ? &p->tp_v : &p->tp_vl);
+  TapeScope scope(p, &p->tp_vr);
   int rc;
   if ((rc = vgg_forward(p, real_nchw, s))) return rc;
   cudaMemcpyAsync(p->v_freal.ptr, p->v_y[15].ptr, p->v_freal.bytes(), cudaMemcpyDeviceToDevice, s);
+  scope.ok = true;
+  return 0;
+}
+
+int dsr_gant_vgg_loss(dsr_gant_t* p, const float* fake_nchw, const float* real_nchw, float* loss, int accumulate,
+                      float* dfake_nchw, void* stream) {
+  if (!p || !p->bound || !p->with_vgg || !fake_nchw || !loss) return -1;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  p->launches = 0;
+  TapeScope scope(p, real_nchw ? (dfake_nchw ? &p->tp_v : &p->tp_vl) : (dfake_nchw ? &p->tp_v2 : &p->tp_vl2));
+  int rc;
+  if (real_nchw) {
+    if ((rc = vgg_forward(p, real_nchw, s))) return rc;
+    cudaMemcpyAsync(p->v_freal.ptr, p->v_y[15].ptr, p->v_freal.bytes(), cudaMemcpyDeviceToDevice, s);
+  }
   if ((rc = vgg_forward(p, fake_nchw, s))) return rc;
   cudaMemsetAsync(p->loss_acc, 0, sizeof(double), s);
   const int top = static_cast<int>(p->v_ga.size()) - 1;

@@ -104,6 +104,7 @@ SIGNATURES = {
     'dsr_gant_d_backward_pair': (i32, [vp, vp, f32, f32, vp, vp]),
     'dsr_gant_bce': (i32, [vp, vp, f32, i32, vp, i32, vp]),
     'dsr_gant_vgg_loss': (i32, [vp, vp, vp, vp, i32, vp, vp]),
+    'dsr_gant_vgg_real': (i32, [vp, vp, vp]),
     'dsr_gant_device_error': (i32, [vp, C.POINTER(i32)]),
     'dsr_gant_last_launches': (i32, [vp]),
     'dsr_gant_tensor': (i32, [vp, C.c_char_p, C.POINTER(vp), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32),

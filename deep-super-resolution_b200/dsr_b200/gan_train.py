@@ -121,9 +121,15 @@ class Trainer:
                                _lib.stream_ptr()), 'dsr_gant_bce')
         self.launch_count += 1
 
+    def vgg_real(self, real) -> None:
+        """VGG features of the real batch alone; ``vgg_loss(fake, None, ...)`` then uses them."""
+        check(lib.dsr_gant_vgg_real(self.handle, real.data_ptr(), _lib.stream_ptr()), 'dsr_gant_vgg_real')
+        self._count()
+
     def vgg_loss(self, fake, real, loss, accumulate: bool, want_grad: bool) -> Optional[torch.Tensor]:
         dfake = torch.empty_like(fake) if want_grad else None
-        check(lib.dsr_gant_vgg_loss(self.handle, fake.data_ptr(), real.data_ptr(), loss.data_ptr(), int(accumulate),
+        check(lib.dsr_gant_vgg_loss(self.handle, fake.data_ptr(), real.data_ptr() if real is not None else None,
+                                    loss.data_ptr(), int(accumulate),
                                     dfake.data_ptr() if want_grad else None, _lib.stream_ptr()), 'dsr_gant_vgg_loss')
         self._count()
         return dfake
@@ -537,6 +543,8 @@ class GanTrainStep:
         self._need_pack = True           # set it again after changing parameters outside do_epoch (load_state_dict)
         self._one_stream = bool(os.environ.get('DSR_GAN_ONE_STREAM'))
         self._side = None if self._one_stream else torch.cuda.Stream(device=device)
+        self._side2 = (torch.cuda.Stream(device=device)
+                       if (not self._one_stream and not os.environ.get('DSR_GAN_VGG_REAL_LATE')) else None)
         with torch.cuda.device(device):
             vgg.pack_into(self.tr, device)
 
@@ -563,7 +571,9 @@ class GanTrainStep:
         #   D chain  D(HR) | D(fake), BCE, backward of both passes, [all-reduce], Adam(D), D(fake) again, BCE -> loss_G
         #   G chain  G(LR) | VGG loss + gradient, generator backward, [all-reduce], Adam(G)
         # Most of their launches run at 24 x 24 .. 48 x 48 where a launch costs its latency, not its work, so the D chain
-        # goes to a second stream and the two overlap (DSR_GAN_ONE_STREAM=1: everything on the caller's stream).
+        # goes to a second stream and the two overlap (DSR_GAN_ONE_STREAM=1: everything on the caller's stream); the VGG
+        # features of the REAL batch run on a third one beside the generator's forward pass (6.69 -> 6.55 ms; a high-
+        # priority stream for the G chain made it slower: 6.88 ms).
         s0 = torch.cuda.current_stream(self.device)
         s1 = s0 if self._one_stream else self._side
         if self._need_pack:
@@ -571,9 +581,15 @@ class GanTrainStep:
             tr.pack(NET_G, fg.flat, force=True)
             self._need_pack = False
         s1.wait_stream(s0)
+        if self._side2 is not None:                  # VGG features of the real batch while the generator runs
+            self._side2.wait_stream(s0)
+            with torch.cuda.stream(self._side2):
+                tr.vgg_real(HR)
         with torch.cuda.stream(s1):
             p_real = tr.d_forward(0, fd.flat, fd.bflat, HR)
         fake = tr.g_forward(fg.flat, fg.bflat, LR, bn_updates=2)        # the two generator passes of do_epoch are identical
+        if self._side2 is not None:
+            s0.wait_stream(self._side2)
         s1.wait_stream(s0)
         with torch.cuda.stream(s1):
             # ---- discriminator step (train_GAN.py:43-53), its update, and its pass on the generated batch for the
@@ -589,7 +605,7 @@ class GanTrainStep:
             tr.pack(NET_D, fd.flat, force=True)
             p_fake2 = tr.d_forward(0, fd.flat, fd.bflat, fake)
         # ---- generator phase: content loss and generator backward (:56-66)
-        dfake = tr.vgg_loss(fake, HR, self.loss_G, False, True)
+        dfake = tr.vgg_loss(fake, None if self._side2 is not None else HR, self.loss_G, False, True)
         s1.wait_stream(s0)                                              # loss_G holds the content term before BCE is added
         with torch.cuda.stream(s1):
             tr.bce(p_fake2, 1.0, self.loss_G, True)

@@ -246,9 +246,13 @@ int dsr_gant_d_backward(dsr_gant_t* p, int slot, const float* params, const floa
 int dsr_gant_d_backward_pair(dsr_gant_t* p, const float* params, float target0, float target1, float* grads, void* stream);
 /* loss[0] (= | +=) nn.BCELoss()(prob[0..n), target) */
 int dsr_gant_bce(dsr_gant_t* p, const float* prob, float target, int n, float* loss, int accumulate, void* stream);
-/* loss[0] (= | +=) MSE(VGG(T(fake)), VGG(T(real))); dfake (may be NULL) = its gradient w.r.t. fake. */
+/* loss[0] (= | +=) MSE(VGG(T(fake)), VGG(T(real))); dfake (may be NULL) = its gradient w.r.t. fake.  real_nchw may be
+ * NULL when dsr_gant_vgg_real computed the real batch's features before (utils/GAN.py:72-93: the two feature passes are
+ * independent; only the second depends on the generator). */
 int dsr_gant_vgg_loss(dsr_gant_t* p, const float* fake_nchw, const float* real_nchw, float* loss, int accumulate,
                       float* dfake_nchw, void* stream);
+/* VGG(T(real)) alone, kept for the next dsr_gant_vgg_loss(..., NULL, ...); it must be complete before that call starts. */
+int dsr_gant_vgg_real(dsr_gant_t* p, const float* real_nchw, void* stream);
 int dsr_gant_device_error(dsr_gant_t* p, int* host_code);
 int dsr_gant_last_launches(const dsr_gant_t* p);
 /* Tests: a named activation of the last pass ([B * P][W][C] tall grid, image b at rows [b P, b P + H)); *f32 receives
