@@ -892,8 +892,8 @@ def run_gan_train(args, rank, local_rank, world):
         ms, ms_e2e, ar_ms = float(t[0]), float(t[1]), float(t[2])
         ar = {'ms_per_step': ar_ms, 'bytes_per_step': nbytes, 'algbw_GBps': nbytes / (ar_ms * 1e-3) / 1e9,
               'busbw_GBps': 2 * (world - 1) / world * nbytes / (ar_ms * 1e-3) / 1e9,
-              'note': 'timed alone; inside the step the discriminator all-reduce runs on a side stream under the VGG / '
-                      'generator-backward phase'}
+              'note': 'timed alone; inside the step the discriminator all-reduce sits in the discriminator chain (second '
+                      'stream), which runs beside the generator chain (VGG loss, generator backward)'}
     if rank != 0:
         return
     pk = peaks()
@@ -906,6 +906,8 @@ def run_gan_train(args, rank, local_rank, world):
             'config': {'workload': f'SRGAN training step (train_GAN.do_epoch), batch {GT_B} of {GT_LR}x{GT_LR} -> 192x192 '
                                    f'patches per GPU, random-weight VGG19 (BASELINE configs[4])', 'batch': GT_B, 'factor': 8,
                        'parallelism': f'dp{world}' if world > 1 else 'single',
+                       'streams': 'discriminator chain, generator chain and the VGG pass of the real batch on three '
+                                  'streams of one process (they share only the generated batch)',
                        'l2': 'activations of one step are ~1.4 GB >> 126 MB L2'},
             'roofline': {'bound': 'tensor', 'kernel': 'whole step: gconv_kernel / gwgrad_kernel (bf16 implicit GEMM) + element-wise family',
                          'achieved': tfl, 'peak': pk['tflops'], 'unit': 'TFLOP/s',

@@ -822,7 +822,7 @@ struct D1Grp { const float* x; const float* dz1; float* dx; };
 template <int NG>
 __global__ void __launch_bounds__(kT) g_dense1_bwd_kernel(const float* __restrict__ W, D1Grp g0, D1Grp g1,
                                                           float* __restrict__ dW, float* __restrict__ db1, int B, int K,
-                                                          int J) {
+                                                          int J, int acc) {      // acc = 0: dW is written, not added to
   extern __shared__ float4 d1bring[];            // [stage][2 * kD1BR][kT], then dzs [jn][8 * NG]
   float* dzs = reinterpret_cast<float*>(d1bring + kD1BS * 2 * kD1BR * kT);
   pdl_sync();
@@ -856,7 +856,7 @@ __global__ void __launch_bounds__(kT) g_dense1_bwd_kernel(const float* __restric
         const int j = jb + rg * kD1BR + r;
         if (j < je) {
           cp_async16(st + (2 * r) * kT, W4 + static_cast<long long>(j) * k4n);
-          cp_async16(st + (2 * r + 1) * kT, G4 + static_cast<long long>(j) * k4n);
+          if (acc) cp_async16(st + (2 * r + 1) * kT, G4 + static_cast<long long>(j) * k4n);
         }
       }
     }
@@ -881,7 +881,7 @@ __global__ void __launch_bounds__(kT) g_dense1_bwd_kernel(const float* __restric
       const int j = jb + rg * kD1BR + r;
       if (j < je) {
         const float4 w = st[(2 * r) * kT];
-        float4 o = st[(2 * r + 1) * kT];
+        float4 o = acc ? st[(2 * r + 1) * kT] : make_float4(0.f, 0.f, 0.f, 0.f);
         const float4* dzj = reinterpret_cast<const float4*>(&dzs[(j - jb) * 8 * NG]);
 #pragma unroll
         for (int g = 0; g < NG; ++g)
@@ -1354,11 +1354,11 @@ int gl_dense1_bwd(const float* W, const float* x, const float* dz1, float* dW, f
   cudaMemsetAsync(dx, 0, static_cast<size_t>(B) * K * sizeof(float), s);
   const D1Grp g0{x, dz1, dx};
   launch_k(g_dense1_bwd_kernel<1>, dim3((K / 4 + kT - 1) / kT, kD1Split), dim3(kT),
-           kD1BwdRing + static_cast<size_t>(jn) * 8 * sizeof(float), s, W, g0, g0, dW, db1, B, K, J);
+           kD1BwdRing + static_cast<size_t>(jn) * 8 * sizeof(float), s, W, g0, g0, dW, db1, B, K, J, 1);
   GL_CHECK();
 }
 int gl_dense1_bwd2(const float* W, const float* x0, const float* dz0, float* dx0, const float* x1, const float* dz1,
-                   float* dx1, float* dW, float* db1, int B, int K, int J, cudaStream_t s) {
+                   float* dx1, float* dW, float* db1, int B, int K, int J, int accumulate, cudaStream_t s) {
   if (B > 8 || (K & 3)) return -54;
   const int jn = (J + kD1Split - 1) / kD1Split;
   if (jn > 1024) return -54;
@@ -1367,7 +1367,7 @@ int gl_dense1_bwd2(const float* W, const float* x0, const float* dz0, float* dx0
   cudaMemsetAsync(dx1, 0, static_cast<size_t>(B) * K * sizeof(float), s);
   const D1Grp g0{x0, dz0, dx0}, g1{x1, dz1, dx1};
   launch_k(g_dense1_bwd_kernel<2>, dim3((K / 4 + kT - 1) / kT, kD1Split), dim3(kT),
-           kD1BwdRing + static_cast<size_t>(jn) * 16 * sizeof(float), s, W, g0, g1, dW, db1, B, K, J);
+           kD1BwdRing + static_cast<size_t>(jn) * 16 * sizeof(float), s, W, g0, g1, dW, db1, B, K, J, accumulate);
   GL_CHECK();
 }
 int gl_bce(const float* prob, float target, int B, float* loss_out, int accumulate, cudaStream_t s) {

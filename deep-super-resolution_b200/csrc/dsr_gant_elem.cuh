@@ -48,7 +48,7 @@ int gl_dense1_bwd(const float* W, const float* x, const float* dz1, float* dW, f
                   cudaStream_t s);
 // the same for two groups of B samples (two forward passes) in one sweep over W / dW
 int gl_dense1_bwd2(const float* W, const float* x0, const float* dz0, float* dx0, const float* x1, const float* dz1,
-                   float* dx1, float* dW, float* db1, int B, int K, int J, cudaStream_t s);
+                   float* dx1, float* dW, float* db1, int B, int K, int J, int accumulate, cudaStream_t s);
 int gl_bce(const float* prob, float target, int B, float* loss_out, int accumulate, cudaStream_t s);
 // weights
 int gl_pack_weight(const float* w_oihw, const float* bias, int cout, int cin, int ks, int cout_pad, int cin_pad,

@@ -121,6 +121,7 @@ struct dsr_gant {
   float* dw_arena[2] = {nullptr, nullptr}; // packed weight gradients of G / D
   size_t dw_bytes[2] = {0, 0};
   int launches = 0;
+  int dense_overwrite = 0;                 // d_backward_pair writes (not adds) dense1.weight's gradient
   // one-launch weight packing / gradient unpacking per network: item tables (host copy, device copy, grid size)
   std::vector<GPackItem> h_pack[3];
   std::vector<GUnpackItem> h_unpack[2];
@@ -802,7 +803,7 @@ int dsr_gant_d_backward_pair(dsr_gant_t* p, const float* params, float target0, 
     GCHK(gl_dense2_bwd(p->d_prob[slot], nullptr, tg[slot], p->d_z1[slot], params + p->d_w2, p->d_dz1[slot], grads + p->d_w2,
                        grads + p->d_b2, p->B, 1024, s));
   GCHK(gl_dense1_bwd2(params + p->d_w1, p->d_flat[0], p->d_dz1[0], p->d_dflat[0], p->d_flat[1], p->d_dz1[1], p->d_dflat[1],
-                      grads + p->d_w1, grads + p->d_b1, p->B, p->d_K, 1024, s));
+                      grads + p->d_w1, grads + p->d_b1, p->B, p->d_K, 1024, p->dense_overwrite ? 0 : 1, s));
   const int n = p->launches;
   int rc = d_convs_backward(p, 0, params, grads, s);
   if (rc) return rc;
@@ -810,6 +811,12 @@ int dsr_gant_d_backward_pair(dsr_gant_t* p, const float* params, float target0, 
   rc = d_convs_backward(p, 1, params, grads, s);
   p->launches += n0 - n;
   return rc;
+}
+
+int dsr_gant_dense_grad_overwrite(dsr_gant_t* p, int on) {
+  if (!p) return -1;
+  p->dense_overwrite = on ? 1 : 0;
+  return 0;
 }
 
 int dsr_gant_bce(dsr_gant_t* p, const float* prob, float target, int n, float* loss, int accumulate, void* stream) {

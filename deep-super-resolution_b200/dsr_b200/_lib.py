@@ -103,6 +103,7 @@ SIGNATURES = {
     'dsr_gant_d_backward': (i32, [vp, i32, vp, vp, f32, vp, vp]),
     'dsr_gant_d_backward_pair': (i32, [vp, vp, f32, f32, vp, vp]),
     'dsr_gant_bce': (i32, [vp, vp, f32, i32, vp, i32, vp]),
+    'dsr_gant_dense_grad_overwrite': (i32, [vp, i32]),
     'dsr_gant_vgg_loss': (i32, [vp, vp, vp, vp, i32, vp, vp]),
     'dsr_gant_vgg_real': (i32, [vp, vp, vp]),
     'dsr_gant_device_error': (i32, [vp, C.POINTER(i32)]),

@@ -111,9 +111,16 @@ class Trainer:
                                       float(target), grads.data_ptr(), _lib.stream_ptr()), 'dsr_gant_d_backward')
         self._count()
 
-    def d_backward_pair(self, params, grads, target0: float, target1: float) -> None:
-        check(lib.dsr_gant_d_backward_pair(self.handle, params.data_ptr(), float(target0), float(target1), grads.data_ptr(),
-                                           _lib.stream_ptr()), 'dsr_gant_d_backward_pair')
+    def d_backward_pair(self, params, grads, target0: float, target1: float, dense_overwrite: bool = False) -> None:
+        """``dense_overwrite``: the gradient of dense1.weight is written, not added to (the caller skipped clearing it)."""
+        if dense_overwrite:
+            check(lib.dsr_gant_dense_grad_overwrite(self.handle, 1))
+        try:
+            check(lib.dsr_gant_d_backward_pair(self.handle, params.data_ptr(), float(target0), float(target1),
+                                               grads.data_ptr(), _lib.stream_ptr()), 'dsr_gant_d_backward_pair')
+        finally:
+            if dense_overwrite:
+                check(lib.dsr_gant_dense_grad_overwrite(self.handle, 0))
         self._count()
 
     def bce(self, prob, target: float, loss, accumulate: bool) -> None:
@@ -541,6 +548,8 @@ class GanTrainStep:
         self.device = device
         self._pending_batches = [0, 0]
         self._need_pack = True           # set it again after changing parameters outside do_epoch (load_state_dict)
+        span = [(off, off + n) for name, off, n in self.tr.layout(NET_D)['params'] if name == 'dense1.weight']
+        self._dense_span = span[0]
         self._one_stream = bool(os.environ.get('DSR_GAN_ONE_STREAM'))
         self._side = None if self._one_stream else torch.cuda.Stream(device=device)
         self._side2 = (torch.cuda.Stream(device=device)
@@ -597,8 +606,12 @@ class GanTrainStep:
             p_fake = tr.d_forward(1, fd.flat, fd.bflat, fake)
             tr.bce(p_real, 1.0, self.loss_D, False)
             tr.bce(p_fake, 0.0, self.loss_D, True)
-            fd.gflat.zero_()
-            tr.d_backward_pair(fd.flat, fd.gflat, 1.0, 0.0)
+            # zero_grad() + loss_D.backward(): dense1.weight's gradient (302 of the 321 MB) is written by the backward
+            # pass instead of cleared here and added to there
+            a, b = self._dense_span
+            fd.gflat[:a].zero_()
+            fd.gflat[b:].zero_()
+            tr.d_backward_pair(fd.flat, fd.gflat, 1.0, 0.0, dense_overwrite=True)
             if self.dp:
                 self.xch.allreduce_mean(fd.gflat)
             self._adam(fd.flat, fd.gflat, self.mD, self.vD)

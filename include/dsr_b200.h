@@ -244,6 +244,10 @@ int dsr_gant_d_backward(dsr_gant_t* p, int slot, const float* params, const floa
 /* Both kept passes in one call (loss_D.backward() of do_epoch): slot 0 against target0, slot 1 against target1, BCE fused;
  * the dense head's 73 728 x 1024 matrix and its gradient are swept once for the two passes. */
 int dsr_gant_d_backward_pair(dsr_gant_t* p, const float* params, float target0, float target1, float* grads, void* stream);
+/* on != 0: dsr_gant_d_backward_pair WRITES the gradient of dense1.weight (73 728 x 1024, 302 MB) instead of adding to it,
+ * so the caller need not clear that part of `grads` before the call (loss_D.backward() after zero_grad(),
+ * train_GAN.py:50-52): saves one 302 MB fill and one 302 MB read per step.  Every other gradient is still added. */
+int dsr_gant_dense_grad_overwrite(dsr_gant_t* p, int on);
 /* loss[0] (= | +=) nn.BCELoss()(prob[0..n), target) */
 int dsr_gant_bce(dsr_gant_t* p, const float* prob, float target, int n, float* loss, int accumulate, void* stream);
 /* loss[0] (= | +=) MSE(VGG(T(fake)), VGG(T(real))); dfake (may be NULL) = its gradient w.r.t. fake.  real_nchw may be
