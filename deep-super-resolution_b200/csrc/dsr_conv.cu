@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);   // one arrive per epilogue warp
+      mbar_init(&tempty_bar[s], (blockDim.x >> 5) - 2);   // one arrive per epilogue warp (4 or 8)
     }
     fence_barrier_init();
   }
@@ -163,9 +163,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     }
   } else {
     // ===================== epilogue: TMEM -> registers -> HBM (+ BN statistics) =====================
+    // 8 epilogue warps: two per TMEM lane quarter, which take the even / the odd 16-column chunks (layers with a small
+    // K -- the 32-channel first layer: 18 MMAs per tile -- are bound by this epilogue, not by the MMAs)
     const int quarter = warp & 3;              // TMEM lane quarter this warp may read
     const int row = quarter * 32 + lane;       // pixel index inside the tile
     const int nchunks = p.n_mma >> 4;
+    const int cmask = (blockDim.x >> 5) > 6 ? 1 : 0, chalf = (warp - 2) >> 2;
     float acc_s[9], acc_q[9];
 #pragma unroll
     for (int c = 0; c < 9; ++c) { acc_s[c] = 0.f; acc_q[c] = 0.f; }
@@ -183,7 +186,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       const long long obase = ci.out_off + static_cast<long long>(y) * p.out_sy + static_cast<long long>(x) * p.out_sx;
 #pragma unroll
       for (int c = 0; c < 9; ++c) {
-        if (c < nchunks) {
+        if (c < nchunks && (c & cmask) == (chalf & cmask)) {
           uint32_t v[16];
           tmem_ld16(taddr + static_cast<uint32_t>(c * 16), v);
           tmem_ld_wait();
@@ -249,7 +252,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
 #pragma unroll
       for (int c = 0; c < 9; ++c) {
-        if (c < nchunks) {
+        if (c < nchunks && (c & cmask) == (chalf & cmask)) {
           acc_add_f(&p.stats[c * 16 + col], acc_s[c]);
           acc_add_f(&p.stats[p.n_mma + c * 16 + col], acc_q[c]);
         }
@@ -1504,7 +1507,8 @@ int launch_conv_gemm(const ConvGemmParams& p, int num_sms, cudaStream_t stream) 
   const int ntiles = p.ncls ? p.cls_tile0[p.ncls] : p.tiles_x * p.tiles_y;
   if (ntiles <= 0) return 0;
   const int grid = ntiles < num_sms ? ntiles : num_sms;
-  launch_k(conv_gemm_kernel, dim3(grid), dim3(kConvThreads), kConvSmemBytes, stream, p);
+  static const int threads = getenv("DSR_CONV_EPI4") ? 192 : kConvThreads;
+  launch_k(conv_gemm_kernel, dim3(grid), dim3(threads), kConvSmemBytes, stream, p);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -13,7 +13,7 @@
 
 namespace dsr {
 
-constexpr int kConvThreads = 192;       // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue
+constexpr int kConvThreads = 320;       // warp 0: TMA producer, warp 1: MMA issuer, warps 2-9: epilogue (2 per lane quarter)
 constexpr int kConvStages = 5;
 constexpr int kConvStageA = 128 * 128;  // 128 pixels x 64 ch x 2 B
 constexpr int kConvStageB = 144 * 128;  // up to 144 rows x 64 ch x 2 B
