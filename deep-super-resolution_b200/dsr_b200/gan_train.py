@@ -597,9 +597,9 @@ class GanTrainStep:
         with torch.cuda.stream(s1):
             p_real = tr.d_forward(0, fd.flat, fd.bflat, HR)
         fake = tr.g_forward(fg.flat, fg.bflat, LR, bn_updates=2)        # the two generator passes of do_epoch are identical
+        s1.wait_stream(s0)                                              # `fake` is complete (before s0 joins the VGG pass)
         if self._side2 is not None:
             s0.wait_stream(self._side2)
-        s1.wait_stream(s0)
         with torch.cuda.stream(s1):
             # ---- discriminator step (train_GAN.py:43-53), its update, and its pass on the generated batch for the
             # adversarial term of loss_G (:58-59).  The bf16 GEMM copies of the weights are refreshed after each Adam step
