@@ -157,6 +157,46 @@ __global__ void __launch_bounds__(256) ssim_kernel(const float* __restrict__ pre
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// eval_GAN.py:50-53 image writer path: resolved image [B][C][H][W] fp32 -> [B][H][W][C] uint8 ON THE DEVICE, so that a
+// quarter of the bytes crosses PCIe and the host only encodes the PNG.
+//   clip = 0: (x.transpose(1, 2, 0) * 255).astype(np.uint8) of eval_GAN.py:52 -- numpy's cast truncates towards zero and
+//             keeps the low byte (the generator ends in tanh: negative values wrap, -127.5 -> 129), NaN -> 0
+//   clip = 1: np.clip(x * 255, 0, 255).astype(np.uint8) of utils/common.py:81 (np_to_pil)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned int to_u8(float v, int clip) {
+  float t = v * 255.f;
+  if (clip) t = fminf(fmaxf(t, 0.f), 255.f);            // fmaxf(NaN, 0) = 0, as np.clip propagates NaN -> cast 0
+  return static_cast<unsigned int>(__float2int_rz(t)) & 0xFFu;
+}
+__global__ void image_to_u8_hwc_kernel(const float* __restrict__ chw, int C, long long hw, int clip,
+                                       unsigned char* __restrict__ out) {
+  pdl_sync();
+  const float* src = chw + static_cast<long long>(blockIdx.y) * C * hw;
+  unsigned char* dst = out + static_cast<long long>(blockIdx.y) * C * hw;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  if (C == 3 && (hw & 3) == 0) {
+    // 4 pixels per thread: one float4 per plane in, three 32-bit words (12 bytes) out
+    for (long long q = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; q < (hw >> 2); q += stride) {
+      float4 v[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) v[c] = __ldg(reinterpret_cast<const float4*>(src + c * hw) + q);
+      const float f[12] = {v[0].x, v[1].x, v[2].x, v[0].y, v[1].y, v[2].y, v[0].z, v[1].z, v[2].z, v[0].w, v[1].w, v[2].w};
+      unsigned int w[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+        w[k] = to_u8(f[4 * k], clip) | (to_u8(f[4 * k + 1], clip) << 8) | (to_u8(f[4 * k + 2], clip) << 16) |
+               (to_u8(f[4 * k + 3], clip) << 24);
+      unsigned int* o = reinterpret_cast<unsigned int*>(dst) + q * 3;
+      o[0] = w[0]; o[1] = w[1]; o[2] = w[2];
+    }
+    return;
+  }
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < hw; i += stride)
+    for (int c = 0; c < C; ++c) dst[i * C + c] = static_cast<unsigned char>(to_u8(src[c * hw + i], clip));
+}
+
 }  // namespace
 }  // namespace dsr
 
@@ -203,6 +243,18 @@ int dsr_ssim(const float* pred, const float* target, int planes, int H, int W, f
   const float c1 = (0.01f * data_range) * (0.01f * data_range), c2 = (0.03f * data_range) * (0.03f * data_range);
   launch_k(ssim_kernel, dim3(static_cast<unsigned>(planes * tiles)), dim3(256), 0, static_cast<cudaStream_t>(stream), pred,
            target, planes, H, W, c1, c2, static_cast<MetricWs*>(workspace), out);
+  return static_cast<int>(cudaGetLastError());
+}
+
+
+int dsr_image_to_u8_hwc(const float* chw, int B, int C, int H, int W, int clip, unsigned char* out_hwc, void* stream) {
+  if (!chw || !out_hwc || B < 1 || C < 1 || H < 1 || W < 1) return -1;
+  const long long hw = static_cast<long long>(H) * W;
+  if ((reinterpret_cast<uintptr_t>(chw) & 15) || (reinterpret_cast<uintptr_t>(out_hwc) & 3)) return -3;
+  long long blocks = ((C == 3 && (hw & 3) == 0 ? hw / 4 : hw) + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  launch_k(image_to_u8_hwc_kernel, dim3(static_cast<unsigned>(blocks), static_cast<unsigned>(B)), dim3(256), 0,
+           static_cast<cudaStream_t>(stream), chw, C, hw, clip, out_hwc);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -11,3 +11,4 @@ from .optim import optimize, get_params, get_noise, fill_noise   # noqa: F401
 from .dip import DIP_ISR, dip_sr_fused                # noqa: F401
 from .gan import Generator                            # noqa: F401
 from .metrics import PeakSignalNoiseRatio, StructuralSimilarityIndexMeasure   # noqa: F401
+from .evalgan import to_uint8_hwc, GAN_ISR_Batch_eval   # noqa: F401

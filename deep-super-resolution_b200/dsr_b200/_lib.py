@@ -85,6 +85,7 @@ SIGNATURES = {
     'dsr_metric_workspace_bytes': (sz, []),
     'dsr_psnr': (i32, [vp, vp, i64, f32, vp, vp, vp]),
     'dsr_ssim': (i32, [vp, vp, i32, i32, i32, f32, vp, vp, vp]),
+    'dsr_image_to_u8_hwc': (i32, [vp, i32, i32, i32, i32, i32, vp, vp]),
     'dsr_plan_deterministic': (i32, [vp]),
     'dsr_gant_create': (i32, [C.POINTER(vp), i32, i32, i32, i32, i32, i32]),
     'dsr_gant_destroy': (None, [vp]),

@@ -204,6 +204,12 @@ int dsr_psnr(const float* pred, const float* target, long long n, float data_ran
  * k2 0.03, averaged over the pixels whose window lies inside the image. */
 int dsr_ssim(const float* pred, const float* target, int planes, int H, int W, float data_range, void* workspace,
              float* out, void* stream);
+/* ---- image writer path of eval_GAN.py:50-53 (GAN_ISR_Batch_eval) and utils/common.py:76-88 (np_to_pil) ----------
+ * out_hwc[b][y][x][c] = uint8 of chw[b][c][y][x] * 255 on the device, so that a quarter of the bytes crosses PCIe and
+ * the host only encodes the PNG.  clip = 0: numpy's (x * 255).astype(np.uint8) of eval_GAN.py:52 (truncate towards
+ * zero, keep the low byte: the generator ends in tanh and negative values wrap; NaN -> 0); clip = 1:
+ * np.clip(x * 255, 0, 255).astype(np.uint8) of utils/common.py:81.  chw 16-byte aligned, out_hwc 4-byte aligned. */
+int dsr_image_to_u8_hwc(const float* chw, int B, int C, int H, int W, int clip, unsigned char* out_hwc, void* stream);
 /* 1 when the plan was created with DSR_DETERMINISTIC=1 (two-stage split-K weight gradients: bit-identical runs). */
 int dsr_plan_deterministic(const dsr_plan_t* p);
 
