@@ -525,7 +525,7 @@ int build_conv(dsr_plan* p, ConvLayer& c) {
     // small layers get few CTAs (>= kWgMinBlocks pixel blocks each) -- less atomic traffic, and SMs left free for
     // the main stream's conv kernels that run beside the weight-gradient stream
     int nsplit = p->num_sms / g.ngroups;
-    const int kWgMinBlocks = getenv("DSR_WG_MINBLK") ? atoi(getenv("DSR_WG_MINBLK")) : 16;
+    const int kWgMinBlocks = getenv("DSR_WG_MINBLK") ? atoi(getenv("DSR_WG_MINBLK")) : 8;   // A/B: 16 -> 635.9, 8 -> 639.6, 4 -> 633.7, 2 -> 628.2 it/s
     if (nsplit > npb / kWgMinBlocks) nsplit = npb / kWgMinBlocks;
     if (nsplit > npb) nsplit = npb;
     if (nsplit < 1) nsplit = 1;
@@ -648,7 +648,7 @@ int build_conv(dsr_plan* p, ConvLayer& c) {
     // small layers get few CTAs (>= kWgMinBlocks pixel blocks each) -- less atomic traffic, and SMs left free for
     // the main stream's conv kernels that run beside the weight-gradient stream
     int nsplit = p->num_sms / g.ngroups;
-    const int kWgMinBlocks = getenv("DSR_WG_MINBLK") ? atoi(getenv("DSR_WG_MINBLK")) : 16;
+    const int kWgMinBlocks = getenv("DSR_WG_MINBLK") ? atoi(getenv("DSR_WG_MINBLK")) : 8;   // A/B: 16 -> 635.9, 8 -> 639.6, 4 -> 633.7, 2 -> 628.2 it/s
     if (nsplit > npb / kWgMinBlocks) nsplit = npb / kWgMinBlocks;
     if (nsplit > npb) nsplit = npb;
     if (nsplit < 1) nsplit = 1;
