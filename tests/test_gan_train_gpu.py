@@ -219,6 +219,50 @@ def test_workspace_invariants_after_training_steps(env):
     assert tr.guard_intact() and tr.device_error() == 0
 
 
+def test_three_stream_step_equals_the_single_stream_order(env, monkeypatch):
+    """GanTrainStep runs the discriminator chain, the generator chain and the real-batch VGG pass on three streams
+    (DESIGN.md 10 Streams); DSR_GAN_ONE_STREAM=1 issues the same calls on one.  Same seeds, same batch: the losses and
+    the gradients of both networks after the first step, and the losses of the second step (which see the first step's
+    Adam updates and BatchNorm statistics), agree to the noise of the fp32 atomics' order -- a missing event between
+    the streams (a race on `fake`, on the packed weights, on the BatchNorm scratch) would not."""
+    dsr_b200, GT, O, dev = env
+    LR, HR = O.synthetic_batch(41, 4, (16, 16), 8)
+    runs = []
+    for one_stream in (True, True, False):              # the single-stream order twice: the run-to-run yardstick
+        if one_stream:
+            monkeypatch.setenv('DSR_GAN_ONE_STREAM', '1')
+        else:
+            monkeypatch.delenv('DSR_GAN_ONE_STREAM', raising=False)
+        torch.manual_seed(23)
+        G, D = dsr_b200.Generator(8).train(), GT.Discriminator((128, 128)).train()
+        torch.manual_seed(1023)
+        V = GT.Vgg19Loss(pretrained=False).to(dev)
+        step = GT.GanTrainStep(G, D, V, 1e-4, 4, (16, 16), dev)
+        assert (step._side is None) == one_stream
+        lD, lG = step.do_epoch(LR, HR)
+        torch.cuda.synchronize()
+        first = (float(lD), float(lG), step.fg.gflat.clone(), step.fd.gflat.clone())
+        for _ in range(2):
+            lD, lG = step.do_epoch(LR, HR)
+        torch.cuda.synchronize()
+        runs.append(first + (float(lD), float(lG)))
+        assert step.tr.device_error() == 0
+    a0, a, b = runs
+
+    def show(tag, x, y):
+        print(f'{tag}: loss_D {x[0]:.6f} / {y[0]:.6f}  loss_G {x[1]:.6f} / {y[1]:.6f}  gradient cosine G {cos(x[2], y[2]):.7f} '
+              f'D {cos(x[3], y[3]):.7f}; third step loss_D {x[4]:.6f} / {y[4]:.6f}  loss_G {x[5]:.6f} / {y[5]:.6f}')
+    show('one stream, run 1 / run 2', a0, a)
+    show('one stream / three streams', a, b)
+    # loss_D and both gradients of the first step come before any update: equal up to the order of the fp32 atomics.
+    # loss_G of the first step already holds BCE(D'(fake)) after Adam(D), which turns that noise into +-lr steps.
+    assert a[0] == pytest.approx(b[0], rel=1e-5)
+    assert cos(a[2], b[2]) > 0.99999 and cos(a[3], b[3]) > 0.9999
+    assert a[1] == pytest.approx(b[1], rel=max(2e-3, 5 * abs(a0[1] - a[1]) / abs(a[1])))
+    assert a[4] == pytest.approx(b[4], rel=max(0.15, 5 * abs(a0[4] - a[4]) / abs(a[4])))     # measured run to run: 2 %
+    assert a[5] == pytest.approx(b[5], rel=max(0.05, 5 * abs(a0[5] - a[5]) / abs(a[5])))     # measured run to run: 0.3 %
+
+
 def test_factor16_step_with_12x12_patches(env):
     """train_GAN.py --downsample: factor 16, HR patch 192 -> LR patch 12 x 12 (train_GAN.py:240-270); four PixelShuffle
     blocks and level widths that are no multiple of the 8-pixel tiles.  One fused step against the oracle."""
