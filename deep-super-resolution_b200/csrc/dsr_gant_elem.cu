@@ -251,10 +251,15 @@ __global__ void g_bn_bwd_apply_kernel(const bf16_t* __restrict__ dy, const bf16_
                                       const double* __restrict__ stats, const float* __restrict__ gamma,
                                       const float* __restrict__ beta, const float* __restrict__ slope_p, TG g,
                                       double inv_count, const double* __restrict__ sums, float* __restrict__ dgamma,
-                                      float* __restrict__ dbeta, float* __restrict__ dslope) {
+                                      float* __restrict__ dbeta, float* __restrict__ dslope, double* __restrict__ next_sums) {
   __shared__ BnTabG tab;
   __shared__ float s_mg[512], s_mgx[512];
   pdl_sync();
+  // the OTHER half of the ping-pong scratch is cleared here for the next BatchNorm backward of this network (its last
+  // reader, the previous apply kernel, completed before this call's statistics kernel started; its next writer starts
+  // after this kernel): no memset node between the kernels, so the programmatic launch overlap of the chain survives
+  if (blockIdx.x == 0 && next_sums != nullptr)
+    for (int c = threadIdx.x; c < kBnSumsHalf; c += kT) next_sums[c] = 0.0;      // the whole half: the next layer's C may be larger
   for (int c = threadIdx.x; c < g.C; c += kT) {
     s_mg[c] = static_cast<float>(sums[c] * inv_count);
     s_mgx[c] = static_cast<float>(sums[g.C + c] * inv_count);
@@ -1212,10 +1217,15 @@ int gl_bn_apply(const GT& raw, const GT& out, const bf16_t* res, const double* s
   GL_CHECK();
 }
 int gl_bn_bwd(const GT& dy, const GT& raw, const GT& draw, const double* stats, const float* gamma, const float* beta,
-              int act, const float* slope, double* sums, float* dgamma, float* dbeta, float* dslope, cudaStream_t s) {
+              int act, const float* slope, double* sums2, int* parity, float* dgamma, float* dbeta, float* dslope,
+              cudaStream_t s) {
   const int C = raw.C;
   if (C > 512 || (C & 7) || (kT % (C / 8))) return -51;
-  cudaMemsetAsync(sums, 0, (2 * C + 1) * sizeof(double), s);
+  // sums2: two halves of kBnSumsHalf doubles, both zero at bind time; *parity selects the half this call accumulates
+  // into, the apply kernel clears the other one
+  double* sums = sums2 + (*parity ? kBnSumsHalf : 0);
+  double* other = sums2 + (*parity ? 0 : kBnSumsHalf);
+  *parity ^= 1;
   const long long np = static_cast<long long>(raw.B) * raw.H * raw.W;
   const double inv = 1.0 / static_cast<double>(np);
   const dim3 g1(grid_for(np * (C / 8), 2)), g2(grid_for(np * (C / 8)));
@@ -1225,13 +1235,13 @@ int gl_bn_bwd(const GT& dy, const GT& raw, const GT& draw, const double* stats, 
   const TG g = tg_of(raw);
   if (act == GACT_NONE) {
     launch_k(g_bn_bwd_stats_kernel<GACT_NONE>, g1, dim3(kT), 0, s, d, r, stats, gamma, beta, slope, g, inv, sums);
-    launch_k(g_bn_bwd_apply_kernel<GACT_NONE>, g2, dim3(kT), 0, s, d, r, o, stats, gamma, beta, slope, g, inv, static_cast<const double*>(sums), dgamma, dbeta, dslope);
+    launch_k(g_bn_bwd_apply_kernel<GACT_NONE>, g2, dim3(kT), 0, s, d, r, o, stats, gamma, beta, slope, g, inv, static_cast<const double*>(sums), dgamma, dbeta, dslope, other);
   } else if (act == GACT_LRELU) {
     launch_k(g_bn_bwd_stats_kernel<GACT_LRELU>, g1, dim3(kT), 0, s, d, r, stats, gamma, beta, slope, g, inv, sums);
-    launch_k(g_bn_bwd_apply_kernel<GACT_LRELU>, g2, dim3(kT), 0, s, d, r, o, stats, gamma, beta, slope, g, inv, static_cast<const double*>(sums), dgamma, dbeta, dslope);
+    launch_k(g_bn_bwd_apply_kernel<GACT_LRELU>, g2, dim3(kT), 0, s, d, r, o, stats, gamma, beta, slope, g, inv, static_cast<const double*>(sums), dgamma, dbeta, dslope, other);
   } else {
     launch_k(g_bn_bwd_stats_kernel<GACT_PRELU>, g1, dim3(kT), 0, s, d, r, stats, gamma, beta, slope, g, inv, sums);
-    launch_k(g_bn_bwd_apply_kernel<GACT_PRELU>, g2, dim3(kT), 0, s, d, r, o, stats, gamma, beta, slope, g, inv, static_cast<const double*>(sums), dgamma, dbeta, dslope);
+    launch_k(g_bn_bwd_apply_kernel<GACT_PRELU>, g2, dim3(kT), 0, s, d, r, o, stats, gamma, beta, slope, g, inv, static_cast<const double*>(sums), dgamma, dbeta, dslope, other);
   }
   GL_CHECK();
 }

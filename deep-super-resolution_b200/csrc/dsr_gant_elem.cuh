@@ -17,9 +17,13 @@ int gl_tanh_bwd(const float* dout_nchw, const float* out_nchw, const GT& dz, flo
 // rm / rv (may be nullptr): running statistics, updated run_times times by block 0 (conv_bias: the bias the conv dropped)
 int gl_bn_apply(const GT& raw, const GT& out, const bf16_t* res, const double* stats, const float* gamma, const float* beta,
                 int act, const float* slope, const float* conv_bias, float* rm, float* rv, int run_times, cudaStream_t s);
-// backward of out = act(bn(raw)): dy -> draw, dgamma / dbeta / dslope accumulated (+=); sums = scratch [2][C] + 1 doubles
+// backward of out = act(bn(raw)): dy -> draw, dgamma / dbeta / dslope accumulated (+=).  sums2 = ping-pong scratch of two
+// halves of kBnSumsHalf doubles (zero at bind time; the apply kernel clears the half the NEXT call uses, so no memset node
+// sits between the kernels of a backward chain), *parity = the half of this call (host state of the owning chain)
+constexpr int kBnSumsHalf = 2 * 512 + 8;
 int gl_bn_bwd(const GT& dy, const GT& raw, const GT& draw, const double* stats, const float* gamma, const float* beta,
-              int act, const float* slope, double* sums, float* dgamma, float* dbeta, float* dslope, cudaStream_t s);
+              int act, const float* slope, double* sums2, int* parity, float* dgamma, float* dbeta, float* dslope,
+              cudaStream_t s);
 // PixelShuffle(2) + PReLU
 int gl_shuffle_fwd(const GT& sraw, const GT& u, const float* slope, cudaStream_t s);
 int gl_shuffle_bwd(const GT& du, const GT& sraw, const GT& ds, const float* slope, float* dbias256, float* dslope,

@@ -116,6 +116,7 @@ struct dsr_gant {
   int v_Hr = 0, v_Wr = 0, v_top = 0, v_left = 0;
   // ---- shared
   double* sums = nullptr;                  // BatchNorm-backward scratch [2 * 512 + 1] of the generator's backward pass
+  int sums_par = 0, sums_d_par = 0;        // ping-pong halves of the two scratch areas (gl_bn_bwd)
   double* sums_d = nullptr;                // the discriminator's own (its backward may run on another stream, beside G's)
   double* loss_acc = nullptr;
   float* dw_arena[2] = {nullptr, nullptr}; // packed weight gradients of G / D
@@ -193,8 +194,8 @@ size_t layout(dsr_gant* p, uint8_t* base) {
   p->err = static_cast<int*>(a.take(1024));
   for (int n = 0; n < 3; ++n) p->t_pack[n] = static_cast<GPackItem*>(a.take(48 * sizeof(GPackItem)));
   for (int n = 0; n < 2; ++n) p->t_unpack[n] = static_cast<GUnpackItem*>(a.take(48 * sizeof(GUnpackItem)));
-  p->sums = static_cast<double*>(a.take((2 * 512 + 1) * sizeof(double)));
-  p->sums_d = static_cast<double*>(a.take((2 * 512 + 1) * sizeof(double)));
+  p->sums = static_cast<double*>(a.take(2 * kBnSumsHalf * sizeof(double)));
+  p->sums_d = static_cast<double*>(a.take(2 * kBnSumsHalf * sizeof(double)));
   p->loss_acc = static_cast<double*>(a.take(64));
   // ---------------- generator ----------------
   {
@@ -543,6 +544,7 @@ int dsr_gant_bind(dsr_gant_t* p, void* workspace, size_t bytes, void* stream) {
   for (Tape* t : {&p->tp_gf, &p->tp_gb, &p->tp_df[0], &p->tp_df[1], &p->tp_db[0], &p->tp_db[1], &p->tp_v, &p->tp_vl, &p->tp_vr,
                   &p->tp_v2, &p->tp_vl2})
     t->clear();
+  p->sums_par = p->sums_d_par = 0;
   const int rc = build_group_tables(p, s);
   if (rc) return rc;
   p->bound = true;
@@ -673,7 +675,7 @@ int dsr_gant_g_backward(dsr_gant_t* p, const float* params, const float* dout_nc
   }
   // t = x0 + bn(conv2(x_last))
   double* st = p->g_stats + (2 * p->blocks) * 128;
-  GCHK(gl_bn_bwd(p->g_dT, p->g_rt, p->g_dR, st, params + p->g_bn.g_off, params + p->g_bn.b_off, GACT_NONE, nullptr, p->sums,
+  GCHK(gl_bn_bwd(p->g_dT, p->g_rt, p->g_dR, st, params + p->g_bn.g_off, params + p->g_bn.b_off, GACT_NONE, nullptr, p->sums, &p->sums_par,
                  grads + p->g_bn.g_off, grads + p->g_bn.b_off, nullptr, s));
   p->launches += 3;
   GCHK(run_wgrad(p, p->g_conv2, p->g_dR, p->g_x[p->blocks], s));
@@ -684,12 +686,12 @@ int dsr_gant_g_backward(dsr_gant_t* p, const float* params, const float* dout_nc
     double* sb = p->g_stats + (2 * k + 1) * 128;
     const BnL& ba = p->g_bna[k];
     const BnL& bb = p->g_bnb[k];
-    GCHK(gl_bn_bwd(p->g_dX[cur], p->g_r2[k], p->g_dR, sb, params + bb.g_off, params + bb.b_off, GACT_NONE, nullptr, p->sums,
+    GCHK(gl_bn_bwd(p->g_dX[cur], p->g_r2[k], p->g_dR, sb, params + bb.g_off, params + bb.b_off, GACT_NONE, nullptr, p->sums, &p->sums_par,
                    grads + bb.g_off, grads + bb.b_off, nullptr, s));
     GCHK(run_wgrad(p, p->g_cb[k], p->g_dR, p->g_a1[k], s));
     GCHK(run_dgrad(p, p->g_cb[k], p->g_dR, p->g_dA, nullptr, nullptr, 0.f, s));
     GCHK(gl_bn_bwd(p->g_dA, p->g_r1[k], p->g_dR, sa, params + ba.g_off, params + ba.b_off, GACT_PRELU,
-                   params + p->g_prelu_blk[k], p->sums, grads + ba.g_off, grads + ba.b_off, grads + p->g_prelu_blk[k], s));
+                   params + p->g_prelu_blk[k], p->sums, &p->sums_par, grads + ba.g_off, grads + ba.b_off, grads + p->g_prelu_blk[k], s));
     GCHK(run_wgrad(p, p->g_ca[k], p->g_dR, p->g_x[k], s));
     GCHK(run_dgrad(p, p->g_ca[k], p->g_dR, p->g_dX[cur ^ 1], static_cast<const bf16_t*>(p->g_dX[cur].ptr), nullptr, 0.f, s));
     p->launches += 6;
@@ -745,7 +747,7 @@ static int d_convs_backward(dsr_gant* p, int slot, const float* params, float* g
     const BnL& b = p->d_bn[k];
     const GT& in = (k == 0) ? p->d_h0[slot] : p->d_h[slot][k - 1];
     GCHK(gl_bn_bwd(p->d_ga[k], p->d_raw[slot][k], p->d_gb[k], st, params + b.g_off, params + b.b_off, GACT_LRELU, nullptr,
-                   p->sums_d, grads + b.g_off, grads + b.b_off, nullptr, s));
+                   p->sums_d, &p->sums_d_par, grads + b.g_off, grads + b.b_off, nullptr, s));
     p->launches += 1;
     GCHK(run_wgrad(p, p->d_c[k], p->d_gb[k], in, s));
     if (k > 0) {
