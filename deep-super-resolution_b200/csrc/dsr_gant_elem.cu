@@ -7,6 +7,7 @@
 #include "dsr_gant_elem.cuh"
 #include <cuda_fp16.h>
 
+#include "dsr_host.h"
 #include "dsr_launch.cuh"
 
 namespace dsr {
@@ -1327,7 +1328,8 @@ int gl_unflatten(const float* dflat, const GT& dh, cudaStream_t s) {
 }
 int gl_dense1_fwd(const float* W, const float* bias, const float* x, float* z1, int B, int K, int J, cudaStream_t s) {
   if (B > 8 || (K & 3) || (J % kD1Rows)) return -54;
-  static bool attr = false;
+  static bool attr_dev[kMaxDevices] = {};            // opt-in shared memory is a per-device function attribute
+  bool& attr = attr_dev[device_slot()];
   if (!attr) {
     if (cudaFuncSetAttribute(g_dense1_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kD1FwdSmem) != cudaSuccess) return -59;
     attr = true;
@@ -1347,7 +1349,8 @@ int gl_dense2_bwd(const float* prob, const float* dprob, float target, const flo
   GL_CHECK();
 }
 static int dense1_bwd_attr() {
-  static bool attr = false;
+  static bool attr_dev[kMaxDevices] = {};
+  bool& attr = attr_dev[device_slot()];
   if (attr) return 0;
   const int cap = kD1BwdRing + 1024 * 16 * static_cast<int>(sizeof(float));
   if (cudaFuncSetAttribute(g_dense1_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap) != cudaSuccess) return -59;
