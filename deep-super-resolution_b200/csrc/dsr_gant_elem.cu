@@ -935,28 +935,6 @@ __global__ void g_bce_kernel(const float* __restrict__ prob, float target, int B
 // ---------------------------------------------------------------------------------------------
 // weights
 // ---------------------------------------------------------------------------------------------
-__global__ void g_pack_weight_kernel(const float* __restrict__ w, const float* __restrict__ bias, int cout, int cin, int ks,
-                                     int cout_pad, int cin_pad, bf16_t* __restrict__ w_f, bf16_t* __restrict__ w_d,
-                                     float* __restrict__ bias_pad, int f16_fwd) {
-  pdl_sync();
-  const long long total = static_cast<long long>(ks) * ks * cout_pad * cin_pad;
-  for (long long i = static_cast<long long>(blockIdx.x) * kT + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * kT) {
-    const int ci = static_cast<int>(i % cin_pad);
-    const long long r = i / cin_pad;
-    const int co = static_cast<int>(r % cout_pad);
-    const int tap = static_cast<int>(r / cout_pad);
-    float v = 0.f;
-    if (co < cout && ci < cin) v = w[(static_cast<long long>(co) * cin + ci) * ks * ks + tap];
-    const bf16_t h = __float2bfloat16_rn(v);
-    if (w_f != nullptr) {
-      if (f16_fwd) reinterpret_cast<__half*>(w_f)[i] = __float2half_rn(v);
-      else w_f[i] = h;
-    }
-    if (w_d != nullptr) w_d[(static_cast<long long>(tap) * cin_pad + ci) * cout_pad + co] = h;
-    if (bias_pad != nullptr && tap == 0 && ci == 0) bias_pad[co] = (bias != nullptr && co < cout) ? bias[co] : 0.f;
-  }
-}
-
 // One launch for all convolutions of a network (a launch at these sizes costs 4 us whatever it does; the generator has
 // 36 layers): block b works on the item whose [blk0, blk0 + nblk) holds it, grid-striding over the item's blocks.
 __global__ void g_pack_group_kernel(const float* __restrict__ params, const GPackItem* __restrict__ items, int n) {
@@ -999,19 +977,6 @@ __global__ void g_unpack_group_kernel(float* __restrict__ grads, const GUnpackIt
     const int ci = static_cast<int>(r % q.cin);
     const int co = static_cast<int>(r / q.cin);
     g[i] += q.dw[(static_cast<long long>(tap) * q.cout + co) * q.cin + ci];
-  }
-}
-
-__global__ void g_unpack_wgrad_kernel(const float* __restrict__ dw, float* __restrict__ g, int cout, int cin, int ks) {
-  pdl_sync();
-  const int kk = ks * ks;
-  const long long total = static_cast<long long>(cout) * cin * kk;
-  for (long long i = static_cast<long long>(blockIdx.x) * kT + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * kT) {
-    const int tap = static_cast<int>(i % kk);
-    const long long r = i / kk;
-    const int ci = static_cast<int>(r % cin);
-    const int co = static_cast<int>(r / cin);
-    g[i] += dw[(static_cast<long long>(tap) * cout + co) * cin + ci];
   }
 }
 
@@ -1388,12 +1353,6 @@ int gl_bce(const float* prob, float target, int B, float* loss_out, int accumula
   GL_CHECK();
 }
 
-int gl_pack_weight(const float* w, const float* bias, int cout, int cin, int ks, int cout_pad, int cin_pad, bf16_t* w_f,
-                   bf16_t* w_d, float* bias_pad, int f16_fwd, cudaStream_t s) {
-  launch_k(g_pack_weight_kernel, dim3(grid_for(static_cast<long long>(ks) * ks * cout_pad * cin_pad)), dim3(kT), 0, s, w,
-           bias, cout, cin, ks, cout_pad, cin_pad, w_f, w_d, bias_pad, f16_fwd);
-  GL_CHECK();
-}
 int gl_group_blocks(long long items) {
   long long b = (items + 4 * kT - 1) / (4 * kT);
   return static_cast<int>(b < 1 ? 1 : (b > 1024 ? 1024 : b));
@@ -1406,11 +1365,6 @@ int gl_pack_group(const float* params, const GPackItem* items_dev, int n, int to
 int gl_unpack_group(float* grads, const GUnpackItem* items_dev, int n, int total_blocks, cudaStream_t s) {
   if (n <= 0) return 0;
   launch_k(g_unpack_group_kernel, dim3(total_blocks), dim3(kT), 0, s, grads, items_dev, n);
-  GL_CHECK();
-}
-int gl_unpack_wgrad(const float* dw_pack, float* g, int cout, int cin, int ks, cudaStream_t s) {
-  launch_k(g_unpack_wgrad_kernel, dim3(grid_for(static_cast<long long>(ks) * ks * cout * cin)), dim3(kT), 0, s, dw_pack, g,
-           cout, cin, ks);
   GL_CHECK();
 }
 int gl_expand9(const GT& dz16, const GT& dz9, cudaStream_t s) {

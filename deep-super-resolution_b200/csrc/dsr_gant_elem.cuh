@@ -55,10 +55,9 @@ int gl_dense1_bwd2(const float* W, const float* x0, const float* dz0, float* dx0
                    float* dx1, float* dW, float* db1, int B, int K, int J, int accumulate, cudaStream_t s);
 int gl_bce(const float* prob, float target, int B, float* loss_out, int accumulate, cudaStream_t s);
 // weights
-int gl_pack_weight(const float* w_oihw, const float* bias, int cout, int cin, int ks, int cout_pad, int cin_pad,
-                   bf16_t* w_f, bf16_t* w_d, float* bias_pad, int f16_fwd, cudaStream_t s);   // f16_fwd: w_f as IEEE half
-int gl_unpack_wgrad(const float* dw_pack, float* g_oihw, int cout, int cin, int ks, cudaStream_t s);
-// the same two operations for ALL layers of a network in one launch each: tables in device memory, built at bind time
+// bf16 GEMM layouts [tap][Cout][Cin] / [tap][Cin][Cout] (+ padded bias) of ALL layers of a network from its flat fp32
+// parameters, and its packed weight gradients added back in OIHW order: one launch each, item tables in device memory
+// (built at bind time)
 struct GPackItem {
   long long w_off, b_off;        // offsets into the flat parameter array; b_off < 0: bias_pad is written as zero
   bf16_t* w_f; bf16_t* w_d; float* bias_pad;
