@@ -640,11 +640,11 @@ int dsr_gant_g_backward(dsr_gant_t* p, const float* params, const float* dout_nc
   p->launches = 0;
   TapeScope scope(p, &p->tp_gb);
   cudaMemsetAsync(p->dw_arena[0], 0, p->dw_bytes[0], s);
+  cudaMemsetAsync(p->g_dw9, 0, 9 * 64 * 64 * 4, s);           // here, not between the kernels below (a memset node breaks their overlap)
   const int last = p->nshuf - 1;
   GCHK(gl_tanh_bwd(dout_nchw, p->g_out, p->g_dz16, grads + p->g_conv3.b_off, s));
   // conv3 (9 x 9, 64 -> 3) backward with the kx taps folded into the channels: 9-tap tensor-core problems (dsr_gant_elem.cu)
   GCHK(gl_expand9(p->g_dz16, p->g_dz9, s));
-  cudaMemsetAsync(p->g_dw9, 0, 9 * 64 * 64 * 4, s);
   {
     Tape& t = *p->tape;
     if (!t.built) {
@@ -738,9 +738,15 @@ int dsr_gant_d_forward(dsr_gant_t* p, int slot, const float* params, float* buff
 }
 
 // the convolutional part of the discriminator backward, from the gradient of the flattened features on
-static int d_convs_backward(dsr_gant* p, int slot, const float* params, float* grads, cudaStream_t s) {
+// clear / unpack: the packed weight gradients (tensor-core layers and the folded conv0) are cleared before and added to
+// `grads` after this pass; the paired call clears once, lets both passes accumulate, and unpacks once
+static int d_convs_backward(dsr_gant* p, int slot, const float* params, float* grads, cudaStream_t s, bool clear = true,
+                            bool unpack = true) {
   TapeScope scope(p, &p->tp_db[slot]);
-  cudaMemsetAsync(p->dw_arena[1], 0, p->dw_bytes[1], s);
+  if (clear) {
+    cudaMemsetAsync(p->dw_arena[1], 0, p->dw_bytes[1], s);
+    cudaMemsetAsync(p->d_dw3, 0, 3 * 64 * 64 * 4, s);
+  }
   GCHK(gl_unflatten(p->d_dflat[slot], p->d_ga[6], s));
   for (int k = 6; k >= 0; --k) {
     double* st = p->d_stats[slot] + k * 1024;
@@ -760,7 +766,6 @@ static int d_convs_backward(dsr_gant* p, int slot, const float* params, float* g
   }
   // conv0 (3 x 3, 3 -> 64) weight gradient with the kx taps folded into the input channels: a 3-tap gwgrad_kernel
   GCHK(gl_expand3(p->d_img[slot], p->d_x9, s));
-  cudaMemsetAsync(p->d_dw3, 0, 3 * 64 * 64 * 4, s);
   {
     Tape& t = *p->tape;
     if (!t.built) {
@@ -773,9 +778,11 @@ static int d_convs_backward(dsr_gant* p, int slot, const float* params, float* g
     }
     GCHK(launch_gwgrad(t.wgs[t.wi++], s));
   }
-  GCHK(gl_unpack3(p->d_dw3, grads + p->d_conv0.w_off, s));
   GCHK(gl_chan_sum(p->d_dz0, grads + p->d_conv0.b_off, s));
-  GCHK(gl_unpack_group(grads, p->t_unpack[1], static_cast<int>(p->h_unpack[1].size()), p->unpack_blocks[1], s));
+  if (unpack) {
+    GCHK(gl_unpack3(p->d_dw3, grads + p->d_conv0.w_off, s));
+    GCHK(gl_unpack_group(grads, p->t_unpack[1], static_cast<int>(p->h_unpack[1].size()), p->unpack_blocks[1], s));
+  }
   scope.ok = true;
   return 0;
 }
@@ -807,10 +814,10 @@ int dsr_gant_d_backward_pair(dsr_gant_t* p, const float* params, float target0, 
   GCHK(gl_dense1_bwd2(params + p->d_w1, p->d_flat[0], p->d_dz1[0], p->d_dflat[0], p->d_flat[1], p->d_dz1[1], p->d_dflat[1],
                       grads + p->d_w1, grads + p->d_b1, p->B, p->d_K, 1024, p->dense_overwrite ? 0 : 1, s));
   const int n = p->launches;
-  int rc = d_convs_backward(p, 0, params, grads, s);
+  int rc = d_convs_backward(p, 0, params, grads, s, true, false);
   if (rc) return rc;
   const int n0 = p->launches;
-  rc = d_convs_backward(p, 1, params, grads, s);
+  rc = d_convs_backward(p, 1, params, grads, s, false, true);
   p->launches += n0 - n;
   return rc;
 }
