@@ -15,12 +15,17 @@ utils/DIP.py:35-38.
              get_params, optimize and a closure written like DIP.py:47-95) with HOST buffers: the step's perturbed
              input z comes from pinned host memory (H2D inside the timed region, as DIP.py:57 does) and out_HR /
              out_LR / loss are read back every step (DIP.py:90-91).
-* roofline   the dominant kernel, conv_halo2_kernel on the stride-1 3x3 layers (fprop + dgrad, 56 % of the iteration's
-             FLOPs): algorithmic FLOPs / CUDA-event time per launch, summed over a profiled pass (all 5 levels, the
-             latency-bound 16x16..64x64 launches included), against MEASURED_PEAKS.json bf16 (sustained) peak.  Its
-             1x1 launches (64 FLOP per byte) are listed against the HBM roof, the other tensor-core kernels beside.
-* cpu_baseline / --impl reference   the CPU restatement of the reference path (oracle/dip_oracle.py: the same
-             torch CPU primitives the reference's nn.Modules call), all host threads, same workload.
+* roofline   the tensor-core kernel class with the LARGEST time per iteration (today wgrad_halo_kernel): algorithmic
+             FLOPs / time per launch, summed over profiled iterations (all 5 levels, the latency-bound 16x16..64x64
+             launches included; in-kernel %globaltimer stamps, dependencies satisfied -> last CTA done), against the
+             BURST bf16 peak of MEASURED_PEAKS.json.  Every class is listed under roofline.classes (the 1x1 launches,
+             64 FLOP per byte, against the HBM roof), the largest launch of the two big classes and the whole step too.
+* cpu_baseline / --impl reference   the UNMODIFIED reference modules (baseline/_ref, staged by __graft_entry__.build())
+             with a closure written like DIP.py:47-69 and torch.optim.Adam on the box's host cores, all threads, same
+             workload; gpu_eager_baseline = the same modules on stock PyTorch CUDA eager (fp32, TF32 off).
+* secondary / secondary_gan_train   short single-GPU runs of the two other BASELINE workloads (generator inference,
+             configs[3]; SRGAN training step, configs[4]); their full lines: --workload gan_eval / gan_train (the
+             latter data-parallel under torchrun, NCCL all-reduce of the flat gradients).
 """
 import argparse
 import json
