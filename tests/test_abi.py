@@ -172,6 +172,9 @@ def test_drop_in_module_names_resolve_to_this_package():
     assert importlib.import_module('utils.downsampler').Downsampler is dsr_b200.Downsampler
     m = importlib.import_module('utils.DIP')
     assert m.optimize is dsr_b200.optimize and m.get_noise is dsr_b200.get_noise and m.get_params is dsr_b200.get_params
+    common = importlib.import_module('utils.common')
+    assert os.path.realpath(common.__file__).startswith(os.path.realpath(os.path.join(ROOT, 'deep-super-resolution_b200')))
+    assert m.save_image is common.save_image and m.np_to_pil is common.np_to_pil     # utils/DIP.py:3 re-exports utils.common
 
 
 # ---- SRResNet generator (dsr_gen_*): host-side checks, no GPU work ------------------------------------------
@@ -268,7 +271,14 @@ def test_gan_training_surface_without_gpu():
     assert lib.dsr_gant_param_numel(h, 2) == 20024384                            # VGG19 features[:36]
     assert lib.dsr_gant_workspace_bytes(h) > 0
     assert lib.dsr_gant_g_forward(h, None, None, None, None, 1, None) == -1     # unbound / null arguments
+    assert lib.dsr_gant_vgg_real(h, None, None) == -1 and lib.dsr_gant_vgg_loss(h, None, None, None, 0, None, None) == -1
+    assert lib.dsr_gant_dense_grad_overwrite(None, 1) == -1 and lib.dsr_gant_dense_grad_overwrite(h, 1) == 0
+    assert lib.dsr_gant_dense_grad_overwrite(h, 0) == 0
     lib.dsr_gant_destroy(h)
+    # image writer path: argument checks happen before any CUDA call
+    assert lib.dsr_image_to_u8_hwc(None, 1, 3, 8, 8, 0, None, None) == -1
+    with pytest.raises(RuntimeError):
+        dsr_b200.to_uint8_hwc(torch.rand(3, 8, 8))                               # CPU tensor: no fallback
     # same seed -> the reference's initial state (incl. the running statistics fc_input_shape leaves behind)
     torch.manual_seed(4)
     sdG = GO.init_state_dict(8)
